@@ -1,0 +1,286 @@
+"""ctypes binding of include/alens_b200.h (one method per entry point, same names minus the prefix)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+BLOCK_DTYPE = np.dtype(
+    [
+        ("delta0", "<f8"), ("gamma", "<f8"), ("gammaLB", "<f8"),
+        ("gidI", "<i4"), ("gidJ", "<i4"), ("globalIndexI", "<i4"), ("globalIndexJ", "<i4"),
+        ("oneSide", "u1"), ("bilateral", "u1"), ("pad_", "u1", 6),
+        ("kappa", "<f8"),
+        ("normI", "<f8", 3), ("normJ", "<f8", 3), ("posI", "<f8", 3), ("posJ", "<f8", 3),
+        ("labI", "<f8", 3), ("labJ", "<f8", 3), ("stress", "<f8", 9),
+    ],
+    align=True,
+)
+assert BLOCK_DTYPE.itemsize == 272
+
+# every symbol include/alens_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "alens_create", "alens_destroy", "alens_last_error", "alens_version", "alens_set_stream",
+    "alens_set_domain", "alens_set_collision_params", "alens_set_rods", "alens_set_rods_aos",
+    "alens_get_positions", "alens_collect_pair_collision", "alens_append_constraints",
+    "alens_clear_constraints", "alens_num_constraints", "alens_get_constraints", "alens_calc_mobility",
+    "alens_mobility_apply", "alens_solve_constraints", "alens_setup_constraints", "alens_operator_apply",
+    "alens_get_history", "alens_get_gamma", "alens_get_force_velocity", "alens_step_euler",
+    "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
+    "alens_comm_unique_id", "alens_comm_init",
+]
+
+
+class SolveReport(C.Structure):
+    _fields_ = [("status", C.c_int), ("iterations", C.c_int), ("matvecs", C.c_int), ("history_rows", C.c_int),
+                ("residual", C.c_double), ("step", C.c_double), ("n_constraints", C.c_longlong),
+                ("n_rods", C.c_int)]
+
+
+class Timers(C.Structure):
+    _fields_ = [("upload_ms", C.c_double), ("collect_ms", C.c_double), ("setup_ms", C.c_double),
+                ("solve_ms", C.c_double), ("split_ms", C.c_double), ("download_ms", C.c_double),
+                ("op_force_vel_ms", C.c_double), ("op_dtrans_ms", C.c_double), ("op_launches", C.c_longlong),
+                ("total_launches", C.c_longlong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class AlensError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"alens_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(HERE, "libalens_b200.so")
+
+
+def build(verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... (alens_b200/csrc/Makefile); cross-compiles without a GPU."""
+    cmd = ["make", "-C", os.path.join(HERE, "csrc"), "-j4"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+    return lib_path()
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+class Library:
+    """The loaded shared library.  Fails loudly if the CUDA extension has not been built."""
+
+    _inst = None
+
+    def __init__(self, path=None):
+        path = path or lib_path()
+        if not os.path.exists(path):
+            raise AlensError(-100, f"{path} not found: build it with alens_b200.build() / __graft_entry__.build(); "
+                             "there is no CPU fallback")
+        self.path = path
+        self.dll = C.CDLL(path)
+        d = self.dll
+        d.alens_last_error.restype = C.c_char_p
+        d.alens_last_error.argtypes = [C.c_void_p]
+        d.alens_version.restype = C.c_char_p
+        d.alens_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        d.alens_destroy.argtypes = [C.c_void_p]
+        d.alens_destroy.restype = None
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            cls._inst = Library()
+        return cls._inst
+
+    def version(self):
+        return self.dll.alens_version().decode()
+
+
+class Context:
+    """One alens_ctx (one GPU).  Method names follow the C entry points."""
+
+    def __init__(self, device=0, rank=0, nranks=1, library=None):
+        self.lib = library or Library.get()
+        self.h = C.c_void_p()
+        rc = self.lib.dll.alens_create(device, rank, nranks, C.byref(self.h))
+        if rc != 0:
+            raise AlensError(rc, self.lib.dll.alens_last_error(None).decode())
+        self.n_rods = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.dll.alens_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise AlensError(rc, self.lib.dll.alens_last_error(self.h).decode())
+
+    def _call(self, name, *args):
+        self._ck(getattr(self.lib.dll, name)(self.h, *args))
+
+    # ---- configuration
+    def set_stream(self, cuda_stream):
+        self._call("alens_set_stream", C.c_void_p(cuda_stream))
+
+    def set_domain(self, lo, hi, pbc):
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        pbc = np.ascontiguousarray(pbc, dtype=np.int32)
+        self._call("alens_set_domain", _dp(lo), _dp(hi), pbc.ctypes.data_as(C.POINTER(C.c_int)))
+
+    def set_collision_params(self, diameter_col_ratio=1.0, length_col_ratio=1.0, col_buf=0.0):
+        self._call("alens_set_collision_params", C.c_double(diameter_col_ratio), C.c_double(length_col_ratio),
+                   C.c_double(col_buf))
+
+    # ---- rods
+    def set_rods(self, gid, pos, orientation, length, radius, immovable=None, wrap=True):
+        n = len(gid)
+        self._keep = [np.ascontiguousarray(gid, dtype=np.int32),
+                      np.ascontiguousarray(pos, dtype=np.float64).reshape(-1),
+                      np.ascontiguousarray(orientation, dtype=np.float64).reshape(-1),
+                      np.ascontiguousarray(length, dtype=np.float64),
+                      np.ascontiguousarray(radius, dtype=np.float64),
+                      None if immovable is None else np.ascontiguousarray(immovable, dtype=np.uint8)]
+        g, p, q, le, ra, im = self._keep
+        assert p.size == 3 * n and q.size == 4 * n and le.size == n and ra.size == n
+        self._call("alens_set_rods", C.c_int(n), g.ctypes.data_as(C.POINTER(C.c_int)), _dp(p), _dp(q), _dp(le),
+                   _dp(ra), None if im is None else im.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int(1 if wrap else 0))
+        self.n_rods = n
+
+    def set_rods_raw(self, n, gid_p, pos_p, quat_p, len_p, rad_p, imm_p, wrap=True):
+        """pointer version (pinned host buffers owned by the caller, e.g. torch pinned tensors)"""
+        self._call("alens_set_rods", C.c_int(n), C.c_void_p(gid_p), C.c_void_p(pos_p), C.c_void_p(quat_p),
+                   C.c_void_p(len_p), C.c_void_p(rad_p), C.c_void_p(imm_p), C.c_int(1 if wrap else 0))
+        self.n_rods = n
+
+    def set_rods_aos(self, records, stride=568, wrap=True):
+        buf = np.ascontiguousarray(records, dtype=np.uint8)
+        n = buf.size // stride
+        self._call("alens_set_rods_aos", C.c_int(n), C.c_void_p(buf.ctypes.data), C.c_size_t(stride),
+                   C.c_int(1 if wrap else 0))
+        self.n_rods = n
+
+    def get_positions(self):
+        out = np.zeros((self.n_rods, 3))
+        self._call("alens_get_positions", _dp(out))
+        return out
+
+    def get_rod_state(self):
+        pos = np.zeros((self.n_rods, 3))
+        q = np.zeros((self.n_rods, 4))
+        self._call("alens_get_rod_state", _dp(pos), _dp(q))
+        return pos, q
+
+    # ---- constraints
+    def collect_pair_collision(self):
+        n = C.c_longlong(0)
+        self._call("alens_collect_pair_collision", C.byref(n))
+        return n.value
+
+    def append_constraints(self, blocks):
+        blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+        self._call("alens_append_constraints", C.c_void_p(blocks.ctypes.data), C.c_longlong(len(blocks)))
+
+    def clear_constraints(self):
+        self._call("alens_clear_constraints")
+
+    def num_constraints(self):
+        n = C.c_longlong(0)
+        self._call("alens_num_constraints", C.byref(n))
+        return n.value
+
+    def get_constraints(self, with_stress=True, write_back=False):
+        n = self.num_constraints()
+        out = np.zeros(max(n, 1), dtype=BLOCK_DTYPE)
+        self._call("alens_get_constraints", C.c_void_p(out.ctypes.data), C.c_longlong(len(out)),
+                   C.c_int(1 if with_stress else 0), C.c_int(1 if write_back else 0))
+        return out[:n]
+
+    # ---- mobility / solve
+    def calc_mobility(self, viscosity):
+        self._call("alens_calc_mobility", C.c_double(viscosity))
+
+    def mobility_apply(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        self._call("alens_mobility_apply", _dp(x), _dp(y))
+        return y
+
+    def setup_constraints(self, vel_nc, dt):
+        v = None if vel_nc is None else np.ascontiguousarray(vel_nc, dtype=np.float64)
+        self._call("alens_setup_constraints", _dp(v), C.c_double(dt))
+
+    def solve_constraints(self, vel_nc, dt, res, max_ite, solver_choice=0):
+        v = None if vel_nc is None else np.ascontiguousarray(vel_nc, dtype=np.float64)
+        rep = SolveReport()
+        self._call("alens_solve_constraints", _dp(v), C.c_double(dt), C.c_double(res), C.c_int(max_ite),
+                   C.c_int(solver_choice), C.byref(rep))
+        return rep
+
+    def solve_constraints_raw(self, vel_nc_p, dt, res, max_ite, solver_choice=0):
+        rep = SolveReport()
+        self._call("alens_solve_constraints", C.c_void_p(vel_nc_p), C.c_double(dt), C.c_double(res),
+                   C.c_int(max_ite), C.c_int(solver_choice), C.byref(rep))
+        return rep
+
+    def operator_apply(self, x, want_force_vel=False):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(max(len(x), 1))
+        if want_force_vel:
+            f = np.zeros(6 * self.n_rods)
+            v = np.zeros(6 * self.n_rods)
+            self._call("alens_operator_apply", _dp(x), _dp(y), _dp(f), _dp(v))
+            return y[:len(x)], f, v
+        self._call("alens_operator_apply", _dp(x), _dp(y), None, None)
+        return y[:len(x)]
+
+    def get_history(self):
+        n = C.c_int(0)
+        self._call("alens_get_history", None, C.c_int(0), C.byref(n))
+        rows = np.zeros((max(n.value, 1), 6))
+        self._call("alens_get_history", _dp(rows), C.c_int(len(rows)), C.byref(n))
+        return rows[:n.value]
+
+    def get_gamma(self):
+        n = self.num_constraints()
+        g = np.zeros(max(n, 1))
+        self._call("alens_get_gamma", _dp(g), C.c_longlong(len(g)))
+        return g[:n]
+
+    def get_force_velocity(self):
+        out = [np.zeros(6 * self.n_rods) for _ in range(4)]
+        self._call("alens_get_force_velocity", *[_dp(o) for o in out])
+        return dict(forceU=out[0], velU=out[1], forceB=out[2], velB=out[3])
+
+    def get_force_velocity_raw(self, fu_p, vu_p, fb_p, vb_p):
+        self._call("alens_get_force_velocity", C.c_void_p(fu_p), C.c_void_p(vu_p), C.c_void_p(fb_p), C.c_void_p(vb_p))
+
+    def step_euler(self, dt):
+        self._call("alens_step_euler", C.c_double(dt))
+
+    # ---- instrumentation
+    def get_timers(self):
+        t = Timers()
+        self._call("alens_get_timers", C.byref(t))
+        return t.as_dict()
+
+    def reset_timers(self):
+        self._call("alens_reset_timers")
+
+    def get_collect_stats(self):
+        a, b, c = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        self._call("alens_get_collect_stats", C.byref(a), C.byref(b), C.byref(c))
+        return dict(cells=a.value, candidates=b.value, hits=c.value)

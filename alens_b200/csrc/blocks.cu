@@ -1,0 +1,212 @@
+// blocks.cu -- ConstraintBlock traffic across the boundary: host-generated blocks pushed into the pool
+// (boundary / link / protein constraints) and the refill of a host pool for output and stress.
+//
+// Reference: SimToolbox/Constraint/ConstraintBlock.hpp:30-127 (record), ConstraintCollector::writeBackGamma
+// (Constraint/ConstraintCollector.cpp:439-461), CalcSylinderNearForce::collideStress
+// (Sylinder/SylinderNear.hpp:432-519).  Compiled with -fmad=false (geometry.cuh).
+#include "context.hpp"
+#include "geometry.cuh"
+
+#include <cstring>
+#include <vector>
+
+namespace alens {
+
+static_assert(sizeof(alens_constraint_block) == 272, "ConstraintBlock layout");
+
+struct AppendIn {
+    const int *uI, *uJ, *gidI, *gidJ;
+    const unsigned char *oneSide, *bi;
+    const double *delta0, *gamma, *kappa;
+    const double *vec; // [15][n]: n(3) pI(3) pJ(3) labI(3) labJ(3)
+    long long n;
+};
+struct ConOut {
+    int *idxI, *idxJ, *gidI, *gidJ;
+    signed char *shift;
+    unsigned char *bi, *oneSide;
+    double *delta0, *gamma0, *invKappa, *kappa;
+    double *n, *pI, *pJ, *labI, *labJ;
+    size_t stride;
+};
+
+__global__ void k_append(AppendIn in, ConOut o, const int *__restrict__ userToSorted, long long base) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    const size_t k = (size_t)(base + i), S = o.stride, N = (size_t)in.n;
+    o.idxI[k] = userToSorted[in.uI[i]];
+    o.idxJ[k] = in.oneSide[i] ? -1 : userToSorted[in.uJ[i]];
+    o.gidI[k] = in.gidI[i];
+    o.gidJ[k] = in.gidJ[i];
+    o.shift[k] = 13;
+    o.bi[k] = in.bi[i];
+    o.oneSide[k] = in.oneSide[i];
+    o.delta0[k] = in.delta0[i];
+    o.gamma0[k] = in.gamma[i];
+    const double kap = in.kappa[i];
+    o.kappa[k] = kap;
+    o.invKappa[k] = (in.bi[i] && kap > 0) ? 1 / kap : 0.0; // ConstraintCollector.cpp:415-418
+    for (int c = 0; c < 3; c++) {
+        o.n[k + c * S] = in.vec[(0 + c) * N + i];
+        o.pI[k + c * S] = in.vec[(3 + c) * N + i];
+        o.pJ[k + c * S] = in.vec[(6 + c) * N + i];
+        o.labI[k + c * S] = in.vec[(9 + c) * N + i];
+        o.labJ[k + c * S] = in.vec[(12 + c) * N + i];
+    }
+}
+
+void appendBlocks(Context &c, const alens_constraint_block *b, long long n) {
+    if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_append_constraints: call alens_set_rods first"};
+    if (n <= 0) return;
+    const int off = 0; // rank offset of globalIndex (single rank; slab ranks add their scan offset)
+    std::vector<int> uI(n), uJ(n), gI(n), gJ(n);
+    std::vector<unsigned char> one(n), bi(n);
+    std::vector<double> d0(n), gm(n), kp(n), vec(15 * (size_t)n);
+    for (long long i = 0; i < n; i++) {
+        const alens_constraint_block &q = b[i];
+        const int li = q.globalIndexI - off, lj = q.globalIndexJ - off;
+        if (li < 0 || li >= c.nRods || (!q.oneSide && (lj < 0 || lj >= c.nRods)))
+            throw ArgError{ALENS_ERR_ARG, "alens_append_constraints: globalIndex out of range"};
+        if (!q.oneSide)
+            for (int k = 0; k < 3; k++)
+                if (q.normJ[k] != -q.normI[k])
+                    throw ArgError{ALENS_ERR_UNSUPPORTED, "alens_append_constraints: two-sided block with normJ != -normI"};
+        uI[i] = li; uJ[i] = q.oneSide ? li : lj;
+        gI[i] = q.gidI; gJ[i] = q.gidJ;
+        one[i] = q.oneSide ? 1 : 0; bi[i] = q.bilateral ? 1 : 0;
+        d0[i] = q.delta0; gm[i] = q.gamma; kp[i] = q.kappa;
+        for (int k = 0; k < 3; k++) {
+            vec[(0 + k) * n + i] = q.normI[k];
+            vec[(3 + k) * n + i] = q.posI[k];
+            vec[(6 + k) * n + i] = q.posJ[k];
+            vec[(9 + k) * n + i] = q.labI[k];
+            vec[(12 + k) * n + i] = q.labJ[k];
+        }
+    }
+    cudaStream_t st = c.stream;
+    reserveConstraints(c, (size_t)(c.nCon + n), true);
+    DevBuf<int> dI, dJ, dgI, dgJ;
+    DevBuf<unsigned char> dOne, dBi;
+    DevBuf<double> dD0, dGm, dKp, dVec;
+    dI.reserve(n); dJ.reserve(n); dgI.reserve(n); dgJ.reserve(n); dOne.reserve(n); dBi.reserve(n);
+    dD0.reserve(n); dGm.reserve(n); dKp.reserve(n); dVec.reserve(15 * (size_t)n);
+    auto up = [&](void *d, const void *h, size_t bytes) {
+        ALENS_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
+    };
+    up(dI.p, uI.data(), 4 * n); up(dJ.p, uJ.data(), 4 * n); up(dgI.p, gI.data(), 4 * n); up(dgJ.p, gJ.data(), 4 * n);
+    up(dOne.p, one.data(), n); up(dBi.p, bi.data(), n);
+    up(dD0.p, d0.data(), 8 * n); up(dGm.p, gm.data(), 8 * n); up(dKp.p, kp.data(), 8 * n);
+    up(dVec.p, vec.data(), 8 * 15 * (size_t)n);
+    AppendIn in{dI.p, dJ.p, dgI.p, dgJ.p, dOne.p, dBi.p, dD0.p, dGm.p, dKp.p, dVec.p, n};
+    ConOut o{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cDelta0.p, c.cGamma0.p,
+             c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
+    k_append<<<gridFor(n, 256), 256, 0, st>>>(in, o, c.userToSorted.p, c.nCon);
+    c.launches++;
+    ALENS_CUDA(cudaGetLastError());
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    c.hostBlocks.insert(c.hostBlocks.end(), b, b + n);
+    c.nCon += n;
+    c.haveSetup = false;
+    c.haveSolution = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct BlocksIn {
+    const int *idxI, *idxJ, *gidI, *gidJ, *sUser;
+    const signed char *shift;
+    const double *delta0, *gamma0, *n, *pI, *pJ, *labI, *labJ;
+    const double *sX, *sY, *sZ, *sDx, *sDy, *sDz, *sLc, *sRc;
+    const double *gamma; // solved values or nullptr
+    size_t stride;
+    Box box;
+    int globalIndexBase;
+};
+
+// one thread per collision block: assemble the 272-byte record (and the unit-gamma stress)
+__global__ void k_blocks_out(long long n, BlocksIn in, int withStress, int writeBack, alens_constraint_block *out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t S = in.stride;
+    alens_constraint_block b;
+    memset(&b, 0, sizeof(b));
+    const int si = in.idxI[k], sj = in.idxJ[k];
+    b.delta0 = in.delta0[k];
+    b.gamma = in.gamma0[k];
+    b.gammaLB = 0;
+    b.gidI = in.gidI[k];
+    b.gidJ = in.gidJ[k];
+    b.globalIndexI = in.globalIndexBase + in.sUser[si];
+    b.globalIndexJ = in.globalIndexBase + in.sUser[sj];
+    b.oneSide = 0;
+    b.bilateral = 0;
+    b.kappa = 0;
+    for (int c = 0; c < 3; c++) {
+        b.normI[c] = in.n[k + c * S];
+        b.normJ[c] = -b.normI[c];
+        b.posI[c] = in.pI[k + c * S];
+        b.posJ[c] = in.pJ[k + c * S];
+        b.labI[c] = in.labI[k + c * S];
+        b.labJ[c] = in.labJ[k + c * S];
+    }
+    if (withStress) {
+        const int code = in.shift[k];
+        const int kx = code % 3 - 1, ky = (code / 3) % 3 - 1, kz = code / 9 - 1;
+        const Vec3 cI = v3(in.sX[si], in.sY[si], in.sZ[si]);
+        const Vec3 cJ = v3(in.sX[sj] + kx * in.box.len[0], in.sY[sj] + ky * in.box.len[1],
+                           in.sZ[sj] + kz * in.box.len[2]);
+        const Vec3 dI = v3(in.sDx[si], in.sDy[si], in.sDz[si]), dJ = v3(in.sDx[sj], in.sDy[sj], in.sDz[sj]);
+        const double lcI = in.sLc[si], rcI = in.sRc[si], lcJ = in.sLc[sj], rcJ = in.sRc[sj];
+        const bool sa = lcI < 2 * rcI, sb = lcJ < 2 * rcJ;
+        const Vec3 labI = v3(b.labI[0], b.labI[1], b.labI[2]), labJ = v3(b.labJ[0], b.labJ[1], b.labJ[2]);
+        const Vec3 ez = v3(0, 0, 1);
+        if (sa && sb) { // SylinderNear.hpp:289-290
+            collideStress(ez, ez, cI, cJ, 0, 0, lcI * 0.5 + rcI, lcJ * 0.5 + rcJ, 1.0, labI, labJ, b.stress);
+        } else if (sa) { // sphere I, sylinder J: SylinderNear.hpp:350-351
+            collideStress(ez, dJ, cI, cJ, 0, lcJ, lcI * 0.5 + rcI, rcJ, 1.0, labI, labJ, b.stress);
+        } else if (sb) { // sylinder I, sphere J: same call with (sphere, sylinder) argument order
+            collideStress(ez, dI, cJ, cI, 0, lcI, lcJ * 0.5 + rcJ, rcI, 1.0, labJ, labI, b.stress);
+        } else { // SylinderNear.hpp:409-410
+            collideStress(dI, dJ, cI, cJ, lcI, lcJ, rcI, rcJ, 1.0, labI, labJ, b.stress);
+        }
+    }
+    if (writeBack && in.gamma) { // ConstraintCollector.cpp:449-458
+        b.gamma = in.gamma[k];
+        for (int c = 0; c < 9; c++) b.stress[c] *= b.gamma;
+    }
+    out[k] = b;
+}
+
+void downloadBlocks(Context &c, alens_constraint_block *out, long long cap, bool withStress, bool writeBack) {
+    if (cap < c.nCon) throw ArgError{ALENS_ERR_ARG, "alens_get_constraints: output capacity too small"};
+    if (writeBack && !c.haveSolution) throw ArgError{ALENS_ERR_STATE, "alens_get_constraints: writeBack needs a solve"};
+    cudaStream_t st = c.stream;
+    const long long nColl = c.nColl, nHost = c.nCon - c.nColl;
+    if (nColl > 0) {
+        DevBuf<alens_constraint_block> dOut;
+        dOut.reserve((size_t)nColl);
+        BlocksIn in{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.sUser.p, c.cShift.p, c.cDelta0.p, c.cGamma0.p,
+                    c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p,
+                    c.sDz.p, c.sLc.p, c.sRc.p, writeBack ? c.xSolution : nullptr, c.conCap, c.box, 0};
+        k_blocks_out<<<gridFor(nColl, 128), 128, 0, st>>>(nColl, in, withStress ? 1 : 0, writeBack ? 1 : 0, dOut.p);
+        c.launches++;
+        ALENS_CUDA(cudaGetLastError());
+        ALENS_CUDA(cudaMemcpyAsync(out, dOut.p, sizeof(alens_constraint_block) * (size_t)nColl,
+                                   cudaMemcpyDeviceToHost, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+    }
+    if (nHost > 0) {
+        memcpy(out + nColl, c.hostBlocks.data(), sizeof(alens_constraint_block) * (size_t)nHost);
+        if (writeBack) {
+            std::vector<double> g((size_t)nHost);
+            ALENS_CUDA(cudaMemcpyAsync(g.data(), c.xSolution + nColl, 8 * (size_t)nHost, cudaMemcpyDeviceToHost, st));
+            ALENS_CUDA(cudaStreamSynchronize(st));
+            for (long long i = 0; i < nHost; i++) {
+                alens_constraint_block &b = out[nColl + i];
+                b.gamma = g[i];
+                for (int k = 0; k < 9; k++) b.stress[k] *= b.gamma;
+            }
+        }
+    }
+}
+
+} // namespace alens

@@ -1,0 +1,341 @@
+// capi.cu -- the extern "C" boundary (include/alens_b200.h).  Every entry point converts exceptions
+// into error codes + a message retrievable with alens_last_error(); nothing here computes on the CPU.
+#include "context.hpp"
+
+#include <cstring>
+#include <new>
+
+using namespace alens;
+
+struct alens_ctx {
+    Context c;
+};
+
+static thread_local std::string g_createErr;
+
+template <typename F>
+static int guarded(alens_ctx *ctx, F &&f) {
+    if (!ctx) return ALENS_ERR_ARG;
+    try {
+        ALENS_CUDA(cudaSetDevice(ctx->c.device));
+        f(ctx->c);
+        return ALENS_OK;
+    } catch (const CudaError &e) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) in `%s` at %s:%d", (int)e.code, cudaGetErrorString(e.code),
+                 e.what, e.file, e.line);
+        ctx->c.err = buf;
+        cudaGetLastError();
+        return ALENS_ERR_CUDA;
+    } catch (const ArgError &e) {
+        ctx->c.err = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        ctx->c.err = "host allocation failed";
+        return ALENS_ERR_ARG;
+    }
+}
+
+static float evMs(Context &c, int a, int b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev[a], c.ev[b]);
+    return ms;
+}
+
+extern "C" {
+
+const char *alens_version(void) { return "alens_b200 0.1 (sm_100a)"; }
+
+int alens_create(int device, int rank, int nranks, alens_ctx **out) {
+    if (!out) return ALENS_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_createErr = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+        cudaGetLastError();
+        return ALENS_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev || nranks < 1 || rank < 0 || rank >= nranks) {
+        g_createErr = "alens_create: bad device/rank";
+        return ALENS_ERR_ARG;
+    }
+    alens_ctx *ctx = new (std::nothrow) alens_ctx();
+    if (!ctx) return ALENS_ERR_ARG;
+    ctx->c.device = device;
+    ctx->c.rank = rank;
+    ctx->c.nranks = nranks;
+    int rc = guarded(ctx, [](Context &c) { ctxInit(c); });
+    if (rc != ALENS_OK) {
+        g_createErr = ctx->c.err;
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return ALENS_OK;
+}
+
+void alens_destroy(alens_ctx *ctx) {
+    if (!ctx) return;
+    ctxFree(ctx->c);
+    delete ctx;
+}
+
+const char *alens_last_error(const alens_ctx *ctx) { return ctx ? ctx->c.err.c_str() : g_createErr.c_str(); }
+
+int alens_set_stream(alens_ctx *ctx, void *s) {
+    return guarded(ctx, [&](Context &c) {
+        ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        if (c.ownStream && c.stream) cudaStreamDestroy(c.stream);
+        if (s) {
+            c.stream = (cudaStream_t)s;
+            c.ownStream = false;
+        } else {
+            ALENS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            c.ownStream = true;
+        }
+    });
+}
+
+int alens_set_domain(alens_ctx *ctx, const double lo[3], const double hi[3], const int pbc[3]) {
+    return guarded(ctx, [&](Context &c) {
+        for (int k = 0; k < 3; k++) {
+            if (!(hi[k] > lo[k])) throw ArgError{ALENS_ERR_ARG, "alens_set_domain: boxHigh must exceed boxLow"};
+            c.box.lo[k] = lo[k];
+            c.box.hi[k] = hi[k];
+            c.box.len[k] = hi[k] - lo[k]; // PS::F64ort::getFullLength
+            c.box.pbc[k] = pbc[k] ? 1 : 0;
+        }
+        c.haveBox = true;
+    });
+}
+
+int alens_set_collision_params(alens_ctx *ctx, double dRatio, double lRatio, double colBuf) {
+    return guarded(ctx, [&](Context &c) {
+        if (!(dRatio > 0) || !(lRatio > 0) || !(colBuf >= 0))
+            throw ArgError{ALENS_ERR_ARG, "alens_set_collision_params: ratios must be > 0 and colBuf >= 0"};
+        c.dRatio = dRatio;
+        c.lRatio = lRatio;
+        c.colBuf = colBuf;
+    });
+}
+
+int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, const double *quat, const double *len,
+                   const double *rad, const unsigned char *imm, int wrap) {
+    return guarded(ctx, [&](Context &c) {
+        if (!c.haveBox) throw ArgError{ALENS_ERR_STATE, "alens_set_rods: call alens_set_domain first"};
+        if (n < 0 || (n > 0 && (!gid || !pos || !quat || !len || !rad)))
+            throw ArgError{ALENS_ERR_ARG, "alens_set_rods: null input"};
+        cudaStream_t st = c.stream;
+        ALENS_CUDA(cudaEventRecord(c.ev[0], st));
+        c.nRods = n;
+        const size_t N = (size_t)n;
+        c.uGid.reserve(N + 1); c.uPos.reserve(3 * N + 3); c.uQuat.reserve(4 * N + 4);
+        c.uLen.reserve(N + 1); c.uRad.reserve(N + 1); c.uImm.reserve(N + 1);
+        if (n > 0) {
+            ALENS_CUDA(cudaMemcpyAsync(c.uGid.p, gid, 4 * N, cudaMemcpyHostToDevice, st));
+            ALENS_CUDA(cudaMemcpyAsync(c.uPos.p, pos, 24 * N, cudaMemcpyHostToDevice, st));
+            ALENS_CUDA(cudaMemcpyAsync(c.uQuat.p, quat, 32 * N, cudaMemcpyHostToDevice, st));
+            ALENS_CUDA(cudaMemcpyAsync(c.uLen.p, len, 8 * N, cudaMemcpyHostToDevice, st));
+            ALENS_CUDA(cudaMemcpyAsync(c.uRad.p, rad, 8 * N, cudaMemcpyHostToDevice, st));
+            if (imm) ALENS_CUDA(cudaMemcpyAsync(c.uImm.p, imm, N, cudaMemcpyHostToDevice, st));
+            else ALENS_CUDA(cudaMemsetAsync(c.uImm.p, 0, N, st));
+        }
+        g_lastMaxR = hostMaxRadius(n, len, rad, c.lRatio, c.dRatio); // overlaps with the copies
+        rodsUploaded(c, wrap != 0);
+        ALENS_CUDA(cudaEventRecord(c.ev[1], st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        c.timers.upload_ms = evMs(c, 0, 1);
+    });
+}
+
+int alens_set_rods_aos(alens_ctx *ctx, int n, const void *sy, size_t stride, int wrap) {
+    if (!ctx) return ALENS_ERR_ARG;
+    if (n < 0 || (n > 0 && !sy) || stride < 136) {
+        ctx->c.err = "alens_set_rods_aos: bad arguments";
+        return ALENS_ERR_ARG;
+    }
+    // field offsets of the reference `Sylinder` record (Sylinder.hpp:38-57): gid 0, isImmovable 16,
+    // radius 24, length 40, pos 80, orientation 104
+    std::vector<int> gid(n);
+    std::vector<double> pos(3 * (size_t)n), q(4 * (size_t)n), len(n), rad(n);
+    std::vector<unsigned char> imm(n);
+    const char *base = (const char *)sy;
+    for (int i = 0; i < n; i++) {
+        const char *p = base + (size_t)i * stride;
+        memcpy(&gid[i], p + 0, 4);
+        imm[i] = *(const unsigned char *)(p + 16);
+        memcpy(&rad[i], p + 24, 8);
+        memcpy(&len[i], p + 40, 8);
+        memcpy(&pos[3 * (size_t)i], p + 80, 24);
+        memcpy(&q[4 * (size_t)i], p + 104, 32);
+    }
+    return alens_set_rods(ctx, n, gid.data(), pos.data(), q.data(), len.data(), rad.data(), imm.data(), wrap);
+}
+
+int alens_get_positions(alens_ctx *ctx, double *pos) {
+    return guarded(ctx, [&](Context &c) {
+        if (c.nRods > 0) {
+            ALENS_CUDA(cudaMemcpyAsync(pos, c.uPos.p, 24 * (size_t)c.nRods, cudaMemcpyDeviceToHost, c.stream));
+            ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        }
+    });
+}
+
+int alens_get_rod_state(alens_ctx *ctx, double *pos, double *quat) {
+    return guarded(ctx, [&](Context &c) {
+        if (c.nRods > 0) {
+            if (pos) ALENS_CUDA(cudaMemcpyAsync(pos, c.uPos.p, 24 * (size_t)c.nRods, cudaMemcpyDeviceToHost, c.stream));
+            if (quat)
+                ALENS_CUDA(cudaMemcpyAsync(quat, c.uQuat.p, 32 * (size_t)c.nRods, cudaMemcpyDeviceToHost, c.stream));
+            ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        }
+    });
+}
+
+int alens_collect_pair_collision(alens_ctx *ctx, long long *nCon) {
+    return guarded(ctx, [&](Context &c) {
+        ALENS_CUDA(cudaEventRecord(c.ev[0], c.stream));
+        collectPairs(c);
+        ALENS_CUDA(cudaEventRecord(c.ev[1], c.stream));
+        ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        c.timers.collect_ms = evMs(c, 0, 1);
+        if (nCon) *nCon = c.nCon;
+    });
+}
+
+int alens_append_constraints(alens_ctx *ctx, const alens_constraint_block *b, long long n) {
+    return guarded(ctx, [&](Context &c) {
+        if (n < 0 || (n > 0 && !b)) throw ArgError{ALENS_ERR_ARG, "alens_append_constraints: bad arguments"};
+        appendBlocks(c, b, n);
+    });
+}
+
+int alens_clear_constraints(alens_ctx *ctx) {
+    return guarded(ctx, [&](Context &c) {
+        c.nCon = c.nColl = 0;
+        c.hostBlocks.clear();
+        c.haveSetup = false;
+        c.haveSolution = false;
+    });
+}
+
+int alens_num_constraints(alens_ctx *ctx, long long *n) {
+    return guarded(ctx, [&](Context &c) {
+        if (n) *n = c.nCon;
+    });
+}
+
+int alens_get_constraints(alens_ctx *ctx, alens_constraint_block *out, long long cap, int withStress, int writeBack) {
+    return guarded(ctx, [&](Context &c) { downloadBlocks(c, out, cap, withStress != 0, writeBack != 0); });
+}
+
+int alens_calc_mobility(alens_ctx *ctx, double mu) {
+    return guarded(ctx, [&](Context &c) { calcMobility(c, mu); });
+}
+
+int alens_mobility_apply(alens_ctx *ctx, const double *x, double *y) {
+    return guarded(ctx, [&](Context &c) { mobilityApply(c, x, y); });
+}
+
+int alens_setup_constraints(alens_ctx *ctx, const double *velNC, double dt) {
+    return guarded(ctx, [&](Context &c) {
+        ALENS_CUDA(cudaEventRecord(c.ev[0], c.stream));
+        setupConstraints(c, velNC, dt);
+        ALENS_CUDA(cudaEventRecord(c.ev[1], c.stream));
+        ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        c.timers.setup_ms = evMs(c, 0, 1);
+    });
+}
+
+int alens_solve_constraints(alens_ctx *ctx, const double *velNC, double dt, double res, int maxIte, int choice,
+                            alens_solve_report *rep) {
+    int rc = alens_setup_constraints(ctx, velNC, dt);
+    if (rc != ALENS_OK) return rc;
+    rc = guarded(ctx, [&](Context &c) {
+        if (maxIte < 0) throw ArgError{ALENS_ERR_ARG, "alens_solve_constraints: maxIte < 0"};
+        solveConstraints(c, res, maxIte, choice);
+    });
+    if (rep && ctx) *rep = ctx->c.lastReport;
+    return rc;
+}
+
+int alens_operator_apply(alens_ctx *ctx, const double *x, double *y, double *force, double *vel) {
+    return guarded(ctx, [&](Context &c) { operatorApply(c, x, y, force, vel); });
+}
+
+int alens_get_history(alens_ctx *ctx, double *rows, int cap, int *nRows) {
+    return guarded(ctx, [&](Context &c) {
+        const int have = (int)(c.hist.size() / 6);
+        const int n = have < cap ? have : cap;
+        if (rows && n > 0) memcpy(rows, c.hist.data(), 48 * (size_t)n);
+        if (nRows) *nRows = have;
+    });
+}
+
+int alens_get_gamma(alens_ctx *ctx, double *gamma, long long cap) {
+    return guarded(ctx, [&](Context &c) {
+        if (!c.haveSolution) throw ArgError{ALENS_ERR_STATE, "alens_get_gamma: no solution available"};
+        if (cap < c.nCon) throw ArgError{ALENS_ERR_ARG, "alens_get_gamma: capacity too small"};
+        if (c.nCon > 0) {
+            ALENS_CUDA(cudaMemcpyAsync(gamma, c.xSolution, 8 * (size_t)c.nCon, cudaMemcpyDeviceToHost, c.stream));
+            ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        }
+    });
+}
+
+int alens_get_force_velocity(alens_ctx *ctx, double *fU, double *vU, double *fB, double *vB) {
+    return guarded(ctx, [&](Context &c) {
+        if (!c.haveSolution) throw ArgError{ALENS_ERR_STATE, "alens_get_force_velocity: no solution available"};
+        const size_t bytes = 48 * (size_t)c.nRods;
+        cudaStream_t st = c.stream;
+        ALENS_CUDA(cudaEventRecord(c.ev[0], st));
+        if (bytes) {
+            if (fU) ALENS_CUDA(cudaMemcpyAsync(fU, c.outFU.p, bytes, cudaMemcpyDeviceToHost, st));
+            if (vU) ALENS_CUDA(cudaMemcpyAsync(vU, c.outVU.p, bytes, cudaMemcpyDeviceToHost, st));
+            if (fB) ALENS_CUDA(cudaMemcpyAsync(fB, c.outFB.p, bytes, cudaMemcpyDeviceToHost, st));
+            if (vB) ALENS_CUDA(cudaMemcpyAsync(vB, c.outVB.p, bytes, cudaMemcpyDeviceToHost, st));
+        }
+        ALENS_CUDA(cudaEventRecord(c.ev[1], st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        c.timers.download_ms = evMs(c, 0, 1);
+    });
+}
+
+int alens_step_euler(alens_ctx *ctx, double dt) {
+    return guarded(ctx, [&](Context &c) { stepEuler(c, dt); });
+}
+
+int alens_get_timers(alens_ctx *ctx, alens_timers *t) {
+    return guarded(ctx, [&](Context &c) {
+        c.timers.total_launches = c.launches;
+        if (t) *t = c.timers;
+    });
+}
+
+int alens_reset_timers(alens_ctx *ctx) {
+    return guarded(ctx, [&](Context &c) {
+        memset(&c.timers, 0, sizeof(c.timers));
+        c.launches = 0;
+    });
+}
+
+int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCand, long long *nHits) {
+    return guarded(ctx, [&](Context &c) {
+        if (nCells) *nCells = c.grid.ncell;
+        if (nCand) *nCand = c.statCand;
+        if (nHits) *nHits = c.nColl;
+    });
+}
+
+int alens_comm_unique_id(void *id128) {
+    (void)id128;
+    return ALENS_ERR_UNSUPPORTED;
+}
+int alens_comm_init(alens_ctx *ctx, const void *id128) {
+    (void)id128;
+    if (ctx) ctx->c.err = "multi-GPU communicator not built in this configuration";
+    return ALENS_ERR_UNSUPPORTED;
+}
+
+} // extern "C"

@@ -1,0 +1,210 @@
+// context.hpp -- the state behind alens_ctx: device buffers, configuration, per-phase timers.
+// All device memory is owned here (grow-only buffers sized for the largest step seen so far).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/alens_b200.h"
+
+namespace alens {
+
+struct CudaError {
+    cudaError_t code;
+    const char *what;
+    const char *file;
+    int line;
+};
+
+#define ALENS_CUDA(expr)                                                                                            \
+    do {                                                                                                            \
+        cudaError_t e__ = (expr);                                                                                   \
+        if (e__ != cudaSuccess) throw ::alens::CudaError{e__, #expr, __FILE__, __LINE__};                           \
+    } while (0)
+
+struct ArgError {
+    int code;
+    std::string msg;
+};
+
+// grow-only device array
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // contents are NOT preserved on growth unless keep=true
+    void reserve(size_t n, cudaStream_t st = 0, bool keep = false, size_t keepN = 0) {
+        if (n <= cap) return;
+        size_t ncap = n + n / 4 + 64;
+        T *np = nullptr;
+        ALENS_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
+        if (keep && p && keepN) ALENS_CUDA(cudaMemcpyAsync(np, p, keepN * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        if (p) {
+            ALENS_CUDA(cudaStreamSynchronize(st));
+            cudaFree(p);
+        }
+        p = np;
+        cap = ncap;
+    }
+};
+
+// pinned host staging buffer (grow-only)
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    void *reserve(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            cap = bytes + bytes / 4 + 4096;
+            ALENS_CUDA(cudaMallocHost(&p, cap));
+        }
+        return p;
+    }
+};
+
+struct Box {
+    double lo[3], hi[3], len[3];
+    int pbc[3];
+};
+
+struct CellGrid {
+    int n[3];       // cells per axis
+    int ncell;      // product
+    double inv[3];  // n[k] / len[k]
+    double cutoff;
+};
+
+// scalar block shared between the BCQP kernels (lives in device memory, mirrored to pinned host)
+struct SolverScalars {
+    double alpha;      // current step (BBPGD alpha / APGD tk)
+    double res;        // last resPhi
+    double dotA, dotB; // last a, b of the BB step
+    int ite;           // iteCount
+    int mv;            // mvCount
+    int done;          // 1 converged, 2 stagnated, 3 projection error
+    int nhist;         // history rows written
+    unsigned int ticket; // last-block election counter
+    int pad_;
+};
+
+struct Context {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    bool ownStream = true;
+    std::string err;
+
+    Box box{};
+    bool haveBox = false;
+    double dRatio = 1.0, lRatio = 1.0, colBuf = 0.0;
+    double viscosity = 0.0;
+    bool haveMob = false;
+
+    // ---- rods, user order (what the host uploaded) ----
+    int nRods = 0;
+    DevBuf<int> uGid;
+    DevBuf<double> uPos, uQuat, uLen, uRad; // 3n, 4n, n, n
+    DevBuf<unsigned char> uImm;
+    DevBuf<int> uCell;      // cell id per rod
+    DevBuf<int> userToSorted;
+    DevBuf<double> uVelNC;  // 6n, user order
+    bool haveVelNC = false;
+
+    // ---- cell list + rods, sorted (cell-major) order ----
+    CellGrid grid{};
+    DevBuf<int> cellCount, cellStart, cellFill; // ncell(+1)
+    DevBuf<int> sUser;                          // sorted -> user index
+    DevBuf<int> sGid;
+    DevBuf<double> sX, sY, sZ, sDx, sDy, sDz, sLc, sRc; // collision geometry
+    DevBuf<double> sLen, sRad;                           // hydrodynamic length/radius
+    DevBuf<unsigned char> sImm;
+    DevBuf<double> sInvDrag; // 3 per rod: 1/para, 1/perp, 1/rot (0 if immovable)
+    bool sorted = false;
+
+    // ---- constraints (solver order) ----
+    long long nCon = 0, nColl = 0; // total / produced by pair collection
+    DevBuf<int> cellHits, cellHitStart;
+    DevBuf<int> cIdxI, cIdxJ; // sorted rod index; cIdxJ = -1 for oneSide
+    DevBuf<int> cGidI, cGidJ;
+    DevBuf<double> cN, cPI, cPJ;     // SoA by component: [3][cap] each (stride = conCap)
+    DevBuf<double> cLabI, cLabJ;     // [3][cap]
+    DevBuf<double> cDelta0, cGamma0, cInvKappa; // invKappa = 1/kappa (not yet /dt)
+    DevBuf<double> cKappa;
+    DevBuf<unsigned char> cBi, cOneSide;
+    DevBuf<signed char> cShift; // image of J relative to I, code = (kx+1)+3(ky+1)+9(kz+1)
+    DevBuf<double> cStressHost; // 9 per appended block (host supplied), indexed k - nColl
+    size_t conCap = 0;          // component stride of the SoA arrays
+    std::vector<alens_constraint_block> hostBlocks; // verbatim copies of appended blocks (for the refill)
+    long long statCand = 0;
+    DevBuf<unsigned long long> dCounters; // [0] candidates, [1] hits
+
+    // ---- incidence (rod -> constraints), built in setup ----
+    DevBuf<int> incDeg, incStart, incFill; // nRods(+1)
+    DevBuf<int> incCon;                    // constraint id per slot
+    DevBuf<double> incCol;                 // 6 per slot: D column block for that (rod, constraint)
+    long long nInc = 0;
+    bool haveSetup = false;
+    double dt = 0.0;
+
+    // ---- solver vectors ----
+    DevBuf<double> vX0, vX1, vG0, vG1, vB, vLbFlag; // x/g ping-pong, q, bilateral flag as double
+    DevBuf<double> vTmp0, vTmp1, vTmp2, vTmp3, vTmp4, vTmp5; // APGD work vectors
+    DevBuf<double> rU, rF;                         // 6 per rod: vel, force of the last apply
+    DevBuf<double> rUb, rFb;                       // bilateral part
+    DevBuf<double> outFU, outVU, outFB, outVB;     // user order results
+    DevBuf<double> redPartial;                     // per-block partial reductions
+    DevBuf<SolverScalars> dScal;
+    DevBuf<double> dHist;                          // 6 per row
+    int histCap = 0;
+    SolverScalars *hScal = nullptr;                // pinned mirror
+    std::vector<double> hist;                      // host copy of the last history
+    double *xLastApplied = nullptr;                // device ptr of the vector the operator last saw
+    double *xSolution = nullptr;                   // device ptr of the returned iterate
+    bool haveSolution = false;
+    alens_solve_report lastReport{};
+
+    // ---- instrumentation ----
+    alens_timers timers{};
+    cudaEvent_t ev[8] = {};
+    long long launches = 0;
+
+    PinnedBuf pin0, pin1;
+
+    // ---- multi-GPU ----
+    void *nccl = nullptr; // ncclComm_t
+};
+
+// kernels' host entry points (collide.cu / solver.cu)
+void ctxInit(Context &c);
+void ctxFree(Context &c);
+void rodsUploaded(Context &c, bool wrap);           // rod_pack + cell list + sorted SoA
+void collectPairs(Context &c);                      // broad + narrow phase
+void appendBlocks(Context &c, const alens_constraint_block *b, long long n);
+void downloadBlocks(Context &c, alens_constraint_block *out, long long cap, bool withStress, bool writeBack);
+void calcMobility(Context &c, double mu);
+void mobilityApply(Context &c, const double *x, double *y);
+void setupConstraints(Context &c, const double *velNC, double dt);
+void operatorApply(Context &c, const double *x, double *y, double *force, double *vel);
+void solveConstraints(Context &c, double res, int maxIte, int choice);
+void stepEuler(Context &c, double dt);
+void reserveConstraints(Context &c, size_t n, bool keep);
+
+inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }
+
+// shared small kernels (collide.cu)
+void launchScanInt(const int *in, int *out, int n, cudaStream_t st);
+extern double g_lastMaxR;
+double hostMaxRadius(int n, const double *len, const double *rad, double lRatio, double dRatio);
+
+} // namespace alens

@@ -1,0 +1,912 @@
+// solver.cu -- mobility, matrix-free constraint operator and the BCQP (BBPGD / APGD) loops.
+//
+// Replaces ConstraintCollector::buildConstraintMatrixVector (SimToolbox/Constraint/ConstraintCollector.cpp:237-423),
+// SylinderSystem::calcMobMatrix (SimToolbox/Sylinder/SylinderSystem.cpp:622-717), ConstraintOperator
+// (Constraint/ConstraintOperator.cpp:4-71), ConstraintSolver::setup/solveConstraints
+// (Constraint/ConstraintSolver.cpp:4-107) and BCQPSolver::solveBBPGD/solveAPGD (Constraint/BCQPSolver.cpp:134-497).
+//
+// D is never materialised as CSR.  A constraint k stores (n, posI, posJ, idxI, idxJ); row k of D^T is
+// [n, posI x n] on rod I and [-n, posJ x (-n)] on rod J (ConstraintCollector.cpp:298-341 with normJ = -normI).
+//   k_force_vel : f = D x (gather over the rod -> constraint incidence, staged through shared memory),
+//                 u = M f applied analytically from (q, 1/drag) -- one launch per operator apply
+//   k_bb_tail   : y = D^T u + K^-1 x, g = y + b, projected-gradient residual, BB dot products,
+//                 deterministic two-level reduction, step-size/termination logic in the last CTA
+// Compiled with -fmad=false so that elementwise arithmetic rounds like the CPU restatement.
+#include "context.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace alens {
+
+static constexpr int kFvBlock = 128;  // rods per CTA in k_force_vel
+static constexpr int kFvChunk = 512;  // incidence slots staged per pass
+static constexpr int kVecBlock = 256; // threads per CTA of the per-constraint kernels
+static constexpr double kHuge = DBL_MAX / 10; // BCQPSolver.cpp:499-510
+
+// ------------------------------------------------------------------------------------------------
+// mobility coefficients: Sylinder::calcDragCoeff (Sylinder.cpp:69-82); immovable rods get zero
+// mobility (SylinderSystem.cpp:660-662)
+__global__ void k_mob_coeff(int n, const double *__restrict__ len, const double *__restrict__ rad,
+                            const unsigned char *__restrict__ imm, double mu, double *__restrict__ invDrag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double Pi = 3.14159265358979323846;
+    const double length = len[i], radius = rad[i];
+    double dPara, dPerp, dRot;
+    if (length < radius * 2) {
+        const double r = 0.5 * length + radius;
+        dPara = 6 * Pi * r * mu;
+        dPerp = dPara;
+        dRot = 8 * Pi * r * r * r * mu;
+    } else {
+        const double b = -(1 + 2 * log(radius / (length)));
+        dPara = 8 * Pi * length * mu / (2 * b);
+        dPerp = 8 * Pi * length * mu / (b + 2);
+        dRot = 2 * Pi * mu * length * length * length / (3 * (b + 2));
+    }
+    const bool im = imm[i] != 0;
+    invDrag[i] = im ? 0.0 : 1 / dPara;
+    invDrag[n + i] = im ? 0.0 : 1 / dPerp;
+    invDrag[2 * n + i] = im ? 0.0 : 1 / dRot;
+}
+
+struct MobIn {
+    const double *dx, *dy, *dz; // unit direction q
+    const double *invDrag;      // [3][n]
+    int n;
+};
+
+// u = M f with Mtt = qq^T/zPara + (I - qq^T)/zPerp, Mrr = I/zRot (SylinderSystem.cpp:664-665)
+__device__ __forceinline__ void applyMob(const MobIn &m, int r, const double f[6], double u[6]) {
+    const double qx = m.dx[r], qy = m.dy[r], qz = m.dz[r];
+    const double iPara = m.invDrag[r], iPerp = m.invDrag[m.n + r], iRot = m.invDrag[2 * m.n + r];
+    const double qf = qx * f[0] + qy * f[1] + qz * f[2];
+    const double px = qf * qx, py = qf * qy, pz = qf * qz;
+    u[0] = iPara * px + iPerp * (f[0] - px);
+    u[1] = iPara * py + iPerp * (f[1] - py);
+    u[2] = iPara * pz + iPerp * (f[2] - pz);
+    u[3] = iRot * f[3];
+    u[4] = iRot * f[4];
+    u[5] = iRot * f[5];
+}
+
+// y = M x on 6n vectors given in USER order (alens_mobility_apply)
+__global__ void k_mob_apply_user(MobIn m, const int *__restrict__ userToSorted, const double *__restrict__ x,
+                                 double *__restrict__ y) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= m.n) return;
+    double f[6], o[6];
+    for (int c = 0; c < 6; c++) f[c] = x[6 * u + c];
+    applyMob(m, userToSorted[u], f, o);
+    for (int c = 0; c < 6; c++) y[6 * u + c] = o[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// incidence rod -> constraints (replaces the explicit transpose of ConstraintOperator.cpp:14-20)
+__global__ void k_inc_count(long long nc, const int *__restrict__ idxI, const int *__restrict__ idxJ,
+                            int *__restrict__ deg) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    atomicAdd(&deg[idxI[k]], 1);
+    const int j = idxJ[k];
+    if (j >= 0) atomicAdd(&deg[j], 1);
+}
+
+__global__ void k_inc_fill(long long nc, const int *__restrict__ idxI, const int *__restrict__ idxJ,
+                           const int *__restrict__ start, int *__restrict__ fill, int *__restrict__ incCon) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    const int i = idxI[k], j = idxJ[k];
+    incCon[start[i] + atomicAdd(&fill[i], 1)] = (int)(2 * k);
+    if (j >= 0) incCon[start[j] + atomicAdd(&fill[j], 1)] = (int)(2 * k + 1);
+}
+
+struct ConGeom {
+    const int *idxI, *idxJ;
+    const double *n, *pI, *pJ; // [3][stride]
+    size_t stride;
+};
+
+// per rod: sort the slot list by (constraint, side) -> deterministic summation order, then emit the
+// 6-vector D column block of every slot: s*[n, p x n] (ConstraintCollector.cpp:313-318)
+__global__ void k_inc_finish(int nRods, const int *__restrict__ start, int *__restrict__ incCon, ConGeom g,
+                             double *__restrict__ incCol, size_t nInc) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRods) return;
+    const int b = start[r], e = start[r + 1];
+    for (int a = b + 1; a < e; a++) { // insertion sort, lists are short
+        const int v = incCon[a];
+        int p = a - 1;
+        while (p >= b && incCon[p] > v) {
+            incCon[p + 1] = incCon[p];
+            p--;
+        }
+        incCon[p + 1] = v;
+    }
+    for (int s = b; s < e; s++) {
+        const int k2 = incCon[s];
+        const size_t k = (size_t)(k2 >> 1);
+        const bool sideJ = k2 & 1;
+        double gx = g.n[k], gy = g.n[k + g.stride], gz = g.n[k + 2 * g.stride];
+        const double *P = sideJ ? g.pJ : g.pI;
+        const double px = P[k], py = P[k + g.stride], pz = P[k + 2 * g.stride];
+        if (sideJ) { gx = -gx; gy = -gy; gz = -gz; }
+        incCol[s] = gx;
+        incCol[nInc + s] = gy;
+        incCol[2 * nInc + s] = gz;
+        incCol[3 * nInc + s] = (gz * py - gy * pz);
+        incCol[4 * nInc + s] = (gx * pz - gz * px);
+        incCol[5 * nInc + s] = (gy * px - gx * py);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup: q = delta0/dt + D^T v_nc (ConstraintSolver.cpp:18-27), K^-1/dt, bilateral flag, x0 = gamma guess
+__global__ void k_setup(long long nc, ConGeom g, const int *__restrict__ sUser, const double *__restrict__ velNC,
+                        const double *__restrict__ delta0, const double *__restrict__ gamma0,
+                        const double *__restrict__ invKappa, const unsigned char *__restrict__ bi, double invDt,
+                        double *__restrict__ b, double *__restrict__ invKdt, double *__restrict__ lbFlag,
+                        double *__restrict__ x0) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    double dnc = 0;
+    if (velNC) {
+        const double gx = g.n[k], gy = g.n[k + g.stride], gz = g.n[k + 2 * g.stride];
+        {
+            const double *v = velNC + 6 * (size_t)sUser[g.idxI[k]];
+            const double px = g.pI[k], py = g.pI[k + g.stride], pz = g.pI[k + 2 * g.stride];
+            dnc = gx * v[0];
+            dnc += gy * v[1];
+            dnc += gz * v[2];
+            dnc += (gz * py - gy * pz) * v[3];
+            dnc += (gx * pz - gz * px) * v[4];
+            dnc += (gy * px - gx * py) * v[5];
+        }
+        const int j = g.idxJ[k];
+        if (j >= 0) {
+            const double *v = velNC + 6 * (size_t)sUser[j];
+            const double px = g.pJ[k], py = g.pJ[k + g.stride], pz = g.pJ[k + 2 * g.stride];
+            const double hx = -gx, hy = -gy, hz = -gz;
+            dnc += hx * v[0];
+            dnc += hy * v[1];
+            dnc += hz * v[2];
+            dnc += (hz * py - hy * pz) * v[3];
+            dnc += (hx * pz - hz * px) * v[4];
+            dnc += (hy * px - hx * py) * v[5];
+        }
+    }
+    b[k] = 1.0 * (delta0[k] * invDt) + 1.0 * dnc;
+    invKdt[k] = invKappa[k] * invDt;
+    lbFlag[k] = bi[k] ? 1.0 : 0.0;
+    x0[k] = gamma0[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// f = D x, u = M f.  One CTA owns kFvBlock consecutive rods = one contiguous range of incidence slots;
+// the range is streamed (fully coalesced, SoA) through shared memory in chunks and each thread then
+// sums its own rod's slots in slot order.
+struct FvIn {
+    const int *incStart, *incCon;
+    const double *incCol; // [6][nInc]
+    size_t nInc;
+    int nRods;
+};
+
+template <bool MASK, bool WRITE_F>
+__global__ void __launch_bounds__(kFvBlock)
+k_force_vel(FvIn in, MobIn mob, const double *__restrict__ x, const double *__restrict__ mask,
+            double *__restrict__ U, double *__restrict__ F, const SolverScalars *__restrict__ scal) {
+    if (scal && scal->done) return;
+    __shared__ double sm[6][kFvChunk];
+    const int r0 = blockIdx.x * kFvBlock;
+    const int rEnd = min(in.nRods, r0 + kFvBlock);
+    const int r = r0 + threadIdx.x;
+    const int sBeg = in.incStart[r0], sEnd = in.incStart[rEnd];
+    int myBeg = 0, myEnd = 0;
+    if (r < rEnd) {
+        myBeg = in.incStart[r];
+        myEnd = in.incStart[r + 1];
+    }
+    double f[6] = {0, 0, 0, 0, 0, 0};
+    for (int c0 = sBeg; c0 < sEnd; c0 += kFvChunk) {
+        const int n = min(kFvChunk, sEnd - c0);
+        for (int s = threadIdx.x; s < n; s += kFvBlock) {
+            const size_t gs = (size_t)c0 + s;
+            const int k = in.incCon[gs] >> 1;
+            double xv = x[k];
+            if (MASK) xv = 1.0 * xv * mask[k];
+#pragma unroll
+            for (int c = 0; c < 6; c++) sm[c][s] = in.incCol[c * in.nInc + gs] * xv;
+        }
+        __syncthreads();
+        const int lo = max(myBeg, c0) - c0, hi = min(myEnd, c0 + n) - c0;
+        for (int s = lo; s < hi; s++) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) f[c] += sm[c][s];
+        }
+        __syncthreads();
+    }
+    if (r < rEnd) {
+        double u[6];
+        applyMob(mob, r, f, u);
+        double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
+        Up[0] = make_double2(u[0], u[1]);
+        Up[1] = make_double2(u[2], u[3]);
+        Up[2] = make_double2(u[4], u[5]);
+        if (WRITE_F) {
+            double2 *Fp = reinterpret_cast<double2 *>(F + 6 * (size_t)r);
+            Fp[0] = make_double2(f[0], f[1]);
+            Fp[1] = make_double2(f[2], f[3]);
+            Fp[2] = make_double2(f[4], f[5]);
+        }
+    }
+}
+
+// row k of D^T times u
+__device__ __forceinline__ double dtransRow(const ConGeom &g, size_t k, const double *__restrict__ U) {
+    const double gx = g.n[k], gy = g.n[k + g.stride], gz = g.n[k + 2 * g.stride];
+    double y;
+    {
+        const double2 *u = reinterpret_cast<const double2 *>(U + 6 * (size_t)g.idxI[k]);
+        const double2 a = u[0], b = u[1], c = u[2];
+        const double px = g.pI[k], py = g.pI[k + g.stride], pz = g.pI[k + 2 * g.stride];
+        y = gx * a.x;
+        y += gy * a.y;
+        y += gz * b.x;
+        y += (gz * py - gy * pz) * b.y;
+        y += (gx * pz - gz * px) * c.x;
+        y += (gy * px - gx * py) * c.y;
+    }
+    const int j = g.idxJ[k];
+    if (j >= 0) {
+        const double2 *u = reinterpret_cast<const double2 *>(U + 6 * (size_t)j);
+        const double2 a = u[0], b = u[1], c = u[2];
+        const double px = g.pJ[k], py = g.pJ[k + g.stride], pz = g.pJ[k + 2 * g.stride];
+        const double hx = -gx, hy = -gy, hz = -gz;
+        y += hx * a.x;
+        y += hy * a.y;
+        y += hz * b.x;
+        y += (hz * py - hy * pz) * b.y;
+        y += (hx * pz - hz * px) * c.x;
+        y += (hy * px - hx * py) * c.y;
+    }
+    return y;
+}
+
+// plain operator tail: y = D^T u + (K^-1/dt) x   (ConstraintOperator.cpp:54-69)
+__global__ void k_dtrans(long long nc, ConGeom g, const double *__restrict__ U, const double *__restrict__ x,
+                         const double *__restrict__ invKdt, double *__restrict__ y) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    double v = dtransRow(g, (size_t)k, U);
+    v += 1.0 * invKdt[k] * x[k];
+    y[k] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic CTA reduction of (sum0, sum1, sum2, max) -> out[4]
+__device__ __forceinline__ void blockReduce4(double s0, double s1, double s2, double mx, double out[4]) {
+    __shared__ double red[kVecBlock / 32][4];
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, o);
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        red[w][0] = s0; red[w][1] = s1; red[w][2] = s2; red[w][3] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0, m = 0;
+        for (int i = 0; i < kVecBlock / 32; i++) {
+            a += red[i][0]; b += red[i][1]; c += red[i][2]; m = fmax(m, red[i][3]);
+        }
+        out[0] = a; out[1] = b; out[2] = c; out[3] = m;
+    }
+    __syncthreads();
+}
+
+// Dai & Fletcher eq. 2.2 projected gradient (BCQPSolver.cpp:461-497); bounds: lb = -0.1*DBL_MAX*biFlag
+// (ConstraintSolver.cpp:69), ub = DBL_MAX/10 (BCQPSolver.cpp:499-510)
+__device__ __forceinline__ double projGrad(double x, double g, double lbFlag, int &err) {
+    const double eps = DBL_EPSILON * 100;
+    const double lb = (-DBL_MAX * .1) * lbFlag, ub = kHuge;
+    if (x < lb + eps) return g < 0.0 ? g : 0.0;
+    if (x > ub - eps) return g > 0.0 ? g : 0.0;
+    if (x > lb && x < ub) return g;
+    err = 1;
+    return 0.0;
+}
+
+// x = P(xprev - alpha*gprev)   (BCQPSolver.cpp:191-192, :431-459)
+__global__ void k_bb_update(long long nc, const double *__restrict__ xprev, const double *__restrict__ gprev,
+                            const double *__restrict__ lbFlag, double *__restrict__ x,
+                            const SolverScalars *__restrict__ scal) {
+    if (scal->done) return;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    const double alpha = scal->alpha;
+    double v = (-alpha) * gprev[k] + 1.0 * xprev[k];
+    const double lb = (-DBL_MAX * .1) * lbFlag[k];
+    v = v > lb ? v : lb;
+    v = v < kHuge ? v : kHuge;
+    x[k] = v;
+}
+
+struct BbTail {
+    long long nc;
+    ConGeom g;
+    const double *U, *x, *xprev, *gprev, *b, *invKdt, *lbFlag;
+    double *gout;
+    double *partial; // [gridDim][4]
+    SolverScalars *scal;
+    double *hist;
+    int histCap;
+    double tol;
+    int ite; // iteration number of this launch (0 = initial gradient)
+};
+
+// g = A x + b, residual, BB dots; the last CTA to finish turns the partials into the next step size
+// (BCQPSolver.cpp:195-233) -- one launch replaces ~9 vector passes and 3 allreduces.
+__global__ void __launch_bounds__(kVecBlock) k_bb_tail(BbTail p) {
+    if (p.scal->done) return;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double s0 = 0, s1 = 0, s2 = 0, mx = 0;
+    int err = 0;
+    if (k < p.nc) {
+        const double x = p.x[k];
+        double y = dtransRow(p.g, (size_t)k, p.U);
+        y += 1.0 * p.invKdt[k] * x;
+        const double gk = 1.0 * p.b[k] + 1.0 * y;
+        p.gout[k] = gk;
+        const double q = projGrad(x, gk, p.lbFlag[k], err);
+        mx = fabs(q);
+        if (p.ite > 0) {
+            const double dx = 1.0 * x + (-1.0) * p.xprev[k];
+            const double dg = 1.0 * gk + (-1.0) * p.gprev[k];
+            s0 = dx * dx;
+            s1 = dx * dg;
+            s2 = dg * dg;
+        }
+        if (err) mx = INFINITY;
+    }
+    __shared__ double out[4];
+    __shared__ bool last;
+    blockReduce4(s0, s1, s2, mx, out);
+    if (threadIdx.x == 0) {
+        double *dst = p.partial + 4 * (size_t)blockIdx.x;
+        dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
+        __threadfence();
+        const unsigned t = atomicAdd(&p.scal->ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // fixed-order reduction of the per-CTA partials
+    s0 = s1 = s2 = mx = 0;
+    const volatile double *pp = p.partial;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += kVecBlock) {
+        s0 += pp[4 * i]; s1 += pp[4 * i + 1]; s2 += pp[4 * i + 2]; mx = fmax(mx, pp[4 * i + 3]);
+    }
+    blockReduce4(s0, s1, s2, mx, out);
+    if (threadIdx.x == 0) {
+        SolverScalars *sc = p.scal;
+        sc->ticket = 0;
+        sc->mv += 1;
+        sc->ite = p.ite;
+        const double res = out[3];
+        const double alphaUsed = p.ite == 0 ? 0.0 : sc->alpha;
+        if (sc->nhist < p.histCap) {
+            double *h = p.hist + 6 * (size_t)sc->nhist;
+            h[0] = 1.0 * p.ite; h[1] = 0; h[2] = 0; h[3] = alphaUsed; h[4] = res; h[5] = 1.0 * sc->mv;
+        }
+        sc->nhist += 1;
+        sc->res = res;
+        if (isinf(res) || isnan(res)) {
+            sc->done = 3; // projection error
+        } else if (fabs(res) < p.tol) {
+            sc->done = 1;
+        } else if (p.ite == 0) {
+            sc->alpha = 1.0 / res; // Dai & Fletcher 2005 section 5 (BCQPSolver.cpp:183)
+        } else {
+            double a, b;
+            if (p.ite % 2 == 0) { a = out[0]; b = out[1]; } // BB1
+            else { a = out[1]; b = out[2]; }                // BB2
+            if (fabs(b) < 10 * DBL_EPSILON) b += 10 * DBL_EPSILON;
+            const double alpha = a / b;
+            sc->dotA = a; sc->dotB = b;
+            sc->alpha = alpha;
+            if (alpha < DBL_EPSILON * 10) sc->done = 2; // stagnation (BCQPSolver.cpp:229-233)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic vector kernels for APGD (BCQPSolver.cpp:249-389)
+__global__ void k_update2(long long n, double *y, double a, const double *A, double b, const double *B, double g) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    y[i] = (g == 0.0 ? 0.0 : g * y[i]) + a * A[i] + b * B[i];
+}
+__global__ void k_fill(long long n, double *y, double v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = v;
+}
+__global__ void k_project(long long n, double *x, const double *lbFlag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double lb = (-DBL_MAX * .1) * lbFlag[i];
+    double v = x[i];
+    v = v > lb ? v : lb;
+    v = v < kHuge ? v : kHuge;
+    x[i] = v;
+}
+// up to three dot products + one projected-gradient max in one pass: out = {a.b, c.d, e.f, max|q(x,g)|}
+struct Dot3 {
+    const double *a, *b, *c, *d, *e, *f, *x, *g, *lbFlag;
+    double addB; // q uses g + addB*bvec ... unused
+};
+__global__ void __launch_bounds__(kVecBlock)
+k_dot3(long long n, Dot3 p, double *partial, unsigned int *ticket, double *result) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double s0 = 0, s1 = 0, s2 = 0, mx = 0;
+    int err = 0;
+    if (i < n) {
+        if (p.a) s0 = p.a[i] * p.b[i];
+        if (p.c) s1 = p.c[i] * p.d[i];
+        if (p.e) s2 = p.e[i] * p.f[i];
+        if (p.x) {
+            mx = fabs(projGrad(p.x[i], p.g[i], p.lbFlag[i], err));
+            if (err) mx = INFINITY;
+        }
+    }
+    __shared__ double out[4];
+    __shared__ bool last;
+    blockReduce4(s0, s1, s2, mx, out);
+    if (threadIdx.x == 0) {
+        double *dst = partial + 4 * (size_t)blockIdx.x;
+        dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    s0 = s1 = s2 = mx = 0;
+    const volatile double *pp = partial;
+    for (unsigned j = threadIdx.x; j < gridDim.x; j += kVecBlock) {
+        s0 += pp[4 * j]; s1 += pp[4 * j + 1]; s2 += pp[4 * j + 2]; mx = fmax(mx, pp[4 * j + 3]);
+    }
+    blockReduce4(s0, s1, s2, mx, out);
+    if (threadIdx.x == 0) {
+        result[0] = out[0]; result[1] = out[1]; result[2] = out[2]; result[3] = out[3];
+        *ticket = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// results: uni/bi split (ConstraintSolver.cpp:95-106) + permutation back to the caller's rod order
+__global__ void k_split_out(int n, const int *__restrict__ sUser, const double *__restrict__ F,
+                            const double *__restrict__ U, const double *__restrict__ Fb,
+                            const double *__restrict__ Ub, double *__restrict__ oFU, double *__restrict__ oVU,
+                            double *__restrict__ oFB, double *__restrict__ oVB) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const size_t u = 6 * (size_t)sUser[s], r = 6 * (size_t)s;
+    for (int c = 0; c < 6; c++) {
+        const double fb = Fb ? Fb[r + c] : 0.0, ub = Ub ? Ub[r + c] : 0.0;
+        oFU[u + c] = 1.0 * F[r + c] + (-1.0) * fb;
+        oVU[u + c] = 1.0 * U[r + c] + (-1.0) * ub;
+        oFB[u + c] = fb;
+        oVB[u + c] = ub;
+    }
+}
+__global__ void k_permute6_to_user(int n, const int *__restrict__ sUser, const double *__restrict__ in,
+                                   double *__restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const size_t u = 6 * (size_t)sUser[s], r = 6 * (size_t)s;
+    for (int c = 0; c < 6; c++) out[u + c] = in[r + c];
+}
+
+// sumForceVelocity + stepEuler (SylinderSystem.cpp:802-827; Sylinder.cpp:91-99; EquatnHelper.hpp:74-90)
+__global__ void k_step_euler(int n, double dt, const double *__restrict__ velNC, const double *__restrict__ vU,
+                             const double *__restrict__ vB, double *__restrict__ pos, double *__restrict__ quat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v[6];
+    for (int c = 0; c < 6; c++) {
+        const double nb = velNC ? velNC[6 * (size_t)i + c] : 0.0;
+        v[c] = ((nb + 0.0) + vU[6 * (size_t)i + c]) + vB[6 * (size_t)i + c]; // velNonB + velBrown(=0) + velCol + velBi
+    }
+    for (int c = 0; c < 3; c++) pos[3 * (size_t)i + c] += v[c] * dt;
+    const double ox = v[3], oy = v[4], oz = v[5];
+    const double w = sqrt(ox * ox + oy * oy + oz * oz);
+    if (w < (double)FLT_EPSILON) return;
+    double *q = quat + 4 * (size_t)i; // (x,y,z,w)
+    const double winv = 1 / w, sw = sin(w * dt / 2), cw = cos(w * dt / 2);
+    const double s = q[3], px = q[0], py = q[1], pz = q[2];
+    const double cx = oy * pz - oz * py, cy = oz * px - ox * pz, cz = ox * py - oy * px; // omega x p
+    double nx = s * sw * ox * winv + cw * px + sw * winv * cx;
+    double ny = s * sw * oy * winv + cw * py + sw * winv * cy;
+    double nz = s * sw * oz * winv + cw * pz + sw * winv * cz;
+    double nw = s * cw - (px * ox + py * oy + pz * oz) * sw * winv;
+    const double nn = sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+    q[0] = nx / nn; q[1] = ny / nn; q[2] = nz / nn; q[3] = nw / nn;
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+static MobIn mobIn(Context &c) { return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.nRods}; }
+static ConGeom conGeom(Context &c) { return ConGeom{c.cIdxI.p, c.cIdxJ.p, c.cN.p, c.cPI.p, c.cPJ.p, c.conCap}; }
+static FvIn fvIn(Context &c) { return FvIn{c.incStart.p, c.incCon.p, c.incCol.p, (size_t)c.nInc, c.nRods}; }
+
+void calcMobility(Context &c, double mu) {
+    if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_calc_mobility: call alens_set_rods first"};
+    c.viscosity = mu;
+    const int n = c.nRods;
+    c.sInvDrag.reserve(3 * (size_t)n + 3);
+    if (n > 0) {
+        k_mob_coeff<<<gridFor(n, 256), 256, 0, c.stream>>>(n, c.sLen.p, c.sRad.p, c.sImm.p, mu, c.sInvDrag.p);
+        c.launches++;
+    }
+    ALENS_CUDA(cudaGetLastError());
+    c.haveMob = true;
+}
+
+void mobilityApply(Context &c, const double *x, double *y) {
+    if (!c.haveMob) throw ArgError{ALENS_ERR_STATE, "alens_mobility_apply: call alens_calc_mobility first"};
+    const int n = c.nRods;
+    if (n == 0) return;
+    c.vTmp0.reserve(6 * (size_t)n);
+    c.vTmp1.reserve(6 * (size_t)n);
+    ALENS_CUDA(cudaMemcpyAsync(c.vTmp0.p, x, 48 * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+    k_mob_apply_user<<<gridFor(n, 256), 256, 0, c.stream>>>(mobIn(c), c.userToSorted.p, c.vTmp0.p, c.vTmp1.p);
+    c.launches++;
+    ALENS_CUDA(cudaMemcpyAsync(y, c.vTmp1.p, 48 * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+    ALENS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+void setupConstraints(Context &c, const double *velNC, double dt) {
+    if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "setup: call alens_set_rods first"};
+    if (!c.haveMob) throw ArgError{ALENS_ERR_STATE, "setup: call alens_calc_mobility first"};
+    if (!(dt > 0)) throw ArgError{ALENS_ERR_ARG, "setup: dt must be > 0"};
+    cudaStream_t st = c.stream;
+    const int n = c.nRods;
+    const long long nc = c.nCon;
+    c.dt = dt;
+    // velNonCon (user order)
+    c.haveVelNC = velNC != nullptr;
+    if (velNC && n > 0) {
+        c.uVelNC.reserve(6 * (size_t)n);
+        ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, velNC, 48 * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    // incidence
+    c.incDeg.reserve(n + 1);
+    c.incStart.reserve(n + 2);
+    c.incFill.reserve(n + 1);
+    ALENS_CUDA(cudaMemsetAsync(c.incDeg.p, 0, sizeof(int) * (n + 1), st));
+    ALENS_CUDA(cudaMemsetAsync(c.incFill.p, 0, sizeof(int) * (n + 1), st));
+    if (nc > 0) {
+        k_inc_count<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.incDeg.p);
+        c.launches++;
+    }
+    launchScanInt(c.incDeg.p, c.incStart.p, n, st);
+    c.launches++;
+    int nInc = 0;
+    ALENS_CUDA(cudaMemcpyAsync(&nInc, c.incStart.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    c.nInc = nInc;
+    c.incCon.reserve((size_t)nInc + 1);
+    c.incCol.reserve(6 * (size_t)nInc + 6);
+    const size_t vcap = (size_t)nc + 1;
+    c.vX0.reserve(vcap); c.vX1.reserve(vcap); c.vG0.reserve(vcap); c.vG1.reserve(vcap);
+    c.vB.reserve(vcap); c.vLbFlag.reserve(vcap); c.vTmp5.reserve(vcap); // vTmp5 = invKdt
+    c.rU.reserve(6 * (size_t)n + 6); c.rF.reserve(6 * (size_t)n + 6);
+    c.rUb.reserve(6 * (size_t)n + 6); c.rFb.reserve(6 * (size_t)n + 6);
+    c.outFU.reserve(6 * (size_t)n + 6); c.outVU.reserve(6 * (size_t)n + 6);
+    c.outFB.reserve(6 * (size_t)n + 6); c.outVB.reserve(6 * (size_t)n + 6);
+    c.redPartial.reserve(4 * (size_t)(gridFor(std::max<long long>(nc, 1), kVecBlock) + 1));
+    if (nc > 0) {
+        k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.incStart.p, c.incFill.p,
+                                                     c.incCon.p);
+        k_inc_finish<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incCon.p, conGeom(c), c.incCol.p,
+                                                      (size_t)nInc);
+        k_setup<<<gridFor(nc, 256), 256, 0, st>>>(nc, conGeom(c), c.sUser.p, velNC ? c.uVelNC.p : nullptr,
+                                                  c.cDelta0.p, c.cGamma0.p, c.cInvKappa.p, c.cBi.p, 1.0 / dt,
+                                                  c.vB.p, c.vTmp5.p, c.vLbFlag.p, c.vX0.p);
+        c.launches += 3;
+    }
+    ALENS_CUDA(cudaGetLastError());
+    c.haveSetup = true;
+    c.haveSolution = false;
+    c.xLastApplied = nullptr;
+    c.xSolution = nullptr;
+}
+
+template <bool MASK, bool WF>
+static void launchForceVel(Context &c, const double *x, double *U, double *F, const SolverScalars *scal) {
+    const int n = c.nRods;
+    if (n == 0) return;
+    k_force_vel<MASK, WF><<<gridFor(n, kFvBlock), kFvBlock, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F,
+                                                                          scal);
+    c.launches++;
+    c.timers.op_launches++;
+}
+
+void operatorApply(Context &c, const double *x, double *y, double *force, double *vel) {
+    if (!c.haveSetup) throw ArgError{ALENS_ERR_STATE, "alens_operator_apply: call alens_setup_constraints first"};
+    cudaStream_t st = c.stream;
+    const long long nc = c.nCon;
+    const int n = c.nRods;
+    c.vTmp0.reserve((size_t)nc + 1);
+    c.vTmp1.reserve((size_t)nc + 1);
+    if (nc > 0) ALENS_CUDA(cudaMemcpyAsync(c.vTmp0.p, x, 8 * (size_t)nc, cudaMemcpyHostToDevice, st));
+    launchForceVel<false, true>(c, c.vTmp0.p, c.rU.p, c.rF.p, nullptr);
+    if (nc > 0) {
+        k_dtrans<<<gridFor(nc, kVecBlock), kVecBlock, 0, st>>>(nc, conGeom(c), c.rU.p, c.vTmp0.p, c.vTmp5.p,
+                                                               c.vTmp1.p);
+        c.launches++;
+        ALENS_CUDA(cudaMemcpyAsync(y, c.vTmp1.p, 8 * (size_t)nc, cudaMemcpyDeviceToHost, st));
+    }
+    if (n > 0 && (force || vel)) {
+        if (force) {
+            k_permute6_to_user<<<gridFor(n, 256), 256, 0, st>>>(n, c.sUser.p, c.rF.p, c.outFU.p);
+            ALENS_CUDA(cudaMemcpyAsync(force, c.outFU.p, 48 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        }
+        if (vel) {
+            k_permute6_to_user<<<gridFor(n, 256), 256, 0, st>>>(n, c.sUser.p, c.rU.p, c.outVU.p);
+            ALENS_CUDA(cudaMemcpyAsync(vel, c.outVU.p, 48 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    ALENS_CUDA(cudaGetLastError());
+    ALENS_CUDA(cudaStreamSynchronize(st));
+}
+
+static void syncScalars(Context &c) {
+    ALENS_CUDA(cudaMemcpyAsync(c.hScal, c.dScal.p, sizeof(SolverScalars), cudaMemcpyDeviceToHost, c.stream));
+    ALENS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// BCQPSolver::solveBBPGD (BCQPSolver.cpp:134-247).  Iterations are enqueued in batches without host
+// synchronisation; every kernel is a no-op once the device-side `done` flag is set, so the iterate and
+// the history are exactly those of the sequential loop.
+static int solveBBPGD(Context &c, double tol, int maxIte) {
+    cudaStream_t st = c.stream;
+    const long long nc = c.nCon;
+    double *X[2] = {c.vX0.p, c.vX1.p}, *G[2] = {c.vG0.p, c.vG1.p};
+    const int grid = gridFor(nc, kVecBlock);
+    BbTail t{};
+    t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.lbFlag = c.vLbFlag.p;
+    t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = c.histCap; t.tol = tol;
+    // iteration 0: g0 = A x0 + b
+    launchForceVel<false, false>(c, X[0], c.rU.p, nullptr, c.dScal.p);
+    t.ite = 0; t.x = X[0]; t.xprev = X[0]; t.gprev = G[0]; t.gout = G[0];
+    k_bb_tail<<<grid, kVecBlock, 0, st>>>(t);
+    c.launches++; c.timers.op_launches++;
+    int ite = 0;
+    const int batch = nc > 200000 ? 8 : 32;
+    syncScalars(c);
+    while (!c.hScal->done && ite < maxIte) {
+        const int nb = std::min(batch, maxIte - ite);
+        for (int b = 0; b < nb; b++) {
+            ite++;
+            const int cur = (ite - 1) & 1, nxt = ite & 1;
+            k_bb_update<<<grid, kVecBlock, 0, st>>>(nc, X[cur], G[cur], c.vLbFlag.p, X[nxt], c.dScal.p);
+            launchForceVel<false, false>(c, X[nxt], c.rU.p, nullptr, c.dScal.p);
+            t.ite = ite; t.x = X[nxt]; t.xprev = X[cur]; t.gprev = G[cur]; t.gout = G[nxt];
+            k_bb_tail<<<grid, kVecBlock, 0, st>>>(t);
+            c.launches += 2; c.timers.op_launches += 2;
+        }
+        syncScalars(c);
+    }
+    ALENS_CUDA(cudaGetLastError());
+    const int n = c.hScal->ite; // iterations actually executed
+    c.xLastApplied = X[n & 1];
+    if (c.hScal->done || n == 0) c.xSolution = X[n & 1];
+    else c.xSolution = X[(n - 1) & 1]; // iteMax exit returns the older iterate (BCQPSolver.cpp:237-241)
+    return c.hScal->done == 2 ? 1 : 0;
+}
+
+// host-driven helpers for APGD
+static void dot3(Context &c, long long n, const Dot3 &p, double out[4]) {
+    const int grid = gridFor(std::max<long long>(n, 1), kVecBlock);
+    double *res = reinterpret_cast<double *>(c.dCounters.p); // 4 doubles of scratch
+    k_dot3<<<grid, kVecBlock, 0, c.stream>>>(n, p, c.redPartial.p, &c.dScal.p->ticket, res);
+    c.launches++;
+    ALENS_CUDA(cudaMemcpyAsync(out, res, 32, cudaMemcpyDeviceToHost, c.stream));
+    ALENS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+static void applyA(Context &c, const double *x, double *y) { // y = A x, caches U
+    launchForceVel<false, false>(c, x, c.rU.p, nullptr, nullptr);
+    k_dtrans<<<gridFor(c.nCon, kVecBlock), kVecBlock, 0, c.stream>>>(c.nCon, conGeom(c), c.rU.p, x, c.vTmp5.p, y);
+    c.launches++; c.timers.op_launches++;
+    c.xLastApplied = const_cast<double *>(x);
+}
+
+// BCQPSolver::solveAPGD (BCQPSolver.cpp:249-389); scalar control flow stays on the host.
+static int solveAPGD(Context &c, double tol, int maxIte) {
+    cudaStream_t st = c.stream;
+    const long long n = c.nCon;
+    const size_t vcap = (size_t)n + 1;
+    c.vTmp0.reserve(vcap); c.vTmp1.reserve(vcap); c.vTmp2.reserve(vcap); c.vTmp3.reserve(vcap); c.vTmp4.reserve(vcap);
+    DevBuf<double> bXk1, bYk1, bXhat, bAxb1, bXdiff; // extra work vectors (APGD is not the default path)
+    bXk1.reserve(vcap); bYk1.reserve(vcap); bXhat.reserve(vcap); bAxb1.reserve(vcap); bXdiff.reserve(vcap);
+    const int grid = gridFor(n, kVecBlock);
+    double *xk = c.vX0.p, *yk = c.vX1.p, *xkp1 = bXk1.p, *ykp1 = bYk1.p, *gVec = c.vG0.p, *tempVec = c.vG1.p;
+    double *xhatk = bXhat.p, *xkdiff = bXdiff.p, *Axb = c.vTmp0.p, *Axbkp1 = bAxb1.p;
+    const double *b = c.vB.p, *lbf = c.vLbFlag.p;
+    auto upd2 = [&](double *y, double a, const double *A, double bb, const double *B) {
+        k_update2<<<grid, kVecBlock, 0, st>>>(n, y, a, A, bb, B, 0.0);
+        c.launches++;
+    };
+    std::vector<double> &H = c.hist;
+    H.clear();
+    int mv = 0;
+    ALENS_CUDA(cudaMemcpyAsync(yk, xk, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    k_fill<<<grid, kVecBlock, 0, st>>>(n, xhatk, 1.0);
+    upd2(xkdiff, -1.0, xhatk, 1.0, xk);
+    applyA(c, xkdiff, tempVec);
+    mv++;
+    double r[4];
+    dot3(c, n, Dot3{tempVec, tempVec, xkdiff, xkdiff, nullptr, nullptr, nullptr, nullptr, nullptr, 0}, r);
+    double Lk = sqrt(r[0]) / sqrt(r[1]);
+    double tk = 1.0 / Lk;
+    H.insert(H.end(), {0, 0, 0, tk, 0, 1.0 * mv});
+    int ite = 0, stag = 0, perr = 0;
+    double thetak = 1, thetakp1 = 1, resmin = DBL_MAX, resPhi = 0;
+    while (ite < maxIte) {
+        ite++;
+        applyA(c, yk, Axb);
+        mv++;
+        upd2(gVec, 1.0, b, 1.0, Axb);
+        upd2(xkp1, 1.0, yk, -tk, gVec);
+        k_project<<<grid, kVecBlock, 0, st>>>(n, xkp1, lbf);
+        dot3(c, n, Dot3{yk, Axb, yk, b, nullptr, nullptr, nullptr, nullptr, nullptr, 0}, r);
+        const double right1 = r[0] * 0.5, right2 = r[1];
+        while (true) {
+            upd2(xkdiff, 1.0, xkp1, -1.0, yk);
+            applyA(c, xkp1, Axbkp1);
+            mv++;
+            dot3(c, n, Dot3{xkp1, Axbkp1, xkp1, b, gVec, xkdiff, nullptr, nullptr, nullptr, 0}, r);
+            const double left1 = r[0] * 0.5, left2 = r[1], right3 = r[2];
+            double r2[4];
+            dot3(c, n, Dot3{xkdiff, xkdiff, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0}, r2);
+            const double right4 = 0.5 * Lk * r2[0];
+            if ((left1 + left2) <= (right1 + right2 + right3 + right4)) break;
+            Lk *= 2;
+            tk = 1 / Lk;
+            upd2(xkp1, 1.0, yk, -tk, gVec);
+            k_project<<<grid, kVecBlock, 0, st>>>(n, xkp1, lbf);
+        }
+        if (tk < DBL_EPSILON * 10) { stag = 1; break; }
+        thetakp1 = (-thetak * thetak + thetak * sqrt(4 + thetak * thetak)) / 2;
+        const double betakp1 = thetak * (1 - thetak) / (thetak * thetak + thetakp1);
+        upd2(ykp1, (1 + betakp1), xkp1, -betakp1, xk);
+        k_update2<<<grid, kVecBlock, 0, st>>>(n, Axbkp1, 1.0, b, 0.0, b, 1.0); // Axbkp1 += b
+        dot3(c, n, Dot3{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, xkp1, Axbkp1, lbf, 0}, r);
+        resPhi = fabs(r[3]);
+        if (std::isinf(resPhi) || std::isnan(resPhi)) { perr = 1; break; }
+        if (resPhi < resmin) {
+            resmin = resPhi;
+            ALENS_CUDA(cudaMemcpyAsync(xhatk, xkp1, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        }
+        H.insert(H.end(), {1.0 * ite, 0, 0, tk, resPhi, 1.0 * mv});
+        if (resPhi < tol) break;
+        upd2(tempVec, 1.0, xkp1, -1.0, xk);
+        dot3(c, n, Dot3{gVec, tempVec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0}, r);
+        if (r[0] > 0) {
+            ALENS_CUDA(cudaMemcpyAsync(ykp1, xkp1, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            thetakp1 = 1;
+        }
+        Lk *= 0.9;
+        tk = 1 / Lk;
+        std::swap(yk, ykp1);
+        std::swap(xk, xkp1);
+        thetak = thetakp1;
+    }
+    // the solution is copied into vX0 so that the work vectors can be released
+    ALENS_CUDA(cudaMemcpyAsync(c.vTmp1.p, xhatk, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    // the operator's cached force/vel belong to the last apply: keep that vector too
+    ALENS_CUDA(cudaMemcpyAsync(c.vTmp2.p, c.xLastApplied, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    c.xSolution = c.vTmp1.p;
+    c.xLastApplied = c.vTmp2.p;
+    c.hScal->ite = ite;
+    c.hScal->mv = mv;
+    c.hScal->res = resPhi;
+    c.hScal->alpha = tk;
+    c.hScal->done = perr ? 3 : (stag ? 2 : 1);
+    c.hScal->nhist = (int)(H.size() / 6);
+    ALENS_CUDA(cudaGetLastError());
+    return stag;
+}
+
+void solveConstraints(Context &c, double res, int maxIte, int choice) {
+    if (!c.haveSetup) throw ArgError{ALENS_ERR_STATE, "solve: setup has not been run"};
+    cudaStream_t st = c.stream;
+    const long long nc = c.nCon;
+    const int n = c.nRods;
+    const double tol = res * (1.0 / c.dt); // ConstraintSolver.cpp:76
+    alens_solve_report &rep = c.lastReport;
+    memset(&rep, 0, sizeof(rep));
+    rep.n_constraints = nc;
+    rep.n_rods = n;
+    c.timers.op_launches = 0;
+    c.hist.clear();
+    // history capacity
+    const int wantHist = (int)std::min<long long>((long long)maxIte + 2, 1 << 20);
+    if (wantHist > c.histCap) {
+        c.dHist.reserve(6 * (size_t)wantHist);
+        c.histCap = wantHist;
+    }
+    ALENS_CUDA(cudaMemsetAsync(c.dScal.p, 0, sizeof(SolverScalars), st));
+    ALENS_CUDA(cudaEventRecord(c.ev[2], st));
+    int status = 0;
+    if (nc == 0) {
+        // empty problem: residual 0 < tol, zero forces (the reference returns after the first check)
+        if (n > 0) {
+            ALENS_CUDA(cudaMemsetAsync(c.rU.p, 0, 48 * (size_t)n, st));
+            ALENS_CUDA(cudaMemsetAsync(c.rF.p, 0, 48 * (size_t)n, st));
+        }
+        c.hist = {0, 0, 0, 0, 0, 1};
+        memset(c.hScal, 0, sizeof(SolverScalars));
+        c.hScal->mv = 1; c.hScal->nhist = 1; c.hScal->done = 1;
+    } else if (choice == ALENS_SOLVER_APGD) {
+        status = solveAPGD(c, tol, maxIte);
+    } else {
+        status = solveBBPGD(c, tol, maxIte);
+        const int rows = std::min(c.hScal->nhist, c.histCap);
+        c.hist.resize(6 * (size_t)rows);
+        if (rows) ALENS_CUDA(cudaMemcpyAsync(c.hist.data(), c.dHist.p, 48 * (size_t)rows, cudaMemcpyDeviceToHost, st));
+    }
+    ALENS_CUDA(cudaEventRecord(c.ev[3], st));
+    // split (ConstraintSolver.cpp:95-106): force/vel of the LAST apply minus the bilateral part
+    if (nc > 0) {
+        launchForceVel<false, true>(c, c.xLastApplied, c.rU.p, c.rF.p, nullptr);
+        launchForceVel<true, true>(c, c.xSolution, c.rUb.p, c.rFb.p, nullptr);
+    }
+    if (n > 0) {
+        k_split_out<<<gridFor(n, 256), 256, 0, st>>>(n, c.sUser.p, c.rF.p, c.rU.p, nc > 0 ? c.rFb.p : nullptr,
+                                                     nc > 0 ? c.rUb.p : nullptr, c.outFU.p, c.outVU.p, c.outFB.p,
+                                                     c.outVB.p);
+        c.launches++;
+    }
+    ALENS_CUDA(cudaEventRecord(c.ev[4], st));
+    ALENS_CUDA(cudaGetLastError());
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]);
+    c.timers.solve_ms = ms;
+    cudaEventElapsedTime(&ms, c.ev[3], c.ev[4]);
+    c.timers.split_ms = ms;
+    rep.status = status;
+    rep.iterations = c.hScal->ite;
+    rep.matvecs = c.hScal->mv;
+    rep.history_rows = (int)(c.hist.size() / 6);
+    rep.residual = c.hScal->res;
+    rep.step = c.hScal->alpha;
+    c.haveSolution = true;
+    if (c.hScal->done == 3) throw ArgError{ALENS_ERR_PROJECTION, "projection error occured (BCQPSolver.cpp:484-494)"};
+}
+
+void stepEuler(Context &c, double dt) {
+    if (!c.haveSolution) throw ArgError{ALENS_ERR_STATE, "alens_step_euler: no solution available"};
+    const int n = c.nRods;
+    if (n == 0) return;
+    k_step_euler<<<gridFor(n, 256), 256, 0, c.stream>>>(n, dt, c.haveVelNC ? c.uVelNC.p : nullptr, c.outVU.p,
+                                                        c.outVB.p, c.uPos.p, c.uQuat.p);
+    c.launches++;
+    ALENS_CUDA(cudaGetLastError());
+    ALENS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+} // namespace alens

@@ -1,0 +1,176 @@
+/*
+ * alens_b200.h -- C ABI of libalens_b200.so: the B200-native (sm_100a) implementation of the
+ * aLENS / SimToolbox per-timestep collision-constraint path.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain pointers and sizes
+ * (no torch / Tpetra / Eigen types) and replaces one piece of the reference's CPU path; the
+ * reference-side citation (relative to the aLENS tree) is given at each declaration.  The C++ classes
+ * in include/alens_b200/*.hpp (SylinderSystem / ConstraintSolver / ConstraintCollector / BCQPSolver
+ * with the reference's method names) are thin forwarding wrappers over these functions.
+ *
+ * Conventions
+ *   - every function returns ALENS_OK (0) or a negative error code; alens_last_error() gives the text.
+ *   - host pointers are caller-owned; the library owns all device memory.
+ *   - calls are synchronous at the boundary (they return after the work on the context's stream
+ *     finished) unless the name ends in _async.
+ *   - rods are identified by their LOCAL index (position in the arrays given to alens_set_rods);
+ *     ConstraintBlock::globalIndexI/J = rank offset + local index as in
+ *     SimToolbox/Sylinder/SylinderSystem.cpp:868-880 (updateSylinderMap).
+ *   - there is NO CPU fallback: without a CUDA device alens_create fails.
+ */
+#ifndef ALENS_B200_H_
+#define ALENS_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALENS_OK 0
+#define ALENS_ERR_CUDA (-1)      /* a CUDA runtime call failed                      */
+#define ALENS_ERR_ARG (-2)       /* bad argument / call order                       */
+#define ALENS_ERR_STATE (-3)     /* required earlier stage has not been run         */
+#define ALENS_ERR_UNSUPPORTED (-4)
+#define ALENS_ERR_PROJECTION (-5) /* BCQPSolver.cpp:484-494 "projection error"      */
+#define ALENS_ERR_COMM (-6)
+
+#define ALENS_SOLVER_BBPGD 0 /* SylinderConfig conSolverChoice, ConstraintSolver.cpp:74-84 */
+#define ALENS_SOLVER_APGD 1
+
+typedef struct alens_ctx alens_ctx;
+
+/* Binary-compatible with SimToolbox/Constraint/ConstraintBlock.hpp:30-48 (272 bytes, x86-64). */
+typedef struct alens_constraint_block {
+    double delta0, gamma, gammaLB;
+    int gidI, gidJ, globalIndexI, globalIndexJ;
+    unsigned char oneSide, bilateral, pad_[6];
+    double kappa;
+    double normI[3], normJ[3], posI[3], posJ[3], labI[3], labJ[3];
+    double stress[9];
+} alens_constraint_block;
+
+/* Outcome of one constraint solve; history rows follow BCQPSolver.hpp:23 (IteHistory). */
+typedef struct alens_solve_report {
+    int status;       /* 0 ok, 1 stagnated (BCQPSolver.cpp:229-233 / :332-336)           */
+    int iterations;   /* iteCount                                                          */
+    int matvecs;      /* mvCount                                                           */
+    int history_rows; /* rows available through alens_get_history                          */
+    double residual;  /* last resPhi (velocity units, i.e. before the *dt of the log line) */
+    double step;      /* last alpha (BBPGD) or tk (APGD)                                   */
+    long long n_constraints;
+    int n_rods;
+} alens_solve_report;
+
+/* per-phase device time of the last step, milliseconds (CUDA events on the context's stream);
+ * names follow the reference's Teuchos timers (SylinderSystem.cpp:831-851, ConstraintOperator.cpp:8-11) */
+typedef struct alens_timers {
+    double upload_ms;         /* alens_set_rods H2D + rod_pack                                  */
+    double collect_ms;        /* SylinderSystem::CollectCollision                               */
+    double setup_ms;          /* ConstraintSolver::setup equivalent (incidence, q, bounds)      */
+    double solve_ms;          /* SylinderSystem::SolveConstraints (BCQP loop only)              */
+    double split_ms;          /* uni/bi split + result permutation                              */
+    double download_ms;       /* D2H of results                                                 */
+    double op_force_vel_ms;   /* ConstraintOperator::ApplyDMat + ApplyMobility (accumulated)    */
+    double op_dtrans_ms;      /* ConstraintOperator::ApplyDMatTrans + fused vector work         */
+    long long op_launches;    /* kernel launches inside the last BCQP loop                      */
+    long long total_launches; /* kernel launches since alens_reset_timers                       */
+} alens_timers;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* device: CUDA ordinal.  rank/nranks: position in the slab decomposition (1 process per GPU).
+ * Replaces SylinderSystem::initialize's solver/collector construction (SylinderSystem.cpp:53-55). */
+int alens_create(int device, int rank, int nranks, alens_ctx **out);
+void alens_destroy(alens_ctx *ctx);
+const char *alens_last_error(const alens_ctx *ctx);
+const char *alens_version(void);
+/* use an externally created cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream */
+int alens_set_stream(alens_ctx *ctx, void *cuda_stream);
+
+/* ---- configuration -------------------------------------------------------------------------- */
+/* simBoxLow/High/PBC: SylinderSystem::setDomainInfo (SylinderSystem.cpp:569-610) */
+int alens_set_domain(alens_ctx *ctx, const double boxLow[3], const double boxHigh[3], const int pbc[3]);
+/* sylinderDiameterColRatio / sylinderLengthColRatio / sylinderColBuf: SylinderSystem.cpp:897-905 */
+int alens_set_collision_params(alens_ctx *ctx, double diameterColRatio, double lengthColRatio, double colBuf);
+
+/* ---- rods ----------------------------------------------------------------------------------- */
+/* Host SoA of the Sylinder fields the path reads (SimToolbox/Sylinder/Sylinder.hpp:38-84):
+ * gid[n], pos[3n], orientation[4n] (Eigen coeff order x,y,z,w), length[n], radius[n],
+ * immovable[n] (may be NULL = all movable).  wrapIntoBox != 0 applies applyBoxBC
+ * (FDPS/particle_system.hpp:798-843: all three axes).  Also performs prepareStep's per-rod work
+ * (collision radius/length, direction = q*z; SylinderNear.hpp:74-90). */
+int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, const double *orientation,
+                   const double *length, const double *radius, const unsigned char *immovable, int wrapIntoBox);
+/* same from an array of reference `Sylinder` records (568-byte AoS), stride in bytes */
+int alens_set_rods_aos(alens_ctx *ctx, int n, const void *sylinders, size_t stride, int wrapIntoBox);
+/* wrapped positions back (what applyBoxBC left in the container), pos[3n] */
+int alens_get_positions(alens_ctx *ctx, double *pos);
+
+/* ---- constraint collection ------------------------------------------------------------------ */
+/* SylinderSystem::collectPairCollision (SylinderSystem.cpp:1152-1160) = FDPS calcForceAll +
+ * CalcSylinderNearForce (SylinderNear.hpp:197-414).  Clears the pool first (conCollectorPtr->clear(),
+ * SylinderSystem.cpp:925).  The list is the full geometric list (SURVEY.md 8c contract), in a
+ * deterministic order. */
+int alens_collect_pair_collision(alens_ctx *ctx, long long *nConstraints);
+/* host-generated blocks pushed into the pool (boundary / link / protein bilateral constraints:
+ * SylinderSystem.cpp:1093-1150, :1386-1482, SRC/TubuleSystem.cpp:694-745).  Two-sided blocks must
+ * have normJ == -normI (true for every producer in the reference). */
+int alens_append_constraints(alens_ctx *ctx, const alens_constraint_block *blocks, long long n);
+int alens_clear_constraints(alens_ctx *ctx); /* ConstraintCollector::clear */
+/* ConstraintCollector::getLocalNumberOfConstraints (ConstraintCollector.cpp:30-36) */
+int alens_num_constraints(alens_ctx *ctx, long long *n);
+/* refill a host pool: blocks in solver order.  withStress: evaluate collideStress
+ * (SylinderNear.hpp:432-484).  writeBack: gamma = solved value and stress *= gamma
+ * (ConstraintCollector::writeBackGamma, ConstraintCollector.cpp:439-461). */
+int alens_get_constraints(alens_ctx *ctx, alens_constraint_block *out, long long cap, int withStress,
+                          int writeBack);
+
+/* ---- mobility ------------------------------------------------------------------------------- */
+/* SylinderSystem::calcMobOperator / calcMobMatrix (SylinderSystem.cpp:622-722) with
+ * Sylinder::calcDragCoeff (Sylinder.cpp:69-82): stored as 3 inverse drag scalars per rod. */
+int alens_calc_mobility(alens_ctx *ctx, double viscosity);
+/* y = M x on 6n vectors in local rod order (mobilityOperatorRcp->apply, SylinderSystem.cpp:734) */
+int alens_mobility_apply(alens_ctx *ctx, const double *x, double *y);
+
+/* ---- solve ---------------------------------------------------------------------------------- */
+/* ConstraintSolver::setup + setControlParams + solveConstraints (ConstraintSolver.cpp:4-107,
+ * driven from SylinderSystem::resolveConstraints, SylinderSystem.cpp:829-866) with
+ * BCQPSolver::solveBBPGD / solveAPGD (BCQPSolver.cpp:134-389).  velNonCon: 6n host doubles in local
+ * rod order (may be NULL = 0).  res is conResTol (the loop stops at resPhi < res/dt). */
+int alens_solve_constraints(alens_ctx *ctx, const double *velNonCon, double dt, double res, int maxIte,
+                            int solverChoice, alens_solve_report *report);
+/* only the setup part (q, bounds, incidence); lets tests call alens_operator_apply */
+int alens_setup_constraints(alens_ctx *ctx, const double *velNonCon, double dt);
+/* ConstraintOperator::apply (ConstraintOperator.cpp:30-71): y = (D^T M D + K^-1/dt) x, host vectors of
+ * length nConstraints; force/vel (6n, may be NULL) = the cached D x and M D x. */
+int alens_operator_apply(alens_ctx *ctx, const double *x, double *y, double *force, double *vel);
+/* IteHistory rows {ite,0,0,alpha,resPhi,mvCount} (BCQPSolver.hpp:23) */
+int alens_get_history(alens_ctx *ctx, double *rows6, int capRows, int *nRows);
+/* gamma in solver (= alens_get_constraints) order */
+int alens_get_gamma(alens_ctx *ctx, double *gamma, long long cap);
+/* ConstraintSolver::getForceUni/getVelocityUni/getForceBi/getVelocityBi (ConstraintSolver.hpp:83-88),
+ * 6n each in local rod order; any pointer may be NULL.  This is what
+ * SylinderSystem::saveForceVelocityConstraints (SylinderSystem.cpp:971-1018) copies into the rods. */
+int alens_get_force_velocity(alens_ctx *ctx, double *forceUni, double *velUni, double *forceBi, double *velBi);
+
+/* ---- next rows: device-resident time stepping --------------------------------- */
+/* sumForceVelocity + stepEuler (SylinderSystem.cpp:802-827, Sylinder.cpp:91-99, EquatnHelper.hpp:74-90)
+ * on the device copy of the rods: vel = velNonCon + velUni + velBi; pos += vel*dt; q rotated by omega*dt */
+int alens_step_euler(alens_ctx *ctx, double dt);
+int alens_get_rod_state(alens_ctx *ctx, double *pos, double *orientation);
+
+/* ---- instrumentation ---------------------------------------------------------------------------- */
+int alens_get_timers(alens_ctx *ctx, alens_timers *t);
+int alens_reset_timers(alens_ctx *ctx);
+/* number of rods / cells / candidate pairs that passed the broad phase in the last collection */
+int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCandidates, long long *nHits);
+
+/* ---- multi-GPU (one process per GPU) ---------------------------------------------- */
+/* 128-byte ncclUniqueId created on rank 0 and broadcast by the host program, then a collective init */
+int alens_comm_unique_id(void *id128);
+int alens_comm_init(alens_ctx *ctx, const void *id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALENS_B200_H_ */

@@ -1,0 +1,111 @@
+"""GPU pair collection vs the CPU oracle: bit-exact blocks (SURVEY.md 8c contract: P_gpu == P_geo)."""
+import numpy as np
+import pytest
+
+from scenarios import canonical_order, random_rods
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("delta0", "gamma", "gammaLB", "gidI", "gidJ", "globalIndexI", "globalIndexJ", "oneSide", "bilateral",
+          "kappa", "normI", "normJ", "posI", "posJ", "labI", "labJ")
+
+
+def gpu_collect(ctx, rods, lo, hi, pbc, colbuf, dratio=1.0, lratio=1.0):
+    ctx.set_domain(lo, hi, pbc)
+    ctx.set_collision_params(dratio, lratio, colbuf)
+    ctx.set_rods(rods["gid"], rods["pos"], rods["quat"], rods["length"], rods["radius"], rods["immovable"], wrap=True)
+    n = ctx.collect_pair_collision()
+    blocks = ctx.get_constraints(with_stress=True)
+    assert len(blocks) == n
+    return blocks
+
+
+def oracle_collect(oracle, rods, lo, hi, pbc, colbuf, dratio=1.0, lratio=1.0, method="cells"):
+    pos = oracle.wrap_positions(rods["pos"], lo, hi)
+    orods = oracle.make_rods(rods["gid"], rods["radius"], rods["length"], pos, rods["quat"], dratio, lratio, colbuf)
+    return oracle.collect_pairs(orods, lo, hi, pbc, with_stress=True, method=method), orods
+
+
+def assert_blocks_equal(g, o, stress_rtol=0.0):
+    assert len(g) == len(o), (len(g), len(o))
+    g = g[canonical_order(g)]
+    o = o[canonical_order(o)]
+    for f in FIELDS:
+        assert np.array_equal(g[f], o[f]), f"field {f} differs"
+    if stress_rtol == 0.0:
+        assert np.array_equal(g["stress"], o["stress"]), "stress differs"
+    else:
+        np.testing.assert_allclose(g["stress"], o["stress"], rtol=stress_rtol, atol=1e-300)
+
+
+@pytest.mark.parametrize("pbc", [(0, 0, 0), (1, 1, 1), (1, 0, 1)])
+@pytest.mark.parametrize("n,box,L", [(3000, 2.0, 0.25), (1500, 3.0, 1.0)])
+def test_collect_matches_oracle(ctx, oracle, pbc, n, box, L):
+    rods = random_rods(n, box, length=L, radius=0.0125, seed=n + sum(pbc))
+    lo, hi = [0, 0, 0], [box] * 3
+    g = gpu_collect(ctx, rods, lo, hi, pbc, 0.025)
+    o, _ = oracle_collect(oracle, rods, lo, hi, pbc, 0.025)
+    assert len(o) > n // 4
+    assert_blocks_equal(g, o)
+
+
+def test_collect_spheres_and_mixed(ctx, oracle):
+    rods = random_rods(2500, 1.2, length=0.25, radius=0.0125, seed=5, frac_sphere=0.4)
+    lo, hi, pbc = [0, 0, 0], [1.2] * 3, (1, 1, 1)
+    g = gpu_collect(ctx, rods, lo, hi, pbc, 0.02, dratio=1.1, lratio=0.9)
+    o, _ = oracle_collect(oracle, rods, lo, hi, pbc, 0.02, dratio=1.1, lratio=0.9)
+    assert len(o) > 500
+    assert_blocks_equal(g, o)
+
+
+def test_collect_tiny_periodic_box(ctx, oracle):
+    # box barely larger than the interaction range: 2 cells per axis / 1 cell per axis with wrap
+    for box, n in ((0.7, 500), (0.45, 120)):
+        rods = random_rods(n, box, length=0.25, radius=0.0125, seed=11, lo=-box / 2)
+        lo, hi, pbc = [-box / 2] * 3, [box / 2] * 3, (1, 1, 1)
+        g = gpu_collect(ctx, rods, lo, hi, pbc, 0.025)
+        o, _ = oracle_collect(oracle, rods, lo, hi, pbc, 0.025, method="brute")
+        assert_blocks_equal(g, o)
+
+
+def test_collect_rods_outside_box_are_wrapped(ctx, oracle):
+    rods = random_rods(1000, 2.0, seed=3)
+    rods["pos"] = rods["pos"] * 3.0 - 2.0  # many rods outside [0,2]^3
+    lo, hi, pbc = [0, 0, 0], [2.0] * 3, (1, 1, 0)
+    g = gpu_collect(ctx, rods, lo, hi, pbc, 0.025)
+    o, _ = oracle_collect(oracle, rods, lo, hi, pbc, 0.025)
+    np.testing.assert_array_equal(ctx.get_positions(), oracle.wrap_positions(rods["pos"], lo, hi))
+    assert_blocks_equal(g, o)
+
+
+def test_collect_edge_cases(ctx, oracle):
+    lo, hi, pbc = [0, 0, 0], [1.0] * 3, (0, 0, 0)
+    # empty
+    rods = random_rods(0, 1.0)
+    g = gpu_collect(ctx, rods, lo, hi, pbc, 0.025)
+    assert len(g) == 0
+    # single rod
+    rods = random_rods(1, 1.0)
+    assert len(gpu_collect(ctx, rods, lo, hi, pbc, 0.025)) == 0
+    # the reference's fixed pair (SylinderNear_test.cpp:43-111): one block, known stress
+    P0, P1 = np.array([1, 0, 0.0]), np.array([0, np.sqrt(3), 0.0])
+    Q0, Q1 = np.array([0, 0, 1.0]), np.array([2, 2 * np.sqrt(3), 1.0])
+    from scenarios import quat_from_z_to
+
+    rods = dict(gid=np.array([0, 1], dtype=np.int32), pos=np.array([(P0 + P1) / 2, (Q0 + Q1) / 2]),
+                quat=quat_from_z_to(np.array([P1 - P0, Q1 - Q0])),
+                length=np.array([np.linalg.norm(P1 - P0), np.linalg.norm(Q1 - Q0)]), radius=np.array([0.4, 0.5]),
+                immovable=np.zeros(2, dtype=np.uint8))
+    g = gpu_collect(ctx, rods, [-5] * 3, [5] * 3, pbc, 0.5)
+    assert len(g) == 1
+    want = np.array([0, 0, 0.0160681, 0, 0, 0.0278307, 0.0160681, 0.0278307, 1.0])
+    assert np.abs(g[0]["stress"] - want).max() < 1e-6
+    assert abs(g[0]["delta0"] - 0.1) < 1e-12
+
+
+def test_collect_is_deterministic(ctx):
+    rods = random_rods(4000, 2.0, seed=9)
+    lo, hi, pbc = [0, 0, 0], [2.0] * 3, (1, 1, 1)
+    a = gpu_collect(ctx, rods, lo, hi, pbc, 0.025).copy()
+    b = gpu_collect(ctx, rods, lo, hi, pbc, 0.025)
+    assert a.tobytes() == b.tobytes()  # same order, same bits, run to run
