@@ -29,7 +29,8 @@ EXPORTS = [
     "alens_mobility_apply", "alens_solve_constraints", "alens_setup_constraints", "alens_operator_apply",
     "alens_get_history", "alens_get_gamma", "alens_get_force_velocity", "alens_step_euler",
     "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
-    "alens_comm_unique_id", "alens_comm_init",
+    "alens_comm_unique_id", "alens_comm_init", "alens_prepare_step", "alens_set_velocity_noncon",
+    "alens_set_profiling",
 ]
 
 
@@ -42,8 +43,9 @@ class SolveReport(C.Structure):
 class Timers(C.Structure):
     _fields_ = [("upload_ms", C.c_double), ("collect_ms", C.c_double), ("setup_ms", C.c_double),
                 ("solve_ms", C.c_double), ("split_ms", C.c_double), ("download_ms", C.c_double),
-                ("op_force_vel_ms", C.c_double), ("op_dtrans_ms", C.c_double), ("op_launches", C.c_longlong),
-                ("total_launches", C.c_longlong)]
+                ("op_force_vel_ms", C.c_double), ("op_dtrans_ms", C.c_double), ("op_update_ms", C.c_double),
+                ("op_force_vel_n", C.c_longlong), ("op_dtrans_n", C.c_longlong), ("op_update_n", C.c_longlong),
+                ("op_launches", C.c_longlong), ("total_launches", C.c_longlong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -172,6 +174,16 @@ class Context:
         self._call("alens_set_rods_aos", C.c_int(n), C.c_void_p(buf.ctypes.data), C.c_size_t(stride),
                    C.c_int(1 if wrap else 0))
         self.n_rods = n
+
+    def prepare_step(self, wrap=True):
+        self._call("alens_prepare_step", C.c_int(1 if wrap else 0))
+
+    def set_velocity_noncon(self, v):
+        v = None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+        self._call("alens_set_velocity_noncon", _dp(v))
+
+    def set_profiling(self, on):
+        self._call("alens_set_profiling", C.c_int(1 if on else 0))
 
     def get_positions(self):
         out = np.zeros((self.n_rods, 3))

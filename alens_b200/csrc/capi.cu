@@ -128,6 +128,7 @@ int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, con
             throw ArgError{ALENS_ERR_ARG, "alens_set_rods: null input"};
         cudaStream_t st = c.stream;
         ALENS_CUDA(cudaEventRecord(c.ev[0], st));
+        if (n != c.nRods) c.haveVelNC = false;
         c.nRods = n;
         const size_t N = (size_t)n;
         c.uGid.reserve(N + 1); c.uPos.reserve(3 * N + 3); c.uQuat.reserve(4 * N + 4);
@@ -171,6 +172,34 @@ int alens_set_rods_aos(alens_ctx *ctx, int n, const void *sy, size_t stride, int
         memcpy(&q[4 * (size_t)i], p + 104, 32);
     }
     return alens_set_rods(ctx, n, gid.data(), pos.data(), q.data(), len.data(), rad.data(), imm.data(), wrap);
+}
+
+int alens_prepare_step(alens_ctx *ctx, int wrap) {
+    return guarded(ctx, [&](Context &c) {
+        if (!c.haveBox || c.uPos.p == nullptr) throw ArgError{ALENS_ERR_STATE, "alens_prepare_step: no resident rods"};
+        ALENS_CUDA(cudaEventRecord(c.ev[0], c.stream));
+        rodsUploaded(c, wrap != 0);
+        ALENS_CUDA(cudaEventRecord(c.ev[1], c.stream));
+        ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        c.timers.upload_ms = evMs(c, 0, 1);
+    });
+}
+
+int alens_set_velocity_noncon(alens_ctx *ctx, const double *v) {
+    return guarded(ctx, [&](Context &c) {
+        if (!v || c.nRods == 0) {
+            c.haveVelNC = false;
+            return;
+        }
+        c.uVelNC.reserve(6 * (size_t)c.nRods);
+        ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, v, 48 * (size_t)c.nRods, cudaMemcpyHostToDevice, c.stream));
+        ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        c.haveVelNC = true;
+    });
+}
+
+int alens_set_profiling(alens_ctx *ctx, int on) {
+    return guarded(ctx, [&](Context &c) { c.profiling = on != 0; });
 }
 
 int alens_get_positions(alens_ctx *ctx, double *pos) {

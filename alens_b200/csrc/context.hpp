@@ -178,6 +178,10 @@ struct Context {
     alens_timers timers{};
     cudaEvent_t ev[8] = {};
     long long launches = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> profEv; // pool for per-kernel timing
+    std::vector<int> profKind;       // kernel kind per event pair
+    int profUsed = 0;
 
     PinnedBuf pin0, pin1;
 
@@ -198,6 +202,7 @@ void setupConstraints(Context &c, const double *velNC, double dt);
 void operatorApply(Context &c, const double *x, double *y, double *force, double *vel);
 void solveConstraints(Context &c, double res, int maxIte, int choice);
 void stepEuler(Context &c, double dt);
+void profFlush(Context &c);
 void reserveConstraints(Context &c, size_t n, bool keep);
 
 inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }

@@ -583,11 +583,12 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     const long long nc = c.nCon;
     c.dt = dt;
     // velNonCon (user order)
-    c.haveVelNC = velNC != nullptr;
     if (velNC && n > 0) {
         c.uVelNC.reserve(6 * (size_t)n);
         ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, velNC, 48 * (size_t)n, cudaMemcpyHostToDevice, st));
+        c.haveVelNC = true;
     }
+    const bool useV = c.haveVelNC && n > 0;
     // incidence
     c.incDeg.reserve(n + 1);
     c.incStart.reserve(n + 2);
@@ -619,7 +620,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
                                                      c.incCon.p);
         k_inc_finish<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incCon.p, conGeom(c), c.incCol.p,
                                                       (size_t)nInc);
-        k_setup<<<gridFor(nc, 256), 256, 0, st>>>(nc, conGeom(c), c.sUser.p, velNC ? c.uVelNC.p : nullptr,
+        k_setup<<<gridFor(nc, 256), 256, 0, st>>>(nc, conGeom(c), c.sUser.p, useV ? c.uVelNC.p : nullptr,
                                                   c.cDelta0.p, c.cGamma0.p, c.cInvKappa.p, c.cBi.p, 1.0 / dt,
                                                   c.vB.p, c.vTmp5.p, c.vLbFlag.p, c.vX0.p);
         c.launches += 3;
@@ -631,12 +632,44 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.xSolution = nullptr;
 }
 
+// ---- optional per-kernel timing (alens_set_profiling): event pair around a launch, summed in profFlush
+static void profBegin(Context &c, int kind) {
+    if (!c.profiling) return;
+    if ((size_t)c.profUsed + 2 > c.profEv.size()) {
+        const size_t old = c.profEv.size();
+        c.profEv.resize(old + 64);
+        for (size_t i = old; i < c.profEv.size(); i++) ALENS_CUDA(cudaEventCreate(&c.profEv[i]));
+    }
+    c.profKind.resize(c.profEv.size() / 2);
+    c.profKind[c.profUsed / 2] = kind;
+    ALENS_CUDA(cudaEventRecord(c.profEv[c.profUsed], c.stream));
+}
+static void profEnd(Context &c) {
+    if (!c.profiling) return;
+    ALENS_CUDA(cudaEventRecord(c.profEv[c.profUsed + 1], c.stream));
+    c.profUsed += 2;
+}
+void profFlush(Context &c) { // call after a stream synchronisation
+    for (int i = 0; i < c.profUsed; i += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.profEv[i], c.profEv[i + 1]);
+        switch (c.profKind[i / 2]) {
+        case 0: c.timers.op_force_vel_ms += ms; c.timers.op_force_vel_n++; break;
+        case 1: c.timers.op_dtrans_ms += ms; c.timers.op_dtrans_n++; break;
+        default: c.timers.op_update_ms += ms; c.timers.op_update_n++; break;
+        }
+    }
+    c.profUsed = 0;
+}
+
 template <bool MASK, bool WF>
 static void launchForceVel(Context &c, const double *x, double *U, double *F, const SolverScalars *scal) {
     const int n = c.nRods;
     if (n == 0) return;
+    profBegin(c, 0);
     k_force_vel<MASK, WF><<<gridFor(n, kFvBlock), kFvBlock, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F,
                                                                           scal);
+    profEnd(c);
     c.launches++;
     c.timers.op_launches++;
 }
@@ -689,23 +722,32 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     // iteration 0: g0 = A x0 + b
     launchForceVel<false, false>(c, X[0], c.rU.p, nullptr, c.dScal.p);
     t.ite = 0; t.x = X[0]; t.xprev = X[0]; t.gprev = G[0]; t.gout = G[0];
+    profBegin(c, 1);
     k_bb_tail<<<grid, kVecBlock, 0, st>>>(t);
+    profEnd(c);
     c.launches++; c.timers.op_launches++;
     int ite = 0;
     const int batch = nc > 200000 ? 8 : 32;
     syncScalars(c);
+    profFlush(c);
     while (!c.hScal->done && ite < maxIte) {
         const int nb = std::min(batch, maxIte - ite);
         for (int b = 0; b < nb; b++) {
             ite++;
             const int cur = (ite - 1) & 1, nxt = ite & 1;
+            profBegin(c, 2);
             k_bb_update<<<grid, kVecBlock, 0, st>>>(nc, X[cur], G[cur], c.vLbFlag.p, X[nxt], c.dScal.p);
+            profEnd(c);
             launchForceVel<false, false>(c, X[nxt], c.rU.p, nullptr, c.dScal.p);
             t.ite = ite; t.x = X[nxt]; t.xprev = X[cur]; t.gprev = G[cur]; t.gout = G[nxt];
+            profBegin(c, 1);
             k_bb_tail<<<grid, kVecBlock, 0, st>>>(t);
+            profEnd(c);
             c.launches += 2; c.timers.op_launches += 2;
         }
         syncScalars(c);
+        if (c.hScal->done) c.profUsed = 0; // this batch contains early-exit no-ops: not representative
+        else profFlush(c);
     }
     ALENS_CUDA(cudaGetLastError());
     const int n = c.hScal->ite; // iterations actually executed
@@ -841,6 +883,7 @@ void solveConstraints(Context &c, double res, int maxIte, int choice) {
     rep.n_constraints = nc;
     rep.n_rods = n;
     c.timers.op_launches = 0;
+    c.profUsed = 0;
     c.hist.clear();
     // history capacity
     const int wantHist = (int)std::min<long long>((long long)maxIte + 2, 1 << 20);

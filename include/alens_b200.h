@@ -73,6 +73,8 @@ typedef struct alens_timers {
     double download_ms;       /* D2H of results                                                 */
     double op_force_vel_ms;   /* ConstraintOperator::ApplyDMat + ApplyMobility (accumulated)    */
     double op_dtrans_ms;      /* ConstraintOperator::ApplyDMatTrans + fused vector work         */
+    double op_update_ms;      /* x = P(x - alpha g) passes                                      */
+    long long op_force_vel_n, op_dtrans_n, op_update_n; /* launches behind the three sums       */
     long long op_launches;    /* kernel launches inside the last BCQP loop                      */
     long long total_launches; /* kernel launches since alens_reset_timers                       */
 } alens_timers;
@@ -103,6 +105,9 @@ int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, con
                    const double *length, const double *radius, const unsigned char *immovable, int wrapIntoBox);
 /* same from an array of reference `Sylinder` records (568-byte AoS), stride in bytes */
 int alens_set_rods_aos(alens_ctx *ctx, int n, const void *sylinders, size_t stride, int wrapIntoBox);
+/* SylinderSystem::prepareStep on the rods already resident on the device (after alens_step_euler or a
+ * previous alens_set_rods): box wrap, cell list, sorted SoA -- no host traffic. */
+int alens_prepare_step(alens_ctx *ctx, int wrapIntoBox);
 /* wrapped positions back (what applyBoxBC left in the container), pos[3n] */
 int alens_get_positions(alens_ctx *ctx, double *pos);
 
@@ -136,9 +141,13 @@ int alens_mobility_apply(alens_ctx *ctx, const double *x, double *y);
 /* ConstraintSolver::setup + setControlParams + solveConstraints (ConstraintSolver.cpp:4-107,
  * driven from SylinderSystem::resolveConstraints, SylinderSystem.cpp:829-866) with
  * BCQPSolver::solveBBPGD / solveAPGD (BCQPSolver.cpp:134-389).  velNonCon: 6n host doubles in local
- * rod order (may be NULL = 0).  res is conResTol (the loop stops at resPhi < res/dt). */
+ * rod order (NULL = the resident vector, zero by default).  res is conResTol (the loop stops at resPhi < res/dt). */
 int alens_solve_constraints(alens_ctx *ctx, const double *velNonCon, double dt, double res, int maxIte,
                             int solverChoice, alens_solve_report *report);
+/* velocityNonCon of SylinderSystem::calcVelocityNonCon (SylinderSystem.cpp:724-800) made resident on the
+ * device: 6n host doubles in local rod order, NULL = zero.  alens_solve_constraints / alens_setup_constraints
+ * called with velNonCon == NULL use this resident vector. */
+int alens_set_velocity_noncon(alens_ctx *ctx, const double *velNonCon);
 /* only the setup part (q, bounds, incidence); lets tests call alens_operator_apply */
 int alens_setup_constraints(alens_ctx *ctx, const double *velNonCon, double dt);
 /* ConstraintOperator::apply (ConstraintOperator.cpp:30-71): y = (D^T M D + K^-1/dt) x, host vectors of
@@ -161,6 +170,9 @@ int alens_get_rod_state(alens_ctx *ctx, double *pos, double *orientation);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 int alens_get_timers(alens_ctx *ctx, alens_timers *t);
+/* on != 0: bracket every kernel of the BCQP loop with CUDA events and accumulate per-kernel device time
+ * into alens_timers.op_*_ms (the reference's ConstraintOperator::* Teuchos timers) */
+int alens_set_profiling(alens_ctx *ctx, int on);
 int alens_reset_timers(alens_ctx *ctx);
 /* number of rods / cells / candidate pairs that passed the broad phase in the last collection */
 int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCandidates, long long *nHits);
