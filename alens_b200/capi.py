@@ -30,7 +30,7 @@ EXPORTS = [
     "alens_get_history", "alens_get_gamma", "alens_get_force_velocity", "alens_step_euler",
     "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
     "alens_comm_unique_id", "alens_comm_init", "alens_prepare_step", "alens_set_velocity_noncon",
-    "alens_set_profiling",
+    "alens_set_profiling", "alens_bcqp_solve",
 ]
 
 
@@ -183,7 +183,7 @@ class Context:
         self._call("alens_set_velocity_noncon", _dp(v))
 
     def set_profiling(self, on):
-        self._call("alens_set_profiling", C.c_int(1 if on else 0))
+        self._call("alens_set_profiling", "alens_bcqp_solve", C.c_int(1 if on else 0))
 
     def get_positions(self):
         out = np.zeros((self.n_rods, 3))
@@ -247,6 +247,16 @@ class Context:
         self._call("alens_solve_constraints", C.c_void_p(vel_nc_p), C.c_double(dt), C.c_double(res),
                    C.c_int(max_ite), C.c_int(solver_choice), C.byref(rep))
         return rep
+
+    def bcqp_solve(self, b, x0, tol, max_ite, solver_choice=0):
+        b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        x = np.array(x0, dtype=np.float64)
+        if len(x) == 0:
+            x = np.zeros(1)
+        rep = SolveReport()
+        self._call("alens_bcqp_solve", _dp(b), _dp(x), C.c_double(tol), C.c_int(max_ite), C.c_int(solver_choice),
+                   C.byref(rep))
+        return x[:len(x0)], rep
 
     def operator_apply(self, x, want_force_vel=False):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -289,6 +289,26 @@ int alens_solve_constraints(alens_ctx *ctx, const double *velNC, double dt, doub
     return rc;
 }
 
+int alens_bcqp_solve(alens_ctx *ctx, const double *b, double *x, double tol, int maxIte, int choice,
+                     alens_solve_report *rep) {
+    int rc = guarded(ctx, [&](Context &c) {
+        if (!c.haveSetup) throw ArgError{ALENS_ERR_STATE, "alens_bcqp_solve: call alens_setup_constraints first"};
+        if (maxIte < 0 || !x) throw ArgError{ALENS_ERR_ARG, "alens_bcqp_solve: bad arguments"};
+        const size_t bytes = 8 * (size_t)c.nCon;
+        if (bytes) {
+            if (b) ALENS_CUDA(cudaMemcpyAsync(c.vB.p, b, bytes, cudaMemcpyHostToDevice, c.stream));
+            ALENS_CUDA(cudaMemcpyAsync(c.vX0.p, x, bytes, cudaMemcpyHostToDevice, c.stream));
+        }
+        solveCore(c, tol, maxIte, choice);
+        if (bytes) {
+            ALENS_CUDA(cudaMemcpyAsync(x, c.xSolution, bytes, cudaMemcpyDeviceToHost, c.stream));
+            ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        }
+    });
+    if (rep && ctx) *rep = ctx->c.lastReport;
+    return rc;
+}
+
 int alens_operator_apply(alens_ctx *ctx, const double *x, double *y, double *force, double *vel) {
     return guarded(ctx, [&](Context &c) { operatorApply(c, x, y, force, vel); });
 }

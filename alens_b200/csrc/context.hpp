@@ -201,6 +201,7 @@ void mobilityApply(Context &c, const double *x, double *y);
 void setupConstraints(Context &c, const double *velNC, double dt);
 void operatorApply(Context &c, const double *x, double *y, double *force, double *vel);
 void solveConstraints(Context &c, double res, int maxIte, int choice);
+void solveCore(Context &c, double tol, int maxIte, int choice);
 void stepEuler(Context &c, double dt);
 void profFlush(Context &c);
 void reserveConstraints(Context &c, size_t n, bool keep);

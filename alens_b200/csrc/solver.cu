@@ -874,10 +874,14 @@ static int solveAPGD(Context &c, double tol, int maxIte) {
 
 void solveConstraints(Context &c, double res, int maxIte, int choice) {
     if (!c.haveSetup) throw ArgError{ALENS_ERR_STATE, "solve: setup has not been run"};
+    solveCore(c, res * (1.0 / c.dt), maxIte, choice); // ConstraintSolver.cpp:76
+}
+
+void solveCore(Context &c, double tol, int maxIte, int choice) {
+    if (!c.haveSetup) throw ArgError{ALENS_ERR_STATE, "solve: setup has not been run"};
     cudaStream_t st = c.stream;
     const long long nc = c.nCon;
     const int n = c.nRods;
-    const double tol = res * (1.0 / c.dt); // ConstraintSolver.cpp:76
     alens_solve_report &rep = c.lastReport;
     memset(&rep, 0, sizeof(rep));
     rep.n_constraints = nc;

@@ -5,7 +5,7 @@
  * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain pointers and sizes
  * (no torch / Tpetra / Eigen types) and replaces one piece of the reference's CPU path; the
  * reference-side citation (relative to the aLENS tree) is given at each declaration.  The C++ classes
- * in include/alens_b200/*.hpp (SylinderSystem / ConstraintSolver / ConstraintCollector / BCQPSolver
+ * in include/alens_b200/ (SylinderSystem.hpp, / ConstraintSolver / ConstraintCollector / BCQPSolver
  * with the reference's method names) are thin forwarding wrappers over these functions.
  *
  * Conventions
@@ -153,6 +153,13 @@ int alens_setup_constraints(alens_ctx *ctx, const double *velNonCon, double dt);
 /* ConstraintOperator::apply (ConstraintOperator.cpp:30-71): y = (D^T M D + K^-1/dt) x, host vectors of
  * length nConstraints; force/vel (6n, may be NULL) = the cached D x and M D x. */
 int alens_operator_apply(alens_ctx *ctx, const double *x, double *y, double *force, double *vel);
+/* BCQPSolver::solveBBPGD / solveAPGD (BCQPSolver.hpp:75-97) on the operator built by the last setup:
+ * min 1/2 x^T A x + b^T x with the bounds ConstraintSolver sets (0 / -inf by the bilateral flag).
+ * b: host vector of length nConstraints or NULL (= q of the setup); x: in = initial guess, out = returned
+ * iterate; tol is absolute (the caller has already divided by dt).  The force/velocity results of
+ * alens_get_force_velocity are refreshed as in ConstraintSolver::solveConstraints. */
+int alens_bcqp_solve(alens_ctx *ctx, const double *b, double *x, double tol, int maxIte, int solverChoice,
+                     alens_solve_report *report);
 /* IteHistory rows {ite,0,0,alpha,resPhi,mvCount} (BCQPSolver.hpp:23) */
 int alens_get_history(alens_ctx *ctx, double *rows6, int capRows, int *nRows);
 /* gamma in solver (= alens_get_constraints) order */

@@ -1,0 +1,256 @@
+// SylinderSystem.hpp -- the hot members of SimToolbox/Sylinder/SylinderSystem.{hpp,cpp} with the
+// reference's names and call sequence, implemented over the C ABI (include/alens_b200.h):
+//   prepareStep :886-932, calcMobOperator :719-722, calcVelocityNonCon :724-800, collectPairCollision
+//   :1152-1160, resolveConstraints :829-866, saveForceVelocityConstraints :971-1018, sumForceVelocity
+//   :802-814, stepEuler :816-827, runStep :948-969, setForceNonBrown/setVelocityNonBrown :934-946.
+// Not here (they stay with the host application, SURVEY.md section 8 "out of scope"): file/VTK I/O, YAML,
+// Brownian noise, boundaries, links, domain decomposition by FDPS.
+#ifndef ALENS_B200_SYLINDERSYSTEM_HPP_
+#define ALENS_B200_SYLINDERSYSTEM_HPP_
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ConstraintSolver.hpp"
+#include "Sylinder.hpp"
+#include "SylinderConfig.hpp"
+
+class SylinderSystem {
+    alens_ctx *ctx_ = nullptr;
+    int stepCount = 0;
+    std::vector<Sylinder> sylinderContainer;
+    std::shared_ptr<ConstraintSolver> conSolverPtr;
+    std::shared_ptr<ConstraintCollector> conCollectorPtr;
+    Teuchos::RCP<const TV> forceUniRcp, velocityUniRcp, forceBiRcp, velocityBiRcp;
+    Teuchos::RCP<TV> forcePartNonBrownRcp, velocityPartNonBrownRcp, velocityBrownRcp, velocityNonConRcp;
+    Teuchos::RCP<const TCOMM> commRcp;
+    Teuchos::RCP<TMAP> sylinderMapRcp, sylinderMobilityMapRcp;
+    Teuchos::RCP<TOP> mobilityOperatorRcp; ///< placeholder: the mobility lives on the device
+
+    void ck(int rc) const {
+        if (rc != ALENS_OK) throw std::runtime_error(alens_last_error(ctx_));
+    }
+    void updateSylinderMap() { // :868-880
+        const int nLocal = (int)sylinderContainer.size();
+        sylinderMapRcp = getTMAPFromLocalSize(nLocal, commRcp);
+        sylinderMobilityMapRcp = getTMAPFromLocalSize(nLocal * 6, commRcp);
+        const int base = sylinderMapRcp->getMinGlobalIndex();
+        for (int i = 0; i < nLocal; i++) sylinderContainer[i].globalIndex = i + base;
+    }
+
+  public:
+    SylinderConfig runConfig;
+
+    SylinderSystem() = default;
+    SylinderSystem(const SylinderConfig &config, std::vector<Sylinder> rods, int device = 0) {
+        initialize(config, std::move(rods), device);
+    }
+    ~SylinderSystem() {
+        if (ctx_) alens_destroy(ctx_);
+    }
+    SylinderSystem(const SylinderSystem &) = delete;
+    SylinderSystem &operator=(const SylinderSystem &) = delete;
+
+    /// rods are handed over by the caller (the reference reads them from file or draws them, :35-104)
+    void initialize(const SylinderConfig &config, std::vector<Sylinder> rods, int device = 0) {
+        runConfig = config;
+        stepCount = 0;
+        commRcp = getMPIWORLDTCOMM();
+        if (alens_create(device, 0, 1, &ctx_) != ALENS_OK) throw std::runtime_error(alens_last_error(nullptr));
+        conSolverPtr = std::make_shared<ConstraintSolver>(ctx_);
+        conCollectorPtr = std::make_shared<ConstraintCollector>();
+        sylinderContainer = std::move(rods);
+        const int pbc[3] = {runConfig.simBoxPBC[0], runConfig.simBoxPBC[1], runConfig.simBoxPBC[2]};
+        ck(alens_set_domain(ctx_, runConfig.simBoxLow, runConfig.simBoxHigh, pbc)); // setDomainInfo :569-610
+        if (!runConfig.sylinderFixed) { // initial collision resolution, :88-101
+            for (int i = 0; i < runConfig.initPreSteps; i++) {
+                prepareStep();
+                calcVelocityNonCon();
+                resolveConstraints();
+                saveForceVelocityConstraints();
+                sumForceVelocity();
+                stepEuler();
+            }
+        }
+    }
+
+    alens_ctx *deviceContext() { return ctx_; }
+    const std::vector<Sylinder> &getContainer() { return sylinderContainer; }
+    std::vector<Sylinder> &getContainerNonConst() { return sylinderContainer; }
+    Teuchos::RCP<const TCOMM> &getCommRcp() { return commRcp; }
+    ConstraintBlockPool &getConstraintPoolNonConst() { return *(conCollectorPtr->constraintPoolPtr); }
+    std::shared_ptr<ConstraintSolver> &getConstraintSolver() { return conSolverPtr; }
+    std::shared_ptr<ConstraintCollector> &getConstraintCollector() { return conCollectorPtr; }
+    int getStepCount() { return stepCount; }
+
+    void prepareStep() { // :886-932
+        ck(alens_set_collision_params(ctx_, runConfig.sylinderDiameterColRatio, runConfig.sylinderLengthColRatio,
+                                      runConfig.sylinderColBuf));
+        const int nLocal = (int)sylinderContainer.size();
+        for (int i = 0; i < nLocal; i++) {
+            auto &sy = sylinderContainer[i];
+            sy.clear();
+            sy.radiusCollision = sy.radius * runConfig.sylinderDiameterColRatio;
+            sy.lengthCollision = sy.length * runConfig.sylinderLengthColRatio;
+            sy.rank = commRcp->getRank();
+            sy.colBuf = runConfig.sylinderColBuf;
+        }
+        if (runConfig.monolayer) { // :907-918 (direction flattened into the xy plane)
+            const double monoZ = (runConfig.simBoxHigh[2] + runConfig.simBoxLow[2]) / 2;
+            for (auto &sy : sylinderContainer) {
+                sy.pos[2] = monoZ;
+                const double *q = sy.orientation;
+                double dx = 2 * (q[0] * q[2] + q[3] * q[1]), dy = 2 * (q[1] * q[2] - q[3] * q[0]);
+                const double n = std::sqrt(dx * dx + dy * dy);
+                if (n > 0) { // FromTwoVectors(z, d) with d in the xy plane
+                    dx /= n; dy /= n;
+                    const double s = std::sqrt(2.0);
+                    sy.orientation[0] = -dy / s; sy.orientation[1] = dx / s; sy.orientation[2] = 0; sy.orientation[3] = s * 0.5;
+                }
+            }
+        }
+        updateSylinderMap();
+        // upload (+ applyBoxBC + cell list) and bring the wrapped positions back into the container
+        ck(alens_set_rods_aos(ctx_, nLocal, sylinderContainer.data(), sizeof(Sylinder), 1));
+        if (nLocal > 0) {
+            std::vector<double> pos(3 * (size_t)nLocal);
+            ck(alens_get_positions(ctx_, pos.data()));
+            for (int i = 0; i < nLocal; i++)
+                for (int k = 0; k < 3; k++) sylinderContainer[i].pos[k] = pos[3 * (size_t)i + k];
+        }
+        calcMobOperator();
+        conCollectorPtr->clear();
+        forcePartNonBrownRcp.reset();
+        velocityPartNonBrownRcp.reset();
+        velocityBrownRcp.reset();
+    }
+
+    void calcMobMatrix() { ck(alens_calc_mobility(ctx_, runConfig.viscosity)); } // :622-717
+    void calcMobOperator() { calcMobMatrix(); }                                   // :719-722
+
+    void setForceNonBrown(const std::vector<double> &f) { // :934-939
+        if (f.size() != 6 * sylinderContainer.size()) throw std::invalid_argument("forceNonBrown.size() != 6 * nLocal");
+        forcePartNonBrownRcp = getTVFromVector(f, commRcp);
+    }
+    void setVelocityNonBrown(const std::vector<double> &v) { // :941-946
+        if (v.size() != 6 * sylinderContainer.size()) throw std::invalid_argument("velNonBrown.size() != 6 * nLocal");
+        velocityPartNonBrownRcp = getTVFromVector(v, commRcp);
+    }
+    /// Brownian velocity is generated by the host application (RNG is out of scope); 6 per rod
+    void setVelocityBrown(const std::vector<double> &v) { velocityBrownRcp = getTVFromVector(v, commRcp); }
+
+    void calcVelocityNonCon() { // :724-800
+        const int nLocal = (int)sylinderContainer.size();
+        velocityNonConRcp = Teuchos::RCP<TV>(std::make_shared<TV>(Teuchos::RCP<const TMAP>(sylinderMobilityMapRcp), true));
+        double *v = velocityNonConRcp->data();
+        auto monoZero = [&](double *p) {
+            if (!runConfig.monolayer) return;
+            for (int i = 0; i < nLocal; i++) p[6 * i + 2] = p[6 * i + 3] = p[6 * i + 4] = 0;
+        };
+        if (!forcePartNonBrownRcp.is_null()) {
+            ck(alens_mobility_apply(ctx_, forcePartNonBrownRcp->data(), v)); // mobilityOperatorRcp->apply
+            monoZero(v);
+            const double *f = forcePartNonBrownRcp->data();
+            for (int i = 0; i < nLocal; i++)
+                for (int k = 0; k < 3; k++) {
+                    sylinderContainer[i].forceNonB[k] = f[6 * i + k];
+                    sylinderContainer[i].torqueNonB[k] = f[6 * i + 3 + k];
+                }
+        }
+        if (!velocityPartNonBrownRcp.is_null()) {
+            monoZero(velocityPartNonBrownRcp->data());
+            velocityNonConRcp->update(1.0, *velocityPartNonBrownRcp, 1.0);
+        }
+        for (int i = 0; i < nLocal; i++)
+            for (int k = 0; k < 3; k++) {
+                sylinderContainer[i].velNonB[k] = v[6 * i + k];
+                sylinderContainer[i].omegaNonB[k] = v[6 * i + 3 + k];
+            }
+        if (!velocityBrownRcp.is_null()) {
+            monoZero(velocityBrownRcp->data());
+            velocityNonConRcp->update(1.0, *velocityBrownRcp, 1.0);
+            const double *b = velocityBrownRcp->data();
+            for (int i = 0; i < nLocal; i++)
+                for (int k = 0; k < 3; k++) {
+                    sylinderContainer[i].velBrown[k] = b[6 * i + k];
+                    sylinderContainer[i].omegaBrown[k] = b[6 * i + 3 + k];
+                }
+        }
+    }
+
+    void collectPairCollision() { // :1152-1160
+        long long n = 0;
+        ck(alens_collect_pair_collision(ctx_, &n));
+    }
+
+    void resolveConstraints() { // :829-866
+        collectPairCollision();
+        // collectBoundaryCollision / collectLinkBilateral: host application pushes those blocks into the pool
+        conSolverPtr->setup(*conCollectorPtr, mobilityOperatorRcp, velocityNonConRcp, runConfig.dt);
+        conSolverPtr->setControlParams(runConfig.conResTol, runConfig.conMaxIte, runConfig.conSolverChoice);
+        conSolverPtr->solveConstraints();
+        // writebackGamma is deferred: conSolverPtr->writebackGamma() on snapshot steps (272 B/constraint D2H)
+        saveForceVelocityConstraints();
+    }
+
+    void saveForceVelocityConstraints() { // :971-1018
+        forceUniRcp = conSolverPtr->getForceUni();
+        velocityUniRcp = conSolverPtr->getVelocityUni();
+        forceBiRcp = conSolverPtr->getForceBi();
+        velocityBiRcp = conSolverPtr->getVelocityBi();
+        const double *vu = velocityUniRcp->data(), *vb = velocityBiRcp->data();
+        const double *fu = forceUniRcp->data(), *fb = forceBiRcp->data();
+        const int n = (int)sylinderContainer.size();
+        for (int i = 0; i < n; i++) {
+            auto &sy = sylinderContainer[i];
+            for (int k = 0; k < 3; k++) {
+                sy.velCol[k] = vu[6 * i + k];     sy.omegaCol[k] = vu[6 * i + 3 + k];
+                sy.velBi[k] = vb[6 * i + k];      sy.omegaBi[k] = vb[6 * i + 3 + k];
+                sy.forceCol[k] = fu[6 * i + k];   sy.torqueCol[k] = fu[6 * i + 3 + k];
+                sy.forceBi[k] = fb[6 * i + k];    sy.torqueBi[k] = fb[6 * i + 3 + k];
+            }
+        }
+    }
+
+    void sumForceVelocity() { // :802-814
+        for (auto &sy : sylinderContainer)
+            for (int k = 0; k < 3; k++) {
+                sy.vel[k] = sy.velNonB[k] + sy.velBrown[k] + sy.velCol[k] + sy.velBi[k];
+                sy.omega[k] = sy.omegaNonB[k] + sy.omegaBrown[k] + sy.omegaCol[k] + sy.omegaBi[k];
+                sy.force[k] = sy.forceNonB[k] + sy.forceCol[k] + sy.forceBi[k];
+                sy.torque[k] = sy.torqueNonB[k] + sy.torqueCol[k] + sy.torqueBi[k];
+            }
+    }
+
+    /// Euler step on the device copy (vel = velNonCon + velUni + velBi, quaternion rotated by omega*dt,
+    /// Sylinder.cpp:91-99 / EquatnHelper.hpp:74-90), then pos/orientation are mirrored into the container
+    void stepEuler() { // :816-827
+        if (runConfig.sylinderFixed) return;
+        ck(alens_step_euler(ctx_, runConfig.dt));
+        const size_t n = sylinderContainer.size();
+        std::vector<double> pos(3 * n), q(4 * n);
+        ck(alens_get_rod_state(ctx_, pos.data(), q.data()));
+        for (size_t i = 0; i < n; i++) {
+            for (int k = 0; k < 3; k++) sylinderContainer[i].pos[k] = pos[3 * i + k];
+            for (int k = 0; k < 4; k++) sylinderContainer[i].orientation[k] = q[4 * i + k];
+        }
+    }
+
+    void runStep(bool count_flag = true) { // :948-969 (Brownian velocity and writeResult are the host's business)
+        calcVelocityNonCon();
+        resolveConstraints();
+        sumForceVelocity();
+        stepEuler();
+        if (count_flag) stepCount++;
+    }
+
+    Teuchos::RCP<TV> getVelocityNonCon() const { return velocityNonConRcp; }
+    Teuchos::RCP<const TV> getForceUni() const { return forceUniRcp; }
+    Teuchos::RCP<const TV> getVelocityUni() const { return velocityUniRcp; }
+    Teuchos::RCP<const TV> getForceBi() const { return forceBiRcp; }
+    Teuchos::RCP<const TV> getVelocityBi() const { return velocityBiRcp; }
+};
+
+#endif
