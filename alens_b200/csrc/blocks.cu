@@ -105,6 +105,10 @@ void appendBlocks(Context &c, const alens_constraint_block *b, long long n) {
     ALENS_CUDA(cudaGetLastError());
     ALENS_CUDA(cudaStreamSynchronize(st));
     c.hostBlocks.insert(c.hostBlocks.end(), b, b + n);
+    for (long long i = 0; i < n; i++) {
+        c.nOneSide += b[i].oneSide ? 1 : 0;
+        c.nBilateral += b[i].bilateral ? 1 : 0;
+    }
     c.nCon += n;
     c.haveSetup = false;
     c.haveSolution = false;

@@ -2,6 +2,7 @@
 // into error codes + a message retrievable with alens_last_error(); nothing here computes on the CPU.
 #include "context.hpp"
 
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -243,6 +244,7 @@ int alens_append_constraints(alens_ctx *ctx, const alens_constraint_block *b, lo
 int alens_clear_constraints(alens_ctx *ctx) {
     return guarded(ctx, [&](Context &c) {
         c.nCon = c.nColl = 0;
+        c.nOneSide = c.nBilateral = 0;
         c.hostBlocks.clear();
         c.haveSetup = false;
         c.haveSolution = false;
@@ -366,6 +368,16 @@ int alens_reset_timers(alens_ctx *ctx) {
     return guarded(ctx, [&](Context &c) {
         memset(&c.timers, 0, sizeof(c.timers));
         c.launches = 0;
+    });
+}
+
+int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
+    return guarded(ctx, [&](Context &c) {
+        const std::string k = name ? name : "";
+        if (k == "force_pipe") c.optForcePipe = value != 0;
+        else if (k == "tail_ctas_per_sm") c.optTailCtasPerSM = (int)std::max(1LL, std::min(8LL, value));
+        else if (k == "bbpgd_batch") c.optBatch = (int)std::max(0LL, std::min(1024LL, value));
+        else throw ArgError{ALENS_ERR_ARG, "alens_set_option: unknown option '" + k + "'"};
     });
 }
 

@@ -13,10 +13,14 @@
 //   k_scan_int      exclusive scan of the histogram                      (single CTA)
 //   k_cell_scatter  counting-sort scatter                                (1 thread / rod)
 //   k_cell_order    per-cell sort by user index (determinism) + gather of the sorted SoA (1 warp / cell)
-//   k_pairs<false>  count pass: one warp per cell, half stencil (14 cells); centre-distance broad phase
-//                   with warp ballot compaction into a shared-memory queue, dense narrow-phase batches
-//   k_scan_int      exclusive scan of per-cell hit counts
-//   k_pairs<true>   fill pass: same traversal, writes the constraint SoA at deterministic offsets
+//   k_pairs_find    one warp per cell, half stencil as 5 x-contiguous rows; broad phase = bounding-sphere test
+//                   (fp64) + two point/axis capsule tests (fp32, conservative slack) with warp ballot
+//                   compaction into a shared-memory queue; dense 32-lane narrow-phase (DCP) batches; hits
+//                   are staged as 16-byte records (i, j, cell, seq|image) through a warp-aggregated atomic
+//   scan            exclusive scan of per-cell hit counts (3-kernel tiled scan)
+//   k_pairs_emit    one thread per staged hit: contact re-evaluated for the hits only and written to the
+//                   constraint SoA at cellHitStart[cell] + seq  (deterministic order, one DCP pass over
+//                   the candidates instead of two)
 #include "context.hpp"
 #include "geometry.cuh"
 
@@ -65,7 +69,8 @@ __global__ void k_rod_pack(int n, double *__restrict__ pos, Box box, CellGrid g,
     atomicAdd(&cellCount[cell], 1);
 }
 
-// single-CTA exclusive scan; out has n+1 entries (out[n] = total).  n up to a few million.
+// single-CTA exclusive scan; out has n+1 entries (out[n] = total).  Used for short arrays and for the
+// tile sums of the tiled scan below.
 __global__ void k_scan_int(const int *__restrict__ in, int *__restrict__ out, int n) {
     __shared__ int sPart[1024];
     const int t = threadIdx.x, T = blockDim.x;
@@ -91,6 +96,59 @@ __global__ void k_scan_int(const int *__restrict__ in, int *__restrict__ out, in
     if (t == T - 1) out[n] = sPart[T - 1];
 }
 
+// tiled scan: tile sums -> single-CTA scan of the sums -> per-tile rescan with the tile offset
+static constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int blockExclusive256(int v, int &total) { // exclusive scan over 256 threads
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int i = 0; i < 8; i++) {
+        const int x = wsum[i];
+        if (i < w) base += x;
+        tot += x;
+    }
+    total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const int *__restrict__ in, int n,
+                                                                 int *__restrict__ tileSum) {
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) s += (base + i < n) ? in[base + i] : 0;
+    int tot;
+    blockExclusive256(s, tot);
+    if (threadIdx.x == 0) tileSum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_apply(const int *__restrict__ in, int *__restrict__ out,
+                                                                  int n, const int *__restrict__ tileOff) {
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems], s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        s += v[i];
+    }
+    int tot;
+    int run = tileOff[blockIdx.x] + blockExclusive256(s, tot);
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) out[n] = run;
+}
+
 __global__ void k_cell_scatter(int n, const int *__restrict__ cellOf, const int *__restrict__ cellStart,
                                int *__restrict__ cellFill, int *__restrict__ order) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,6 +167,7 @@ struct RodArrays {
     int *sUser, *sGid, *userToSorted;
     double *sX, *sY, *sZ, *sDx, *sDy, *sDz, *sLc, *sRc, *sLen, *sRad;
     unsigned char *sImm;
+    float *bUx, *bUy, *bUz, *bH, *bRho;
 };
 
 // one warp per cell: rank-sort the cell's rods by user index, then gather/compute the sorted SoA.
@@ -143,9 +202,22 @@ __global__ void k_cell_order(int ncell, const int *__restrict__ cellStart, const
         const double len = a.uLen[u], rad = a.uRad[u];
         a.sLen[s] = len;
         a.sRad[s] = rad;
-        a.sLc[s] = len * lRatio;
-        a.sRc[s] = rad * dRatio;
+        const double lc = len * lRatio, rc = rad * dRatio;
+        a.sLc[s] = lc;
+        a.sRc[s] = rc;
         a.sImm[s] = a.uImm ? a.uImm[u] : 0;
+        // broad-phase shape (axis segment of half length h around the centre, thickened by rho): a rod with
+        // lc < 2 rc collides as a sphere of radius lc/2 + rc (SylinderNear.hpp:241,259).  The axis is
+        // normalised here so that a non-unit quaternion cannot make the capsule tests optimistic.
+        const double ddx = a.sDx[s], ddy = a.sDy[s], ddz = a.sDz[s];
+        const double dn = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+        const bool sphere = lc < 2 * rc;
+        const bool okAxis = dn > 0 && isfinite(dn);
+        a.bUx[s] = okAxis ? (float)(ddx / dn) : 0.f;
+        a.bUy[s] = okAxis ? (float)(ddy / dn) : 0.f;
+        a.bUz[s] = okAxis ? (float)(ddz / dn) : 1.f;
+        a.bH[s] = (sphere || !okAxis) ? 0.f : __double2float_ru(0.5 * lc * dn);
+        a.bRho[s] = __double2float_ru(sphere ? (0.5 * lc + rc) : rc);
     }
 }
 
@@ -154,11 +226,13 @@ struct PairIn {
     const int *cellStart;
     const int *sGid;
     const double *sX, *sY, *sZ, *sDx, *sDy, *sDz, *sLc, *sRc;
+    const float *bUx, *bUy, *bUz, *bH, *bRho;
 };
 struct PairOut {
     int *idxI, *idxJ, *gidI, *gidJ;
     signed char *shift;
-    double *delta0, *gamma0;
+    unsigned char *bi, *oneSide;
+    double *delta0, *gamma0, *invKappa, *kappa;
     double *n, *pI, *pJ, *labI, *labJ; // [3][stride]
     size_t stride;
 };
@@ -172,22 +246,28 @@ __device__ __forceinline__ RodGeom loadRod(const PairIn &in, int s) {
     return r;
 }
 
-// Narrow phase for up to 32 queued candidates (one per lane); returns the number of hits.
+__device__ __forceinline__ void imageOf(int code, int &kx, int &ky, int &kz) {
+    kx = code % 3 - 1;
+    ky = (code / 3) % 3 - 1;
+    kz = code / 9 - 1;
+}
+
+// Narrow phase for up to 32 queued candidates (one per lane); returns the number of hits and stages them.
 // Canonical roles (reference: gid filter SylinderNear.hpp:210,225 + FDPS image rule
 // FDPS/tree_for_force_utils.hpp:256-262): I = lower gid at its own position, J = higher gid at
 // pos + k*boxLen where k is J's image relative to I.
-template <bool FILL>
-__device__ __forceinline__ int narrowBatch(const PairIn &in, const PairOut &out, const Box &box, double colBuf,
-                                           int cnt, const int *qi, const int *qj, const int *qs, int lane,
-                                           int outBase) {
+__device__ __forceinline__ int narrowBatch(const PairIn &in, const Box &box, double colBuf, int cnt, const int *qi,
+                                           const int *qj, const int *qs, int lane, int cell, int seqBase,
+                                           int4 *__restrict__ hitList, unsigned long long hitCap,
+                                           unsigned long long *__restrict__ counters) {
     bool hit = false;
-    Contact ct;
     int si = 0, sj = 0, code = 13;
     if (lane < cnt) {
         si = qi[lane];
         sj = qj[lane];
         code = qs[lane]; // image of sj relative to si
-        int kx = code % 3 - 1, ky = (code / 3) % 3 - 1, kz = code / 9 - 1;
+        int kx, ky, kz;
+        imageOf(code, kx, ky, kz);
         if (in.sGid[si] > in.sGid[sj]) { // swap roles; relative image flips sign
             const int t = si; si = sj; sj = t;
             kx = -kx; ky = -ky; kz = -kz;
@@ -195,148 +275,220 @@ __device__ __forceinline__ int narrowBatch(const PairIn &in, const PairOut &out,
         }
         RodGeom a = loadRod(in, si), b = loadRod(in, sj);
         b.c = v3(b.c.x + kx * box.len[0], b.c.y + ky * box.len[1], b.c.z + kz * box.len[2]);
+        Contact ct;
         hit = pairContact(a, b, colBuf, ct);
     }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (FILL && hit) {
-        const size_t k = (size_t)outBase + __popc(m & ((1u << lane) - 1));
-        const size_t S = out.stride;
-        out.idxI[k] = si;
-        out.idxJ[k] = sj;
-        out.gidI[k] = in.sGid[si];
-        out.gidJ[k] = in.sGid[sj];
-        out.shift[k] = (signed char)code;
-        out.delta0[k] = ct.sep;
-        out.gamma0[k] = ct.sep < 0 ? -ct.sep : 0;
-        out.n[k] = ct.normI.x; out.n[k + S] = ct.normI.y; out.n[k + 2 * S] = ct.normI.z;
-        out.pI[k] = ct.posI.x; out.pI[k + S] = ct.posI.y; out.pI[k + 2 * S] = ct.posI.z;
-        out.pJ[k] = ct.posJ.x; out.pJ[k + S] = ct.posJ.y; out.pJ[k + 2 * S] = ct.posJ.z;
-        out.labI[k] = ct.labI.x; out.labI[k + S] = ct.labI.y; out.labI[k + 2 * S] = ct.labI.z;
-        out.labJ[k] = ct.labJ.x; out.labJ[k + S] = ct.labJ.y; out.labJ[k + 2 * S] = ct.labJ.z;
+    const int nh = __popc(m);
+    if (nh == 0) return 0;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)nh);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (hit) {
+        const int r = __popc(m & ((1u << lane) - 1));
+        const unsigned long long p = base + r;
+        if (p < hitCap) hitList[p] = make_int4(si, sj, cell, ((seqBase + r) << 5) | code);
     }
-    return __popc(m);
+    return nh;
 }
 
-template <bool FILL>
+// One warp per cell.  The half stencil (own cell + 13 "positive" neighbours) is walked as 5 rows of
+// x-adjacent cells: cells adjacent in x are adjacent in the sorted arrays, so a row is one contiguous
+// range of source rods (plus at most two wrapped single cells at a periodic boundary).
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_pairs(PairIn in, PairOut out, Box box, CellGrid g, double colBuf, int *__restrict__ cellHits,
-        const int *__restrict__ cellHitStart, unsigned long long *__restrict__ counters) {
-    __shared__ double sI[kWarpsPerCta][4][kITile]; // x, y, z, R of the staged target rods
+k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ cellHits, int4 *__restrict__ hitList,
+             unsigned long long hitCap, unsigned long long *__restrict__ counters) {
+    __shared__ double sP[kWarpsPerCta][4][kITile]; // x, y, z, A = h + rho + colBuf (+ rounding slack)
+    __shared__ float sF[kWarpsPerCta][5][kITile];  // ux, uy, uz, h, B = rho + colBuf (+ slack)
     __shared__ int sQ[kWarpsPerCta][3][kQueue];    // queue: i, j, image code
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cell = blockIdx.x * kWarpsPerCta + w;
     if (cell >= g.ncell) return;
     const int ib = in.cellStart[cell], ie = in.cellStart[cell + 1];
     if (ib == ie) {
-        if (!FILL && lane == 0) cellHits[cell] = 0;
+        if (lane == 0) cellHits[cell] = 0;
         return;
     }
     const int cx = cell % g.n[0], cy = (cell / g.n[0]) % g.n[1], cz = cell / (g.n[0] * g.n[1]);
     int *qi = sQ[w][0], *qj = sQ[w][1], *qs = sQ[w][2];
-    int qn = 0;       // queue fill (warp-uniform)
-    int nHits = 0;    // hits so far in this cell (warp-uniform)
+    int qn = 0;    // queue fill (warp-uniform)
+    int nHits = 0; // hits so far in this cell (warp-uniform)
     unsigned long long nCand = 0;
-    const int outBase = FILL ? cellHitStart[cell] : 0;
     const double slack = 1.0 + 1e-10;
+    const float slackF = 1.0f + 1e-5f;
 
     for (int i0 = ib; i0 < ie; i0 += kITile) {
         const int nI = min(kITile, ie - i0);
         __syncwarp();
         for (int m = lane; m < nI; m += 32) {
             const int s = i0 + m;
-            sI[w][0][m] = in.sX[s];
-            sI[w][1][m] = in.sY[s];
-            sI[w][2][m] = in.sZ[s];
-            sI[w][3][m] = 0.5 * in.sLc[s] + in.sRc[s];
+            const double x = in.sX[s], y = in.sY[s], z = in.sZ[s];
+            const float h = in.bH[s], rho = in.bRho[s];
+            // absolute slack: rounding of coordinate differences in the narrow phase
+            const double sl = 256.0 * DBL_EPSILON * (fabs(x) + fabs(y) + fabs(z) + box.len[0] + box.len[1] + box.len[2]);
+            sP[w][0][m] = x;
+            sP[w][1][m] = y;
+            sP[w][2][m] = z;
+            sP[w][3][m] = (double)h + (double)rho + colBuf + sl;
+            sF[w][0][m] = in.bUx[s];
+            sF[w][1][m] = in.bUy[s];
+            sF[w][2][m] = in.bUz[s];
+            sF[w][3][m] = h;
+            sF[w][4][m] = __double2float_ru((double)rho + colBuf + sl);
         }
         __syncwarp();
-        // half stencil: self, then the 13 "positive" neighbours
-        for (int nb = 0; nb < 14; nb++) {
-            int dx, dy, dz;
-            if (nb == 0) { dx = 0; dy = 0; dz = 0; }
-            else if (nb == 1) { dx = 1; dy = 0; dz = 0; }
-            else if (nb < 5) { dx = nb - 3; dy = 1; dz = 0; }
-            else { dx = (nb - 5) % 3 - 1; dy = (nb - 5) / 3 - 1; dz = 1; }
-            int o[3] = {cx + dx, cy + dy, cz + dz};
-            int kimg[3] = {0, 0, 0};
+        for (int row = 0; row < 5; row++) {
+            const int dy = row == 0 ? 0 : (row == 1 ? 1 : row - 3);
+            const int dz = row < 2 ? 0 : 1;
+            int oy = cy + dy, oz = cz + dz, ky = 0, kz = 0;
             bool ok = true;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                if (o[k] < 0) {
-                    if (!box.pbc[k]) ok = false;
-                    o[k] += g.n[k];
-                    kimg[k] = -1;
-                } else if (o[k] >= g.n[k]) {
-                    if (!box.pbc[k]) ok = false;
-                    o[k] -= g.n[k];
-                    kimg[k] = 1;
-                }
-            }
+            if (oy < 0) { ok = ok && box.pbc[1]; oy += g.n[1]; ky = -1; }
+            else if (oy >= g.n[1]) { ok = ok && box.pbc[1]; oy -= g.n[1]; ky = 1; }
+            if (oz >= g.n[2]) { ok = ok && box.pbc[2]; oz -= g.n[2]; kz = 1; }
             if (!ok) continue;
-            const int cj = (o[2] * g.n[1] + o[1]) * g.n[0] + o[0];
-            const int code = (kimg[0] + 1) + 3 * (kimg[1] + 1) + 9 * (kimg[2] + 1);
-            const double shx = kimg[0] * box.len[0], shy = kimg[1] * box.len[1], shz = kimg[2] * box.len[2];
-            const int jb = in.cellStart[cj], je = in.cellStart[cj + 1];
-            for (int j0 = jb; j0 < je; j0 += 32) {
-                const int sj = j0 + lane;
-                const bool jv = sj < je;
-                double xj = 0, yj = 0, zj = 0, Rj = 0;
-                if (jv) {
-                    xj = in.sX[sj] + shx;
-                    yj = in.sY[sj] + shy;
-                    zj = in.sZ[sj] + shz;
-                    Rj = 0.5 * in.sLc[sj] + in.sRc[sj];
-                }
-                for (int m = 0; m < nI; m++) {
-                    const int si = i0 + m;
-                    bool pass = jv;
-                    if (nb == 0) pass = pass && (sj > si);         // own cell: each unordered pair once
-                    else pass = pass && (sj != si);                // a rod never pairs with its own image
-                    if (pass) {
-                        const double ddx = xj - sI[w][0][m], ddy = yj - sI[w][1][m], ddz = zj - sI[w][2][m];
-                        const double cut = sI[w][3][m] + Rj + colBuf;
-                        pass = (ddx * ddx + ddy * ddy + ddz * ddz) <= cut * cut * slack;
+            const int rowBase = (oz * g.n[1] + oy) * g.n[0];
+            const int xlo = row == 0 ? cx : cx - 1, xhi = cx + 1;
+            for (int seg = 0; seg < 3; seg++) {
+                int ca, cb, kx; // cell range [ca, cb] of this row, image in x
+                if (seg == 0) { ca = max(xlo, 0); cb = min(xhi, g.n[0] - 1); kx = 0; }
+                else if (seg == 1) { if (xlo >= 0 || !box.pbc[0]) continue; ca = cb = g.n[0] - 1; kx = -1; }
+                else { if (xhi < g.n[0] || !box.pbc[0]) continue; ca = cb = 0; kx = 1; }
+                const int jb = in.cellStart[rowBase + ca], je = in.cellStart[rowBase + cb + 1];
+                if (jb == je) continue;
+                const int code = (kx + 1) + 3 * (ky + 1) + 9 * (kz + 1);
+                const bool own = (code == 13) && row == 0; // contains the target cell itself: each pair once
+                const double shx = kx * box.len[0], shy = ky * box.len[1], shz = kz * box.len[2];
+                for (int j0 = jb; j0 < je; j0 += 32) {
+                    const int sj = j0 + lane;
+                    const bool jv = sj < je;
+                    double xj = 0, yj = 0, zj = 0, Sj = 0;
+                    float ujx = 0, ujy = 0, ujz = 1, hj = 0, rj = 0, SjF = 0;
+                    if (jv) {
+                        xj = in.sX[sj] + shx;
+                        yj = in.sY[sj] + shy;
+                        zj = in.sZ[sj] + shz;
+                        hj = in.bH[sj];
+                        rj = in.bRho[sj];
+                        ujx = in.bUx[sj]; ujy = in.bUy[sj]; ujz = in.bUz[sj];
+                        Sj = (double)hj + (double)rj;
+                        SjF = __double2float_ru(Sj);
                     }
-                    const unsigned msk = __ballot_sync(0xffffffffu, pass);
-                    if (msk == 0) continue;
-                    if (pass) {
-                        const int p = qn + __popc(msk & ((1u << lane) - 1));
-                        qi[p] = si;
-                        qj[p] = sj;
-                        qs[p] = code;
-                    }
-                    qn += __popc(msk);
-                    nCand += __popc(msk);
-                    __syncwarp();
-                    if (qn >= 32) {
-                        nHits += narrowBatch<FILL>(in, out, box, colBuf, 32, qi, qj, qs, lane, outBase + nHits);
+                    for (int m = 0; m < nI; m++) {
+                        const int si = i0 + m;
+                        bool pass = jv && (own ? (sj > si) : (sj != si)); // a rod never pairs with its own image
+                        const double ddx = xj - sP[w][0][m], ddy = yj - sP[w][1][m], ddz = zj - sP[w][2][m];
+                        const double cut = sP[w][3][m] + Sj;
+                        pass = pass && ((ddx * ddx + ddy * ddy + ddz * ddz) <= cut * cut * slack);
+                        if (__any_sync(0xffffffffu, pass)) {
+                            // capsule tests (fp32): dist(c_j, axis_i) <= h_j + rho_i + rho_j + buf and
+                            //                        dist(c_i, axis_j) <= h_i + rho_i + rho_j + buf
+                            const float fx = (float)ddx, fy = (float)ddy, fz = (float)ddz;
+                            const float cutF = (float)cut * 1e-5f; // absolute slack of the fp32 evaluation
+                            const float uix = sF[w][0][m], uiy = sF[w][1][m], uiz = sF[w][2][m], hi = sF[w][3][m];
+                            const float Bi = sF[w][4][m];
+                            float t = __fmaf_rn(fx, uix, __fmaf_rn(fy, uiy, fz * uiz));
+                            t = fminf(fmaxf(t, -hi), hi);
+                            float ex = __fmaf_rn(-t, uix, fx), ey = __fmaf_rn(-t, uiy, fy), ez = __fmaf_rn(-t, uiz, fz);
+                            float c2 = (Bi + SjF) * slackF + cutF;
+                            pass = pass && (__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez)) <= c2 * c2);
+                            t = -__fmaf_rn(fx, ujx, __fmaf_rn(fy, ujy, fz * ujz));
+                            t = fminf(fmaxf(t, -hj), hj);
+                            ex = __fmaf_rn(t, ujx, fx); ey = __fmaf_rn(t, ujy, fy); ez = __fmaf_rn(t, ujz, fz);
+                            c2 = (Bi + hi + rj) * slackF + cutF;
+                            pass = pass && (__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez)) <= c2 * c2);
+                        }
+                        const unsigned msk = __ballot_sync(0xffffffffu, pass);
+                        if (msk == 0) continue;
+                        if (pass) {
+                            const int p = qn + __popc(msk & ((1u << lane) - 1));
+                            qi[p] = si;
+                            qj[p] = sj;
+                            qs[p] = code;
+                        }
+                        qn += __popc(msk);
+                        nCand += __popc(msk);
                         __syncwarp();
-                        // move the tail to the front
-                        const int rem = qn - 32;
-                        int ti = 0, tj = 0, ts = 0;
-                        if (lane < rem) { ti = qi[32 + lane]; tj = qj[32 + lane]; ts = qs[32 + lane]; }
-                        __syncwarp();
-                        if (lane < rem) { qi[lane] = ti; qj[lane] = tj; qs[lane] = ts; }
-                        qn = rem;
-                        __syncwarp();
+                        if (qn >= 32) {
+                            nHits += narrowBatch(in, box, colBuf, 32, qi, qj, qs, lane, cell, nHits, hitList, hitCap,
+                                                 counters);
+                            __syncwarp();
+                            // move the tail to the front
+                            const int rem = qn - 32;
+                            int ti = 0, tj = 0, ts = 0;
+                            if (lane < rem) { ti = qi[32 + lane]; tj = qj[32 + lane]; ts = qs[32 + lane]; }
+                            __syncwarp();
+                            if (lane < rem) { qi[lane] = ti; qj[lane] = tj; qs[lane] = ts; }
+                            qn = rem;
+                            __syncwarp();
+                        }
                     }
                 }
             }
         }
     }
-    if (qn > 0) nHits += narrowBatch<FILL>(in, out, box, colBuf, qn, qi, qj, qs, lane, outBase + nHits);
-    if (!FILL && lane == 0) {
+    if (qn > 0) nHits += narrowBatch(in, box, colBuf, qn, qi, qj, qs, lane, cell, nHits, hitList, hitCap, counters);
+    if (lane == 0) {
         cellHits[cell] = nHits;
         atomicAdd(&counters[0], nCand);
-        atomicAdd(&counters[1], (unsigned long long)nHits);
     }
 }
 
-void launchScanInt(const int *in, int *out, int n, cudaStream_t st) { k_scan_int<<<1, 1024, 0, st>>>(in, out, n); }
+// one thread per staged hit: evaluate the contact (hits only) and write the constraint at its
+// deterministic position cellHitStart[cell] + seq
+__global__ void __launch_bounds__(128)
+k_pairs_emit(long long nHits, const int4 *__restrict__ hitList, const int *__restrict__ cellHitStart, PairIn in,
+             PairOut out, Box box, double colBuf) {
+    const long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nHits) return;
+    const int4 rec = hitList[h];
+    const int si = rec.x, sj = rec.y, code = rec.w & 31;
+    const size_t k = (size_t)cellHitStart[rec.z] + (size_t)(rec.w >> 5);
+    int kx, ky, kz;
+    imageOf(code, kx, ky, kz);
+    RodGeom a = loadRod(in, si), b = loadRod(in, sj);
+    b.c = v3(b.c.x + kx * box.len[0], b.c.y + ky * box.len[1], b.c.z + kz * box.len[2]);
+    Contact ct;
+    pairContact(a, b, colBuf, ct); // same code, same inputs as in k_pairs_find: a hit
+    const size_t S = out.stride;
+    out.idxI[k] = si;
+    out.idxJ[k] = sj;
+    out.gidI[k] = in.sGid[si];
+    out.gidJ[k] = in.sGid[sj];
+    out.shift[k] = (signed char)code;
+    out.bi[k] = 0;
+    out.oneSide[k] = 0;
+    out.delta0[k] = ct.sep;
+    out.gamma0[k] = ct.sep < 0 ? -ct.sep : 0;
+    out.invKappa[k] = 0;
+    out.kappa[k] = 0;
+    out.n[k] = ct.normI.x; out.n[k + S] = ct.normI.y; out.n[k + 2 * S] = ct.normI.z;
+    out.pI[k] = ct.posI.x; out.pI[k + S] = ct.posI.y; out.pI[k + 2 * S] = ct.posI.z;
+    out.pJ[k] = ct.posJ.x; out.pJ[k + S] = ct.posJ.y; out.pJ[k + 2 * S] = ct.posJ.z;
+    out.labI[k] = ct.labI.x; out.labI[k + S] = ct.labI.y; out.labI[k + 2 * S] = ct.labI.z;
+    out.labJ[k] = ct.labJ.x; out.labJ[k + S] = ct.labJ.y; out.labJ[k + 2 * S] = ct.labJ.z;
+}
+
+// exclusive scan of n ints into out[0..n] (out[n] = total)
+void launchScanInt(Context &c, const int *in, int *out, int n) {
+    cudaStream_t st = c.stream;
+    if (n <= 4 * kScanTile) {
+        k_scan_int<<<1, 1024, 0, st>>>(in, out, n);
+        c.launches++;
+        return;
+    }
+    const int tiles = (n + kScanTile - 1) / kScanTile;
+    c.scanTmp.reserve(2 * (size_t)tiles + 4);
+    int *tileSum = c.scanTmp.p, *tileOff = c.scanTmp.p + tiles + 1;
+    k_scan_tile_sums<<<tiles, kScanThreads, 0, st>>>(in, n, tileSum);
+    k_scan_int<<<1, 1024, 0, st>>>(tileSum, tileOff, tiles);
+    k_scan_tile_apply<<<tiles, kScanThreads, 0, st>>>(in, out, n, tileOff);
+    c.launches += 3;
+}
 
 // ------------------------------------------------------------------------------------------------
 void ctxInit(Context &c) {
     ALENS_CUDA(cudaSetDevice(c.device));
+    ALENS_CUDA(cudaDeviceGetAttribute(&c.numSMs, cudaDevAttrMultiProcessorCount, c.device));
     ALENS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     c.ownStream = true;
     for (auto &e : c.ev) ALENS_CUDA(cudaEventCreate(&e));
@@ -409,6 +561,7 @@ void rodsUploaded(Context &c, bool wrap) {
     c.sDx.reserve(n); c.sDy.reserve(n); c.sDz.reserve(n);
     c.sLc.reserve(n); c.sRc.reserve(n); c.sLen.reserve(n); c.sRad.reserve(n);
     c.sImm.reserve(n);
+    c.bUx.reserve(n); c.bUy.reserve(n); c.bUz.reserve(n); c.bH.reserve(n); c.bRho.reserve(n);
     DevBuf<int> &order = c.incFill; // scratch (rebuilt later by setup)
     order.reserve(n + 1);
     ALENS_CUDA(cudaMemsetAsync(c.cellCount.p, 0, sizeof(int) * (g.ncell + 1), st));
@@ -417,13 +570,12 @@ void rodsUploaded(Context &c, bool wrap) {
         k_rod_pack<<<gridFor(n, 256), 256, 0, st>>>(n, c.uPos.p, c.box, g, wrap ? 1 : 0, c.uCell.p, c.cellCount.p);
         c.launches++;
     }
-    k_scan_int<<<1, 1024, 0, st>>>(c.cellCount.p, c.cellStart.p, g.ncell);
-    c.launches++;
+    launchScanInt(c, c.cellCount.p, c.cellStart.p, g.ncell);
     if (n > 0) {
         k_cell_scatter<<<gridFor(n, 256), 256, 0, st>>>(n, c.uCell.p, c.cellStart.p, c.cellFill.p, order.p);
         RodArrays a{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.sUser.p, c.sGid.p,
                     c.userToSorted.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLc.p, c.sRc.p,
-                    c.sLen.p, c.sRad.p, c.sImm.p};
+                    c.sLen.p, c.sRad.p, c.sImm.p, c.bUx.p, c.bUy.p, c.bUz.p, c.bH.p, c.bRho.p};
         k_cell_order<<<gridFor((long long)g.ncell * 32, 128), 128, 0, st>>>(g.ncell, c.cellStart.p, order.p, a,
                                                                             c.dRatio, c.lRatio);
         c.launches += 2;
@@ -434,6 +586,7 @@ void rodsUploaded(Context &c, bool wrap) {
     c.haveSetup = false;
     c.haveSolution = false;
     c.nCon = c.nColl = 0;
+    c.nOneSide = c.nBilateral = 0;
     c.hostBlocks.clear();
 }
 
@@ -467,7 +620,8 @@ void reserveConstraints(Context &c, size_t n, bool keep) {
 }
 
 static PairIn pairIn(Context &c) {
-    return PairIn{c.cellStart.p, c.sGid.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLc.p, c.sRc.p};
+    return PairIn{c.cellStart.p, c.sGid.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLc.p, c.sRc.p,
+                  c.bUx.p, c.bUy.p, c.bUz.p, c.bH.p, c.bRho.p};
 }
 
 void collectPairs(Context &c) {
@@ -475,35 +629,38 @@ void collectPairs(Context &c) {
     cudaStream_t st = c.stream;
     const CellGrid g = c.grid;
     c.nCon = c.nColl = 0;
+    c.nOneSide = c.nBilateral = 0;
     c.hostBlocks.clear();
     c.haveSetup = false;
     c.haveSolution = false;
     c.cellHits.reserve(g.ncell + 1);
     c.cellHitStart.reserve(g.ncell + 1);
-    ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 4 * sizeof(unsigned long long), st));
+    c.hitList.reserve(4 * (size_t)std::max(c.nRods, 256));
     const int ctas = gridFor(g.ncell, kWarpsPerCta);
-    PairOut none{};
-    k_pairs<false><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), none, c.box, g, c.colBuf, c.cellHits.p, nullptr,
-                                                       c.dCounters.p);
-    k_scan_int<<<1, 1024, 0, st>>>(c.cellHits.p, c.cellHitStart.p, g.ncell);
-    c.launches += 2;
-    int total = 0;
-    unsigned long long cnt[2];
-    ALENS_CUDA(cudaMemcpyAsync(&total, c.cellHitStart.p + g.ncell, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ALENS_CUDA(cudaMemcpyAsync(cnt, c.dCounters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-    ALENS_CUDA(cudaStreamSynchronize(st));
-    c.statCand = (long long)cnt[0];
+    long long total = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 4 * sizeof(unsigned long long), st));
+        k_pairs_find<<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p, c.hitList.p,
+                                                         (unsigned long long)c.hitList.cap, c.dCounters.p);
+        c.launches++;
+        unsigned long long cnt[2];
+        ALENS_CUDA(cudaMemcpyAsync(cnt, c.dCounters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        launchScanInt(c, c.cellHits.p, c.cellHitStart.p, g.ncell); // overlaps with the readback
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        c.statCand = (long long)cnt[0];
+        total = (long long)cnt[1];
+        if ((size_t)total <= c.hitList.cap) break;
+        if (attempt == 1) throw ArgError{ALENS_ERR_STATE, "collect: hit list overflow after regrowth"};
+        c.hitList.reserve((size_t)total + (size_t)total / 8); // staged records were dropped: run the search again
+    }
+    if (total > 0x7fffffffLL) throw ArgError{ALENS_ERR_UNSUPPORTED, "collect: more than 2^31 constraints on one GPU"};
     reserveConstraints(c, (size_t)total, false);
     if (total > 0) {
-        PairOut out{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cDelta0.p,
-                    c.cGamma0.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
-        k_pairs<true><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), out, c.box, g, c.colBuf, nullptr,
-                                                          c.cellHitStart.p, c.dCounters.p);
+        PairOut out{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cDelta0.p,
+                    c.cGamma0.p, c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
+        k_pairs_emit<<<gridFor(total, 128), 128, 0, st>>>(total, c.hitList.p, c.cellHitStart.p, pairIn(c), out, c.box,
+                                                          c.colBuf);
         c.launches++;
-        ALENS_CUDA(cudaMemsetAsync(c.cBi.p, 0, (size_t)total, st));
-        ALENS_CUDA(cudaMemsetAsync(c.cOneSide.p, 0, (size_t)total, st));
-        ALENS_CUDA(cudaMemsetAsync(c.cInvKappa.p, 0, (size_t)total * sizeof(double), st));
-        ALENS_CUDA(cudaMemsetAsync(c.cKappa.p, 0, (size_t)total * sizeof(double), st));
     }
     ALENS_CUDA(cudaGetLastError());
     c.nCon = c.nColl = total;

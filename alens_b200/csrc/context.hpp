@@ -101,6 +101,7 @@ struct SolverScalars {
 
 struct Context {
     int device = 0, rank = 0, nranks = 1;
+    int numSMs = 148;
     cudaStream_t stream = nullptr;
     bool ownStream = true;
     std::string err;
@@ -124,10 +125,12 @@ struct Context {
     // ---- cell list + rods, sorted (cell-major) order ----
     CellGrid grid{};
     DevBuf<int> cellCount, cellStart, cellFill; // ncell(+1)
+    DevBuf<int> scanTmp;                        // tile sums / offsets of the tiled scan
     DevBuf<int> sUser;                          // sorted -> user index
     DevBuf<int> sGid;
     DevBuf<double> sX, sY, sZ, sDx, sDy, sDz, sLc, sRc; // collision geometry
     DevBuf<double> sLen, sRad;                           // hydrodynamic length/radius
+    DevBuf<float> bUx, bUy, bUz, bH, bRho;               // broad phase: unit axis, half length, radius (fp32)
     DevBuf<unsigned char> sImm;
     DevBuf<double> sInvDrag; // 3 per rod: 1/para, 1/perp, 1/rot (0 if immovable)
     bool sorted = false;
@@ -135,6 +138,7 @@ struct Context {
     // ---- constraints (solver order) ----
     long long nCon = 0, nColl = 0; // total / produced by pair collection
     DevBuf<int> cellHits, cellHitStart;
+    DevBuf<int4> hitList;      // staged hits of k_pairs_find: (i, j, cell, seq<<5 | image code)
     DevBuf<int> cIdxI, cIdxJ; // sorted rod index; cIdxJ = -1 for oneSide
     DevBuf<int> cGidI, cGidJ;
     DevBuf<double> cN, cPI, cPJ;     // SoA by component: [3][cap] each (stride = conCap)
@@ -153,7 +157,11 @@ struct Context {
     DevBuf<int> incDeg, incStart, incFill; // nRods(+1)
     DevBuf<int> incCon;                    // constraint id per slot
     DevBuf<double> incCol;                 // 6 per slot: D column block for that (rod, constraint)
-    long long nInc = 0;
+    long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
+    long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
+    int optForcePipe = 1;                   // 1: k_force_vel_pipe (TMA bulk ring), 0: k_force_vel
+    int optTailCtasPerSM = 2;               // persistent grid of k_bb_tail
+    int optBatch = 0;                       // BBPGD iterations enqueued per host check (0 = automatic)
     bool haveSetup = false;
     double dt = 0.0;
 
@@ -209,7 +217,7 @@ void reserveConstraints(Context &c, size_t n, bool keep);
 inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }
 
 // shared small kernels (collide.cu)
-void launchScanInt(const int *in, int *out, int n, cudaStream_t st);
+void launchScanInt(Context &c, const int *in, int *out, int n);
 extern double g_lastMaxR;
 double hostMaxRadius(int n, const double *len, const double *rad, double lRatio, double dRatio);
 

@@ -190,7 +190,7 @@ __global__ void k_setup(long long nc, ConGeom g, const int *__restrict__ sUser, 
 // sums its own rod's slots in slot order.
 struct FvIn {
     const int *incStart, *incCon;
-    const double *incCol; // [6][nInc]
+    const double *incCol; // [6][nInc]; nInc here = component stride (Context::incStride, multiple of 4)
     size_t nInc;
     int nRods;
 };
@@ -242,6 +242,202 @@ k_force_vel(FvIn in, MobIn mob, const double *__restrict__ x, const double *__re
             Fp[1] = make_double2(f[2], f[3]);
             Fp[2] = make_double2(f[4], f[5]);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hot-path variant of k_force_vel<false,false>: persistent CTAs (one per SM) walk tiles of `tileRods`
+// consecutive rods.  A tile's incidence range is 7 contiguous arrays (6 column components + constraint ids),
+// fetched with cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) into a 3-stage shared-memory ring and signalled
+// through mbarriers, so HBM stays busy while the warps gather x and sum.  Per iteration i the CTA
+//   (b) waits for tile i+1's bytes and issues its x gathers (L2) into registers,
+//   (c) sums tile i from shared memory (2 threads per rod: translation / rotation half) and applies M,
+//   (d) parks the gathered x of tile i+1 in shared memory,
+//   (f) issues the bulk copies of tile i+3 into the stage tile i just released and writes U coalesced.
+// Products and summation order per rod are those of k_force_vel, so both kernels give identical bits.
+__device__ __forceinline__ unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    do { // try_wait suspends the thread in hardware until the phase flips or a time limit passes
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smemAddr(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
+static constexpr int kPipeThreads = 256;
+static constexpr int kPipeMaxRods = 128; // 2 threads per rod
+
+template <int CAP, int NST>
+struct PipeSmem {
+    double col[NST][6][CAP];
+    double xs[NST][CAP];
+    double ust[2][kPipeMaxRods * 6];
+    int con[NST][CAP];
+    unsigned long long bar[NST];
+};
+
+struct TileBounds {
+    int r0, nR, sBeg, sEnd; // rods [r0, r0+nR), slots [sBeg, sEnd)
+    __device__ __forceinline__ int a0() const { return sBeg & ~3; }
+    __device__ __forceinline__ int n4() const { return ((sEnd + 3) & ~3) - (sBeg & ~3); }
+};
+
+template <int CAP, int NST>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+k_force_vel_pipe(FvIn in, MobIn mob, const double *__restrict__ x, double *__restrict__ U,
+                 const SolverScalars *__restrict__ scal, int tileRods, int nTiles) {
+    extern __shared__ __align__(128) unsigned char smRaw[];
+    PipeSmem<CAP, NST> &sm = *reinterpret_cast<PipeSmem<CAP, NST> *>(smRaw);
+    if (scal && *reinterpret_cast<const volatile int *>(&scal->done)) return;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < NST; i++) mbarInit(&sm.bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int myTiles = (nTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto bounds = [&](int j) { // tile j of this CTA (uniform loads)
+        TileBounds b{0, 0, 0, 0};
+        if (j < myTiles) {
+            const int t = blockIdx.x + j * gridDim.x;
+            b.r0 = t * tileRods;
+            b.nR = min(tileRods, in.nRods - b.r0);
+            b.sBeg = __ldg(in.incStart + b.r0);
+            b.sEnd = __ldg(in.incStart + b.r0 + b.nR);
+        }
+        return b;
+    };
+    auto issue = [&](int j, const TileBounds &b) { // thread 0 only, j < myTiles
+        unsigned long long *bar = &sm.bar[j % NST];
+        const int n4 = b.n4();
+        if (n4 == 0 || n4 > CAP) { // nothing to fetch (or oversize: direct path) -> flip the phase
+            mbarExpectTx(bar, 0);
+            return;
+        }
+        const int st = j % NST, a0 = b.a0();
+        mbarExpectTx(bar, (unsigned)n4 * 52u);
+#pragma unroll
+        for (int c = 0; c < 6; c++) bulkLoad(&sm.col[st][c][0], in.incCol + c * in.nInc + a0, (unsigned)n4 * 8u, bar);
+        bulkLoad(&sm.con[st][0], in.incCon + a0, (unsigned)n4 * 4u, bar);
+    };
+    constexpr int GPT = CAP / kPipeThreads; // gathers per thread
+    double xg[GPT];
+    auto gatherIssue = [&](int j, const TileBounds &b) { // x of tile j -> registers
+        const int st = j % NST, lo = b.sBeg - b.a0(), hi = b.sEnd - b.a0();
+        const bool ok = j < myTiles && b.n4() <= CAP;
+#pragma unroll
+        for (int q = 0; q < GPT; q++) {
+            const int sl = tid + q * kPipeThreads;
+            xg[q] = 0.0;
+            if (ok && sl >= lo && sl < hi) xg[q] = __ldg(x + (sm.con[st][sl] >> 1));
+        }
+    };
+    auto gatherStore = [&](int j) {
+        const int st = j % NST;
+#pragma unroll
+        for (int q = 0; q < GPT; q++) sm.xs[st][tid + q * kPipeThreads] = xg[q];
+    };
+
+    TileBounds b0 = bounds(0), b1 = bounds(1), b2 = bounds(2), b3;
+    static_assert(NST == 3, "bounds rotation below assumes a 3-stage ring");
+    if (tid == 0) {
+        if (0 < myTiles) issue(0, b0);
+        if (1 < myTiles) issue(1, b1);
+        if (2 < myTiles) issue(2, b2);
+    }
+    if (myTiles == 0) return;
+    mbarWait(&sm.bar[0], 0);
+    gatherIssue(0, b0);
+    gatherStore(0);
+    __syncthreads();
+
+    const int half = tid >> 7, lr = tid & (kPipeMaxRods - 1);
+    for (int i = 0; i < myTiles; i++) {
+        const int st = i % NST;
+        b3 = bounds(i + 3);
+        // (a) per-rod slot range and mobility inputs of tile i
+        const bool act = lr < b0.nR;
+        const int r = b0.r0 + lr;
+        int myBeg = 0, myEnd = 0;
+        double m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0;
+        if (act) {
+            myBeg = __ldg(in.incStart + r);
+            myEnd = __ldg(in.incStart + r + 1);
+            if (half == 0) {
+                m0 = mob.dx[r]; m1 = mob.dy[r]; m2 = mob.dz[r];
+                m3 = mob.invDrag[r]; m4 = mob.invDrag[mob.n + r];
+            } else {
+                m0 = mob.invDrag[2 * mob.n + r];
+            }
+        }
+        // (b) tile i+1 has landed? gather its x
+        if (i + 1 < myTiles) mbarWait(&sm.bar[(i + 1) % NST], (unsigned)(((i + 1) / NST) & 1));
+        gatherIssue(i + 1, b1);
+        // (c) sum tile i
+        double f0 = 0, f1 = 0, f2 = 0;
+        if (act) {
+            if (b0.n4() <= CAP) {
+                const int a0 = b0.a0();
+                const double *c0 = &sm.col[st][3 * half][0], *c1 = &sm.col[st][3 * half + 1][0],
+                             *c2 = &sm.col[st][3 * half + 2][0], *xs = &sm.xs[st][0];
+                for (int sl = myBeg - a0; sl < myEnd - a0; sl++) {
+                    const double xv = xs[sl];
+                    f0 += c0[sl] * xv;
+                    f1 += c1[sl] * xv;
+                    f2 += c2[sl] * xv;
+                }
+            } else { // oversize tile: straight from global memory
+                const double *c0 = in.incCol + (size_t)(3 * half) * in.nInc, *c1 = c0 + in.nInc, *c2 = c1 + in.nInc;
+                for (int sl = myBeg; sl < myEnd; sl++) {
+                    const double xv = x[in.incCon[sl] >> 1];
+                    f0 += c0[sl] * xv;
+                    f1 += c1[sl] * xv;
+                    f2 += c2[sl] * xv;
+                }
+            }
+            double *ud = &sm.ust[i & 1][lr * 6 + 3 * half];
+            if (half == 0) { // Mtt = qq^T/zPara + (I - qq^T)/zPerp
+                const double qf = m0 * f0 + m1 * f1 + m2 * f2;
+                const double px = qf * m0, py = qf * m1, pz = qf * m2;
+                ud[0] = m3 * px + m4 * (f0 - px);
+                ud[1] = m3 * py + m4 * (f1 - py);
+                ud[2] = m3 * pz + m4 * (f2 - pz);
+            } else { // Mrr = I/zRot
+                ud[0] = m0 * f0;
+                ud[1] = m0 * f1;
+                ud[2] = m0 * f2;
+            }
+        }
+        // (d) park x of tile i+1
+        if (i + 1 < myTiles) gatherStore(i + 1);
+        __syncthreads(); // (e) U staged, x parked, stage `st` free
+        // (f) refill the freed stage, write U of tile i
+        if (tid == 0 && i + NST < myTiles) issue(i + NST, b3);
+        {
+            const double2 *src = reinterpret_cast<const double2 *>(&sm.ust[i & 1][0]);
+            double2 *dst = reinterpret_cast<double2 *>(U + 6 * (size_t)b0.r0);
+            for (int e = tid; e < b0.nR * 3; e += kPipeThreads) dst[e] = src[e];
+        }
+        b0 = b1; b1 = b2; b2 = b3;
     }
 }
 
@@ -323,18 +519,40 @@ __device__ __forceinline__ double projGrad(double x, double g, double lbFlag, in
     return 0.0;
 }
 
+// streaming (read-once) loads bypass L1 allocation and are first in line for L2 eviction, so that the
+// gather targets (U, x) stay resident
+// gather targets (U, x) stay resident.  `asm volatile` pins the issue order: the SM issues in order, so a
+// dependent gather placed between independent streaming loads would stall everything behind it.
+__device__ __forceinline__ double ldStream(const double *p) {
+    double v;
+    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldStream(const int *p) {
+    int v;
+    asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldGather2(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 // x = P(xprev - alpha*gprev)   (BCQPSolver.cpp:191-192, :431-459)
 __global__ void k_bb_update(long long nc, const double *__restrict__ xprev, const double *__restrict__ gprev,
                             const double *__restrict__ lbFlag, double *__restrict__ x,
                             const SolverScalars *__restrict__ scal) {
-    if (scal->done) return;
+    const int done = *reinterpret_cast<const volatile int *>(&scal->done);
+    const double alpha = *reinterpret_cast<const volatile double *>(&scal->alpha);
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nc) return;
-    const double alpha = scal->alpha;
-    double v = (-alpha) * gprev[k] + 1.0 * xprev[k];
-    const double lb = (-DBL_MAX * .1) * lbFlag[k];
+    const double gp = ldStream(gprev + k), xp = ldStream(xprev + k), lbf = ldStream(lbFlag + k);
+    double v = (-alpha) * gp + 1.0 * xp;
+    const double lb = (-DBL_MAX * .1) * lbf;
     v = v > lb ? v : lb;
     v = v < kHuge ? v : kHuge;
+    if (done) return;
     x[k] = v;
 }
 
@@ -351,29 +569,105 @@ struct BbTail {
     int ite; // iteration number of this launch (0 = initial gradient)
 };
 
+// last-CTA epilogue shared by the BBPGD tail kernels: fixed-order reduction of the per-CTA partials, then the
+// scalar logic of BCQPSolver.cpp:195-233 (residual test, BB1/BB2 step, stagnation)
+__device__ __forceinline__ void bbScalarStep(const BbTail &p, const double out[4]) {
+    SolverScalars *sc = p.scal;
+    sc->ticket = 0;
+    sc->mv += 1;
+    sc->ite = p.ite;
+    const double res = out[3];
+    const double alphaUsed = p.ite == 0 ? 0.0 : sc->alpha;
+    if (sc->nhist < p.histCap) {
+        double *h = p.hist + 6 * (size_t)sc->nhist;
+        h[0] = 1.0 * p.ite; h[1] = 0; h[2] = 0; h[3] = alphaUsed; h[4] = res; h[5] = 1.0 * sc->mv;
+    }
+    sc->nhist += 1;
+    sc->res = res;
+    if (isinf(res) || isnan(res)) {
+        sc->done = 3; // projection error
+    } else if (fabs(res) < p.tol) {
+        sc->done = 1;
+    } else if (p.ite == 0) {
+        sc->alpha = 1.0 / res; // Dai & Fletcher 2005 section 5 (BCQPSolver.cpp:183)
+    } else {
+        double a, b;
+        if (p.ite % 2 == 0) { a = out[0]; b = out[1]; } // BB1
+        else { a = out[1]; b = out[2]; }                // BB2
+        if (fabs(b) < 10 * DBL_EPSILON) b += 10 * DBL_EPSILON;
+        const double alpha = a / b;
+        sc->dotA = a; sc->dotB = b;
+        sc->alpha = alpha;
+        if (alpha < DBL_EPSILON * 10) sc->done = 2; // stagnation (BCQPSolver.cpp:229-233)
+    }
+}
+
+// all streaming operands of constraint row k (136 B)
+struct TailRow {
+    int iI, iJ;
+    double gx, gy, gz, pIx, pIy, pIz, pJx, pJy, pJz, x, invK, b, lbf, xp, gp;
+};
+__device__ __forceinline__ void loadTailRow(const BbTail &p, size_t k, TailRow &r) {
+    const size_t S = p.g.stride;
+    r.iI = ldStream(p.g.idxI + k); r.iJ = ldStream(p.g.idxJ + k);
+    r.gx = ldStream(p.g.n + k); r.gy = ldStream(p.g.n + k + S); r.gz = ldStream(p.g.n + k + 2 * S);
+    r.pIx = ldStream(p.g.pI + k); r.pIy = ldStream(p.g.pI + k + S); r.pIz = ldStream(p.g.pI + k + 2 * S);
+    r.pJx = ldStream(p.g.pJ + k); r.pJy = ldStream(p.g.pJ + k + S); r.pJz = ldStream(p.g.pJ + k + 2 * S);
+    r.x = ldStream(p.x + k); r.invK = ldStream(p.invKdt + k); r.b = ldStream(p.b + k);
+    r.lbf = ldStream(p.lbFlag + k); r.xp = ldStream(p.xprev + k); r.gp = ldStream(p.gprev + k);
+}
+
 // g = A x + b, residual, BB dots; the last CTA to finish turns the partials into the next step size
 // (BCQPSolver.cpp:195-233) -- one launch replaces ~9 vector passes and 3 allreduces.
-__global__ void __launch_bounds__(kVecBlock) k_bb_tail(BbTail p) {
-    if (p.scal->done) return;
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// Persistent grid-stride kernel, software-pipelined: the streaming operands of the NEXT row are requested
+// before the rod velocities of the CURRENT row are gathered, so a thread always has one DRAM round trip
+// (136 B) and one L2 round trip (96 B) in flight and never waits on an index before issuing loads.
+__global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
+    const int done = *reinterpret_cast<const volatile int *>(&p.scal->done);
+    const long long stride = (long long)gridDim.x * kVecBlock;
+    long long k = (long long)blockIdx.x * kVecBlock + threadIdx.x;
     double s0 = 0, s1 = 0, s2 = 0, mx = 0;
-    int err = 0;
-    if (k < p.nc) {
-        const double x = p.x[k];
-        double y = dtransRow(p.g, (size_t)k, p.U);
-        y += 1.0 * p.invKdt[k] * x;
-        const double gk = 1.0 * p.b[k] + 1.0 * y;
-        p.gout[k] = gk;
-        const double q = projGrad(x, gk, p.lbFlag[k], err);
-        mx = fabs(q);
-        if (p.ite > 0) {
-            const double dx = 1.0 * x + (-1.0) * p.xprev[k];
-            const double dg = 1.0 * gk + (-1.0) * p.gprev[k];
-            s0 = dx * dx;
-            s1 = dx * dg;
-            s2 = dg * dg;
+    TailRow cur, nxt;
+    if (k < p.nc) loadTailRow(p, (size_t)k, cur);
+    if (done) return;
+    while (k < p.nc) {
+        const long long kn = k + stride;
+        if (kn < p.nc) loadTailRow(p, (size_t)kn, nxt);
+        const double2 *uI = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)cur.iI);
+        const double2 *uJ = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)(cur.iJ >= 0 ? cur.iJ : cur.iI));
+        const double2 a = ldGather2(uI), b = ldGather2(uI + 1), c = ldGather2(uI + 2);
+        const double2 d = ldGather2(uJ), e = ldGather2(uJ + 1), f = ldGather2(uJ + 2);
+        const double gx = cur.gx, gy = cur.gy, gz = cur.gz;
+        double y = gx * a.x;
+        y += gy * a.y;
+        y += gz * b.x;
+        y += (gz * cur.pIy - gy * cur.pIz) * b.y;
+        y += (gx * cur.pIz - gz * cur.pIx) * c.x;
+        y += (gy * cur.pIx - gx * cur.pIy) * c.y;
+        if (cur.iJ >= 0) {
+            const double hx = -gx, hy = -gy, hz = -gz;
+            y += hx * d.x;
+            y += hy * d.y;
+            y += hz * e.x;
+            y += (hz * cur.pJy - hy * cur.pJz) * e.y;
+            y += (hx * cur.pJz - hz * cur.pJx) * f.x;
+            y += (hy * cur.pJx - hx * cur.pJy) * f.y;
         }
-        if (err) mx = INFINITY;
+        y += 1.0 * cur.invK * cur.x;
+        const double gk = 1.0 * cur.b + 1.0 * y;
+        p.gout[k] = gk;
+        int err = 0;
+        const double q = projGrad(cur.x, gk, cur.lbf, err);
+        mx = fmax(mx, err ? INFINITY : fabs(q));
+        if (p.ite > 0) {
+            const double dx = 1.0 * cur.x + (-1.0) * cur.xp;
+            const double dg = 1.0 * gk + (-1.0) * cur.gp;
+            s0 += dx * dx;
+            s1 += dx * dg;
+            s2 += dg * dg;
+        }
+        cur = nxt;
+        k = kn;
     }
     __shared__ double out[4];
     __shared__ bool last;
@@ -395,36 +689,7 @@ __global__ void __launch_bounds__(kVecBlock) k_bb_tail(BbTail p) {
         s0 += pp[4 * i]; s1 += pp[4 * i + 1]; s2 += pp[4 * i + 2]; mx = fmax(mx, pp[4 * i + 3]);
     }
     blockReduce4(s0, s1, s2, mx, out);
-    if (threadIdx.x == 0) {
-        SolverScalars *sc = p.scal;
-        sc->ticket = 0;
-        sc->mv += 1;
-        sc->ite = p.ite;
-        const double res = out[3];
-        const double alphaUsed = p.ite == 0 ? 0.0 : sc->alpha;
-        if (sc->nhist < p.histCap) {
-            double *h = p.hist + 6 * (size_t)sc->nhist;
-            h[0] = 1.0 * p.ite; h[1] = 0; h[2] = 0; h[3] = alphaUsed; h[4] = res; h[5] = 1.0 * sc->mv;
-        }
-        sc->nhist += 1;
-        sc->res = res;
-        if (isinf(res) || isnan(res)) {
-            sc->done = 3; // projection error
-        } else if (fabs(res) < p.tol) {
-            sc->done = 1;
-        } else if (p.ite == 0) {
-            sc->alpha = 1.0 / res; // Dai & Fletcher 2005 section 5 (BCQPSolver.cpp:183)
-        } else {
-            double a, b;
-            if (p.ite % 2 == 0) { a = out[0]; b = out[1]; } // BB1
-            else { a = out[1]; b = out[2]; }                // BB2
-            if (fabs(b) < 10 * DBL_EPSILON) b += 10 * DBL_EPSILON;
-            const double alpha = a / b;
-            sc->dotA = a; sc->dotB = b;
-            sc->alpha = alpha;
-            if (alpha < DBL_EPSILON * 10) sc->done = 2; // stagnation (BCQPSolver.cpp:229-233)
-        }
-    }
+    if (threadIdx.x == 0) bbScalarStep(p, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -496,16 +761,16 @@ __global__ void k_split_out(int n, const int *__restrict__ sUser, const double *
                             const double *__restrict__ U, const double *__restrict__ Fb,
                             const double *__restrict__ Ub, double *__restrict__ oFU, double *__restrict__ oVU,
                             double *__restrict__ oFB, double *__restrict__ oVB) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const size_t u = 6 * (size_t)sUser[s], r = 6 * (size_t)s;
-    for (int c = 0; c < 6; c++) {
-        const double fb = Fb ? Fb[r + c] : 0.0, ub = Ub ? Ub[r + c] : 0.0;
-        oFU[u + c] = 1.0 * F[r + c] + (-1.0) * fb;
-        oVU[u + c] = 1.0 * U[r + c] + (-1.0) * ub;
-        oFB[u + c] = fb;
-        oVB[u + c] = ub;
-    }
+    // one thread per (rod, component): coalesced reads in sorted order, 48-byte runs on the permuted side
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 6LL * n) return;
+    const int s = (int)(e / 6), c = (int)(e - 6LL * s);
+    const size_t u = 6 * (size_t)sUser[s] + c;
+    const double fb = Fb ? Fb[e] : 0.0, ub = Ub ? Ub[e] : 0.0;
+    oFU[u] = 1.0 * F[e] + (-1.0) * fb;
+    oVU[u] = 1.0 * U[e] + (-1.0) * ub;
+    oFB[u] = fb;
+    oVB[u] = ub;
 }
 __global__ void k_permute6_to_user(int n, const int *__restrict__ sUser, const double *__restrict__ in,
                                    double *__restrict__ out) {
@@ -546,7 +811,7 @@ __global__ void k_step_euler(int n, double dt, const double *__restrict__ velNC,
 // =================================================================================================
 static MobIn mobIn(Context &c) { return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.nRods}; }
 static ConGeom conGeom(Context &c) { return ConGeom{c.cIdxI.p, c.cIdxJ.p, c.cN.p, c.cPI.p, c.cPJ.p, c.conCap}; }
-static FvIn fvIn(Context &c) { return FvIn{c.incStart.p, c.incCon.p, c.incCol.p, (size_t)c.nInc, c.nRods}; }
+static FvIn fvIn(Context &c) { return FvIn{c.incStart.p, c.incCon.p, c.incCol.p, (size_t)c.incStride, c.nRods}; }
 
 void calcMobility(Context &c, double mu) {
     if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_calc_mobility: call alens_set_rods first"};
@@ -591,7 +856,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     const bool useV = c.haveVelNC && n > 0;
     // incidence
     c.incDeg.reserve(n + 1);
-    c.incStart.reserve(n + 2);
+    c.incStart.reserve(n + 8);
     c.incFill.reserve(n + 1);
     ALENS_CUDA(cudaMemsetAsync(c.incDeg.p, 0, sizeof(int) * (n + 1), st));
     ALENS_CUDA(cudaMemsetAsync(c.incFill.p, 0, sizeof(int) * (n + 1), st));
@@ -599,14 +864,14 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
         k_inc_count<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.incDeg.p);
         c.launches++;
     }
-    launchScanInt(c.incDeg.p, c.incStart.p, n, st);
-    c.launches++;
-    int nInc = 0;
-    ALENS_CUDA(cudaMemcpyAsync(&nInc, c.incStart.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ALENS_CUDA(cudaStreamSynchronize(st));
+    launchScanInt(c, c.incDeg.p, c.incStart.p, n);
+    // slots = 2 per two-sided + 1 per one-sided constraint: known on the host, no readback
+    const long long nInc = 2 * nc - c.nOneSide;
+    if (nInc > 0x7fffffffLL - 16) throw ArgError{ALENS_ERR_UNSUPPORTED, "setup: more than 2^31 incidence slots"};
     c.nInc = nInc;
-    c.incCon.reserve((size_t)nInc + 1);
-    c.incCol.reserve(6 * (size_t)nInc + 6);
+    c.incStride = ((nInc + 3) & ~3LL) + 4; // component stride: 16-byte aligned bulk copies may over-read < 4 slots
+    c.incCon.reserve((size_t)c.incStride + 4);
+    c.incCol.reserve(6 * (size_t)c.incStride + 8);
     const size_t vcap = (size_t)nc + 1;
     c.vX0.reserve(vcap); c.vX1.reserve(vcap); c.vG0.reserve(vcap); c.vG1.reserve(vcap);
     c.vB.reserve(vcap); c.vLbFlag.reserve(vcap); c.vTmp5.reserve(vcap); // vTmp5 = invKdt
@@ -619,7 +884,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
         k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.incStart.p, c.incFill.p,
                                                      c.incCon.p);
         k_inc_finish<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incCon.p, conGeom(c), c.incCol.p,
-                                                      (size_t)nInc);
+                                                      (size_t)c.incStride);
         k_setup<<<gridFor(nc, 256), 256, 0, st>>>(nc, conGeom(c), c.sUser.p, useV ? c.uVelNC.p : nullptr,
                                                   c.cDelta0.p, c.cGamma0.p, c.cInvKappa.p, c.cBi.p, 1.0 / dt,
                                                   c.vB.p, c.vTmp5.p, c.vLbFlag.p, c.vX0.p);
@@ -662,13 +927,32 @@ void profFlush(Context &c) { // call after a stream synchronisation
     c.profUsed = 0;
 }
 
+static constexpr int kPipeCap = 1024, kPipeStages = 3;
+
 template <bool MASK, bool WF>
 static void launchForceVel(Context &c, const double *x, double *U, double *F, const SolverScalars *scal) {
     const int n = c.nRods;
     if (n == 0) return;
     profBegin(c, 0);
-    k_force_vel<MASK, WF><<<gridFor(n, kFvBlock), kFvBlock, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F,
-                                                                          scal);
+    if (!MASK && !WF && c.optForcePipe) {
+        using Sm = PipeSmem<kPipeCap, kPipeStages>;
+        static bool attr = false;
+        if (!attr) {
+            ALENS_CUDA(cudaFuncSetAttribute(k_force_vel_pipe<kPipeCap, kPipeStages>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sm)));
+            attr = true;
+        }
+        // rods per tile: ~80 % of the stage capacity on average, 2 threads per rod
+        const double avgDeg = std::max(1.0, (double)c.nInc / n);
+        int tileRods = (int)(0.8 * kPipeCap / avgDeg) & ~7;
+        tileRods = std::max(8, std::min(kPipeMaxRods, tileRods));
+        const int nTiles = gridFor(n, tileRods);
+        k_force_vel_pipe<kPipeCap, kPipeStages><<<std::min(nTiles, c.numSMs), kPipeThreads, sizeof(Sm), c.stream>>>(
+            fvIn(c), mobIn(c), x, U, scal, tileRods, nTiles);
+    } else {
+        k_force_vel<MASK, WF><<<gridFor(n, kFvBlock), kFvBlock, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F,
+                                                                              scal);
+    }
     profEnd(c);
     c.launches++;
     c.timers.op_launches++;
@@ -716,6 +1000,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     const long long nc = c.nCon;
     double *X[2] = {c.vX0.p, c.vX1.p}, *G[2] = {c.vG0.p, c.vG1.p};
     const int grid = gridFor(nc, kVecBlock);
+    const int gridTail = std::min(grid, c.numSMs * c.optTailCtasPerSM); // persistent (2 resident CTAs per SM)
     BbTail t{};
     t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.lbFlag = c.vLbFlag.p;
     t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = c.histCap; t.tol = tol;
@@ -723,11 +1008,11 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     launchForceVel<false, false>(c, X[0], c.rU.p, nullptr, c.dScal.p);
     t.ite = 0; t.x = X[0]; t.xprev = X[0]; t.gprev = G[0]; t.gout = G[0];
     profBegin(c, 1);
-    k_bb_tail<<<grid, kVecBlock, 0, st>>>(t);
+    k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
     profEnd(c);
     c.launches++; c.timers.op_launches++;
     int ite = 0;
-    const int batch = nc > 200000 ? 8 : 32;
+    const int batch = c.optBatch > 0 ? c.optBatch : (nc > 200000 ? 8 : 32);
     syncScalars(c);
     profFlush(c);
     while (!c.hScal->done && ite < maxIte) {
@@ -741,7 +1026,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
             launchForceVel<false, false>(c, X[nxt], c.rU.p, nullptr, c.dScal.p);
             t.ite = ite; t.x = X[nxt]; t.xprev = X[cur]; t.gprev = G[cur]; t.gout = G[nxt];
             profBegin(c, 1);
-            k_bb_tail<<<grid, kVecBlock, 0, st>>>(t);
+            k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
             profEnd(c);
             c.launches += 2; c.timers.op_launches += 2;
         }
@@ -919,12 +1204,14 @@ void solveCore(Context &c, double tol, int maxIte, int choice) {
     // split (ConstraintSolver.cpp:95-106): force/vel of the LAST apply minus the bilateral part
     if (nc > 0) {
         launchForceVel<false, true>(c, c.xLastApplied, c.rU.p, c.rF.p, nullptr);
-        launchForceVel<true, true>(c, c.xSolution, c.rUb.p, c.rFb.p, nullptr);
+        // no bilateral block in the pool: gamma_b = 0, the bilateral force/velocity are exactly zero
+        if (c.nBilateral > 0) launchForceVel<true, true>(c, c.xSolution, c.rUb.p, c.rFb.p, nullptr);
     }
     if (n > 0) {
-        k_split_out<<<gridFor(n, 256), 256, 0, st>>>(n, c.sUser.p, c.rF.p, c.rU.p, nc > 0 ? c.rFb.p : nullptr,
-                                                     nc > 0 ? c.rUb.p : nullptr, c.outFU.p, c.outVU.p, c.outFB.p,
-                                                     c.outVB.p);
+        const bool bi = nc > 0 && c.nBilateral > 0;
+        k_split_out<<<gridFor(6LL * n, 256), 256, 0, st>>>(n, c.sUser.p, c.rF.p, c.rU.p, bi ? c.rFb.p : nullptr,
+                                                           bi ? c.rUb.p : nullptr, c.outFU.p, c.outVU.p, c.outFB.p,
+                                                           c.outVB.p);
         c.launches++;
     }
     ALENS_CUDA(cudaEventRecord(c.ev[4], st));

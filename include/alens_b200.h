@@ -181,6 +181,10 @@ int alens_get_timers(alens_ctx *ctx, alens_timers *t);
  * into alens_timers.op_*_ms (the reference's ConstraintOperator::* Teuchos timers) */
 int alens_set_profiling(alens_ctx *ctx, int on);
 int alens_reset_timers(alens_ctx *ctx);
+/* tuning knobs (no effect on results): "force_pipe" 0/1 selects k_force_vel / k_force_vel_pipe for the
+ * operator's D x + M step; "tail_ctas_per_sm" sizes the persistent grid of k_bb_tail; "bbpgd_batch" = BBPGD
+ * iterations enqueued between two host-side convergence checks (0 = automatic) */
+int alens_set_option(alens_ctx *ctx, const char *name, long long value);
 /* number of rods / cells / candidate pairs that passed the broad phase in the last collection */
 int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCandidates, long long *nHits);
 
