@@ -30,7 +30,7 @@ EXPORTS = [
     "alens_get_history", "alens_get_gamma", "alens_get_force_velocity", "alens_step_euler",
     "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
     "alens_comm_unique_id", "alens_comm_init", "alens_prepare_step", "alens_set_velocity_noncon",
-    "alens_set_profiling", "alens_bcqp_solve", "alens_set_option",
+    "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
 ]
 
 
@@ -187,6 +187,11 @@ class Context:
 
     def set_option(self, name, value):
         self._call("alens_set_option", C.c_char_p(name.encode()), C.c_longlong(int(value)))
+
+    def time_kernel(self, which, reps=20):
+        us = C.c_double(0)
+        self._call("alens_time_kernel", C.c_char_p(which.encode()), C.c_int(reps), C.byref(us))
+        return us.value
 
     def get_positions(self):
         out = np.zeros((self.n_rods, 3))

@@ -558,7 +558,7 @@ void rodsUploaded(Context &c, bool wrap) {
     c.cellFill.reserve(g.ncell + 1);
     c.sUser.reserve(n); c.sGid.reserve(n);
     c.sX.reserve(n); c.sY.reserve(n); c.sZ.reserve(n);
-    c.sDx.reserve(n); c.sDy.reserve(n); c.sDz.reserve(n);
+    c.sDx.reserve(n + 2); c.sDy.reserve(n + 2); c.sDz.reserve(n + 2); // +2: 16-byte bulk copies over-read
     c.sLc.reserve(n); c.sRc.reserve(n); c.sLen.reserve(n); c.sRad.reserve(n);
     c.sImm.reserve(n);
     c.bUx.reserve(n); c.bUy.reserve(n); c.bUz.reserve(n); c.bH.reserve(n); c.bRho.reserve(n);

@@ -155,12 +155,14 @@ struct Context {
 
     // ---- incidence (rod -> constraints), built in setup ----
     DevBuf<int> incDeg, incStart, incFill; // nRods(+1)
-    DevBuf<int> incCon;                    // constraint id per slot
+    DevBuf<int> incCon;                    // 2*constraint + side per slot, level-major inside a 32-rod group
+    DevBuf<int> incRaw;                    // rod-major slot lists before k_inc_emit
     DevBuf<double> incCol;                 // 6 per slot: D column block for that (rod, constraint)
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
-    int optForcePipe = 1;                   // 1: k_force_vel_pipe (TMA bulk ring), 0: k_force_vel
+    int optForcePipe = 3;                   // D x + M kernel: 1/2 = k_force_vel_pipe (1 / 2 CTAs per SM), 3/4 = k_force_vel_lm (chunk 2 / 4)
     int optTailCtasPerSM = 2;               // persistent grid of k_bb_tail
+    int optPipeDebug = 0;                   // timing experiments on k_force_vel_pipe (results invalid when != 0)
     int optBatch = 0;                       // BBPGD iterations enqueued per host check (0 = automatic)
     bool haveSetup = false;
     double dt = 0.0;
@@ -212,6 +214,7 @@ void solveConstraints(Context &c, double res, int maxIte, int choice);
 void solveCore(Context &c, double tol, int maxIte, int choice);
 void stepEuler(Context &c, double dt);
 void profFlush(Context &c);
+double timeKernel(Context &c, int which, int reps);
 void reserveConstraints(Context &c, size_t n, bool keep);
 
 inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }

@@ -7,7 +7,7 @@
 //
 // D is never materialised as CSR.  A constraint k stores (n, posI, posJ, idxI, idxJ); row k of D^T is
 // [n, posI x n] on rod I and [-n, posJ x (-n)] on rod J (ConstraintCollector.cpp:298-341 with normJ = -normI).
-//   k_force_vel : f = D x (gather over the rod -> constraint incidence, staged through shared memory),
+//   k_force_vel_pipe : f = D x (rod -> constraint incidence streamed through a TMA-bulk shared-memory ring),
 //                 u = M f applied analytically from (q, 1/drag) -- one launch per operator apply
 //   k_bb_tail   : y = D^T u + K^-1 x, g = y + b, projected-gradient residual, BB dot products,
 //                 deterministic two-level reduction, step-size/termination logic in the last CTA
@@ -21,8 +21,6 @@
 
 namespace alens {
 
-static constexpr int kFvBlock = 128;  // rods per CTA in k_force_vel
-static constexpr int kFvChunk = 512;  // incidence slots staged per pass
 static constexpr int kVecBlock = 256; // threads per CTA of the per-constraint kernels
 static constexpr double kHuge = DBL_MAX / 10; // BCQPSolver.cpp:499-510
 
@@ -30,7 +28,8 @@ static constexpr double kHuge = DBL_MAX / 10; // BCQPSolver.cpp:499-510
 // mobility coefficients: Sylinder::calcDragCoeff (Sylinder.cpp:69-82); immovable rods get zero
 // mobility (SylinderSystem.cpp:660-662)
 __global__ void k_mob_coeff(int n, const double *__restrict__ len, const double *__restrict__ rad,
-                            const unsigned char *__restrict__ imm, double mu, double *__restrict__ invDrag) {
+                            const unsigned char *__restrict__ imm, double mu, double *__restrict__ invDrag,
+                            size_t stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double Pi = 3.14159265358979323846;
@@ -49,20 +48,21 @@ __global__ void k_mob_coeff(int n, const double *__restrict__ len, const double 
     }
     const bool im = imm[i] != 0;
     invDrag[i] = im ? 0.0 : 1 / dPara;
-    invDrag[n + i] = im ? 0.0 : 1 / dPerp;
-    invDrag[2 * n + i] = im ? 0.0 : 1 / dRot;
+    invDrag[stride + i] = im ? 0.0 : 1 / dPerp;
+    invDrag[2 * stride + i] = im ? 0.0 : 1 / dRot;
 }
 
 struct MobIn {
     const double *dx, *dy, *dz; // unit direction q
-    const double *invDrag;      // [3][n]
+    const double *invDrag;      // [3][stride]
     int n;
+    size_t stride;              // even (16-byte aligned component arrays)
 };
 
 // u = M f with Mtt = qq^T/zPara + (I - qq^T)/zPerp, Mrr = I/zRot (SylinderSystem.cpp:664-665)
 __device__ __forceinline__ void applyMob(const MobIn &m, int r, const double f[6], double u[6]) {
     const double qx = m.dx[r], qy = m.dy[r], qz = m.dz[r];
-    const double iPara = m.invDrag[r], iPerp = m.invDrag[m.n + r], iRot = m.invDrag[2 * m.n + r];
+    const double iPara = m.invDrag[r], iPerp = m.invDrag[m.stride + r], iRot = m.invDrag[2 * m.stride + r];
     const double qf = qx * f[0] + qy * f[1] + qz * f[2];
     const double px = qf * qx, py = qf * qy, pz = qf * qz;
     u[0] = iPara * px + iPerp * (f[0] - px);
@@ -110,36 +110,54 @@ struct ConGeom {
     size_t stride;
 };
 
-// per rod: sort the slot list by (constraint, side) -> deterministic summation order, then emit the
-// 6-vector D column block of every slot: s*[n, p x n] (ConstraintCollector.cpp:313-318)
-__global__ void k_inc_finish(int nRods, const int *__restrict__ start, int *__restrict__ incCon, ConGeom g,
-                             double *__restrict__ incCol, size_t nInc) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nRods) return;
-    const int b = start[r], e = start[r + 1];
+// One warp per group of 32 consecutive rods.  Each lane sorts its rod's raw slot list by (constraint, side)
+// -> fixed summation order; the group's slots are then emitted LEVEL-MAJOR (the 1st slot of every rod of
+// the group, then the 2nd, ...).  In the force kernel lane l of a warp reads the k-th slot of rod l: with
+// this layout consecutive lanes touch consecutive addresses (no shared-memory bank conflicts, coalesced
+// writes here).  Each slot gets its 6-vector D column block s*[n, p x n] (ConstraintCollector.cpp:313-318).
+__global__ void k_inc_emit(int nRods, const int *__restrict__ start, int *__restrict__ raw, ConGeom g,
+                           int *__restrict__ incCon, double *__restrict__ incCol, size_t stride) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp * 32 >= nRods) return;
+    const int r = warp * 32 + lane;
+    int b = 0, e = 0;
+    if (r < nRods) {
+        b = start[r];
+        e = start[r + 1];
+    }
     for (int a = b + 1; a < e; a++) { // insertion sort, lists are short
-        const int v = incCon[a];
+        const int v = raw[a];
         int p = a - 1;
-        while (p >= b && incCon[p] > v) {
-            incCon[p + 1] = incCon[p];
+        while (p >= b && raw[p] > v) {
+            raw[p + 1] = raw[p];
             p--;
         }
-        incCon[p + 1] = v;
+        raw[p + 1] = v;
     }
-    for (int s = b; s < e; s++) {
-        const int k2 = incCon[s];
-        const size_t k = (size_t)(k2 >> 1);
-        const bool sideJ = k2 & 1;
-        double gx = g.n[k], gy = g.n[k + g.stride], gz = g.n[k + 2 * g.stride];
-        const double *P = sideJ ? g.pJ : g.pI;
-        const double px = P[k], py = P[k + g.stride], pz = P[k + 2 * g.stride];
-        if (sideJ) { gx = -gx; gy = -gy; gz = -gz; }
-        incCol[s] = gx;
-        incCol[nInc + s] = gy;
-        incCol[2 * nInc + s] = gz;
-        incCol[3 * nInc + s] = (gz * py - gy * pz);
-        incCol[4 * nInc + s] = (gx * pz - gz * px);
-        incCol[5 * nInc + s] = (gy * px - gx * py);
+    const int d = e - b;
+    int off = __shfl_sync(0xffffffffu, b, 0); // first slot of the group
+    const unsigned lt = (1u << lane) - 1;
+    for (int k = 0;; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, k < d);
+        if (!m) break;
+        if (k < d) {
+            const size_t s = (size_t)(off + __popc(m & lt));
+            const int k2 = raw[b + k];
+            const size_t kk = (size_t)(k2 >> 1);
+            const bool sideJ = k2 & 1;
+            double gx = g.n[kk], gy = g.n[kk + g.stride], gz = g.n[kk + 2 * g.stride];
+            const double *P = sideJ ? g.pJ : g.pI;
+            const double px = P[kk], py = P[kk + g.stride], pz = P[kk + 2 * g.stride];
+            if (sideJ) { gx = -gx; gy = -gy; gz = -gz; }
+            incCon[s] = k2;
+            incCol[s] = gx;
+            incCol[stride + s] = gy;
+            incCol[2 * stride + s] = gz;
+            incCol[3 * stride + s] = (gz * py - gy * pz);
+            incCol[4 * stride + s] = (gx * pz - gz * px);
+            incCol[5 * stride + s] = (gy * px - gx * py);
+        }
+        off += __popc(m);
     }
 }
 
@@ -185,76 +203,45 @@ __global__ void k_setup(long long nc, ConGeom g, const int *__restrict__ sUser, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// f = D x, u = M f.  One CTA owns kFvBlock consecutive rods = one contiguous range of incidence slots;
-// the range is streamed (fully coalesced, SoA) through shared memory in chunks and each thread then
-// sums its own rod's slots in slot order.
+// streaming (read-once) loads bypass L1 allocation and are first in line for L2 eviction, so that the
+// gather targets (U, x) stay resident
+// gather targets (U, x) stay resident.  `asm volatile` pins the issue order: the SM issues in order, so a
+// dependent gather placed between independent streaming loads would stall everything behind it.
+__device__ __forceinline__ double ldStream(const double *p) {
+    double v;
+    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldStream(const int *p) {
+    int v;
+    asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ldGather2(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// f = D x, u = M f
 struct FvIn {
-    const int *incStart, *incCon;
+    const int *incStart, *incCon; // slots of a 32-rod group are stored level-major (k_inc_emit)
     const double *incCol; // [6][nInc]; nInc here = component stride (Context::incStride, multiple of 4)
     size_t nInc;
     int nRods;
 };
 
-template <bool MASK, bool WRITE_F>
-__global__ void __launch_bounds__(kFvBlock)
-k_force_vel(FvIn in, MobIn mob, const double *__restrict__ x, const double *__restrict__ mask,
-            double *__restrict__ U, double *__restrict__ F, const SolverScalars *__restrict__ scal) {
-    if (scal && scal->done) return;
-    __shared__ double sm[6][kFvChunk];
-    const int r0 = blockIdx.x * kFvBlock;
-    const int rEnd = min(in.nRods, r0 + kFvBlock);
-    const int r = r0 + threadIdx.x;
-    const int sBeg = in.incStart[r0], sEnd = in.incStart[rEnd];
-    int myBeg = 0, myEnd = 0;
-    if (r < rEnd) {
-        myBeg = in.incStart[r];
-        myEnd = in.incStart[r + 1];
-    }
-    double f[6] = {0, 0, 0, 0, 0, 0};
-    for (int c0 = sBeg; c0 < sEnd; c0 += kFvChunk) {
-        const int n = min(kFvChunk, sEnd - c0);
-        for (int s = threadIdx.x; s < n; s += kFvBlock) {
-            const size_t gs = (size_t)c0 + s;
-            const int k = in.incCon[gs] >> 1;
-            double xv = x[k];
-            if (MASK) xv = 1.0 * xv * mask[k];
-#pragma unroll
-            for (int c = 0; c < 6; c++) sm[c][s] = in.incCol[c * in.nInc + gs] * xv;
-        }
-        __syncthreads();
-        const int lo = max(myBeg, c0) - c0, hi = min(myEnd, c0 + n) - c0;
-        for (int s = lo; s < hi; s++) {
-#pragma unroll
-            for (int c = 0; c < 6; c++) f[c] += sm[c][s];
-        }
-        __syncthreads();
-    }
-    if (r < rEnd) {
-        double u[6];
-        applyMob(mob, r, f, u);
-        double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
-        Up[0] = make_double2(u[0], u[1]);
-        Up[1] = make_double2(u[2], u[3]);
-        Up[2] = make_double2(u[4], u[5]);
-        if (WRITE_F) {
-            double2 *Fp = reinterpret_cast<double2 *>(F + 6 * (size_t)r);
-            Fp[0] = make_double2(f[0], f[1]);
-            Fp[1] = make_double2(f[2], f[3]);
-            Fp[2] = make_double2(f[4], f[5]);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Hot-path variant of k_force_vel<false,false>: persistent CTAs (one per SM) walk tiles of `tileRods`
-// consecutive rods.  A tile's incidence range is 7 contiguous arrays (6 column components + constraint ids),
+// Persistent CTAs (one or two per SM) walk tiles of `tileRods` consecutive rods (a multiple of 32).  A tile's incidence range is 7 contiguous arrays (6 column components + constraint ids),
 // fetched with cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) into a 3-stage shared-memory ring and signalled
 // through mbarriers, so HBM stays busy while the warps gather x and sum.  Per iteration i the CTA
 //   (b) waits for tile i+1's bytes and issues its x gathers (L2) into registers,
 //   (c) sums tile i from shared memory (2 threads per rod: translation / rotation half) and applies M,
 //   (d) parks the gathered x of tile i+1 in shared memory,
 //   (f) issues the bulk copies of tile i+3 into the stage tile i just released and writes U coalesced.
-// Products and summation order per rod are those of k_force_vel, so both kernels give identical bits.
+// Each rod's slots are summed in slot (= constraint id) order: no atomics, run-to-run bit-reproducible.
+// MASK: x is multiplied by the bilateral flag (gamma_b = gamma o biFlag, ConstraintSolver.cpp:99);
+// WRITE_F: the force f = D x is written as well (split, ConstraintSolver.cpp:100-106).
 __device__ __forceinline__ unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(unsigned long long *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
@@ -283,161 +270,280 @@ __device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, u
                  : "memory");
 }
 
-static constexpr int kPipeThreads = 256;
-static constexpr int kPipeMaxRods = 128; // 2 threads per rod
+static constexpr int kPipeMaxTiles = 512; // tile bounds of one CTA are staged in shared memory up front
 
-template <int CAP, int NST>
+template <int CAP, int NST, int NT>
 struct PipeSmem {
-    double col[NST][6][CAP];
-    double xs[NST][CAP];
-    double ust[2][kPipeMaxRods * 6];
-    int con[NST][CAP];
+    double col[NST][6][CAP];       // D column blocks of the staged slot range
+    double xs[NST][CAP];           // gathered x per slot
+    double mob[NST][6][NT / 2];    // qx, qy, qz, 1/zPara, 1/zPerp, 1/zRot of the tile's rods
+    double ust[2][(NT / 2) * 6];   // U of the tile, staged for a coalesced write
+    int con[NST][CAP];             // constraint id (x2 + side) per slot
+    int rs[NST][NT / 2 + 4];       // incStart[r0 .. r0+nR]
+    int2 tb[kPipeMaxTiles];        // (sBeg, sEnd) of every tile this CTA owns
     unsigned long long bar[NST];
 };
 
-struct TileBounds {
-    int r0, nR, sBeg, sEnd; // rods [r0, r0+nR), slots [sBeg, sEnd)
-    __device__ __forceinline__ int a0() const { return sBeg & ~3; }
-    __device__ __forceinline__ int n4() const { return ((sEnd + 3) & ~3) - (sBeg & ~3); }
-};
-
-template <int CAP, int NST>
-__global__ void __launch_bounds__(kPipeThreads, 1)
-k_force_vel_pipe(FvIn in, MobIn mob, const double *__restrict__ x, double *__restrict__ U,
-                 const SolverScalars *__restrict__ scal, int tileRods, int nTiles) {
+template <int CAP, int NST, int NT, int MINB, bool MASK, bool WRITE_F>
+__global__ void __launch_bounds__(NT, MINB)
+k_force_vel_pipe(FvIn in, MobIn mob, const double *__restrict__ x, const double *__restrict__ mask,
+                 double *__restrict__ U, double *__restrict__ F, const SolverScalars *__restrict__ scal,
+                 int tileRods, int nTiles, int dbg) {
+    // dbg (timing experiments only, results invalid): 1 = no x gather, 2 = no summation
     extern __shared__ __align__(128) unsigned char smRaw[];
-    PipeSmem<CAP, NST> &sm = *reinterpret_cast<PipeSmem<CAP, NST> *>(smRaw);
-    if (scal && *reinterpret_cast<const volatile int *>(&scal->done)) return;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        for (int i = 0; i < NST; i++) mbarInit(&sm.bar[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int myTiles = (nTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    auto bounds = [&](int j) { // tile j of this CTA (uniform loads)
-        TileBounds b{0, 0, 0, 0};
-        if (j < myTiles) {
-            const int t = blockIdx.x + j * gridDim.x;
-            b.r0 = t * tileRods;
-            b.nR = min(tileRods, in.nRods - b.r0);
-            b.sBeg = __ldg(in.incStart + b.r0);
-            b.sEnd = __ldg(in.incStart + b.r0 + b.nR);
-        }
-        return b;
-    };
-    auto issue = [&](int j, const TileBounds &b) { // thread 0 only, j < myTiles
-        unsigned long long *bar = &sm.bar[j % NST];
-        const int n4 = b.n4();
-        if (n4 == 0 || n4 > CAP) { // nothing to fetch (or oversize: direct path) -> flip the phase
-            mbarExpectTx(bar, 0);
-            return;
-        }
-        const int st = j % NST, a0 = b.a0();
-        mbarExpectTx(bar, (unsigned)n4 * 52u);
-#pragma unroll
-        for (int c = 0; c < 6; c++) bulkLoad(&sm.col[st][c][0], in.incCol + c * in.nInc + a0, (unsigned)n4 * 8u, bar);
-        bulkLoad(&sm.con[st][0], in.incCon + a0, (unsigned)n4 * 4u, bar);
-    };
-    constexpr int GPT = CAP / kPipeThreads; // gathers per thread
-    double xg[GPT];
-    auto gatherIssue = [&](int j, const TileBounds &b) { // x of tile j -> registers
-        const int st = j % NST, lo = b.sBeg - b.a0(), hi = b.sEnd - b.a0();
-        const bool ok = j < myTiles && b.n4() <= CAP;
-#pragma unroll
-        for (int q = 0; q < GPT; q++) {
-            const int sl = tid + q * kPipeThreads;
-            xg[q] = 0.0;
-            if (ok && sl >= lo && sl < hi) xg[q] = __ldg(x + (sm.con[st][sl] >> 1));
-        }
-    };
-    auto gatherStore = [&](int j) {
-        const int st = j % NST;
-#pragma unroll
-        for (int q = 0; q < GPT; q++) sm.xs[st][tid + q * kPipeThreads] = xg[q];
-    };
+    using Sm = PipeSmem<CAP, NST, NT>;
+    Sm &sm = *reinterpret_cast<Sm *>(smRaw);
+    constexpr int MAXR = NT / 2;  // 2 threads per rod
+    constexpr int GPT = CAP / NT; // x gathers per thread
+    static_assert(MAXR % 32 == 0, "a warp owns one 32-rod group");
+    if (scal && scal->done) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int allTiles = (nTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int half = tid / MAXR, lr = tid - half * MAXR, grp0 = (lr >> 5) * 32;
+    const unsigned lt = (1u << lane) - 1;
 
-    TileBounds b0 = bounds(0), b1 = bounds(1), b2 = bounds(2), b3;
-    static_assert(NST == 3, "bounds rotation below assumes a 3-stage ring");
-    if (tid == 0) {
-        if (0 < myTiles) issue(0, b0);
-        if (1 < myTiles) issue(1, b1);
-        if (2 < myTiles) issue(2, b2);
-    }
-    if (myTiles == 0) return;
-    mbarWait(&sm.bar[0], 0);
-    gatherIssue(0, b0);
-    gatherStore(0);
-    __syncthreads();
-
-    const int half = tid >> 7, lr = tid & (kPipeMaxRods - 1);
-    for (int i = 0; i < myTiles; i++) {
-        const int st = i % NST;
-        b3 = bounds(i + 3);
-        // (a) per-rod slot range and mobility inputs of tile i
-        const bool act = lr < b0.nR;
-        const int r = b0.r0 + lr;
-        int myBeg = 0, myEnd = 0;
-        double m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0;
-        if (act) {
-            myBeg = __ldg(in.incStart + r);
-            myEnd = __ldg(in.incStart + r + 1);
-            if (half == 0) {
-                m0 = mob.dx[r]; m1 = mob.dy[r]; m2 = mob.dz[r];
-                m3 = mob.invDrag[r]; m4 = mob.invDrag[mob.n + r];
-            } else {
-                m0 = mob.invDrag[2 * mob.n + r];
+    // the tile table holds kPipeMaxTiles entries: very large systems take several rounds
+    for (int base = 0; base < allTiles; base += kPipeMaxTiles) {
+        const int myTiles = min(kPipeMaxTiles, allTiles - base);
+        auto tileR0 = [&](int j) { return (int)(blockIdx.x + (base + j) * gridDim.x) * tileRods; };
+        auto tileNR = [&](int j) { return min(tileRods, in.nRods - tileR0(j)); };
+        __syncthreads();
+        for (int j = tid; j < myTiles; j += NT) {
+            const int r0 = tileR0(j);
+            sm.tb[j] = make_int2(__ldg(in.incStart + r0), __ldg(in.incStart + r0 + tileNR(j)));
+        }
+        if (tid == 0) {
+            for (int i = 0; i < NST; i++) {
+                if (base > 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smemAddr(&sm.bar[i])) : "memory");
+                mbarInit(&sm.bar[i], 1);
             }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        // (b) tile i+1 has landed? gather its x
-        if (i + 1 < myTiles) mbarWait(&sm.bar[(i + 1) % NST], (unsigned)(((i + 1) / NST) & 1));
-        gatherIssue(i + 1, b1);
-        // (c) sum tile i
-        double f0 = 0, f1 = 0, f2 = 0;
-        if (act) {
-            if (b0.n4() <= CAP) {
-                const int a0 = b0.a0();
-                const double *c0 = &sm.col[st][3 * half][0], *c1 = &sm.col[st][3 * half + 1][0],
-                             *c2 = &sm.col[st][3 * half + 2][0], *xs = &sm.xs[st][0];
-                for (int sl = myBeg - a0; sl < myEnd - a0; sl++) {
-                    const double xv = xs[sl];
-                    f0 += c0[sl] * xv;
-                    f1 += c1[sl] * xv;
-                    f2 += c2[sl] * xv;
-                }
-            } else { // oversize tile: straight from global memory
-                const double *c0 = in.incCol + (size_t)(3 * half) * in.nInc, *c1 = c0 + in.nInc, *c2 = c1 + in.nInc;
-                for (int sl = myBeg; sl < myEnd; sl++) {
-                    const double xv = x[in.incCon[sl] >> 1];
-                    f0 += c0[sl] * xv;
-                    f1 += c1[sl] * xv;
-                    f2 += c2[sl] * xv;
+        __syncthreads();
+        // slot range of tile j rounded out to multiples of 4 (16-byte bulk copies): [a0, a0 + n4)
+        auto tileA0 = [&](int j) { return sm.tb[j].x & ~3; };
+        auto tileN4 = [&](int j) { return ((sm.tb[j].y + 3) & ~3) - (sm.tb[j].x & ~3); };
+        auto issue = [&](int j) { // thread 0 only, j < myTiles: all bulk copies of tile j into stage j % NST
+            const int st = j % NST, r0 = tileR0(j), nR = tileNR(j), n4 = tileN4(j), a0 = tileA0(j);
+            unsigned long long *bar = &sm.bar[st];
+            const unsigned nR2 = (unsigned)((nR + 1) & ~1), nR4 = (unsigned)((nR + 1 + 3) & ~3);
+            const bool slots = n4 > 0 && n4 <= CAP; // oversize tiles take the direct path
+            mbarExpectTx(bar, (slots ? (unsigned)n4 * 52u : 0u) + nR2 * 48u + nR4 * 4u);
+            if (slots) {
+#pragma unroll
+                for (int c = 0; c < 6; c++)
+                    bulkLoad(&sm.col[st][c][0], in.incCol + c * in.nInc + a0, (unsigned)n4 * 8u, bar);
+                bulkLoad(&sm.con[st][0], in.incCon + a0, (unsigned)n4 * 4u, bar);
+            }
+            bulkLoad(&sm.rs[st][0], in.incStart + r0, nR4 * 4u, bar);
+            bulkLoad(&sm.mob[st][0][0], mob.dx + r0, nR2 * 8u, bar);
+            bulkLoad(&sm.mob[st][1][0], mob.dy + r0, nR2 * 8u, bar);
+            bulkLoad(&sm.mob[st][2][0], mob.dz + r0, nR2 * 8u, bar);
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                bulkLoad(&sm.mob[st][3 + c][0], mob.invDrag + (size_t)c * mob.stride + r0, nR2 * 8u, bar);
+        };
+        double xg[GPT];
+        auto gatherIssue = [&](int j) { // x of tile j -> registers (tile j has landed)
+            const int st = j % NST;
+            const bool ok = j < myTiles && tileN4(j) <= CAP && !(dbg & 1);
+            const int lo = ok ? sm.tb[j].x - tileA0(j) : 0, hi = ok ? sm.tb[j].y - tileA0(j) : 0;
+#pragma unroll
+            for (int q = 0; q < GPT; q++) {
+                const int sl = tid + q * NT;
+                xg[q] = 0.0;
+                if (sl >= lo && sl < hi) {
+                    const int k = sm.con[st][sl] >> 1;
+                    double xv = __ldg(x + k);
+                    if (MASK) xv = 1.0 * xv * __ldg(mask + k);
+                    xg[q] = xv;
                 }
             }
-            double *ud = &sm.ust[i & 1][lr * 6 + 3 * half];
-            if (half == 0) { // Mtt = qq^T/zPara + (I - qq^T)/zPerp
-                const double qf = m0 * f0 + m1 * f1 + m2 * f2;
-                const double px = qf * m0, py = qf * m1, pz = qf * m2;
-                ud[0] = m3 * px + m4 * (f0 - px);
-                ud[1] = m3 * py + m4 * (f1 - py);
-                ud[2] = m3 * pz + m4 * (f2 - pz);
-            } else { // Mrr = I/zRot
-                ud[0] = m0 * f0;
-                ud[1] = m0 * f1;
-                ud[2] = m0 * f2;
+        };
+        auto gatherStore = [&](int j) {
+            const int st = j % NST;
+#pragma unroll
+            for (int q = 0; q < GPT; q++) sm.xs[st][tid + q * NT] = xg[q];
+        };
+
+        if (tid == 0)
+            for (int j = 0; j < NST && j < myTiles; j++) issue(j);
+        mbarWait(&sm.bar[0], 0);
+        gatherIssue(0);
+
+        for (int i = 0; i < myTiles; i++) {
+            const int st = i % NST;
+            // (a) park the x of tile i (gathered during the previous iteration)
+            gatherStore(i);
+            __syncthreads();
+            // (b) tile i+1 has landed? request its x: the latency hides behind (c)..(f)
+            if (i + 1 < myTiles) mbarWait(&sm.bar[(i + 1) % NST], (unsigned)(((i + 1) / NST) & 1));
+            gatherIssue(i + 1);
+            // (c) sum tile i: thread (lr, half) owns 3 of the 6 components of rod lr; a warp walks its 32-rod
+            // group level by level (k-th slot of every rod), positions from ballot/popc
+            const int r0 = tileR0(i), nR = tileNR(i);
+            {
+                int d = 0;
+                if (lr < nR) d = sm.rs[st][lr + 1] - sm.rs[st][lr];
+                const int dmax = (dbg & 2) ? 0 : __reduce_max_sync(0xffffffffu, d);
+                double f0 = 0, f1 = 0, f2 = 0;
+                if (tileN4(i) <= CAP) {
+                    int off = sm.rs[st][min(grp0, nR)] - tileA0(i);
+                    const double *c0 = &sm.col[st][3 * half][0], *c1 = &sm.col[st][3 * half + 1][0],
+                                 *c2 = &sm.col[st][3 * half + 2][0], *xs = &sm.xs[st][0];
+#pragma unroll 2
+                    for (int k = 0; k < dmax; k++) {
+                        const unsigned m = __ballot_sync(0xffffffffu, k < d);
+                        if (k < d) {
+                            const int pos = off + __popc(m & lt);
+                            const double xv = xs[pos];
+                            f0 += c0[pos] * xv;
+                            f1 += c1[pos] * xv;
+                            f2 += c2[pos] * xv;
+                        }
+                        off += __popc(m);
+                    }
+                } else { // oversize tile: straight from global memory
+                    size_t off = (size_t)sm.rs[st][min(grp0, nR)];
+                    const double *c0 = in.incCol + (size_t)(3 * half) * in.nInc, *c1 = c0 + in.nInc, *c2 = c1 + in.nInc;
+                    for (int k = 0; k < dmax; k++) {
+                        const unsigned m = __ballot_sync(0xffffffffu, k < d);
+                        if (k < d) {
+                            const size_t pos = off + __popc(m & lt);
+                            const int kc = in.incCon[pos] >> 1;
+                            double xv = x[kc];
+                            if (MASK) xv = 1.0 * xv * mask[kc];
+                            f0 += c0[pos] * xv;
+                            f1 += c1[pos] * xv;
+                            f2 += c2[pos] * xv;
+                        }
+                        off += __popc(m);
+                    }
+                }
+                if (lr < nR) {
+                    if (WRITE_F) {
+                        double *fd = F + 6 * (size_t)(r0 + lr) + 3 * half;
+                        fd[0] = f0; fd[1] = f1; fd[2] = f2;
+                    }
+                    double *ud = &sm.ust[i & 1][lr * 6 + 3 * half];
+                    if (half == 0) { // Mtt = qq^T/zPara + (I - qq^T)/zPerp
+                        const double qx = sm.mob[st][0][lr], qy = sm.mob[st][1][lr], qz = sm.mob[st][2][lr];
+                        const double iPara = sm.mob[st][3][lr], iPerp = sm.mob[st][4][lr];
+                        const double qf = qx * f0 + qy * f1 + qz * f2;
+                        const double px = qf * qx, py = qf * qy, pz = qf * qz;
+                        ud[0] = iPara * px + iPerp * (f0 - px);
+                        ud[1] = iPara * py + iPerp * (f1 - py);
+                        ud[2] = iPara * pz + iPerp * (f2 - pz);
+                    } else { // Mrr = I/zRot
+                        const double iRot = sm.mob[st][5][lr];
+                        ud[0] = iRot * f0;
+                        ud[1] = iRot * f1;
+                        ud[2] = iRot * f2;
+                    }
+                }
+            }
+            __syncthreads(); // (e) U staged, stage `st` free
+            // (f) refill the freed stage, write U of tile i
+            if (tid == 0 && i + NST < myTiles) issue(i + NST);
+            {
+                const double2 *src = reinterpret_cast<const double2 *>(&sm.ust[i & 1][0]);
+                double2 *dst = reinterpret_cast<double2 *>(U + 6 * (size_t)r0);
+                for (int e = tid; e < nR * 3; e += NT) dst[e] = src[e];
             }
         }
-        // (d) park x of tile i+1
-        if (i + 1 < myTiles) gatherStore(i + 1);
-        __syncthreads(); // (e) U staged, x parked, stage `st` free
-        // (f) refill the freed stage, write U of tile i
-        if (tid == 0 && i + NST < myTiles) issue(i + NST, b3);
-        {
-            const double2 *src = reinterpret_cast<const double2 *>(&sm.ust[i & 1][0]);
-            double2 *dst = reinterpret_cast<double2 *>(U + 6 * (size_t)b0.r0);
-            for (int e = tid; e < b0.nR * 3; e += kPipeThreads) dst[e] = src[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// f = D x, u = M f straight from global memory: one warp per 32-rod group, lane = rod.  With the level-major
+// slot layout (k_inc_emit) the k-th slots of the 32 rods are adjacent, so every column / id load of a level is
+// one fully coalesced request; positions come from ballot/popc on the per-lane degree.  Levels are processed
+// CHUNK at a time and software-pipelined: the constraint ids of chunk c+1 are requested before the x gathers
+// and column loads of chunk c, so a warp never waits on an id before it can issue loads.
+template <int CHUNK, bool MASK, bool WRITE_F>
+__global__ void __launch_bounds__(256)
+k_force_vel_lm(FvIn in, MobIn mob, const double *__restrict__ x, const double *__restrict__ mask,
+               double *__restrict__ U, double *__restrict__ F, const SolverScalars *__restrict__ scal) {
+    if (scal && scal->done) return;
+    const int lane = threadIdx.x & 31;
+    const int grp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (grp * 32 >= in.nRods) return;
+    const int r = grp * 32 + lane;
+    const bool act = r < in.nRods;
+    int b = 0, d = 0;
+    if (act) {
+        b = __ldg(in.incStart + r);
+        d = __ldg(in.incStart + r + 1) - b;
+    }
+    double qx = 0, qy = 0, qz = 0, iPara = 0, iPerp = 0, iRot = 0;
+    if (act) {
+        qx = mob.dx[r]; qy = mob.dy[r]; qz = mob.dz[r];
+        iPara = mob.invDrag[r]; iPerp = mob.invDrag[mob.stride + r]; iRot = mob.invDrag[2 * mob.stride + r];
+    }
+    const unsigned lt = (1u << lane) - 1;
+    const int dmax = __reduce_max_sync(0xffffffffu, d);
+    size_t off = (size_t)__shfl_sync(0xffffffffu, b, 0); // first slot of the group
+    const double *col = in.incCol;
+    const size_t S = in.nInc;
+    double f[6] = {0, 0, 0, 0, 0, 0};
+    // positions + ids of the first chunk
+    size_t pos[CHUNK], posN[CHUNK];
+    int con[CHUNK], conN[CHUNK];
+#pragma unroll
+    for (int q = 0; q < CHUNK; q++) {
+        const unsigned m = __ballot_sync(0xffffffffu, q < d);
+        pos[q] = off + __popc(m & lt);
+        off += __popc(m);
+        con[q] = (q < d) ? __ldg(in.incCon + pos[q]) : 0;
+    }
+    for (int k0 = 0; k0 < dmax; k0 += CHUNK) {
+        double xv[CHUNK], cv[CHUNK][6];
+#pragma unroll
+        for (int q = 0; q < CHUNK; q++) { // x gathers of this chunk (ids arrived one chunk ago)
+            xv[q] = 0.0;
+            if (k0 + q < d) {
+                const int kc = con[q] >> 1;
+                xv[q] = __ldg(x + kc);
+                if (MASK) xv[q] = 1.0 * xv[q] * __ldg(mask + kc);
+            }
         }
-        b0 = b1; b1 = b2; b2 = b3;
+#pragma unroll
+        for (int q = 0; q < CHUNK; q++) // column blocks of this chunk
+#pragma unroll
+            for (int c = 0; c < 6; c++) cv[q][c] = (k0 + q < d) ? ldStream(col + c * S + pos[q]) : 0.0;
+#pragma unroll
+        for (int q = 0; q < CHUNK; q++) { // ids of the next chunk
+            const int k = k0 + CHUNK + q;
+            const unsigned m = __ballot_sync(0xffffffffu, k < d);
+            posN[q] = off + __popc(m & lt);
+            off += __popc(m);
+            conN[q] = (k < d) ? __ldg(in.incCon + posN[q]) : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < CHUNK; q++) {
+            if (k0 + q < d) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) f[c] += cv[q][c] * xv[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < CHUNK; q++) {
+            pos[q] = posN[q];
+            con[q] = conN[q];
+        }
+    }
+    if (!act) return;
+    const double qf = qx * f[0] + qy * f[1] + qz * f[2];
+    const double px = qf * qx, py = qf * qy, pz = qf * qz;
+    double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
+    Up[0] = make_double2(iPara * px + iPerp * (f[0] - px), iPara * py + iPerp * (f[1] - py));
+    Up[1] = make_double2(iPara * pz + iPerp * (f[2] - pz), iRot * f[3]);
+    Up[2] = make_double2(iRot * f[4], iRot * f[5]);
+    if (WRITE_F) {
+        double2 *Fp = reinterpret_cast<double2 *>(F + 6 * (size_t)r);
+        Fp[0] = make_double2(f[0], f[1]);
+        Fp[1] = make_double2(f[2], f[3]);
+        Fp[2] = make_double2(f[4], f[5]);
     }
 }
 
@@ -519,32 +625,14 @@ __device__ __forceinline__ double projGrad(double x, double g, double lbFlag, in
     return 0.0;
 }
 
-// streaming (read-once) loads bypass L1 allocation and are first in line for L2 eviction, so that the
-// gather targets (U, x) stay resident
-// gather targets (U, x) stay resident.  `asm volatile` pins the issue order: the SM issues in order, so a
-// dependent gather placed between independent streaming loads would stall everything behind it.
-__device__ __forceinline__ double ldStream(const double *p) {
-    double v;
-    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int ldStream(const int *p) {
-    int v;
-    asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double2 ldGather2(const double2 *p) {
-    double2 v;
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-
 // x = P(xprev - alpha*gprev)   (BCQPSolver.cpp:191-192, :431-459)
 __global__ void k_bb_update(long long nc, const double *__restrict__ xprev, const double *__restrict__ gprev,
                             const double *__restrict__ lbFlag, double *__restrict__ x,
                             const SolverScalars *__restrict__ scal) {
-    const int done = *reinterpret_cast<const volatile int *>(&scal->done);
-    const double alpha = *reinterpret_cast<const volatile double *>(&scal->alpha);
+    // plain loads: every thread reads the same two words, which L1 broadcasts (a volatile / system-scope
+    // load from 3.4M threads serialises on one L2 slice: 68 us instead of 20 us for this kernel)
+    const int done = scal->done;
+    const double alpha = scal->alpha;
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nc) return;
     const double gp = ldStream(gprev + k), xp = ldStream(xprev + k), lbf = ldStream(lbFlag + k);
@@ -623,7 +711,7 @@ __device__ __forceinline__ void loadTailRow(const BbTail &p, size_t k, TailRow &
 // before the rod velocities of the CURRENT row are gathered, so a thread always has one DRAM round trip
 // (136 B) and one L2 round trip (96 B) in flight and never waits on an index before issuing loads.
 __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
-    const int done = *reinterpret_cast<const volatile int *>(&p.scal->done);
+    const int done = p.scal->done;
     const long long stride = (long long)gridDim.x * kVecBlock;
     long long k = (long long)blockIdx.x * kVecBlock + threadIdx.x;
     double s0 = 0, s1 = 0, s2 = 0, mx = 0;
@@ -809,7 +897,8 @@ __global__ void k_step_euler(int n, double dt, const double *__restrict__ velNC,
 // =================================================================================================
 // host side
 // =================================================================================================
-static MobIn mobIn(Context &c) { return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.nRods}; }
+static size_t mobStride(int n) { return ((size_t)n + 3) & ~(size_t)1; }
+static MobIn mobIn(Context &c) { return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.nRods, mobStride(c.nRods)}; }
 static ConGeom conGeom(Context &c) { return ConGeom{c.cIdxI.p, c.cIdxJ.p, c.cN.p, c.cPI.p, c.cPJ.p, c.conCap}; }
 static FvIn fvIn(Context &c) { return FvIn{c.incStart.p, c.incCon.p, c.incCol.p, (size_t)c.incStride, c.nRods}; }
 
@@ -817,9 +906,10 @@ void calcMobility(Context &c, double mu) {
     if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_calc_mobility: call alens_set_rods first"};
     c.viscosity = mu;
     const int n = c.nRods;
-    c.sInvDrag.reserve(3 * (size_t)n + 3);
+    c.sInvDrag.reserve(3 * mobStride(n) + 4);
     if (n > 0) {
-        k_mob_coeff<<<gridFor(n, 256), 256, 0, c.stream>>>(n, c.sLen.p, c.sRad.p, c.sImm.p, mu, c.sInvDrag.p);
+        k_mob_coeff<<<gridFor(n, 256), 256, 0, c.stream>>>(n, c.sLen.p, c.sRad.p, c.sImm.p, mu, c.sInvDrag.p,
+                                                           mobStride(n));
         c.launches++;
     }
     ALENS_CUDA(cudaGetLastError());
@@ -871,6 +961,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.nInc = nInc;
     c.incStride = ((nInc + 3) & ~3LL) + 4; // component stride: 16-byte aligned bulk copies may over-read < 4 slots
     c.incCon.reserve((size_t)c.incStride + 4);
+    c.incRaw.reserve((size_t)nInc + 4);
     c.incCol.reserve(6 * (size_t)c.incStride + 8);
     const size_t vcap = (size_t)nc + 1;
     c.vX0.reserve(vcap); c.vX1.reserve(vcap); c.vG0.reserve(vcap); c.vG1.reserve(vcap);
@@ -882,9 +973,9 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.redPartial.reserve(4 * (size_t)(gridFor(std::max<long long>(nc, 1), kVecBlock) + 1));
     if (nc > 0) {
         k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.incStart.p, c.incFill.p,
-                                                     c.incCon.p);
-        k_inc_finish<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incCon.p, conGeom(c), c.incCol.p,
-                                                      (size_t)c.incStride);
+                                                     c.incRaw.p);
+        k_inc_emit<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incRaw.p, conGeom(c), c.incCon.p, c.incCol.p,
+                                                    (size_t)c.incStride);
         k_setup<<<gridFor(nc, 256), 256, 0, st>>>(nc, conGeom(c), c.sUser.p, useV ? c.uVelNC.p : nullptr,
                                                   c.cDelta0.p, c.cGamma0.p, c.cInvKappa.p, c.cBi.p, 1.0 / dt,
                                                   c.vB.p, c.vTmp5.p, c.vLbFlag.p, c.vX0.p);
@@ -927,32 +1018,39 @@ void profFlush(Context &c) { // call after a stream synchronisation
     c.profUsed = 0;
 }
 
-static constexpr int kPipeCap = 1024, kPipeStages = 3;
+template <int CAP, int NT, int MINB, bool MASK, bool WF>
+static void launchPipe(Context &c, const double *x, double *U, double *F, const SolverScalars *scal) {
+    using Sm = PipeSmem<CAP, 3, NT>;
+    auto kern = k_force_vel_pipe<CAP, 3, NT, MINB, MASK, WF>;
+    static bool attr = false;
+    if (!attr) {
+        ALENS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sm)));
+        attr = true;
+    }
+    // rods per tile: a multiple of 32 (one warp per 32-rod group, 2 threads per rod) filling ~85 % of the
+    // stage capacity on average; denser tiles fall back to direct global reads inside the kernel
+    const int n = c.nRods;
+    const double avgDeg = std::max(1.0, (double)c.nInc / n);
+    int tileRods = (int)(0.85 * CAP / avgDeg) & ~31;
+    tileRods = std::max(32, std::min(NT / 2, tileRods));
+    const int nTiles = gridFor(n, tileRods);
+    const int grid = std::min(nTiles, c.numSMs * MINB);
+    kern<<<grid, NT, sizeof(Sm), c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal, tileRods, nTiles,
+                                             c.optPipeDebug);
+}
 
 template <bool MASK, bool WF>
 static void launchForceVel(Context &c, const double *x, double *U, double *F, const SolverScalars *scal) {
     const int n = c.nRods;
     if (n == 0) return;
     profBegin(c, 0);
-    if (!MASK && !WF && c.optForcePipe) {
-        using Sm = PipeSmem<kPipeCap, kPipeStages>;
-        static bool attr = false;
-        if (!attr) {
-            ALENS_CUDA(cudaFuncSetAttribute(k_force_vel_pipe<kPipeCap, kPipeStages>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sm)));
-            attr = true;
-        }
-        // rods per tile: ~80 % of the stage capacity on average, 2 threads per rod
-        const double avgDeg = std::max(1.0, (double)c.nInc / n);
-        int tileRods = (int)(0.8 * kPipeCap / avgDeg) & ~7;
-        tileRods = std::max(8, std::min(kPipeMaxRods, tileRods));
-        const int nTiles = gridFor(n, tileRods);
-        k_force_vel_pipe<kPipeCap, kPipeStages><<<std::min(nTiles, c.numSMs), kPipeThreads, sizeof(Sm), c.stream>>>(
-            fvIn(c), mobIn(c), x, U, scal, tileRods, nTiles);
-    } else {
-        k_force_vel<MASK, WF><<<gridFor(n, kFvBlock), kFvBlock, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F,
-                                                                              scal);
-    }
+    const int grid = gridFor((long long)gridFor(n, 32) * 32, 256);
+    if (c.optForcePipe == 1) launchPipe<1024, 256, 1, MASK, WF>(c, x, U, F, scal);     // 1 CTA / SM, 3 x 52 KB ring
+    else if (c.optForcePipe == 2) launchPipe<512, 128, 2, MASK, WF>(c, x, U, F, scal); // 2 CTAs / SM, 26 KB stages
+    else if (c.optForcePipe == 4)
+        k_force_vel_lm<4, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal);
+    else
+        k_force_vel_lm<2, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal);
     profEnd(c);
     c.launches++;
     c.timers.op_launches++;
@@ -1040,6 +1138,41 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     if (c.hScal->done || n == 0) c.xSolution = X[n & 1];
     else c.xSolution = X[(n - 1) & 1]; // iteMax exit returns the older iterate (BCQPSolver.cpp:237-241)
     return c.hScal->done == 2 ? 1 : 0;
+}
+
+// instrumentation: average device time of one BBPGD kernel on the current setup (alens_time_kernel).
+// Leaves the solver scalars / iterates in an unspecified state: run a setup or solve afterwards.
+double timeKernel(Context &c, int which, int reps) {
+    if (!c.haveSetup || c.nCon == 0) throw ArgError{ALENS_ERR_STATE, "alens_time_kernel: call alens_setup_constraints first"};
+    cudaStream_t st = c.stream;
+    const long long nc = c.nCon;
+    const int grid = gridFor(nc, kVecBlock);
+    const int gridTail = std::min(grid, c.numSMs * c.optTailCtasPerSM);
+    ALENS_CUDA(cudaMemsetAsync(c.dScal.p, 0, sizeof(SolverScalars), st));
+    BbTail t{};
+    t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.lbFlag = c.vLbFlag.p;
+    t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = 0; t.tol = -1.0;
+    t.ite = 1; t.x = c.vX0.p; t.xprev = c.vX0.p; t.gprev = c.vB.p; t.gout = c.vG1.p;
+    ALENS_CUDA(cudaMemsetAsync(c.rU.p, 0, 48 * (size_t)c.nRods, st));
+    const bool prof = c.profiling;
+    c.profiling = false;
+    auto one = [&]() {
+        if (which == 0) launchForceVel<false, false>(c, c.vX0.p, c.rU.p, nullptr, c.dScal.p);
+        else if (which == 1) k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
+        else k_bb_update<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, c.vB.p, c.vLbFlag.p, c.vX1.p, c.dScal.p);
+    };
+    for (int i = 0; i < 3; i++) one();
+    ALENS_CUDA(cudaEventRecord(c.ev[5], st));
+    for (int i = 0; i < reps; i++) one();
+    ALENS_CUDA(cudaEventRecord(c.ev[6], st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    ALENS_CUDA(cudaGetLastError());
+    c.profiling = prof;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev[5], c.ev[6]);
+    c.haveSetup = false;
+    c.haveSolution = false;
+    return 1e3 * ms / std::max(reps, 1);
 }
 
 // host-driven helpers for APGD

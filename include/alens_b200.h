@@ -185,6 +185,9 @@ int alens_reset_timers(alens_ctx *ctx);
  * operator's D x + M step; "tail_ctas_per_sm" sizes the persistent grid of k_bb_tail; "bbpgd_batch" = BBPGD
  * iterations enqueued between two host-side convergence checks (0 = automatic) */
 int alens_set_option(alens_ctx *ctx, const char *name, long long value);
+/* average device time (CUDA events) of `reps` back-to-back launches of one BBPGD kernel -- "force_vel",
+ * "tail" or "update" -- on the operator of the last alens_setup_constraints.  Invalidates the setup. */
+int alens_time_kernel(alens_ctx *ctx, const char *which, int reps, double *avgMicroseconds);
 /* number of rods / cells / candidate pairs that passed the broad phase in the last collection */
 int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCandidates, long long *nHits);
 

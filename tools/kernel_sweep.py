@@ -23,9 +23,10 @@ def step():
 
 out = []
 ref_gamma = None
-for opts in ({"force_pipe": 0, "tail_ctas_per_sm": 2}, {"force_pipe": 1, "tail_ctas_per_sm": 2},
-             {"force_pipe": 1, "tail_ctas_per_sm": 1}, {"force_pipe": 1, "tail_ctas_per_sm": 4},
-             {"force_pipe": 1, "tail_ctas_per_sm": 2, "bbpgd_batch": 16}):
+SWEEP = json.loads(os.environ.get("ALENS_SWEEP", "null")) or [
+    {"force_pipe": 0, "tail_ctas_per_sm": 2}, {"force_pipe": 1, "tail_ctas_per_sm": 2},
+    {"force_pipe": 2, "tail_ctas_per_sm": 2}, {"force_pipe": 2, "tail_ctas_per_sm": 3}]
+for opts in SWEEP:
     for k, v in opts.items():
         ctx.set_option(k, v)
     step()
