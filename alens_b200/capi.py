@@ -29,9 +29,19 @@ EXPORTS = [
     "alens_mobility_apply", "alens_solve_constraints", "alens_setup_constraints", "alens_operator_apply",
     "alens_get_history", "alens_get_gamma", "alens_get_force_velocity", "alens_step_euler",
     "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
-    "alens_comm_unique_id", "alens_comm_init", "alens_prepare_step", "alens_set_velocity_noncon",
+    "alens_set_decomposition", "alens_comm_create", "alens_comm_blob_size", "alens_comm_export",
+    "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
 ]
+
+
+def comm_connect_local(contexts):
+    """single-process bootstrap: contexts in rank order, each driven by its own host thread afterwards"""
+    lib = contexts[0].lib
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = lib.dll.alens_comm_connect_local(arr, C.c_int(len(contexts)))
+    if rc != 0:
+        raise AlensError(rc, lib.dll.alens_last_error(contexts[0].h).decode())
 
 
 class SolveReport(C.Structure):
@@ -187,6 +197,29 @@ class Context:
 
     def set_option(self, name, value):
         self._call("alens_set_option", C.c_char_p(name.encode()), C.c_longlong(int(value)))
+
+    # ---- multi-GPU
+    def set_decomposition(self, axis, slab_lo, slab_hi, skin, max_bounding_radius, global_base=0):
+        self._call("alens_set_decomposition", C.c_int(axis), C.c_double(slab_lo), C.c_double(slab_hi),
+                   C.c_double(skin), C.c_double(max_bounding_radius), C.c_int(global_base))
+
+    def comm_create(self, max_local_rods):
+        self._call("alens_comm_create", C.c_longlong(int(max_local_rods)))
+
+    def comm_export(self):
+        n = self.lib.dll.alens_comm_blob_size()
+        buf = C.create_string_buffer(n)
+        self._call("alens_comm_export", buf)
+        return buf.raw
+
+    def comm_connect(self, blobs):
+        """blobs: list of bytes in rank order (e.g. from torch.distributed.all_gather_object)"""
+        self._call("alens_comm_connect", C.c_char_p(b"".join(blobs)))
+
+    def num_ghosts(self):
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._call("alens_num_ghosts", C.byref(a), C.byref(b), C.byref(c))
+        return dict(ghosts=a.value, sent_left=b.value, sent_right=c.value)
 
     def time_kernel(self, which, reps=20):
         us = C.c_double(0)

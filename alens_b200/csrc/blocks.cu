@@ -24,7 +24,7 @@ struct AppendIn {
 struct ConOut {
     int *idxI, *idxJ, *gidI, *gidJ;
     signed char *shift;
-    unsigned char *bi, *oneSide;
+    unsigned char *bi, *oneSide, *own;
     double *delta0, *gamma0, *invKappa, *kappa;
     double *n, *pI, *pJ, *labI, *labJ;
     size_t stride;
@@ -41,6 +41,7 @@ __global__ void k_append(AppendIn in, ConOut o, const int *__restrict__ userToSo
     o.shift[k] = 13;
     o.bi[k] = in.bi[i];
     o.oneSide[k] = in.oneSide[i];
+    o.own[k] = 1;
     o.delta0[k] = in.delta0[i];
     o.gamma0[k] = in.gamma[i];
     const double kap = in.kappa[i];
@@ -58,14 +59,14 @@ __global__ void k_append(AppendIn in, ConOut o, const int *__restrict__ userToSo
 void appendBlocks(Context &c, const alens_constraint_block *b, long long n) {
     if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_append_constraints: call alens_set_rods first"};
     if (n <= 0) return;
-    const int off = 0; // rank offset of globalIndex (single rank; slab ranks add their scan offset)
+    const int off = c.globalBase; // rank offset of globalIndex (SylinderSystem.cpp:868-880)
     std::vector<int> uI(n), uJ(n), gI(n), gJ(n);
     std::vector<unsigned char> one(n), bi(n);
     std::vector<double> d0(n), gm(n), kp(n), vec(15 * (size_t)n);
     for (long long i = 0; i < n; i++) {
         const alens_constraint_block &q = b[i];
         const int li = q.globalIndexI - off, lj = q.globalIndexJ - off;
-        if (li < 0 || li >= c.nRods || (!q.oneSide && (lj < 0 || lj >= c.nRods)))
+        if (li < 0 || li >= c.nLocal || (!q.oneSide && (lj < 0 || lj >= c.nLocal)))
             throw ArgError{ALENS_ERR_ARG, "alens_append_constraints: globalIndex out of range"};
         if (!q.oneSide)
             for (int k = 0; k < 3; k++)
@@ -98,8 +99,8 @@ void appendBlocks(Context &c, const alens_constraint_block *b, long long n) {
     up(dD0.p, d0.data(), 8 * n); up(dGm.p, gm.data(), 8 * n); up(dKp.p, kp.data(), 8 * n);
     up(dVec.p, vec.data(), 8 * 15 * (size_t)n);
     AppendIn in{dI.p, dJ.p, dgI.p, dgJ.p, dOne.p, dBi.p, dD0.p, dGm.p, dKp.p, dVec.p, n};
-    ConOut o{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cDelta0.p, c.cGamma0.p,
-             c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
+    ConOut o{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cOwn.p, c.cDelta0.p,
+             c.cGamma0.p, c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
     k_append<<<gridFor(n, 256), 256, 0, st>>>(in, o, c.userToSorted.p, c.nCon);
     c.launches++;
     ALENS_CUDA(cudaGetLastError());
@@ -116,7 +117,7 @@ void appendBlocks(Context &c, const alens_constraint_block *b, long long n) {
 
 // ------------------------------------------------------------------------------------------------
 struct BlocksIn {
-    const int *idxI, *idxJ, *gidI, *gidJ, *sUser;
+    const int *idxI, *idxJ, *gidI, *gidJ, *sUser, *uGlobalIdx;
     const signed char *shift;
     const double *delta0, *gamma0, *n, *pI, *pJ, *labI, *labJ;
     const double *sX, *sY, *sZ, *sDx, *sDy, *sDz, *sLc, *sRc;
@@ -139,8 +140,8 @@ __global__ void k_blocks_out(long long n, BlocksIn in, int withStress, int write
     b.gammaLB = 0;
     b.gidI = in.gidI[k];
     b.gidJ = in.gidJ[k];
-    b.globalIndexI = in.globalIndexBase + in.sUser[si];
-    b.globalIndexJ = in.globalIndexBase + in.sUser[sj];
+    b.globalIndexI = in.uGlobalIdx[in.sUser[si]];
+    b.globalIndexJ = in.uGlobalIdx[in.sUser[sj]];
     b.oneSide = 0;
     b.bilateral = 0;
     b.kappa = 0;
@@ -188,7 +189,7 @@ void downloadBlocks(Context &c, alens_constraint_block *out, long long cap, bool
     if (nColl > 0) {
         DevBuf<alens_constraint_block> dOut;
         dOut.reserve((size_t)nColl);
-        BlocksIn in{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.sUser.p, c.cShift.p, c.cDelta0.p, c.cGamma0.p,
+        BlocksIn in{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.sUser.p, c.uGlobalIdx.p, c.cShift.p, c.cDelta0.p, c.cGamma0.p,
                     c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p,
                     c.sDz.p, c.sLc.p, c.sRc.p, writeBack ? c.xSolution : nullptr, c.conCap, c.box, 0};
         k_blocks_out<<<gridFor(nColl, 128), 128, 0, st>>>(nColl, in, withStress ? 1 : 0, writeBack ? 1 : 0, dOut.p);
@@ -211,6 +212,14 @@ void downloadBlocks(Context &c, alens_constraint_block *out, long long cap, bool
             }
         }
     }
+}
+
+// Force the (lazily loaded) kernels of this file into the context now: loading a kernel at its first launch can
+// synchronise the context, which deadlocks against a peer rank's waiting kernel when two ranks share one GPU.
+void preloadBlockKernels() {
+    cudaFuncAttributes a;
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_append));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_blocks_out));
 }
 
 } // namespace alens

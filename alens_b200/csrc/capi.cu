@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <vector>
 
 using namespace alens;
 
@@ -19,6 +20,8 @@ static int guarded(alens_ctx *ctx, F &&f) {
     if (!ctx) return ALENS_ERR_ARG;
     try {
         ALENS_CUDA(cudaSetDevice(ctx->c.device));
+        g_allocStream = ctx->c.stream; // device allocations of this call are ordered on the context's stream
+        g_allocAsync = true;
         f(ctx->c);
         return ALENS_OK;
     } catch (const CudaError &e) {
@@ -78,6 +81,10 @@ int alens_create(int device, int rank, int nranks, alens_ctx **out) {
 
 void alens_destroy(alens_ctx *ctx) {
     if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaDeviceSynchronize();
+    commFree(ctx->c);
+    g_allocAsync = false; // the stream goes away: remaining buffers are released with cudaFree
     ctxFree(ctx->c);
     delete ctx;
 }
@@ -95,6 +102,7 @@ int alens_set_stream(alens_ctx *ctx, void *s) {
             ALENS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
             c.ownStream = true;
         }
+        g_allocStream = c.stream;
     });
 }
 
@@ -129,7 +137,8 @@ int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, con
             throw ArgError{ALENS_ERR_ARG, "alens_set_rods: null input"};
         cudaStream_t st = c.stream;
         ALENS_CUDA(cudaEventRecord(c.ev[0], st));
-        if (n != c.nRods) c.haveVelNC = false;
+        if (n != c.nLocal) c.haveVelNC = false;
+        c.nLocal = n;
         c.nRods = n;
         const size_t N = (size_t)n;
         c.uGid.reserve(N + 1); c.uPos.reserve(3 * N + 3); c.uQuat.reserve(4 * N + 4);
@@ -188,12 +197,12 @@ int alens_prepare_step(alens_ctx *ctx, int wrap) {
 
 int alens_set_velocity_noncon(alens_ctx *ctx, const double *v) {
     return guarded(ctx, [&](Context &c) {
-        if (!v || c.nRods == 0) {
+        if (!v || c.nLocal == 0) {
             c.haveVelNC = false;
             return;
         }
-        c.uVelNC.reserve(6 * (size_t)c.nRods);
-        ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, v, 48 * (size_t)c.nRods, cudaMemcpyHostToDevice, c.stream));
+        c.uVelNC.reserve(6 * (size_t)c.nRods + 6);
+        ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, v, 48 * (size_t)c.nLocal, cudaMemcpyHostToDevice, c.stream));
         ALENS_CUDA(cudaStreamSynchronize(c.stream));
         c.haveVelNC = true;
     });
@@ -205,8 +214,8 @@ int alens_set_profiling(alens_ctx *ctx, int on) {
 
 int alens_get_positions(alens_ctx *ctx, double *pos) {
     return guarded(ctx, [&](Context &c) {
-        if (c.nRods > 0) {
-            ALENS_CUDA(cudaMemcpyAsync(pos, c.uPos.p, 24 * (size_t)c.nRods, cudaMemcpyDeviceToHost, c.stream));
+        if (c.nLocal > 0) {
+            ALENS_CUDA(cudaMemcpyAsync(pos, c.uPos.p, 24 * (size_t)c.nLocal, cudaMemcpyDeviceToHost, c.stream));
             ALENS_CUDA(cudaStreamSynchronize(c.stream));
         }
     });
@@ -214,10 +223,10 @@ int alens_get_positions(alens_ctx *ctx, double *pos) {
 
 int alens_get_rod_state(alens_ctx *ctx, double *pos, double *quat) {
     return guarded(ctx, [&](Context &c) {
-        if (c.nRods > 0) {
-            if (pos) ALENS_CUDA(cudaMemcpyAsync(pos, c.uPos.p, 24 * (size_t)c.nRods, cudaMemcpyDeviceToHost, c.stream));
+        if (c.nLocal > 0) {
+            if (pos) ALENS_CUDA(cudaMemcpyAsync(pos, c.uPos.p, 24 * (size_t)c.nLocal, cudaMemcpyDeviceToHost, c.stream));
             if (quat)
-                ALENS_CUDA(cudaMemcpyAsync(quat, c.uQuat.p, 32 * (size_t)c.nRods, cudaMemcpyDeviceToHost, c.stream));
+                ALENS_CUDA(cudaMemcpyAsync(quat, c.uQuat.p, 32 * (size_t)c.nLocal, cudaMemcpyDeviceToHost, c.stream));
             ALENS_CUDA(cudaStreamSynchronize(c.stream));
         }
     });
@@ -338,7 +347,7 @@ int alens_get_gamma(alens_ctx *ctx, double *gamma, long long cap) {
 int alens_get_force_velocity(alens_ctx *ctx, double *fU, double *vU, double *fB, double *vB) {
     return guarded(ctx, [&](Context &c) {
         if (!c.haveSolution) throw ArgError{ALENS_ERR_STATE, "alens_get_force_velocity: no solution available"};
-        const size_t bytes = 48 * (size_t)c.nRods;
+        const size_t bytes = 48 * (size_t)c.nLocal;
         cudaStream_t st = c.stream;
         ALENS_CUDA(cudaEventRecord(c.ev[0], st));
         if (bytes) {
@@ -400,14 +409,74 @@ int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCand,
     });
 }
 
-int alens_comm_unique_id(void *id128) {
-    (void)id128;
-    return ALENS_ERR_UNSUPPORTED;
+/* ---- multi-GPU ---------------------------------------------------------------------------------- */
+int alens_set_decomposition(alens_ctx *ctx, int axis, double slabLow, double slabHigh, double skin,
+                            double maxBoundingRadius, int globalIndexBase) {
+    return guarded(ctx, [&](Context &c) {
+        if (axis < 0 || axis > 2 || !(slabHigh > slabLow) || !(skin >= 0) || !(maxBoundingRadius >= 0))
+            throw ArgError{ALENS_ERR_ARG, "alens_set_decomposition: bad arguments"};
+        c.slabAxis = axis;
+        c.slabLo = slabLow;
+        c.slabHi = slabHigh;
+        c.skin = skin;
+        c.maxRadiusGlobal = maxBoundingRadius;
+        c.globalBase = globalIndexBase;
+    });
 }
-int alens_comm_init(alens_ctx *ctx, const void *id128) {
-    (void)id128;
-    if (ctx) ctx->c.err = "multi-GPU communicator not built in this configuration";
-    return ALENS_ERR_UNSUPPORTED;
+
+int alens_comm_create(alens_ctx *ctx, long long maxLocalRods) {
+    return guarded(ctx, [&](Context &c) {
+        if (maxLocalRods < 1) throw ArgError{ALENS_ERR_ARG, "alens_comm_create: maxLocalRods < 1"};
+        commAllocWindow(c, maxLocalRods);
+    });
+}
+
+int alens_comm_blob_size(void) { return (int)sizeof(CommBlob); }
+
+int alens_comm_export(alens_ctx *ctx, void *blob) {
+    return guarded(ctx, [&](Context &c) {
+        if (!c.comm.win || !blob) throw ArgError{ALENS_ERR_STATE, "alens_comm_export: call alens_comm_create first"};
+        commExport(c, blob);
+    });
+}
+
+int alens_comm_connect(alens_ctx *ctx, const void *blobsInRankOrder) {
+    return guarded(ctx, [&](Context &c) {
+        if (!c.comm.win || !blobsInRankOrder) throw ArgError{ALENS_ERR_STATE, "alens_comm_connect: call alens_comm_create first"};
+        if (!c.haveBox) throw ArgError{ALENS_ERR_STATE, "alens_comm_connect: call alens_set_domain first"};
+        commImport(c, blobsInRankOrder);
+    });
+}
+
+int alens_comm_connect_local(alens_ctx **ctxs, int n) {
+    if (!ctxs || n < 1) return ALENS_ERR_ARG;
+    std::vector<Context *> v;
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i] || !ctxs[i]->c.comm.win || !ctxs[i]->c.haveBox) return ALENS_ERR_STATE;
+        v.push_back(&ctxs[i]->c);
+    }
+    try {
+        commConnectLocal(v.data(), n);
+        return ALENS_OK;
+    } catch (const CudaError &e) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) in `%s` at %s:%d", (int)e.code, cudaGetErrorString(e.code),
+                 e.what, e.file, e.line);
+        ctxs[0]->c.err = buf;
+        cudaGetLastError();
+        return ALENS_ERR_CUDA;
+    } catch (const ArgError &e) {
+        ctxs[0]->c.err = e.msg;
+        return e.code;
+    }
+}
+
+int alens_num_ghosts(alens_ctx *ctx, int *nGhost, int *nSentLeft, int *nSentRight) {
+    return guarded(ctx, [&](Context &c) {
+        if (nGhost) *nGhost = c.nGhost;
+        if (nSentLeft) *nSentLeft = c.comm.nSend[0];
+        if (nSentRight) *nSentRight = c.comm.nSend[1];
+    });
 }
 
 } // extern "C"

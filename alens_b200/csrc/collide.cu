@@ -37,7 +37,7 @@ static constexpr int kQueue = 64;  // compaction queue entries per warp
 // ------------------------------------------------------------------------------------------------
 // rod_pack: applyBoxBC (FDPS/particle_system.hpp:798-843) + cell id + histogram
 __global__ void k_rod_pack(int n, double *__restrict__ pos, Box box, CellGrid g, int wrap, int *__restrict__ cellOf,
-                           int *__restrict__ cellCount) {
+                           int *__restrict__ cellCount, const signed char *__restrict__ img) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double p[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
@@ -55,7 +55,8 @@ __global__ void k_rod_pack(int n, double *__restrict__ pos, Box box, CellGrid g,
             }
             p[k] = x;
         }
-        int ci = (int)floor((x - box.lo[k]) * g.inv[k]);
+        if (k == g.axis && img) x += img[i] * g.axisLen; // a ghost is binned where it appears in this slab's frame
+        int ci = (int)floor((x - g.lo[k]) * g.inv[k]);
         ci = ci < 0 ? 0 : (ci >= g.n[k] ? g.n[k] - 1 : ci);
         c[k] = ci;
     }
@@ -67,6 +68,36 @@ __global__ void k_rod_pack(int n, double *__restrict__ pos, Box box, CellGrid g,
     const int cell = (c[2] * g.n[1] + c[1]) * g.n[0] + c[0];
     cellOf[i] = cell;
     atomicAdd(&cellCount[cell], 1);
+}
+
+// applyBoxBC alone (multi-rank: the owned rods are wrapped before the ghost exchange)
+__global__ void k_rod_wrap(int n, double *__restrict__ pos, Box box) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double x = pos[3 * i + k];
+        const double len = box.len[k];
+        if (len > 0 && isfinite(x)) {
+            if (fabs(x - box.lo[k]) > 64.0 * len) x = box.lo[k] + fmod(x - box.lo[k], len);
+            while (x < box.lo[k]) x += len;
+            while (x >= box.hi[k]) x -= len;
+            if (x == box.hi[k]) x = box.lo[k];
+        }
+        pos[3 * i + k] = x;
+    }
+}
+__global__ void k_global_index(int n, int base, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = base + i;
+}
+// rods that left their slab by more than the skin (the host has to migrate them)
+__global__ void k_count_strays(int n, const double *__restrict__ pos, int axis, double lo, double hi, double skin,
+                               int *__restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = pos[3 * (size_t)i + axis];
+    if (x < lo - skin || x >= hi + skin) atomicAdd(count, 1);
 }
 
 // single-CTA exclusive scan; out has n+1 entries (out[n] = total).  Used for short arrays and for the
@@ -163,10 +194,13 @@ struct RodArrays {
     const int *uGid;
     const double *uPos, *uQuat, *uLen, *uRad;
     const unsigned char *uImm;
+    const signed char *uImg;
+    int nLocal;
     // sorted outputs
     int *sUser, *sGid, *userToSorted;
     double *sX, *sY, *sZ, *sDx, *sDy, *sDz, *sLc, *sRc, *sLen, *sRad;
-    unsigned char *sImm;
+    unsigned char *sImm, *sGhost;
+    signed char *sImg;
     float *bUx, *bUy, *bUz, *bH, *bRho;
 };
 
@@ -206,6 +240,8 @@ __global__ void k_cell_order(int ncell, const int *__restrict__ cellStart, const
         a.sLc[s] = lc;
         a.sRc[s] = rc;
         a.sImm[s] = a.uImm ? a.uImm[u] : 0;
+        a.sGhost[s] = u >= a.nLocal ? 1 : 0;
+        a.sImg[s] = a.uImg[u];
         // broad-phase shape (axis segment of half length h around the centre, thickened by rho): a rod with
         // lc < 2 rc collides as a sphere of radius lc/2 + rc (SylinderNear.hpp:241,259).  The axis is
         // normalised here so that a non-unit quaternion cannot make the capsule tests optimistic.
@@ -227,11 +263,13 @@ struct PairIn {
     const int *sGid;
     const double *sX, *sY, *sZ, *sDx, *sDy, *sDz, *sLc, *sRc;
     const float *bUx, *bUy, *bUz, *bH, *bRho;
+    const signed char *sImg;      // image along the slab axis (0 on a single rank)
+    const unsigned char *sGhost;
 };
 struct PairOut {
     int *idxI, *idxJ, *gidI, *gidJ;
     signed char *shift;
-    unsigned char *bi, *oneSide;
+    unsigned char *bi, *oneSide, *own;
     double *delta0, *gamma0, *invKappa, *kappa;
     double *n, *pI, *pJ, *labI, *labJ; // [3][stride]
     size_t stride;
@@ -301,7 +339,9 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
     __shared__ double sP[kWarpsPerCta][4][kITile]; // x, y, z, A = h + rho + colBuf (+ rounding slack)
     __shared__ float sF[kWarpsPerCta][5][kITile];  // ux, uy, uz, h, B = rho + colBuf (+ slack)
     __shared__ int sQ[kWarpsPerCta][3][kQueue];    // queue: i, j, image code
+    __shared__ signed char sG[kWarpsPerCta][kITile]; // target: image along the slab axis, +64 if ghost
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int axMul = g.axis == 0 ? 1 : (g.axis == 1 ? 3 : (g.axis == 2 ? 9 : 0));
     const int cell = blockIdx.x * kWarpsPerCta + w;
     if (cell >= g.ncell) return;
     const int ib = in.cellStart[cell], ie = in.cellStart[cell + 1];
@@ -322,7 +362,13 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
         __syncwarp();
         for (int m = lane; m < nI; m += 32) {
             const int s = i0 + m;
-            const double x = in.sX[s], y = in.sY[s], z = in.sZ[s];
+            double x = in.sX[s], y = in.sY[s], z = in.sZ[s];
+            const int im = in.sImg[s];
+            sG[w][m] = (signed char)(im + (in.sGhost[s] ? 64 : 0));
+            if (im) { // apparent position in this slab's frame
+                const double sh = im * g.axisLen;
+                if (g.axis == 0) x += sh; else if (g.axis == 1) y += sh; else z += sh;
+            }
             const float h = in.bH[s], rho = in.bRho[s];
             // absolute slack: rounding of coordinate differences in the narrow phase
             const double sl = 256.0 * DBL_EPSILON * (fabs(x) + fabs(y) + fabs(z) + box.len[0] + box.len[1] + box.len[2]);
@@ -342,17 +388,17 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
             const int dz = row < 2 ? 0 : 1;
             int oy = cy + dy, oz = cz + dz, ky = 0, kz = 0;
             bool ok = true;
-            if (oy < 0) { ok = ok && box.pbc[1]; oy += g.n[1]; ky = -1; }
-            else if (oy >= g.n[1]) { ok = ok && box.pbc[1]; oy -= g.n[1]; ky = 1; }
-            if (oz >= g.n[2]) { ok = ok && box.pbc[2]; oz -= g.n[2]; kz = 1; }
+            if (oy < 0) { ok = ok && g.per[1]; oy += g.n[1]; ky = -1; }
+            else if (oy >= g.n[1]) { ok = ok && g.per[1]; oy -= g.n[1]; ky = 1; }
+            if (oz >= g.n[2]) { ok = ok && g.per[2]; oz -= g.n[2]; kz = 1; }
             if (!ok) continue;
             const int rowBase = (oz * g.n[1] + oy) * g.n[0];
             const int xlo = row == 0 ? cx : cx - 1, xhi = cx + 1;
             for (int seg = 0; seg < 3; seg++) {
                 int ca, cb, kx; // cell range [ca, cb] of this row, image in x
                 if (seg == 0) { ca = max(xlo, 0); cb = min(xhi, g.n[0] - 1); kx = 0; }
-                else if (seg == 1) { if (xlo >= 0 || !box.pbc[0]) continue; ca = cb = g.n[0] - 1; kx = -1; }
-                else { if (xhi < g.n[0] || !box.pbc[0]) continue; ca = cb = 0; kx = 1; }
+                else if (seg == 1) { if (xlo >= 0 || !g.per[0]) continue; ca = cb = g.n[0] - 1; kx = -1; }
+                else { if (xhi < g.n[0] || !g.per[0]) continue; ca = cb = 0; kx = 1; }
                 const int jb = in.cellStart[rowBase + ca], je = in.cellStart[rowBase + cb + 1];
                 if (jb == je) continue;
                 const int code = (kx + 1) + 3 * (ky + 1) + 9 * (kz + 1);
@@ -363,10 +409,17 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                     const bool jv = sj < je;
                     double xj = 0, yj = 0, zj = 0, Sj = 0;
                     float ujx = 0, ujy = 0, ujz = 1, hj = 0, rj = 0, SjF = 0;
+                    int gj = 0; // image along the slab axis, +64 if ghost
                     if (jv) {
                         xj = in.sX[sj] + shx;
                         yj = in.sY[sj] + shy;
                         zj = in.sZ[sj] + shz;
+                        const int im = in.sImg[sj];
+                        gj = im + (in.sGhost[sj] ? 64 : 0);
+                        if (im) {
+                            const double sh = im * g.axisLen;
+                            if (g.axis == 0) xj += sh; else if (g.axis == 1) yj += sh; else zj += sh;
+                        }
                         hj = in.bH[sj];
                         rj = in.bRho[sj];
                         ujx = in.bUx[sj]; ujy = in.bUy[sj]; ujz = in.bUz[sj];
@@ -376,6 +429,8 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                     for (int m = 0; m < nI; m++) {
                         const int si = i0 + m;
                         bool pass = jv && (own ? (sj > si) : (sj != si)); // a rod never pairs with its own image
+                        const int gi = sG[w][m];
+                        pass = pass && !(gi >= 32 && gj >= 32); // two ghosts: not this rank's constraint
                         const double ddx = xj - sP[w][0][m], ddy = yj - sP[w][1][m], ddz = zj - sP[w][2][m];
                         const double cut = sP[w][3][m] + Sj;
                         pass = pass && ((ddx * ddx + ddy * ddy + ddz * ddz) <= cut * cut * slack);
@@ -403,7 +458,8 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                             const int p = qn + __popc(msk & ((1u << lane) - 1));
                             qi[p] = si;
                             qj[p] = sj;
-                            qs[p] = code;
+                            // image of j relative to i: cell wrap + difference of the ghost images
+                            qs[p] = code + (((gj + 32) & 63) - ((gi + 32) & 63)) * axMul;
                         }
                         qn += __popc(msk);
                         nCand += __popc(msk);
@@ -457,6 +513,7 @@ k_pairs_emit(long long nHits, const int4 *__restrict__ hitList, const int *__res
     out.shift[k] = (signed char)code;
     out.bi[k] = 0;
     out.oneSide[k] = 0;
+    out.own[k] = in.sGhost[si] ? 0 : 1; // the owner of rod I counts the row in global reductions
     out.delta0[k] = ct.sep;
     out.gamma0[k] = ct.sep < 0 ? -ct.sep : 0;
     out.invKappa[k] = 0;
@@ -491,6 +548,14 @@ void ctxInit(Context &c) {
     ALENS_CUDA(cudaDeviceGetAttribute(&c.numSMs, cudaDevAttrMultiProcessorCount, c.device));
     ALENS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     c.ownStream = true;
+    {
+        cudaMemPool_t pool;
+        ALENS_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
+        unsigned long long keep = ~0ULL; // grow-only buffers: never hand memory back to the driver
+        ALENS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    g_allocStream = c.stream;
+    g_allocAsync = true;
     for (auto &e : c.ev) ALENS_CUDA(cudaEventCreate(&e));
     c.dScal.reserve(1);
     ALENS_CUDA(cudaMemset(c.dScal.p, 0, sizeof(SolverScalars)));
@@ -512,9 +577,21 @@ static void chooseGrid(Context &c, double maxR) {
     CellGrid &g = c.grid;
     g.cutoff = (2 * maxR + c.colBuf) * (1.0 + 1e-9);
     if (!(g.cutoff > 0)) g.cutoff = 1.0;
+    const bool multi = c.comm.active;
+    g.axis = multi ? c.slabAxis : -1;
+    g.axisLen = multi ? c.box.len[c.slabAxis] : 0.0;
+    double ext[3];
     long long total = 1;
     for (int k = 0; k < 3; k++) {
-        double m = std::floor(c.box.len[k] / g.cutoff);
+        ext[k] = c.box.len[k];
+        g.lo[k] = c.box.lo[k];
+        g.per[k] = c.box.pbc[k];
+        if (multi && k == c.slabAxis) { // the slab plus a ghost layer on both sides; images come as ghost rods
+            ext[k] = (c.slabHi - c.slabLo) + 2 * c.ghostWidth;
+            g.lo[k] = c.slabLo - c.ghostWidth;
+            g.per[k] = 0;
+        }
+        double m = std::floor(ext[k] / g.cutoff);
         if (!(m >= 1)) m = 1;
         if (m > 1024) m = 1024;
         g.n[k] = (int)m;
@@ -531,7 +608,7 @@ static void chooseGrid(Context &c, double maxR) {
         total *= g.n[k];
     }
     g.ncell = (int)total;
-    for (int k = 0; k < 3; k++) g.inv[k] = c.box.len[k] > 0 ? g.n[k] / c.box.len[k] : 0.0;
+    for (int k = 0; k < 3; k++) g.inv[k] = ext[k] > 0 ? g.n[k] / ext[k] : 0.0;
 }
 
 // host: max bounding radius; called with the host arrays at upload time
@@ -545,11 +622,42 @@ double hostMaxRadius(int n, const double *len, const double *rad, double lRatio,
 }
 
 double g_lastMaxR = 0; // set by the C API before rodsUploaded (single-threaded boundary)
+thread_local cudaStream_t g_allocStream = nullptr;
+thread_local bool g_allocAsync = false;
 
 void rodsUploaded(Context &c, bool wrap) {
-    const int n = c.nRods;
     cudaStream_t st = c.stream;
-    chooseGrid(c, g_lastMaxR);
+    const bool multi = c.comm.active;
+    c.nRods = c.nLocal;
+    c.nGhost = 0;
+    {
+        const size_t NL = (size_t)c.nLocal;
+        c.uImg.reserve(NL + 1);
+        c.uGlobalIdx.reserve(NL + 1);
+        ALENS_CUDA(cudaMemsetAsync(c.uImg.p, 0, NL + 1, st));
+        if (c.nLocal > 0) k_global_index<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.globalBase, c.uGlobalIdx.p);
+    }
+    double maxR = g_lastMaxR;
+    if (multi) {
+        c.ghostWidth = (2 * c.maxRadiusGlobal + c.colBuf) * (1.0 + 1e-9) + c.skin;
+        if (c.slabHi - c.slabLo < 2 * c.ghostWidth)
+            throw ArgError{ALENS_ERR_ARG, "slab decomposition: a slab must be at least 2 x (cutoff + skin) wide"};
+        // owned rods are wrapped first, then the neighbours' rods near my faces are appended as ghosts
+        if (wrap && c.nLocal > 0) k_rod_wrap<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.uPos.p, c.box);
+        ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 4 * sizeof(unsigned long long), st));
+        if (c.nLocal > 0)
+            k_count_strays<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.uPos.p, c.slabAxis, c.slabLo, c.slabHi,
+                                                                  c.skin, reinterpret_cast<int *>(c.dCounters.p));
+        int strays = 0;
+        ALENS_CUDA(cudaMemcpyAsync(&strays, c.dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        c.strays = strays;
+        commExchangeGhosts(c); // sets nRods = nLocal + nGhost (collective; strays are reported afterwards)
+        wrap = false;
+        maxR = c.maxRadiusGlobal;
+    }
+    const int n = c.nRods;
+    chooseGrid(c, maxR);
     const CellGrid g = c.grid;
     c.uCell.reserve(n);
     c.userToSorted.reserve(n);
@@ -560,27 +668,29 @@ void rodsUploaded(Context &c, bool wrap) {
     c.sX.reserve(n); c.sY.reserve(n); c.sZ.reserve(n);
     c.sDx.reserve(n + 2); c.sDy.reserve(n + 2); c.sDz.reserve(n + 2); // +2: 16-byte bulk copies over-read
     c.sLc.reserve(n); c.sRc.reserve(n); c.sLen.reserve(n); c.sRad.reserve(n);
-    c.sImm.reserve(n);
+    c.sImm.reserve(n); c.sGhost.reserve(n); c.sImg.reserve(n);
     c.bUx.reserve(n); c.bUy.reserve(n); c.bUz.reserve(n); c.bH.reserve(n); c.bRho.reserve(n);
     DevBuf<int> &order = c.incFill; // scratch (rebuilt later by setup)
     order.reserve(n + 1);
     ALENS_CUDA(cudaMemsetAsync(c.cellCount.p, 0, sizeof(int) * (g.ncell + 1), st));
     ALENS_CUDA(cudaMemsetAsync(c.cellFill.p, 0, sizeof(int) * (g.ncell + 1), st));
     if (n > 0) {
-        k_rod_pack<<<gridFor(n, 256), 256, 0, st>>>(n, c.uPos.p, c.box, g, wrap ? 1 : 0, c.uCell.p, c.cellCount.p);
+        k_rod_pack<<<gridFor(n, 256), 256, 0, st>>>(n, c.uPos.p, c.box, g, wrap ? 1 : 0, c.uCell.p, c.cellCount.p,
+                                                    c.uImg.p);
         c.launches++;
     }
     launchScanInt(c, c.cellCount.p, c.cellStart.p, g.ncell);
     if (n > 0) {
         k_cell_scatter<<<gridFor(n, 256), 256, 0, st>>>(n, c.uCell.p, c.cellStart.p, c.cellFill.p, order.p);
-        RodArrays a{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.sUser.p, c.sGid.p,
-                    c.userToSorted.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLc.p, c.sRc.p,
-                    c.sLen.p, c.sRad.p, c.sImm.p, c.bUx.p, c.bUy.p, c.bUz.p, c.bH.p, c.bRho.p};
+        RodArrays a{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.uImg.p, c.nLocal, c.sUser.p,
+                    c.sGid.p, c.userToSorted.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLc.p, c.sRc.p,
+                    c.sLen.p, c.sRad.p, c.sImm.p, c.sGhost.p, c.sImg.p, c.bUx.p, c.bUy.p, c.bUz.p, c.bH.p, c.bRho.p};
         k_cell_order<<<gridFor((long long)g.ncell * 32, 128), 128, 0, st>>>(g.ncell, c.cellStart.p, order.p, a,
                                                                             c.dRatio, c.lRatio);
         c.launches += 2;
     }
     ALENS_CUDA(cudaGetLastError());
+    if (multi) commExchangeGhostIndices(c);
     c.sorted = true;
     c.haveMob = false;
     c.haveSetup = false;
@@ -588,6 +698,8 @@ void rodsUploaded(Context &c, bool wrap) {
     c.nCon = c.nColl = 0;
     c.nOneSide = c.nBilateral = 0;
     c.hostBlocks.clear();
+    if (multi && c.strays > 0)
+        throw ArgError{ALENS_ERR_STATE, "a rod left its slab by more than the skin: redistribute the rods (alens_get_rod_state / alens_set_rods)"};
 }
 
 void reserveConstraints(Context &c, size_t n, bool keep) {
@@ -599,29 +711,25 @@ void reserveConstraints(Context &c, size_t n, bool keep) {
     cudaStream_t st = c.stream;
     auto grow1 = [&](auto &buf, size_t comps) {
         using T = std::remove_pointer_t<decltype(buf.p)>;
-        T *np = nullptr;
-        ALENS_CUDA(cudaMalloc(&np, ncap * comps * sizeof(T)));
+        T *np = static_cast<T *>(devAlloc(ncap * comps * sizeof(T)));
         if (live && buf.p)
             for (size_t k = 0; k < comps; k++)
                 ALENS_CUDA(cudaMemcpyAsync(np + k * ncap, buf.p + k * old, live * sizeof(T), cudaMemcpyDeviceToDevice,
                                            st));
-        if (buf.p) {
-            ALENS_CUDA(cudaStreamSynchronize(st));
-            cudaFree(buf.p);
-        }
+        devFree(buf.p);
         buf.p = np;
         buf.cap = ncap * comps;
     };
     grow1(c.cIdxI, 1); grow1(c.cIdxJ, 1); grow1(c.cGidI, 1); grow1(c.cGidJ, 1);
     grow1(c.cN, 3); grow1(c.cPI, 3); grow1(c.cPJ, 3); grow1(c.cLabI, 3); grow1(c.cLabJ, 3);
     grow1(c.cDelta0, 1); grow1(c.cGamma0, 1); grow1(c.cInvKappa, 1); grow1(c.cKappa, 1);
-    grow1(c.cBi, 1); grow1(c.cOneSide, 1); grow1(c.cShift, 1);
+    grow1(c.cBi, 1); grow1(c.cOneSide, 1); grow1(c.cShift, 1); grow1(c.cOwn, 1);
     c.conCap = ncap;
 }
 
 static PairIn pairIn(Context &c) {
     return PairIn{c.cellStart.p, c.sGid.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLc.p, c.sRc.p,
-                  c.bUx.p, c.bUy.p, c.bUz.p, c.bH.p, c.bRho.p};
+                  c.bUx.p, c.bUy.p, c.bUz.p, c.bH.p, c.bRho.p, c.sImg.p, c.sGhost.p};
 }
 
 void collectPairs(Context &c) {
@@ -656,7 +764,7 @@ void collectPairs(Context &c) {
     if (total > 0x7fffffffLL) throw ArgError{ALENS_ERR_UNSUPPORTED, "collect: more than 2^31 constraints on one GPU"};
     reserveConstraints(c, (size_t)total, false);
     if (total > 0) {
-        PairOut out{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cDelta0.p,
+        PairOut out{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cOwn.p, c.cDelta0.p,
                     c.cGamma0.p, c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
         k_pairs_emit<<<gridFor(total, 128), 128, 0, st>>>(total, c.hitList.p, c.cellHitStart.p, pairIn(c), out, c.box,
                                                           c.colBuf);
@@ -664,6 +772,23 @@ void collectPairs(Context &c) {
     }
     ALENS_CUDA(cudaGetLastError());
     c.nCon = c.nColl = total;
+}
+
+// Force the (lazily loaded) kernels of this file into the context now: loading a kernel at its first launch can
+// synchronise the context, which deadlocks against a peer rank's waiting kernel when two ranks share one GPU.
+void preloadCollideKernels() {
+    cudaFuncAttributes a;
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_pack));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_wrap));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_global_index));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_count_strays));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_scan_int));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_scan_tile_sums));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_scan_tile_apply));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_cell_scatter));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_cell_order));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_pairs_find));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_pairs_emit));
 }
 
 } // namespace alens

@@ -30,28 +30,46 @@ struct ArgError {
     std::string msg;
 };
 
+// Stream all device allocations of the calling thread are ordered on (set at every C-API entry).  Stream-ordered
+// allocation (cudaMallocAsync / cudaFreeAsync) never synchronises the whole device -- cudaFree does, which would
+// deadlock two ranks that share one GPU (tests) while one of them waits in a kernel for the other.
+extern thread_local cudaStream_t g_allocStream;
+extern thread_local bool g_allocAsync;
+
+inline void *devAlloc(size_t bytes) {
+    void *p = nullptr;
+    if (g_allocAsync) ALENS_CUDA(cudaMallocAsync(&p, bytes, g_allocStream));
+    else ALENS_CUDA(cudaMalloc(&p, bytes));
+    return p;
+}
+inline void devFree(void *p) {
+    if (!p) return;
+    if (g_allocAsync) cudaFreeAsync(p, g_allocStream);
+    else cudaFree(p);
+}
+
 // grow-only device array
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
+    bool external = false; // memory owned elsewhere (a region of the communication window): fixed capacity
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p && !external) devFree(p);
         p = nullptr;
         cap = 0;
+        external = false;
     }
-    // contents are NOT preserved on growth unless keep=true
-    void reserve(size_t n, cudaStream_t st = 0, bool keep = false, size_t keepN = 0) {
+    // contents are NOT preserved on growth unless keep=true; everything is ordered on the context's stream
+    void reserve(size_t n, cudaStream_t = 0, bool keep = false, size_t keepN = 0) {
         if (n <= cap) return;
+        if (external) throw ArgError{ALENS_ERR_COMM, "buffer inside the communication window is too small"};
         size_t ncap = n + n / 4 + 64;
-        T *np = nullptr;
-        ALENS_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
-        if (keep && p && keepN) ALENS_CUDA(cudaMemcpyAsync(np, p, keepN * sizeof(T), cudaMemcpyDeviceToDevice, st));
-        if (p) {
-            ALENS_CUDA(cudaStreamSynchronize(st));
-            cudaFree(p);
-        }
+        T *np = static_cast<T *>(devAlloc(ncap * sizeof(T)));
+        if (keep && p && keepN)
+            ALENS_CUDA(cudaMemcpyAsync(np, p, keepN * sizeof(T), cudaMemcpyDeviceToDevice, g_allocStream));
+        devFree(p);
         p = np;
         cap = ncap;
     }
@@ -82,8 +100,12 @@ struct Box {
 struct CellGrid {
     int n[3];       // cells per axis
     int ncell;      // product
-    double inv[3];  // n[k] / len[k]
+    double inv[3];  // n[k] / extent[k]
     double cutoff;
+    double lo[3];   // origin (box low corner; along the slab axis: slab low face - ghost width)
+    int per[3];     // neighbour cells wrap around (periodic axis of a box the grid spans completely)
+    int axis;       // slab axis (-1: single rank)
+    double axisLen; // box length along the slab axis
 };
 
 // scalar block shared between the BCQP kernels (lives in device memory, mirrored to pinned host)
@@ -99,6 +121,58 @@ struct SolverScalars {
     int pad_;
 };
 
+// ---- multi-GPU (comm.cu) ----------------------------------------------------------------------
+static constexpr int kMaxRanks = 16;
+static constexpr int kGhostRec = 17; // doubles per ghost record
+
+// start of every rank's window; every word below is written by a PEER (remote store) and polled locally
+struct CommHeader {
+    unsigned long long chanSeq[2]; // ghost payload arrived from my left / right neighbour
+    long long chanCount[2];
+    unsigned long long ackSeq[2];  // sorted indices of the rods I mirrored on my left / right neighbour arrived
+    unsigned long long haloSeq[2]; // ghost rows of U pushed by my left / right neighbour
+    unsigned long long vecSeq[2];  // ghost rows of velNonCon pushed
+    unsigned long long mailSeq[2][kMaxRanks]; // [parity][source rank]
+    double mail[2][kMaxRanks][4];             // BBPGD partial sums {dx.dx, dx.dg, dg.dg, max |q|}
+    int error;                                // set by a waiter that timed out
+};
+
+struct CommBlob { // what a rank publishes to its peers (multi-process bootstrap)
+    cudaIpcMemHandle_t handle;
+    unsigned long long bytes;
+    int device, rank;
+};
+
+struct GhostSrc {
+    const int *gid;
+    const double *pos, *quat, *len, *rad;
+    const unsigned char *imm;
+    const double *velNC;
+    int globalBase;
+};
+struct GhostDst {
+    int *gid;
+    double *pos, *quat, *len, *rad;
+    unsigned char *imm;
+    signed char *img;
+    int *globalIdx;
+    double *velNC;
+};
+
+struct Comm {
+    bool active = false;
+    int left = -1, right = -1; // neighbour ranks along the slab axis (-1 = none)
+    unsigned char *win = nullptr;
+    size_t winBytes = 0;
+    unsigned char *peerWin[kMaxRanks] = {};
+    bool ipcMapped[kMaxRanks] = {};
+    size_t offChan[2] = {}, offAck[2] = {}, offU = 0, capGhost = 0, capRods = 0;
+    unsigned long long seqGhost = 0, seqAck = 0, seqVec = 0, seqHalo = 0, seqMail = 0; // lockstep counters
+    DevBuf<int> sendIdx[2];    // user index of my rods mirrored on the left / right neighbour
+    DevBuf<int> sendSorted[2]; // their sorted index (source rows of the U halo)
+    int nSend[2] = {0, 0}, nRecv[2] = {0, 0};
+};
+
 struct Context {
     int device = 0, rank = 0, nranks = 1;
     int numSMs = 148;
@@ -112,8 +186,22 @@ struct Context {
     double viscosity = 0.0;
     bool haveMob = false;
 
-    // ---- rods, user order (what the host uploaded) ----
-    int nRods = 0;
+    // ---- slab decomposition (nranks > 1) ----
+    Comm comm;
+    int slabAxis = 0;
+    double slabLo = 0, slabHi = 0; // my slab along slabAxis
+    double skin = 0;               // how far a rod may stray outside its owner's slab
+    double ghostWidth = 0;         // cutoff + skin
+    double maxRadiusGlobal = 0;    // max over ALL ranks of lengthCollision/2 + radiusCollision (sets the cell size)
+    int strays = 0;
+    int globalBase = 0;            // global index of my first rod (updateSylinderMap, SylinderSystem.cpp:868-880)
+
+    // ---- rods, user order (what the host uploaded; ghosts appended behind the nLocal owned rods) ----
+    int nRods = 0;  // owned + ghost rods: what the kernels see
+    int nLocal = 0; // owned rods: what the caller sees
+    int nGhost = 0;
+    DevBuf<signed char> uImg; // image of a ghost along the slab axis (-1, 0, +1); 0 for owned rods
+    DevBuf<int> uGlobalIdx;   // global index (owner's numbering)
     DevBuf<int> uGid;
     DevBuf<double> uPos, uQuat, uLen, uRad; // 3n, 4n, n, n
     DevBuf<unsigned char> uImm;
@@ -132,6 +220,8 @@ struct Context {
     DevBuf<double> sLen, sRad;                           // hydrodynamic length/radius
     DevBuf<float> bUx, bUy, bUz, bH, bRho;               // broad phase: unit axis, half length, radius (fp32)
     DevBuf<unsigned char> sImm;
+    DevBuf<unsigned char> sGhost; // 1 = ghost rod (owned by a neighbour rank)
+    DevBuf<signed char> sImg;     // image along the slab axis
     DevBuf<double> sInvDrag; // 3 per rod: 1/para, 1/perp, 1/rot (0 if immovable)
     bool sorted = false;
 
@@ -146,6 +236,7 @@ struct Context {
     DevBuf<double> cDelta0, cGamma0, cInvKappa; // invKappa = 1/kappa (not yet /dt)
     DevBuf<double> cKappa;
     DevBuf<unsigned char> cBi, cOneSide;
+    DevBuf<unsigned char> cOwn; // 1 = this rank counts the row in global dot products (owner of rod I)
     DevBuf<signed char> cShift; // image of J relative to I, code = (kx+1)+3(ky+1)+9(kz+1)
     DevBuf<double> cStressHost; // 9 per appended block (host supplied), indexed k - nColl
     size_t conCap = 0;          // component stride of the SoA arrays
@@ -215,6 +306,20 @@ void solveCore(Context &c, double tol, int maxIte, int choice);
 void stepEuler(Context &c, double dt);
 void profFlush(Context &c);
 double timeKernel(Context &c, int which, int reps);
+void preloadCollideKernels();
+void preloadSolverKernels();
+void preloadBlockKernels();
+void preloadCommKernels();
+// comm.cu
+void commAllocWindow(Context &c, long long maxLocalRods);
+void commExport(Context &c, void *blob);
+void commImport(Context &c, const void *blobs);
+void commConnectLocal(Context **ctxs, int n);
+void commFree(Context &c);
+void commExchangeGhosts(Context &c);
+void commExchangeGhostIndices(Context &c);
+void commHaloVelNC(Context &c);
+void commPushU(Context &c, unsigned long long seq);
 void reserveConstraints(Context &c, size_t n, bool keep);
 
 inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }

@@ -13,6 +13,7 @@
 //                 deterministic two-level reduction, step-size/termination logic in the last CTA
 // Compiled with -fmad=false so that elementwise arithmetic rounds like the CPU restatement.
 #include "context.hpp"
+#include "comm_dev.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -57,6 +58,7 @@ struct MobIn {
     const double *invDrag;      // [3][stride]
     int n;
     size_t stride;              // even (16-byte aligned component arrays)
+    const unsigned char *ghost; // 1 = rod owned by a neighbour rank: its U row arrives through the halo
 };
 
 // u = M f with Mtt = qq^T/zPara + (I - qq^T)/zPerp, Mrr = I/zRot (SylinderSystem.cpp:664-665)
@@ -87,21 +89,22 @@ __global__ void k_mob_apply_user(MobIn m, const int *__restrict__ userToSorted, 
 // ------------------------------------------------------------------------------------------------
 // incidence rod -> constraints (replaces the explicit transpose of ConstraintOperator.cpp:14-20)
 __global__ void k_inc_count(long long nc, const int *__restrict__ idxI, const int *__restrict__ idxJ,
-                            int *__restrict__ deg) {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nc) return;
-    atomicAdd(&deg[idxI[k]], 1);
-    const int j = idxJ[k];
-    if (j >= 0) atomicAdd(&deg[j], 1);
-}
-
-__global__ void k_inc_fill(long long nc, const int *__restrict__ idxI, const int *__restrict__ idxJ,
-                           const int *__restrict__ start, int *__restrict__ fill, int *__restrict__ incCon) {
+                            const unsigned char *__restrict__ ghost, int *__restrict__ deg) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nc) return;
     const int i = idxI[k], j = idxJ[k];
-    incCon[start[i] + atomicAdd(&fill[i], 1)] = (int)(2 * k);
-    if (j >= 0) incCon[start[j] + atomicAdd(&fill[j], 1)] = (int)(2 * k + 1);
+    if (!ghost[i]) atomicAdd(&deg[i], 1); // ghost rods get no slots: their force/velocity is the owner's business
+    if (j >= 0 && !ghost[j]) atomicAdd(&deg[j], 1);
+}
+
+__global__ void k_inc_fill(long long nc, const int *__restrict__ idxI, const int *__restrict__ idxJ,
+                           const unsigned char *__restrict__ ghost, const int *__restrict__ start,
+                           int *__restrict__ fill, int *__restrict__ incCon) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    const int i = idxI[k], j = idxJ[k];
+    if (!ghost[i]) incCon[start[i] + atomicAdd(&fill[i], 1)] = (int)(2 * k);
+    if (j >= 0 && !ghost[j]) incCon[start[j] + atomicAdd(&fill[j], 1)] = (int)(2 * k + 1);
 }
 
 struct ConGeom {
@@ -532,7 +535,7 @@ k_force_vel_lm(FvIn in, MobIn mob, const double *__restrict__ x, const double *_
             con[q] = conN[q];
         }
     }
-    if (!act) return;
+    if (!act || mob.ghost[r]) return;
     const double qf = qx * f[0] + qy * f[1] + qz * f[2];
     const double px = qf * qx, py = qf * qy, pz = qf * qz;
     double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
@@ -655,6 +658,8 @@ struct BbTail {
     int histCap;
     double tol;
     int ite; // iteration number of this launch (0 = initial gradient)
+    const unsigned char *own; // multi-rank: 1 = this rank counts the row in the dot products (nullptr = all)
+    double *redOut;           // multi-rank: the reduced partials go here, k_bb_reduce finishes the step
 };
 
 // last-CTA epilogue shared by the BBPGD tail kernels: fixed-order reduction of the per-CTA partials, then the
@@ -747,7 +752,7 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
         int err = 0;
         const double q = projGrad(cur.x, gk, cur.lbf, err);
         mx = fmax(mx, err ? INFINITY : fabs(q));
-        if (p.ite > 0) {
+        if (p.ite > 0 && (!p.own || p.own[k])) { // a row mirrored on two ranks is counted by the owner of rod I
             const double dx = 1.0 * cur.x + (-1.0) * cur.xp;
             const double dg = 1.0 * gk + (-1.0) * cur.gp;
             s0 += dx * dx;
@@ -777,7 +782,50 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
         s0 += pp[4 * i]; s1 += pp[4 * i + 1]; s2 += pp[4 * i + 2]; mx = fmax(mx, pp[4 * i + 3]);
     }
     blockReduce4(s0, s1, s2, mx, out);
-    if (threadIdx.x == 0) bbScalarStep(p, out);
+    if (threadIdx.x == 0) {
+        if (p.redOut) { // multi-rank: k_bb_reduce combines the ranks and takes the scalar step
+            p.redOut[0] = out[0]; p.redOut[1] = out[1]; p.redOut[2] = out[2]; p.redOut[3] = out[3];
+            p.scal->ticket = 0;
+        } else {
+            bbScalarStep(p, out);
+        }
+    }
+}
+
+// multi-rank end of a BBPGD iteration: every rank drops its 4 partials into every peer's mailbox (remote
+// stores + system-scope release of the sequence number), then sums all mailboxes in rank order -- each rank
+// performs the same additions in the same order, so alpha, the residual and `done` agree bit for bit.
+// Replaces the 3 MPI allreduces per iteration of BCQPSolver.cpp:200-233.
+struct ReduceArgs {
+    double *mailPeer[kMaxRanks];             // my slot in each peer's mailbox of this parity
+    unsigned long long *seqPeer[kMaxRanks];
+    const double *mailMine;                  // [R][4] of this parity in my window
+    const unsigned long long *seqMine;       // [R]
+    int *err;
+    int R;
+    unsigned long long seq;
+};
+__global__ void k_bb_reduce(ReduceArgs a, BbTail p) {
+    if (p.scal->done) return;
+    const int t = threadIdx.x;
+    if (t < a.R) {
+        double *dst = a.mailPeer[t];
+        dst[0] = p.redOut[0]; dst[1] = p.redOut[1]; dst[2] = p.redOut[2]; dst[3] = p.redOut[3];
+        __threadfence_system();
+        stReleaseSys(a.seqPeer[t], a.seq);
+    }
+    __syncwarp();
+    if (t != 0) return;
+    double out[4] = {0, 0, 0, 0};
+    for (int q = 0; q < a.R; q++) {
+        if (!waitSeq(a.seqMine + q, a.seq, a.err)) {
+            p.scal->done = 4;
+            return;
+        }
+        const volatile double *m = a.mailMine + 4 * q;
+        out[0] += m[0]; out[1] += m[1]; out[2] += m[2]; out[3] = fmax(out[3], m[3]);
+    }
+    bbScalarStep(p, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -845,7 +893,7 @@ k_dot3(long long n, Dot3 p, double *partial, unsigned int *ticket, double *resul
 
 // ------------------------------------------------------------------------------------------------
 // results: uni/bi split (ConstraintSolver.cpp:95-106) + permutation back to the caller's rod order
-__global__ void k_split_out(int n, const int *__restrict__ sUser, const double *__restrict__ F,
+__global__ void k_split_out(int n, int nLocal, const int *__restrict__ sUser, const double *__restrict__ F,
                             const double *__restrict__ U, const double *__restrict__ Fb,
                             const double *__restrict__ Ub, double *__restrict__ oFU, double *__restrict__ oVU,
                             double *__restrict__ oFB, double *__restrict__ oVB) {
@@ -853,6 +901,7 @@ __global__ void k_split_out(int n, const int *__restrict__ sUser, const double *
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= 6LL * n) return;
     const int s = (int)(e / 6), c = (int)(e - 6LL * s);
+    if (sUser[s] >= nLocal) return; // ghost rod
     const size_t u = 6 * (size_t)sUser[s] + c;
     const double fb = Fb ? Fb[e] : 0.0, ub = Ub ? Ub[e] : 0.0;
     oFU[u] = 1.0 * F[e] + (-1.0) * fb;
@@ -898,7 +947,9 @@ __global__ void k_step_euler(int n, double dt, const double *__restrict__ velNC,
 // host side
 // =================================================================================================
 static size_t mobStride(int n) { return ((size_t)n + 3) & ~(size_t)1; }
-static MobIn mobIn(Context &c) { return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.nRods, mobStride(c.nRods)}; }
+static MobIn mobIn(Context &c) {
+    return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.nRods, mobStride(c.nRods), c.sGhost.p};
+}
 static ConGeom conGeom(Context &c) { return ConGeom{c.cIdxI.p, c.cIdxJ.p, c.cN.p, c.cPI.p, c.cPJ.p, c.conCap}; }
 static FvIn fvIn(Context &c) { return FvIn{c.incStart.p, c.incCon.p, c.incCol.p, (size_t)c.incStride, c.nRods}; }
 
@@ -939,9 +990,16 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.dt = dt;
     // velNonCon (user order)
     if (velNC && n > 0) {
-        c.uVelNC.reserve(6 * (size_t)n);
-        ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, velNC, 48 * (size_t)n, cudaMemcpyHostToDevice, st));
+        c.uVelNC.reserve(6 * (size_t)n + 6);
+        if (c.nLocal > 0)
+            ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, velNC, 48 * (size_t)c.nLocal, cudaMemcpyHostToDevice, st));
         c.haveVelNC = true;
+    }
+    if (c.comm.active) { // ghost rows of velNonCon (collective: every rank must pass the same NULL / non-NULL)
+        if (c.haveVelNC) {
+            c.uVelNC.reserve(6 * (size_t)n + 6, st, true, 6 * (size_t)c.nLocal);
+            commHaloVelNC(c);
+        }
     }
     const bool useV = c.haveVelNC && n > 0;
     // incidence
@@ -951,12 +1009,19 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     ALENS_CUDA(cudaMemsetAsync(c.incDeg.p, 0, sizeof(int) * (n + 1), st));
     ALENS_CUDA(cudaMemsetAsync(c.incFill.p, 0, sizeof(int) * (n + 1), st));
     if (nc > 0) {
-        k_inc_count<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.incDeg.p);
+        k_inc_count<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.sGhost.p, c.incDeg.p);
         c.launches++;
     }
     launchScanInt(c, c.incDeg.p, c.incStart.p, n);
-    // slots = 2 per two-sided + 1 per one-sided constraint: known on the host, no readback
-    const long long nInc = 2 * nc - c.nOneSide;
+    // slots = 2 per two-sided + 1 per one-sided constraint: known on the host, no readback (with ghost rods
+    // the sides that fall on a ghost are skipped: read the total back)
+    long long nInc = 2 * nc - c.nOneSide;
+    if (c.comm.active) {
+        int tot = 0;
+        ALENS_CUDA(cudaMemcpyAsync(&tot, c.incStart.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        nInc = tot;
+    }
     if (nInc > 0x7fffffffLL - 16) throw ArgError{ALENS_ERR_UNSUPPORTED, "setup: more than 2^31 incidence slots"};
     c.nInc = nInc;
     c.incStride = ((nInc + 3) & ~3LL) + 4; // component stride: 16-byte aligned bulk copies may over-read < 4 slots
@@ -972,7 +1037,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.outFB.reserve(6 * (size_t)n + 6); c.outVB.reserve(6 * (size_t)n + 6);
     c.redPartial.reserve(4 * (size_t)(gridFor(std::max<long long>(nc, 1), kVecBlock) + 1));
     if (nc > 0) {
-        k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.incStart.p, c.incFill.p,
+        k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.sGhost.p, c.incStart.p, c.incFill.p,
                                                      c.incRaw.p);
         k_inc_emit<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incRaw.p, conGeom(c), c.incCon.p, c.incCol.p,
                                                     (size_t)c.incStride);
@@ -1045,9 +1110,10 @@ static void launchForceVel(Context &c, const double *x, double *U, double *F, co
     if (n == 0) return;
     profBegin(c, 0);
     const int grid = gridFor((long long)gridFor(n, 32) * 32, 256);
-    if (c.optForcePipe == 1) launchPipe<1024, 256, 1, MASK, WF>(c, x, U, F, scal);     // 1 CTA / SM, 3 x 52 KB ring
-    else if (c.optForcePipe == 2) launchPipe<512, 128, 2, MASK, WF>(c, x, U, F, scal); // 2 CTAs / SM, 26 KB stages
-    else if (c.optForcePipe == 4)
+    const int variant = c.comm.active && c.optForcePipe < 3 ? 3 : c.optForcePipe; // ghost rows: lm kernels only
+    if (variant == 1) launchPipe<1024, 256, 1, MASK, WF>(c, x, U, F, scal);     // 1 CTA / SM, 3 x 52 KB ring
+    else if (variant == 2) launchPipe<512, 128, 2, MASK, WF>(c, x, U, F, scal); // 2 CTAs / SM, 26 KB stages
+    else if (variant == 4)
         k_force_vel_lm<4, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal);
     else
         k_force_vel_lm<2, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal);
@@ -1058,6 +1124,7 @@ static void launchForceVel(Context &c, const double *x, double *U, double *F, co
 
 void operatorApply(Context &c, const double *x, double *y, double *force, double *vel) {
     if (!c.haveSetup) throw ArgError{ALENS_ERR_STATE, "alens_operator_apply: call alens_setup_constraints first"};
+    if (c.comm.active) throw ArgError{ALENS_ERR_UNSUPPORTED, "alens_operator_apply: single-rank test entry"};
     cudaStream_t st = c.stream;
     const long long nc = c.nCon;
     const int n = c.nRods;
@@ -1093,24 +1160,56 @@ static void syncScalars(Context &c) {
 // BCQPSolver::solveBBPGD (BCQPSolver.cpp:134-247).  Iterations are enqueued in batches without host
 // synchronisation; every kernel is a no-op once the device-side `done` flag is set, so the iterate and
 // the history are exactly those of the sequential loop.
+static void launchReduce(Context &c, const BbTail &t) { // multi-rank: combine the ranks' partials, take the step
+    Comm &m = c.comm;
+    const unsigned long long seq = ++m.seqMail;
+    const int par = (int)(seq & 1);
+    ReduceArgs a{};
+    for (int q = 0; q < c.nranks; q++) {
+        CommHeader *h = reinterpret_cast<CommHeader *>(m.peerWin[q]);
+        a.mailPeer[q] = &h->mail[par][c.rank][0];
+        a.seqPeer[q] = &h->mailSeq[par][c.rank];
+    }
+    CommHeader *me = reinterpret_cast<CommHeader *>(m.win);
+    a.mailMine = &me->mail[par][0][0];
+    a.seqMine = &me->mailSeq[par][0];
+    a.err = &me->error;
+    a.R = c.nranks;
+    a.seq = seq;
+    k_bb_reduce<<<1, 32, 0, c.stream>>>(a, t);
+    c.launches++;
+}
+
 static int solveBBPGD(Context &c, double tol, int maxIte) {
     cudaStream_t st = c.stream;
     const long long nc = c.nCon;
+    const bool multi = c.comm.active;
     double *X[2] = {c.vX0.p, c.vX1.p}, *G[2] = {c.vG0.p, c.vG1.p};
-    const int grid = gridFor(nc, kVecBlock);
+    const int grid = std::max(1, gridFor(nc, kVecBlock));
     const int gridTail = std::min(grid, c.numSMs * c.optTailCtasPerSM); // persistent (2 resident CTAs per SM)
     BbTail t{};
     t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.lbFlag = c.vLbFlag.p;
     t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = c.histCap; t.tol = tol;
+    if (multi) {
+        t.own = c.cOwn.p;
+        t.redOut = reinterpret_cast<double *>(c.dCounters.p); // 4 doubles of scratch
+    }
+    // one operator apply + fused tail; multi-rank: ghost rows of U are pushed to / awaited from the neighbours
+    // between the two kernels, and k_bb_reduce replaces the last-CTA scalar step
+    auto applyAndTail = [&](const double *x) {
+        launchForceVel<false, false>(c, x, c.rU.p, nullptr, c.dScal.p);
+        if (multi) commPushU(c, ++c.comm.seqHalo);
+        profBegin(c, 1);
+        k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
+        profEnd(c);
+        c.launches++; c.timers.op_launches++;
+        if (multi) launchReduce(c, t);
+    };
     // iteration 0: g0 = A x0 + b
-    launchForceVel<false, false>(c, X[0], c.rU.p, nullptr, c.dScal.p);
     t.ite = 0; t.x = X[0]; t.xprev = X[0]; t.gprev = G[0]; t.gout = G[0];
-    profBegin(c, 1);
-    k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
-    profEnd(c);
-    c.launches++; c.timers.op_launches++;
+    applyAndTail(X[0]);
     int ite = 0;
-    const int batch = c.optBatch > 0 ? c.optBatch : (nc > 200000 ? 8 : 32);
+    const int batch = c.optBatch > 0 ? c.optBatch : (nc > 200000 || multi ? 8 : 32);
     syncScalars(c);
     profFlush(c);
     while (!c.hScal->done && ite < maxIte) {
@@ -1121,18 +1220,16 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
             profBegin(c, 2);
             k_bb_update<<<grid, kVecBlock, 0, st>>>(nc, X[cur], G[cur], c.vLbFlag.p, X[nxt], c.dScal.p);
             profEnd(c);
-            launchForceVel<false, false>(c, X[nxt], c.rU.p, nullptr, c.dScal.p);
+            c.launches++; c.timers.op_launches++;
             t.ite = ite; t.x = X[nxt]; t.xprev = X[cur]; t.gprev = G[cur]; t.gout = G[nxt];
-            profBegin(c, 1);
-            k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
-            profEnd(c);
-            c.launches += 2; c.timers.op_launches += 2;
+            applyAndTail(X[nxt]);
         }
         syncScalars(c);
         if (c.hScal->done) c.profUsed = 0; // this batch contains early-exit no-ops: not representative
         else profFlush(c);
     }
     ALENS_CUDA(cudaGetLastError());
+    if (c.hScal->done == 4) throw ArgError{ALENS_ERR_COMM, "solve: timed out waiting for a peer rank"};
     const int n = c.hScal->ite; // iterations actually executed
     c.xLastApplied = X[n & 1];
     if (c.hScal->done || n == 0) c.xSolution = X[n & 1];
@@ -1303,7 +1400,7 @@ void solveCore(Context &c, double tol, int maxIte, int choice) {
     alens_solve_report &rep = c.lastReport;
     memset(&rep, 0, sizeof(rep));
     rep.n_constraints = nc;
-    rep.n_rods = n;
+    rep.n_rods = c.nLocal;
     c.timers.op_launches = 0;
     c.profUsed = 0;
     c.hist.clear();
@@ -1316,7 +1413,10 @@ void solveCore(Context &c, double tol, int maxIte, int choice) {
     ALENS_CUDA(cudaMemsetAsync(c.dScal.p, 0, sizeof(SolverScalars), st));
     ALENS_CUDA(cudaEventRecord(c.ev[2], st));
     int status = 0;
-    if (nc == 0) {
+    const bool multi = c.comm.active;
+    if (multi && choice == ALENS_SOLVER_APGD)
+        throw ArgError{ALENS_ERR_UNSUPPORTED, "solve: APGD is single-rank only (use BBPGD with the slab decomposition)"};
+    if (nc == 0 && !multi) {
         // empty problem: residual 0 < tol, zero forces (the reference returns after the first check)
         if (n > 0) {
             ALENS_CUDA(cudaMemsetAsync(c.rU.p, 0, 48 * (size_t)n, st));
@@ -1335,14 +1435,14 @@ void solveCore(Context &c, double tol, int maxIte, int choice) {
     }
     ALENS_CUDA(cudaEventRecord(c.ev[3], st));
     // split (ConstraintSolver.cpp:95-106): force/vel of the LAST apply minus the bilateral part
-    if (nc > 0) {
+    if (nc > 0 || multi) {
         launchForceVel<false, true>(c, c.xLastApplied, c.rU.p, c.rF.p, nullptr);
         // no bilateral block in the pool: gamma_b = 0, the bilateral force/velocity are exactly zero
         if (c.nBilateral > 0) launchForceVel<true, true>(c, c.xSolution, c.rUb.p, c.rFb.p, nullptr);
     }
     if (n > 0) {
         const bool bi = nc > 0 && c.nBilateral > 0;
-        k_split_out<<<gridFor(6LL * n, 256), 256, 0, st>>>(n, c.sUser.p, c.rF.p, c.rU.p, bi ? c.rFb.p : nullptr,
+        k_split_out<<<gridFor(6LL * n, 256), 256, 0, st>>>(n, c.nLocal, c.sUser.p, c.rF.p, c.rU.p, bi ? c.rFb.p : nullptr,
                                                            bi ? c.rUb.p : nullptr, c.outFU.p, c.outVU.p, c.outFB.p,
                                                            c.outVB.p);
         c.launches++;
@@ -1367,13 +1467,42 @@ void solveCore(Context &c, double tol, int maxIte, int choice) {
 
 void stepEuler(Context &c, double dt) {
     if (!c.haveSolution) throw ArgError{ALENS_ERR_STATE, "alens_step_euler: no solution available"};
-    const int n = c.nRods;
+    const int n = c.nLocal;
     if (n == 0) return;
     k_step_euler<<<gridFor(n, 256), 256, 0, c.stream>>>(n, dt, c.haveVelNC ? c.uVelNC.p : nullptr, c.outVU.p,
                                                         c.outVB.p, c.uPos.p, c.uQuat.p);
     c.launches++;
     ALENS_CUDA(cudaGetLastError());
     ALENS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// Force the (lazily loaded) kernels of this file into the context now: loading a kernel at its first launch can
+// synchronise the context, which deadlocks against a peer rank's waiting kernel when two ranks share one GPU.
+void preloadSolverKernels() {
+    cudaFuncAttributes a;
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_mob_coeff));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_mob_apply_user));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_count));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_fill));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_setup));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_dtrans));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_update));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_tail));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_reduce));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_update2));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_fill));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_project));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_dot3));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_split_out));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_permute6_to_user));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_step_euler));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, false, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, false, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, true, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, false, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, false, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, true, true>)));
 }
 
 } // namespace alens

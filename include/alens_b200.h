@@ -191,10 +191,33 @@ int alens_time_kernel(alens_ctx *ctx, const char *which, int reps, double *avgMi
 /* number of rods / cells / candidate pairs that passed the broad phase in the last collection */
 int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCandidates, long long *nHits);
 
-/* ---- multi-GPU (one process per GPU) ---------------------------------------------- */
-/* 128-byte ncclUniqueId created on rank 0 and broadcast by the host program, then a collective init */
-int alens_comm_unique_id(void *id128);
-int alens_comm_init(alens_ctx *ctx, const void *id128);
+/* ---- multi-GPU (one rank per GPU) ------------------------------------------------------
+ * Slab decomposition along one box axis.  Replaces, for the constraint path, the FDPS ghost exchange inside
+ * TreeSylinderNear::calcForceAll (FDPS/tree_for_force.hpp:759-842), Tpetra's ghost-column Import
+ * (ConstraintOperator.cpp:44-57) and the allreduces of BCQPSolver.cpp:183-233.  Transport: device memory windows
+ * mapped between the ranks (NVLink peer access; cudaIpc between processes), written with remote stores and
+ * sequence numbers -- see alens_b200/csrc/comm.cu.
+ *
+ * Every rank owns the rods whose centre lies in [slabLow, slabHigh) along `axis` (a rod may stray up to `skin`
+ * outside before the host has to redistribute: alens_prepare_step / alens_set_rods then return ALENS_ERR_STATE).
+ * maxBoundingRadius = max over ALL ranks of lengthCollision/2 + radiusCollision.  globalIndexBase = exclusive scan
+ * of the local rod counts over the ranks (SylinderSystem::updateSylinderMap, SylinderSystem.cpp:868-880).
+ * With a decomposition in place alens_set_rods / alens_prepare_step / alens_solve_constraints are COLLECTIVE
+ * (every rank must call them, with the same dt / res / maxIte); results are returned for the owned rods only;
+ * constraints that couple rods of two ranks are held (bit-identically) by both. */
+int alens_set_decomposition(alens_ctx *ctx, int axis, double slabLow, double slabHigh, double skin,
+                            double maxBoundingRadius, int globalIndexBase);
+/* allocate this rank's window; maxLocalRods bounds the owned rods per rank (ghost capacity = a third of it) */
+int alens_comm_create(alens_ctx *ctx, long long maxLocalRods);
+/* multi-process bootstrap: export a blob of alens_comm_blob_size() bytes, all-gather the blobs in rank order with
+ * the host program's own means (MPI_Allgather, torch.distributed.all_gather, ...), then connect (collective) */
+int alens_comm_blob_size(void);
+int alens_comm_export(alens_ctx *ctx, void *blob);
+int alens_comm_connect(alens_ctx *ctx, const void *blobsInRankOrder);
+/* single-process bootstrap: n contexts (rank order) driven by n host threads; devices may coincide */
+int alens_comm_connect_local(alens_ctx **ctxs, int n);
+/* ghost rods received / owned rods mirrored on the left and right neighbour in the last exchange */
+int alens_num_ghosts(alens_ctx *ctx, int *nGhost, int *nSentLeft, int *nSentRight);
 
 #ifdef __cplusplus
 }

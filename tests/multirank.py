@@ -1,0 +1,82 @@
+"""Harness for the slab decomposition: run R ranks (one alens_ctx each, one host thread each) inside one process.
+With a single GPU every rank uses device 0; with >= R GPUs each rank gets its own device (same code path as the
+multi-process bench, only the bootstrap differs: alens_comm_connect_local instead of cudaIpc blobs)."""
+import threading
+
+import numpy as np
+
+import alens_b200
+
+
+def split_slabs(rods, box_lo, box_hi, nranks, axis=0):
+    """owner rank of every rod by its wrapped centre; returns list of index arrays (global order preserved)"""
+    L = box_hi[axis] - box_lo[axis]
+    x = rods["pos"][:, axis]
+    xw = box_lo[axis] + np.mod(x - box_lo[axis], L)
+    w = L / nranks
+    owner = np.minimum((np.floor((xw - box_lo[axis]) / w)).astype(int), nranks - 1)
+    return [np.nonzero(owner == r)[0] for r in range(nranks)]
+
+
+def take(rods, idx):
+    return {k: v[idx] for k, v in rods.items()}
+
+
+def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None, skin=None, axis=0, devices=None,
+              steps=1, want_blocks=True):
+    """returns per-rank dicts (idx = global rod indices owned, blocks, gamma, forceU/velU/..., report, history)"""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    parts = split_slabs(rods, lo, hi, nranks, axis)
+    max_r = float(np.max(0.5 * rods["length"] + rods["radius"]))
+    cutoff = 2 * max_r + colbuf
+    skin = 0.25 * cutoff if skin is None else skin
+    w = (hi[axis] - lo[axis]) / nranks
+    devices = devices or [0] * nranks
+    ctxs = []
+    base = 0
+    for r in range(nranks):
+        c = alens_b200.Context(device=devices[r], rank=r, nranks=nranks)
+        c.set_domain(lo, hi, pbc)
+        c.set_collision_params(1.0, 1.0, colbuf)
+        c.set_decomposition(axis, lo[axis] + r * w, lo[axis] + (r + 1) * w, skin, max_r, base)
+        c.comm_create(max(4096, 2 * max(len(p) for p in parts)))
+        base += len(parts[r])
+        ctxs.append(c)
+    alens_b200.comm_connect_local(ctxs)
+    out = [None] * nranks
+    errs = [None] * nranks
+
+    def work(r):
+        try:
+            c, idx = ctxs[r], parts[r]
+            loc = take(rods, idx)
+            c.set_rods(loc["gid"], loc["pos"], loc["quat"], loc["length"], loc["radius"], loc["immovable"], wrap=True)
+            v = None if vnc is None else np.ascontiguousarray(vnc.reshape(-1, 6)[idx]).reshape(-1)
+            res_r = dict(idx=idx)
+            for s in range(steps):
+                if s > 0:
+                    c.step_euler(dt)
+                    c.prepare_step(True)
+                nc = c.collect_pair_collision()
+                c.calc_mobility(mu)
+                rep = c.solve_constraints(v, dt, res, max_ite, 0)
+            res_r.update(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), ghosts=c.num_ghosts())
+            res_r.update(c.get_force_velocity())
+            if want_blocks:
+                res_r["blocks"] = c.get_constraints(with_stress=True, write_back=True)
+            res_r["state"] = c.get_rod_state()
+            out[r] = res_r
+        except Exception as e:  # noqa: BLE001
+            errs[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for c in ctxs:
+        c.close()
+    for e in errs:
+        if e is not None:
+            raise e
+    return out
