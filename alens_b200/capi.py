@@ -80,8 +80,15 @@ def build(verbose=False):
     return lib_path()
 
 
+_EMPTY = np.zeros(1)
+
+
 def _dp(a):
-    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+    if a is None:
+        return None
+    if a.size == 0:  # a zero-length array still means "given" (non-NULL) across the C ABI
+        a = _EMPTY
+    return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
 class Library:

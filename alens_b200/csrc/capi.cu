@@ -197,12 +197,13 @@ int alens_prepare_step(alens_ctx *ctx, int wrap) {
 
 int alens_set_velocity_noncon(alens_ctx *ctx, const double *v) {
     return guarded(ctx, [&](Context &c) {
-        if (!v || c.nLocal == 0) {
+        if (!v) {
             c.haveVelNC = false;
             return;
         }
         c.uVelNC.reserve(6 * (size_t)c.nRods + 6);
-        ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, v, 48 * (size_t)c.nLocal, cudaMemcpyHostToDevice, c.stream));
+        if (c.nLocal > 0)
+            ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, v, 48 * (size_t)c.nLocal, cudaMemcpyHostToDevice, c.stream));
         ALENS_CUDA(cudaStreamSynchronize(c.stream));
         c.haveVelNC = true;
     });

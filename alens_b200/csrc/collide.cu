@@ -91,13 +91,22 @@ __global__ void k_global_index(int n, int base, int *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = base + i;
 }
-// rods that left their slab by more than the skin (the host has to migrate them)
-__global__ void k_count_strays(int n, const double *__restrict__ pos, int axis, double lo, double hi, double skin,
-                               int *__restrict__ count) {
+// Image of every OWNED rod in its slab's frame: a rod that strayed (by less than the skin) across a periodic box
+// face has a wrapped coordinate at the far end of the box; img = -1 / +1 brings it back next to its slab.
+// Rods further than the skin from their slab are counted: the host has to migrate them.
+__global__ void k_local_image(int n, const double *__restrict__ pos, int axis, double lo, double hi, double skin,
+                              double boxLen, int periodic, signed char *__restrict__ img, int *__restrict__ strays) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double x = pos[3 * (size_t)i + axis];
-    if (x < lo - skin || x >= hi + skin) atomicAdd(count, 1);
+    int im = 0;
+    bool ok = x >= lo - skin && x < hi + skin;
+    if (!ok && periodic) {
+        if (x - boxLen >= lo - skin && x - boxLen < hi + skin) { im = -1; ok = true; }
+        else if (x + boxLen >= lo - skin && x + boxLen < hi + skin) { im = 1; ok = true; }
+    }
+    img[i] = (signed char)im;
+    if (!ok) atomicAdd(strays, 1);
 }
 
 // single-CTA exclusive scan; out has n+1 entries (out[n] = total).  Used for short arrays and for the
@@ -646,8 +655,9 @@ void rodsUploaded(Context &c, bool wrap) {
         if (wrap && c.nLocal > 0) k_rod_wrap<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.uPos.p, c.box);
         ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 4 * sizeof(unsigned long long), st));
         if (c.nLocal > 0)
-            k_count_strays<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.uPos.p, c.slabAxis, c.slabLo, c.slabHi,
-                                                                  c.skin, reinterpret_cast<int *>(c.dCounters.p));
+            k_local_image<<<gridFor(c.nLocal, 256), 256, 0, st>>>(
+                c.nLocal, c.uPos.p, c.slabAxis, c.slabLo, c.slabHi, c.skin, c.box.len[c.slabAxis],
+                c.box.pbc[c.slabAxis], c.uImg.p, reinterpret_cast<int *>(c.dCounters.p));
         int strays = 0;
         ALENS_CUDA(cudaMemcpyAsync(&strays, c.dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         ALENS_CUDA(cudaStreamSynchronize(st));
@@ -781,7 +791,7 @@ void preloadCollideKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_pack));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_wrap));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_global_index));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, k_count_strays));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_local_image));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_scan_int));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_scan_tile_sums));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_scan_tile_apply));

@@ -46,11 +46,12 @@ __global__ void k_signal(unsigned long long *f0, long long *c0, long long n0, un
 
 // ------------------------------------------------------------------------------------------------
 // ghost selection: local rods whose apparent coordinate along the slab axis lies within `gw` of a slab face
-__global__ void k_ghost_flags(int n, const double *__restrict__ pos, int axis, double lo, double hi, double gw,
-                              int haveLeft, int haveRight, int *__restrict__ fL, int *__restrict__ fR) {
+__global__ void k_ghost_flags(int n, const double *__restrict__ pos, const signed char *__restrict__ img, double boxLen,
+                              int axis, double lo, double hi, double gw, int haveLeft, int haveRight,
+                              int *__restrict__ fL, int *__restrict__ fR) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double x = pos[3 * (size_t)i + axis];
+    const double x = pos[3 * (size_t)i + axis] + img[i] * boxLen;
     fL[i] = (haveLeft && x < lo + gw) ? 1 : 0;
     fR[i] = (haveRight && x >= hi - gw) ? 1 : 0;
 }
@@ -71,7 +72,7 @@ __global__ void k_ghost_pack(int n, const int *__restrict__ list, GhostSrc s, in
     d[8] = s.rad[i];
     for (int k = 0; k < 6; k++) d[9 + k] = s.velNC ? s.velNC[6 * (size_t)i + k] : 0.0;
     d[15] = __hiloint2double(s.gid[i], s.globalBase + i);
-    d[16] = __hiloint2double(s.imm ? (int)s.imm[i] : 0, image);
+    d[16] = __hiloint2double(s.imm ? (int)s.imm[i] : 0, image + s.img[i]); // own image + the channel's
 }
 __global__ void k_ghost_unpack(int n, const double *__restrict__ src, GhostDst o, int base) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,8 +259,8 @@ void commExchangeGhosts(Context &c) {
     DevBuf<int> scanL, scanR;
     scanL.reserve(n + 8); scanR.reserve(n + 8);
     if (n > 0)
-        k_ghost_flags<<<gridFor(n, 256), 256, 0, st>>>(n, c.uPos.p, ax, c.slabLo, c.slabHi, gw, m.left >= 0, m.right >= 0,
-                                                       fL.p, fR.p);
+        k_ghost_flags<<<gridFor(n, 256), 256, 0, st>>>(n, c.uPos.p, c.uImg.p, c.box.len[ax], ax, c.slabLo, c.slabHi, gw,
+                                                       m.left >= 0, m.right >= 0, fL.p, fR.p);
     launchScanInt(c, fL.p, scanL.p, n);
     launchScanInt(c, fR.p, scanR.p, n);
     int cnt[2] = {0, 0};
@@ -278,8 +279,8 @@ void commExchangeGhosts(Context &c) {
     }
     // pack straight into the neighbours' windows; image = how the rod appears in the receiver's frame
     const unsigned long long seq = ++m.seqGhost;
-    GhostSrc src{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.haveVelNC ? c.uVelNC.p : nullptr,
-                 c.globalBase};
+    GhostSrc src{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.uImg.p,
+                 c.haveVelNC ? c.uVelNC.p : nullptr, c.globalBase};
     unsigned long long *sf[2] = {nullptr, nullptr};
     long long *sc[2] = {nullptr, nullptr};
     for (int d = 0; d < 2; d++) {
@@ -311,9 +312,8 @@ void commExchangeGhosts(Context &c) {
     c.uGid.reserve(N + 1, st, true, n); c.uPos.reserve(3 * N + 3, st, true, 3 * (size_t)n);
     c.uQuat.reserve(4 * N + 4, st, true, 4 * (size_t)n); c.uLen.reserve(N + 1, st, true, n);
     c.uRad.reserve(N + 1, st, true, n); c.uImm.reserve(N + 1, st, true, n);
-    c.uImg.reserve(N + 1); c.uGlobalIdx.reserve(N + 1, st, true, n);
+    c.uImg.reserve(N + 1, st, true, n); c.uGlobalIdx.reserve(N + 1, st, true, n);
     if (c.haveVelNC) c.uVelNC.reserve(6 * N + 6, st, true, 6 * (size_t)n);
-    ALENS_CUDA(cudaMemsetAsync(c.uImg.p, 0, N + 1, st));
     GhostDst dst{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.uImg.p, c.uGlobalIdx.p,
                  c.haveVelNC ? c.uVelNC.p : nullptr};
     int base = n;

@@ -147,6 +147,7 @@ struct GhostSrc {
     const int *gid;
     const double *pos, *quat, *len, *rad;
     const unsigned char *imm;
+    const signed char *img;
     const double *velNC;
     int globalBase;
 };

@@ -989,7 +989,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     const long long nc = c.nCon;
     c.dt = dt;
     // velNonCon (user order)
-    if (velNC && n > 0) {
+    if (velNC) { // (also on a rank that owns no rods: the ghost-row exchange below is collective)
         c.uVelNC.reserve(6 * (size_t)n + 6);
         if (c.nLocal > 0)
             ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, velNC, 48 * (size_t)c.nLocal, cudaMemcpyHostToDevice, st));

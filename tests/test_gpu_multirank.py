@@ -83,6 +83,39 @@ def test_multirank_matches_single(nranks, pbc):
         np.testing.assert_allclose(h[:, 3:5], hr[:, 3:5], rtol=1e-7)
 
 
+def test_multirank_time_stepping_across_periodic_face():
+    """three resident steps (solve -> stepEuler -> prepareStep) from an overlapping start: rods drift across slab
+    faces and across the periodic box face; positions must follow the single-rank trajectory"""
+    import alens_b200
+
+    n, box, colbuf, mu, dt, res, steps = 5000, (4.0, 1.5, 1.5), 0.025, 1.0, 1e-4, 1e-6, 3
+    lo, hi, pbc = [0.0] * 3, list(box), (1, 1, 1)
+    rods = slab_ordered(random_rods(n, box, seed=77), lo, hi, 2)
+    c = alens_b200.Context(0)
+    c.set_domain(lo, hi, pbc)
+    c.set_collision_params(1.0, 1.0, colbuf)
+    c.set_rods(rods["gid"], rods["pos"], rods["quat"], rods["length"], rods["radius"], rods["immovable"], wrap=True)
+    for s in range(steps):
+        if s > 0:
+            c.step_euler(dt)
+            c.prepare_step(True)
+        c.collect_pair_collision()
+        c.calc_mobility(mu)
+        rep = c.solve_constraints(None, dt, res, 2000, 0)
+    pos_ref, quat_ref = c.get_rod_state()
+    vel_ref = c.get_force_velocity()["velU"]
+    c.close()
+    ranks = run_ranks(rods, lo, hi, pbc, 2, colbuf, mu, dt, res, 2000, vnc=None, skin=0.15, steps=steps,
+                      want_blocks=False)
+    for r in ranks:
+        pos, quat = r["state"]
+        assert np.abs(pos - pos_ref[r["idx"]]).max() < 1e-9
+        assert np.abs(quat - quat_ref[r["idx"]]).max() < 1e-9
+        v = r["velU"].reshape(-1, 6)
+        assert np.abs(v - vel_ref.reshape(-1, 6)[r["idx"]]).max() < 1e-7 * np.abs(vel_ref).max()
+        assert r["report"].iterations == rep.iterations
+
+
 def test_multirank_empty_rank_and_no_contacts():
     """a rank without rods and a system without contacts still run the collective protocol"""
     n, box = 300, (6.0, 1.0, 1.0)
