@@ -386,6 +386,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
         const std::string k = name ? name : "";
         if (k == "force_pipe") c.optForcePipe = (int)std::max(1LL, std::min(4LL, value));
         else if (k == "tail_ctas_per_sm") c.optTailCtasPerSM = (int)std::max(1LL, std::min(8LL, value));
+        else if (k == "comm_fused") c.comm.fused = value != 0;
         else if (k == "pipe_debug") c.optPipeDebug = (int)value;
         else if (k == "bbpgd_batch") c.optBatch = (int)std::max(0LL, std::min(1024LL, value));
         else throw ArgError{ALENS_ERR_ARG, "alens_set_option: unknown option '" + k + "'"};

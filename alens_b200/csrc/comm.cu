@@ -102,6 +102,16 @@ __global__ void k_map_indices(int n, const int *__restrict__ list, const int *__
     if (e < n) out[e] = userToSorted[list[e]];
 }
 
+__global__ void k_fill_int(int n, int v, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+__global__ void k_build_mirror(int n, const int *__restrict__ sorted, const int *__restrict__ remote,
+                               int *__restrict__ mirror) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) mirror[sorted[e]] = remote[e];
+}
+
 // 6-vector halo: dst[6*dstIdx[e] ..] = src[6*srcIdx[e] ..] for the rods mirrored on a neighbour (remote stores)
 __global__ void k_halo_push6(int n0, const int *__restrict__ src0, const int *__restrict__ dst0, double *__restrict__ out0,
                              int n1, const int *__restrict__ src1, const int *__restrict__ dst1, double *__restrict__ out1,
@@ -162,6 +172,10 @@ void commFinishConnect(Context &c) {
     c.rU.cap = m.capRods * 6;
     c.rU.external = true;
     m.active = R > 1;
+    m.fused = true; // waiting inside compute kernels is only safe when no two ranks share a device
+    for (int a = 0; a < R; a++)
+        for (int b = a + 1; b < R; b++)
+            if (m.devOfRank[a] == m.devOfRank[b]) m.fused = false;
     preloadCollideKernels();
     preloadSolverKernels();
     preloadBlockKernels();
@@ -193,7 +207,9 @@ void commImport(Context &c, const void *blobs) {
         ALENS_CUDA(cudaIpcOpenMemHandle(&p, b.handle, cudaIpcMemLazyEnablePeerAccess));
         m.peerWin[q] = (unsigned char *)p;
         m.ipcMapped[q] = true;
+        m.devOfRank[q] = b.device;
     }
+    m.devOfRank[c.rank] = c.device;
     commFinishConnect(c);
 }
 
@@ -211,6 +227,7 @@ void commConnectLocal(Context **ctxs, int n) {
                 cudaGetLastError();
             }
             c.comm.peerWin[b] = p.comm.win;
+            c.comm.devOfRank[b] = p.device;
         }
     }
     for (int a = 0; a < n; a++) {
@@ -355,7 +372,15 @@ void commExchangeGhostIndices(Context &c) {
         if (m.nSend[d] > 0)
             k_map_indices<<<gridFor(m.nSend[d], 256), 256, 0, st>>>(m.nSend[d], m.sendIdx[d].p, c.userToSorted.p,
                                                                    m.sendSorted[d].p);
-    c.launches += 4;
+    // per-rod mirror rows for the fused halo push of k_force_vel_lm
+    for (int d = 0; d < 2; d++) {
+        m.mirror[d].reserve((size_t)c.nRods + 1);
+        if (c.nRods > 0) k_fill_int<<<gridFor(c.nRods, 256), 256, 0, st>>>(c.nRods, -1, m.mirror[d].p);
+        if (m.nSend[d] > 0 && nbWin(c, d))
+            k_build_mirror<<<gridFor(m.nSend[d], 256), 256, 0, st>>>(
+                m.nSend[d], m.sendSorted[d].p, reinterpret_cast<const int *>(m.win + m.offAck[d]), m.mirror[d].p);
+    }
+    c.launches += 8;
     ALENS_CUDA(cudaGetLastError());
     ALENS_CUDA(cudaStreamSynchronize(st));
     checkCommError(c);
@@ -391,6 +416,17 @@ void commHaloVelNC(Context &c) {
     }
     c.launches += 4;
     ALENS_CUDA(cudaGetLastError());
+}
+
+// fused path: k_force_vel_lm has stored the mirrored rows; release the sequence number on both neighbours
+void commSignalHalo(Context &c, unsigned long long seq) {
+    unsigned long long *sf[2] = {nullptr, nullptr};
+    for (int d = 0; d < 2; d++) {
+        unsigned char *w = nbWin(c, d);
+        if (w) sf[d] = &hdrOf(w)->haloSeq[1 - d];
+    }
+    k_signal<<<1, 1, 0, c.stream>>>(sf[0], nullptr, 0, sf[1], nullptr, 0, seq, c.dScal.p);
+    c.launches++;
 }
 
 // per operator apply: my rows of U -> the ghost rows on the neighbours, then the sequence number
@@ -433,6 +469,8 @@ void preloadCommKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_map_indices));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_halo_push6));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_copy6_rows));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_fill_int));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_build_mirror));
 }
 
 } // namespace alens

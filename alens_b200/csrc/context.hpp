@@ -117,8 +117,8 @@ struct SolverScalars {
     int mv;            // mvCount
     int done;          // 1 converged, 2 stagnated, 3 projection error
     int nhist;         // history rows written
-    unsigned int ticket; // last-block election counter
-    int pad_;
+    unsigned int ticket;   // last-block election counter of k_bb_tail
+    unsigned int ticketFv; // ... of k_force_vel_lm (fused halo push)
 };
 
 // ---- multi-GPU (comm.cu) ----------------------------------------------------------------------
@@ -171,6 +171,9 @@ struct Comm {
     unsigned long long seqGhost = 0, seqAck = 0, seqVec = 0, seqHalo = 0, seqMail = 0; // lockstep counters
     DevBuf<int> sendIdx[2];    // user index of my rods mirrored on the left / right neighbour
     DevBuf<int> sendSorted[2]; // their sorted index (source rows of the U halo)
+    DevBuf<int> mirror[2];     // per sorted rod: its row on the left / right neighbour, -1 if not mirrored there
+    bool fused = false;        // every rank has its own device: kernels may wait on peers (see solver.cu)
+    int devOfRank[kMaxRanks] = {};
     int nSend[2] = {0, 0}, nRecv[2] = {0, 0};
 };
 
@@ -321,6 +324,7 @@ void commExchangeGhosts(Context &c);
 void commExchangeGhostIndices(Context &c);
 void commHaloVelNC(Context &c);
 void commPushU(Context &c, unsigned long long seq);
+void commSignalHalo(Context &c, unsigned long long seq);
 void reserveConstraints(Context &c, size_t n, bool keep);
 
 inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }

@@ -463,14 +463,24 @@ k_force_vel_pipe(FvIn in, MobIn mob, const double *__restrict__ x, const double 
 // one fully coalesced request; positions come from ballot/popc on the per-lane degree.  Levels are processed
 // CHUNK at a time and software-pipelined: the constraint ids of chunk c+1 are requested before the x gathers
 // and column loads of chunk c, so a warp never waits on an id before it can issue loads.
+// Multi-GPU, fused: rows of U that a neighbour mirrors as ghost rods are stored to the neighbour's window as well
+// (NVLink remote stores from the kernel that computes them).  mir[d][r] = row of rod r on neighbour d, -1 if it
+// is not mirrored there.  The halo sequence number is released by a one-thread kernel right behind this one (a
+// last-CTA election inside the kernel costs every CTA a barrier + an atomic: measured +40 us per launch).
+struct HaloPush {
+    const int *mir[2];
+    double *rem[2];
+    int on;
+};
+
 template <int CHUNK, bool MASK, bool WRITE_F>
 __global__ void __launch_bounds__(256)
 k_force_vel_lm(FvIn in, MobIn mob, const double *__restrict__ x, const double *__restrict__ mask,
-               double *__restrict__ U, double *__restrict__ F, const SolverScalars *__restrict__ scal) {
+               double *__restrict__ U, double *__restrict__ F, const SolverScalars *__restrict__ scal, HaloPush hp) {
     if (scal && scal->done) return;
+
     const int lane = threadIdx.x & 31;
     const int grp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    if (grp * 32 >= in.nRods) return;
     const int r = grp * 32 + lane;
     const bool act = r < in.nRods;
     int b = 0, d = 0;
@@ -535,18 +545,31 @@ k_force_vel_lm(FvIn in, MobIn mob, const double *__restrict__ x, const double *_
             con[q] = conN[q];
         }
     }
-    if (!act || mob.ghost[r]) return;
-    const double qf = qx * f[0] + qy * f[1] + qz * f[2];
-    const double px = qf * qx, py = qf * qy, pz = qf * qz;
-    double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
-    Up[0] = make_double2(iPara * px + iPerp * (f[0] - px), iPara * py + iPerp * (f[1] - py));
-    Up[1] = make_double2(iPara * pz + iPerp * (f[2] - pz), iRot * f[3]);
-    Up[2] = make_double2(iRot * f[4], iRot * f[5]);
-    if (WRITE_F) {
-        double2 *Fp = reinterpret_cast<double2 *>(F + 6 * (size_t)r);
-        Fp[0] = make_double2(f[0], f[1]);
-        Fp[1] = make_double2(f[2], f[3]);
-        Fp[2] = make_double2(f[4], f[5]);
+    if (act && !mob.ghost[r]) {
+        const double qf = qx * f[0] + qy * f[1] + qz * f[2];
+        const double px = qf * qx, py = qf * qy, pz = qf * qz;
+        const double2 u0 = make_double2(iPara * px + iPerp * (f[0] - px), iPara * py + iPerp * (f[1] - py));
+        const double2 u1 = make_double2(iPara * pz + iPerp * (f[2] - pz), iRot * f[3]);
+        const double2 u2 = make_double2(iRot * f[4], iRot * f[5]);
+        double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
+        Up[0] = u0; Up[1] = u1; Up[2] = u2;
+        if (WRITE_F) {
+            double2 *Fp = reinterpret_cast<double2 *>(F + 6 * (size_t)r);
+            Fp[0] = make_double2(f[0], f[1]);
+            Fp[1] = make_double2(f[2], f[3]);
+            Fp[2] = make_double2(f[4], f[5]);
+        }
+        if (hp.on) {
+#pragma unroll
+            for (int dd = 0; dd < 2; dd++) {
+                if (!hp.mir[dd]) continue;
+                const int rr = hp.mir[dd][r];
+                if (rr >= 0) {
+                    double2 *Rp = reinterpret_cast<double2 *>(hp.rem[dd] + 6 * (size_t)rr);
+                    Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+                }
+            }
+        }
     }
 }
 
@@ -647,6 +670,15 @@ __global__ void k_bb_update(long long nc, const double *__restrict__ xprev, cons
     x[k] = v;
 }
 
+struct ReduceArgs {
+    double *mailPeer[kMaxRanks];             // my slot in each peer's mailbox of this parity
+    unsigned long long *seqPeer[kMaxRanks];
+    const double *mailMine;                  // [R][4] of this parity in my window
+    const unsigned long long *seqMine;       // [R]
+    int *err;
+    int R;
+    unsigned long long seq;
+};
 struct BbTail {
     long long nc;
     ConGeom g;
@@ -660,6 +692,12 @@ struct BbTail {
     int ite; // iteration number of this launch (0 = initial gradient)
     const unsigned char *own; // multi-rank: 1 = this rank counts the row in the dot products (nullptr = all)
     double *redOut;           // multi-rank: the reduced partials go here, k_bb_reduce finishes the step
+    // fused multi-GPU variant (one rank per device): the kernel itself waits for the neighbours' ghost rows of U
+    // before its first gather, and its last CTA runs the mailbox allreduce
+    const unsigned long long *waitFlag[2];
+    unsigned long long waitSeq;
+    int fusedReduce;
+    ReduceArgs red;
 };
 
 // last-CTA epilogue shared by the BBPGD tail kernels: fixed-order reduction of the per-CTA partials, then the
@@ -723,6 +761,13 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     TailRow cur, nxt;
     if (k < p.nc) loadTailRow(p, (size_t)k, cur);
     if (done) return;
+    if (p.waitSeq) { // ghost rows of U: pushed by the neighbours' k_force_vel_lm (streaming loads above are in flight)
+        if (threadIdx.x == 0) {
+            if (p.waitFlag[0]) waitSeq(p.waitFlag[0], p.waitSeq, p.red.err);
+            if (p.waitFlag[1]) waitSeq(p.waitFlag[1], p.waitSeq, p.red.err);
+        }
+        __syncthreads();
+    }
     while (k < p.nc) {
         const long long kn = k + stride;
         if (kn < p.nc) loadTailRow(p, (size_t)kn, nxt);
@@ -783,7 +828,26 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     }
     blockReduce4(s0, s1, s2, mx, out);
     if (threadIdx.x == 0) {
-        if (p.redOut) { // multi-rank: k_bb_reduce combines the ranks and takes the scalar step
+        if (p.fusedReduce) { // allreduce over the ranks' mailboxes, in rank order on every rank
+            const ReduceArgs &a = p.red;
+            for (int q = 0; q < a.R; q++) {
+                double *dst = a.mailPeer[q];
+                dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
+                __threadfence_system();
+                stReleaseSys(a.seqPeer[q], a.seq);
+            }
+            double tot[4] = {0, 0, 0, 0};
+            for (int q = 0; q < a.R; q++) {
+                if (!waitSeq(a.seqMine + q, a.seq, a.err)) {
+                    p.scal->ticket = 0;
+                    p.scal->done = 4;
+                    return;
+                }
+                const volatile double *m = a.mailMine + 4 * q;
+                tot[0] += m[0]; tot[1] += m[1]; tot[2] += m[2]; tot[3] = fmax(tot[3], m[3]);
+            }
+            bbScalarStep(p, tot);
+        } else if (p.redOut) { // multi-rank, unfused: k_bb_reduce combines the ranks and takes the scalar step
             p.redOut[0] = out[0]; p.redOut[1] = out[1]; p.redOut[2] = out[2]; p.redOut[3] = out[3];
             p.scal->ticket = 0;
         } else {
@@ -796,15 +860,6 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
 // stores + system-scope release of the sequence number), then sums all mailboxes in rank order -- each rank
 // performs the same additions in the same order, so alpha, the residual and `done` agree bit for bit.
 // Replaces the 3 MPI allreduces per iteration of BCQPSolver.cpp:200-233.
-struct ReduceArgs {
-    double *mailPeer[kMaxRanks];             // my slot in each peer's mailbox of this parity
-    unsigned long long *seqPeer[kMaxRanks];
-    const double *mailMine;                  // [R][4] of this parity in my window
-    const unsigned long long *seqMine;       // [R]
-    int *err;
-    int R;
-    unsigned long long seq;
-};
 __global__ void k_bb_reduce(ReduceArgs a, BbTail p) {
     if (p.scal->done) return;
     const int t = threadIdx.x;
@@ -1105,18 +1160,20 @@ static void launchPipe(Context &c, const double *x, double *U, double *F, const 
 }
 
 template <bool MASK, bool WF>
-static void launchForceVel(Context &c, const double *x, double *U, double *F, const SolverScalars *scal) {
+static void launchForceVel(Context &c, const double *x, double *U, double *F, const SolverScalars *scal,
+                           const HaloPush *push = nullptr) {
     const int n = c.nRods;
-    if (n == 0) return;
+    const HaloPush hp = push ? *push : HaloPush{};
+    if (n == 0 && !push) return;
     profBegin(c, 0);
-    const int grid = gridFor((long long)gridFor(n, 32) * 32, 256);
+    const int grid = std::max(1, gridFor((long long)gridFor(n, 32) * 32, 256));
     const int variant = c.comm.active && c.optForcePipe < 3 ? 3 : c.optForcePipe; // ghost rows: lm kernels only
     if (variant == 1) launchPipe<1024, 256, 1, MASK, WF>(c, x, U, F, scal);     // 1 CTA / SM, 3 x 52 KB ring
     else if (variant == 2) launchPipe<512, 128, 2, MASK, WF>(c, x, U, F, scal); // 2 CTAs / SM, 26 KB stages
     else if (variant == 4)
-        k_force_vel_lm<4, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal);
+        k_force_vel_lm<4, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal, hp);
     else
-        k_force_vel_lm<2, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal);
+        k_force_vel_lm<2, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal, hp);
     profEnd(c);
     c.launches++;
     c.timers.op_launches++;
@@ -1160,7 +1217,7 @@ static void syncScalars(Context &c) {
 // BCQPSolver::solveBBPGD (BCQPSolver.cpp:134-247).  Iterations are enqueued in batches without host
 // synchronisation; every kernel is a no-op once the device-side `done` flag is set, so the iterate and
 // the history are exactly those of the sequential loop.
-static void launchReduce(Context &c, const BbTail &t) { // multi-rank: combine the ranks' partials, take the step
+static ReduceArgs reduceArgs(Context &c) { // next mailbox round
     Comm &m = c.comm;
     const unsigned long long seq = ++m.seqMail;
     const int par = (int)(seq & 1);
@@ -1176,8 +1233,7 @@ static void launchReduce(Context &c, const BbTail &t) { // multi-rank: combine t
     a.err = &me->error;
     a.R = c.nranks;
     a.seq = seq;
-    k_bb_reduce<<<1, 32, 0, c.stream>>>(a, t);
-    c.launches++;
+    return a;
 }
 
 static int solveBBPGD(Context &c, double tol, int maxIte) {
@@ -1196,14 +1252,46 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     }
     // one operator apply + fused tail; multi-rank: ghost rows of U are pushed to / awaited from the neighbours
     // between the two kernels, and k_bb_reduce replaces the last-CTA scalar step
+    const bool fused = multi && c.comm.fused;
     auto applyAndTail = [&](const double *x) {
+        if (fused) {
+            // the force kernel also stores the mirrored rows of U into the neighbours' windows, a one-thread kernel
+            // releases their halo flags; the tail waits for its own flags before the first gather and finishes
+            // with the mailbox allreduce: no separate wait / reduce launches, nothing goes through the host
+            Comm &m = c.comm;
+            const unsigned long long seq = ++m.seqHalo;
+            CommHeader *me = reinterpret_cast<CommHeader *>(m.win);
+            HaloPush hp{};
+            for (int d = 0; d < 2; d++) {
+                const int q = d == 0 ? m.left : m.right;
+                if (q < 0) continue;
+                hp.mir[d] = m.mirror[d].p;
+                hp.rem[d] = reinterpret_cast<double *>(m.peerWin[q] + m.offU);
+            }
+            hp.on = 1;
+            launchForceVel<false, false>(c, x, c.rU.p, nullptr, c.dScal.p, &hp);
+            commSignalHalo(c, seq);
+            t.waitFlag[0] = m.left >= 0 ? &me->haloSeq[0] : nullptr;
+            t.waitFlag[1] = m.right >= 0 ? &me->haloSeq[1] : nullptr;
+            t.waitSeq = seq;
+            t.fusedReduce = 1;
+            t.red = reduceArgs(c);
+            profBegin(c, 1);
+            k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
+            profEnd(c);
+            c.launches++; c.timers.op_launches++;
+            return;
+        }
         launchForceVel<false, false>(c, x, c.rU.p, nullptr, c.dScal.p);
         if (multi) commPushU(c, ++c.comm.seqHalo);
         profBegin(c, 1);
         k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
         profEnd(c);
         c.launches++; c.timers.op_launches++;
-        if (multi) launchReduce(c, t);
+        if (multi) {
+            k_bb_reduce<<<1, 32, 0, st>>>(reduceArgs(c), t);
+            c.launches++;
+        }
     };
     // iteration 0: g0 = A x0 + b
     t.ite = 0; t.x = X[0]; t.xprev = X[0]; t.gprev = G[0]; t.gout = G[0];

@@ -1,6 +1,7 @@
 """Harness for the slab decomposition: run R ranks (one alens_ctx each, one host thread each) inside one process.
 With a single GPU every rank uses device 0; with >= R GPUs each rank gets its own device (same code path as the
 multi-process bench, only the bootstrap differs: alens_comm_connect_local instead of cudaIpc blobs)."""
+import os
 import threading
 
 import numpy as np
@@ -31,7 +32,9 @@ def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None,
     cutoff = 2 * max_r + colbuf
     skin = 0.25 * cutoff if skin is None else skin
     w = (hi[axis] - lo[axis]) / nranks
-    devices = devices or [0] * nranks
+    if devices is None:  # ALENS_TEST_DEVICES=0,1,...: spread the ranks over several GPUs (enables the fused kernels)
+        env = [int(x) for x in os.environ.get("ALENS_TEST_DEVICES", "0").split(",")]
+        devices = [env[r % len(env)] for r in range(nranks)]
     ctxs = []
     base = 0
     for r in range(nranks):
