@@ -384,10 +384,9 @@ int alens_reset_timers(alens_ctx *ctx) {
 int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
     return guarded(ctx, [&](Context &c) {
         const std::string k = name ? name : "";
-        if (k == "force_pipe") c.optForcePipe = (int)std::max(1LL, std::min(4LL, value));
+        if (k == "force_chunk") c.optForceChunk = value == 4 ? 4 : 2;
         else if (k == "tail_ctas_per_sm") c.optTailCtasPerSM = (int)std::max(1LL, std::min(8LL, value));
         else if (k == "comm_fused") c.comm.fused = value != 0;
-        else if (k == "pipe_debug") c.optPipeDebug = (int)value;
         else if (k == "bbpgd_batch") c.optBatch = (int)std::max(0LL, std::min(1024LL, value));
         else throw ArgError{ALENS_ERR_ARG, "alens_set_option: unknown option '" + k + "'"};
     });
@@ -396,8 +395,8 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
 int alens_time_kernel(alens_ctx *ctx, const char *which, int reps, double *avgMicroseconds) {
     return guarded(ctx, [&](Context &c) {
         const std::string k = which ? which : "";
-        const int w = k == "force_vel" ? 0 : (k == "tail" ? 1 : (k == "update" ? 2 : -1));
-        if (w < 0 || reps < 1) throw ArgError{ALENS_ERR_ARG, "alens_time_kernel: which = force_vel | tail | update"};
+        const int w = k == "force_vel" ? 0 : (k == "tail" ? 1 : (k == "force_vel_plain" ? 2 : -1));
+        if (w < 0 || reps < 1) throw ArgError{ALENS_ERR_ARG, "alens_time_kernel: which = force_vel | tail | force_vel_plain"};
         const double us = timeKernel(c, w, reps);
         if (avgMicroseconds) *avgMicroseconds = us;
     });

@@ -250,20 +250,20 @@ struct Context {
 
     // ---- incidence (rod -> constraints), built in setup ----
     DevBuf<int> incDeg, incStart, incFill; // nRods(+1)
-    DevBuf<int> incCon;                    // 2*constraint + side per slot, level-major inside a 32-rod group
+    DevBuf<int> incCon;                    // 4*constraint + 2*bilateral + side per slot, level-major inside a 32-rod group
     DevBuf<int> incRaw;                    // rod-major slot lists before k_inc_emit
     DevBuf<double> incCol;                 // 6 per slot: D column block for that (rod, constraint)
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
-    int optForcePipe = 3;                   // D x + M kernel: 1/2 = k_force_vel_pipe (1 / 2 CTAs per SM), 3/4 = k_force_vel_lm (chunk 2 / 4)
+    int optForceChunk = 2;                  // k_force_vel_lm: incidence levels per software-pipeline stage (2 or 4)
     int optTailCtasPerSM = 2;               // persistent grid of k_bb_tail
-    int optPipeDebug = 0;                   // timing experiments on k_force_vel_pipe (results invalid when != 0)
     int optBatch = 0;                       // BBPGD iterations enqueued per host check (0 = automatic)
     bool haveSetup = false;
     double dt = 0.0;
 
     // ---- solver vectors ----
-    DevBuf<double> vX0, vX1, vG0, vG1, vB, vLbFlag; // x/g ping-pong, q, bilateral flag as double
+    DevBuf<double> vX0, vX1, vG0, vG1, vB, vLbFlag; // x0 / unpacked iterates, APGD work, q, bilateral flag as double
+    DevBuf<double2> vXG0, vXG1;                     // BBPGD iterates as interleaved {x, g} pairs (ping-pong)
     DevBuf<double> vTmp0, vTmp1, vTmp2, vTmp3, vTmp4, vTmp5; // APGD work vectors
     DevBuf<double> rU, rF;                         // 6 per rod: vel, force of the last apply
     DevBuf<double> rUb, rFb;                       // bilateral part

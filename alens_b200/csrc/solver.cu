@@ -7,10 +7,12 @@
 //
 // D is never materialised as CSR.  A constraint k stores (n, posI, posJ, idxI, idxJ); row k of D^T is
 // [n, posI x n] on rod I and [-n, posJ x (-n)] on rod J (ConstraintCollector.cpp:298-341 with normJ = -normI).
-//   k_force_vel_pipe : f = D x (rod -> constraint incidence streamed through a TMA-bulk shared-memory ring),
-//                 u = M f applied analytically from (q, 1/drag) -- one launch per operator apply
-//   k_bb_tail   : y = D^T u + K^-1 x, g = y + b, projected-gradient residual, BB dot products,
-//                 deterministic two-level reduction, step-size/termination logic in the last CTA
+//   k_force_vel_lm : f = D x over the level-major rod -> constraint incidence, u = M f applied analytically from
+//                 (q, 1/drag) -- one launch per operator apply.  Inside the BBPGD loop x is not read but
+//                 recomputed on the fly as P(x_prev - alpha g_prev) from the interleaved {x, g} pairs
+//   k_bb_tail   : x = P(x_prev - alpha g_prev) again (same arithmetic, same bits), y = D^T u + K^-1 x, g = y + b,
+//                 projected-gradient residual, BB dot products, deterministic two-level reduction,
+//                 step-size/termination logic in the last CTA.  One BBPGD iteration = these two launches.
 // Compiled with -fmad=false so that elementwise arithmetic rounds like the CPU restatement.
 #include "context.hpp"
 #include "comm_dev.cuh"
@@ -97,14 +99,17 @@ __global__ void k_inc_count(long long nc, const int *__restrict__ idxI, const in
     if (j >= 0 && !ghost[j]) atomicAdd(&deg[j], 1);
 }
 
+// slot code = 4*constraint + 2*bilateral + side (side 1 = the J rod): the force kernel needs the bilateral flag
+// of a gathered constraint (lower bound of the projection, gamma_b mask) and gets it with the id
 __global__ void k_inc_fill(long long nc, const int *__restrict__ idxI, const int *__restrict__ idxJ,
-                           const unsigned char *__restrict__ ghost, const int *__restrict__ start,
-                           int *__restrict__ fill, int *__restrict__ incCon) {
+                           const unsigned char *__restrict__ bi, const unsigned char *__restrict__ ghost,
+                           const int *__restrict__ start, int *__restrict__ fill, int *__restrict__ incCon) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nc) return;
     const int i = idxI[k], j = idxJ[k];
-    if (!ghost[i]) incCon[start[i] + atomicAdd(&fill[i], 1)] = (int)(2 * k);
-    if (j >= 0 && !ghost[j]) incCon[start[j] + atomicAdd(&fill[j], 1)] = (int)(2 * k + 1);
+    const int code = (int)(4 * k) + (bi[k] ? 2 : 0);
+    if (!ghost[i]) incCon[start[i] + atomicAdd(&fill[i], 1)] = code;
+    if (j >= 0 && !ghost[j]) incCon[start[j] + atomicAdd(&fill[j], 1)] = code + 1;
 }
 
 struct ConGeom {
@@ -146,7 +151,7 @@ __global__ void k_inc_emit(int nRods, const int *__restrict__ start, int *__rest
         if (k < d) {
             const size_t s = (size_t)(off + __popc(m & lt));
             const int k2 = raw[b + k];
-            const size_t kk = (size_t)(k2 >> 1);
+            const size_t kk = (size_t)(k2 >> 2);
             const bool sideJ = k2 & 1;
             double gx = g.n[kk], gy = g.n[kk + g.stride], gz = g.n[kk + 2 * g.stride];
             const double *P = sideJ ? g.pJ : g.pI;
@@ -235,229 +240,6 @@ struct FvIn {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Persistent CTAs (one or two per SM) walk tiles of `tileRods` consecutive rods (a multiple of 32).  A tile's incidence range is 7 contiguous arrays (6 column components + constraint ids),
-// fetched with cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) into a 3-stage shared-memory ring and signalled
-// through mbarriers, so HBM stays busy while the warps gather x and sum.  Per iteration i the CTA
-//   (b) waits for tile i+1's bytes and issues its x gathers (L2) into registers,
-//   (c) sums tile i from shared memory (2 threads per rod: translation / rotation half) and applies M,
-//   (d) parks the gathered x of tile i+1 in shared memory,
-//   (f) issues the bulk copies of tile i+3 into the stage tile i just released and writes U coalesced.
-// Each rod's slots are summed in slot (= constraint id) order: no atomics, run-to-run bit-reproducible.
-// MASK: x is multiplied by the bilateral flag (gamma_b = gamma o biFlag, ConstraintSolver.cpp:99);
-// WRITE_F: the force f = D x is written as well (split, ConstraintSolver.cpp:100-106).
-__device__ __forceinline__ unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbarInit(unsigned long long *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbarExpectTx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarWait(unsigned long long *bar, unsigned parity) {
-    unsigned ok;
-    do { // try_wait suspends the thread in hardware until the phase flips or a time limit passes
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smemAddr(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smemAddr(dstSmem)),
-                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
-                 : "memory");
-}
-
-static constexpr int kPipeMaxTiles = 512; // tile bounds of one CTA are staged in shared memory up front
-
-template <int CAP, int NST, int NT>
-struct PipeSmem {
-    double col[NST][6][CAP];       // D column blocks of the staged slot range
-    double xs[NST][CAP];           // gathered x per slot
-    double mob[NST][6][NT / 2];    // qx, qy, qz, 1/zPara, 1/zPerp, 1/zRot of the tile's rods
-    double ust[2][(NT / 2) * 6];   // U of the tile, staged for a coalesced write
-    int con[NST][CAP];             // constraint id (x2 + side) per slot
-    int rs[NST][NT / 2 + 4];       // incStart[r0 .. r0+nR]
-    int2 tb[kPipeMaxTiles];        // (sBeg, sEnd) of every tile this CTA owns
-    unsigned long long bar[NST];
-};
-
-template <int CAP, int NST, int NT, int MINB, bool MASK, bool WRITE_F>
-__global__ void __launch_bounds__(NT, MINB)
-k_force_vel_pipe(FvIn in, MobIn mob, const double *__restrict__ x, const double *__restrict__ mask,
-                 double *__restrict__ U, double *__restrict__ F, const SolverScalars *__restrict__ scal,
-                 int tileRods, int nTiles, int dbg) {
-    // dbg (timing experiments only, results invalid): 1 = no x gather, 2 = no summation
-    extern __shared__ __align__(128) unsigned char smRaw[];
-    using Sm = PipeSmem<CAP, NST, NT>;
-    Sm &sm = *reinterpret_cast<Sm *>(smRaw);
-    constexpr int MAXR = NT / 2;  // 2 threads per rod
-    constexpr int GPT = CAP / NT; // x gathers per thread
-    static_assert(MAXR % 32 == 0, "a warp owns one 32-rod group");
-    if (scal && scal->done) return;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int allTiles = (nTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int half = tid / MAXR, lr = tid - half * MAXR, grp0 = (lr >> 5) * 32;
-    const unsigned lt = (1u << lane) - 1;
-
-    // the tile table holds kPipeMaxTiles entries: very large systems take several rounds
-    for (int base = 0; base < allTiles; base += kPipeMaxTiles) {
-        const int myTiles = min(kPipeMaxTiles, allTiles - base);
-        auto tileR0 = [&](int j) { return (int)(blockIdx.x + (base + j) * gridDim.x) * tileRods; };
-        auto tileNR = [&](int j) { return min(tileRods, in.nRods - tileR0(j)); };
-        __syncthreads();
-        for (int j = tid; j < myTiles; j += NT) {
-            const int r0 = tileR0(j);
-            sm.tb[j] = make_int2(__ldg(in.incStart + r0), __ldg(in.incStart + r0 + tileNR(j)));
-        }
-        if (tid == 0) {
-            for (int i = 0; i < NST; i++) {
-                if (base > 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smemAddr(&sm.bar[i])) : "memory");
-                mbarInit(&sm.bar[i], 1);
-            }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        // slot range of tile j rounded out to multiples of 4 (16-byte bulk copies): [a0, a0 + n4)
-        auto tileA0 = [&](int j) { return sm.tb[j].x & ~3; };
-        auto tileN4 = [&](int j) { return ((sm.tb[j].y + 3) & ~3) - (sm.tb[j].x & ~3); };
-        auto issue = [&](int j) { // thread 0 only, j < myTiles: all bulk copies of tile j into stage j % NST
-            const int st = j % NST, r0 = tileR0(j), nR = tileNR(j), n4 = tileN4(j), a0 = tileA0(j);
-            unsigned long long *bar = &sm.bar[st];
-            const unsigned nR2 = (unsigned)((nR + 1) & ~1), nR4 = (unsigned)((nR + 1 + 3) & ~3);
-            const bool slots = n4 > 0 && n4 <= CAP; // oversize tiles take the direct path
-            mbarExpectTx(bar, (slots ? (unsigned)n4 * 52u : 0u) + nR2 * 48u + nR4 * 4u);
-            if (slots) {
-#pragma unroll
-                for (int c = 0; c < 6; c++)
-                    bulkLoad(&sm.col[st][c][0], in.incCol + c * in.nInc + a0, (unsigned)n4 * 8u, bar);
-                bulkLoad(&sm.con[st][0], in.incCon + a0, (unsigned)n4 * 4u, bar);
-            }
-            bulkLoad(&sm.rs[st][0], in.incStart + r0, nR4 * 4u, bar);
-            bulkLoad(&sm.mob[st][0][0], mob.dx + r0, nR2 * 8u, bar);
-            bulkLoad(&sm.mob[st][1][0], mob.dy + r0, nR2 * 8u, bar);
-            bulkLoad(&sm.mob[st][2][0], mob.dz + r0, nR2 * 8u, bar);
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                bulkLoad(&sm.mob[st][3 + c][0], mob.invDrag + (size_t)c * mob.stride + r0, nR2 * 8u, bar);
-        };
-        double xg[GPT];
-        auto gatherIssue = [&](int j) { // x of tile j -> registers (tile j has landed)
-            const int st = j % NST;
-            const bool ok = j < myTiles && tileN4(j) <= CAP && !(dbg & 1);
-            const int lo = ok ? sm.tb[j].x - tileA0(j) : 0, hi = ok ? sm.tb[j].y - tileA0(j) : 0;
-#pragma unroll
-            for (int q = 0; q < GPT; q++) {
-                const int sl = tid + q * NT;
-                xg[q] = 0.0;
-                if (sl >= lo && sl < hi) {
-                    const int k = sm.con[st][sl] >> 1;
-                    double xv = __ldg(x + k);
-                    if (MASK) xv = 1.0 * xv * __ldg(mask + k);
-                    xg[q] = xv;
-                }
-            }
-        };
-        auto gatherStore = [&](int j) {
-            const int st = j % NST;
-#pragma unroll
-            for (int q = 0; q < GPT; q++) sm.xs[st][tid + q * NT] = xg[q];
-        };
-
-        if (tid == 0)
-            for (int j = 0; j < NST && j < myTiles; j++) issue(j);
-        mbarWait(&sm.bar[0], 0);
-        gatherIssue(0);
-
-        for (int i = 0; i < myTiles; i++) {
-            const int st = i % NST;
-            // (a) park the x of tile i (gathered during the previous iteration)
-            gatherStore(i);
-            __syncthreads();
-            // (b) tile i+1 has landed? request its x: the latency hides behind (c)..(f)
-            if (i + 1 < myTiles) mbarWait(&sm.bar[(i + 1) % NST], (unsigned)(((i + 1) / NST) & 1));
-            gatherIssue(i + 1);
-            // (c) sum tile i: thread (lr, half) owns 3 of the 6 components of rod lr; a warp walks its 32-rod
-            // group level by level (k-th slot of every rod), positions from ballot/popc
-            const int r0 = tileR0(i), nR = tileNR(i);
-            {
-                int d = 0;
-                if (lr < nR) d = sm.rs[st][lr + 1] - sm.rs[st][lr];
-                const int dmax = (dbg & 2) ? 0 : __reduce_max_sync(0xffffffffu, d);
-                double f0 = 0, f1 = 0, f2 = 0;
-                if (tileN4(i) <= CAP) {
-                    int off = sm.rs[st][min(grp0, nR)] - tileA0(i);
-                    const double *c0 = &sm.col[st][3 * half][0], *c1 = &sm.col[st][3 * half + 1][0],
-                                 *c2 = &sm.col[st][3 * half + 2][0], *xs = &sm.xs[st][0];
-#pragma unroll 2
-                    for (int k = 0; k < dmax; k++) {
-                        const unsigned m = __ballot_sync(0xffffffffu, k < d);
-                        if (k < d) {
-                            const int pos = off + __popc(m & lt);
-                            const double xv = xs[pos];
-                            f0 += c0[pos] * xv;
-                            f1 += c1[pos] * xv;
-                            f2 += c2[pos] * xv;
-                        }
-                        off += __popc(m);
-                    }
-                } else { // oversize tile: straight from global memory
-                    size_t off = (size_t)sm.rs[st][min(grp0, nR)];
-                    const double *c0 = in.incCol + (size_t)(3 * half) * in.nInc, *c1 = c0 + in.nInc, *c2 = c1 + in.nInc;
-                    for (int k = 0; k < dmax; k++) {
-                        const unsigned m = __ballot_sync(0xffffffffu, k < d);
-                        if (k < d) {
-                            const size_t pos = off + __popc(m & lt);
-                            const int kc = in.incCon[pos] >> 1;
-                            double xv = x[kc];
-                            if (MASK) xv = 1.0 * xv * mask[kc];
-                            f0 += c0[pos] * xv;
-                            f1 += c1[pos] * xv;
-                            f2 += c2[pos] * xv;
-                        }
-                        off += __popc(m);
-                    }
-                }
-                if (lr < nR) {
-                    if (WRITE_F) {
-                        double *fd = F + 6 * (size_t)(r0 + lr) + 3 * half;
-                        fd[0] = f0; fd[1] = f1; fd[2] = f2;
-                    }
-                    double *ud = &sm.ust[i & 1][lr * 6 + 3 * half];
-                    if (half == 0) { // Mtt = qq^T/zPara + (I - qq^T)/zPerp
-                        const double qx = sm.mob[st][0][lr], qy = sm.mob[st][1][lr], qz = sm.mob[st][2][lr];
-                        const double iPara = sm.mob[st][3][lr], iPerp = sm.mob[st][4][lr];
-                        const double qf = qx * f0 + qy * f1 + qz * f2;
-                        const double px = qf * qx, py = qf * qy, pz = qf * qz;
-                        ud[0] = iPara * px + iPerp * (f0 - px);
-                        ud[1] = iPara * py + iPerp * (f1 - py);
-                        ud[2] = iPara * pz + iPerp * (f2 - pz);
-                    } else { // Mrr = I/zRot
-                        const double iRot = sm.mob[st][5][lr];
-                        ud[0] = iRot * f0;
-                        ud[1] = iRot * f1;
-                        ud[2] = iRot * f2;
-                    }
-                }
-            }
-            __syncthreads(); // (e) U staged, stage `st` free
-            // (f) refill the freed stage, write U of tile i
-            if (tid == 0 && i + NST < myTiles) issue(i + NST);
-            {
-                const double2 *src = reinterpret_cast<const double2 *>(&sm.ust[i & 1][0]);
-                double2 *dst = reinterpret_cast<double2 *>(U + 6 * (size_t)r0);
-                for (int e = tid; e < nR * 3; e += NT) dst[e] = src[e];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // f = D x, u = M f straight from global memory: one warp per 32-rod group, lane = rod.  With the level-major
 // slot layout (k_inc_emit) the k-th slots of the 32 rods are adjacent, so every column / id load of a level is
 // one fully coalesced request; positions come from ballot/popc on the per-lane degree.  Levels are processed
@@ -473,11 +255,33 @@ struct HaloPush {
     int on;
 };
 
-template <int CHUNK, bool MASK, bool WRITE_F>
+// Where the force kernel takes x from.  XMODE 0: a plain vector.  XMODE 1: gamma_b = gamma o biFlag
+// (ConstraintSolver.cpp:99), the flag being bit 1 of the slot code.  XMODE 2: the BBPGD iterate is never stored
+// before it is used -- x = P(x_prev - alpha g_prev) (BCQPSolver.cpp:191-192, :431-459) is evaluated from the
+// interleaved {x_prev, g_prev} pair of the gathered constraint (one 16-byte gather), with the arithmetic of
+// k_bb_tail, which evaluates and stores the same x: both see identical bits.
+struct XIn {
+    const double *x;     // XMODE 0 / 1
+    const double2 *xg;   // XMODE 2: {x_prev, g_prev}
+    int update;          // XMODE 2: 0 = iteration 0 (x = x_prev as given), 1 = projected gradient step
+};
+
+// x = P(xp - alpha*gp); lb = -0.1*DBL_MAX*biFlag (-0.0 for unilateral rows, ConstraintSolver.cpp:69), ub = DBL_MAX/10
+__device__ __forceinline__ double bbStep(double xp, double gp, double alpha, bool bi) {
+    double v = (-alpha) * gp + 1.0 * xp;
+    const double lb = bi ? (-DBL_MAX * .1) : -0.0;
+    v = v > lb ? v : lb;
+    v = v < kHuge ? v : kHuge;
+    return v;
+}
+
+template <int CHUNK, int XMODE, bool WRITE_F>
 __global__ void __launch_bounds__(256)
-k_force_vel_lm(FvIn in, MobIn mob, const double *__restrict__ x, const double *__restrict__ mask,
-               double *__restrict__ U, double *__restrict__ F, const SolverScalars *__restrict__ scal, HaloPush hp) {
+k_force_vel_lm(FvIn in, MobIn mob, XIn xin, double *__restrict__ U, double *__restrict__ F,
+               const SolverScalars *__restrict__ scal, HaloPush hp) {
     if (scal && scal->done) return;
+    double alpha = 0.0;
+    if (XMODE == 2) alpha = scal->alpha; // plain load, L1 broadcast
 
     const int lane = threadIdx.x & 31;
     const int grp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -511,13 +315,15 @@ k_force_vel_lm(FvIn in, MobIn mob, const double *__restrict__ x, const double *_
     }
     for (int k0 = 0; k0 < dmax; k0 += CHUNK) {
         double xv[CHUNK], cv[CHUNK][6];
+        double2 xg[CHUNK];
 #pragma unroll
         for (int q = 0; q < CHUNK; q++) { // x gathers of this chunk (ids arrived one chunk ago)
             xv[q] = 0.0;
+            xg[q] = make_double2(0.0, 0.0);
             if (k0 + q < d) {
-                const int kc = con[q] >> 1;
-                xv[q] = __ldg(x + kc);
-                if (MASK) xv[q] = 1.0 * xv[q] * __ldg(mask + kc);
+                const int kc = con[q] >> 2;
+                if (XMODE == 2) xg[q] = ldGather2(xin.xg + kc);
+                else xv[q] = __ldg(xin.x + kc);
             }
         }
 #pragma unroll
@@ -535,8 +341,13 @@ k_force_vel_lm(FvIn in, MobIn mob, const double *__restrict__ x, const double *_
 #pragma unroll
         for (int q = 0; q < CHUNK; q++) {
             if (k0 + q < d) {
+                const bool bi = (con[q] & 2) != 0;
+                double x;
+                if (XMODE == 2) x = xin.update ? bbStep(xg[q].x, xg[q].y, alpha, bi) : xg[q].x;
+                else if (XMODE == 1) x = 1.0 * xv[q] * (bi ? 1.0 : 0.0);
+                else x = xv[q];
 #pragma unroll
-                for (int c = 0; c < 6; c++) f[c] += cv[q][c] * xv[q];
+                for (int c = 0; c < 6; c++) f[c] += cv[q][c] * x;
             }
         }
 #pragma unroll
@@ -651,25 +462,6 @@ __device__ __forceinline__ double projGrad(double x, double g, double lbFlag, in
     return 0.0;
 }
 
-// x = P(xprev - alpha*gprev)   (BCQPSolver.cpp:191-192, :431-459)
-__global__ void k_bb_update(long long nc, const double *__restrict__ xprev, const double *__restrict__ gprev,
-                            const double *__restrict__ lbFlag, double *__restrict__ x,
-                            const SolverScalars *__restrict__ scal) {
-    // plain loads: every thread reads the same two words, which L1 broadcasts (a volatile / system-scope
-    // load from 3.4M threads serialises on one L2 slice: 68 us instead of 20 us for this kernel)
-    const int done = scal->done;
-    const double alpha = scal->alpha;
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nc) return;
-    const double gp = ldStream(gprev + k), xp = ldStream(xprev + k), lbf = ldStream(lbFlag + k);
-    double v = (-alpha) * gp + 1.0 * xp;
-    const double lb = (-DBL_MAX * .1) * lbf;
-    v = v > lb ? v : lb;
-    v = v < kHuge ? v : kHuge;
-    if (done) return;
-    x[k] = v;
-}
-
 struct ReduceArgs {
     double *mailPeer[kMaxRanks];             // my slot in each peer's mailbox of this parity
     unsigned long long *seqPeer[kMaxRanks];
@@ -682,8 +474,10 @@ struct ReduceArgs {
 struct BbTail {
     long long nc;
     ConGeom g;
-    const double *U, *x, *xprev, *gprev, *b, *invKdt, *lbFlag;
-    double *gout;
+    const double *U, *b, *invKdt;
+    const double2 *xgPrev; // {x, g} of the previous iteration (iteration 0: {x0, anything})
+    double2 *xgOut;        // {x, g} of this iteration (iteration 0: written in place)
+    const unsigned char *bi;
     double *partial; // [gridDim][4]
     SolverScalars *scal;
     double *hist;
@@ -733,33 +527,53 @@ __device__ __forceinline__ void bbScalarStep(const BbTail &p, const double out[4
     }
 }
 
-// all streaming operands of constraint row k (136 B)
+// all streaming operands of constraint row k: 2 ids + 9 geometry doubles + {x_prev, g_prev} + b (+ K^-1/dt) + flag
+// = 113 B (121 B with K^-1), plus the 16-byte {x, g} store
 struct TailRow {
     int iI, iJ;
-    double gx, gy, gz, pIx, pIy, pIz, pJx, pJy, pJz, x, invK, b, lbf, xp, gp;
+    double gx, gy, gz, pIx, pIy, pIz, pJx, pJy, pJz, invK, b;
+    double2 xg;
+    unsigned char bi;
 };
+__device__ __forceinline__ double2 ldStream2(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned char ldStreamU8(const unsigned char *p) {
+    unsigned v;
+    asm volatile("ld.global.cs.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return (unsigned char)v;
+}
+template <bool HASK>
 __device__ __forceinline__ void loadTailRow(const BbTail &p, size_t k, TailRow &r) {
     const size_t S = p.g.stride;
     r.iI = ldStream(p.g.idxI + k); r.iJ = ldStream(p.g.idxJ + k);
     r.gx = ldStream(p.g.n + k); r.gy = ldStream(p.g.n + k + S); r.gz = ldStream(p.g.n + k + 2 * S);
     r.pIx = ldStream(p.g.pI + k); r.pIy = ldStream(p.g.pI + k + S); r.pIz = ldStream(p.g.pI + k + 2 * S);
     r.pJx = ldStream(p.g.pJ + k); r.pJy = ldStream(p.g.pJ + k + S); r.pJz = ldStream(p.g.pJ + k + 2 * S);
-    r.x = ldStream(p.x + k); r.invK = ldStream(p.invKdt + k); r.b = ldStream(p.b + k);
-    r.lbf = ldStream(p.lbFlag + k); r.xp = ldStream(p.xprev + k); r.gp = ldStream(p.gprev + k);
+    r.xg = ldStream2(p.xgPrev + k);
+    r.b = ldStream(p.b + k);
+    r.invK = HASK ? ldStream(p.invKdt + k) : 0.0;
+    r.bi = ldStreamU8(p.bi + k);
 }
 
-// g = A x + b, residual, BB dots; the last CTA to finish turns the partials into the next step size
-// (BCQPSolver.cpp:195-233) -- one launch replaces ~9 vector passes and 3 allreduces.
+// x = P(x_prev - alpha g_prev), g = A x + b, residual, BB dots; the last CTA to finish turns the partials into the
+// next step size (BCQPSolver.cpp:191-233) -- one launch replaces ~10 vector passes and 3 allreduces.
 // Persistent grid-stride kernel, software-pipelined: the streaming operands of the NEXT row are requested
 // before the rod velocities of the CURRENT row are gathered, so a thread always has one DRAM round trip
-// (136 B) and one L2 round trip (96 B) in flight and never waits on an index before issuing loads.
+// and one L2 round trip (96 B) in flight and never waits on an index before issuing loads.
+// HASK = false: no row has a finite stiffness (K^-1 = 0 everywhere: collision-only pools), the K^-1 x term and its
+// 8 B/row are skipped.
+template <bool HASK>
 __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     const int done = p.scal->done;
+    const double alpha = p.scal->alpha; // plain loads: every thread reads the same two words, which L1 broadcasts
     const long long stride = (long long)gridDim.x * kVecBlock;
     long long k = (long long)blockIdx.x * kVecBlock + threadIdx.x;
     double s0 = 0, s1 = 0, s2 = 0, mx = 0;
     TailRow cur, nxt;
-    if (k < p.nc) loadTailRow(p, (size_t)k, cur);
+    if (k < p.nc) loadTailRow<HASK>(p, (size_t)k, cur);
     if (done) return;
     if (p.waitSeq) { // ghost rows of U: pushed by the neighbours' k_force_vel_lm (streaming loads above are in flight)
         if (threadIdx.x == 0) {
@@ -770,11 +584,13 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     }
     while (k < p.nc) {
         const long long kn = k + stride;
-        if (kn < p.nc) loadTailRow(p, (size_t)kn, nxt);
+        if (kn < p.nc) loadTailRow<HASK>(p, (size_t)kn, nxt);
         const double2 *uI = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)cur.iI);
         const double2 *uJ = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)(cur.iJ >= 0 ? cur.iJ : cur.iI));
         const double2 a = ldGather2(uI), b = ldGather2(uI + 1), c = ldGather2(uI + 2);
         const double2 d = ldGather2(uJ), e = ldGather2(uJ + 1), f = ldGather2(uJ + 2);
+        const double xp = cur.xg.x, gp = cur.xg.y;
+        const double x = p.ite > 0 ? bbStep(xp, gp, alpha, cur.bi != 0) : xp;
         const double gx = cur.gx, gy = cur.gy, gz = cur.gz;
         double y = gx * a.x;
         y += gy * a.y;
@@ -791,15 +607,15 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
             y += (hx * cur.pJz - hz * cur.pJx) * f.x;
             y += (hy * cur.pJx - hx * cur.pJy) * f.y;
         }
-        y += 1.0 * cur.invK * cur.x;
+        if (HASK) y += 1.0 * cur.invK * x;
         const double gk = 1.0 * cur.b + 1.0 * y;
-        p.gout[k] = gk;
+        p.xgOut[k] = make_double2(x, gk);
         int err = 0;
-        const double q = projGrad(cur.x, gk, cur.lbf, err);
+        const double q = projGrad(x, gk, cur.bi ? 1.0 : 0.0, err);
         mx = fmax(mx, err ? INFINITY : fabs(q));
         if (p.ite > 0 && (!p.own || p.own[k])) { // a row mirrored on two ranks is counted by the owner of rod I
-            const double dx = 1.0 * cur.x + (-1.0) * cur.xp;
-            const double dg = 1.0 * gk + (-1.0) * cur.gp;
+            const double dx = 1.0 * x + (-1.0) * xp;
+            const double dg = 1.0 * gk + (-1.0) * gp;
             s0 += dx * dx;
             s1 += dx * dg;
             s2 += dg * dg;
@@ -854,6 +670,19 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
             bbScalarStep(p, out);
         }
     }
+}
+
+// BBPGD keeps its iterates as interleaved {x, g} pairs: start from x0, and unpack the two newest iterates afterwards
+__global__ void k_bb_init(long long nc, const double *__restrict__ x0, double2 *__restrict__ xg) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nc) xg[k] = make_double2(x0[k], 0.0);
+}
+__global__ void k_bb_extract(long long nc, const double2 *__restrict__ xgNew, const double2 *__restrict__ xgOld,
+                             double *__restrict__ xNew, double *__restrict__ xOld) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    xNew[k] = xgNew[k].x;
+    if (xgOld) xOld[k] = xgOld[k].x;
 }
 
 // multi-rank end of a BBPGD iteration: every rank drops its 4 partials into every peer's mailbox (remote
@@ -1077,7 +906,8 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
         ALENS_CUDA(cudaStreamSynchronize(st));
         nInc = tot;
     }
-    if (nInc > 0x7fffffffLL - 16) throw ArgError{ALENS_ERR_UNSUPPORTED, "setup: more than 2^31 incidence slots"};
+    if (nInc > 0x7fffffffLL - 16 || nc >= (1LL << 29))
+        throw ArgError{ALENS_ERR_UNSUPPORTED, "setup: more than 2^29 constraints / 2^31 incidence slots on one GPU"};
     c.nInc = nInc;
     c.incStride = ((nInc + 3) & ~3LL) + 4; // component stride: 16-byte aligned bulk copies may over-read < 4 slots
     c.incCon.reserve((size_t)c.incStride + 4);
@@ -1092,8 +922,8 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.outFB.reserve(6 * (size_t)n + 6); c.outVB.reserve(6 * (size_t)n + 6);
     c.redPartial.reserve(4 * (size_t)(gridFor(std::max<long long>(nc, 1), kVecBlock) + 1));
     if (nc > 0) {
-        k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.sGhost.p, c.incStart.p, c.incFill.p,
-                                                     c.incRaw.p);
+        k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.cBi.p, c.sGhost.p, c.incStart.p,
+                                                     c.incFill.p, c.incRaw.p);
         k_inc_emit<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incRaw.p, conGeom(c), c.incCon.p, c.incCol.p,
                                                     (size_t)c.incStride);
         k_setup<<<gridFor(nc, 256), 256, 0, st>>>(nc, conGeom(c), c.sUser.p, useV ? c.uVelNC.p : nullptr,
@@ -1138,46 +968,23 @@ void profFlush(Context &c) { // call after a stream synchronisation
     c.profUsed = 0;
 }
 
-template <int CAP, int NT, int MINB, bool MASK, bool WF>
-static void launchPipe(Context &c, const double *x, double *U, double *F, const SolverScalars *scal) {
-    using Sm = PipeSmem<CAP, 3, NT>;
-    auto kern = k_force_vel_pipe<CAP, 3, NT, MINB, MASK, WF>;
-    static bool attr = false;
-    if (!attr) {
-        ALENS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sm)));
-        attr = true;
-    }
-    // rods per tile: a multiple of 32 (one warp per 32-rod group, 2 threads per rod) filling ~85 % of the
-    // stage capacity on average; denser tiles fall back to direct global reads inside the kernel
-    const int n = c.nRods;
-    const double avgDeg = std::max(1.0, (double)c.nInc / n);
-    int tileRods = (int)(0.85 * CAP / avgDeg) & ~31;
-    tileRods = std::max(32, std::min(NT / 2, tileRods));
-    const int nTiles = gridFor(n, tileRods);
-    const int grid = std::min(nTiles, c.numSMs * MINB);
-    kern<<<grid, NT, sizeof(Sm), c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal, tileRods, nTiles,
-                                             c.optPipeDebug);
-}
-
-template <bool MASK, bool WF>
-static void launchForceVel(Context &c, const double *x, double *U, double *F, const SolverScalars *scal,
+template <int XMODE, bool WF>
+static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, const SolverScalars *scal,
                            const HaloPush *push = nullptr) {
     const int n = c.nRods;
     const HaloPush hp = push ? *push : HaloPush{};
     if (n == 0 && !push) return;
     profBegin(c, 0);
     const int grid = std::max(1, gridFor((long long)gridFor(n, 32) * 32, 256));
-    const int variant = c.comm.active && c.optForcePipe < 3 ? 3 : c.optForcePipe; // ghost rows: lm kernels only
-    if (variant == 1) launchPipe<1024, 256, 1, MASK, WF>(c, x, U, F, scal);     // 1 CTA / SM, 3 x 52 KB ring
-    else if (variant == 2) launchPipe<512, 128, 2, MASK, WF>(c, x, U, F, scal); // 2 CTAs / SM, 26 KB stages
-    else if (variant == 4)
-        k_force_vel_lm<4, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal, hp);
+    if (c.optForceChunk == 4)
+        k_force_vel_lm<4, XMODE, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), xin, U, F, scal, hp);
     else
-        k_force_vel_lm<2, MASK, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), x, c.vLbFlag.p, U, F, scal, hp);
+        k_force_vel_lm<2, XMODE, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), xin, U, F, scal, hp);
     profEnd(c);
     c.launches++;
     c.timers.op_launches++;
 }
+static XIn xPlain(const double *x) { return XIn{x, nullptr, 0}; }
 
 void operatorApply(Context &c, const double *x, double *y, double *force, double *vel) {
     if (!c.haveSetup) throw ArgError{ALENS_ERR_STATE, "alens_operator_apply: call alens_setup_constraints first"};
@@ -1188,7 +995,7 @@ void operatorApply(Context &c, const double *x, double *y, double *force, double
     c.vTmp0.reserve((size_t)nc + 1);
     c.vTmp1.reserve((size_t)nc + 1);
     if (nc > 0) ALENS_CUDA(cudaMemcpyAsync(c.vTmp0.p, x, 8 * (size_t)nc, cudaMemcpyHostToDevice, st));
-    launchForceVel<false, true>(c, c.vTmp0.p, c.rU.p, c.rF.p, nullptr);
+    launchForceVel<0, true>(c, xPlain(c.vTmp0.p), c.rU.p, c.rF.p, nullptr);
     if (nc > 0) {
         k_dtrans<<<gridFor(nc, kVecBlock), kVecBlock, 0, st>>>(nc, conGeom(c), c.rU.p, c.vTmp0.p, c.vTmp5.p,
                                                                c.vTmp1.p);
@@ -1236,24 +1043,36 @@ static ReduceArgs reduceArgs(Context &c) { // next mailbox round
     return a;
 }
 
+static void launchTail(Context &c, const BbTail &t, int gridTail) {
+    profBegin(c, 1);
+    if (c.nBilateral > 0) k_bb_tail<true><<<gridTail, kVecBlock, 0, c.stream>>>(t);
+    else k_bb_tail<false><<<gridTail, kVecBlock, 0, c.stream>>>(t);
+    profEnd(c);
+    c.launches++;
+    c.timers.op_launches++;
+}
+
 static int solveBBPGD(Context &c, double tol, int maxIte) {
     cudaStream_t st = c.stream;
     const long long nc = c.nCon;
     const bool multi = c.comm.active;
-    double *X[2] = {c.vX0.p, c.vX1.p}, *G[2] = {c.vG0.p, c.vG1.p};
+    c.vXG0.reserve((size_t)nc + 1);
+    c.vXG1.reserve((size_t)nc + 1);
+    double2 *XG[2] = {c.vXG0.p, c.vXG1.p};
     const int grid = std::max(1, gridFor(nc, kVecBlock));
     const int gridTail = std::min(grid, c.numSMs * c.optTailCtasPerSM); // persistent (2 resident CTAs per SM)
     BbTail t{};
-    t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.lbFlag = c.vLbFlag.p;
+    t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.bi = c.cBi.p;
     t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = c.histCap; t.tol = tol;
     if (multi) {
         t.own = c.cOwn.p;
         t.redOut = reinterpret_cast<double *>(c.dCounters.p); // 4 doubles of scratch
     }
-    // one operator apply + fused tail; multi-rank: ghost rows of U are pushed to / awaited from the neighbours
-    // between the two kernels, and k_bb_reduce replaces the last-CTA scalar step
+    // one BBPGD iteration = force kernel (x recomputed from {x_prev, g_prev} on the fly, f = D x, u = M f) + tail;
+    // multi-rank: ghost rows of U are pushed to / awaited from the neighbours between the two kernels, and
+    // k_bb_reduce replaces the last-CTA scalar step
     const bool fused = multi && c.comm.fused;
-    auto applyAndTail = [&](const double *x) {
+    auto applyAndTail = [&](const XIn &x) {
         if (fused) {
             // the force kernel also stores the mirrored rows of U into the neighbours' windows, a one-thread kernel
             // releases their halo flags; the tail waits for its own flags before the first gather and finishes
@@ -1269,33 +1088,31 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
                 hp.rem[d] = reinterpret_cast<double *>(m.peerWin[q] + m.offU);
             }
             hp.on = 1;
-            launchForceVel<false, false>(c, x, c.rU.p, nullptr, c.dScal.p, &hp);
+            launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p, &hp);
             commSignalHalo(c, seq);
             t.waitFlag[0] = m.left >= 0 ? &me->haloSeq[0] : nullptr;
             t.waitFlag[1] = m.right >= 0 ? &me->haloSeq[1] : nullptr;
             t.waitSeq = seq;
             t.fusedReduce = 1;
             t.red = reduceArgs(c);
-            profBegin(c, 1);
-            k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
-            profEnd(c);
-            c.launches++; c.timers.op_launches++;
+            launchTail(c, t, gridTail);
             return;
         }
-        launchForceVel<false, false>(c, x, c.rU.p, nullptr, c.dScal.p);
+        launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p);
         if (multi) commPushU(c, ++c.comm.seqHalo);
-        profBegin(c, 1);
-        k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
-        profEnd(c);
-        c.launches++; c.timers.op_launches++;
+        launchTail(c, t, gridTail);
         if (multi) {
             k_bb_reduce<<<1, 32, 0, st>>>(reduceArgs(c), t);
             c.launches++;
         }
     };
-    // iteration 0: g0 = A x0 + b
-    t.ite = 0; t.x = X[0]; t.xprev = X[0]; t.gprev = G[0]; t.gout = G[0];
-    applyAndTail(X[0]);
+    // iteration 0: g0 = A x0 + b, {x0, g0} written in place
+    if (nc > 0) {
+        k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, XG[0]);
+        c.launches++;
+    }
+    t.ite = 0; t.xgPrev = XG[0]; t.xgOut = XG[0];
+    applyAndTail(XIn{nullptr, XG[0], 0});
     int ite = 0;
     const int batch = c.optBatch > 0 ? c.optBatch : (nc > 200000 || multi ? 8 : 32);
     syncScalars(c);
@@ -1305,12 +1122,8 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
         for (int b = 0; b < nb; b++) {
             ite++;
             const int cur = (ite - 1) & 1, nxt = ite & 1;
-            profBegin(c, 2);
-            k_bb_update<<<grid, kVecBlock, 0, st>>>(nc, X[cur], G[cur], c.vLbFlag.p, X[nxt], c.dScal.p);
-            profEnd(c);
-            c.launches++; c.timers.op_launches++;
-            t.ite = ite; t.x = X[nxt]; t.xprev = X[cur]; t.gprev = G[cur]; t.gout = G[nxt];
-            applyAndTail(X[nxt]);
+            t.ite = ite; t.xgPrev = XG[cur]; t.xgOut = XG[nxt];
+            applyAndTail(XIn{nullptr, XG[cur], 1});
         }
         syncScalars(c);
         if (c.hScal->done) c.profUsed = 0; // this batch contains early-exit no-ops: not representative
@@ -1319,9 +1132,14 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     ALENS_CUDA(cudaGetLastError());
     if (c.hScal->done == 4) throw ArgError{ALENS_ERR_COMM, "solve: timed out waiting for a peer rank"};
     const int n = c.hScal->ite; // iterations actually executed
-    c.xLastApplied = X[n & 1];
-    if (c.hScal->done || n == 0) c.xSolution = X[n & 1];
-    else c.xSolution = X[(n - 1) & 1]; // iteMax exit returns the older iterate (BCQPSolver.cpp:237-241)
+    // unpack: vX0 = the iterate the operator last saw, vX1 = the one before it
+    const bool older = !(c.hScal->done || n == 0);
+    if (nc > 0) {
+        k_bb_extract<<<grid, kVecBlock, 0, st>>>(nc, XG[n & 1], older ? XG[(n - 1) & 1] : nullptr, c.vX0.p, c.vX1.p);
+        c.launches++;
+    }
+    c.xLastApplied = c.vX0.p;
+    c.xSolution = older ? c.vX1.p : c.vX0.p; // iteMax exit returns the older iterate (BCQPSolver.cpp:237-241)
     return c.hScal->done == 2 ? 1 : 0;
 }
 
@@ -1334,17 +1152,20 @@ double timeKernel(Context &c, int which, int reps) {
     const int grid = gridFor(nc, kVecBlock);
     const int gridTail = std::min(grid, c.numSMs * c.optTailCtasPerSM);
     ALENS_CUDA(cudaMemsetAsync(c.dScal.p, 0, sizeof(SolverScalars), st));
+    c.vXG0.reserve((size_t)nc + 1);
+    c.vXG1.reserve((size_t)nc + 1);
+    k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, c.vXG0.p);
     BbTail t{};
-    t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.lbFlag = c.vLbFlag.p;
+    t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.bi = c.cBi.p;
     t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = 0; t.tol = -1.0;
-    t.ite = 1; t.x = c.vX0.p; t.xprev = c.vX0.p; t.gprev = c.vB.p; t.gout = c.vG1.p;
+    t.ite = 1; t.xgPrev = c.vXG0.p; t.xgOut = c.vXG1.p;
     ALENS_CUDA(cudaMemsetAsync(c.rU.p, 0, 48 * (size_t)c.nRods, st));
     const bool prof = c.profiling;
     c.profiling = false;
     auto one = [&]() {
-        if (which == 0) launchForceVel<false, false>(c, c.vX0.p, c.rU.p, nullptr, c.dScal.p);
-        else if (which == 1) k_bb_tail<<<gridTail, kVecBlock, 0, st>>>(t);
-        else k_bb_update<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, c.vB.p, c.vLbFlag.p, c.vX1.p, c.dScal.p);
+        if (which == 0) launchForceVel<2, false>(c, XIn{nullptr, c.vXG0.p, 1}, c.rU.p, nullptr, c.dScal.p);
+        else if (which == 1) launchTail(c, t, gridTail);
+        else launchForceVel<0, false>(c, xPlain(c.vX0.p), c.rU.p, nullptr, c.dScal.p);
     };
     for (int i = 0; i < 3; i++) one();
     ALENS_CUDA(cudaEventRecord(c.ev[5], st));
@@ -1371,7 +1192,7 @@ static void dot3(Context &c, long long n, const Dot3 &p, double out[4]) {
 }
 
 static void applyA(Context &c, const double *x, double *y) { // y = A x, caches U
-    launchForceVel<false, false>(c, x, c.rU.p, nullptr, nullptr);
+    launchForceVel<0, false>(c, xPlain(x), c.rU.p, nullptr, nullptr);
     k_dtrans<<<gridFor(c.nCon, kVecBlock), kVecBlock, 0, c.stream>>>(c.nCon, conGeom(c), c.rU.p, x, c.vTmp5.p, y);
     c.launches++; c.timers.op_launches++;
     c.xLastApplied = const_cast<double *>(x);
@@ -1524,9 +1345,9 @@ void solveCore(Context &c, double tol, int maxIte, int choice) {
     ALENS_CUDA(cudaEventRecord(c.ev[3], st));
     // split (ConstraintSolver.cpp:95-106): force/vel of the LAST apply minus the bilateral part
     if (nc > 0 || multi) {
-        launchForceVel<false, true>(c, c.xLastApplied, c.rU.p, c.rF.p, nullptr);
+        launchForceVel<0, true>(c, xPlain(c.xLastApplied), c.rU.p, c.rF.p, nullptr);
         // no bilateral block in the pool: gamma_b = 0, the bilateral force/velocity are exactly zero
-        if (c.nBilateral > 0) launchForceVel<true, true>(c, c.xSolution, c.rUb.p, c.rFb.p, nullptr);
+        if (c.nBilateral > 0) launchForceVel<1, true>(c, xPlain(c.xSolution), c.rUb.p, c.rFb.p, nullptr);
     }
     if (n > 0) {
         const bool bi = nc > 0 && c.nBilateral > 0;
@@ -1575,8 +1396,10 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_setup));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_dtrans));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_update));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_tail));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_init));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_extract));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_tail<true>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_tail<false>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_reduce));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_update2));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_fill));
@@ -1585,12 +1408,14 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_split_out));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_permute6_to_user));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_step_euler));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, false, false>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, false, true>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, true, true>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, false, false>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, false, true>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, true, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, 0, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, 0, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, 1, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<2, 2, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 0, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 0, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 1, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 2, false>)));
 }
 
 } // namespace alens

@@ -329,10 +329,12 @@ def main():
     # ---- roofline of the dominant BCQP kernel (algorithmic bytes: DESIGN.md "Kernels") ----
     peak, peak_src = peaks()
     ninc = 2 * nc  # two-sided constraints only in this workload
+    # k_force_vel_lm: 52 B per incidence slot (6 column doubles + id), the {x, g} pair of every constraint once
+    # (16 B), q + 1/drag (48 B) and the U row (48 B) per rod.  k_bb_tail (collision-only pool, no K^-1 term):
+    # 2 ids + 9 geometry doubles + {x, g} in + b + flag = 113 B read, {x, g} out = 16 B written per constraint.
     kern = {
-        "k_force_vel": (tm["op_force_vel_ms"], tm["op_force_vel_n"], 52.0 * ninc + 8.0 * nc + 96.0 * n),
-        "k_bb_tail": (tm["op_dtrans_ms"], tm["op_dtrans_n"], 136.0 * nc),
-        "k_bb_update": (tm["op_update_ms"], tm["op_update_n"], 32.0 * nc),
+        "k_force_vel_lm": (tm["op_force_vel_ms"], tm["op_force_vel_n"], 52.0 * ninc + 16.0 * nc + 96.0 * n),
+        "k_bb_tail": (tm["op_dtrans_ms"], tm["op_dtrans_n"], 129.0 * nc),
     }
     dom = max(kern, key=lambda k: kern[k][0])
     t_ms, cnt, bytes_ = kern[dom]

@@ -17,6 +17,6 @@ timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
     --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_launch.log 2>&1
 tail -2 gpurun_out/ncu_launch.log
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
-    -k regex:"k_force_vel|k_bb_tail|k_pairs|k_bb_update|k_inc_finish" -c 12 -f -o gpurun_out/prof python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
+    -k regex:"k_force_vel|k_bb_tail|k_pairs|k_inc_emit" -c 10 -f -o gpurun_out/prof python tools/profile_step.py > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 ls -la gpurun_out

@@ -1,5 +1,5 @@
 """Micro-benchmark of the BBPGD kernels on the 1M-rod bench workload (alens_time_kernel) under option sets.
-ALENS_MICRO='[{"force_pipe":1},...]' python tools/kernel_micro.py [n_rods]"""
+ALENS_MICRO='[{"force_chunk":4},...]' python tools/kernel_micro.py [n_rods]"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -15,12 +15,12 @@ vnc = thermal_velocity(rods, bench.MU, bench.DT, seed=bench.SEED + 17)
 ctx.set_rods(rods["gid"], rods["pos"], rods["quat"], rods["length"], rods["radius"], rods["immovable"])
 nc = ctx.collect_pair_collision()
 ctx.calc_mobility(bench.MU)
-sets = json.loads(os.environ.get("ALENS_MICRO", "null")) or [{"force_pipe": 0}, {"force_pipe": 1}, {"force_pipe": 2}]
+sets = json.loads(os.environ.get("ALENS_MICRO", "null")) or [{"force_chunk": 2}, {"force_chunk": 4}]
 for opts in sets:
     for k, v in opts.items():
         ctx.set_option(k, v)
     row = {"opts": opts, "nc": nc}
-    for which in ("force_vel", "tail", "update"):
+    for which in ("force_vel", "tail", "force_vel_plain"):
         ctx.setup_constraints(vnc, bench.DT)
         row[which + "_us"] = round(ctx.time_kernel(which, 30), 2)
     print(json.dumps(row), flush=True)
