@@ -385,6 +385,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
     return guarded(ctx, [&](Context &c) {
         const std::string k = name ? name : "";
         if (k == "force_chunk") c.optForceChunk = value == 4 ? 4 : 2;
+        else if (k == "force_block") c.optForceBlock = value == 32 ? 32 : (value == 64 ? 64 : (value == 128 ? 128 : 256));
         else if (k == "tail_ctas_per_sm") c.optTailCtasPerSM = (int)std::max(1LL, std::min(8LL, value));
         else if (k == "comm_fused") c.comm.fused = value != 0;
         else if (k == "bbpgd_batch") c.optBatch = (int)std::max(0LL, std::min(1024LL, value));

@@ -339,18 +339,44 @@ __device__ __forceinline__ int narrowBatch(const PairIn &in, const Box &box, dou
     return nh;
 }
 
-// One warp per cell.  The half stencil (own cell + 13 "positive" neighbours) is walked as 5 rows of
-// x-adjacent cells: cells adjacent in x are adjacent in the sorted arrays, so a row is one contiguous
-// range of source rods (plus at most two wrapped single cells at a periodic boundary).
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+// ------------------------------------------------------------------------------------------------
+// Search kernel.  One warp per cell.  The half stencil (own cell + 13 "positive" neighbours) is walked as 5 rows of
+// x-adjacent cells: cells adjacent in x are adjacent in the sorted arrays, so a row is one contiguous range of source
+// rods (plus at most two wrapped single cells at a periodic boundary).  Three stages with two warp-private
+// compaction queues, so that every stage runs on (nearly) full warps.
+//   stage 1  bounding-sphere test, fp32, lanes = source rods (two per lane: independent dependency chains),
+//            loop over the target tile; passers are queued as (target slot, source slot)
+//   stage 2  on 32 queued pairs at a time: the two point/axis capsule tests, fp32, operands of both rods from
+//            the shared-memory tiles; passers are queued as (i, j, image code)
+//   stage 3  narrowBatch: exact fp64 closest-point query on 32 queued candidates at a time
+// (The first version of this kernel ran the capsule tests for the whole warp whenever ANY lane passed an fp64 sphere
+// test -- 56 % of the iterations for 2.5 % of the lanes; profiles/README.md.)
+// The broad phase works on coordinates RELATIVE TO THE CENTRE OF THE TARGET CELL in fp32.  Conservativeness:
+// converting a relative coordinate to fp32 moves a centre by at most 2^-24 |coord| per axis; every rod carries
+// eps = 2^-22 (|x-Ox| + |y-Oy| + |z-Oz|) in its radius-like terms (rounded up), the fp32 arithmetic (relative error
+// ~1e-6 of |dd| <= cut once the sphere test has passed) is covered by the factor 1 + 2e-5 and the absolute slack
+// 1e-5 cut.  A pair the fp64 narrow phase would accept is never rejected; what is accepted in excess is decided
+// exactly by the narrow phase.  The candidate order (hence the constraint order inside a cell) is deterministic:
+// (target tile, stencil row, source tile, target, source).
+static constexpr int kJTile = 64; // source rods staged per warp
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ cellHits, int4 *__restrict__ hitList,
-             unsigned long long hitCap, unsigned long long *__restrict__ counters) {
-    __shared__ double sP[kWarpsPerCta][4][kITile]; // x, y, z, A = h + rho + colBuf (+ rounding slack)
-    __shared__ float sF[kWarpsPerCta][5][kITile];  // ux, uy, uz, h, B = rho + colBuf (+ slack)
-    __shared__ int sQ[kWarpsPerCta][3][kQueue];    // queue: i, j, image code
-    __shared__ signed char sG[kWarpsPerCta][kITile]; // target: image along the slab axis, +64 if ghost
+              unsigned long long hitCap, unsigned long long *__restrict__ counters) {
+    __shared__ float4 tA[kWarpsPerCta][kITile]; // target: x, y, z (relative), A = h + rho + colBuf + slack
+    __shared__ float4 tB[kWarpsPerCta][kITile]; //         ux, uy, uz, h
+    __shared__ float2 tC[kWarpsPerCta][kITile]; //         B = rho + colBuf + slack, B + h
+    __shared__ float4 jA[kWarpsPerCta][kJTile]; // source: x, y, z (relative, image applied), S = h + rho + eps
+    __shared__ float4 jB[kWarpsPerCta][kJTile]; //         ux, uy, uz, h
+    __shared__ float jC[kWarpsPerCta][kJTile];  //         rho + eps
+    __shared__ unsigned short sQ1[kWarpsPerCta][32 + 2 * 32]; // stage-1 queue: target slot | source slot << 6
+    __shared__ int sQ[kWarpsPerCta][3][kQueue];               // stage-2 queue: i, j, image code
+    __shared__ signed char sG[kWarpsPerCta][kITile];  // target: image along the slab axis, +64 if ghost
+    __shared__ signed char sGj[kWarpsPerCta][kJTile]; // source: same
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1;
     const int axMul = g.axis == 0 ? 1 : (g.axis == 1 ? 3 : (g.axis == 2 ? 9 : 0));
+    const bool multi = g.axis >= 0; // ghost rods exist
     const int cell = blockIdx.x * kWarpsPerCta + w;
     if (cell >= g.ncell) return;
     const int ib = in.cellStart[cell], ie = in.cellStart[cell + 1];
@@ -359,12 +385,17 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
         return;
     }
     const int cx = cell % g.n[0], cy = (cell / g.n[0]) % g.n[1], cz = cell / (g.n[0] * g.n[1]);
+    const double Ox = g.inv[0] > 0 ? g.lo[0] + (cx + 0.5) / g.inv[0] : g.lo[0];
+    const double Oy = g.inv[1] > 0 ? g.lo[1] + (cy + 0.5) / g.inv[1] : g.lo[1];
+    const double Oz = g.inv[2] > 0 ? g.lo[2] + (cz + 0.5) / g.inv[2] : g.lo[2];
+    unsigned short *q1 = sQ1[w];
     int *qi = sQ[w][0], *qj = sQ[w][1], *qs = sQ[w][2];
-    int qn = 0;    // queue fill (warp-uniform)
+    int qn1 = 0;   // stage-1 queue fill (warp-uniform)
+    int qn = 0;    // stage-2 queue fill (warp-uniform)
     int nHits = 0; // hits so far in this cell (warp-uniform)
     unsigned long long nCand = 0;
-    const double slack = 1.0 + 1e-10;
-    const float slackF = 1.0f + 1e-5f;
+    const float slackF = 1.0f + 2e-5f;
+    const double kEps = 2.384185791015625e-07; // 2^-22
 
     for (int i0 = ib; i0 < ie; i0 += kITile) {
         const int nI = min(kITile, ie - i0);
@@ -379,17 +410,14 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                 if (g.axis == 0) x += sh; else if (g.axis == 1) y += sh; else z += sh;
             }
             const float h = in.bH[s], rho = in.bRho[s];
-            // absolute slack: rounding of coordinate differences in the narrow phase
-            const double sl = 256.0 * DBL_EPSILON * (fabs(x) + fabs(y) + fabs(z) + box.len[0] + box.len[1] + box.len[2]);
-            sP[w][0][m] = x;
-            sP[w][1][m] = y;
-            sP[w][2][m] = z;
-            sP[w][3][m] = (double)h + (double)rho + colBuf + sl;
-            sF[w][0][m] = in.bUx[s];
-            sF[w][1][m] = in.bUy[s];
-            sF[w][2][m] = in.bUz[s];
-            sF[w][3][m] = h;
-            sF[w][4][m] = __double2float_ru((double)rho + colBuf + sl);
+            // absolute slack: rounding of coordinate differences in the narrow phase + the fp32 conversion here
+            const double rx = x - Ox, ry = y - Oy, rz = z - Oz;
+            const double sl = 256.0 * DBL_EPSILON * (fabs(x) + fabs(y) + fabs(z) + box.len[0] + box.len[1] + box.len[2]) +
+                              kEps * (fabs(rx) + fabs(ry) + fabs(rz));
+            const float B = __double2float_ru((double)rho + colBuf + sl);
+            tA[w][m] = make_float4((float)rx, (float)ry, (float)rz, __double2float_ru((double)h + (double)rho + colBuf + sl));
+            tB[w][m] = make_float4(in.bUx[s], in.bUy[s], in.bUz[s], h);
+            tC[w][m] = make_float2(B, __fadd_ru(B, h));
         }
         __syncwarp();
         for (int row = 0; row < 5; row++) {
@@ -412,81 +440,131 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                 if (jb == je) continue;
                 const int code = (kx + 1) + 3 * (ky + 1) + 9 * (kz + 1);
                 const bool own = (code == 13) && row == 0; // contains the target cell itself: each pair once
-                const double shx = kx * box.len[0], shy = ky * box.len[1], shz = kz * box.len[2];
-                for (int j0 = jb; j0 < je; j0 += 32) {
-                    const int sj = j0 + lane;
-                    const bool jv = sj < je;
-                    double xj = 0, yj = 0, zj = 0, Sj = 0;
-                    float ujx = 0, ujy = 0, ujz = 1, hj = 0, rj = 0, SjF = 0;
-                    int gj = 0; // image along the slab axis, +64 if ghost
-                    if (jv) {
-                        xj = in.sX[sj] + shx;
-                        yj = in.sY[sj] + shy;
-                        zj = in.sZ[sj] + shz;
-                        const int im = in.sImg[sj];
-                        gj = im + (in.sGhost[sj] ? 64 : 0);
-                        if (im) {
-                            const double sh = im * g.axisLen;
-                            if (g.axis == 0) xj += sh; else if (g.axis == 1) yj += sh; else zj += sh;
-                        }
-                        hj = in.bH[sj];
-                        rj = in.bRho[sj];
-                        ujx = in.bUx[sj]; ujy = in.bUy[sj]; ujz = in.bUz[sj];
-                        Sj = (double)hj + (double)rj;
-                        SjF = __double2float_ru(Sj);
-                    }
-                    for (int m = 0; m < nI; m++) {
-                        const int si = i0 + m;
-                        bool pass = jv && (own ? (sj > si) : (sj != si)); // a rod never pairs with its own image
-                        const int gi = sG[w][m];
-                        pass = pass && !(gi >= 32 && gj >= 32); // two ghosts: not this rank's constraint
-                        const double ddx = xj - sP[w][0][m], ddy = yj - sP[w][1][m], ddz = zj - sP[w][2][m];
-                        const double cut = sP[w][3][m] + Sj;
-                        pass = pass && ((ddx * ddx + ddy * ddy + ddz * ddz) <= cut * cut * slack);
-                        if (__any_sync(0xffffffffu, pass)) {
-                            // capsule tests (fp32): dist(c_j, axis_i) <= h_j + rho_i + rho_j + buf and
-                            //                        dist(c_i, axis_j) <= h_i + rho_i + rho_j + buf
-                            const float fx = (float)ddx, fy = (float)ddy, fz = (float)ddz;
-                            const float cutF = (float)cut * 1e-5f; // absolute slack of the fp32 evaluation
-                            const float uix = sF[w][0][m], uiy = sF[w][1][m], uiz = sF[w][2][m], hi = sF[w][3][m];
-                            const float Bi = sF[w][4][m];
-                            float t = __fmaf_rn(fx, uix, __fmaf_rn(fy, uiy, fz * uiz));
-                            t = fminf(fmaxf(t, -hi), hi);
-                            float ex = __fmaf_rn(-t, uix, fx), ey = __fmaf_rn(-t, uiy, fy), ez = __fmaf_rn(-t, uiz, fz);
-                            float c2 = (Bi + SjF) * slackF + cutF;
-                            pass = pass && (__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez)) <= c2 * c2);
-                            t = -__fmaf_rn(fx, ujx, __fmaf_rn(fy, ujy, fz * ujz));
-                            t = fminf(fmaxf(t, -hj), hj);
-                            ex = __fmaf_rn(t, ujx, fx); ey = __fmaf_rn(t, ujy, fy); ez = __fmaf_rn(t, ujz, fz);
-                            c2 = (Bi + hi + rj) * slackF + cutF;
-                            pass = pass && (__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez)) <= c2 * c2);
-                        }
-                        const unsigned msk = __ballot_sync(0xffffffffu, pass);
-                        if (msk == 0) continue;
-                        if (pass) {
-                            const int p = qn + __popc(msk & ((1u << lane) - 1));
-                            qi[p] = si;
-                            qj[p] = sj;
-                            // image of j relative to i: cell wrap + difference of the ghost images
-                            qs[p] = code + (((gj + 32) & 63) - ((gi + 32) & 63)) * axMul;
-                        }
-                        qn += __popc(msk);
-                        nCand += __popc(msk);
-                        __syncwarp();
-                        if (qn >= 32) {
-                            nHits += narrowBatch(in, box, colBuf, 32, qi, qj, qs, lane, cell, nHits, hitList, hitCap,
-                                                 counters);
-                            __syncwarp();
-                            // move the tail to the front
-                            const int rem = qn - 32;
-                            int ti = 0, tj = 0, ts = 0;
-                            if (lane < rem) { ti = qi[32 + lane]; tj = qj[32 + lane]; ts = qs[32 + lane]; }
-                            __syncwarp();
-                            if (lane < rem) { qi[lane] = ti; qj[lane] = tj; qs[lane] = ts; }
-                            qn = rem;
-                            __syncwarp();
+                const double shx = kx * box.len[0] - Ox, shy = ky * box.len[1] - Oy, shz = kz * box.len[2] - Oz;
+                for (int j0 = jb; j0 < je; j0 += kJTile) {
+                    // ---- stage the source tile: lane owns slots lane and lane + 32.  A slot without a rod sits
+                    // far away (the sphere test fails) and has index -1.
+                    float xj[2], yj[2], zj[2], Sj[2];
+                    int sjv[2];
+                    bool gh[2];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int js = 32 * q + lane, sj = j0 + js;
+                        const bool jv = sj < je;
+                        sjv[q] = jv ? sj : -1;
+                        xj[q] = 1e18f; yj[q] = zj[q] = 0.f; Sj[q] = 0.f;
+                        gh[q] = false;
+                        if (jv) {
+                            double x = in.sX[sj] + shx, y = in.sY[sj] + shy, z = in.sZ[sj] + shz;
+                            const int im = in.sImg[sj];
+                            gh[q] = in.sGhost[sj] != 0;
+                            if (im) {
+                                const double sh = im * g.axisLen;
+                                if (g.axis == 0) x += sh; else if (g.axis == 1) y += sh; else z += sh;
+                            }
+                            const float e = __double2float_ru(kEps * (fabs(x) + fabs(y) + fabs(z)));
+                            const float h = in.bH[sj], r = in.bRho[sj];
+                            const float rE = __fadd_ru(r, e);
+                            xj[q] = (float)x; yj[q] = (float)y; zj[q] = (float)z;
+                            Sj[q] = __fadd_ru(h, rE);
+                            jA[w][js] = make_float4(xj[q], yj[q], zj[q], Sj[q]);
+                            jB[w][js] = make_float4(in.bUx[sj], in.bUy[sj], in.bUz[sj], h);
+                            jC[w][js] = rE;
+                            sGj[w][js] = (signed char)(im + (gh[q] ? 64 : 0));
                         }
                     }
+                    __syncwarp();
+                    // m == nI is the flush pass: the staged source tile is about to be replaced
+                    for (int m = 0; m <= nI; m++) {
+                        const bool flush = m == nI;
+                        if (!flush) {
+                            // ---- stage 1: target m against the 64 staged sources (branch-free)
+                            const int si = i0 + m;
+                            const float4 a = tA[w][m];
+                            const bool gi = multi && sG[w][m] >= 32;
+                            unsigned pass[2];
+#pragma unroll
+                            for (int q = 0; q < 2; q++) {
+                                const float fx = xj[q] - a.x, fy = yj[q] - a.y, fz = zj[q] - a.z;
+                                const float cutS = (a.w + Sj[q]) * slackF;
+                                const unsigned near = __fmaf_rn(fx, fx, __fmaf_rn(fy, fy, fz * fz)) <= cutS * cutS;
+                                // each pair once inside the target cell; a rod never pairs with its own image
+                                const unsigned keep = own ? (sjv[q] > si) : (sjv[q] != si);
+                                const unsigned gg = gi & gh[q]; // two ghosts: not this rank's constraint
+                                pass[q] = near & keep & (gg ^ 1u);
+                            }
+                            const unsigned m0 = __ballot_sync(0xffffffffu, pass[0]), m1 = __ballot_sync(0xffffffffu, pass[1]);
+                            if ((m0 | m1) == 0) continue;
+                            const int n0 = __popc(m0);
+                            if (pass[0]) q1[qn1 + __popc(m0 & lt)] = (unsigned short)(m | (lane << 6));
+                            if (pass[1]) q1[qn1 + n0 + __popc(m1 & lt)] = (unsigned short)(m | ((32 + lane) << 6));
+                            qn1 += n0 + __popc(m1);
+                            __syncwarp();
+                        }
+                        while (qn1 >= 32 || (flush && qn1 > 0)) {
+                            // ---- stage 2 on the first min(32, qn1) queued pairs: the two capsule tests
+                            const int cnt = min(32, qn1);
+                            bool pass = false;
+                            int tm = 0, js = 0;
+                            if (lane < cnt) {
+                                const unsigned e = q1[lane];
+                                tm = e & 63; js = e >> 6;
+                                const float4 a = tA[w][tm], b = tB[w][tm], ja = jA[w][js], jb4 = jB[w][js];
+                                const float2 c = tC[w][tm];
+                                const float rE = jC[w][js];
+                                const float fx = ja.x - a.x, fy = ja.y - a.y, fz = ja.z - a.z;
+                                const float cutF = (a.w + ja.w) * 1e-5f; // absolute slack of the fp32 evaluation (|dd| <= cut)
+                                // dist(c_j, axis_i) <= h_j + rho_i + rho_j + buf, dist(c_i, axis_j) <= h_i + rho_i + rho_j + buf
+                                float t = __fmaf_rn(fx, b.x, __fmaf_rn(fy, b.y, fz * b.z));
+                                t = fminf(fmaxf(t, -b.w), b.w);
+                                float ex = __fmaf_rn(-t, b.x, fx), ey = __fmaf_rn(-t, b.y, fy), ez = __fmaf_rn(-t, b.z, fz);
+                                float c2 = __fmaf_rn(c.x + ja.w, slackF, cutF);
+                                const bool p1 = __fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez)) <= c2 * c2;
+                                t = -__fmaf_rn(fx, jb4.x, __fmaf_rn(fy, jb4.y, fz * jb4.z));
+                                t = fminf(fmaxf(t, -jb4.w), jb4.w);
+                                ex = __fmaf_rn(t, jb4.x, fx); ey = __fmaf_rn(t, jb4.y, fy); ez = __fmaf_rn(t, jb4.z, fz);
+                                c2 = __fmaf_rn(c.y + rE, slackF, cutF);
+                                pass = p1 & (__fmaf_rn(ex, ex, __fmaf_rn(ey, ey, ez * ez)) <= c2 * c2);
+                            }
+                            { // move the tail of the stage-1 queue (< 64 entries) to the front
+                                const int rem = qn1 - cnt;
+                                unsigned short t0 = 0, t1 = 0;
+                                if (lane < rem) t0 = q1[32 + lane];
+                                if (32 + lane < rem) t1 = q1[64 + lane];
+                                __syncwarp();
+                                if (lane < rem) q1[lane] = t0;
+                                if (32 + lane < rem) q1[32 + lane] = t1;
+                                qn1 = rem;
+                            }
+                            const unsigned msk = __ballot_sync(0xffffffffu, pass);
+                            if (msk) {
+                                if (pass) {
+                                    const int p = qn + __popc(msk & lt);
+                                    const int gi = sG[w][tm], gj = sGj[w][js];
+                                    qi[p] = i0 + tm;
+                                    qj[p] = j0 + js;
+                                    // image of j relative to i: cell wrap + difference of the ghost images
+                                    qs[p] = code + (((gj + 32) & 63) - ((gi + 32) & 63)) * axMul;
+                                }
+                                qn += __popc(msk);
+                                nCand += __popc(msk);
+                                __syncwarp();
+                                if (qn >= 32) { // ---- stage 3: exact closest-point query on 32 candidates
+                                    nHits += narrowBatch(in, box, colBuf, 32, qi, qj, qs, lane, cell, nHits, hitList, hitCap,
+                                                         counters);
+                                    __syncwarp();
+                                    const int rem = qn - 32; // move the tail to the front
+                                    int ti = 0, tj = 0, ts = 0;
+                                    if (lane < rem) { ti = qi[32 + lane]; tj = qj[32 + lane]; ts = qs[32 + lane]; }
+                                    __syncwarp();
+                                    if (lane < rem) { qi[lane] = ti; qj[lane] = tj; qs[lane] = ts; }
+                                    qn = rem;
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }

@@ -256,6 +256,7 @@ struct Context {
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceChunk = 2;                  // k_force_vel_lm: incidence levels per software-pipeline stage (2 or 4)
+    int optForceBlock = 64;                 // k_force_vel_lm: threads per CTA (small CTAs: groups differ in depth, a CTA lives as long as its deepest group)
     int optTailCtasPerSM = 2;               // persistent grid of k_bb_tail
     int optBatch = 0;                       // BBPGD iterations enqueued per host check (0 = automatic)
     bool haveSetup = false;

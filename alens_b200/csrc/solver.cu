@@ -835,7 +835,9 @@ static MobIn mobIn(Context &c) {
     return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.nRods, mobStride(c.nRods), c.sGhost.p};
 }
 static ConGeom conGeom(Context &c) { return ConGeom{c.cIdxI.p, c.cIdxJ.p, c.cN.p, c.cPI.p, c.cPJ.p, c.conCap}; }
-static FvIn fvIn(Context &c) { return FvIn{c.incStart.p, c.incCon.p, c.incCol.p, (size_t)c.incStride, c.nRods}; }
+static FvIn fvIn(Context &c) {
+    return FvIn{c.incStart.p, c.incCon.p, c.incCol.p, (size_t)c.incStride, c.nRods};
+}
 
 void calcMobility(Context &c, double mu) {
     if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_calc_mobility: call alens_set_rods first"};
@@ -975,11 +977,12 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
     const HaloPush hp = push ? *push : HaloPush{};
     if (n == 0 && !push) return;
     profBegin(c, 0);
-    const int grid = std::max(1, gridFor((long long)gridFor(n, 32) * 32, 256));
+    const int block = c.optForceBlock;
+    const int grid = std::max(1, gridFor((long long)gridFor(n, 32) * 32, block));
     if (c.optForceChunk == 4)
-        k_force_vel_lm<4, XMODE, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), xin, U, F, scal, hp);
+        k_force_vel_lm<4, XMODE, WF><<<grid, block, 0, c.stream>>>(fvIn(c), mobIn(c), xin, U, F, scal, hp);
     else
-        k_force_vel_lm<2, XMODE, WF><<<grid, 256, 0, c.stream>>>(fvIn(c), mobIn(c), xin, U, F, scal, hp);
+        k_force_vel_lm<2, XMODE, WF><<<grid, block, 0, c.stream>>>(fvIn(c), mobIn(c), xin, U, F, scal, hp);
     profEnd(c);
     c.launches++;
     c.timers.op_launches++;

@@ -24,8 +24,7 @@ def step():
 out = []
 ref_gamma = None
 SWEEP = json.loads(os.environ.get("ALENS_SWEEP", "null")) or [
-    {"force_chunk": 2, "tail_ctas_per_sm": 2}, {"force_chunk": 4, "tail_ctas_per_sm": 2},
-    {"force_chunk": 2, "tail_ctas_per_sm": 3}, {"force_chunk": 2, "tail_ctas_per_sm": 4}]
+    {"force_block": 64, "force_chunk": 2, "tail_ctas_per_sm": 2}, {"force_block": 256}, {"force_block": 64, "force_chunk": 4}]
 for opts in SWEEP:
     for k, v in opts.items():
         ctx.set_option(k, v)
@@ -46,7 +45,7 @@ for opts in SWEEP:
     row = dict(opts=opts, nc=nc, iters=rep.iterations, phases=acc,
                force_vel_us=1e3 * tm["op_force_vel_ms"] / max(tm["op_force_vel_n"], 1),
                tail_us=1e3 * tm["op_dtrans_ms"] / max(tm["op_dtrans_n"], 1),
-               gamma_identical=bool((g == ref_gamma).all()), cand=ctx.get_collect_stats())
+               gamma_identical=bool(g.shape == ref_gamma.shape and (g == ref_gamma).all()), cand=ctx.get_collect_stats())
     print(json.dumps(row), flush=True)
     out.append(row)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
