@@ -384,7 +384,13 @@ int alens_reset_timers(alens_ctx *ctx) {
 int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
     return guarded(ctx, [&](Context &c) {
         const std::string k = name ? name : "";
-        if (k == "force_chunk") c.optForceChunk = value == 4 ? 4 : 2;
+        if (k == "force_kernel") c.optForceKernel = value == 0 ? 0 : 1;
+        else if (k == "force_minb") c.optForceMinB = (value == 6 || value == 8 || value == 10) ? (int)value : 5;
+        else if (k == "keep_xg") c.optKeepXG = value != 0;
+        else if (k == "force_dbg") c.optForceDbg = (int)value;
+        else if (k == "force_mask") c.optForceMask = value != 0;
+        else if (k == "force_waves") c.optForceWaves = (int)std::max(1LL, std::min(64LL, value));
+        else if (k == "force_chunk") c.optForceChunk = value == 4 ? 4 : 2;
         else if (k == "force_block") c.optForceBlock = value == 32 ? 32 : (value == 64 ? 64 : (value == 128 ? 128 : 256));
         else if (k == "tail_ctas_per_sm") c.optTailCtasPerSM = (int)std::max(1LL, std::min(8LL, value));
         else if (k == "comm_fused") c.comm.fused = value != 0;
@@ -396,7 +402,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
 int alens_time_kernel(alens_ctx *ctx, const char *which, int reps, double *avgMicroseconds) {
     return guarded(ctx, [&](Context &c) {
         const std::string k = which ? which : "";
-        const int w = k == "force_vel" ? 0 : (k == "tail" ? 1 : (k == "force_vel_plain" ? 2 : -1));
+        const int w = k == "force_vel" ? 0 : (k == "tail" ? 1 : (k == "force_vel_plain" ? 2 : (k == "force_vel_last" ? 3 : -1)));
         if (w < 0 || reps < 1) throw ArgError{ALENS_ERR_ARG, "alens_time_kernel: which = force_vel | tail | force_vel_plain"};
         const double us = timeKernel(c, w, reps);
         if (avgMicroseconds) *avgMicroseconds = us;

@@ -255,6 +255,13 @@ struct Context {
     DevBuf<double> incCol;                 // 6 per slot: D column block for that (rod, constraint)
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
+    int optForceKernel = 1;                 // 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
+    int optForceMinB = 5;                   // k_force_vel_act: resident CTAs per SM asked of the compiler (5: 96 regs, 6: 80 regs + small spill)
+    int optKeepXG = 1;                      // {x, g} pairs stored / gathered with the L2 evict_last policy
+    int optForceDbg = 0;                    // k_force_vel_act experiment switches (timing only)
+    int optForceMask = 1;                   // k_force_vel_act consults the tail kernel's "may be non-zero" bit mask before gathering {x, g}
+    int optForceWaves = 1;                  // k_force_vel_act: grid = resident CTAs x this (1 = persistent)
+    int incLayout = 1;                      // layout built by the last setup (= optForceKernel at that time)
     int optForceChunk = 2;                  // k_force_vel_lm: incidence levels per software-pipeline stage (2 or 4)
     int optForceBlock = 64;                 // k_force_vel_lm: threads per CTA (small CTAs: groups differ in depth, a CTA lives as long as its deepest group)
     int optTailCtasPerSM = 2;               // persistent grid of k_bb_tail
@@ -264,6 +271,7 @@ struct Context {
 
     // ---- solver vectors ----
     DevBuf<double> vX0, vX1, vG0, vG1, vB, vLbFlag; // x0 / unpacked iterates, APGD work, q, bilateral flag as double
+    DevBuf<unsigned> vMask;                         // 1 bit per constraint: 0 = the next BBPGD iterate is certainly 0 there
     DevBuf<double2> vXG0, vXG1;                     // BBPGD iterates as interleaved {x, g} pairs (ping-pong)
     DevBuf<double> vTmp0, vTmp1, vTmp2, vTmp3, vTmp4, vTmp5; // APGD work vectors
     DevBuf<double> rU, rF;                         // 6 per rod: vel, force of the last apply
@@ -275,6 +283,7 @@ struct Context {
     int histCap = 0;
     SolverScalars *hScal = nullptr;                // pinned mirror
     std::vector<double> hist;                      // host copy of the last history
+    const double2 *lastXG = nullptr;               // {x, g} pairs the last BBPGD force kernel read
     double *xLastApplied = nullptr;                // device ptr of the vector the operator last saw
     double *xSolution = nullptr;                   // device ptr of the returned iterate
     bool haveSolution = false;

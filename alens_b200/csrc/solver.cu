@@ -169,6 +169,41 @@ __global__ void k_inc_emit(int nRods, const int *__restrict__ start, int *__rest
     }
 }
 
+// Rod-major variant for k_force_vel_act: each lane sorts its rod's slot list in place (incCon IS the sorted raw
+// list), then the warp walks the group's contiguous slot range slot-parallel and writes each slot's column block as
+// one 48-byte record (array of structures): a reader that needs only SOME slots touches 2 sectors per slot.
+__global__ void k_inc_emit_rm(int nRods, const int *__restrict__ start, int *__restrict__ incCon, ConGeom g,
+                              double *__restrict__ incCol6) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp * 32 >= nRods) return;
+    const int r = warp * 32 + lane;
+    const int b = start[min(r, nRods)], e = start[min(r + 1, nRods)];
+    for (int a = b + 1; a < e; a++) { // insertion sort, lists are short
+        const int v = incCon[a];
+        int p = a - 1;
+        while (p >= b && incCon[p] > v) {
+            incCon[p + 1] = incCon[p];
+            p--;
+        }
+        incCon[p + 1] = v;
+    }
+    __syncwarp();
+    const int gb = __shfl_sync(0xffffffffu, b, 0), ge = __shfl_sync(0xffffffffu, e, 31);
+    for (int p = gb + lane; p < ge; p += 32) {
+        const int k2 = incCon[p];
+        const size_t kk = (size_t)(k2 >> 2);
+        const bool sideJ = k2 & 1;
+        double gx = g.n[kk], gy = g.n[kk + g.stride], gz = g.n[kk + 2 * g.stride];
+        const double *P = sideJ ? g.pJ : g.pI;
+        const double px = P[kk], py = P[kk + g.stride], pz = P[kk + 2 * g.stride];
+        if (sideJ) { gx = -gx; gy = -gy; gz = -gz; }
+        double2 *o = reinterpret_cast<double2 *>(incCol6 + 6 * (size_t)p);
+        o[0] = make_double2(gx, gy);
+        o[1] = make_double2(gz, (gz * py - gy * pz));
+        o[2] = make_double2((gx * pz - gz * px), (gy * px - gx * py));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // setup: q = delta0/dt + D^T v_nc (ConstraintSolver.cpp:18-27), K^-1/dt, bilateral flag, x0 = gamma guess
 __global__ void k_setup(long long nc, ConGeom g, const int *__restrict__ sUser, const double *__restrict__ velNC,
@@ -225,6 +260,28 @@ __device__ __forceinline__ int ldStream(const int *p) {
     asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ double2 ldStream2(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+// L2 residency control for the one array both BBPGD kernels share through L2: the tail kernel stores {x, g}
+// (16 B/row, 55 MB at 3.4M rows) and the force kernel gathers the rows that can be non-zero right afterwards.
+// Stored and gathered with an evict_last policy the pairs survive the 400 MB the tail streams past them; the tail's
+// own read of the PREVIOUS pairs is a streaming load (evict-first), which demotes the old buffer again.
+__device__ __forceinline__ unsigned long long policyEvictLast() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ldGather2Keep(const double2 *p, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stKeep2(double2 *p, double2 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ double2 ldGather2(const double2 *p) {
     double2 v;
     asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
@@ -264,6 +321,7 @@ struct XIn {
     const double *x;     // XMODE 0 / 1
     const double2 *xg;   // XMODE 2: {x_prev, g_prev}
     int update;          // XMODE 2: 0 = iteration 0 (x = x_prev as given), 1 = projected gradient step
+    const unsigned *mask; // XMODE 2, k_force_vel_act: bit k = 0 -> x_k is certainly 0 (nullptr: unknown)
 };
 
 // x = P(xp - alpha*gp); lb = -0.1*DBL_MAX*biFlag (-0.0 for unilateral rows, ConstraintSolver.cpp:69), ub = DBL_MAX/10
@@ -384,6 +442,225 @@ k_force_vel_lm(FvIn in, MobIn mob, XIn xin, double *__restrict__ U, double *__re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// f = D x, u = M f, touching only the incidence slots whose multiplier can be non-zero.
+// In a BCQP iterate most unilateral rows sit on their bound (x = 0: the rods are within colBuf of each other but not
+// pushing); measured on the bench workload 84 % of the rows, every iteration.  A slot with x = 0 adds +-0 to f, which
+// leaves every bit of f unchanged (f starts at +0 and a round-to-nearest sum never produces -0 from a non-zero
+// cancellation), so skipping it is exact -- and neither its {x, g} pair nor its 48-byte column block is fetched.
+// Which rows can be non-zero is known one kernel earlier: k_bb_tail publishes one bit per row (XIn::mask).
+// One warp per 32-rod group, slots rod-major (k_inc_emit_rm), per batch of 256 slots:
+//   1  slot-parallel: lane l takes slots base + l + 32 k: ids (coalesced, streaming), mask bits (a 0.4 MB array,
+//      L1/L2 hits); the surviving slots are compacted, in slot order, into a warp-private queue (ballot / popc)
+//   2  a lane finds the queue range of ITS rod by binary search for its first slot (the queue is sorted); its end
+//      is the next lane's start
+//   3  64 queued slots at a time, lane l takes entries l and l + 32: multiplier ({x_prev, g_prev} gather + the
+//      projected step, or a plain x), then -- only if it is non-zero -- the column block (three 16-byte streaming
+//      loads), and leaves the 6 products in shared memory; then lane = rod adds the products of its slots in
+//      ascending slot order: the summation order of the level-major kernel and of the CPU restatement.
+// The kernel is issue-latency bound, not bandwidth bound (ncu: ~800 warp instructions per group on 5 warps per
+// scheduler in its first version), hence: few instructions per slot, no per-slot arithmetic before the mask test,
+// small register footprint for many resident warps.
+static constexpr int kActWarps = 4;   // warps per CTA
+static constexpr int kActBatch = 256; // slots per warp and batch (8 per lane)
+struct FvAct {
+    const int *incStart, *incCon; // rod-major
+    const double *incCol6;        // 6 doubles per slot, contiguous
+    int nRods;
+    int dbg; // experiment switches (alens_set_option "force_dbg"): timing only, results are garbage when non-zero
+};
+
+template <int XMODE>
+__device__ __forceinline__ double actMultiplier(const XIn &xin, int code, double alpha, unsigned long long keep) {
+    const bool bi = (code & 2) != 0;
+    if (XMODE == 2) {
+        const double2 xg = keep ? ldGather2Keep(xin.xg + (code >> 2), keep) : ldGather2(xin.xg + (code >> 2));
+        return xin.update ? bbStep(xg.x, xg.y, alpha, bi) : xg.x;
+    }
+    const double xv = __ldg(xin.x + (code >> 2));
+    return XMODE == 1 ? 1.0 * xv * (bi ? 1.0 : 0.0) : xv;
+}
+
+template <int XMODE, bool WRITE_F, int MINB>
+__global__ void __launch_bounds__(kActWarps * 32, MINB)
+k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__restrict__ F,
+                const SolverScalars *__restrict__ scal, HaloPush hp) {
+    __shared__ int sCode[kActWarps][kActBatch];            // queued slot codes
+    __shared__ unsigned short sSlot[kActWarps][kActBatch]; // queued slots, relative to the batch base
+    __shared__ double sProd[kActWarps][2][6][32];
+    if (scal && scal->done) return;
+    double alpha = 0.0;
+    if (XMODE == 2) alpha = scal->alpha; // plain load, L1 broadcast
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1;
+    constexpr int PER = kActBatch / 32;
+    const int nGroups = (in.nRods + 31) >> 5;
+    const int gStride = gridDim.x * kActWarps;
+    int grp = blockIdx.x * kActWarps + w;
+    if (grp >= nGroups) return;
+    const bool useMask = XMODE == 2 && xin.mask != nullptr;
+    const unsigned long long keep = (XMODE == 2 && !(in.dbg & 64)) ? policyEvictLast() : 0ull;
+    // Persistent warps, software-pipelined over their groups: while group g is being worked on, the slot range of
+    // g + stride and the ids of its first batch are already in flight.
+    int b, e;      // slot range of my rod in the current group
+    int code[PER]; // ids of the first batch of the current group
+    {
+        const int r = grp * 32 + lane;
+        b = __ldg(in.incStart + min(r, in.nRods));
+        e = __ldg(in.incStart + min(r + 1, in.nRods));
+        const int gb = __shfl_sync(0xffffffffu, b, 0), ge = __shfl_sync(0xffffffffu, e, 31);
+        const int lim = min(ge, gb + kActBatch);
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int p = gb + 32 * k + lane;
+            code[k] = (p < lim && !(in.dbg & 32)) ? ldStream(in.incCon + p) : -1;
+        }
+    }
+    while (true) {
+        const int r = grp * 32 + lane;
+        const bool act = r < in.nRods;
+        const int grpN = grp + gStride;
+        const bool more = grpN < nGroups; // warp-uniform
+        int bN = 0, eN = 0;               // next group's slot range: in flight during everything below
+        if (more) {
+            const int rN = grpN * 32 + lane;
+            bN = __ldg(in.incStart + min(rN, in.nRods));
+            eN = __ldg(in.incStart + min(rN + 1, in.nRods));
+        }
+        double qx = 0, qy = 0, qz = 0, iPara = 0, iPerp = 0, iRot = 0;
+        unsigned ghost = 1;
+        const int gb = __shfl_sync(0xffffffffu, b, 0), ge = __shfl_sync(0xffffffffu, e, 31);
+        double f[6] = {0, 0, 0, 0, 0, 0};
+        for (int base = gb; base == gb || base < ge; base += kActBatch) {
+            const bool lastBatch = base + kActBatch >= ge;
+            if (base != gb) { // further batches of a crowded group: not prefetched
+                const int lim = min(ge, base + kActBatch);
+#pragma unroll
+                for (int k = 0; k < PER; k++) {
+                    const int p = base + 32 * k + lane;
+                    code[k] = p < lim ? ldStream(in.incCon + p) : -1;
+                }
+            }
+            // ---- 1: mask test + compaction
+            unsigned mw[PER];
+            if (useMask) {
+#pragma unroll
+                for (int k = 0; k < PER; k++) mw[k] = code[k] >= 0 ? __ldg(xin.mask + (code[k] >> 7)) : 0u;
+            }
+            int qn = 0;
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                bool on = code[k] >= 0;
+                if (useMask) on = on && ((mw[k] >> ((code[k] >> 2) & 31)) & 1u);
+                if (in.dbg & 16) on = false;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                    const int pos = qn + __popc(m & lt);
+                    sSlot[w][pos] = (unsigned short)(32 * k + lane);
+                    sCode[w][pos] = code[k];
+                }
+                qn += __popc(m);
+            }
+            __syncwarp();
+            if (lastBatch) { // the id registers are free: request the next group's first ids and this group's rod data
+                if (more) {
+                    const int gbN = __shfl_sync(0xffffffffu, bN, 0), geN = __shfl_sync(0xffffffffu, eN, 31);
+                    const int limN = min(geN, gbN + kActBatch);
+#pragma unroll
+                    for (int k = 0; k < PER; k++) {
+                        const int p = gbN + 32 * k + lane;
+                        code[k] = (p < limN && !(in.dbg & 32)) ? ldStream(in.incCon + p) : -1;
+                    }
+                }
+                if (act && !(in.dbg & 8)) { // read once per launch: streaming loads
+                    qx = ldStream(mob.dx + r); qy = ldStream(mob.dy + r); qz = ldStream(mob.dz + r);
+                    iPara = ldStream(mob.invDrag + r); iPerp = ldStream(mob.invDrag + mob.stride + r);
+                    iRot = ldStream(mob.invDrag + 2 * mob.stride + r);
+                    ghost = mob.ghost[r];
+                }
+                if (in.dbg & 8) ghost = 0;
+            }
+            if (qn == 0) continue;
+            // ---- 2: entries [lo, hi) of the queue belong to my rod
+            const int bo = b - base;
+            int lo = 0;
+            for (int step = 1 << (31 - __clz(qn)); step >= 1; step >>= 1) {
+                const int t = lo + step;
+                if (t <= qn && (int)sSlot[w][t - 1] < bo) lo = t;
+            }
+            int hi = __shfl_down_sync(0xffffffffu, lo, 1);
+            if (lane == 31) hi = qn;
+            // ---- 3: multipliers, column blocks, products; two queue chunks in flight
+            for (int c0 = 0; c0 < qn; c0 += 64) {
+                const int i0 = c0 + lane, i1 = c0 + 32 + lane;
+                double x0 = 0.0, x1 = 0.0;
+                if (in.dbg & 2) {
+                    x0 = i0 < qn ? ((i0 & 7) == 0 ? 1.0 : 0.0) : 0.0; // no gather; 1 in 8 survivors "active"
+                    x1 = i1 < qn ? ((i1 & 7) == 0 ? 1.0 : 0.0) : 0.0;
+                } else {
+                    if (i0 < qn) x0 = actMultiplier<XMODE>(xin, sCode[w][i0], alpha, keep);
+                    if (i1 < qn) x1 = actMultiplier<XMODE>(xin, sCode[w][i1], alpha, keep);
+                }
+                double2 a01 = make_double2(0.0, 0.0), a23 = a01, a45 = a01, b01 = a01, b23 = a01, b45 = a01;
+                if (in.dbg & 1) { a01 = a23 = a45 = b01 = b23 = b45 = make_double2(1.0, 2.0); x0 = x1 = 0.0; }
+                if (x0 != 0.0) {
+                    const double2 *cp = reinterpret_cast<const double2 *>(in.incCol6 + 6 * ((size_t)base + sSlot[w][i0]));
+                    a01 = ldStream2(cp); a23 = ldStream2(cp + 1); a45 = ldStream2(cp + 2);
+                }
+                if (x1 != 0.0) {
+                    const double2 *cp = reinterpret_cast<const double2 *>(in.incCol6 + 6 * ((size_t)base + sSlot[w][i1]));
+                    b01 = ldStream2(cp); b23 = ldStream2(cp + 1); b45 = ldStream2(cp + 2);
+                }
+                sProd[w][0][0][lane] = a01.x * x0; sProd[w][0][1][lane] = a01.y * x0;
+                sProd[w][0][2][lane] = a23.x * x0; sProd[w][0][3][lane] = a23.y * x0;
+                sProd[w][0][4][lane] = a45.x * x0; sProd[w][0][5][lane] = a45.y * x0;
+                if (c0 + 32 < qn) {
+                    sProd[w][1][0][lane] = b01.x * x1; sProd[w][1][1][lane] = b01.y * x1;
+                    sProd[w][1][2][lane] = b23.x * x1; sProd[w][1][3][lane] = b23.y * x1;
+                    sProd[w][1][4][lane] = b45.x * x1; sProd[w][1][5][lane] = b45.y * x1;
+                }
+                __syncwarp();
+                const int s = max(lo, c0) - c0, t = min(hi, c0 + 64) - c0;
+                for (int j = s; j < t; j++) {
+#pragma unroll
+                    for (int c = 0; c < 6; c++) f[c] += sProd[w][j >> 5][c][j & 31];
+                }
+                __syncwarp();
+            }
+        }
+        if (act && !ghost) {
+            const double qf = qx * f[0] + qy * f[1] + qz * f[2];
+            const double px = qf * qx, py = qf * qy, pz = qf * qz;
+            const double2 u0 = make_double2(iPara * px + iPerp * (f[0] - px), iPara * py + iPerp * (f[1] - py));
+            const double2 u1 = make_double2(iPara * pz + iPerp * (f[2] - pz), iRot * f[3]);
+            const double2 u2 = make_double2(iRot * f[4], iRot * f[5]);
+            double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
+            if (!(in.dbg & 4) || u0.x == 12345.678) { Up[0] = u0; Up[1] = u1; Up[2] = u2; }
+            if (WRITE_F) {
+                double2 *Fp = reinterpret_cast<double2 *>(F + 6 * (size_t)r);
+                Fp[0] = make_double2(f[0], f[1]);
+                Fp[1] = make_double2(f[2], f[3]);
+                Fp[2] = make_double2(f[4], f[5]);
+            }
+            if (hp.on) {
+#pragma unroll
+                for (int dd = 0; dd < 2; dd++) {
+                    if (!hp.mir[dd]) continue;
+                    const int rr = hp.mir[dd][r];
+                    if (rr >= 0) {
+                        double2 *Rp = reinterpret_cast<double2 *>(hp.rem[dd] + 6 * (size_t)rr);
+                        Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+                    }
+                }
+            }
+        }
+        if (!more) break;
+        grp = grpN;
+        b = bN;
+        e = eN;
+    }
+}
+
 // row k of D^T times u
 __device__ __forceinline__ double dtransRow(const ConGeom &g, size_t k, const double *__restrict__ U) {
     const double gx = g.n[k], gy = g.n[k + g.stride], gz = g.n[k + 2 * g.stride];
@@ -484,6 +761,8 @@ struct BbTail {
     int histCap;
     double tol;
     int ite; // iteration number of this launch (0 = initial gradient)
+    int keepXG;               // store {x, g} with the L2 evict_last policy (the force kernel gathers it next)
+    unsigned *maskOut;        // bit k = 1 unless the NEXT iterate's x_k is certainly 0 (see k_bb_tail); nc/32 words
     const unsigned char *own; // multi-rank: 1 = this rank counts the row in the dot products (nullptr = all)
     double *redOut;           // multi-rank: the reduced partials go here, k_bb_reduce finishes the step
     // fused multi-GPU variant (one rank per device): the kernel itself waits for the neighbours' ghost rows of U
@@ -535,11 +814,6 @@ struct TailRow {
     double2 xg;
     unsigned char bi;
 };
-__device__ __forceinline__ double2 ldStream2(const double2 *p) {
-    double2 v;
-    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ unsigned char ldStreamU8(const unsigned char *p) {
     unsigned v;
     asm volatile("ld.global.cs.u8 %0, [%1];" : "=r"(v) : "l"(p));
@@ -582,44 +856,64 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
         }
         __syncthreads();
     }
-    while (k < p.nc) {
+    // The loop condition is warp-uniform (first row of the warp), rows past the end are predicated off: every
+    // trip ends with a ballot that publishes, for the NEXT iteration's force kernel, which rows can be non-zero.
+    // x_next = P(x - alpha_next g) with alpha_next > 0 (the loop stops on alpha < 10 eps): a unilateral row with
+    // x = 0 and g >= 0 stays exactly 0 whatever alpha_next turns out to be -- its bit is 0.
+    const int lane = threadIdx.x & 31;
+    const unsigned long long keepPol = policyEvictLast();
+    while (k - lane < p.nc) {
+        const bool valid = k < p.nc;
         const long long kn = k + stride;
-        if (kn < p.nc) loadTailRow<HASK>(p, (size_t)kn, nxt);
-        const double2 *uI = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)cur.iI);
-        const double2 *uJ = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)(cur.iJ >= 0 ? cur.iJ : cur.iI));
+        // (1) the six 16-byte gathers of this row's two U rows (L2 hits, needed first), unconditional and back to back:
+        // a one-sided row gathers rod I twice, a lane past the end gathers row 0
+        const int iI = valid ? cur.iI : 0;
+        const bool two = valid && cur.iJ >= 0;
+        const int iJ = two ? cur.iJ : iI;
+        const double2 *uI = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)iI);
+        const double2 *uJ = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)iJ);
         const double2 a = ldGather2(uI), b = ldGather2(uI + 1), c = ldGather2(uI + 2);
         const double2 d = ldGather2(uJ), e = ldGather2(uJ + 1), f = ldGather2(uJ + 2);
-        const double xp = cur.xg.x, gp = cur.xg.y;
-        const double x = p.ite > 0 ? bbStep(xp, gp, alpha, cur.bi != 0) : xp;
-        const double gx = cur.gx, gy = cur.gy, gz = cur.gz;
-        double y = gx * a.x;
-        y += gy * a.y;
-        y += gz * b.x;
-        y += (gz * cur.pIy - gy * cur.pIz) * b.y;
-        y += (gx * cur.pIz - gz * cur.pIx) * c.x;
-        y += (gy * cur.pIx - gx * cur.pIy) * c.y;
-        if (cur.iJ >= 0) {
-            const double hx = -gx, hy = -gy, hz = -gz;
-            y += hx * d.x;
-            y += hy * d.y;
-            y += hz * e.x;
-            y += (hz * cur.pJy - hy * cur.pJz) * e.y;
-            y += (hx * cur.pJz - hz * cur.pJx) * f.x;
-            y += (hy * cur.pJx - hx * cur.pJy) * f.y;
+        // (2) the streaming operands of the next row (DRAM, needed one trip later)
+        if (kn < p.nc) loadTailRow<HASK>(p, (size_t)kn, nxt);
+        bool on = false;
+        if (valid) {
+            const double xp = cur.xg.x, gp = cur.xg.y;
+            const double x = p.ite > 0 ? bbStep(xp, gp, alpha, cur.bi != 0) : xp;
+            const double gx = cur.gx, gy = cur.gy, gz = cur.gz;
+            double y = gx * a.x;
+            y += gy * a.y;
+            y += gz * b.x;
+            y += (gz * cur.pIy - gy * cur.pIz) * b.y;
+            y += (gx * cur.pIz - gz * cur.pIx) * c.x;
+            y += (gy * cur.pIx - gx * cur.pIy) * c.y;
+            if (two) { // (the gathers above do not wait for this test)
+                const double hx = -gx, hy = -gy, hz = -gz;
+                y += hx * d.x;
+                y += hy * d.y;
+                y += hz * e.x;
+                y += (hz * cur.pJy - hy * cur.pJz) * e.y;
+                y += (hx * cur.pJz - hz * cur.pJx) * f.x;
+                y += (hy * cur.pJx - hx * cur.pJy) * f.y;
+            }
+            if (HASK) y += 1.0 * cur.invK * x;
+            const double gk = 1.0 * cur.b + 1.0 * y;
+            if (p.keepXG) stKeep2(p.xgOut + k, make_double2(x, gk), keepPol);
+            else p.xgOut[k] = make_double2(x, gk);
+            on = cur.bi != 0 || !(x == 0.0) || !(gk >= 0.0); // NaN counts as "may be non-zero"
+            int err = 0;
+            const double q = projGrad(x, gk, cur.bi ? 1.0 : 0.0, err);
+            mx = fmax(mx, err ? INFINITY : fabs(q));
+            if (p.ite > 0 && (!p.own || p.own[k])) { // a row mirrored on two ranks is counted by the owner of rod I
+                const double dx = 1.0 * x + (-1.0) * xp;
+                const double dg = 1.0 * gk + (-1.0) * gp;
+                s0 += dx * dx;
+                s1 += dx * dg;
+                s2 += dg * dg;
+            }
         }
-        if (HASK) y += 1.0 * cur.invK * x;
-        const double gk = 1.0 * cur.b + 1.0 * y;
-        p.xgOut[k] = make_double2(x, gk);
-        int err = 0;
-        const double q = projGrad(x, gk, cur.bi ? 1.0 : 0.0, err);
-        mx = fmax(mx, err ? INFINITY : fabs(q));
-        if (p.ite > 0 && (!p.own || p.own[k])) { // a row mirrored on two ranks is counted by the owner of rod I
-            const double dx = 1.0 * x + (-1.0) * xp;
-            const double dg = 1.0 * gk + (-1.0) * gp;
-            s0 += dx * dx;
-            s1 += dx * dg;
-            s2 += dg * dg;
-        }
+        const unsigned mbits = __ballot_sync(0xffffffffu, on);
+        if (lane == 0 && p.maskOut) p.maskOut[k >> 5] = mbits;
         cur = nxt;
         k = kn;
     }
@@ -673,9 +967,17 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
 }
 
 // BBPGD keeps its iterates as interleaved {x, g} pairs: start from x0, and unpack the two newest iterates afterwards
-__global__ void k_bb_init(long long nc, const double *__restrict__ x0, double2 *__restrict__ xg) {
+__global__ void k_bb_init(long long nc, const double *__restrict__ x0, double2 *__restrict__ xg,
+                          unsigned *__restrict__ mask) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nc) xg[k] = make_double2(x0[k], 0.0);
+    bool on = false;
+    if (k < nc) {
+        const double x = x0[k];
+        xg[k] = make_double2(x, 0.0);
+        on = !(x == 0.0);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, on); // rows of the initial guess that can contribute to D x0
+    if ((threadIdx.x & 31) == 0 && k < nc && mask) mask[k >> 5] = m;
 }
 __global__ void k_bb_extract(long long nc, const double2 *__restrict__ xgNew, const double2 *__restrict__ xgOld,
                              double *__restrict__ xNew, double *__restrict__ xOld) {
@@ -911,6 +1213,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     if (nInc > 0x7fffffffLL - 16 || nc >= (1LL << 29))
         throw ArgError{ALENS_ERR_UNSUPPORTED, "setup: more than 2^29 constraints / 2^31 incidence slots on one GPU"};
     c.nInc = nInc;
+    c.incLayout = c.optForceKernel; // fixed for this setup: the force kernels follow the layout that was built
     c.incStride = ((nInc + 3) & ~3LL) + 4; // component stride: 16-byte aligned bulk copies may over-read < 4 slots
     c.incCon.reserve((size_t)c.incStride + 4);
     c.incRaw.reserve((size_t)nInc + 4);
@@ -924,10 +1227,16 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.outFB.reserve(6 * (size_t)n + 6); c.outVB.reserve(6 * (size_t)n + 6);
     c.redPartial.reserve(4 * (size_t)(gridFor(std::max<long long>(nc, 1), kVecBlock) + 1));
     if (nc > 0) {
-        k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.cBi.p, c.sGhost.p, c.incStart.p,
-                                                     c.incFill.p, c.incRaw.p);
-        k_inc_emit<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incRaw.p, conGeom(c), c.incCon.p, c.incCol.p,
-                                                    (size_t)c.incStride);
+        if (c.incLayout == 1) { // rod-major: the raw slot lists are sorted in place and ARE incCon
+            k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.cBi.p, c.sGhost.p, c.incStart.p,
+                                                         c.incFill.p, c.incCon.p);
+            k_inc_emit_rm<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incCon.p, conGeom(c), c.incCol.p);
+        } else {
+            k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.cBi.p, c.sGhost.p, c.incStart.p,
+                                                         c.incFill.p, c.incRaw.p);
+            k_inc_emit<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incRaw.p, conGeom(c), c.incCon.p,
+                                                        c.incCol.p, (size_t)c.incStride);
+        }
         k_setup<<<gridFor(nc, 256), 256, 0, st>>>(nc, conGeom(c), c.sUser.p, useV ? c.uVelNC.p : nullptr,
                                                   c.cDelta0.p, c.cGamma0.p, c.cInvKappa.p, c.cBi.p, 1.0 / dt,
                                                   c.vB.p, c.vTmp5.p, c.vLbFlag.p, c.vX0.p);
@@ -970,6 +1279,24 @@ void profFlush(Context &c) { // call after a stream synchronisation
     c.profUsed = 0;
 }
 
+// persistent grid: as many CTAs as stay resident (each keeps 16 KB of warp queues: ask for the large shared-memory
+// split), every warp walks its groups with stride gridDim * kActWarps
+template <int XMODE, bool WF, int MINB>
+static void launchForceAct(Context &c, const XIn &xin, double *U, double *F, const SolverScalars *scal,
+                           const HaloPush &hp) {
+    static int perSM = 0;
+    if (perSM == 0) {
+        cudaFuncSetAttribute((k_force_vel_act<XMODE, WF, MINB>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        ALENS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (k_force_vel_act<XMODE, WF, MINB>),
+                                                                 kActWarps * 32, 0));
+        perSM = std::max(perSM, 1);
+    }
+    const int n = c.nRods;
+    const FvAct fa{c.incStart.p, c.incCon.p, c.incCol.p, n, c.optForceDbg | (c.optKeepXG ? 0 : 64)};
+    const int grid = std::max(1, std::min(gridFor(gridFor(n, 32), kActWarps), c.numSMs * perSM * c.optForceWaves));
+    k_force_vel_act<XMODE, WF, MINB><<<grid, kActWarps * 32, 0, c.stream>>>(fa, mobIn(c), xin, U, F, scal, hp);
+}
+
 template <int XMODE, bool WF>
 static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, const SolverScalars *scal,
                            const HaloPush *push = nullptr) {
@@ -977,6 +1304,16 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
     const HaloPush hp = push ? *push : HaloPush{};
     if (n == 0 && !push) return;
     profBegin(c, 0);
+    if (c.incLayout == 1) { // rod-major slots: active-set kernel
+        if (c.optForceMinB == 6) launchForceAct<XMODE, WF, 6>(c, xin, U, F, scal, hp);
+        else if (c.optForceMinB == 8) launchForceAct<XMODE, WF, 8>(c, xin, U, F, scal, hp);
+        else if (c.optForceMinB == 10) launchForceAct<XMODE, WF, 10>(c, xin, U, F, scal, hp);
+        else launchForceAct<XMODE, WF, 5>(c, xin, U, F, scal, hp);
+        profEnd(c);
+        c.launches++;
+        c.timers.op_launches++;
+        return;
+    }
     const int block = c.optForceBlock;
     const int grid = std::max(1, gridFor((long long)gridFor(n, 32) * 32, block));
     if (c.optForceChunk == 4)
@@ -987,7 +1324,7 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
     c.launches++;
     c.timers.op_launches++;
 }
-static XIn xPlain(const double *x) { return XIn{x, nullptr, 0}; }
+static XIn xPlain(const double *x) { return XIn{x, nullptr, 0, nullptr}; }
 
 void operatorApply(Context &c, const double *x, double *y, double *force, double *vel) {
     if (!c.haveSetup) throw ArgError{ALENS_ERR_STATE, "alens_operator_apply: call alens_setup_constraints first"};
@@ -1062,11 +1399,15 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     c.vXG0.reserve((size_t)nc + 1);
     c.vXG1.reserve((size_t)nc + 1);
     double2 *XG[2] = {c.vXG0.p, c.vXG1.p};
+    c.vMask.reserve((size_t)(nc >> 5) + 2);
+    const unsigned *mask = c.optForceMask ? c.vMask.p : nullptr;
     const int grid = std::max(1, gridFor(nc, kVecBlock));
     const int gridTail = std::min(grid, c.numSMs * c.optTailCtasPerSM); // persistent (2 resident CTAs per SM)
     BbTail t{};
     t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.bi = c.cBi.p;
     t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = c.histCap; t.tol = tol;
+    t.maskOut = c.optForceMask ? c.vMask.p : nullptr;
+    t.keepXG = c.optKeepXG;
     if (multi) {
         t.own = c.cOwn.p;
         t.redOut = reinterpret_cast<double *>(c.dCounters.p); // 4 doubles of scratch
@@ -1111,11 +1452,11 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     };
     // iteration 0: g0 = A x0 + b, {x0, g0} written in place
     if (nc > 0) {
-        k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, XG[0]);
+        k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, XG[0], c.vMask.p);
         c.launches++;
     }
     t.ite = 0; t.xgPrev = XG[0]; t.xgOut = XG[0];
-    applyAndTail(XIn{nullptr, XG[0], 0});
+    applyAndTail(XIn{nullptr, XG[0], 0, mask});
     int ite = 0;
     const int batch = c.optBatch > 0 ? c.optBatch : (nc > 200000 || multi ? 8 : 32);
     syncScalars(c);
@@ -1126,7 +1467,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
             ite++;
             const int cur = (ite - 1) & 1, nxt = ite & 1;
             t.ite = ite; t.xgPrev = XG[cur]; t.xgOut = XG[nxt];
-            applyAndTail(XIn{nullptr, XG[cur], 1});
+            applyAndTail(XIn{nullptr, XG[cur], 1, mask});
         }
         syncScalars(c);
         if (c.hScal->done) c.profUsed = 0; // this batch contains early-exit no-ops: not representative
@@ -1141,6 +1482,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
         k_bb_extract<<<grid, kVecBlock, 0, st>>>(nc, XG[n & 1], older ? XG[(n - 1) & 1] : nullptr, c.vX0.p, c.vX1.p);
         c.launches++;
     }
+    c.lastXG = XG[(std::max(n, 1) - 1) & 1]; // {x, g} the last force kernel started from (alens_time_kernel)
     c.xLastApplied = c.vX0.p;
     c.xSolution = older ? c.vX1.p : c.vX0.p; // iteMax exit returns the older iterate (BCQPSolver.cpp:237-241)
     return c.hScal->done == 2 ? 1 : 0;
@@ -1154,10 +1496,35 @@ double timeKernel(Context &c, int which, int reps) {
     const long long nc = c.nCon;
     const int grid = gridFor(nc, kVecBlock);
     const int gridTail = std::min(grid, c.numSMs * c.optTailCtasPerSM);
+    if (which == 3) { // the BBPGD force kernel on the iterate / mask / step size the last solve left behind
+        if (!c.haveSolution || !c.lastXG) throw ArgError{ALENS_ERR_STATE, "alens_time_kernel: force_vel_last needs a BBPGD solve"};
+        const bool prof = c.profiling;
+        c.profiling = false;
+        SolverScalars sc;
+        ALENS_CUDA(cudaMemcpyAsync(&sc, c.dScal.p, sizeof(sc), cudaMemcpyDeviceToHost, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        SolverScalars run = sc;
+        run.done = 0;
+        ALENS_CUDA(cudaMemcpyAsync(c.dScal.p, &run, sizeof(run), cudaMemcpyHostToDevice, st));
+        const XIn xi{nullptr, c.lastXG, 1, c.optForceMask ? c.vMask.p : nullptr};
+        c.rUb.reserve(6 * (size_t)c.nRods + 6);
+        for (int i = 0; i < 3; i++) launchForceVel<2, false>(c, xi, c.rUb.p, nullptr, c.dScal.p);
+        ALENS_CUDA(cudaEventRecord(c.ev[5], st));
+        for (int i = 0; i < reps; i++) launchForceVel<2, false>(c, xi, c.rUb.p, nullptr, c.dScal.p);
+        ALENS_CUDA(cudaEventRecord(c.ev[6], st));
+        ALENS_CUDA(cudaMemcpyAsync(c.dScal.p, &sc, sizeof(sc), cudaMemcpyHostToDevice, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        ALENS_CUDA(cudaGetLastError());
+        c.profiling = prof;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.ev[5], c.ev[6]);
+        return 1e3 * ms / std::max(reps, 1);
+    }
     ALENS_CUDA(cudaMemsetAsync(c.dScal.p, 0, sizeof(SolverScalars), st));
     c.vXG0.reserve((size_t)nc + 1);
     c.vXG1.reserve((size_t)nc + 1);
-    k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, c.vXG0.p);
+    c.vMask.reserve((size_t)(nc >> 5) + 2);
+    k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, c.vXG0.p, c.vMask.p);
     BbTail t{};
     t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.bi = c.cBi.p;
     t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = 0; t.tol = -1.0;
@@ -1166,7 +1533,9 @@ double timeKernel(Context &c, int which, int reps) {
     const bool prof = c.profiling;
     c.profiling = false;
     auto one = [&]() {
-        if (which == 0) launchForceVel<2, false>(c, XIn{nullptr, c.vXG0.p, 1}, c.rU.p, nullptr, c.dScal.p);
+        if (which == 0)
+            launchForceVel<2, false>(c, XIn{nullptr, c.vXG0.p, 1, c.optForceMask ? c.vMask.p : nullptr}, c.rU.p, nullptr,
+                                     c.dScal.p);
         else if (which == 1) launchTail(c, t, gridTail);
         else launchForceVel<0, false>(c, xPlain(c.vX0.p), c.rU.p, nullptr, c.dScal.p);
     };
@@ -1419,6 +1788,23 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 0, true>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 1, true>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 2, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 5>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 5>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 5>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 5>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 8>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 8>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 8>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 8>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 10>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 10>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 10>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 10>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 6>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 6>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 6>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 6>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit_rm));
 }
 
 } // namespace alens

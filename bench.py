@@ -241,11 +241,9 @@ def main():
         ctx.set_collision_params(1.0, 1.0, COLBUF)
         ctx.set_decomposition(0, rank * box, (rank + 1) * box, skin, max_r, rank * n)
         ctx.comm_create(int(1.25 * n))
-        blob = np.frombuffer(ctx.comm_export(), dtype=np.uint8).copy()
-        mine = torch.from_numpy(blob).cuda()
-        allb = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allb, mine)
-        ctx.comm_connect([bytes(t.cpu().numpy().tobytes()) for t in allb])
+        from alens_b200 import slabs
+
+        ctx.comm_connect(slabs.exchange_blobs(ctx.comm_export()))  # the only host-side collective of the data path
     rods, relax_info = relax_on_gpu(ctx, rods, box, a.relax, configured=world > 1)
     vnc = thermal_velocity(rods, MU, DT, seed=SEED + 17 + rank)
 

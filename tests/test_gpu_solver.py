@@ -143,6 +143,45 @@ def check_solution(ctx, oracle, rods, orods, blocks, vnc, res, max_ite, choice, 
     return rep, ref, hist
 
 
+@pytest.mark.parametrize("colbuf,zero_frac", [(0.025, 0.0), (0.025, 0.85), (0.15, 0.5), (0.15, 1.0)])
+def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
+    """k_force_vel_act (rod-major slots, x == 0 skipped) against k_force_vel_lm (level-major, dense) and the oracle.
+    Skipping a zero multiplier must not change a single bit; colbuf 0.15 gives 32-rod groups with more than 256
+    slots (several batches per warp)."""
+    rods = random_rods(2000, 1.6, seed=21, frac_sphere=0.1)
+    lo, hi = [0, 0, 0], [1.6] * 3
+    blocks = gpu_collect(ctx, rods, lo, hi, (1, 1, 1), colbuf).copy()
+    orods = oracle.make_rods(rods["gid"], rods["radius"], rods["length"], oracle.wrap_positions(rods["pos"], lo, hi),
+                             rods["quat"], 1.0, 1.0, colbuf)
+    nc = len(blocks)
+    assert nc > (20000 if colbuf > 0.1 else 1000)
+    ctx.calc_mobility(MU)
+    rng = np.random.default_rng(5)
+    x = np.abs(rng.normal(size=nc))
+    x[rng.uniform(size=nc) < zero_frac] = 0.0
+    x[::7] *= -1.0  # negative multipliers and -0.0 occur in plain operator applies
+    res = {}
+    for kern in (1, 0):
+        ctx.set_option("force_kernel", kern)
+        ctx.setup_constraints(None, DT)
+        res[kern] = ctx.operator_apply(x, want_force_vel=True)
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    yo, fo, vo = oracle.operator_apply(blocks, orods, rods["immovable"], MU, DT, x)
+    for a, b in zip(res[1], (yo, fo, vo)):
+        assert relerr(a, b) < 1e-12 or np.abs(b).max() == 0
+    # the BBPGD loop (x recomputed on the fly from {x_prev, g_prev}) gives the same iterates with both kernels
+    vnc = thermal_velocity(rods, MU, DT, seed=9)
+    gam = {}
+    for kern in (1, 0):
+        ctx.set_option("force_kernel", kern)
+        rep = ctx.solve_constraints(vnc, DT, 1e-30, 15, 0)
+        assert rep.iterations == 15
+        gam[kern] = (ctx.get_gamma(), ctx.get_force_velocity()["velU"])
+    assert np.array_equal(gam[0][0], gam[1][0]) and np.array_equal(gam[0][1], gam[1][1])
+    ctx.set_option("force_kernel", 1)
+
+
 def test_bbpgd_matches_oracle_iterates(ctx, oracle):
     rods, orods, blocks = setup_case(ctx, oracle, n=2000, seed=7)
     vnc = thermal_velocity(rods, MU, DT, seed=3)

@@ -24,7 +24,7 @@ def step():
 out = []
 ref_gamma = None
 SWEEP = json.loads(os.environ.get("ALENS_SWEEP", "null")) or [
-    {"force_block": 64, "force_chunk": 2, "tail_ctas_per_sm": 2}, {"force_block": 256}, {"force_block": 64, "force_chunk": 4}]
+    {"force_kernel": 1}, {"force_kernel": 0, "force_block": 64, "force_chunk": 2}]
 for opts in SWEEP:
     for k, v in opts.items():
         ctx.set_option(k, v)
