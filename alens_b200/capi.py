@@ -55,7 +55,8 @@ class Timers(C.Structure):
                 ("solve_ms", C.c_double), ("split_ms", C.c_double), ("download_ms", C.c_double),
                 ("op_force_vel_ms", C.c_double), ("op_dtrans_ms", C.c_double), ("op_update_ms", C.c_double),
                 ("op_force_vel_n", C.c_longlong), ("op_dtrans_n", C.c_longlong), ("op_update_n", C.c_longlong),
-                ("op_launches", C.c_longlong), ("total_launches", C.c_longlong)]
+                ("op_launches", C.c_longlong), ("total_launches", C.c_longlong),
+                ("op_rows_live", C.c_longlong), ("op_applies", C.c_longlong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

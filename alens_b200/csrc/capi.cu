@@ -385,9 +385,11 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
     return guarded(ctx, [&](Context &c) {
         const std::string k = name ? name : "";
         if (k == "force_kernel") c.optForceKernel = value == 0 ? 0 : 1;
-        else if (k == "force_minb") c.optForceMinB = (value == 6 || value == 8 || value == 10) ? (int)value : 5;
+        else if (k == "force_minb") c.optForceMinB = value == 4 ? 4 : 5;
+        else if (k == "pdl") c.optPdl = (int)std::max(0LL, std::min(2LL, value));
+        else if (k == "poll") c.optPoll = value != 0;
+        else if (k == "lookahead") c.optLookahead = (int)std::max(1LL, std::min(64LL, value));
         else if (k == "keep_xg") c.optKeepXG = value != 0;
-        else if (k == "force_dbg") c.optForceDbg = (int)value;
         else if (k == "force_mask") c.optForceMask = value != 0;
         else if (k == "force_waves") c.optForceWaves = (int)std::max(1LL, std::min(64LL, value));
         else if (k == "force_chunk") c.optForceChunk = value == 4 ? 4 : 2;

@@ -648,6 +648,13 @@ void ctxInit(Context &c) {
     ALENS_CUDA(cudaMemset(c.dScal.p, 0, sizeof(SolverScalars)));
     ALENS_CUDA(cudaMallocHost((void **)&c.hScal, sizeof(SolverScalars)));
     memset(c.hScal, 0, sizeof(SolverScalars));
+    if (cudaHostAlloc((void **)&c.hProg, 64, cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer((void **)&c.hProgDev, c.hProg, 0) == cudaSuccess) {
+        c.hProg[0] = c.hProg[1] = 0;
+    } else { // no mapped host memory: the solver falls back to batched launches + stream synchronisation
+        cudaGetLastError();
+        c.hProg = c.hProgDev = nullptr;
+    }
     c.dCounters.reserve(4);
 }
 
@@ -657,6 +664,7 @@ void ctxFree(Context &c) {
     for (auto &e : c.ev)
         if (e) cudaEventDestroy(e);
     if (c.hScal) cudaFreeHost(c.hScal);
+    if (c.hProg) cudaFreeHost(c.hProg);
     if (c.ownStream && c.stream) cudaStreamDestroy(c.stream);
 }
 

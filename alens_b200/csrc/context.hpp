@@ -119,6 +119,9 @@ struct SolverScalars {
     int nhist;         // history rows written
     unsigned int ticket;   // last-block election counter of k_bb_tail
     unsigned int ticketFv; // ... of k_force_vel_lm (fused halo push)
+    unsigned long long maybeAcc;  // rows marked "may be non-zero" by the running k_bb_tail
+    unsigned long long maybeRows; // ... by the last completed one
+    unsigned long long maybeSum;  // ... summed over the applies of this solve
 };
 
 // ---- multi-GPU (comm.cu) ----------------------------------------------------------------------
@@ -257,8 +260,12 @@ struct Context {
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 1;                 // 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
     int optForceMinB = 5;                   // k_force_vel_act: resident CTAs per SM asked of the compiler (5: 96 regs, 6: 80 regs + small spill)
+    int optPdl = 1;                         // BBPGD kernels launched with programmatic stream serialization (single rank)
+    int optPoll = 1;                        // BBPGD host loop throttled by a progress word in pinned memory instead of stream syncs
+    int optLookahead = 3;                   // iterations queued behind the running one
+    bool pdlNow = false, profMute = false;  // state of the current solve
+    int *hProg = nullptr, *hProgDev = nullptr; // {completed applies, done} in mapped pinned host memory
     int optKeepXG = 1;                      // {x, g} pairs stored / gathered with the L2 evict_last policy
-    int optForceDbg = 0;                    // k_force_vel_act experiment switches (timing only)
     int optForceMask = 1;                   // k_force_vel_act consults the tail kernel's "may be non-zero" bit mask before gathering {x, g}
     int optForceWaves = 1;                  // k_force_vel_act: grid = resident CTAs x this (1 = persistent)
     int incLayout = 1;                      // layout built by the last setup (= optForceKernel at that time)
@@ -271,6 +278,7 @@ struct Context {
 
     // ---- solver vectors ----
     DevBuf<double> vX0, vX1, vG0, vG1, vB, vLbFlag; // x0 / unpacked iterates, APGD work, q, bilateral flag as double
+    DevBuf<unsigned> vMask2;                        // same for a plain vector handed to the operator (k_mask_from_x)
     DevBuf<unsigned> vMask;                         // 1 bit per constraint: 0 = the next BBPGD iterate is certainly 0 there
     DevBuf<double2> vXG0, vXG1;                     // BBPGD iterates as interleaved {x, g} pairs (ping-pong)
     DevBuf<double> vTmp0, vTmp1, vTmp2, vTmp3, vTmp4, vTmp5; // APGD work vectors
@@ -318,7 +326,7 @@ void operatorApply(Context &c, const double *x, double *y, double *force, double
 void solveConstraints(Context &c, double res, int maxIte, int choice);
 void solveCore(Context &c, double tol, int maxIte, int choice);
 void stepEuler(Context &c, double dt);
-void profFlush(Context &c);
+void profFlush(Context &c, int maxEvents = 1 << 30);
 double timeKernel(Context &c, int which, int reps);
 void preloadCollideKernels();
 void preloadSolverKernels();

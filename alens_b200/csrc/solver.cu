@@ -24,6 +24,12 @@
 
 namespace alens {
 
+static constexpr int kProfEvery = 8; // profiling on: every 8th BBPGD iteration (1, 9, 17, ...) carries event pairs
+static inline void cpuRelax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
 static constexpr int kVecBlock = 256; // threads per CTA of the per-constraint kernels
 static constexpr double kHuge = DBL_MAX / 10; // BCQPSolver.cpp:499-510
 
@@ -265,6 +271,15 @@ __device__ __forceinline__ double2 ldStream2(const double2 *p) {
     asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
+// Programmatic dependent launch (PDL): inside the BBPGD loop the force and tail kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs become resident while its predecessor drains.
+// pdlWait() returns once the predecessor grid has completed and its writes are visible; everything before it may only
+// touch data that is at least TWO kernels old.  That holds because every kernel signals pdlLaunchDependents() only
+// AFTER its own pdlWait(): when a dependent starts, the predecessor of its predecessor is complete.
+// Both are no-ops in a kernel that was launched without the attribute.
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // L2 residency control for the one array both BBPGD kernels share through L2: the tail kernel stores {x, g}
 // (16 B/row, 55 MB at 3.4M rows) and the force kernel gathers the rows that can be non-zero right afterwards.
 // Stored and gathered with an evict_last policy the pairs survive the 400 MB the tail streams past them; the tail's
@@ -467,17 +482,15 @@ struct FvAct {
     const int *incStart, *incCon; // rod-major
     const double *incCol6;        // 6 doubles per slot, contiguous
     int nRods;
-    int dbg; // experiment switches (alens_set_option "force_dbg"): timing only, results are garbage when non-zero
+    int keepXG; // gather {x, g} with the L2 evict_last policy
+    int pdlTrig; // signal the dependent launch right after the wait (else: implicitly at exit)
 };
 
+// multiplier of a slot from the gathered {x_prev, g_prev} pair (XMODE 2) or the gathered x (XMODE 0 / 1)
 template <int XMODE>
-__device__ __forceinline__ double actMultiplier(const XIn &xin, int code, double alpha, unsigned long long keep) {
+__device__ __forceinline__ double actMultiplier(int update, double2 xg, double xv, int code, double alpha) {
     const bool bi = (code & 2) != 0;
-    if (XMODE == 2) {
-        const double2 xg = keep ? ldGather2Keep(xin.xg + (code >> 2), keep) : ldGather2(xin.xg + (code >> 2));
-        return xin.update ? bbStep(xg.x, xg.y, alpha, bi) : xg.x;
-    }
-    const double xv = __ldg(xin.x + (code >> 2));
+    if (XMODE == 2) return update ? bbStep(xg.x, xg.y, alpha, bi) : xg.x;
     return XMODE == 1 ? 1.0 * xv * (bi ? 1.0 : 0.0) : xv;
 }
 
@@ -488,23 +501,19 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
     __shared__ int sCode[kActWarps][kActBatch];            // queued slot codes
     __shared__ unsigned short sSlot[kActWarps][kActBatch]; // queued slots, relative to the batch base
     __shared__ double sProd[kActWarps][2][6][32];
-    if (scal && scal->done) return;
-    double alpha = 0.0;
-    if (XMODE == 2) alpha = scal->alpha; // plain load, L1 broadcast
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
     constexpr int PER = kActBatch / 32;
     const int nGroups = (in.nRods + 31) >> 5;
     const int gStride = gridDim.x * kActWarps;
     int grp = blockIdx.x * kActWarps + w;
-    if (grp >= nGroups) return;
-    const bool useMask = XMODE == 2 && xin.mask != nullptr;
-    const unsigned long long keep = (XMODE == 2 && !(in.dbg & 64)) ? policyEvictLast() : 0ull;
+    const bool useMask = xin.mask != nullptr;
+    const unsigned long long keep = (XMODE == 2 && in.keepXG) ? policyEvictLast() : 0ull;
     // Persistent warps, software-pipelined over their groups: while group g is being worked on, the slot range of
     // g + stride and the ids of its first batch are already in flight.
-    int b, e;      // slot range of my rod in the current group
-    int code[PER]; // ids of the first batch of the current group
-    {
+    int b = 0, e = 0; // slot range of my rod in the current group
+    int code[PER];    // ids of the first batch of the current group
+    if (grp < nGroups) { // incidence structure: constant during a solve, may be read before the predecessor is done
         const int r = grp * 32 + lane;
         b = __ldg(in.incStart + min(r, in.nRods));
         e = __ldg(in.incStart + min(r + 1, in.nRods));
@@ -513,9 +522,15 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             const int p = gb + 32 * k + lane;
-            code[k] = (p < lim && !(in.dbg & 32)) ? ldStream(in.incCon + p) : -1;
+            code[k] = p < lim ? ldStream(in.incCon + p) : -1;
         }
     }
+    pdlWait(); // the iterate, the mask and the step size come from the previous kernel
+    if (in.pdlTrig) pdlLaunchDependents();
+    if (scal && scal->done) return;
+    if (grp >= nGroups) return;
+    double alpha = 0.0;
+    if (XMODE == 2) alpha = scal->alpha; // plain load, L1 broadcast
     while (true) {
         const int r = grp * 32 + lane;
         const bool act = r < in.nRods;
@@ -552,7 +567,6 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
             for (int k = 0; k < PER; k++) {
                 bool on = code[k] >= 0;
                 if (useMask) on = on && ((mw[k] >> ((code[k] >> 2) & 31)) & 1u);
-                if (in.dbg & 16) on = false;
                 const unsigned m = __ballot_sync(0xffffffffu, on);
                 if (on) {
                     const int pos = qn + __popc(m & lt);
@@ -569,16 +583,15 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
 #pragma unroll
                     for (int k = 0; k < PER; k++) {
                         const int p = gbN + 32 * k + lane;
-                        code[k] = (p < limN && !(in.dbg & 32)) ? ldStream(in.incCon + p) : -1;
+                        code[k] = p < limN ? ldStream(in.incCon + p) : -1;
                     }
                 }
-                if (act && !(in.dbg & 8)) { // read once per launch: streaming loads
+                if (act) { // read once per launch: streaming loads
                     qx = ldStream(mob.dx + r); qy = ldStream(mob.dy + r); qz = ldStream(mob.dz + r);
                     iPara = ldStream(mob.invDrag + r); iPerp = ldStream(mob.invDrag + mob.stride + r);
                     iRot = ldStream(mob.invDrag + 2 * mob.stride + r);
                     ghost = mob.ghost[r];
                 }
-                if (in.dbg & 8) ghost = 0;
             }
             if (qn == 0) continue;
             // ---- 2: entries [lo, hi) of the queue belong to my rod
@@ -593,24 +606,29 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
             // ---- 3: multipliers, column blocks, products; two queue chunks in flight
             for (int c0 = 0; c0 < qn; c0 += 64) {
                 const int i0 = c0 + lane, i1 = c0 + 32 + lane;
-                double x0 = 0.0, x1 = 0.0;
-                if (in.dbg & 2) {
-                    x0 = i0 < qn ? ((i0 & 7) == 0 ? 1.0 : 0.0) : 0.0; // no gather; 1 in 8 survivors "active"
-                    x1 = i1 < qn ? ((i1 & 7) == 0 ? 1.0 : 0.0) : 0.0;
-                } else {
-                    if (i0 < qn) x0 = actMultiplier<XMODE>(xin, sCode[w][i0], alpha, keep);
-                    if (i1 < qn) x1 = actMultiplier<XMODE>(xin, sCode[w][i1], alpha, keep);
-                }
-                double2 a01 = make_double2(0.0, 0.0), a23 = a01, a45 = a01, b01 = a01, b23 = a01, b45 = a01;
-                if (in.dbg & 1) { a01 = a23 = a45 = b01 = b23 = b45 = make_double2(1.0, 2.0); x0 = x1 = 0.0; }
-                if (x0 != 0.0) {
+                // multiplier and column block of an entry are requested TOGETHER (one round trip instead of two): the
+                // mask has already removed the rows that are certainly 0, few of the survivors turn out to be 0
+                double2 g0 = make_double2(0.0, 0.0), g1 = g0;
+                double v0 = 0.0, v1 = 0.0;
+                int cd0 = 0, cd1 = 0;
+                double2 a01 = g0, a23 = g0, a45 = g0, b01 = g0, b23 = g0, b45 = g0;
+                if (i0 < qn) {
+                    cd0 = sCode[w][i0];
+                    if (XMODE == 2) g0 = keep ? ldGather2Keep(xin.xg + (cd0 >> 2), keep) : ldGather2(xin.xg + (cd0 >> 2));
+                    else v0 = __ldg(xin.x + (cd0 >> 2));
                     const double2 *cp = reinterpret_cast<const double2 *>(in.incCol6 + 6 * ((size_t)base + sSlot[w][i0]));
                     a01 = ldStream2(cp); a23 = ldStream2(cp + 1); a45 = ldStream2(cp + 2);
                 }
-                if (x1 != 0.0) {
+                if (i1 < qn) {
+                    cd1 = sCode[w][i1];
+                    if (XMODE == 2) g1 = keep ? ldGather2Keep(xin.xg + (cd1 >> 2), keep) : ldGather2(xin.xg + (cd1 >> 2));
+                    else v1 = __ldg(xin.x + (cd1 >> 2));
                     const double2 *cp = reinterpret_cast<const double2 *>(in.incCol6 + 6 * ((size_t)base + sSlot[w][i1]));
                     b01 = ldStream2(cp); b23 = ldStream2(cp + 1); b45 = ldStream2(cp + 2);
                 }
+                double x0 = 0.0, x1 = 0.0;
+                if (i0 < qn) x0 = actMultiplier<XMODE>(xin.update, g0, v0, cd0, alpha);
+                if (i1 < qn) x1 = actMultiplier<XMODE>(xin.update, g1, v1, cd1, alpha);
                 sProd[w][0][0][lane] = a01.x * x0; sProd[w][0][1][lane] = a01.y * x0;
                 sProd[w][0][2][lane] = a23.x * x0; sProd[w][0][3][lane] = a23.y * x0;
                 sProd[w][0][4][lane] = a45.x * x0; sProd[w][0][5][lane] = a45.y * x0;
@@ -635,7 +653,7 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
             const double2 u1 = make_double2(iPara * pz + iPerp * (f[2] - pz), iRot * f[3]);
             const double2 u2 = make_double2(iRot * f[4], iRot * f[5]);
             double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
-            if (!(in.dbg & 4) || u0.x == 12345.678) { Up[0] = u0; Up[1] = u1; Up[2] = u2; }
+            Up[0] = u0; Up[1] = u1; Up[2] = u2;
             if (WRITE_F) {
                 double2 *Fp = reinterpret_cast<double2 *>(F + 6 * (size_t)r);
                 Fp[0] = make_double2(f[0], f[1]);
@@ -761,6 +779,8 @@ struct BbTail {
     int histCap;
     double tol;
     int ite; // iteration number of this launch (0 = initial gradient)
+    int pdlTrig;              // see FvAct
+    int *prog;                // pinned host words {completed applies, done}: the host throttles its launches on them
     int keepXG;               // store {x, g} with the L2 evict_last policy (the force kernel gathers it next)
     unsigned *maskOut;        // bit k = 1 unless the NEXT iterate's x_k is certainly 0 (see k_bb_tail); nc/32 words
     const unsigned char *own; // multi-rank: 1 = this rank counts the row in the dot products (nullptr = all)
@@ -778,6 +798,8 @@ struct BbTail {
 __device__ __forceinline__ void bbScalarStep(const BbTail &p, const double out[4]) {
     SolverScalars *sc = p.scal;
     sc->ticket = 0;
+    sc->maybeRows = atomicExch(&sc->maybeAcc, 0ull); // all CTAs have added theirs (they fence before taking a ticket)
+    sc->maybeSum += sc->maybeRows;
     sc->mv += 1;
     sc->ite = p.ite;
     const double res = out[3];
@@ -803,6 +825,12 @@ __device__ __forceinline__ void bbScalarStep(const BbTail &p, const double out[4
         sc->dotA = a; sc->dotB = b;
         sc->alpha = alpha;
         if (alpha < DBL_EPSILON * 10) sc->done = 2; // stagnation (BCQPSolver.cpp:229-233)
+    }
+    if (p.prog) { // host flow control: no stream synchronisation inside the loop
+        volatile int *pg = p.prog;
+        pg[1] = sc->done;
+        __threadfence_system();
+        pg[0] = p.ite + 1;
     }
 }
 
@@ -847,7 +875,9 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     long long k = (long long)blockIdx.x * kVecBlock + threadIdx.x;
     double s0 = 0, s1 = 0, s2 = 0, mx = 0;
     TailRow cur, nxt;
-    if (k < p.nc) loadTailRow<HASK>(p, (size_t)k, cur);
+    if (k < p.nc) loadTailRow<HASK>(p, (size_t)k, cur); // all of it at least two kernels old (see pdlWait)
+    pdlWait(); // U comes from the force kernel right in front
+    if (p.pdlTrig) pdlLaunchDependents();
     if (done) return;
     if (p.waitSeq) { // ghost rows of U: pushed by the neighbours' k_force_vel_lm (streaming loads above are in flight)
         if (threadIdx.x == 0) {
@@ -861,6 +891,7 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     // x_next = P(x - alpha_next g) with alpha_next > 0 (the loop stops on alpha < 10 eps): a unilateral row with
     // x = 0 and g >= 0 stays exactly 0 whatever alpha_next turns out to be -- its bit is 0.
     const int lane = threadIdx.x & 31;
+    int nMaybe = 0; // rows of this warp whose bit is set (statistics for the roofline accounting of the force kernel)
     const unsigned long long keepPol = policyEvictLast();
     while (k - lane < p.nc) {
         const bool valid = k < p.nc;
@@ -914,11 +945,13 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
         }
         const unsigned mbits = __ballot_sync(0xffffffffu, on);
         if (lane == 0 && p.maskOut) p.maskOut[k >> 5] = mbits;
+        nMaybe += __popc(mbits);
         cur = nxt;
         k = kn;
     }
     __shared__ double out[4];
     __shared__ bool last;
+    if (lane == 0 && nMaybe) atomicAdd(&p.scal->maybeAcc, (unsigned long long)nMaybe);
     blockReduce4(s0, s1, s2, mx, out);
     if (threadIdx.x == 0) {
         double *dst = p.partial + 4 * (size_t)blockIdx.x;
@@ -964,6 +997,17 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
             bbScalarStep(p, out);
         }
     }
+}
+
+// bit k = x_k can contribute to D x (k_force_vel_act on a plain vector); BIONLY: gamma_b = gamma o biFlag
+template <bool BIONLY>
+__global__ void k_mask_from_x(long long nc, const double *__restrict__ x, const unsigned char *__restrict__ bi,
+                              unsigned *__restrict__ mask) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool on = false;
+    if (k < nc) on = !(x[k] == 0.0) && (!BIONLY || bi[k] != 0);
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0 && k < nc) mask[k >> 5] = m;
 }
 
 // BBPGD keeps its iterates as interleaved {x, g} pairs: start from x0, and unpack the two newest iterates afterwards
@@ -1251,7 +1295,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
 
 // ---- optional per-kernel timing (alens_set_profiling): event pair around a launch, summed in profFlush
 static void profBegin(Context &c, int kind) {
-    if (!c.profiling) return;
+    if (!c.profiling || c.profMute) return;
     if ((size_t)c.profUsed + 2 > c.profEv.size()) {
         const size_t old = c.profEv.size();
         c.profEv.resize(old + 64);
@@ -1262,12 +1306,12 @@ static void profBegin(Context &c, int kind) {
     ALENS_CUDA(cudaEventRecord(c.profEv[c.profUsed], c.stream));
 }
 static void profEnd(Context &c) {
-    if (!c.profiling) return;
+    if (!c.profiling || c.profMute) return;
     ALENS_CUDA(cudaEventRecord(c.profEv[c.profUsed + 1], c.stream));
     c.profUsed += 2;
 }
-void profFlush(Context &c) { // call after a stream synchronisation
-    for (int i = 0; i < c.profUsed; i += 2) {
+void profFlush(Context &c, int maxEvents) { // call after a stream synchronisation
+    for (int i = 0; i < c.profUsed && i < maxEvents; i += 2) {
         float ms = 0;
         cudaEventElapsedTime(&ms, c.profEv[i], c.profEv[i + 1]);
         switch (c.profKind[i / 2]) {
@@ -1292,9 +1336,18 @@ static void launchForceAct(Context &c, const XIn &xin, double *U, double *F, con
         perSM = std::max(perSM, 1);
     }
     const int n = c.nRods;
-    const FvAct fa{c.incStart.p, c.incCon.p, c.incCol.p, n, c.optForceDbg | (c.optKeepXG ? 0 : 64)};
+    const FvAct fa{c.incStart.p, c.incCon.p, c.incCol.p, n, c.optKeepXG, c.optPdl == 2};
     const int grid = std::max(1, std::min(gridFor(gridFor(n, 32), kActWarps), c.numSMs * perSM * c.optForceWaves));
-    k_force_vel_act<XMODE, WF, MINB><<<grid, kActWarps * 32, 0, c.stream>>>(fa, mobIn(c), xin, U, F, scal, hp);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kActWarps * 32);
+    cfg.stream = c.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = c.pdlNow ? 1 : 0; // inside the BBPGD loop: overlap with the drain of the tail kernel in front
+    ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_act<XMODE, WF, MINB>), fa, mobIn(c), xin, U, F, scal, hp));
 }
 
 template <int XMODE, bool WF>
@@ -1305,10 +1358,17 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
     if (n == 0 && !push) return;
     profBegin(c, 0);
     if (c.incLayout == 1) { // rod-major slots: active-set kernel
-        if (c.optForceMinB == 6) launchForceAct<XMODE, WF, 6>(c, xin, U, F, scal, hp);
-        else if (c.optForceMinB == 8) launchForceAct<XMODE, WF, 8>(c, xin, U, F, scal, hp);
-        else if (c.optForceMinB == 10) launchForceAct<XMODE, WF, 10>(c, xin, U, F, scal, hp);
-        else launchForceAct<XMODE, WF, 5>(c, xin, U, F, scal, hp);
+        XIn xm = xin;
+        if (XMODE != 2 && c.optForceMask && c.nCon > 0) { // plain vector: one cheap pass marks its non-zero rows
+            c.vMask2.reserve((size_t)(c.nCon >> 5) + 2);
+            const int g = gridFor(c.nCon, kVecBlock);
+            if (XMODE == 1) k_mask_from_x<true><<<g, kVecBlock, 0, c.stream>>>(c.nCon, xin.x, c.cBi.p, c.vMask2.p);
+            else k_mask_from_x<false><<<g, kVecBlock, 0, c.stream>>>(c.nCon, xin.x, c.cBi.p, c.vMask2.p);
+            c.launches++;
+            xm.mask = c.vMask2.p;
+        }
+        if (c.optForceMinB == 4) launchForceAct<XMODE, WF, 4>(c, xm, U, F, scal, hp);
+        else launchForceAct<XMODE, WF, 5>(c, xm, U, F, scal, hp);
         profEnd(c);
         c.launches++;
         c.timers.op_launches++;
@@ -1385,8 +1445,17 @@ static ReduceArgs reduceArgs(Context &c) { // next mailbox round
 
 static void launchTail(Context &c, const BbTail &t, int gridTail) {
     profBegin(c, 1);
-    if (c.nBilateral > 0) k_bb_tail<true><<<gridTail, kVecBlock, 0, c.stream>>>(t);
-    else k_bb_tail<false><<<gridTail, kVecBlock, 0, c.stream>>>(t);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)gridTail);
+    cfg.blockDim = dim3(kVecBlock);
+    cfg.stream = c.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = c.pdlNow ? 1 : 0;
+    if (c.nBilateral > 0) ALENS_CUDA(cudaLaunchKernelEx(&cfg, k_bb_tail<true>, t));
+    else ALENS_CUDA(cudaLaunchKernelEx(&cfg, k_bb_tail<false>, t));
     profEnd(c);
     c.launches++;
     c.timers.op_launches++;
@@ -1408,6 +1477,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = c.histCap; t.tol = tol;
     t.maskOut = c.optForceMask ? c.vMask.p : nullptr;
     t.keepXG = c.optKeepXG;
+    t.pdlTrig = c.optPdl == 2;
     if (multi) {
         t.own = c.cOwn.p;
         t.redOut = reinterpret_cast<double *>(c.dCounters.p); // 4 doubles of scratch
@@ -1450,29 +1520,61 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
             c.launches++;
         }
     };
+    const bool poll = !multi && c.optPoll && c.hProg != nullptr;
+    if (poll) {
+        c.hProg[0] = 0; c.hProg[1] = 0;
+        t.prog = c.hProgDev;
+    }
+    c.pdlNow = !multi && c.optPdl && c.incLayout == 1;
     // iteration 0: g0 = A x0 + b, {x0, g0} written in place
     if (nc > 0) {
         k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, XG[0], c.vMask.p);
         c.launches++;
     }
     t.ite = 0; t.xgPrev = XG[0]; t.xgOut = XG[0];
+    c.profMute = poll; // iteration 0 (x0: few non-zero rows) is not part of the sample
     applyAndTail(XIn{nullptr, XG[0], 0, mask});
+    c.profMute = false;
     int ite = 0;
-    const int batch = c.optBatch > 0 ? c.optBatch : (nc > 200000 || multi ? 8 : 32);
-    syncScalars(c);
-    profFlush(c);
-    while (!c.hScal->done && ite < maxIte) {
-        const int nb = std::min(batch, maxIte - ite);
-        for (int b = 0; b < nb; b++) {
+    if (poll) {
+        // Single rank: the host never synchronises inside the loop.  The last CTA of every tail kernel publishes
+        // {completed applies, done} in pinned host memory; the host keeps at most `look` iterations queued behind
+        // the running one and stops as soon as it sees `done` (kernels queued past that point exit at once).
+        const int look = std::max(1, c.optLookahead);
+        volatile int *pg = c.hProg;
+        while (ite < maxIte) {
+            while (pg[0] < ite + 1 - look && !pg[1]) cpuRelax();
+            if (pg[1]) break;
             ite++;
             const int cur = (ite - 1) & 1, nxt = ite & 1;
             t.ite = ite; t.xgPrev = XG[cur]; t.xgOut = XG[nxt];
+            c.profMute = (ite % kProfEvery) != 1; // event pairs only around a sample: they break the PDL overlap
             applyAndTail(XIn{nullptr, XG[cur], 1, mask});
         }
+        c.profMute = false;
         syncScalars(c);
-        if (c.hScal->done) c.profUsed = 0; // this batch contains early-exit no-ops: not representative
-        else profFlush(c);
+        // 2 launches x 2 events per sampled iteration; sampled iterations past the last executed one were no-ops
+        profFlush(c, c.hScal->ite >= 1 ? 4 * ((c.hScal->ite - 1) / kProfEvery + 1) : 0);
+    } else {
+        const int batch = c.optBatch > 0 ? c.optBatch : (nc > 200000 || multi ? 8 : 32);
+        syncScalars(c);
+        profFlush(c);
+        while (!c.hScal->done && ite < maxIte) {
+            const int nb = std::min(batch, maxIte - ite);
+            for (int b = 0; b < nb; b++) {
+                ite++;
+                const int cur = (ite - 1) & 1, nxt = ite & 1;
+                t.ite = ite; t.xgPrev = XG[cur]; t.xgOut = XG[nxt];
+                applyAndTail(XIn{nullptr, XG[cur], 1, mask});
+            }
+            syncScalars(c);
+            if (c.hScal->done) c.profUsed = 0; // this batch contains early-exit no-ops: not representative
+            else profFlush(c);
+        }
     }
+    c.pdlNow = false;
+    c.timers.op_rows_live = (long long)c.hScal->maybeSum;
+    c.timers.op_applies = c.hScal->mv;
     ALENS_CUDA(cudaGetLastError());
     if (c.hScal->done == 4) throw ArgError{ALENS_ERR_COMM, "solve: timed out waiting for a peer rank"};
     const int n = c.hScal->ite; // iterations actually executed
@@ -1792,19 +1894,13 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 5>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 5>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 5>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 8>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 8>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 8>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 8>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 10>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 10>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 10>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 10>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 6>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 6>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 6>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 6>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 4>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 4>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 4>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 4>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit_rm));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<true>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<false>));
 }
 
 } // namespace alens

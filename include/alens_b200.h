@@ -77,6 +77,9 @@ typedef struct alens_timers {
     long long op_force_vel_n, op_dtrans_n, op_update_n; /* launches behind the three sums       */
     long long op_launches;    /* kernel launches inside the last BCQP loop                      */
     long long total_launches; /* kernel launches since alens_reset_timers                       */
+    long long op_rows_live;   /* BBPGD: constraint rows that could be non-zero, summed over the
+                                 operator applies of the last solve (the force kernel reads only those) */
+    long long op_applies;     /* ... and the number of applies behind that sum                   */
 } alens_timers;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
