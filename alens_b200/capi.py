@@ -31,6 +31,7 @@ EXPORTS = [
     "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
     "alens_set_decomposition", "alens_comm_create", "alens_comm_blob_size", "alens_comm_export",
     "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
+    "alens_set_velocity_noncon_async",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
 ]
 
@@ -199,6 +200,10 @@ class Context:
     def set_velocity_noncon(self, v):
         v = None if v is None else np.ascontiguousarray(v, dtype=np.float64)
         self._call("alens_set_velocity_noncon", _dp(v))
+
+    def set_velocity_noncon_async_raw(self, v_p):
+        """pinned host pointer; the copy overlaps the calls that follow (see alens_b200.h)"""
+        self._call("alens_set_velocity_noncon_async", C.c_void_p(v_p))
 
     def set_profiling(self, on):
         self._call("alens_set_profiling", C.c_int(1 if on else 0))

@@ -209,6 +209,29 @@ int alens_set_velocity_noncon(alens_ctx *ctx, const double *v) {
     });
 }
 
+int alens_set_velocity_noncon_async(alens_ctx *ctx, const double *v) {
+    return guarded(ctx, [&](Context &c) {
+        if (!v) {
+            c.haveVelNC = false;
+            return;
+        }
+        if (!c.copyStream) {
+            ALENS_CUDA(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+            ALENS_CUDA(cudaEventCreateWithFlags(&c.evVelNC, cudaEventDisableTiming));
+            ALENS_CUDA(cudaEventCreateWithFlags(&c.evMain, cudaEventDisableTiming));
+        }
+        c.uVelNC.reserve(6 * (size_t)c.nRods + 6);
+        // the side stream starts behind everything the main stream has been given so far (allocation, last readers)
+        ALENS_CUDA(cudaEventRecord(c.evMain, c.stream));
+        ALENS_CUDA(cudaStreamWaitEvent(c.copyStream, c.evMain, 0));
+        if (c.nLocal > 0)
+            ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, v, 48 * (size_t)c.nLocal, cudaMemcpyHostToDevice, c.copyStream));
+        ALENS_CUDA(cudaEventRecord(c.evVelNC, c.copyStream));
+        c.velNCPending = true;
+        c.haveVelNC = true;
+    });
+}
+
 int alens_set_profiling(alens_ctx *ctx, int on) {
     return guarded(ctx, [&](Context &c) { c.profiling = on != 0; });
 }

@@ -267,6 +267,7 @@ static unsigned char *nbWin(Context &c, int dir) {
 void commExchangeGhosts(Context &c) {
     Comm &m = c.comm;
     cudaStream_t st = c.stream;
+    waitVelNC(c); // ghost records carry the owner's velNonCon rows
     const int n = c.nLocal, ax = c.slabAxis;
     const double gw = c.ghostWidth;
     CommHeader *me = hdrOf(m.win);

@@ -216,6 +216,9 @@ struct Context {
     DevBuf<int> userToSorted;
     DevBuf<double> uVelNC;  // 6n, user order
     bool haveVelNC = false;
+    cudaStream_t copyStream = nullptr;      // alens_set_velocity_noncon_async
+    cudaEvent_t evVelNC = nullptr, evMain = nullptr;
+    bool velNCPending = false;              // a side-stream copy into uVelNC has not been waited for yet
 
     // ---- cell list + rods, sorted (cell-major) order ----
     CellGrid grid{};
@@ -328,6 +331,13 @@ void solveCore(Context &c, double tol, int maxIte, int choice);
 void stepEuler(Context &c, double dt);
 void profFlush(Context &c, int maxEvents = 1 << 30);
 double timeKernel(Context &c, int which, int reps);
+// make the main stream wait for a pending alens_set_velocity_noncon_async copy (before anything reads uVelNC)
+inline void waitVelNC(Context &c) {
+    if (c.velNCPending) {
+        cudaStreamWaitEvent(c.stream, c.evVelNC, 0);
+        c.velNCPending = false;
+    }
+}
 void preloadCollideKernels();
 void preloadSolverKernels();
 void preloadBlockKernels();

@@ -1220,6 +1220,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     const int n = c.nRods;
     const long long nc = c.nCon;
     c.dt = dt;
+    waitVelNC(c);
     // velNonCon (user order)
     if (velNC) { // (also on a rank that owns no rods: the ghost-row exchange below is collective)
         c.uVelNC.reserve(6 * (size_t)n + 6);
@@ -1852,6 +1853,7 @@ void stepEuler(Context &c, double dt) {
     if (!c.haveSolution) throw ArgError{ALENS_ERR_STATE, "alens_step_euler: no solution available"};
     const int n = c.nLocal;
     if (n == 0) return;
+    waitVelNC(c);
     k_step_euler<<<gridFor(n, 256), 256, 0, c.stream>>>(n, dt, c.haveVelNC ? c.uVelNC.p : nullptr, c.outVU.p,
                                                         c.outVB.p, c.uPos.p, c.uQuat.p);
     c.launches++;

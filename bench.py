@@ -269,9 +269,10 @@ def main():
 
     def step_e2e():
         upload()
+        ctx.set_velocity_noncon_async_raw(h_vnc.data_ptr())  # this step's velNonCon: its H2D overlaps the pair search
         nc = ctx.collect_pair_collision()
         ctx.calc_mobility(MU)
-        rep = ctx.solve_constraints_raw(h_vnc.data_ptr(), DT, RES, MAXITE, 0)
+        rep = ctx.solve_constraints_raw(None, DT, RES, MAXITE, 0)
         ctx.get_force_velocity_raw(*[t.data_ptr() for t in h_out])
         return nc, rep
 

@@ -151,6 +151,11 @@ int alens_solve_constraints(alens_ctx *ctx, const double *velNonCon, double dt, 
  * device: 6n host doubles in local rod order, NULL = zero.  alens_solve_constraints / alens_setup_constraints
  * called with velNonCon == NULL use this resident vector. */
 int alens_set_velocity_noncon(alens_ctx *ctx, const double *velNonCon);
+/* Same, without waiting for the copy: it runs on a side stream and overlaps whatever the caller does next
+ * (typically alens_collect_pair_collision); the next call that reads the vector waits for it on the device.
+ * velNonCon must be page-locked host memory and stay unchanged until alens_solve_constraints /
+ * alens_setup_constraints has returned. */
+int alens_set_velocity_noncon_async(alens_ctx *ctx, const double *velNonCon);
 /* only the setup part (q, bounds, incidence); lets tests call alens_operator_apply */
 int alens_setup_constraints(alens_ctx *ctx, const double *velNonCon, double dt);
 /* ConstraintOperator::apply (ConstraintOperator.cpp:30-71): y = (D^T M D + K^-1/dt) x, host vectors of

@@ -286,3 +286,27 @@ def test_step_euler(ctx, oracle):
     w = np.linalg.norm(v[:, 3:], axis=1)
     ang = 2 * np.arccos(np.clip(np.abs((q0 * q1).sum(axis=1)), -1, 1))
     np.testing.assert_allclose(ang, w * DT, atol=1e-7)
+
+
+def test_velocity_noncon_async_upload(ctx, oracle):
+    """alens_set_velocity_noncon_async (side-stream H2D from pinned memory, overlapping the pair search) gives the
+    same solve as passing the vector to alens_solve_constraints."""
+    import torch
+
+    rods = random_rods(3000, 1.8, seed=31)
+    lo, hi = [0.0] * 3, [1.8] * 3
+    vnc = thermal_velocity(rods, MU, DT, seed=12)
+    pinned = torch.from_numpy(vnc.copy()).pin_memory()
+    ctx.set_domain(lo, hi, (1, 1, 1))
+    ctx.set_collision_params(1.0, 1.0, 0.025)
+    out = []
+    for mode in ("sync", "async"):
+        ctx.set_rods(rods["gid"], rods["pos"], rods["quat"], rods["length"], rods["radius"], rods["immovable"])
+        if mode == "async":
+            ctx.set_velocity_noncon_async_raw(pinned.data_ptr())
+        ctx.collect_pair_collision()
+        ctx.calc_mobility(MU)
+        rep = ctx.solve_constraints(vnc if mode == "sync" else None, DT, 1e-6, 200, 0)
+        out.append((rep.iterations, ctx.get_gamma(), ctx.get_force_velocity()["velU"]))
+    assert out[0][0] == out[1][0] > 0
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
