@@ -817,7 +817,7 @@ void rodsUploaded(Context &c, bool wrap) {
 void reserveConstraints(Context &c, size_t n, bool keep) {
     if (n <= c.conCap) return;
     // SoA arrays use conCap as the component stride, so growth re-lays them out
-    const size_t ncap = n + n / 4 + 1024;
+    const size_t ncap = (n + n / 4 + 1024 + 31) & ~(size_t)31; // component stride: 16-byte aligned components, padded tail
     const size_t old = c.conCap;
     const size_t live = keep ? (size_t)c.nCon : 0;
     cudaStream_t st = c.stream;

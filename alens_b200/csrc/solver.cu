@@ -271,6 +271,35 @@ __device__ __forceinline__ double2 ldStream2(const double2 *p) {
     asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
+// mbarrier + TMA 1-D bulk copy (global -> shared, completion counted in bytes on the barrier)
+__device__ __forceinline__ unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    do { // try_wait suspends the thread in hardware until the phase flips or a time limit passes
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smemAddr(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
 // Programmatic dependent launch (PDL): inside the BBPGD loop the force and tail kernels are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs become resident while its predecessor drains.
 // pdlWait() returns once the predecessor grid has completed and its writes are visible; everything before it may only
@@ -867,91 +896,55 @@ __device__ __forceinline__ void loadTailRow(const BbTail &p, size_t k, TailRow &
 // and one L2 round trip (96 B) in flight and never waits on an index before issuing loads.
 // HASK = false: no row has a finite stiffness (K^-1 = 0 everywhere: collision-only pools), the K^-1 x term and its
 // 8 B/row are skipped.
+// one row of the tail: x = P(x_prev - alpha g_prev), y = row k of D^T times U (+ K^-1 x), g = y + b, the row's share of the
+// residual and of the BB dot products; stores {x, g}; returns the row's "may be non-zero next time" bit
 template <bool HASK>
-__global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
-    const int done = p.scal->done;
-    const double alpha = p.scal->alpha; // plain loads: every thread reads the same two words, which L1 broadcasts
-    const long long stride = (long long)gridDim.x * kVecBlock;
-    long long k = (long long)blockIdx.x * kVecBlock + threadIdx.x;
-    double s0 = 0, s1 = 0, s2 = 0, mx = 0;
-    TailRow cur, nxt;
-    if (k < p.nc) loadTailRow<HASK>(p, (size_t)k, cur); // all of it at least two kernels old (see pdlWait)
-    pdlWait(); // U comes from the force kernel right in front
-    if (p.pdlTrig) pdlLaunchDependents();
-    if (done) return;
-    if (p.waitSeq) { // ghost rows of U: pushed by the neighbours' k_force_vel_lm (streaming loads above are in flight)
-        if (threadIdx.x == 0) {
-            if (p.waitFlag[0]) waitSeq(p.waitFlag[0], p.waitSeq, p.red.err);
-            if (p.waitFlag[1]) waitSeq(p.waitFlag[1], p.waitSeq, p.red.err);
-        }
-        __syncthreads();
+__device__ __forceinline__ bool tailRowMath(const BbTail &p, const TailRow &cur, bool two, long long k, double alpha,
+                                            const double2 &a, const double2 &b, const double2 &c, const double2 &d,
+                                            const double2 &e, const double2 &f, unsigned long long keepPol, double &s0,
+                                            double &s1, double &s2, double &mx) {
+    const double xp = cur.xg.x, gp = cur.xg.y;
+    const double x = p.ite > 0 ? bbStep(xp, gp, alpha, cur.bi != 0) : xp;
+    const double gx = cur.gx, gy = cur.gy, gz = cur.gz;
+    double y = gx * a.x;
+    y += gy * a.y;
+    y += gz * b.x;
+    y += (gz * cur.pIy - gy * cur.pIz) * b.y;
+    y += (gx * cur.pIz - gz * cur.pIx) * c.x;
+    y += (gy * cur.pIx - gx * cur.pIy) * c.y;
+    if (two) { // (the gathers do not wait for this test)
+        const double hx = -gx, hy = -gy, hz = -gz;
+        y += hx * d.x;
+        y += hy * d.y;
+        y += hz * e.x;
+        y += (hz * cur.pJy - hy * cur.pJz) * e.y;
+        y += (hx * cur.pJz - hz * cur.pJx) * f.x;
+        y += (hy * cur.pJx - hx * cur.pJy) * f.y;
     }
-    // The loop condition is warp-uniform (first row of the warp), rows past the end are predicated off: every
-    // trip ends with a ballot that publishes, for the NEXT iteration's force kernel, which rows can be non-zero.
-    // x_next = P(x - alpha_next g) with alpha_next > 0 (the loop stops on alpha < 10 eps): a unilateral row with
-    // x = 0 and g >= 0 stays exactly 0 whatever alpha_next turns out to be -- its bit is 0.
-    const int lane = threadIdx.x & 31;
-    int nMaybe = 0; // rows of this warp whose bit is set (statistics for the roofline accounting of the force kernel)
-    const unsigned long long keepPol = policyEvictLast();
-    while (k - lane < p.nc) {
-        const bool valid = k < p.nc;
-        const long long kn = k + stride;
-        // (1) the six 16-byte gathers of this row's two U rows (L2 hits, needed first), unconditional and back to back:
-        // a one-sided row gathers rod I twice, a lane past the end gathers row 0
-        const int iI = valid ? cur.iI : 0;
-        const bool two = valid && cur.iJ >= 0;
-        const int iJ = two ? cur.iJ : iI;
-        const double2 *uI = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)iI);
-        const double2 *uJ = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)iJ);
-        const double2 a = ldGather2(uI), b = ldGather2(uI + 1), c = ldGather2(uI + 2);
-        const double2 d = ldGather2(uJ), e = ldGather2(uJ + 1), f = ldGather2(uJ + 2);
-        // (2) the streaming operands of the next row (DRAM, needed one trip later)
-        if (kn < p.nc) loadTailRow<HASK>(p, (size_t)kn, nxt);
-        bool on = false;
-        if (valid) {
-            const double xp = cur.xg.x, gp = cur.xg.y;
-            const double x = p.ite > 0 ? bbStep(xp, gp, alpha, cur.bi != 0) : xp;
-            const double gx = cur.gx, gy = cur.gy, gz = cur.gz;
-            double y = gx * a.x;
-            y += gy * a.y;
-            y += gz * b.x;
-            y += (gz * cur.pIy - gy * cur.pIz) * b.y;
-            y += (gx * cur.pIz - gz * cur.pIx) * c.x;
-            y += (gy * cur.pIx - gx * cur.pIy) * c.y;
-            if (two) { // (the gathers above do not wait for this test)
-                const double hx = -gx, hy = -gy, hz = -gz;
-                y += hx * d.x;
-                y += hy * d.y;
-                y += hz * e.x;
-                y += (hz * cur.pJy - hy * cur.pJz) * e.y;
-                y += (hx * cur.pJz - hz * cur.pJx) * f.x;
-                y += (hy * cur.pJx - hx * cur.pJy) * f.y;
-            }
-            if (HASK) y += 1.0 * cur.invK * x;
-            const double gk = 1.0 * cur.b + 1.0 * y;
-            if (p.keepXG) stKeep2(p.xgOut + k, make_double2(x, gk), keepPol);
-            else p.xgOut[k] = make_double2(x, gk);
-            on = cur.bi != 0 || !(x == 0.0) || !(gk >= 0.0); // NaN counts as "may be non-zero"
-            int err = 0;
-            const double q = projGrad(x, gk, cur.bi ? 1.0 : 0.0, err);
-            mx = fmax(mx, err ? INFINITY : fabs(q));
-            if (p.ite > 0 && (!p.own || p.own[k])) { // a row mirrored on two ranks is counted by the owner of rod I
-                const double dx = 1.0 * x + (-1.0) * xp;
-                const double dg = 1.0 * gk + (-1.0) * gp;
-                s0 += dx * dx;
-                s1 += dx * dg;
-                s2 += dg * dg;
-            }
-        }
-        const unsigned mbits = __ballot_sync(0xffffffffu, on);
-        if (lane == 0 && p.maskOut) p.maskOut[k >> 5] = mbits;
-        nMaybe += __popc(mbits);
-        cur = nxt;
-        k = kn;
+    if (HASK) y += 1.0 * cur.invK * x;
+    const double gk = 1.0 * cur.b + 1.0 * y;
+    if (p.keepXG) stKeep2(p.xgOut + k, make_double2(x, gk), keepPol);
+    else p.xgOut[k] = make_double2(x, gk);
+    int err = 0;
+    const double q = projGrad(x, gk, cur.bi ? 1.0 : 0.0, err);
+    mx = fmax(mx, err ? INFINITY : fabs(q));
+    if (p.ite > 0 && (!p.own || p.own[k])) { // a row mirrored on two ranks is counted by the owner of rod I
+        const double dx = 1.0 * x + (-1.0) * xp;
+        const double dg = 1.0 * gk + (-1.0) * gp;
+        s0 += dx * dx;
+        s1 += dx * dg;
+        s2 += dg * dg;
     }
+    // x_next = P(x - alpha_next g) with alpha_next > 0 (the loop stops on alpha < 10 eps): a unilateral row with x = 0 and
+    // g >= 0 stays exactly 0 whatever alpha_next turns out to be -- its bit is 0.  NaN counts as "may be non-zero".
+    return cur.bi != 0 || !(x == 0.0) || !(gk >= 0.0);
+}
+
+// end of a tail kernel: CTA partials, last-CTA election, fixed-order reduction, (multi-rank allreduce,) scalar step
+__device__ __forceinline__ void tailEpilogue(const BbTail &p, double s0, double s1, double s2, double mx, int nMaybe) {
     __shared__ double out[4];
     __shared__ bool last;
-    if (lane == 0 && nMaybe) atomicAdd(&p.scal->maybeAcc, (unsigned long long)nMaybe);
+    if ((threadIdx.x & 31) == 0 && nMaybe) atomicAdd(&p.scal->maybeAcc, (unsigned long long)nMaybe);
     blockReduce4(s0, s1, s2, mx, out);
     if (threadIdx.x == 0) {
         double *dst = p.partial + 4 * (size_t)blockIdx.x;
@@ -997,6 +990,173 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
             bbScalarStep(p, out);
         }
     }
+}
+
+template <bool HASK>
+__global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
+    const int done = p.scal->done;
+    const double alpha = p.scal->alpha; // plain loads: every thread reads the same two words, which L1 broadcasts
+    const long long stride = (long long)gridDim.x * kVecBlock;
+    long long k = (long long)blockIdx.x * kVecBlock + threadIdx.x;
+    double s0 = 0, s1 = 0, s2 = 0, mx = 0;
+    TailRow cur, nxt;
+    if (k < p.nc) loadTailRow<HASK>(p, (size_t)k, cur); // all of it at least two kernels old (see pdlWait)
+    pdlWait(); // U comes from the force kernel right in front
+    if (p.pdlTrig) pdlLaunchDependents();
+    if (done) return;
+    if (p.waitSeq) { // ghost rows of U: pushed by the neighbours' force kernels (the streaming loads above are in flight)
+        if (threadIdx.x == 0) {
+            if (p.waitFlag[0]) waitSeq(p.waitFlag[0], p.waitSeq, p.red.err);
+            if (p.waitFlag[1]) waitSeq(p.waitFlag[1], p.waitSeq, p.red.err);
+        }
+        __syncthreads();
+    }
+    // The loop condition is warp-uniform (first row of the warp), rows past the end are predicated off: every
+    // trip ends with a ballot that publishes, for the NEXT iteration's force kernel, which rows can be non-zero.
+    const int lane = threadIdx.x & 31;
+    int nMaybe = 0; // rows of this warp whose bit is set (statistics for the roofline accounting of the force kernel)
+    const unsigned long long keepPol = policyEvictLast();
+    while (k - lane < p.nc) {
+        const bool valid = k < p.nc;
+        const long long kn = k + stride;
+        // (1) the six 16-byte gathers of this row's two U rows (L2 hits, needed first), unconditional and back to back:
+        // a one-sided row gathers rod I twice, a lane past the end gathers row 0
+        const int iI = valid ? cur.iI : 0;
+        const bool two = valid && cur.iJ >= 0;
+        const int iJ = two ? cur.iJ : iI;
+        const double2 *uI = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)iI);
+        const double2 *uJ = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)iJ);
+        const double2 a = ldGather2(uI), b = ldGather2(uI + 1), c = ldGather2(uI + 2);
+        const double2 d = ldGather2(uJ), e = ldGather2(uJ + 1), f = ldGather2(uJ + 2);
+        // (2) the streaming operands of the next row (DRAM, needed one trip later)
+        if (kn < p.nc) loadTailRow<HASK>(p, (size_t)kn, nxt);
+        bool on = false;
+        if (valid) on = tailRowMath<HASK>(p, cur, two, k, alpha, a, b, c, d, e, f, keepPol, s0, s1, s2, mx);
+        const unsigned mbits = __ballot_sync(0xffffffffu, on);
+        if (lane == 0 && p.maskOut) p.maskOut[k >> 5] = mbits;
+        nMaybe += __popc(mbits);
+        cur = nxt;
+        k = kn;
+    }
+    tailEpilogue(p, s0, s1, s2, mx, nMaybe);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same tail with its 15 streaming operand arrays staged through shared memory by the TMA engine: tiles of 256
+// consecutive rows, one cp.async.bulk per array and tile (SASS UBLKCP) into a ring of NST stages, completion through one
+// mbarrier per stage (expect_tx = bytes of the tile).  One elected thread issues the copies of tile i + NST - 1 before
+// the CTA works on tile i, so NST - 1 tiles (26 KB each) per CTA are in flight independently of what the warps do:
+// the register-staged version above has at most one row per thread (113 B) in flight and pays for it in registers.
+static constexpr int kTailTile = 256;
+template <bool HASK>
+struct TailStage {
+    double n[3][kTailTile], pI[3][kTailTile], pJ[3][kTailTile];
+    double2 xg[kTailTile];
+    double b[kTailTile];
+    double invK[HASK ? kTailTile : 2];
+    int iI[kTailTile], iJ[kTailTile];
+    unsigned char bi[kTailTile];
+};
+
+template <bool HASK, int NST>
+__global__ void __launch_bounds__(kTailTile, 2) k_bb_tail_ring(BbTail p, int nTiles) {
+    extern __shared__ __align__(128) unsigned char smRaw[];
+    using Stage = TailStage<HASK>;
+    Stage *stg = reinterpret_cast<Stage *>(smRaw);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smRaw + NST * sizeof(Stage));
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int done = p.scal->done; // two kernels old (see pdlWait)
+    const double alpha = p.scal->alpha;
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) mbarInit(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t S = p.g.stride;
+    auto issue = [&](int i) { // bulk copies of my i-th tile into stage i % NST (thread 0 only)
+        const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+        if (tile >= nTiles) return;
+        Stage &st = stg[i % NST];
+        unsigned long long *br = &bar[i % NST];
+        const size_t k0 = (size_t)tile * kTailTile;
+        const unsigned cnt = (unsigned)min((long long)kTailTile, p.nc - (long long)k0);
+        const unsigned c16 = (cnt + 15u) & ~15u; // sizes in multiples of 16 B; the arrays are padded accordingly
+        mbarExpectTx(br, c16 * (9u * 8u + 16u + 8u + (HASK ? 8u : 0u) + 4u + 4u + 1u));
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            bulkLoad(st.n[c], p.g.n + k0 + c * S, c16 * 8u, br);
+            bulkLoad(st.pI[c], p.g.pI + k0 + c * S, c16 * 8u, br);
+            bulkLoad(st.pJ[c], p.g.pJ + k0 + c * S, c16 * 8u, br);
+        }
+        bulkLoad(st.xg, p.xgPrev + k0, c16 * 16u, br);
+        bulkLoad(st.b, p.b + k0, c16 * 8u, br);
+        if (HASK) bulkLoad(st.invK, p.invKdt + k0, c16 * 8u, br);
+        bulkLoad(st.iI, p.g.idxI + k0, c16 * 4u, br);
+        bulkLoad(st.iJ, p.g.idxJ + k0, c16 * 4u, br);
+        bulkLoad(st.bi, p.bi + k0, c16, br);
+    };
+    // everything the copies read is at least two kernels old: they may start before the force kernel in front is done
+    if (tid == 0 && !done)
+        for (int i = 0; i < NST - 1; i++) issue(i);
+    pdlWait(); // U comes from the force kernel right in front
+    if (p.pdlTrig) pdlLaunchDependents();
+    if (done) return;
+    if (p.waitSeq) {
+        if (tid == 0) {
+            if (p.waitFlag[0]) waitSeq(p.waitFlag[0], p.waitSeq, p.red.err);
+            if (p.waitFlag[1]) waitSeq(p.waitFlag[1], p.waitSeq, p.red.err);
+        }
+        __syncthreads();
+    }
+    double s0 = 0, s1 = 0, s2 = 0, mx = 0;
+    int nMaybe = 0;
+    const unsigned long long keepPol = policyEvictLast();
+    // The six U gathers of a row (L2 round trip) are requested one trip ahead, as soon as the ids of the next tile have
+    // landed: a warp never waits for a gather it has just issued.
+    int iI = 0, iJ = -1;
+    double2 a, b, c, d, e, f;
+    auto gather = [&](int i) { // ids of my row of tile i from its stage, then the gathers
+        const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+        mbarWait(&bar[i % NST], (unsigned)((i / NST) & 1));
+        const Stage &st = stg[i % NST];
+        const bool valid = tile * kTailTile + tid < p.nc;
+        iI = valid ? st.iI[tid] : 0;
+        iJ = valid ? st.iJ[tid] : -1;
+        const double2 *uI = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)iI);
+        const double2 *uJ = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)(iJ >= 0 ? iJ : iI));
+        a = ldGather2(uI); b = ldGather2(uI + 1); c = ldGather2(uI + 2);
+        d = ldGather2(uJ); e = ldGather2(uJ + 1); f = ldGather2(uJ + 2);
+    };
+    if ((long long)blockIdx.x < nTiles) gather(0);
+    for (int i = 0;; i++) {
+        const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+        if (tile >= nTiles) break;
+        if (tid == 0) issue(i + NST - 1); // into the stage the CTA left behind the barrier at the end of trip i - 1
+        const Stage &st = stg[i % NST];
+        const long long k = tile * kTailTile + tid;
+        const bool valid = k < p.nc;
+        TailRow cur;
+        cur.iI = iI; cur.iJ = iJ;
+        const bool two = iJ >= 0;
+        const double2 a0 = a, b0 = b, c0 = c, d0 = d, e0 = e, f0 = f;
+        if (tile + gridDim.x < nTiles) gather(i + 1); // next trip's gathers: in flight during this trip's arithmetic
+        bool on = false;
+        if (valid) {
+            cur.gx = st.n[0][tid]; cur.gy = st.n[1][tid]; cur.gz = st.n[2][tid];
+            cur.pIx = st.pI[0][tid]; cur.pIy = st.pI[1][tid]; cur.pIz = st.pI[2][tid];
+            cur.pJx = st.pJ[0][tid]; cur.pJy = st.pJ[1][tid]; cur.pJz = st.pJ[2][tid];
+            cur.xg = st.xg[tid];
+            cur.b = st.b[tid];
+            cur.invK = HASK ? st.invK[tid] : 0.0;
+            cur.bi = st.bi[tid];
+            on = tailRowMath<HASK>(p, cur, two, k, alpha, a0, b0, c0, d0, e0, f0, keepPol, s0, s1, s2, mx);
+        }
+        const unsigned mbits = __ballot_sync(0xffffffffu, on);
+        if (lane == 0 && p.maskOut) p.maskOut[k >> 5] = mbits;
+        nMaybe += __popc(mbits);
+        __syncthreads(); // the stage may be refilled
+    }
+    tailEpilogue(p, s0, s1, s2, mx, nMaybe);
 }
 
 // bit k = x_k can contribute to D x (k_force_vel_act on a plain vector); BIONLY: gamma_b = gamma o biFlag
@@ -1263,7 +1423,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.incCon.reserve((size_t)c.incStride + 4);
     c.incRaw.reserve((size_t)nInc + 4);
     c.incCol.reserve(6 * (size_t)c.incStride + 8);
-    const size_t vcap = (size_t)nc + 1;
+    const size_t vcap = (size_t)nc + 32; // (+ padding: bulk copies read whole 16-row groups)
     c.vX0.reserve(vcap); c.vX1.reserve(vcap); c.vG0.reserve(vcap); c.vG1.reserve(vcap);
     c.vB.reserve(vcap); c.vLbFlag.reserve(vcap); c.vTmp5.reserve(vcap); // vTmp5 = invKdt
     c.rU.reserve(6 * (size_t)n + 6); c.rF.reserve(6 * (size_t)n + 6);
@@ -1444,6 +1604,21 @@ static ReduceArgs reduceArgs(Context &c) { // next mailbox round
     return a;
 }
 
+// ring depth: 4 stages of 26.3 KB (two resident CTAs: 210 KB); with the K^-1 array a stage is 28.3 KB: 3 stages
+template <bool HASK>
+static void launchTailRing(cudaLaunchConfig_t &cfg, const BbTail &t, int nTiles) {
+    constexpr int NST = HASK ? 3 : 4;
+    const size_t smem = NST * sizeof(TailStage<HASK>) + 64;
+    static bool once = false;
+    if (!once) {
+        ALENS_CUDA(cudaFuncSetAttribute((k_bb_tail_ring<HASK, NST>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+        once = true;
+    }
+    cfg.dynamicSmemBytes = smem;
+    ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_bb_tail_ring<HASK, NST>), t, nTiles));
+}
+
 static void launchTail(Context &c, const BbTail &t, int gridTail) {
     profBegin(c, 1);
     cudaLaunchConfig_t cfg = {};
@@ -1455,7 +1630,13 @@ static void launchTail(Context &c, const BbTail &t, int gridTail) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = c.pdlNow ? 1 : 0;
-    if (c.nBilateral > 0) ALENS_CUDA(cudaLaunchKernelEx(&cfg, k_bb_tail<true>, t));
+    if (c.optTailRing && t.nc >= 4 * kTailTile) { // TMA-staged variant: tiles of 256 rows through a shared-memory ring
+        const int nTiles = (int)((t.nc + kTailTile - 1) / kTailTile);
+        cfg.gridDim = dim3((unsigned)std::min(nTiles, c.numSMs * 2));
+        cfg.blockDim = dim3(kTailTile);
+        if (c.nBilateral > 0) launchTailRing<true>(cfg, t, nTiles);
+        else launchTailRing<false>(cfg, t, nTiles);
+    } else if (c.nBilateral > 0) ALENS_CUDA(cudaLaunchKernelEx(&cfg, k_bb_tail<true>, t));
     else ALENS_CUDA(cudaLaunchKernelEx(&cfg, k_bb_tail<false>, t));
     profEnd(c);
     c.launches++;
@@ -1466,8 +1647,8 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     cudaStream_t st = c.stream;
     const long long nc = c.nCon;
     const bool multi = c.comm.active;
-    c.vXG0.reserve((size_t)nc + 1);
-    c.vXG1.reserve((size_t)nc + 1);
+    c.vXG0.reserve((size_t)nc + 32); // (+ padding: the bulk copies of k_bb_tail_ring read whole 16-row groups)
+    c.vXG1.reserve((size_t)nc + 32);
     double2 *XG[2] = {c.vXG0.p, c.vXG1.p};
     c.vMask.reserve((size_t)(nc >> 5) + 2);
     const unsigned *mask = c.optForceMask ? c.vMask.p : nullptr;
@@ -1874,6 +2055,8 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_dtrans));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_init));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_extract));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_bb_tail_ring<true, 3>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_bb_tail_ring<false, 4>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_tail<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_tail<false>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_bb_reduce));
