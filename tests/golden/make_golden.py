@@ -30,6 +30,53 @@ def densemonolayer():
                         geo_gidI=geo["gidI"], geo_gidJ=geo["gidJ"], geo_delta0=geo["delta0"])
 
 
+def mixmotorsliding():
+    """Examples/MixMotorSliding as shipped: 2 rods (gid 0 immovable) and 100 doubly bound motors.  The motors become
+    bilateral constraint blocks exactly as TubuleSystem::setProteinConstraints builds them (SRC/TubuleSystem.cpp:694-745):
+    delta0 = |Q - P| - freeLength, gamma0 = -delta0 kappa, normI = (P - Q)/|P - Q|, posI = P - centerI, posJ = Q - centerJ,
+    kappa = 100 pN/um, freeLength = 0.05 um (Examples/MixMotorSliding/ProteinConfig.yaml)."""
+    base = "/root/reference/Examples/MixMotorSliding/"
+    rods = read_rod_file(base + "TubuleInitial.dat")
+    kappa, free_len = 100.0, 0.05
+    P, Q, bI, bJ = [], [], [], []
+    with open(base + "ProteinInitial.dat") as f:
+        for ln in f:
+            t = ln.split()
+            if not t or t[0] != "P":
+                continue
+            P.append([float(x) for x in t[3:6]])
+            Q.append([float(x) for x in t[6:9]])
+            bI.append(int(t[9]))
+            bJ.append(int(t[10]))
+    P, Q, bI, bJ = np.array(P), np.array(Q), np.array(bI), np.array(bJ)
+    both = (bI >= 0) & (bJ >= 0)  # singly bound motors are not constraints (TubuleSystem.cpp:708-711)
+    P, Q, bI, bJ = P[both], Q[both], bI[both], bJ[both]
+    gid2idx = {int(g): i for i, g in enumerate(rods["gid"])}
+    iI = np.array([gid2idx[g] for g in bI])
+    iJ = np.array([gid2idx[g] for g in bJ])
+    from alens_b200.capi import BLOCK_DTYPE
+
+    blk = np.zeros(len(P), dtype=BLOCK_DTYPE)
+    pq = P - Q
+    dist = np.sqrt((pq**2).sum(axis=1))
+    blk["delta0"] = dist - free_len
+    blk["gamma"] = -blk["delta0"] * kappa
+    blk["gidI"], blk["gidJ"] = bI, bJ
+    blk["globalIndexI"], blk["globalIndexJ"] = iI, iJ
+    blk["oneSide"], blk["bilateral"], blk["kappa"] = 0, 1, kappa
+    blk["normI"] = pq / dist[:, None]
+    blk["normJ"] = -blk["normI"]
+    blk["posI"] = P - rods["pos"][iI]
+    blk["posJ"] = Q - rods["pos"][iJ]
+    blk["labI"], blk["labJ"] = P, Q
+    print("MixMotorSliding: rods", len(rods["gid"]), "bilateral blocks", len(blk))
+    np.savez_compressed(os.path.join(HERE, "mixmotorsliding.npz"), gid=rods["gid"], pos=rods["pos"], quat=rods["quat"],
+                        length=rods["length"], radius=rods["radius"], immovable=rods["immovable"],
+                        lo=np.zeros(3), hi=np.array([20.0, 1.0, 1.0]), pbc=np.zeros(3, dtype=np.int32), colbuf=0.025,
+                        dt=1e-5, res=1e-5, mu=1.0, blocks=blk.view(np.uint8))
+
+
 if __name__ == "__main__":
     po.build(ref=True)
     densemonolayer()
+    mixmotorsliding()
