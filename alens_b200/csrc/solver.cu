@@ -1283,21 +1283,27 @@ k_dot3(long long n, Dot3 p, double *partial, unsigned int *ticket, double *resul
 
 // ------------------------------------------------------------------------------------------------
 // results: uni/bi split (ConstraintSolver.cpp:95-106) + permutation back to the caller's rod order
-__global__ void k_split_out(int n, int nLocal, const int *__restrict__ sUser, const double *__restrict__ F,
+// One thread per (local rod in the caller's order, component): the sorted rows are gathered (48-byte runs, every
+// sector fully used by the six threads of a rod), the four result arrays are written fully coalesced.  Without
+// bilateral rows the bilateral outputs are plain memsets.
+__global__ void k_split_out(int nLocal, const int *__restrict__ userToSorted, const double *__restrict__ F,
                             const double *__restrict__ U, const double *__restrict__ Fb,
                             const double *__restrict__ Ub, double *__restrict__ oFU, double *__restrict__ oVU,
                             double *__restrict__ oFB, double *__restrict__ oVB) {
-    // one thread per (rod, component): coalesced reads in sorted order, 48-byte runs on the permuted side
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 6LL * n) return;
-    const int s = (int)(e / 6), c = (int)(e - 6LL * s);
-    if (sUser[s] >= nLocal) return; // ghost rod
-    const size_t u = 6 * (size_t)sUser[s] + c;
-    const double fb = Fb ? Fb[e] : 0.0, ub = Ub ? Ub[e] : 0.0;
-    oFU[u] = 1.0 * F[e] + (-1.0) * fb;
-    oVU[u] = 1.0 * U[e] + (-1.0) * ub;
-    oFB[u] = fb;
-    oVB[u] = ub;
+    if (e >= 6LL * nLocal) return;
+    const int u = (int)(e / 6), c = (int)(e - 6LL * u);
+    const size_t s = 6 * (size_t)userToSorted[u] + c;
+    if (Fb) {
+        const double fb = Fb[s], ub = Ub[s];
+        oFU[e] = 1.0 * F[s] + (-1.0) * fb;
+        oVU[e] = 1.0 * U[s] + (-1.0) * ub;
+        oFB[e] = fb;
+        oVB[e] = ub;
+    } else {
+        oFU[e] = 1.0 * F[s] + (-1.0) * 0.0;
+        oVU[e] = 1.0 * U[s] + (-1.0) * 0.0;
+    }
 }
 __global__ void k_permute6_to_user(int n, const int *__restrict__ sUser, const double *__restrict__ in,
                                    double *__restrict__ out) {
@@ -2007,10 +2013,16 @@ void solveCore(Context &c, double tol, int maxIte, int choice) {
     }
     if (n > 0) {
         const bool bi = nc > 0 && c.nBilateral > 0;
-        k_split_out<<<gridFor(6LL * n, 256), 256, 0, st>>>(n, c.nLocal, c.sUser.p, c.rF.p, c.rU.p, bi ? c.rFb.p : nullptr,
-                                                           bi ? c.rUb.p : nullptr, c.outFU.p, c.outVU.p, c.outFB.p,
-                                                           c.outVB.p);
-        c.launches++;
+        if (c.nLocal > 0) {
+            if (!bi) {
+                ALENS_CUDA(cudaMemsetAsync(c.outFB.p, 0, 48 * (size_t)c.nLocal, st));
+                ALENS_CUDA(cudaMemsetAsync(c.outVB.p, 0, 48 * (size_t)c.nLocal, st));
+            }
+            k_split_out<<<gridFor(6LL * c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.userToSorted.p, c.rF.p, c.rU.p,
+                                                                      bi ? c.rFb.p : nullptr, bi ? c.rUb.p : nullptr,
+                                                                      c.outFU.p, c.outVU.p, c.outFB.p, c.outVB.p);
+            c.launches++;
+        }
     }
     ALENS_CUDA(cudaEventRecord(c.ev[4], st));
     ALENS_CUDA(cudaGetLastError());
