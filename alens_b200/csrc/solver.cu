@@ -354,6 +354,11 @@ struct HaloPush {
     const int *mir[2];
     double *rem[2];
     int on;
+    // k_force_vel_act releases the neighbours' halo sequence numbers itself: the last warp of the grid to finish
+    // (ticket) stores them (flag[d] = nullptr: no neighbour on that side; ticket = nullptr: a separate kernel signals)
+    unsigned long long *flag[2];
+    unsigned long long seq;
+    unsigned int *ticket;
 };
 
 // Where the force kernel takes x from.  XMODE 0: a plain vector.  XMODE 1: gamma_b = gamma o biFlag
@@ -557,10 +562,9 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
     pdlWait(); // the iterate, the mask and the step size come from the previous kernel
     if (in.pdlTrig) pdlLaunchDependents();
     if (scal && scal->done) return;
-    if (grp >= nGroups) return;
     double alpha = 0.0;
     if (XMODE == 2) alpha = scal->alpha; // plain load, L1 broadcast
-    while (true) {
+    while (grp < nGroups) {
         const int r = grp * 32 + lane;
         const bool act = r < in.nRods;
         const int grpN = grp + gStride;
@@ -705,6 +709,19 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
         grp = grpN;
         b = bN;
         e = eN;
+    }
+    if (hp.on && hp.ticket) { // fused multi-GPU: the mirrored rows are out, the last warp of the grid tells the neighbours
+        __threadfence_system(); // every lane's remote stores are performed before this warp takes its ticket
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned t = atomicAdd(hp.ticket, 1u);
+            if (t == gridDim.x * kActWarps - 1) {
+                *hp.ticket = 0;
+                __threadfence_system();
+                if (hp.flag[0]) stReleaseSys(hp.flag[0], hp.seq);
+                if (hp.flag[1]) stReleaseSys(hp.flag[1], hp.seq);
+            }
+        }
     }
 }
 
@@ -974,9 +991,15 @@ __device__ __forceinline__ void tailEpilogue(const BbTail &p, double s0, double 
             }
             double tot[4] = {0, 0, 0, 0};
             for (int q = 0; q < a.R; q++) {
-                if (!waitSeq(a.seqMine + q, a.seq, a.err)) {
+                if (!waitSeq(a.seqMine + q, a.seq, a.err)) { // a peer never arrived: stop the loop, tell the host
                     p.scal->ticket = 0;
                     p.scal->done = 4;
+                    if (p.prog) {
+                        volatile int *pg = p.prog;
+                        pg[1] = 4;
+                        __threadfence_system();
+                        pg[0] = p.ite + 1;
+                    }
                     return;
                 }
                 const volatile double *m = a.mailMine + 4 * q;
@@ -1690,8 +1713,16 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
                 hp.rem[d] = reinterpret_cast<double *>(m.peerWin[q] + m.offU);
             }
             hp.on = 1;
+            if (c.incLayout == 1) { // the force kernel releases the neighbours' halo flags itself (last warp)
+                for (int d = 0; d < 2; d++) {
+                    const int q = d == 0 ? m.left : m.right;
+                    hp.flag[d] = q < 0 ? nullptr : &reinterpret_cast<CommHeader *>(m.peerWin[q])->haloSeq[1 - d];
+                }
+                hp.seq = seq;
+                hp.ticket = &c.dScal.p->ticketFv;
+            }
             launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p, &hp);
-            commSignalHalo(c, seq);
+            if (c.incLayout != 1) commSignalHalo(c, seq);
             t.waitFlag[0] = m.left >= 0 ? &me->haloSeq[0] : nullptr;
             t.waitFlag[1] = m.right >= 0 ? &me->haloSeq[1] : nullptr;
             t.waitSeq = seq;
@@ -1708,12 +1739,15 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
             c.launches++;
         }
     };
-    const bool poll = !multi && c.optPoll && c.hProg != nullptr;
+    // host flow control through the progress words: single rank, or every rank on its own device with the fused kernels
+    // (all ranks take bit-identical scalar steps, so they stop after the same iteration)
+    const bool poll = (!multi || (fused && c.incLayout == 1)) && c.optPoll && c.hProg != nullptr;
+    const unsigned long long halo0 = c.comm.seqHalo, mail0 = c.comm.seqMail;
     if (poll) {
         c.hProg[0] = 0; c.hProg[1] = 0;
         t.prog = c.hProgDev;
     }
-    c.pdlNow = !multi && c.optPdl && c.incLayout == 1;
+    c.pdlNow = (!multi || fused) && c.optPdl && c.incLayout == 1;
     // iteration 0: g0 = A x0 + b, {x0, g0} written in place
     if (nc > 0) {
         k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, XG[0], c.vMask.p);
@@ -1731,7 +1765,16 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
         const int look = std::max(1, c.optLookahead);
         volatile int *pg = c.hProg;
         while (ite < maxIte) {
-            while (pg[0] < ite + 1 - look && !pg[1]) cpuRelax();
+            long long spins = 0;
+            bool stuck = false;
+            while (pg[0] < ite + 1 - look && !pg[1]) {
+                cpuRelax();
+                if ((++spins & 0xfffff) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) { // the stream ran dry or failed
+                    stuck = pg[0] < ite + 1 - look && !pg[1];
+                    break;
+                }
+            }
+            if (stuck) break; // syncScalars below reports the state (or the CUDA error)
             if (pg[1]) break;
             ite++;
             const int cur = (ite - 1) & 1, nxt = ite & 1;
@@ -1741,6 +1784,11 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
         }
         c.profMute = false;
         syncScalars(c);
+        if (multi) { // launches queued past the last executed iteration were no-ops: every rank continues from the
+                     // sequence numbers of the applies that really ran (the ranks may have queued different numbers)
+            c.comm.seqHalo = halo0 + (unsigned long long)c.hScal->mv;
+            c.comm.seqMail = mail0 + (unsigned long long)c.hScal->mv;
+        }
         // 2 launches x 2 events per sampled iteration; sampled iterations past the last executed one were no-ops
         profFlush(c, c.hScal->ite >= 1 ? 4 * ((c.hScal->ite - 1) / kProfEvery + 1) : 0);
     } else {
@@ -1753,8 +1801,10 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
                 ite++;
                 const int cur = (ite - 1) & 1, nxt = ite & 1;
                 t.ite = ite; t.xgPrev = XG[cur]; t.xgOut = XG[nxt];
+                c.profMute = (ite % kProfEvery) != 1;
                 applyAndTail(XIn{nullptr, XG[cur], 1, mask});
             }
+            c.profMute = false;
             syncScalars(c);
             if (c.hScal->done) c.profUsed = 0; // this batch contains early-exit no-ops: not representative
             else profFlush(c);
