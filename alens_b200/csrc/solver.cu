@@ -564,6 +564,7 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
     if (scal && scal->done) return;
     double alpha = 0.0;
     if (XMODE == 2) alpha = scal->alpha; // plain load, L1 broadcast
+    bool pushed = false; // this lane stored into a neighbour's window
     while (grp < nGroups) {
         const int r = grp * 32 + lane;
         const bool act = r < in.nRods;
@@ -577,6 +578,7 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
         }
         double qx = 0, qy = 0, qz = 0, iPara = 0, iPerp = 0, iRot = 0;
         unsigned ghost = 1;
+        int mirL = -1, mirR = -1;
         const int gb = __shfl_sync(0xffffffffu, b, 0), ge = __shfl_sync(0xffffffffu, e, 31);
         double f[6] = {0, 0, 0, 0, 0, 0};
         for (int base = gb; base == gb || base < ge; base += kActBatch) {
@@ -624,6 +626,10 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
                     iPara = ldStream(mob.invDrag + r); iPerp = ldStream(mob.invDrag + mob.stride + r);
                     iRot = ldStream(mob.invDrag + 2 * mob.stride + r);
                     ghost = mob.ghost[r];
+                    if (hp.on) { // where the neighbours keep this rod as a ghost (-1: not mirrored)
+                        if (hp.mir[0]) mirL = hp.mir[0][r];
+                        if (hp.mir[1]) mirR = hp.mir[1][r];
+                    }
                 }
             }
             if (qn == 0) continue;
@@ -693,16 +699,15 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
                 Fp[1] = make_double2(f[2], f[3]);
                 Fp[2] = make_double2(f[4], f[5]);
             }
-            if (hp.on) {
-#pragma unroll
-                for (int dd = 0; dd < 2; dd++) {
-                    if (!hp.mir[dd]) continue;
-                    const int rr = hp.mir[dd][r];
-                    if (rr >= 0) {
-                        double2 *Rp = reinterpret_cast<double2 *>(hp.rem[dd] + 6 * (size_t)rr);
-                        Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
-                    }
-                }
+            if (mirL >= 0) {
+                double2 *Rp = reinterpret_cast<double2 *>(hp.rem[0] + 6 * (size_t)mirL);
+                Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+                pushed = true;
+            }
+            if (mirR >= 0) {
+                double2 *Rp = reinterpret_cast<double2 *>(hp.rem[1] + 6 * (size_t)mirR);
+                Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+                pushed = true;
             }
         }
         if (!more) break;
@@ -711,7 +716,7 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
         e = eN;
     }
     if (hp.on && hp.ticket) { // fused multi-GPU: the mirrored rows are out, the last warp of the grid tells the neighbours
-        __threadfence_system(); // every lane's remote stores are performed before this warp takes its ticket
+        if (pushed) __threadfence_system(); // a lane's remote stores are performed before its warp takes the ticket
         __syncwarp();
         if (lane == 0) {
             const unsigned t = atomicAdd(hp.ticket, 1u);
