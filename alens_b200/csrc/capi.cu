@@ -408,7 +408,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
     return guarded(ctx, [&](Context &c) {
         const std::string k = name ? name : "";
         if (k == "force_kernel") c.optForceKernel = value == 0 ? 0 : 1;
-        else if (k == "force_minb") c.optForceMinB = value == 4 ? 4 : 5;
+        else if (k == "force_minb") c.optForceMinB = (value == 3 || value == 5) ? (int)value : 4;
         else if (k == "tail_ring") c.optTailRing = value != 0;
         else if (k == "pdl") c.optPdl = (int)std::max(0LL, std::min(2LL, value));
         else if (k == "poll") c.optPoll = value != 0;

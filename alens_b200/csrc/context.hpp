@@ -262,7 +262,7 @@ struct Context {
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 1;                 // 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
-    int optForceMinB = 5;                   // k_force_vel_act: resident CTAs per SM asked of the compiler (5: 96 regs, 6: 80 regs + small spill)
+    int optForceMinB = 4;                   // k_force_vel_act: resident CTAs per SM asked of the compiler (4: 128 registers, no spills: fastest; 5: 96 + spills; 3: 168)
     int optTailRing = 0;                    // k_bb_tail_ring (TMA bulk copies into a shared-memory ring) instead of k_bb_tail
     int optPdl = 1;                         // BBPGD kernels launched with programmatic stream serialization (single rank)
     int optPoll = 1;                        // BBPGD host loop throttled by a progress word in pinned memory instead of stream syncs

@@ -528,7 +528,7 @@ __device__ __forceinline__ double actMultiplier(int update, double2 xg, double x
     return XMODE == 1 ? 1.0 * xv * (bi ? 1.0 : 0.0) : xv;
 }
 
-template <int XMODE, bool WRITE_F, int MINB>
+template <int XMODE, bool WRITE_F, int MINB, bool HALO>
 __global__ void __launch_bounds__(kActWarps * 32, MINB)
 k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__restrict__ F,
                 const SolverScalars *__restrict__ scal, HaloPush hp) {
@@ -626,7 +626,7 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
                     iPara = ldStream(mob.invDrag + r); iPerp = ldStream(mob.invDrag + mob.stride + r);
                     iRot = ldStream(mob.invDrag + 2 * mob.stride + r);
                     ghost = mob.ghost[r];
-                    if (hp.on) { // where the neighbours keep this rod as a ghost (-1: not mirrored)
+                    if (HALO && hp.on) { // where the neighbours keep this rod as a ghost (-1: not mirrored)
                         if (hp.mir[0]) mirL = hp.mir[0][r];
                         if (hp.mir[1]) mirR = hp.mir[1][r];
                     }
@@ -699,12 +699,12 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
                 Fp[1] = make_double2(f[2], f[3]);
                 Fp[2] = make_double2(f[4], f[5]);
             }
-            if (mirL >= 0) {
+            if (HALO && mirL >= 0) {
                 double2 *Rp = reinterpret_cast<double2 *>(hp.rem[0] + 6 * (size_t)mirL);
                 Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
                 pushed = true;
             }
-            if (mirR >= 0) {
+            if (HALO && mirR >= 0) {
                 double2 *Rp = reinterpret_cast<double2 *>(hp.rem[1] + 6 * (size_t)mirR);
                 Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
                 pushed = true;
@@ -715,7 +715,7 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
         b = bN;
         e = eN;
     }
-    if (hp.on && hp.ticket) { // fused multi-GPU: the mirrored rows are out, the last warp of the grid tells the neighbours
+    if (HALO && hp.on && hp.ticket) { // fused multi-GPU: the mirrored rows are out, the last warp of the grid tells the neighbours
         if (pushed) __threadfence_system(); // a lane's remote stores are performed before its warp takes the ticket
         __syncwarp();
         if (lane == 0) {
@@ -1520,13 +1520,13 @@ void profFlush(Context &c, int maxEvents) { // call after a stream synchronisati
 
 // persistent grid: as many CTAs as stay resident (each keeps 16 KB of warp queues: ask for the large shared-memory
 // split), every warp walks its groups with stride gridDim * kActWarps
-template <int XMODE, bool WF, int MINB>
-static void launchForceAct(Context &c, const XIn &xin, double *U, double *F, const SolverScalars *scal,
-                           const HaloPush &hp) {
+template <int XMODE, bool WF, int MINB, bool HALO>
+static void launchForceActT(Context &c, const XIn &xin, double *U, double *F, const SolverScalars *scal,
+                            const HaloPush &hp) {
     static int perSM = 0;
     if (perSM == 0) {
-        cudaFuncSetAttribute((k_force_vel_act<XMODE, WF, MINB>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        ALENS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (k_force_vel_act<XMODE, WF, MINB>),
+        cudaFuncSetAttribute((k_force_vel_act<XMODE, WF, MINB, HALO>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        ALENS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (k_force_vel_act<XMODE, WF, MINB, HALO>),
                                                                  kActWarps * 32, 0));
         perSM = std::max(perSM, 1);
     }
@@ -1542,7 +1542,16 @@ static void launchForceAct(Context &c, const XIn &xin, double *U, double *F, con
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = c.pdlNow ? 1 : 0; // inside the BBPGD loop: overlap with the drain of the tail kernel in front
-    ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_act<XMODE, WF, MINB>), fa, mobIn(c), xin, U, F, scal, hp));
+    ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_act<XMODE, WF, MINB, HALO>), fa, mobIn(c), xin, U, F, scal, hp));
+}
+// persistent grid: as many CTAs as stay resident (each keeps 18 KB of warp queues: ask for the large shared-memory
+// split), every warp walks its groups with stride gridDim * kActWarps.  The halo code (mirror indices, remote stores,
+// ticket) is only compiled into the variant the fused multi-GPU loop launches.
+template <int XMODE, bool WF, int MINB>
+static void launchForceAct(Context &c, const XIn &xin, double *U, double *F, const SolverScalars *scal,
+                           const HaloPush &hp) {
+    if (XMODE == 2 && !WF && hp.on) launchForceActT<XMODE, WF, MINB, (XMODE == 2 && !WF)>(c, xin, U, F, scal, hp);
+    else launchForceActT<XMODE, WF, MINB, false>(c, xin, U, F, scal, hp);
 }
 
 template <int XMODE, bool WF>
@@ -1562,8 +1571,9 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
             c.launches++;
             xm.mask = c.vMask2.p;
         }
-        if (c.optForceMinB == 4) launchForceAct<XMODE, WF, 4>(c, xm, U, F, scal, hp);
-        else launchForceAct<XMODE, WF, 5>(c, xm, U, F, scal, hp);
+        if (c.optForceMinB == 3) launchForceAct<XMODE, WF, 3>(c, xm, U, F, scal, hp);
+        else if (c.optForceMinB == 5) launchForceAct<XMODE, WF, 5>(c, xm, U, F, scal, hp);
+        else launchForceAct<XMODE, WF, 4>(c, xm, U, F, scal, hp);
         profEnd(c);
         c.launches++;
         c.timers.op_launches++;
@@ -2142,14 +2152,21 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 0, true>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 1, true>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_lm<4, 2, false>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 5>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 5>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 5>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 5>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 4>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 4>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 4>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 4>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 5, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 5, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 5, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 5, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 4, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 4, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 4, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 4, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 5, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 4, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, false, 3, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<0, true, 3, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 3, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 3, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 3, true>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit_rm));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<false>));
