@@ -591,24 +591,52 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
                     code[k] = p < lim ? ldStream(in.incCon + p) : -1;
                 }
             }
-            // ---- 1: mask test + compaction
-            unsigned mw[PER];
-            if (useMask) {
+            // ---- 1: mask test + compaction.  The ids arrive slot = 32 k + lane (coalesced loads); they are transposed
+            // through shared memory so that lane l holds the 8 CONSECUTIVE slots 8 l .. 8 l + 7: survivors can then be
+            // compacted in slot order with one warp prefix sum (instead of 8 ballot/popc rounds), and the queue range of
+            // a rod follows from two shuffles (instead of a binary search).
+            int *sc = sCode[w];
 #pragma unroll
-                for (int k = 0; k < PER; k++) mw[k] = code[k] >= 0 ? __ldg(xin.mask + (code[k] >> 7)) : 0u;
+            for (int k = 0; k < PER; k++) sc[32 * k + lane] = code[k];
+            __syncwarp();
+            int c8[PER];
+            {
+                const int4 ca = *reinterpret_cast<const int4 *>(sc + 8 * lane);
+                const int4 cb = *reinterpret_cast<const int4 *>(sc + 8 * lane + 4);
+                c8[0] = ca.x; c8[1] = ca.y; c8[2] = ca.z; c8[3] = ca.w;
+                c8[4] = cb.x; c8[5] = cb.y; c8[6] = cb.z; c8[7] = cb.w;
             }
-            int qn = 0;
+            __syncwarp(); // everybody has its ids: the queue may overwrite the staging area
+            unsigned live = 0; // bit k: slot 8 lane + k survives
+            if (useMask) {
+                unsigned mw[PER];
 #pragma unroll
-            for (int k = 0; k < PER; k++) {
-                bool on = code[k] >= 0;
-                if (useMask) on = on && ((mw[k] >> ((code[k] >> 2) & 31)) & 1u);
-                const unsigned m = __ballot_sync(0xffffffffu, on);
-                if (on) {
-                    const int pos = qn + __popc(m & lt);
-                    sSlot[w][pos] = (unsigned short)(32 * k + lane);
-                    sCode[w][pos] = code[k];
+                for (int k = 0; k < PER; k++) mw[k] = c8[k] >= 0 ? __ldg(xin.mask + (c8[k] >> 7)) : 0u;
+#pragma unroll
+                for (int k = 0; k < PER; k++) live |= ((mw[k] >> ((c8[k] >> 2) & 31)) & 1u) << k;
+            } else {
+#pragma unroll
+                for (int k = 0; k < PER; k++) live |= (c8[k] >= 0 ? 1u : 0u) << k;
+            }
+            const int cnt = __popc(live);
+            int incl = cnt; // inclusive prefix sum of the lanes' survivor counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int excl = incl - cnt;
+            const int qn = __shfl_sync(0xffffffffu, incl, 31);
+            {
+                int pos = excl;
+#pragma unroll
+                for (int k = 0; k < PER; k++) {
+                    if ((live >> k) & 1u) {
+                        sSlot[w][pos] = (unsigned short)(8 * lane + k);
+                        sc[pos] = c8[k];
+                        pos++;
+                    }
                 }
-                qn += __popc(m);
             }
             __syncwarp();
             if (lastBatch) { // the id registers are free: request the next group's first ids and this group's rod data
@@ -633,15 +661,16 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
                 }
             }
             if (qn == 0) continue;
-            // ---- 2: entries [lo, hi) of the queue belong to my rod
-            const int bo = b - base;
-            int lo = 0;
-            for (int step = 1 << (31 - __clz(qn)); step >= 1; step >>= 1) {
-                const int t = lo + step;
-                if (t <= qn && (int)sSlot[w][t - 1] < bo) lo = t;
+            // ---- 2: entries [lo, hi) of the queue belong to my rod: number of survivors in front of my first / last slot
+            int lo, hi;
+            {
+                const int bo = min(max(b - base, 0), kActBatch), eo = min(max(e - base, 0), kActBatch);
+                const int lb = min(bo >> 3, 31), le = min(eo >> 3, 31);
+                const int xb = __shfl_sync(0xffffffffu, excl, lb), xe = __shfl_sync(0xffffffffu, excl, le);
+                const unsigned mb = __shfl_sync(0xffffffffu, live, lb), me = __shfl_sync(0xffffffffu, live, le);
+                lo = bo >= kActBatch ? qn : xb + __popc(mb & ((1u << (bo & 7)) - 1u));
+                hi = eo >= kActBatch ? qn : xe + __popc(me & ((1u << (eo & 7)) - 1u));
             }
-            int hi = __shfl_down_sync(0xffffffffu, lo, 1);
-            if (lane == 31) hi = qn;
             // ---- 3: multipliers, column blocks, products; two queue chunks in flight
             for (int c0 = 0; c0 < qn; c0 += 64) {
                 const int i0 = c0 + lane, i1 = c0 + 32 + lane;
