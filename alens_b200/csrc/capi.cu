@@ -407,7 +407,10 @@ int alens_reset_timers(alens_ctx *ctx) {
 int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
     return guarded(ctx, [&](Context &c) {
         const std::string k = name ? name : "";
-        if (k == "force_kernel") c.optForceKernel = value == 0 ? 0 : 1;
+        if (k == "force_kernel") { // 0 dense level-major, 1 k_force_vel_act, 2 k_slot_x + k_rod_sum (both on the rod-major layout)
+            c.optForceKernel = value == 0 ? 0 : 1;
+            c.optForceSplit = value == 2;
+        }
         else if (k == "force_minb") c.optForceMinB = (value == 3 || value == 5) ? (int)value : 4;
         else if (k == "tail_ring") c.optTailRing = value != 0;
         else if (k == "pdl") c.optPdl = (int)std::max(0LL, std::min(2LL, value));

@@ -262,6 +262,9 @@ struct Context {
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 1;                 // 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
+    int optForceSplit = 0;                  // force_kernel = 2: k_slot_x + k_rod_sum instead of k_force_vel_act
+    DevBuf<double> slotX;                   // multiplier per incidence slot (k_slot_x -> k_rod_sum)
+    DevBuf<unsigned> slotLive;              // bit per incidence slot: multiplier non-zero
     int optForceMinB = 4;                   // k_force_vel_act: resident CTAs per SM asked of the compiler (4: 128 registers, no spills: fastest; 5: 96 + spills; 3: 168)
     int optTailRing = 0;                    // k_bb_tail_ring (TMA bulk copies into a shared-memory ring) instead of k_bb_tail
     int optPdl = 1;                         // BBPGD kernels launched with programmatic stream serialization (single rank)

@@ -759,6 +759,138 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same f = D x over live slots as two light kernels (force_kernel = 2).  k_force_vel_act keeps one 32-rod group per
+// warp in ~128 registers and its time is the serial latency of a warp's groups (ids -> mask -> {x,g} + columns -> sums,
+// measured ~10 700 cycles per group at 16 resident warps per SM).  Split by data dependence instead:
+//   k_slot_x      thread per incidence SLOT: id (coalesced), mask bit, {x_prev, g_prev} gather and projected step only
+//                 for live rows; writes the multiplier of a slot whose x != 0 into a slot-indexed array and one bit per
+//                 slot (ballot) into a slot-ordered bitmap.  ~40 registers: 48 warps per SM hide the two gathers.
+//   k_rod_sum     thread per ROD: the bits of its (contiguous) slot range, and for every set bit the multiplier and the
+//                 48-byte column record; sums in ascending slot order (the order of every other force kernel), u = M f.
+// Identical arithmetic (product rounded, then added): bit-identical results.
+struct SlotX {
+    const int *incCon;
+    long long nInc;
+    double *slotX;        // [nInc] multiplier of a slot (only slots whose bit is set are written)
+    unsigned *slotLive;   // [nInc / 32 + 1] bit p = slot p has a non-zero multiplier
+    int keepXG;
+};
+
+template <int XMODE>
+__global__ void __launch_bounds__(256) k_slot_x(SlotX in, XIn xin, const SolverScalars *__restrict__ scal) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int code = p < in.nInc ? ldStream(in.incCon + p) : -1; // constant during a solve: before the wait
+    pdlWait();
+    if (scal && scal->done) return;
+    bool live = code >= 0;
+    if (live && xin.mask) live = (__ldg(xin.mask + (code >> 7)) >> ((code >> 2) & 31)) & 1u;
+    double x = 0.0;
+    if (live) {
+        const bool bi = (code & 2) != 0;
+        if (XMODE == 2) {
+            const double2 xg = in.keepXG ? ldGather2Keep(xin.xg + (code >> 2), policyEvictLast()) : ldGather2(xin.xg + (code >> 2));
+            x = xin.update ? bbStep(xg.x, xg.y, scal->alpha, bi) : xg.x;
+        } else {
+            const double xv = __ldg(xin.x + (code >> 2));
+            x = XMODE == 1 ? 1.0 * xv * (bi ? 1.0 : 0.0) : xv;
+        }
+    }
+    const bool on = live && x != 0.0;
+    if (on) in.slotX[p] = x;
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0 && p < in.nInc + 32) in.slotLive[p >> 5] = m;
+}
+
+struct RodSum {
+    const int *incStart;
+    const double *incCol6, *slotX;
+    const unsigned *slotLive;
+    int nRods;
+};
+
+template <bool WRITE_F, bool HALO>
+__global__ void __launch_bounds__(128) k_rod_sum(RodSum in, MobIn mob, double *__restrict__ U, double *__restrict__ F,
+                                                 const SolverScalars *__restrict__ scal, HaloPush hp) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = r < in.nRods;
+    int b = 0, e = 0;
+    double qx = 0, qy = 0, qz = 0, iPara = 0, iPerp = 0, iRot = 0;
+    unsigned ghost = 1;
+    int mirL = -1, mirR = -1;
+    if (act) { // incidence structure and rod data: constant during a solve, requested before the wait
+        b = __ldg(in.incStart + r);
+        e = __ldg(in.incStart + r + 1);
+        qx = ldStream(mob.dx + r); qy = ldStream(mob.dy + r); qz = ldStream(mob.dz + r);
+        iPara = ldStream(mob.invDrag + r); iPerp = ldStream(mob.invDrag + mob.stride + r);
+        iRot = ldStream(mob.invDrag + 2 * mob.stride + r);
+        ghost = mob.ghost[r];
+        if (HALO && hp.on) {
+            if (hp.mir[0]) mirL = hp.mir[0][r];
+            if (hp.mir[1]) mirR = hp.mir[1][r];
+        }
+    }
+    pdlWait();
+    if (scal && scal->done) return;
+    double f[6] = {0, 0, 0, 0, 0, 0};
+    bool pushed = false;
+    if (act && e > b) {
+        for (int wd = b >> 5; wd <= (e - 1) >> 5; wd++) {
+            unsigned bits = __ldg(in.slotLive + wd);
+            const int lo = wd << 5;
+            if (b > lo) bits &= ~((1u << (b - lo)) - 1u);
+            if (e < lo + 32) bits &= (1u << (e - lo)) - 1u;
+            while (bits) { // ascending slot order
+                const int p = lo + __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const double x = __ldg(in.slotX + p);
+                const double2 *cp = reinterpret_cast<const double2 *>(in.incCol6 + 6 * (size_t)p);
+                const double2 c01 = ldStream2(cp), c23 = ldStream2(cp + 1), c45 = ldStream2(cp + 2);
+                f[0] += c01.x * x; f[1] += c01.y * x; f[2] += c23.x * x;
+                f[3] += c23.y * x; f[4] += c45.x * x; f[5] += c45.y * x;
+            }
+        }
+    }
+    if (act && !ghost) {
+        const double qf = qx * f[0] + qy * f[1] + qz * f[2];
+        const double px = qf * qx, py = qf * qy, pz = qf * qz;
+        const double2 u0 = make_double2(iPara * px + iPerp * (f[0] - px), iPara * py + iPerp * (f[1] - py));
+        const double2 u1 = make_double2(iPara * pz + iPerp * (f[2] - pz), iRot * f[3]);
+        const double2 u2 = make_double2(iRot * f[4], iRot * f[5]);
+        double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
+        Up[0] = u0; Up[1] = u1; Up[2] = u2;
+        if (WRITE_F) {
+            double2 *Fp = reinterpret_cast<double2 *>(F + 6 * (size_t)r);
+            Fp[0] = make_double2(f[0], f[1]);
+            Fp[1] = make_double2(f[2], f[3]);
+            Fp[2] = make_double2(f[4], f[5]);
+        }
+        if (HALO && mirL >= 0) {
+            double2 *Rp = reinterpret_cast<double2 *>(hp.rem[0] + 6 * (size_t)mirL);
+            Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+            pushed = true;
+        }
+        if (HALO && mirR >= 0) {
+            double2 *Rp = reinterpret_cast<double2 *>(hp.rem[1] + 6 * (size_t)mirR);
+            Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+            pushed = true;
+        }
+    }
+    if (HALO && hp.on && hp.ticket) { // fused multi-GPU: the last CTA of the grid releases the neighbours' halo flags
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(hp.ticket, 1u);
+            if (t == gridDim.x - 1) {
+                *hp.ticket = 0;
+                __threadfence_system();
+                if (hp.flag[0]) stReleaseSys(hp.flag[0], hp.seq);
+                if (hp.flag[1]) stReleaseSys(hp.flag[1], hp.seq);
+            }
+        }
+    }
+}
+
 // row k of D^T times u
 __device__ __forceinline__ double dtransRow(const ConGeom &g, size_t k, const double *__restrict__ U) {
     const double gx = g.n[k], gy = g.n[k + g.stride], gz = g.n[k + 2 * g.stride];
@@ -1583,6 +1715,35 @@ static void launchForceAct(Context &c, const XIn &xin, double *U, double *F, con
     else launchForceActT<XMODE, WF, MINB, false>(c, xin, U, F, scal, hp);
 }
 
+// force_kernel = 2: k_slot_x (thread per slot) + k_rod_sum (thread per rod), chained with programmatic dependent launch
+template <int XMODE, bool WF>
+static void launchForceSplit(Context &c, const XIn &xin, double *U, double *F, const SolverScalars *scal,
+                             const HaloPush &hp) {
+    const int n = c.nRods;
+    const long long nInc = c.nInc;
+    c.slotX.reserve((size_t)nInc + 64);
+    c.slotLive.reserve((size_t)(nInc >> 5) + 4);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = c.stream;
+    cfg.attrs = at;
+    // one warp more than needed: the bitmap word behind the last slot is written too (k_rod_sum may read it)
+    cfg.gridDim = dim3((unsigned)std::max(1, gridFor(nInc + 32, 256)));
+    cfg.blockDim = dim3(256);
+    cfg.numAttrs = c.pdlNow ? 1 : 0;
+    const SlotX sx{c.incCon.p, nInc, c.slotX.p, c.slotLive.p, c.optKeepXG};
+    ALENS_CUDA(cudaLaunchKernelEx(&cfg, k_slot_x<XMODE>, sx, xin, scal));
+    const RodSum rs{c.incStart.p, c.incCol.p, c.slotX.p, c.slotLive.p, n};
+    cfg.gridDim = dim3((unsigned)std::max(1, gridFor(n, 128)));
+    cfg.blockDim = dim3(128);
+    cfg.numAttrs = c.optPdl ? 1 : 0; // its predecessor is always k_slot_x
+    if (XMODE == 2 && !WF && hp.on)
+        ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_rod_sum<WF, (XMODE == 2 && !WF)>), rs, mobIn(c), U, F, scal, hp));
+    else ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_rod_sum<WF, false>), rs, mobIn(c), U, F, scal, hp));
+}
+
 template <int XMODE, bool WF>
 static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, const SolverScalars *scal,
                            const HaloPush *push = nullptr) {
@@ -1590,7 +1751,7 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
     const HaloPush hp = push ? *push : HaloPush{};
     if (n == 0 && !push) return;
     profBegin(c, 0);
-    if (c.incLayout == 1) { // rod-major slots: active-set kernel
+    if (c.incLayout == 1) { // rod-major slots: active-set kernels
         XIn xm = xin;
         if (XMODE != 2 && c.optForceMask && c.nCon > 0) { // plain vector: one cheap pass marks its non-zero rows
             c.vMask2.reserve((size_t)(c.nCon >> 5) + 2);
@@ -1599,6 +1760,13 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
             else k_mask_from_x<false><<<g, kVecBlock, 0, c.stream>>>(c.nCon, xin.x, c.cBi.p, c.vMask2.p);
             c.launches++;
             xm.mask = c.vMask2.p;
+        }
+        if (c.optForceSplit) {
+            launchForceSplit<XMODE, WF>(c, xm, U, F, scal, hp);
+            profEnd(c);
+            c.launches += 2;
+            c.timers.op_launches += 2;
+            return;
         }
         if (c.optForceMinB == 3) launchForceAct<XMODE, WF, 3>(c, xm, U, F, scal, hp);
         else if (c.optForceMinB == 5) launchForceAct<XMODE, WF, 5>(c, xm, U, F, scal, hp);
@@ -2196,6 +2364,12 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<1, true, 3, false>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 3, false>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_act<2, false, 3, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_x<0>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_x<1>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_x<2>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_rod_sum<false, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_rod_sum<true, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_rod_sum<false, true>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit_rm));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<false>));

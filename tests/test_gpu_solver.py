@@ -161,24 +161,26 @@ def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
     x[rng.uniform(size=nc) < zero_frac] = 0.0
     x[::7] *= -1.0  # negative multipliers and -0.0 occur in plain operator applies
     res = {}
-    for kern in (1, 0):
+    for kern in (1, 2, 0):  # 1 k_force_vel_act, 2 k_slot_x + k_rod_sum, 0 dense level-major
         ctx.set_option("force_kernel", kern)
         ctx.setup_constraints(None, DT)
         res[kern] = ctx.operator_apply(x, want_force_vel=True)
-    for a, b in zip(res[0], res[1]):
-        assert np.array_equal(a, b)
+    for kern in (1, 2):
+        for a, b in zip(res[0], res[kern]):
+            assert np.array_equal(a, b)
     yo, fo, vo = oracle.operator_apply(blocks, orods, rods["immovable"], MU, DT, x)
     for a, b in zip(res[1], (yo, fo, vo)):
         assert relerr(a, b) < 1e-12 or np.abs(b).max() == 0
     # the BBPGD loop (x recomputed on the fly from {x_prev, g_prev}) gives the same iterates with both kernels
     vnc = thermal_velocity(rods, MU, DT, seed=9)
     gam = {}
-    for kern in (1, 0):
+    for kern in (1, 2, 0):
         ctx.set_option("force_kernel", kern)
         rep = ctx.solve_constraints(vnc, DT, 1e-30, 15, 0)
         assert rep.iterations == 15
         gam[kern] = (ctx.get_gamma(), ctx.get_force_velocity()["velU"])
-    assert np.array_equal(gam[0][0], gam[1][0]) and np.array_equal(gam[0][1], gam[1][1])
+    for kern in (1, 2):
+        assert np.array_equal(gam[0][0], gam[kern][0]) and np.array_equal(gam[0][1], gam[kern][1])
     ctx.set_option("force_kernel", 1)
 
 
