@@ -411,6 +411,9 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
             c.optForceKernel = value == 0 ? 0 : 1;
             c.optForceSplit = value == 2;
         }
+        else if (k == "find_minb") c.optFindMinB = (value == 5 || value == 3) ? (int)value : 4;
+        else if (k == "find_split") c.optFindSplit = value != 0;
+        else if (k == "find_split_minb") c.optFindSplitMinB = value == 6 ? 6 : 8;
         else if (k == "force_minb") c.optForceMinB = (value == 3 || value == 5) ? (int)value : 4;
         else if (k == "tail_ring") c.optTailRing = value != 0;
         else if (k == "pdl") c.optPdl = (int)std::max(0LL, std::min(2LL, value));

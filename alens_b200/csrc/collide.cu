@@ -360,7 +360,25 @@ __device__ __forceinline__ int narrowBatch(const PairIn &in, const Box &box, dou
 // (target tile, stencil row, source tile, target, source).
 static constexpr int kJTile = 64; // source rods staged per warp
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
+// NARROW = false: the kernel stops after stage 2 and stages its queued candidates (i, j, cell, seq | image) instead of
+// running the exact query: without the fp64 closest-point code it needs a third of the registers, and stages 1-2 --
+// dependent fp32 arithmetic, bound by how many warps the scheduler can choose from -- run at 2.5x the occupancy.  The
+// exact query then runs one candidate per thread (k_cand_narrow), see collectPairs.
+__device__ __forceinline__ int stageCandidates(int cnt, const int *qi, const int *qj, const int *qs, int lane, int cell,
+                                               int seqBase, int4 *__restrict__ candList, unsigned long long cap,
+                                               unsigned long long *__restrict__ counters) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&counters[2], (unsigned long long)cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < cnt) {
+        const unsigned long long p = base + lane;
+        if (p < cap) candList[p] = make_int4(qi[lane], qj[lane], cell, ((seqBase + lane) << 5) | qs[lane]);
+    }
+    return cnt;
+}
+
+template <int MINB, bool NARROW>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ cellHits, int4 *__restrict__ hitList,
               unsigned long long hitCap, unsigned long long *__restrict__ counters) {
     __shared__ float4 tA[kWarpsPerCta][kITile]; // target: x, y, z (relative), A = h + rho + colBuf + slack
@@ -563,8 +581,10 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                                 nCand += __popc(msk);
                                 __syncwarp();
                                 if (qn >= 32) { // ---- stage 3: exact closest-point query on 32 candidates
-                                    nHits += narrowBatch(in, box, colBuf, 32, qi, qj, qs, lane, cell, nHits, hitList, hitCap,
-                                                         counters);
+                                    if (NARROW)
+                                        nHits += narrowBatch(in, box, colBuf, 32, qi, qj, qs, lane, cell, nHits, hitList,
+                                                             hitCap, counters);
+                                    else nHits += stageCandidates(32, qi, qj, qs, lane, cell, nHits, hitList, hitCap, counters);
                                     __syncwarp();
                                     const int rem = qn - 32; // move the tail to the front
                                     int ti = 0, tj = 0, ts = 0;
@@ -582,10 +602,14 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
             }
         }
     }
-    if (qn > 0) nHits += narrowBatch(in, box, colBuf, qn, qi, qj, qs, lane, cell, nHits, hitList, hitCap, counters);
+    if (qn > 0) {
+        if (NARROW) nHits += narrowBatch(in, box, colBuf, qn, qi, qj, qs, lane, cell, nHits, hitList, hitCap, counters);
+        else nHits += stageCandidates(qn, qi, qj, qs, lane, cell, nHits, hitList, hitCap, counters);
+    }
     if (lane == 0) {
-        cellHits[cell] = nHits;
+        cellHits[cell] = nHits; // NARROW: contacts of this cell; else: its candidates
         atomicAdd(&counters[0], nCand);
+        if (!NARROW) atomicMax(&counters[3], (unsigned long long)nHits);
     }
 }
 
@@ -623,6 +647,97 @@ k_pairs_emit(long long nHits, const int4 *__restrict__ hitList, const int *__res
     out.pJ[k] = ct.posJ.x; out.pJ[k + S] = ct.posJ.y; out.pJ[k + 2 * S] = ct.posJ.z;
     out.labI[k] = ct.labI.x; out.labI[k + S] = ct.labI.y; out.labI[k + 2 * S] = ct.labI.z;
     out.labJ[k] = ct.labJ.x; out.labJ[k + S] = ct.labJ.y; out.labJ[k + 2 * S] = ct.labJ.z;
+}
+
+// canonical roles of a staged pair (reference: gid filter SylinderNear.hpp:210,225 + FDPS image rule
+// FDPS/tree_for_force_utils.hpp:256-262): I = lower gid at its own position, J = higher gid at pos + k*boxLen
+__device__ __forceinline__ void canonicalPair(const PairIn &in, int &si, int &sj, int &code) {
+    if (in.sGid[si] > in.sGid[sj]) { // swap roles; relative image flips sign
+        int kx, ky, kz;
+        imageOf(code, kx, ky, kz);
+        const int t = si; si = sj; sj = t;
+        code = (1 - kx) + 3 * (1 - ky) + 9 * (1 - kz);
+    }
+}
+
+// Exact narrow phase, one staged candidate per thread (grid-stride; the count is read on the device).  A contact sets
+// bit `seq` of its cell's bitmap: the order of a cell's contacts is the order of its candidates, as in k_pairs_find.
+__global__ void __launch_bounds__(128)
+k_cand_narrow(const unsigned long long *__restrict__ counters, const int4 *__restrict__ cand, unsigned long long cap,
+              PairIn in, Box box, double colBuf, unsigned *__restrict__ bits, int W) {
+    const unsigned long long n = min(counters[2], cap);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const int4 rec = cand[t];
+        int si = rec.x, sj = rec.y, code = rec.w & 31;
+        const int seq = rec.w >> 5;
+        canonicalPair(in, si, sj, code);
+        int kx, ky, kz;
+        imageOf(code, kx, ky, kz);
+        RodGeom a = loadRod(in, si), b = loadRod(in, sj);
+        b.c = v3(b.c.x + kx * box.len[0], b.c.y + ky * box.len[1], b.c.z + kz * box.len[2]);
+        Contact ct;
+        if (pairContact(a, b, colBuf, ct) && seq < 32 * W) atomicOr(&bits[(size_t)rec.z * W + (seq >> 5)], 1u << (seq & 31));
+    }
+}
+
+// per cell: contacts = set bits; the bitmap words get their exclusive prefix counts (rank of a contact = prefix + popc)
+__global__ void k_cell_hit_count(int ncell, const int *__restrict__ cellCand, const unsigned *__restrict__ bits, int W,
+                                 int *__restrict__ prefix, int *__restrict__ cellHits) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= ncell) return;
+    const int nw = min(W, (cellCand[cell] + 31) >> 5);
+    int run = 0;
+    for (int w = 0; w < nw; w++) {
+        prefix[(size_t)cell * W + w] = run;
+        run += __popc(bits[(size_t)cell * W + w]);
+    }
+    cellHits[cell] = run;
+}
+
+// emission for the split search: every staged candidate looks up its bit; a contact recomputes its geometry (hits only)
+// and writes the constraint at cellHitStart[cell] + rank
+__global__ void __launch_bounds__(128, 5)
+k_pairs_emit2(unsigned long long n, const int4 *__restrict__ cand, const unsigned *__restrict__ bits,
+              const int *__restrict__ prefix, int W, const int *__restrict__ cellHitStart, PairIn in, PairOut out, Box box,
+              double colBuf) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    {
+        const int4 rec = cand[t];
+        const int seq = rec.w >> 5;
+        if (seq >= 32 * W) return;
+        const size_t wi = (size_t)rec.z * W + (seq >> 5);
+        const unsigned word = bits[wi];
+        if (!((word >> (seq & 31)) & 1u)) return;
+        const size_t k = (size_t)cellHitStart[rec.z] + (size_t)(prefix[wi] + __popc(word & ((1u << (seq & 31)) - 1u)));
+        int si = rec.x, sj = rec.y, code = rec.w & 31;
+        canonicalPair(in, si, sj, code);
+        int kx, ky, kz;
+        imageOf(code, kx, ky, kz);
+        RodGeom a = loadRod(in, si), b = loadRod(in, sj);
+        b.c = v3(b.c.x + kx * box.len[0], b.c.y + ky * box.len[1], b.c.z + kz * box.len[2]);
+        Contact ct;
+        pairContact(a, b, colBuf, ct); // same code, same inputs as in k_cand_narrow: a hit
+        const size_t S = out.stride;
+        out.idxI[k] = si;
+        out.idxJ[k] = sj;
+        out.gidI[k] = in.sGid[si];
+        out.gidJ[k] = in.sGid[sj];
+        out.shift[k] = (signed char)code;
+        out.bi[k] = 0;
+        out.oneSide[k] = 0;
+        out.own[k] = in.sGhost[si] ? 0 : 1; // the owner of rod I counts the row in global reductions
+        out.delta0[k] = ct.sep;
+        out.gamma0[k] = ct.sep < 0 ? -ct.sep : 0;
+        out.invKappa[k] = 0;
+        out.kappa[k] = 0;
+        out.n[k] = ct.normI.x; out.n[k + S] = ct.normI.y; out.n[k + 2 * S] = ct.normI.z;
+        out.pI[k] = ct.posI.x; out.pI[k + S] = ct.posI.y; out.pI[k + 2 * S] = ct.posI.z;
+        out.pJ[k] = ct.posJ.x; out.pJ[k + S] = ct.posJ.y; out.pJ[k + 2 * S] = ct.posJ.z;
+        out.labI[k] = ct.labI.x; out.labI[k + S] = ct.labI.y; out.labI[k + 2 * S] = ct.labI.z;
+        out.labJ[k] = ct.labJ.x; out.labJ[k + S] = ct.labJ.y; out.labJ[k + 2 * S] = ct.labJ.z;
+    }
 }
 
 // exclusive scan of n ints into out[0..n] (out[n] = total)
@@ -858,10 +973,79 @@ void collectPairs(Context &c) {
     c.hitList.reserve(4 * (size_t)std::max(c.nRods, 256));
     const int ctas = gridFor(g.ncell, kWarpsPerCta);
     long long total = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
+    PairOut out{}; // filled once the constraint arrays have their size
+    auto pairOut = [&]() {
+        return PairOut{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cOwn.p, c.cDelta0.p,
+                       c.cGamma0.p, c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
+    };
+    // ---- split search (default): stages 1-2 at high occupancy -> candidates; exact query and ordered emission in dense
+    // one-candidate-per-thread kernels.  Contacts keep the order of their candidates inside a cell (a bitmap of W words
+    // per cell carries the hit flags), so the constraint list is the one the single-kernel search produces, row for row.
+    bool done = false;
+    if (c.optFindSplit) {
+        int W = std::max(c.candWords, 4);
+        const size_t bitmapBytes = (size_t)g.ncell * W * 8;
+        if (bitmapBytes <= ((size_t)1 << 30)) {
+            c.candBits.reserve((size_t)g.ncell * W + 4);
+            c.candPrefix.reserve((size_t)g.ncell * W + 4);
+            c.hitList.reserve(std::max<size_t>(8 * (size_t)std::max(c.nRods, 256), (size_t)(1.3 * c.lastCand) + 1024));
+            ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 4 * sizeof(unsigned long long), st));
+            ALENS_CUDA(cudaMemsetAsync(c.candBits.p, 0, sizeof(unsigned) * (size_t)g.ncell * W, st));
+            if (c.optFindSplitMinB == 6)
+                k_pairs_find<6, false><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p,
+                                                                           c.hitList.p, (unsigned long long)c.hitList.cap,
+                                                                           c.dCounters.p);
+            else
+                k_pairs_find<8, false><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p,
+                                                                           c.hitList.p, (unsigned long long)c.hitList.cap,
+                                                                           c.dCounters.p);
+            // grids of the dense kernels: sized from the last step's candidate count (grid-stride: any count works)
+            const long long guess = std::max<long long>(c.lastCand + c.lastCand / 4, 1 << 16);
+            const int gridDense = (int)std::min<long long>(gridFor(guess, 128), (long long)c.numSMs * 64);
+            k_cand_narrow<<<gridDense, 128, 0, st>>>(c.dCounters.p, c.hitList.p, (unsigned long long)c.hitList.cap, pairIn(c),
+                                                     c.box, c.colBuf, c.candBits.p, W);
+            c.cellCand.reserve(g.ncell + 1);
+            ALENS_CUDA(cudaMemcpyAsync(c.cellCand.p, c.cellHits.p, sizeof(int) * g.ncell, cudaMemcpyDeviceToDevice, st));
+            k_cell_hit_count<<<gridFor(g.ncell, 128), 128, 0, st>>>(g.ncell, c.cellCand.p, c.candBits.p, W, c.candPrefix.p,
+                                                                    c.cellHits.p);
+            c.launches += 3;
+            unsigned long long cnt[4];
+            ALENS_CUDA(cudaMemcpyAsync(cnt, c.dCounters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+            launchScanInt(c, c.cellHits.p, c.cellHitStart.p, g.ncell);
+            int tot = 0;
+            ALENS_CUDA(cudaMemcpyAsync(&tot, c.cellHitStart.p + g.ncell, sizeof(int), cudaMemcpyDeviceToHost, st));
+            ALENS_CUDA(cudaStreamSynchronize(st));
+            c.statCand = (long long)cnt[0];
+            c.lastCand = (long long)cnt[2];
+            // next step's bitmap width follows the fullest cell; this step is valid only if nothing overflowed
+            const long long maxCell = (long long)cnt[3];
+            c.candWords = (int)std::min<long long>(4096, std::max<long long>(4, (maxCell + maxCell / 2 + 63) / 32));
+            if (cnt[2] <= (unsigned long long)c.hitList.cap && maxCell <= 32LL * W) {
+                total = tot;
+                if (total > 0x7fffffffLL)
+                    throw ArgError{ALENS_ERR_UNSUPPORTED, "collect: more than 2^31 constraints on one GPU"};
+                reserveConstraints(c, (size_t)total, false);
+                if (total > 0) {
+                    k_pairs_emit2<<<gridFor((long long)cnt[2], 128), 128, 0, st>>>(cnt[2], c.hitList.p, c.candBits.p,
+                                                                                   c.candPrefix.p, W, c.cellHitStart.p,
+                                                                                   pairIn(c), pairOut(), c.box, c.colBuf);
+                    c.launches++;
+                }
+                done = true;
+            } // else: a cell or the list overflowed -- the single-kernel search below redoes this step
+        }
+    }
+    for (int attempt = 0; attempt < 2 && !done; attempt++) {
         ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 4 * sizeof(unsigned long long), st));
-        k_pairs_find<<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p, c.hitList.p,
-                                                         (unsigned long long)c.hitList.cap, c.dCounters.p);
+        if (c.optFindMinB == 5)
+            k_pairs_find<5, true><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p, c.hitList.p,
+                                                                      (unsigned long long)c.hitList.cap, c.dCounters.p);
+        else if (c.optFindMinB == 3)
+            k_pairs_find<3, true><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p, c.hitList.p,
+                                                                      (unsigned long long)c.hitList.cap, c.dCounters.p);
+        else
+            k_pairs_find<4, true><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p, c.hitList.p,
+                                                                      (unsigned long long)c.hitList.cap, c.dCounters.p);
         c.launches++;
         unsigned long long cnt[2];
         ALENS_CUDA(cudaMemcpyAsync(cnt, c.dCounters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
@@ -874,14 +1058,15 @@ void collectPairs(Context &c) {
         c.hitList.reserve((size_t)total + (size_t)total / 8); // staged records were dropped: run the search again
     }
     if (total > 0x7fffffffLL) throw ArgError{ALENS_ERR_UNSUPPORTED, "collect: more than 2^31 constraints on one GPU"};
-    reserveConstraints(c, (size_t)total, false);
-    if (total > 0) {
-        PairOut out{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cOwn.p, c.cDelta0.p,
-                    c.cGamma0.p, c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
-        k_pairs_emit<<<gridFor(total, 128), 128, 0, st>>>(total, c.hitList.p, c.cellHitStart.p, pairIn(c), out, c.box,
-                                                          c.colBuf);
-        c.launches++;
+    if (!done) {
+        reserveConstraints(c, (size_t)total, false);
+        if (total > 0) {
+            k_pairs_emit<<<gridFor(total, 128), 128, 0, st>>>(total, c.hitList.p, c.cellHitStart.p, pairIn(c), pairOut(),
+                                                              c.box, c.colBuf);
+            c.launches++;
+        }
     }
+    (void)out;
     ALENS_CUDA(cudaGetLastError());
     c.nCon = c.nColl = total;
 }
@@ -899,7 +1084,14 @@ void preloadCollideKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_scan_tile_apply));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_cell_scatter));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_cell_order));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, k_pairs_find));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<4, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<5, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<3, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<8, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<6, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_cand_narrow));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_cell_hit_count));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_pairs_emit2));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_pairs_emit));
 }
 

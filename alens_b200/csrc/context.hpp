@@ -262,6 +262,13 @@ struct Context {
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 1;                 // 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
+    int optFindSplitMinB = 8;               // ... resident CTAs per SM of its stage-1/2 kernel (8: 64 registers)
+    int optFindSplit = 1;                   // pair search: stages 1-2 -> candidates, dense narrow phase + ordered emission (0: one kernel)
+    int candWords = 16;                     // bitmap words per cell (32 candidates each); follows the fullest cell of the last step
+    long long lastCand = 0;                 // staged candidates of the last step (sizes the dense grids and the list)
+    DevBuf<unsigned> candBits;              // [ncell][candWords] contact flags of the staged candidates
+    DevBuf<int> candPrefix, cellCand;       // exclusive popcounts of the bitmap words; candidates per cell
+    int optFindMinB = 4;                    // k_pairs_find: resident CTAs per SM asked of the compiler (4: 128 registers)
     int optForceSplit = 0;                  // force_kernel = 2: k_slot_x + k_rod_sum instead of k_force_vel_act
     DevBuf<double> slotX;                   // multiplier per incidence slot (k_slot_x -> k_rod_sum)
     DevBuf<unsigned> slotLive;              // bit per incidence slot: multiplier non-zero
