@@ -1149,33 +1149,48 @@ __device__ __forceinline__ void tailEpilogue(const BbTail &p, double s0, double 
         s0 += pp[4 * i]; s1 += pp[4 * i + 1]; s2 += pp[4 * i + 2]; mx = fmax(mx, pp[4 * i + 3]);
     }
     blockReduce4(s0, s1, s2, mx, out);
-    if (threadIdx.x == 0) {
-        if (p.fusedReduce) { // allreduce over the ranks' mailboxes, in rank order on every rank
-            const ReduceArgs &a = p.red;
-            for (int q = 0; q < a.R; q++) {
-                double *dst = a.mailPeer[q];
-                dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
-                __threadfence_system();
-                stReleaseSys(a.seqPeer[q], a.seq);
+    if (p.fusedReduce) { // allreduce over the ranks' mailboxes: thread q talks to rank q, thread 0 sums in rank order
+        __shared__ double tot4[kMaxRanks][4];
+        __shared__ int failed;
+        const ReduceArgs &a = p.red;
+        if (threadIdx.x == 0) failed = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < a.R) { // R remote stores + releases in parallel (one NVLink round trip instead of R)
+            const int q = threadIdx.x;
+            double *dst = a.mailPeer[q];
+            dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
+            __threadfence_system();
+            stReleaseSys(a.seqPeer[q], a.seq);
+            if (!waitSeq(a.seqMine + q, a.seq, a.err)) {
+                failed = 1;
+            } else {
+                const volatile double *m = a.mailMine + 4 * q;
+                tot4[q][0] = m[0]; tot4[q][1] = m[1]; tot4[q][2] = m[2]; tot4[q][3] = m[3];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (failed) { // a peer never arrived: stop the loop, tell the host
+                p.scal->ticket = 0;
+                p.scal->done = 4;
+                if (p.prog) {
+                    volatile int *pg = p.prog;
+                    pg[1] = 4;
+                    __threadfence_system();
+                    pg[0] = p.ite + 1;
+                }
+                return;
             }
             double tot[4] = {0, 0, 0, 0};
-            for (int q = 0; q < a.R; q++) {
-                if (!waitSeq(a.seqMine + q, a.seq, a.err)) { // a peer never arrived: stop the loop, tell the host
-                    p.scal->ticket = 0;
-                    p.scal->done = 4;
-                    if (p.prog) {
-                        volatile int *pg = p.prog;
-                        pg[1] = 4;
-                        __threadfence_system();
-                        pg[0] = p.ite + 1;
-                    }
-                    return;
-                }
-                const volatile double *m = a.mailMine + 4 * q;
-                tot[0] += m[0]; tot[1] += m[1]; tot[2] += m[2]; tot[3] = fmax(tot[3], m[3]);
+            for (int q = 0; q < a.R; q++) { // identical order on every rank: identical bits
+                tot[0] += tot4[q][0]; tot[1] += tot4[q][1]; tot[2] += tot4[q][2]; tot[3] = fmax(tot[3], tot4[q][3]);
             }
             bbScalarStep(p, tot);
-        } else if (p.redOut) { // multi-rank, unfused: k_bb_reduce combines the ranks and takes the scalar step
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        if (p.redOut) { // multi-rank, unfused: k_bb_reduce combines the ranks and takes the scalar step
             p.redOut[0] = out[0]; p.redOut[1] = out[1]; p.redOut[2] = out[2]; p.redOut[3] = out[3];
             p.scal->ticket = 0;
         } else {
