@@ -20,6 +20,9 @@ BLOCK_DTYPE = np.dtype(
 )
 assert BLOCK_DTYPE.itemsize == 272
 
+BOUNDARY_DTYPE = np.dtype([("type", "<i4"), ("inside", "<i4"), ("center", "<f8", 3), ("axis", "<f8", 3), ("radius", "<f8")],
+                          align=True)
+
 # every symbol include/alens_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "alens_create", "alens_destroy", "alens_last_error", "alens_version", "alens_set_stream",
@@ -31,7 +34,7 @@ EXPORTS = [
     "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
     "alens_set_decomposition", "alens_comm_create", "alens_comm_blob_size", "alens_comm_export",
     "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
-    "alens_set_velocity_noncon_async",
+    "alens_set_velocity_noncon_async", "alens_collect_boundary_collision",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
 ]
 
@@ -200,6 +203,13 @@ class Context:
     def set_velocity_noncon(self, v):
         v = None if v is None else np.ascontiguousarray(v, dtype=np.float64)
         self._call("alens_set_velocity_noncon", _dp(v))
+
+    def collect_boundary_collision(self, boundaries):
+        """boundaries: structured array with the fields of alens_boundary (type, inside, center[3], axis[3], radius)"""
+        b = np.ascontiguousarray(boundaries, dtype=BOUNDARY_DTYPE)
+        n = C.c_longlong(0)
+        self._call("alens_collect_boundary_collision", C.c_void_p(b.ctypes.data), C.c_int(len(b)), C.byref(n))
+        return n.value
 
     def set_velocity_noncon_async_raw(self, v_p):
         """pinned host pointer; the copy overlaps the calls that follow (see alens_b200.h)"""

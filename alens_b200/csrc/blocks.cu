@@ -116,6 +116,158 @@ void appendBlocks(Context &c, const alens_constraint_block *b, long long n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Boundary collisions (SylinderSystem::collectBoundaryCollision, SylinderSystem.cpp:1093-1150; Boundary::project,
+// Boundary/Boundary.cpp:25-41, :108-124, :185-209).  Same expression order as the reference (and the oracle): with
+// -fmad=false the blocks are bit-identical.
+__device__ __forceinline__ void boundaryProject(const alens_boundary &b, Vec3 q, Vec3 &proj, Vec3 &delta) {
+    const Vec3 ctr = v3(b.center[0], b.center[1], b.center[2]), ax = v3(b.axis[0], b.axis[1], b.axis[2]);
+    if (b.type == 0) { // spherical shell
+        const Vec3 Q = q - ctr;
+        const double QueryR = norm(Q);
+        const double f = b.radius * (1 / QueryR);
+        const Vec3 P = v3(f * Q.x, f * Q.y, f * Q.z);
+        Vec3 PQ = Q - P;
+        const bool out = QueryR > b.radius;
+        if ((b.inside && out) || (!b.inside && !out)) PQ = v3(PQ.x * -1, PQ.y * -1, PQ.z * -1);
+        proj = P + ctr;
+        delta = PQ;
+    } else if (b.type == 1) { // flat wall
+        const Vec3 CQ = q - ctr;
+        const double t = dot(CQ, ax);
+        const Vec3 P = v3(q.x - t * ax.x, q.y - t * ax.y, q.z - t * ax.z);
+        Vec3 PQ = q - P;
+        if (t < 0) PQ = v3(PQ.x * -1, PQ.y * -1, PQ.z * -1);
+        proj = P;
+        delta = PQ;
+    } else { // infinite tube
+        const Vec3 CQ = q - ctr;
+        const double t = dot(CQ, ax);
+        const Vec3 PA = v3(ctr.x + t * ax.x, ctr.y + t * ax.y, ctr.z + t * ax.z);
+        const Vec3 PAQ = q - PA;
+        const double r = norm(PAQ);
+        const Vec3 P = v3(PA.x + b.radius * (PAQ.x / r), PA.y + b.radius * (PAQ.y / r), PA.z + b.radius * (PAQ.z / r));
+        Vec3 d = q - P;
+        if (r > b.radius) {
+            if (b.inside) d = v3(d.x * -1, d.y * -1, d.z * -1);
+        } else {
+            if (!b.inside) d = v3(d.x * -1, d.y * -1, d.z * -1);
+        }
+        proj = P;
+        delta = d;
+    }
+}
+
+struct BoundaryRods {
+    const int *userToSorted, *sGid;
+    const double *sX, *sY, *sZ, *sDx, *sDy, *sDz, *sLc, *sRc;
+    int nLocal, globalBase;
+    double colBuf;
+};
+
+// checkEnd (SylinderSystem.cpp:1111-1133); returns whether a block is due, fills it when blk != nullptr
+__device__ __forceinline__ bool boundaryCheckEnd(const alens_boundary &b, Vec3 center, Vec3 Query, double radius,
+                                                 double radiusCollision, double colBuf, int gid, int globalIndex,
+                                                 alens_constraint_block *blk) {
+    Vec3 Proj, delta;
+    boundaryProject(b, Query, Proj, delta);
+    const double deltanorm = norm(delta);
+    const double inv = 1 / deltanorm;
+    const Vec3 nrm = v3(delta.x * inv, delta.y * inv, delta.z * inv);
+    const Vec3 posI = Query - center;
+    double d0;
+    if (dot(Query - Proj, delta) < 0) d0 = -deltanorm - radius;
+    else if (deltanorm < (1 + colBuf * 2) * radiusCollision) d0 = deltanorm - radius;
+    else return false;
+    if (blk) {
+        alens_constraint_block q;
+        memset(&q, 0, sizeof(q));
+        q.delta0 = d0;
+        q.gamma = 0;
+        q.gidI = q.gidJ = gid;
+        q.globalIndexI = q.globalIndexJ = globalIndex;
+        q.oneSide = 1;
+        q.bilateral = 0;
+        q.kappa = 0;
+        q.normI[0] = q.normJ[0] = nrm.x; q.normI[1] = q.normJ[1] = nrm.y; q.normI[2] = q.normJ[2] = nrm.z;
+        q.posI[0] = q.posJ[0] = posI.x; q.posI[1] = q.posJ[1] = posI.y; q.posI[2] = q.posJ[2] = posI.z;
+        q.labI[0] = Query.x; q.labI[1] = Query.y; q.labI[2] = Query.z;
+        q.labJ[0] = Proj.x; q.labJ[1] = Proj.y; q.labJ[2] = Proj.z;
+        *blk = q;
+    }
+    return true;
+}
+
+// one thread per (boundary, local rod in the caller's order).  EMIT = false: number of blocks (0..2) -> cnt;
+// EMIT = true: the blocks at out[start[...]], minus end first
+template <bool EMIT>
+__global__ void k_boundary(BoundaryRods R, const alens_boundary *__restrict__ bnd, int nb, int *__restrict__ cnt,
+                           const int *__restrict__ start, alens_constraint_block *__restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)nb * R.nLocal) return;
+    const int ib = (int)(t / R.nLocal), u = (int)(t - (long long)ib * R.nLocal);
+    const alens_boundary b = bnd[ib];
+    const int s = R.userToSorted[u];
+    const Vec3 c = v3(R.sX[s], R.sY[s], R.sZ[s]), d = v3(R.sDx[s], R.sDy[s], R.sDz[s]);
+    const double lc = R.sLc[s], rc = R.sRc[s];
+    const int gid = R.sGid[s], gi = R.globalBase + u;
+    alens_constraint_block *o = EMIT ? out + start[t] : nullptr;
+    int n = 0;
+    if (lc < 2 * rc) { // sphere for collisions (SylinderNear.hpp:241; SylinderSystem.cpp:1135-1137)
+        const double radius = lc * 0.5 + rc;
+        if (boundaryCheckEnd(b, c, c, radius, rc, R.colBuf, gid, gi, EMIT ? o : nullptr)) n++;
+    } else {
+        const double h = lc * 0.5;
+        const Vec3 Qm = v3(c.x - d.x * h, c.y - d.y * h, c.z - d.z * h), Qp = v3(c.x + d.x * h, c.y + d.y * h, c.z + d.z * h);
+        if (boundaryCheckEnd(b, c, Qm, rc, rc, R.colBuf, gid, gi, EMIT ? o : nullptr)) n++;
+        if (boundaryCheckEnd(b, c, Qp, rc, rc, R.colBuf, gid, gi, EMIT ? o + n : nullptr)) n++;
+    }
+    if (!EMIT) cnt[t] = n;
+}
+
+void launchScanInt(Context &c, const int *in, int *out, int n);
+
+long long collectBoundary(Context &c, const alens_boundary *bnd, int nb) {
+    if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_collect_boundary_collision: call alens_set_rods first"};
+    if (nb <= 0 || c.nLocal == 0) return 0;
+    cudaStream_t st = c.stream;
+    std::vector<alens_boundary> hb(bnd, bnd + nb);
+    for (auto &b : hb) { // the reference's constructors normalise the wall normal / tube axis (Boundary.cpp:96-100, :166-172)
+        if (b.type < 0 || b.type > 2) throw ArgError{ALENS_ERR_ARG, "alens_collect_boundary_collision: type must be 0, 1 or 2"};
+        const double a = std::sqrt(b.axis[0] * b.axis[0] + b.axis[1] * b.axis[1] + b.axis[2] * b.axis[2]);
+        if (b.type != 0) {
+            if (!(a > 0)) throw ArgError{ALENS_ERR_ARG, "alens_collect_boundary_collision: zero axis"};
+            for (int k = 0; k < 3; k++) b.axis[k] = b.axis[k] / a;
+        }
+    }
+    const long long nt = (long long)nb * c.nLocal;
+    if (nt > 0x7fffffffLL - 8) throw ArgError{ALENS_ERR_UNSUPPORTED, "alens_collect_boundary_collision: too many (boundary, rod) pairs"};
+    DevBuf<alens_boundary> dB;
+    DevBuf<int> dCnt, dStart;
+    dB.reserve(nb);
+    dCnt.reserve((size_t)nt + 1);
+    dStart.reserve((size_t)nt + 8);
+    ALENS_CUDA(cudaMemcpyAsync(dB.p, hb.data(), sizeof(alens_boundary) * nb, cudaMemcpyHostToDevice, st));
+    const BoundaryRods R{c.userToSorted.p, c.sGid.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLc.p, c.sRc.p,
+                         c.nLocal, c.globalBase, c.colBuf};
+    k_boundary<false><<<gridFor(nt, 128), 128, 0, st>>>(R, dB.p, nb, dCnt.p, nullptr, nullptr);
+    launchScanInt(c, dCnt.p, dStart.p, (int)nt);
+    int total = 0;
+    ALENS_CUDA(cudaMemcpyAsync(&total, dStart.p + nt, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    c.launches += 1;
+    if (total == 0) return 0;
+    DevBuf<alens_constraint_block> dOut;
+    dOut.reserve((size_t)total);
+    k_boundary<true><<<gridFor(nt, 128), 128, 0, st>>>(R, dB.p, nb, nullptr, dStart.p, dOut.p);
+    c.launches += 1;
+    std::vector<alens_constraint_block> host((size_t)total);
+    ALENS_CUDA(cudaMemcpyAsync(host.data(), dOut.p, sizeof(alens_constraint_block) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    appendBlocks(c, host.data(), total); // into the constraint arrays + the host copies kept for the pool refill
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------------
 struct BlocksIn {
     const int *idxI, *idxJ, *gidI, *gidJ, *sUser, *uGlobalIdx;
     const signed char *shift;

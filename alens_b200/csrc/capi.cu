@@ -274,6 +274,14 @@ int alens_append_constraints(alens_ctx *ctx, const alens_constraint_block *b, lo
     });
 }
 
+int alens_collect_boundary_collision(alens_ctx *ctx, const alens_boundary *boundaries, int nBoundaries, long long *nAdded) {
+    return guarded(ctx, [&](Context &c) {
+        if (nBoundaries > 0 && !boundaries) throw ArgError{ALENS_ERR_ARG, "alens_collect_boundary_collision: NULL boundaries"};
+        const long long n = collectBoundary(c, boundaries, nBoundaries);
+        if (nAdded) *nAdded = n;
+    });
+}
+
 int alens_clear_constraints(alens_ctx *ctx) {
     return guarded(ctx, [&](Context &c) {
         c.nCon = c.nColl = 0;

@@ -349,6 +349,7 @@ inline void waitVelNC(Context &c) {
         c.velNCPending = false;
     }
 }
+long long collectBoundary(Context &c, const alens_boundary *bnd, int nb);
 void preloadCollideKernels();
 void preloadSolverKernels();
 void preloadBlockKernels();

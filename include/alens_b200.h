@@ -124,6 +124,18 @@ int alens_collect_pair_collision(alens_ctx *ctx, long long *nConstraints);
  * SylinderSystem.cpp:1093-1150, :1386-1482, SRC/TubuleSystem.cpp:694-745).  Two-sided blocks must
  * have normJ == -normI (true for every producer in the reference). */
 int alens_append_constraints(alens_ctx *ctx, const alens_constraint_block *blocks, long long n);
+/* One boundary of RunConfig::boundaryPtr (SimToolbox/Boundary/Boundary.hpp:24-94).  type: 0 SphereShell(center,
+ * radius, inside), 1 Wall(center, norm), 2 Tube(center, axis, radius, inside); `axis` = wall normal / tube axis and is
+ * normalised here as the reference's constructors do. */
+typedef struct alens_boundary {
+    int type, inside;
+    double center[3], axis[3], radius;
+} alens_boundary;
+/* SylinderSystem::collectBoundaryCollision (SylinderSystem.cpp:1093-1150) on the device: every rod end point (the centre
+ * of a sphere) is projected onto every boundary; a point outside, or inside within (1 + 2 colBuf) radiusCollision, adds a
+ * one-sided block (delta0 = -+|delta| - radius, normI = delta/|delta|, posI = Q - centre, labI = Q, labJ = projection).
+ * Order: (boundary, rod in the caller's order, minus end, plus end).  Call after alens_collect_pair_collision. */
+int alens_collect_boundary_collision(alens_ctx *ctx, const alens_boundary *boundaries, int nBoundaries, long long *nAdded);
 int alens_clear_constraints(alens_ctx *ctx); /* ConstraintCollector::clear */
 /* ConstraintCollector::getLocalNumberOfConstraints (ConstraintCollector.cpp:30-36) */
 int alens_num_constraints(alens_ctx *ctx, long long *n);

@@ -1,7 +1,12 @@
 // SylinderConfig.hpp -- the run parameters the hot path reads (SimToolbox/Sylinder/SylinderConfig.hpp).
-// The YAML parser and the boundary list stay with the host application.
+// The YAML parser stays with the host application; the boundary list is the plain-data form of RunConfig::boundaryPtr
+// (SimToolbox/Boundary/Boundary.hpp): fill one alens_boundary per SphereShell / Wall / Tube.
 #ifndef ALENS_B200_SYLINDERCONFIG_HPP_
 #define ALENS_B200_SYLINDERCONFIG_HPP_
+
+#include <vector>
+
+#include "../alens_b200.h"
 
 class SylinderConfig {
   public:
@@ -20,6 +25,7 @@ class SylinderConfig {
     double conResTol = 1e-5;
     int conMaxIte = 100000;
     int conSolverChoice = 0;
+    std::vector<alens_boundary> boundaries; // SylinderConfig.hpp: boundaryPtr
 };
 
 #endif

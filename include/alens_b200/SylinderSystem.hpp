@@ -4,7 +4,7 @@
 //   :1152-1160, resolveConstraints :829-866, saveForceVelocityConstraints :971-1018, sumForceVelocity
 //   :802-814, stepEuler :816-827, runStep :948-969, setForceNonBrown/setVelocityNonBrown :934-946.
 // Not here (they stay with the host application, SURVEY.md section 8 "out of scope"): file/VTK I/O, YAML,
-// Brownian noise, boundaries, links, domain decomposition by FDPS.
+// Brownian noise, links, domain decomposition by FDPS.  Boundaries: collectBoundaryCollision :1093-1150 (device).
 #ifndef ALENS_B200_SYLINDERSYSTEM_HPP_
 #define ALENS_B200_SYLINDERSYSTEM_HPP_
 
@@ -185,9 +185,16 @@ class SylinderSystem {
         ck(alens_collect_pair_collision(ctx_, &n));
     }
 
+    void collectBoundaryCollision() { // :1093-1150, on the device; blocks follow the pair collisions in the list
+        if (runConfig.boundaries.empty()) return;
+        long long n = 0;
+        ck(alens_collect_boundary_collision(ctx_, runConfig.boundaries.data(), (int)runConfig.boundaries.size(), &n));
+    }
+
     void resolveConstraints() { // :829-866
         collectPairCollision();
-        // collectBoundaryCollision / collectLinkBilateral: host application pushes those blocks into the pool
+        collectBoundaryCollision();
+        // collectLinkBilateral / protein constraints: the host application pushes those blocks into the pool
         conSolverPtr->setup(*conCollectorPtr, mobilityOperatorRcp, velocityNonConRcp, runConfig.dt);
         conSolverPtr->setControlParams(runConfig.conResTol, runConfig.conMaxIte, runConfig.conSolverChoice);
         conSolverPtr->solveConstraints();

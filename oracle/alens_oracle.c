@@ -1112,3 +1112,121 @@ void orc_writeback_gamma(long long nc, orc_block *blocks, const double *gamma) {
         for (int c = 0; c < 9; c++) blocks[k].stress[c] *= blocks[k].gamma;
     }
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * boundaries: Boundary::project of the three shipped shapes, arithmetic in the reference's expression order
+ * (Eigen: a.norm() = sqrt(x^2+y^2+z^2), a.normalized() = a / norm) */
+void orc_boundary_project(const orc_boundary *b, const double query[3], double project[3], double delta[3]) {
+    if (b->type == 0) { /* SphereShell::project, Boundary.cpp:25-41 */
+        double Q[3], Proj[3], PQ[3];
+        sub3(query, b->center, Q);
+        const double QueryR = norm3(Q);
+        const double f = b->radius * (1 / QueryR);
+        for (int k = 0; k < 3; k++) Proj[k] = f * Q[k];
+        for (int k = 0; k < 3; k++) PQ[k] = Q[k] - Proj[k];
+        const int out = QueryR > b->radius;
+        if ((b->inside && out) || (!b->inside && !out))
+            for (int k = 0; k < 3; k++) PQ[k] *= -1;
+        for (int k = 0; k < 3; k++) {
+            project[k] = Proj[k] + b->center[k];
+            delta[k] = PQ[k];
+        }
+    } else if (b->type == 1) { /* Wall::project, Boundary.cpp:108-124 */
+        double CQ[3], Proj[3], PQ[3];
+        sub3(query, b->center, CQ);
+        const double t = dot3(CQ, b->axis);
+        for (int k = 0; k < 3; k++) Proj[k] = query[k] - t * b->axis[k];
+        for (int k = 0; k < 3; k++) PQ[k] = query[k] - Proj[k];
+        if (t < 0)
+            for (int k = 0; k < 3; k++) PQ[k] *= -1;
+        for (int k = 0; k < 3; k++) {
+            project[k] = Proj[k];
+            delta[k] = PQ[k];
+        }
+    } else { /* Tube::project, Boundary.cpp:185-209 */
+        double CQ[3], ProjAxis[3], PAQ[3], Proj[3], d[3];
+        sub3(query, b->center, CQ);
+        const double t = dot3(CQ, b->axis);
+        for (int k = 0; k < 3; k++) ProjAxis[k] = b->center[k] + t * b->axis[k];
+        sub3(query, ProjAxis, PAQ);
+        const double r = norm3(PAQ);
+        for (int k = 0; k < 3; k++) Proj[k] = ProjAxis[k] + b->radius * (PAQ[k] / r);
+        sub3(query, Proj, d);
+        if (r > b->radius) {
+            if (b->inside)
+                for (int k = 0; k < 3; k++) d[k] *= -1;
+        } else {
+            if (!b->inside)
+                for (int k = 0; k < 3; k++) d[k] *= -1;
+        }
+        for (int k = 0; k < 3; k++) {
+            project[k] = Proj[k];
+            delta[k] = d[k];
+        }
+    }
+}
+
+/* checkEnd of SylinderSystem.cpp:1111-1133 for one query point; returns 1 if a block was written */
+static int boundary_check_end(const orc_boundary *b, const orc_rod *sy, const double Query[3], double radius, double colBuf,
+                              orc_block *blk) {
+    double Proj[3], delta[3], norm[3], posI[3], QP[3];
+    orc_boundary_project(b, Query, Proj, delta);
+    const double deltanorm = norm3(delta);
+    const double inv = 1 / deltanorm;
+    for (int k = 0; k < 3; k++) norm[k] = delta[k] * inv;
+    sub3(Query, sy->pos, posI);
+    sub3(Query, Proj, QP);
+    double d0;
+    if (dot3(QP, delta) < 0) d0 = -deltanorm - radius;                              /* outside the boundary */
+    else if (deltanorm < (1 + colBuf * 2) * sy->radiusCollision) d0 = deltanorm - radius; /* inside but close */
+    else return 0;
+    memset(blk, 0, sizeof(*blk));
+    blk->delta0 = d0;
+    blk->gamma = 0;
+    blk->gidI = blk->gidJ = sy->gid;
+    blk->globalIndexI = blk->globalIndexJ = sy->globalIndex;
+    blk->oneSide = 1;
+    blk->bilateral = 0;
+    blk->kappa = 0;
+    for (int k = 0; k < 3; k++) {
+        blk->normI[k] = blk->normJ[k] = norm[k];
+        blk->posI[k] = blk->posJ[k] = posI[k];
+        blk->labI[k] = Query[k];
+        blk->labJ[k] = Proj[k];
+    }
+    return 1;
+}
+
+long long orc_collect_boundary(int n, const orc_rod *rods, int nb, const orc_boundary *bnd, double colBuf, orc_block *out,
+                               long long cap) {
+    long long cnt = 0;
+    orc_block tmp;
+    for (int ib = 0; ib < nb; ib++) {
+        for (int i = 0; i < n; i++) {
+            const orc_rod *sy = &rods[i];
+            if (is_sphere_col(sy)) { /* SylinderSystem.cpp:1135-1137 */
+                const double radius = sy->lengthCollision * 0.5 + sy->radiusCollision;
+                if (boundary_check_end(&bnd[ib], sy, sy->pos, radius, colBuf, &tmp)) {
+                    if (cnt < cap) out[cnt] = tmp;
+                    cnt++;
+                }
+            } else { /* :1138-1146 */
+                double Qm[3], Qp[3];
+                const double h = sy->lengthCollision * 0.5;
+                for (int k = 0; k < 3; k++) {
+                    Qm[k] = sy->pos[k] - sy->direction[k] * h;
+                    Qp[k] = sy->pos[k] + sy->direction[k] * h;
+                }
+                if (boundary_check_end(&bnd[ib], sy, Qm, sy->radiusCollision, colBuf, &tmp)) {
+                    if (cnt < cap) out[cnt] = tmp;
+                    cnt++;
+                }
+                if (boundary_check_end(&bnd[ib], sy, Qp, sy->radiusCollision, colBuf, &tmp)) {
+                    if (cnt < cap) out[cnt] = tmp;
+                    cnt++;
+                }
+            }
+        }
+    }
+    return cnt;
+}

@@ -53,7 +53,20 @@ typedef struct {
     double v[6];
 } orc_hist;
 
+/* SimToolbox/Boundary/Boundary.hpp:24-94: type 0 SphereShell(center, radius, inside), 1 Wall(center, norm),
+ * 2 Tube(center, axis, radius, inside); `axis` holds the wall normal / tube axis (normalised by the constructor) */
+typedef struct {
+    int type, inside;
+    double center[3], axis[3], radius;
+} orc_boundary;
+
 int orc_sizeof_rod(void);
+/* Boundary::project (Boundary.cpp:25-41, :108-124, :185-209) */
+void orc_boundary_project(const orc_boundary *b, const double query[3], double project[3], double delta[3]);
+/* SylinderSystem::collectBoundaryCollision (SylinderSystem.cpp:1093-1150): one-sided blocks of the rods' end points
+ * (centre for spheres) against every boundary, order = (boundary, rod, minus end, plus end); returns the count */
+long long orc_collect_boundary(int n, const orc_rod *rods, int nb, const orc_boundary *bnd, double colBuf, orc_block *out,
+                               long long cap);
 int orc_sizeof_block(void);
 
 /* ---- geometry (Collision/DCPQuery.hpp) */

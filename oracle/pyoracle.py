@@ -189,6 +189,43 @@ def collect_pairs(rods, lo, hi, pbc, with_stress=False, method="cells", nthreads
         cap = int(cnt)
 
 
+BOUNDARY_DTYPE = np.dtype([("type", "<i4"), ("inside", "<i4"), ("center", "<f8", 3), ("axis", "<f8", 3), ("radius", "<f8")],
+                          align=True)
+
+
+def make_boundaries(specs):
+    """specs: list of dicts {type: 'sphere'|'wall'|'tube', center, axis (wall normal / tube axis), radius, inside};
+    axes are normalised as the reference's constructors do (Boundary.cpp:96-100, :166-172)"""
+    out = np.zeros(len(specs), dtype=BOUNDARY_DTYPE)
+    for o, s in zip(out, specs):
+        o["type"] = {"sphere": 0, "wall": 1, "tube": 2}[s["type"]]
+        o["inside"] = 1 if s.get("inside", True) else 0
+        o["center"] = s["center"]
+        a = np.asarray(s.get("axis", [0.0, 0.0, 1.0]), dtype=np.float64)
+        o["axis"] = a / np.sqrt((a * a).sum())
+        o["radius"] = s.get("radius", 0.0)
+    return out
+
+
+def boundary_project(bnd, query):
+    b = np.ascontiguousarray(bnd, dtype=BOUNDARY_DTYPE).reshape(1)
+    q = np.ascontiguousarray(query, dtype=np.float64)
+    proj, delta = np.zeros(3), np.zeros(3)
+    lib().orc_boundary_project(_vp(b), _p(q), _p(proj), _p(delta))
+    return proj, delta
+
+
+def collect_boundary(rods, boundaries, col_buf):
+    rods = np.ascontiguousarray(rods, dtype=ROD_DTYPE)
+    bnd = np.ascontiguousarray(boundaries, dtype=BOUNDARY_DTYPE)
+    cap = max(16, 2 * len(rods) * max(len(bnd), 1))
+    out = np.zeros(cap, dtype=BLOCK_DTYPE)
+    L = lib()
+    L.orc_collect_boundary.restype = C.c_longlong
+    cnt = L.orc_collect_boundary(len(rods), _vp(rods), len(bnd), _vp(bnd), C.c_double(col_buf), _vp(out), C.c_longlong(cap))
+    return out[:cnt].copy()
+
+
 def fdps_collect(rods, lo, hi, pbc, nthreads=1, rebuild=True):
     """The reference's own FDPS neighbour search + functor (oracle/_ref).  Returns (pairs, rods_wrapped)."""
     rods = np.array(rods, dtype=ROD_DTYPE, order="C")
