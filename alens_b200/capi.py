@@ -34,7 +34,7 @@ EXPORTS = [
     "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
     "alens_set_decomposition", "alens_comm_create", "alens_comm_blob_size", "alens_comm_export",
     "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
-    "alens_set_velocity_noncon_async", "alens_collect_boundary_collision",
+    "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
 ]
 
@@ -209,6 +209,14 @@ class Context:
         b = np.ascontiguousarray(boundaries, dtype=BOUNDARY_DTYPE)
         n = C.c_longlong(0)
         self._call("alens_collect_boundary_collision", C.c_void_p(b.ctypes.data), C.c_int(len(b)), C.byref(n))
+        return n.value
+
+    def collect_link_bilateral(self, prev_gid, next_gid, link_kappa, link_gap):
+        p = np.ascontiguousarray(prev_gid, dtype=np.int32)
+        q = np.ascontiguousarray(next_gid, dtype=np.int32)
+        n = C.c_longlong(0)
+        self._call("alens_collect_link_bilateral", p.ctypes.data_as(C.POINTER(C.c_int)), q.ctypes.data_as(C.POINTER(C.c_int)),
+                   C.c_longlong(len(p)), C.c_double(link_kappa), C.c_double(link_gap), C.byref(n))
         return n.value
 
     def set_velocity_noncon_async_raw(self, v_p):

@@ -7,7 +7,9 @@
 #include "context.hpp"
 #include "geometry.cuh"
 
+#include <climits>
 #include <cstring>
+#include <string>
 #include <vector>
 
 namespace alens {
@@ -265,6 +267,151 @@ long long collectBoundary(Context &c, const alens_boundary *bnd, int nb) {
     ALENS_CUDA(cudaStreamSynchronize(st));
     appendBlocks(c, host.data(), total); // into the constraint arrays + the host copies kept for the pool refill
     return total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bilateral links (SylinderSystem::collectLinkBilateral, SylinderSystem.cpp:1386-1482).  gid -> rod through an open
+// addressing hash table built on the device (the reference asks its ZDD data directory).
+static constexpr int kEmptyKey = INT_MIN;
+__device__ __forceinline__ unsigned hashGid(int g) {
+    unsigned x = (unsigned)g;
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__global__ void k_gid_table_build(int nLocal, const int *__restrict__ gid, int *__restrict__ keys, int *__restrict__ vals,
+                                  unsigned mask) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nLocal) return;
+    const int g = gid[u];
+    unsigned h = hashGid(g) & mask;
+    while (true) {
+        const int prev = atomicCAS(&keys[h], kEmptyKey, g);
+        if (prev == kEmptyKey || prev == g) {
+            atomicMin(&vals[h], u); // a duplicated gid resolves to the first rod
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+__device__ __forceinline__ int gidLookup(int g, const int *__restrict__ keys, const int *__restrict__ vals, unsigned mask) {
+    unsigned h = hashGid(g) & mask;
+    while (true) {
+        const int k = keys[h];
+        if (k == g) return vals[h];
+        if (k == kEmptyKey) return -1;
+        h = (h + 1) & mask;
+    }
+}
+// findPBCImage(lb, ub, x, trg) of Util/GeoUtil.hpp:27-60
+__device__ __forceinline__ void pbcImage1(double lb, double ub, double &x) {
+    const double L = ub - lb;
+    while (x >= ub) x -= L;
+    while (x < lb) x += L;
+}
+__device__ __forceinline__ void pbcImage2(double lb, double ub, double &x, double &trg) {
+    pbcImage1(lb, ub, trg);
+    double dist = x - trg;
+    pbcImage1(0.0, ub - lb, dist);
+    if (dist > (ub - lb) * 0.5) x = trg + dist - (ub - lb);
+    else x = trg + dist;
+}
+
+struct LinkRods {
+    const int *userToSorted, *sGid;
+    const double *sX, *sY, *sZ, *sDx, *sDy, *sDz, *sLen, *sRad;
+    int globalBase;
+};
+__global__ void k_links(long long nLinks, const int *__restrict__ prevGid, const int *__restrict__ nextGid,
+                        const int *__restrict__ keys, const int *__restrict__ vals, unsigned mask, LinkRods R, Box box,
+                        double linkKappa, double linkGap, alens_constraint_block *__restrict__ out, int *__restrict__ missing) {
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nLinks) return;
+    const int uI = gidLookup(prevGid[l], keys, vals, mask), uJ = gidLookup(nextGid[l], keys, vals, mask);
+    if (uI < 0 || uJ < 0) {
+        atomicAdd(missing, 1);
+        return;
+    }
+    const int sI = R.userToSorted[uI], sJ = R.userToSorted[uJ];
+    const Vec3 cI = v3(R.sX[sI], R.sY[sI], R.sZ[sI]), dI = v3(R.sDx[sI], R.sDy[sI], R.sDz[sI]);
+    const Vec3 dJ = v3(R.sDx[sJ], R.sDy[sJ], R.sDz[sJ]);
+    double cj[3] = {R.sX[sJ], R.sY[sJ], R.sZ[sJ]};
+    const double ci[3] = {cI.x, cI.y, cI.z};
+    for (int k = 0; k < 3; k++) { // nearest periodic image of J (:1436-1448)
+        if (!box.pbc[k]) continue;
+        double trg = ci[k], xk = cj[k];
+        pbcImage2(box.lo[k], box.hi[k], xk, trg);
+        cj[k] = xk;
+    }
+    const Vec3 cJ = v3(cj[0], cj[1], cj[2]);
+    const double lenI = R.sLen[sI], lenJ = R.sLen[sJ], radI = R.sRad[sI], radJ = R.sRad[sJ];
+    const double hI = 0.5 * lenI, hJ = 0.5 * lenJ;
+    const Vec3 Pp = v3(cI.x + dI.x * hI, cI.y + dI.y * hI, cI.z + dI.z * hI);
+    const Vec3 Qm = v3(cJ.x - dJ.x * hJ, cJ.y - dJ.y * hJ, cJ.z - dJ.z * hJ);
+    const Vec3 rvec = Qm - Pp;
+    const double rnorm = norm(rvec);
+    const double delta0 = rnorm - radI - radJ - linkGap;
+    const Vec3 PQ = Pp - Qm;
+    const double pqn = norm(PQ);
+    const Vec3 nI = pqn > 0 ? v3(PQ.x / pqn, PQ.y / pqn, PQ.z / pqn) : PQ;
+    alens_constraint_block q;
+    memset(&q, 0, sizeof(q));
+    q.delta0 = delta0;
+    q.gamma = delta0 < 0 ? -delta0 : 0;
+    q.gidI = R.sGid[sI];
+    q.gidJ = R.sGid[sJ];
+    q.globalIndexI = R.globalBase + uI;
+    q.globalIndexJ = R.globalBase + uJ;
+    q.oneSide = 0;
+    q.bilateral = 1;
+    q.kappa = linkKappa;
+    q.normI[0] = nI.x; q.normI[1] = nI.y; q.normI[2] = nI.z;
+    q.normJ[0] = -nI.x; q.normJ[1] = -nI.y; q.normJ[2] = -nI.z;
+    q.posI[0] = Pp.x - cI.x; q.posI[1] = Pp.y - cI.y; q.posI[2] = Pp.z - cI.z;
+    q.posJ[0] = Qm.x - cJ.x; q.posJ[1] = Qm.y - cJ.y; q.posJ[2] = Qm.z - cJ.z;
+    q.labI[0] = Pp.x; q.labI[1] = Pp.y; q.labI[2] = Pp.z;
+    q.labJ[0] = Qm.x; q.labJ[1] = Qm.y; q.labJ[2] = Qm.z;
+    collideStress(dI, dJ, cI, cJ, lenI, lenJ, radI, radJ, 1.0, Pp, Qm, q.stress);
+    out[l] = q;
+}
+
+long long collectLinks(Context &c, const int *prevGid, const int *nextGid, long long nLinks, double linkKappa,
+                       double linkGap) {
+    if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_collect_link_bilateral: call alens_set_rods first"};
+    if (nLinks <= 0) return 0;
+    if (!prevGid || !nextGid) throw ArgError{ALENS_ERR_ARG, "alens_collect_link_bilateral: NULL gid list"};
+    cudaStream_t st = c.stream;
+    unsigned size = 64;
+    while (size < 2u * (unsigned)std::max(c.nLocal, 1)) size <<= 1;
+    DevBuf<int> keys, vals, dPrev, dNext, dMissing;
+    keys.reserve(size); vals.reserve(size); dPrev.reserve((size_t)nLinks); dNext.reserve((size_t)nLinks); dMissing.reserve(1);
+    {
+        std::vector<int> fill(size, kEmptyKey);
+        ALENS_CUDA(cudaMemcpyAsync(keys.p, fill.data(), sizeof(int) * size, cudaMemcpyHostToDevice, st));
+        ALENS_CUDA(cudaMemsetAsync(vals.p, 0x7f, sizeof(int) * size, st)); // 0x7f7f7f7f: larger than any rod index
+        ALENS_CUDA(cudaMemsetAsync(dMissing.p, 0, sizeof(int), st));
+        ALENS_CUDA(cudaStreamSynchronize(st)); // `fill` is pageable host memory
+    }
+    ALENS_CUDA(cudaMemcpyAsync(dPrev.p, prevGid, sizeof(int) * (size_t)nLinks, cudaMemcpyHostToDevice, st));
+    ALENS_CUDA(cudaMemcpyAsync(dNext.p, nextGid, sizeof(int) * (size_t)nLinks, cudaMemcpyHostToDevice, st));
+    if (c.nLocal > 0)
+        k_gid_table_build<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.uGid.p, keys.p, vals.p, size - 1);
+    DevBuf<alens_constraint_block> dOut;
+    dOut.reserve((size_t)nLinks);
+    const LinkRods R{c.userToSorted.p, c.sGid.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLen.p, c.sRad.p,
+                     c.globalBase};
+    k_links<<<gridFor(nLinks, 128), 128, 0, st>>>(nLinks, dPrev.p, dNext.p, keys.p, vals.p, size - 1, R, c.box, linkKappa,
+                                                  linkGap, dOut.p, dMissing.p);
+    c.launches += 2;
+    int missing = 0;
+    std::vector<alens_constraint_block> host((size_t)nLinks);
+    ALENS_CUDA(cudaMemcpyAsync(&missing, dMissing.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaMemcpyAsync(host.data(), dOut.p, sizeof(alens_constraint_block) * (size_t)nLinks, cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    if (missing)
+        throw ArgError{ALENS_ERR_ARG, "alens_collect_link_bilateral: " + std::to_string(missing) +
+                                          " link end(s) refer to a gid this rank does not own"};
+    appendBlocks(c, host.data(), nLinks);
+    return nLinks;
 }
 
 // ------------------------------------------------------------------------------------------------

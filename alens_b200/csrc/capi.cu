@@ -282,6 +282,14 @@ int alens_collect_boundary_collision(alens_ctx *ctx, const alens_boundary *bound
     });
 }
 
+int alens_collect_link_bilateral(alens_ctx *ctx, const int *prevGid, const int *nextGid, long long nLinks, double linkKappa,
+                                 double linkGap, long long *nAdded) {
+    return guarded(ctx, [&](Context &c) {
+        const long long n = collectLinks(c, prevGid, nextGid, nLinks, linkKappa, linkGap);
+        if (nAdded) *nAdded = n;
+    });
+}
+
 int alens_clear_constraints(alens_ctx *ctx) {
     return guarded(ctx, [&](Context &c) {
         c.nCon = c.nColl = 0;

@@ -350,6 +350,7 @@ inline void waitVelNC(Context &c) {
     }
 }
 long long collectBoundary(Context &c, const alens_boundary *bnd, int nb);
+long long collectLinks(Context &c, const int *prevGid, const int *nextGid, long long nLinks, double linkKappa, double linkGap);
 void preloadCollideKernels();
 void preloadSolverKernels();
 void preloadBlockKernels();

@@ -136,6 +136,13 @@ typedef struct alens_boundary {
  * one-sided block (delta0 = -+|delta| - radius, normI = delta/|delta|, posI = Q - centre, labI = Q, labJ = projection).
  * Order: (boundary, rod in the caller's order, minus end, plus end).  Call after alens_collect_pair_collision. */
 int alens_collect_boundary_collision(alens_ctx *ctx, const alens_boundary *boundaries, int nBoundaries, long long *nAdded);
+/* SylinderSystem::collectLinkBilateral (SylinderSystem.cpp:1386-1482) on the device: for every link prev -> next (gids,
+ * the reference's linkMap) one bilateral block between the plus end of `prev` and the minus end of `next` (true length and
+ * radius, nearest periodic image), delta0 = distance - rI - rJ - linkGap, kappa = linkKappa, stress by collideStress.
+ * Blocks are appended in link order; the gid -> rod lookup (the reference's ZDD directory) is a device hash table.
+ * Both rods of a link must be owned by this rank (links across slabs: push the block with alens_append_constraints). */
+int alens_collect_link_bilateral(alens_ctx *ctx, const int *prevGid, const int *nextGid, long long nLinks, double linkKappa,
+                                 double linkGap, long long *nAdded);
 int alens_clear_constraints(alens_ctx *ctx); /* ConstraintCollector::clear */
 /* ConstraintCollector::getLocalNumberOfConstraints (ConstraintCollector.cpp:30-36) */
 int alens_num_constraints(alens_ctx *ctx, long long *n);

@@ -4,10 +4,12 @@
 //   :1152-1160, resolveConstraints :829-866, saveForceVelocityConstraints :971-1018, sumForceVelocity
 //   :802-814, stepEuler :816-827, runStep :948-969, setForceNonBrown/setVelocityNonBrown :934-946.
 // Not here (they stay with the host application, SURVEY.md section 8 "out of scope"): file/VTK I/O, YAML,
-// Brownian noise, links, domain decomposition by FDPS.  Boundaries: collectBoundaryCollision :1093-1150 (device).
+// Brownian noise, domain decomposition by FDPS.  Boundaries: collectBoundaryCollision :1093-1150, links:
+// collectLinkBilateral :1386-1482 (both on the device).
 #ifndef ALENS_B200_SYLINDERSYSTEM_HPP_
 #define ALENS_B200_SYLINDERSYSTEM_HPP_
 
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -185,6 +187,27 @@ class SylinderSystem {
         ck(alens_collect_pair_collision(ctx_, &n));
     }
 
+    // links prev gid -> next gid (SylinderSystem.hpp: linkMap, addNewLink / getLinkMap, SylinderSystem.cpp:1363-1384)
+    std::multimap<int, int> linkMap;
+    void addNewLink(const std::vector<Link> &links) {
+        for (const auto &l : links) linkMap.emplace(l.prev, l.next);
+    }
+    const std::multimap<int, int> &getLinkMap() const { return linkMap; }
+
+    void collectLinkBilateral() { // :1386-1482, on the device (gid lookup = device hash table instead of the ZDD directory)
+        if (linkMap.empty()) return;
+        std::vector<int> prev, next;
+        prev.reserve(linkMap.size());
+        next.reserve(linkMap.size());
+        for (const auto &kv : linkMap) {
+            prev.push_back(kv.first);
+            next.push_back(kv.second);
+        }
+        long long n = 0;
+        ck(alens_collect_link_bilateral(ctx_, prev.data(), next.data(), (long long)prev.size(), runConfig.linkKappa,
+                                        runConfig.linkGap, &n));
+    }
+
     void collectBoundaryCollision() { // :1093-1150, on the device; blocks follow the pair collisions in the list
         if (runConfig.boundaries.empty()) return;
         long long n = 0;
@@ -194,7 +217,8 @@ class SylinderSystem {
     void resolveConstraints() { // :829-866
         collectPairCollision();
         collectBoundaryCollision();
-        // collectLinkBilateral / protein constraints: the host application pushes those blocks into the pool
+        collectLinkBilateral();
+        // protein constraints (SRC/TubuleSystem.cpp:694-745): the host application pushes those blocks into the pool
         conSolverPtr->setup(*conCollectorPtr, mobilityOperatorRcp, velocityNonConRcp, runConfig.dt);
         conSolverPtr->setControlParams(runConfig.conResTol, runConfig.conMaxIte, runConfig.conSolverChoice);
         conSolverPtr->solveConstraints();

@@ -1230,3 +1230,89 @@ long long orc_collect_boundary(int n, const orc_rod *rods, int nb, const orc_bou
     }
     return cnt;
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * bilateral links (SylinderSystem.cpp:1386-1482) */
+static void pbc_image1(double lb, double ub, double *x) { /* Util/GeoUtil.hpp:27-36 */
+    const double L = ub - lb;
+    while (*x >= ub) *x -= L;
+    while (*x < lb) *x += L;
+}
+static void pbc_image2(double lb, double ub, double *x, double *trg) { /* Util/GeoUtil.hpp:51-60 */
+    pbc_image1(lb, ub, trg);
+    double dist = *x - *trg;
+    pbc_image1(0.0, ub - lb, &dist);
+    if (dist > (ub - lb) * 0.5) *x = *trg + dist - (ub - lb);
+    else *x = *trg + dist;
+}
+typedef struct {
+    int gid, idx;
+} gid_idx;
+static int cmp_gid(const void *a, const void *b) {
+    const int x = ((const gid_idx *)a)->gid, y = ((const gid_idx *)b)->gid;
+    return (x > y) - (x < y);
+}
+
+long long orc_collect_links(int n, const orc_rod *rods, long long nLinks, const int *prevGid, const int *nextGid,
+                            const double boxLow[3], const double boxHigh[3], const int pbc[3], double linkKappa,
+                            double linkGap, orc_block *out) {
+    gid_idx *map = (gid_idx *)malloc(sizeof(gid_idx) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        map[i].gid = rods[i].gid;
+        map[i].idx = i;
+    }
+    qsort(map, (size_t)n, sizeof(gid_idx), cmp_gid);
+    long long cnt = 0;
+    for (long long l = 0; l < nLinks; l++) {
+        gid_idx key = {prevGid[l], 0};
+        const gid_idx *fi = (const gid_idx *)bsearch(&key, map, (size_t)n, sizeof(gid_idx), cmp_gid);
+        key.gid = nextGid[l];
+        const gid_idx *fj = (const gid_idx *)bsearch(&key, map, (size_t)n, sizeof(gid_idx), cmp_gid);
+        if (!fi || !fj) {
+            free(map);
+            return -1;
+        }
+        const orc_rod *syI = &rods[fi->idx], *syJ = &rods[fj->idx];
+        double centerJ[3] = {syJ->pos[0], syJ->pos[1], syJ->pos[2]};
+        for (int k = 0; k < 3; k++) { /* :1436-1448 */
+            if (!pbc[k]) continue;
+            double trg = syI->pos[k], xk = centerJ[k];
+            pbc_image2(boxLow[k], boxHigh[k], &xk, &trg);
+            centerJ[k] = xk;
+        }
+        double Pp[3], Qm[3], rvec[3], PQ[3];
+        const double hI = 0.5 * syI->length, hJ = 0.5 * syJ->length;
+        for (int k = 0; k < 3; k++) {
+            Pp[k] = syI->pos[k] + syI->direction[k] * hI; /* plus end of I */
+            Qm[k] = centerJ[k] - syJ->direction[k] * hJ;   /* minus end of J */
+        }
+        sub3(Qm, Pp, rvec);
+        const double rnorm = norm3(rvec);
+        const double delta0 = rnorm - syI->radius - syJ->radius - linkGap;
+        sub3(Pp, Qm, PQ);
+        const double pqn = norm3(PQ);
+        orc_block *b = &out[cnt++];
+        memset(b, 0, sizeof(*b));
+        b->delta0 = delta0;
+        b->gamma = delta0 < 0 ? -delta0 : 0;
+        b->gidI = syI->gid;
+        b->gidJ = syJ->gid;
+        b->globalIndexI = syI->globalIndex;
+        b->globalIndexJ = syJ->globalIndex;
+        b->oneSide = 0;
+        b->bilateral = 1;
+        b->kappa = linkKappa;
+        for (int k = 0; k < 3; k++) {
+            b->normI[k] = pqn > 0 ? PQ[k] / pqn : PQ[k];
+            b->normJ[k] = -b->normI[k];
+            b->posI[k] = Pp[k] - syI->pos[k];
+            b->posJ[k] = Qm[k] - centerJ[k];
+            b->labI[k] = Pp[k];
+            b->labJ[k] = Qm[k];
+        }
+        orc_collide_stress(syI->direction, syJ->direction, syI->pos, centerJ, syI->length, syJ->length, syI->radius,
+                           syJ->radius, 1.0, Pp, Qm, b->stress);
+    }
+    free(map);
+    return cnt;
+}

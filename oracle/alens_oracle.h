@@ -65,6 +65,13 @@ int orc_sizeof_rod(void);
 void orc_boundary_project(const orc_boundary *b, const double query[3], double project[3], double delta[3]);
 /* SylinderSystem::collectBoundaryCollision (SylinderSystem.cpp:1093-1150): one-sided blocks of the rods' end points
  * (centre for spheres) against every boundary, order = (boundary, rod, minus end, plus end); returns the count */
+/* SylinderSystem::collectLinkBilateral (SylinderSystem.cpp:1386-1482): one bilateral block per link prev -> next between
+ * the PLUS end of prev and the MINUS end of next (true length / radius, nearest periodic image of next, findPBCImage of
+ * Util/GeoUtil.hpp:27-60), delta0 = |Q - P| - rI - rJ - linkGap, kappa = linkKappa, stress by collideStress.  Blocks in
+ * link order; returns the count, -1 if a gid is unknown. */
+long long orc_collect_links(int n, const orc_rod *rods, long long nLinks, const int *prevGid, const int *nextGid,
+                            const double boxLow[3], const double boxHigh[3], const int pbc[3], double linkKappa,
+                            double linkGap, orc_block *out);
 long long orc_collect_boundary(int n, const orc_rod *rods, int nb, const orc_boundary *bnd, double colBuf, orc_block *out,
                                long long cap);
 int orc_sizeof_block(void);

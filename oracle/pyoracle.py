@@ -226,6 +226,24 @@ def collect_boundary(rods, boundaries, col_buf):
     return out[:cnt].copy()
 
 
+def collect_links(rods, prev_gid, next_gid, lo, hi, pbc, link_kappa, link_gap):
+    rods = np.ascontiguousarray(rods, dtype=ROD_DTYPE)
+    prev_gid = np.ascontiguousarray(prev_gid, dtype=np.int32)
+    next_gid = np.ascontiguousarray(next_gid, dtype=np.int32)
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    pbc = np.ascontiguousarray(pbc, dtype=np.int32)
+    out = np.zeros(max(len(prev_gid), 1), dtype=BLOCK_DTYPE)
+    L = lib()
+    L.orc_collect_links.restype = C.c_longlong
+    cnt = L.orc_collect_links(len(rods), _vp(rods), C.c_longlong(len(prev_gid)), _p(prev_gid, C.c_int),
+                              _p(next_gid, C.c_int), _p(lo), _p(hi), _p(pbc, C.c_int), C.c_double(link_kappa),
+                              C.c_double(link_gap), _vp(out))
+    if cnt < 0:
+        raise ValueError("collect_links: unknown gid")
+    return out[:cnt].copy()
+
+
 def fdps_collect(rods, lo, hi, pbc, nthreads=1, rebuild=True):
     """The reference's own FDPS neighbour search + functor (oracle/_ref).  Returns (pairs, rods_wrapped)."""
     rods = np.array(rods, dtype=ROD_DTYPE, order="C")

@@ -93,6 +93,10 @@ def test_gpu_boundary_blocks_equal_the_oracle(ctx, oracle):
         o["type"] = {"sphere": 0, "wall": 1, "tube": 2}[s["type"]]
         o["inside"] = 1 if s.get("inside", True) else 0
         o["center"], o["axis"], o["radius"] = s["center"], s.get("axis", [0, 0, 1]), s.get("radius", 0.0)
+    assert ctx.collect_boundary_collision(raw[:0]) == 0  # no boundary: nothing happens
+    far = raw[1:2].copy()
+    far["center"] = [0.0, 0.0, -50.0]  # every rod far inside the allowed side: no block
+    assert ctx.collect_boundary_collision(far) == 0
     added = ctx.collect_boundary_collision(raw)
     assert added == len(want)
     got = ctx.get_constraints(with_stress=False)[nc:]
