@@ -747,12 +747,12 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
         b = bN;
         e = eN;
     }
-    if (HALO && hp.on && hp.ticket) { // fused multi-GPU: the mirrored rows are out, the last warp of the grid tells the neighbours
-        if (pushed) __threadfence_system(); // a lane's remote stores are performed before its warp takes the ticket
-        __syncwarp();
-        if (lane == 0) {
+    if (HALO && hp.on && hp.ticket) { // fused multi-GPU: the mirrored rows are out, the last CTA of the grid tells the neighbours
+        if (pushed) __threadfence_system(); // a lane's remote stores are performed before its CTA takes the ticket
+        __syncthreads();                    // (one ticket per CTA: 4x fewer atomics on the one counter than per warp)
+        if (threadIdx.x == 0) {
             const unsigned t = atomicAdd(hp.ticket, 1u);
-            if (t == gridDim.x * kActWarps - 1) {
+            if (t == gridDim.x - 1) {
                 *hp.ticket = 0;
                 __threadfence_system();
                 if (hp.flag[0]) stReleaseSys(hp.flag[0], hp.seq);
