@@ -34,7 +34,7 @@ EXPORTS = [
     "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
     "alens_set_decomposition", "alens_comm_create", "alens_comm_blob_size", "alens_comm_export",
     "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
-    "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral",
+    "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral", "alens_calc_velocity_noncon",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
 ]
 
@@ -210,6 +210,13 @@ class Context:
         n = C.c_longlong(0)
         self._call("alens_collect_boundary_collision", C.c_void_p(b.ctypes.data), C.c_int(len(b)), C.byref(n))
         return n.value
+
+    def calc_velocity_noncon(self, force_nonbrown=None, vel_nonbrown=None, vel_brown=None, monolayer=False):
+        """velNonCon = M f + vNB + vB on the device, kept resident; returns M f + vNB (Sylinder::velNonB / omegaNonB)"""
+        a = [None if x is None else np.ascontiguousarray(x, dtype=np.float64) for x in (force_nonbrown, vel_nonbrown, vel_brown)]
+        out = np.zeros(6 * self.n_rods)
+        self._call("alens_calc_velocity_noncon", _dp(a[0]), _dp(a[1]), _dp(a[2]), C.c_int(1 if monolayer else 0), _dp(out))
+        return out
 
     def collect_link_bilateral(self, prev_gid, next_gid, link_kappa, link_gap):
         p = np.ascontiguousarray(prev_gid, dtype=np.int32)

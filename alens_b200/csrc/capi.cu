@@ -209,6 +209,13 @@ int alens_set_velocity_noncon(alens_ctx *ctx, const double *v) {
     });
 }
 
+int alens_calc_velocity_noncon(alens_ctx *ctx, const double *forceNonBrown, const double *velocityNonBrown,
+                               const double *velocityBrown, int monolayer, double *velNonBOut) {
+    return guarded(ctx, [&](Context &c) {
+        calcVelocityNonCon(c, forceNonBrown, velocityNonBrown, velocityBrown, monolayer, velNonBOut);
+    });
+}
+
 int alens_set_velocity_noncon_async(alens_ctx *ctx, const double *v) {
     return guarded(ctx, [&](Context &c) {
         if (!v) {

@@ -97,6 +97,35 @@ __global__ void k_mob_apply_user(MobIn m, const int *__restrict__ userToSorted, 
     for (int c = 0; c < 6; c++) y[6 * u + c] = o[c];
 }
 
+// calcVelocityNonCon (SylinderSystem.cpp:724-800): vNC = M f + vNB + vB per local rod in the caller's order; the monolayer
+// mask zeroes v_z, omega_x, omega_y of every term (:737-743, :762-769, :789-797); updates are 1.0 * A + 1.0 * Y
+__global__ void k_velocity_noncon(MobIn m, int nLocal, const int *__restrict__ userToSorted, const double *__restrict__ force,
+                                  const double *__restrict__ velNB, const double *__restrict__ velB, int monolayer,
+                                  double *__restrict__ velNC, double *__restrict__ velNonBOut) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nLocal) return;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    if (force) {
+        double f[6];
+        for (int c = 0; c < 6; c++) f[c] = force[6 * (size_t)u + c];
+        applyMob(m, userToSorted[u], f, v);
+        if (monolayer) v[2] = v[3] = v[4] = 0;
+    }
+    if (velNB)
+        for (int c = 0; c < 6; c++) {
+            const double a = (monolayer && (c == 2 || c == 3 || c == 4)) ? 0.0 : velNB[6 * (size_t)u + c];
+            v[c] = 1.0 * a + 1.0 * v[c];
+        }
+    if (velNonBOut)
+        for (int c = 0; c < 6; c++) velNonBOut[6 * (size_t)u + c] = v[c];
+    if (velB)
+        for (int c = 0; c < 6; c++) {
+            const double a = (monolayer && (c == 2 || c == 3 || c == 4)) ? 0.0 : velB[6 * (size_t)u + c];
+            v[c] = 1.0 * a + 1.0 * v[c];
+        }
+    for (int c = 0; c < 6; c++) velNC[6 * (size_t)u + c] = v[c];
+}
+
 // ------------------------------------------------------------------------------------------------
 // incidence rod -> constraints (replaces the explicit transpose of ConstraintOperator.cpp:14-20)
 __global__ void k_inc_count(long long nc, const int *__restrict__ idxI, const int *__restrict__ idxJ,
@@ -1585,6 +1614,32 @@ void mobilityApply(Context &c, const double *x, double *y) {
     ALENS_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+void calcVelocityNonCon(Context &c, const double *force, const double *velNB, const double *velB, int monolayer,
+                        double *velNonBOut) {
+    if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_calc_velocity_noncon: call alens_set_rods first"};
+    if (force && !c.haveMob) throw ArgError{ALENS_ERR_STATE, "alens_calc_velocity_noncon: call alens_calc_mobility first"};
+    cudaStream_t st = c.stream;
+    const int n = c.nLocal;
+    waitVelNC(c);
+    c.uVelNC.reserve(6 * (size_t)c.nRods + 6);
+    const size_t bytes = 48 * (size_t)n;
+    c.vTmp0.reserve(6 * (size_t)n + 6); c.vTmp1.reserve(6 * (size_t)n + 6); c.vTmp2.reserve(6 * (size_t)n + 6);
+    c.vTmp3.reserve(6 * (size_t)n + 6);
+    if (n > 0) {
+        if (force) ALENS_CUDA(cudaMemcpyAsync(c.vTmp0.p, force, bytes, cudaMemcpyHostToDevice, st));
+        if (velNB) ALENS_CUDA(cudaMemcpyAsync(c.vTmp1.p, velNB, bytes, cudaMemcpyHostToDevice, st));
+        if (velB) ALENS_CUDA(cudaMemcpyAsync(c.vTmp2.p, velB, bytes, cudaMemcpyHostToDevice, st));
+        k_velocity_noncon<<<gridFor(n, 128), 128, 0, st>>>(mobIn(c), n, c.userToSorted.p, force ? c.vTmp0.p : nullptr,
+                                                           velNB ? c.vTmp1.p : nullptr, velB ? c.vTmp2.p : nullptr,
+                                                           monolayer, c.uVelNC.p, velNonBOut ? c.vTmp3.p : nullptr);
+        c.launches++;
+        if (velNonBOut) ALENS_CUDA(cudaMemcpyAsync(velNonBOut, c.vTmp3.p, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    ALENS_CUDA(cudaGetLastError());
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    c.haveVelNC = true;
+}
+
 void setupConstraints(Context &c, const double *velNC, double dt) {
     if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "setup: call alens_set_rods first"};
     if (!c.haveMob) throw ArgError{ALENS_ERR_STATE, "setup: call alens_calc_mobility first"};
@@ -2388,6 +2443,7 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_rod_sum<false, false>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_rod_sum<true, false>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_rod_sum<false, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_velocity_noncon));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit_rm));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<false>));

@@ -170,6 +170,13 @@ int alens_solve_constraints(alens_ctx *ctx, const double *velNonCon, double dt, 
  * device: 6n host doubles in local rod order, NULL = zero.  alens_solve_constraints / alens_setup_constraints
  * called with velNonCon == NULL use this resident vector. */
 int alens_set_velocity_noncon(alens_ctx *ctx, const double *velNonCon);
+/* SylinderSystem::calcVelocityNonCon (SylinderSystem.cpp:724-800) in one device pass, result resident:
+ *   velNonCon = M forceNonBrown + velocityNonBrown + velocityBrown
+ * (each term optional: NULL = absent; host arrays of 6n doubles in local rod order; needs alens_calc_mobility).
+ * monolayer != 0 zeroes v_z, omega_x, omega_y of every term as the reference does.  velNonBOut (optional, 6n host doubles)
+ * receives M forceNonBrown + velocityNonBrown, what the reference writes to Sylinder::velNonB / omegaNonB. */
+int alens_calc_velocity_noncon(alens_ctx *ctx, const double *forceNonBrown, const double *velocityNonBrown,
+                               const double *velocityBrown, int monolayer, double *velNonBOut);
 /* Same, without waiting for the copy: it runs on a side stream and overlaps whatever the caller does next
  * (typically alens_collect_pair_collision); the next call that reads the vector waits for it on the device.
  * velNonCon must be page-locked host memory and stay unchanged until alens_solve_constraints /

@@ -312,3 +312,28 @@ def test_velocity_noncon_async_upload(ctx, oracle):
         out.append((rep.iterations, ctx.get_gamma(), ctx.get_force_velocity()["velU"]))
     assert out[0][0] == out[1][0] > 0
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
+@pytest.mark.parametrize("monolayer", [False, True])
+def test_calc_velocity_noncon(ctx, oracle, monolayer):
+    """alens_calc_velocity_noncon = SylinderSystem::calcVelocityNonCon (SylinderSystem.cpp:724-800): M f + vNB + vB with the
+    monolayer mask, resident for the solve that follows (compared with a solve that is handed the host vector)."""
+    rods, orods, blocks = setup_case(ctx, oracle, n=1500, seed=41, frac_sphere=0.2, frac_immovable=0.1)
+    n = len(rods["gid"])
+    rng = np.random.default_rng(7)
+    f, vnb, vb = rng.normal(size=6 * n), rng.normal(size=6 * n), rng.normal(size=6 * n)
+    M = oracle.build_mobility(orods, rods["immovable"], MU)
+    mask = np.ones(6 * n)
+    if monolayer:
+        mask.reshape(-1, 6)[:, [2, 3, 4]] = 0
+    want_nb = (M @ f) * mask + vnb * mask
+    want = want_nb + vb * mask
+    got_nb = ctx.calc_velocity_noncon(f, vnb, vb, monolayer)
+    assert relerr(got_nb, want_nb) < 1e-13
+    rep = ctx.solve_constraints(None, DT, 1e-30, 10, 0)          # the resident vector
+    g_res = ctx.get_gamma()
+    rep2 = ctx.solve_constraints(want, DT, 1e-30, 10, 0)         # the same vector from the host
+    assert rep.iterations == rep2.iterations == 10
+    assert relerr(g_res, ctx.get_gamma()) < 1e-10
+    only_v = ctx.calc_velocity_noncon(None, vnb, None, monolayer)  # absent terms
+    assert np.array_equal(only_v, vnb * mask + 0.0)
