@@ -34,7 +34,7 @@ EXPORTS = [
     "alens_get_rod_state", "alens_get_timers", "alens_reset_timers", "alens_get_collect_stats",
     "alens_set_decomposition", "alens_comm_create", "alens_comm_blob_size", "alens_comm_export",
     "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
-    "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral", "alens_calc_velocity_noncon",
+    "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral", "alens_calc_velocity_noncon", "alens_calc_velocity_brown",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
 ]
 
@@ -210,6 +210,13 @@ class Context:
         n = C.c_longlong(0)
         self._call("alens_collect_boundary_collision", C.c_void_p(b.ctypes.data), C.c_int(len(b)), C.byref(n))
         return n.value
+
+    def calc_velocity_brown(self, kbt, dt, normals12=None, seed=0, step=0):
+        w = None if normals12 is None else np.ascontiguousarray(normals12, dtype=np.float64)
+        out = np.zeros(6 * self.n_rods)
+        self._call("alens_calc_velocity_brown", C.c_double(kbt), C.c_double(dt), _dp(w), C.c_ulonglong(seed),
+                   C.c_ulonglong(step), _dp(out))
+        return out
 
     def calc_velocity_noncon(self, force_nonbrown=None, vel_nonbrown=None, vel_brown=None, monolayer=False):
         """velNonCon = M f + vNB + vB on the device, kept resident; returns M f + vNB (Sylinder::velNonB / omegaNonB)"""

@@ -209,6 +209,11 @@ int alens_set_velocity_noncon(alens_ctx *ctx, const double *v) {
     });
 }
 
+int alens_calc_velocity_brown(alens_ctx *ctx, double kBT, double dt, const double *normals12, unsigned long long seed,
+                              unsigned long long step, double *velBrownOut) {
+    return guarded(ctx, [&](Context &c) { calcVelocityBrown(c, kBT, dt, normals12, seed, step, velBrownOut); });
+}
+
 int alens_calc_velocity_noncon(alens_ctx *ctx, const double *forceNonBrown, const double *velocityNonBrown,
                                const double *velocityBrown, int monolayer, double *velNonBOut) {
     return guarded(ctx, [&](Context &c) {

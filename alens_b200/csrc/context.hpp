@@ -349,6 +349,7 @@ inline void waitVelNC(Context &c) {
         c.velNCPending = false;
     }
 }
+void calcVelocityBrown(Context &c, double kBT, double dt, const double *normals12, unsigned long long seed, unsigned long long step, double *out);
 void calcVelocityNonCon(Context &c, const double *force, const double *velNB, const double *velB, int monolayer, double *velNonBOut);
 long long collectBoundary(Context &c, const alens_boundary *bnd, int nb);
 long long collectLinks(Context &c, const int *prevGid, const int *nextGid, long long nLinks, double linkKappa, double linkGap);

@@ -97,6 +97,111 @@ __global__ void k_mob_apply_user(MobIn m, const int *__restrict__ userToSorted, 
     for (int c = 0; c < 6; c++) y[6 * u + c] = o[c];
 }
 
+// ------------------------------------------------------------------------------------------------
+// calcVelocityBrown (SylinderSystem.cpp:1020-1091).  Counter-based normals: Philox4x32-10 (Salmon et al. 2011) with
+// key = (seed, step) and counter = (gid, draw block), two Box-Muller pairs per block.
+__device__ __forceinline__ void philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                           unsigned out[4]) {
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1,
+                       n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void normals4(unsigned long long seed, unsigned long long step, int gid, int block, double w[4]) {
+    unsigned r[4];
+    philox4x32((unsigned)gid, (unsigned)block, (unsigned)step, (unsigned)(step >> 32), (unsigned)seed, (unsigned)(seed >> 32), r);
+    for (int h = 0; h < 2; h++) { // Box-Muller on (0, 1] x [0, 1)
+        const double u1 = ((double)r[2 * h] + 1.0) * (1.0 / 4294967296.0), u2 = (double)r[2 * h + 1] * (1.0 / 4294967296.0);
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        w[2 * h] = rad * cs;
+        w[2 * h + 1] = rad * sn;
+    }
+}
+// q * (0,0,1) (Eigen quaternion rotation: v + w uv + q.vec x uv, uv = 2 q.vec x v)
+__device__ __forceinline__ void quatZ(const double q[4], double d[3]) {
+    const double ux = q[1] + q[1], uy = -(q[0] + q[0]);
+    d[0] = q[3] * ux + (-(q[2] * uy));
+    d[1] = q[3] * uy + q[2] * ux;
+    d[2] = 1.0 + (q[0] * uy - q[1] * ux);
+}
+__global__ void k_velocity_brown(int nLocal, const int *__restrict__ userToSorted, const int *__restrict__ uGid,
+                                 const double *__restrict__ uQuat, const double *__restrict__ invDrag, size_t stride,
+                                 double kBT, double dt, const double *__restrict__ normals, unsigned long long seed,
+                                 unsigned long long step, double *__restrict__ out) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nLocal) return;
+    const int s = userToSorted[u];
+    const double a = invDrag[s], b = invDrag[stride + s], cR = invDrag[2 * stride + s]; // 1/zPara, 1/zPerp, 1/zRot
+    double W[12];
+    if (normals) {
+        for (int k = 0; k < 12; k++) W[k] = normals[12 * (size_t)u + k];
+    } else {
+        for (int blk = 0; blk < 3; blk++) normals4(seed, step, uGid[u], blk, W + 4 * blk);
+    }
+    const double *Wrot = W, *Wpos = W + 3, *Wrfdrot = W + 6, *Wrfdpos = W + 9;
+    const double delta = dt * 0.1, kBTfactor = sqrt(2 * kBT / dt);
+    double q4[4] = {uQuat[4 * (size_t)u], uQuat[4 * (size_t)u + 1], uQuat[4 * (size_t)u + 2], uQuat[4 * (size_t)u + 3]};
+    double d[3];
+    quatZ(q4, d);
+    double N[3][3], L[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) N[i][j] = (a - b) * (d[i] * d[j]) + b * (i == j ? 1.0 : 0.0);
+    // lower Cholesky factor as Eigen's unblocked LLT: stops at a non-positive pivot, leaving the input's entries (a zero
+    // matrix -- immovable rod -- stays zero)
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) L[i][j] = j <= i ? N[i][j] : 0.0;
+    for (int k = 0; k < 3; k++) {
+        double x = L[k][k];
+        for (int j = 0; j < k; j++) x -= L[k][j] * L[k][j];
+        if (x <= 0) break;
+        x = sqrt(x);
+        L[k][k] = x;
+        for (int i = k + 1; i < 3; i++) {
+            double v = L[i][k];
+            for (int j = 0; j < k; j++) v -= L[i][j] * L[k][j];
+            L[i][k] = v / x;
+        }
+    }
+    // orientation rotated by Wrfdrot * delta (EquatnHelper::rotateEquatn, Util/EquatnHelper.hpp:74-90)
+    {
+        const double ox = Wrfdrot[0], oy = Wrfdrot[1], oz = Wrfdrot[2];
+        const double w = sqrt(ox * ox + oy * oy + oz * oz);
+        if (!(w < (double)FLT_EPSILON)) {
+            const double winv = 1 / w, sw = sin(w * delta / 2), cw = cos(w * delta / 2);
+            const double sc = q4[3], px = q4[0], py = q4[1], pz = q4[2];
+            const double cx = oy * pz - oz * py, cy = oz * px - ox * pz, cz = ox * py - oy * px;
+            const double nx = sc * sw * ox * winv + cw * px + sw * winv * cx;
+            const double ny = sc * sw * oy * winv + cw * py + sw * winv * cy;
+            const double nz = sc * sw * oz * winv + cw * pz + sw * winv * cz;
+            const double nw = sc * cw - (px * ox + py * oy + pz * oz) * sw * winv;
+            const double nn = sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+            q4[0] = nx / nn; q4[1] = ny / nn; q4[2] = nz / nn; q4[3] = nw / nn;
+        }
+    }
+    double dr[3];
+    quatZ(q4, dr);
+    double vel[3];
+    for (int i = 0; i < 3; i++) {
+        double g = 0, r = 0;
+        for (int j = 0; j <= i; j++) g += L[i][j] * Wpos[j];
+        for (int j = 0; j < 3; j++) {
+            const double nr = (a - b) * (dr[i] * dr[j]) + b * (i == j ? 1.0 : 0.0);
+            r += (nr - N[i][j]) * Wrfdpos[j];
+        }
+        vel[i] = kBTfactor * g + (kBT / delta) * r;
+    }
+    const double so = sqrt(cR) * kBTfactor;
+    double *o = out + 6 * (size_t)u;
+    o[0] = vel[0]; o[1] = vel[1]; o[2] = vel[2];
+    o[3] = so * Wrot[0]; o[4] = so * Wrot[1]; o[5] = so * Wrot[2];
+}
+
 // calcVelocityNonCon (SylinderSystem.cpp:724-800): vNC = M f + vNB + vB per local rod in the caller's order; the monolayer
 // mask zeroes v_z, omega_x, omega_y of every term (:737-743, :762-769, :789-797); updates are 1.0 * A + 1.0 * Y
 __global__ void k_velocity_noncon(MobIn m, int nLocal, const int *__restrict__ userToSorted, const double *__restrict__ force,
@@ -1614,6 +1719,27 @@ void mobilityApply(Context &c, const double *x, double *y) {
     ALENS_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+void calcVelocityBrown(Context &c, double kBT, double dt, const double *normals12, unsigned long long seed,
+                       unsigned long long step, double *out) {
+    if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_calc_velocity_brown: call alens_set_rods first"};
+    if (!c.haveMob) throw ArgError{ALENS_ERR_STATE, "alens_calc_velocity_brown: call alens_calc_mobility first"};
+    if (!(dt > 0) || !(kBT >= 0)) throw ArgError{ALENS_ERR_ARG, "alens_calc_velocity_brown: dt > 0 and kBT >= 0 required"};
+    if (!out) throw ArgError{ALENS_ERR_ARG, "alens_calc_velocity_brown: NULL output"};
+    cudaStream_t st = c.stream;
+    const int n = c.nLocal;
+    if (n == 0) return;
+    c.vTmp0.reserve(12 * (size_t)n + 12);
+    c.vTmp1.reserve(6 * (size_t)n + 6);
+    if (normals12) ALENS_CUDA(cudaMemcpyAsync(c.vTmp0.p, normals12, 96 * (size_t)n, cudaMemcpyHostToDevice, st));
+    k_velocity_brown<<<gridFor(n, 128), 128, 0, st>>>(n, c.userToSorted.p, c.uGid.p, c.uQuat.p, c.sInvDrag.p,
+                                                      mobStride(c.nRods), kBT, dt, normals12 ? c.vTmp0.p : nullptr, seed,
+                                                      step, c.vTmp1.p);
+    c.launches++;
+    ALENS_CUDA(cudaMemcpyAsync(out, c.vTmp1.p, 48 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaGetLastError());
+    ALENS_CUDA(cudaStreamSynchronize(st));
+}
+
 void calcVelocityNonCon(Context &c, const double *force, const double *velNB, const double *velB, int monolayer,
                         double *velNonBOut) {
     if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_calc_velocity_noncon: call alens_set_rods first"};
@@ -2444,6 +2570,7 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_rod_sum<true, false>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_rod_sum<false, true>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_velocity_noncon));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_velocity_brown));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit_rm));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<false>));

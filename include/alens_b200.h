@@ -175,6 +175,16 @@ int alens_set_velocity_noncon(alens_ctx *ctx, const double *velNonCon);
  * (each term optional: NULL = absent; host arrays of 6n doubles in local rod order; needs alens_calc_mobility).
  * monolayer != 0 zeroes v_z, omega_x, omega_y of every term as the reference does.  velNonBOut (optional, 6n host doubles)
  * receives M forceNonBrown + velocityNonBrown, what the reference writes to Sylinder::velNonB / omegaNonB. */
+/* SylinderSystem::calcVelocityBrown (SylinderSystem.cpp:1020-1091): random finite difference scheme of Delong et al. per
+ * rod -- N = (1/zPara - 1/zPerp) q q^T + 1/zPerp I, v = sqrt(2 kBT/dt) chol(N) W_pos + (kBT/delta) (N_rfd - N) W_rfdpos with
+ * delta = 0.1 dt and N_rfd at the orientation rotated by W_rfdrot * delta, omega = sqrt(1/zRot) sqrt(2 kBT/dt) W_rot.
+ * normals12: 12 standard normal deviates per local rod in the reference's draw order (W_rot, W_pos, W_rfdrot, W_rfdpos;
+ * hand in the host application's own stream to reproduce its run), or NULL: drawn on the device from a counter-based
+ * Philox4x32-10 generator keyed by (seed, step, rod gid), independent of rod order and of the number of GPUs.
+ * velBrownOut: 6n host doubles (velBrown, omegaBrown per rod); pass it to alens_calc_velocity_noncon.
+ * Needs alens_calc_mobility (the viscosity given there). */
+int alens_calc_velocity_brown(alens_ctx *ctx, double kBT, double dt, const double *normals12, unsigned long long seed,
+                              unsigned long long step, double *velBrownOut);
 int alens_calc_velocity_noncon(alens_ctx *ctx, const double *forceNonBrown, const double *velocityNonBrown,
                                const double *velocityBrown, int monolayer, double *velNonBOut);
 /* Same, without waiting for the copy: it runs on a side stream and overlaps whatever the caller does next

@@ -22,6 +22,7 @@
 class SylinderSystem {
     alens_ctx *ctx_ = nullptr;
     int stepCount = 0;
+    bool brownianOnDevice = false; // runStep() calls calcVelocityBrown() itself when KBT > 0 (else: setVelocityBrown)
     std::vector<Sylinder> sylinderContainer;
     std::shared_ptr<ConstraintSolver> conSolverPtr;
     std::shared_ptr<ConstraintCollector> conCollectorPtr;
@@ -269,7 +270,19 @@ class SylinderSystem {
         }
     }
 
-    void runStep(bool count_flag = true) { // :948-969 (Brownian velocity and writeResult are the host's business)
+    // :1020-1091 on the device.  The reference draws from per-thread TRNG streams (schedule dependent); here the deviates
+    // come from a counter-based generator keyed by (rngSeed, stepCount, gid).  A host application that must reproduce
+    // its own stream calls setVelocityBrown() with its numbers instead (or alens_calc_velocity_brown with `normals12`).
+    void calcVelocityBrown() {
+        const int nLocal = (int)sylinderContainer.size();
+        std::vector<double> v(6 * (size_t)nLocal, 0.0);
+        ck(alens_calc_velocity_brown(ctx_, runConfig.KBT, runConfig.dt, nullptr, (unsigned long long)runConfig.rngSeed,
+                                     (unsigned long long)stepCount, v.data()));
+        velocityBrownRcp = getTVFromVector(v, commRcp);
+    }
+
+    void runStep(bool count_flag = true) { // :948-969 (writeResult is the host's business)
+        if (runConfig.KBT > 0 && brownianOnDevice) calcVelocityBrown();
         calcVelocityNonCon();
         resolveConstraints();
         sumForceVelocity();

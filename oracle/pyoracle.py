@@ -279,6 +279,43 @@ def drag_coeff(radius, length, mu):
     return a.value, b.value, c.value
 
 
+def velocity_brown(quat, radius, length, immovable, mu, kbt, dt, normals12):
+    """SylinderSystem::calcVelocityBrown (SylinderSystem.cpp:1020-1091) for given N(0,1) draws (12 per rod, in the
+    reference's draw order Wrot, Wpos, Wrfdrot, Wrfdpos), plain numpy per rod.  Returns 6n (velBrown, omegaBrown)."""
+    quat = np.asarray(quat, dtype=np.float64)
+    W = np.asarray(normals12, dtype=np.float64).reshape(-1, 12)
+    n = len(quat)
+    out = np.zeros((n, 6))
+    delta, fac = dt * 0.1, np.sqrt(2 * kbt / dt)
+
+    def rot_z(q):  # Eigen: q * (0,0,1), q = (x, y, z, w)
+        x, y, z, w = q
+        return np.array([2 * (w * y + x * z), 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)])
+
+    def rotate(q, omega, t):  # EquatnHelper::rotateEquatn (Util/EquatnHelper.hpp:74-90)
+        w = np.linalg.norm(omega)
+        if w < np.finfo(np.float32).eps:
+            return q
+        sw, cw, p, s = np.sin(w * t / 2), np.cos(w * t / 2), q[:3], q[3]
+        xyz = s * sw * omega / w + cw * p + sw / w * np.cross(omega, p)
+        qw = s * cw - p.dot(omega) * sw / w
+        qn = np.concatenate([xyz, [qw]])
+        return qn / np.linalg.norm(qn)
+
+    for i in range(n):
+        zp, zq, zr = drag_coeff(float(radius[i]), float(length[i]), mu)
+        a, b, c = (0.0, 0.0, 0.0) if immovable[i] else (1 / zp, 1 / zq, 1 / zr)
+        d = rot_z(quat[i])
+        N = (a - b) * np.outer(d, d) + b * np.eye(3)
+        L = np.linalg.cholesky(N) if not immovable[i] else np.zeros((3, 3))  # Eigen's LLT leaves a zero matrix untouched
+        Wrot, Wpos, Wrr, Wrp = W[i, 0:3], W[i, 3:6], W[i, 6:9], W[i, 9:12]
+        dr = rot_z(rotate(quat[i].copy(), Wrr, delta))
+        Nr = (a - b) * np.outer(dr, dr) + b * np.eye(3)
+        out[i, :3] = fac * (L @ Wpos) + (kbt / delta) * ((Nr - N) @ Wrp)
+        out[i, 3:] = np.sqrt(c) * fac * Wrot
+    return out.reshape(-1)
+
+
 def build_dtrans_dense(blocks, n_rods):
     """D^T as a scipy CSR (tests only)."""
     import scipy.sparse as sp

@@ -337,3 +337,39 @@ def test_calc_velocity_noncon(ctx, oracle, monolayer):
     assert relerr(g_res, ctx.get_gamma()) < 1e-10
     only_v = ctx.calc_velocity_noncon(None, vnb, None, monolayer)  # absent terms
     assert np.array_equal(only_v, vnb * mask + 0.0)
+
+
+def test_calc_velocity_brown(ctx, oracle):
+    """alens_calc_velocity_brown = SylinderSystem::calcVelocityBrown (SylinderSystem.cpp:1020-1091): with the caller's
+    normal deviates it reproduces the restated formula (1e-11: Cholesky / trig rounding); with the built-in counter-based
+    generator it is reproducible, keyed by gid (independent of rod order) and has the right second moments."""
+    n, mu, kbt, dt = 3000, 1.0, 0.00411, 1e-4
+    rods = random_rods(n, 3.0, seed=51, frac_sphere=0.2, frac_immovable=0.1)
+    def load(r):
+        ctx.set_domain([0.0] * 3, [3.0] * 3, (1, 1, 1))
+        ctx.set_collision_params(1.0, 1.0, 0.025)
+        ctx.set_rods(r["gid"], r["pos"], r["quat"], r["length"], r["radius"], r["immovable"])
+        ctx.calc_mobility(mu)
+    load(rods)
+    W = np.random.default_rng(5).normal(size=(n, 12))
+    got = ctx.calc_velocity_brown(kbt, dt, W)
+    want = oracle.velocity_brown(rods["quat"], rods["radius"], rods["length"], rods["immovable"], mu, kbt, dt, W)
+    assert relerr(got, want) < 1e-11
+    imm = np.repeat(rods["immovable"] != 0, 6)
+    assert np.all(got[imm] == 0) and np.abs(got[~imm]).min() > 0
+    # device generator: same (seed, step) -> same numbers; another step -> different; keyed by gid, not by storage order
+    a = ctx.calc_velocity_brown(kbt, dt, None, seed=1234, step=7)
+    b = ctx.calc_velocity_brown(kbt, dt, None, seed=1234, step=7)
+    c = ctx.calc_velocity_brown(kbt, dt, None, seed=1234, step=8)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    perm = np.random.default_rng(1).permutation(n)
+    load({k: v[perm] for k, v in rods.items()})
+    ap = ctx.calc_velocity_brown(kbt, dt, None, seed=1234, step=7)
+    assert np.array_equal(ap.reshape(n, 6), a.reshape(n, 6)[perm])
+    # second moments: <omega omega^T> = 2 kBT / (zRot dt) I for every movable rod (SylinderSystem.cpp:1066)
+    om = np.concatenate([ctx.calc_velocity_brown(kbt, dt, None, seed=99, step=s).reshape(n, 6)[:, 3:] for s in range(40)], axis=1)
+    from oracle import pyoracle as po
+    zr = np.array([po.drag_coeff(float(r), float(l), mu)[2] for r, l in zip(rods["radius"][perm], rods["length"][perm])])
+    mov = rods["immovable"][perm] == 0
+    ratio = (om[mov] ** 2).mean(axis=1) / (2 * kbt / (zr[mov] * dt))
+    assert abs(ratio.mean() - 1) < 0.02 and abs(om[mov].mean()) < 0.02 * np.sqrt((om[mov] ** 2).mean())
