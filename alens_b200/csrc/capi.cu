@@ -447,6 +447,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
         else if (k == "pdl") c.optPdl = (int)std::max(0LL, std::min(2LL, value));
         else if (k == "poll") c.optPoll = value != 0;
         else if (k == "lookahead") c.optLookahead = (int)std::max(1LL, std::min(64LL, value));
+        else if (k == "late_halo") c.optLateHalo = value != 0;
         else if (k == "keep_xg") c.optKeepXG = value != 0;
         else if (k == "force_mask") c.optForceMask = value != 0;
         else if (k == "force_waves") c.optForceWaves = (int)std::max(1LL, std::min(64LL, value));

@@ -279,6 +279,8 @@ struct Context {
     int optLookahead = 3;                   // iterations queued behind the running one
     bool pdlNow = false, profMute = false;  // state of the current solve
     int *hProg = nullptr, *hProgDev = nullptr; // {completed applies, done} in mapped pinned host memory
+    int optLateHalo = 1;                    // multi-GPU: k_bb_tail walks the rows that need no halo first and waits for the halo behind them
+    DevBuf<int> ghostRange;                 // [0], [1]: rows reading ghost velocities lie in [0, [0]) and [[1], nc)
     int optKeepXG = 1;                      // {x, g} pairs stored / gathered with the L2 evict_last policy
     int optForceMask = 1;                   // k_force_vel_act consults the tail kernel's "may be non-zero" bit mask before gathering {x, g}
     int optForceWaves = 1;                  // k_force_vel_act: grid = resident CTAs x this (1 = persistent)

@@ -353,9 +353,16 @@ __global__ void k_setup(long long nc, ConGeom g, const int *__restrict__ sUser, 
                         const double *__restrict__ delta0, const double *__restrict__ gamma0,
                         const double *__restrict__ invKappa, const unsigned char *__restrict__ bi, double invDt,
                         double *__restrict__ b, double *__restrict__ invKdt, double *__restrict__ lbFlag,
-                        double *__restrict__ x0) {
+                        double *__restrict__ x0, const unsigned char *__restrict__ ghost, int *__restrict__ ghostRange) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nc) return;
+    if (ghostRange) { // multi-GPU: rows that read a ghost rod's velocity lie in [0, ghostRange[0]) and [ghostRange[1], nc)
+        const int j = g.idxJ[k];
+        if (ghost[g.idxI[k]] || (j >= 0 && ghost[j])) {
+            if (k < nc / 2) atomicMax(&ghostRange[0], (int)k + 1);
+            else atomicMin(&ghostRange[1], (int)k);
+        }
+    }
     double dnc = 0;
     if (velNC) {
         const double gx = g.n[k], gy = g.n[k + g.stride], gz = g.n[k + 2 * g.stride];
@@ -1128,6 +1135,7 @@ struct BbTail {
     int histCap;
     double tol;
     int ite; // iteration number of this launch (0 = initial gradient)
+    const int *ghostRange;    // multi-GPU: rows reading ghost velocities are in [0, [0]) and [[1], nc) (k_setup); nullptr: unknown
     int pdlTrig;              // see FvAct
     int *prog;                // pinned host words {completed applies, done}: the host throttles its launches on them
     int keepXG;               // store {x, g} with the L2 evict_last policy (the force kernel gathers it next)
@@ -1337,29 +1345,45 @@ template <bool HASK>
 __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     const int done = p.scal->done;
     const double alpha = p.scal->alpha; // plain loads: every thread reads the same two words, which L1 broadcasts
-    const long long stride = (long long)gridDim.x * kVecBlock;
-    long long k = (long long)blockIdx.x * kVecBlock + threadIdx.x;
+    // Rows are walked in tiles of 256 (one per CTA trip, grid-stride).  Multi-GPU: the tiles are rotated so that the rows
+    // reading a ghost rod's velocity (the first and last rows when the slab axis is the slowest cell axis, k_setup) come
+    // LAST; the wait for the neighbours' halo sits in front of the first such tile, behind all the work that needs no halo.
+    const int nTiles = (int)((p.nc + kVecBlock - 1) / kVecBlock);
+    int shift = 0, nClean = 0;
+    if (p.waitSeq && p.ghostRange) {
+        const int g0 = p.ghostRange[0], g1 = p.ghostRange[1];
+        shift = min((g0 + kVecBlock - 1) / kVecBlock, nTiles);
+        nClean = max(0, g1 / kVecBlock - shift);
+    }
+    auto rowOf = [&](int tau) -> long long {
+        int tile = tau + shift;
+        if (tile >= nTiles) tile -= nTiles;
+        return (long long)tile * kVecBlock + threadIdx.x;
+    };
+    int tau = blockIdx.x;
+    long long k = tau < nTiles ? rowOf(tau) : p.nc;
     double s0 = 0, s1 = 0, s2 = 0, mx = 0;
     TailRow cur, nxt;
     if (k < p.nc) loadTailRow<HASK>(p, (size_t)k, cur); // all of it at least two kernels old (see pdlWait)
     pdlWait(); // U comes from the force kernel right in front
     if (p.pdlTrig) pdlLaunchDependents();
     if (done) return;
-    if (p.waitSeq) { // ghost rows of U: pushed by the neighbours' force kernels (the streaming loads above are in flight)
-        if (threadIdx.x == 0) {
-            if (p.waitFlag[0]) waitSeq(p.waitFlag[0], p.waitSeq, p.red.err);
-            if (p.waitFlag[1]) waitSeq(p.waitFlag[1], p.waitSeq, p.red.err);
-        }
-        __syncthreads();
-    }
-    // The loop condition is warp-uniform (first row of the warp), rows past the end are predicated off: every
-    // trip ends with a ballot that publishes, for the NEXT iteration's force kernel, which rows can be non-zero.
+    bool waited = p.waitSeq == 0;
     const int lane = threadIdx.x & 31;
     int nMaybe = 0; // rows of this warp whose bit is set (statistics for the roofline accounting of the force kernel)
     const unsigned long long keepPol = policyEvictLast();
-    while (k - lane < p.nc) {
+    while (tau < nTiles) {
+        if (!waited && tau >= nClean) { // ghost rows of U: pushed by the neighbours' force kernels (CTA-uniform test)
+            if (threadIdx.x == 0) {
+                if (p.waitFlag[0]) waitSeq(p.waitFlag[0], p.waitSeq, p.red.err);
+                if (p.waitFlag[1]) waitSeq(p.waitFlag[1], p.waitSeq, p.red.err);
+            }
+            __syncthreads();
+            waited = true;
+        }
         const bool valid = k < p.nc;
-        const long long kn = k + stride;
+        const int tauN = tau + gridDim.x;
+        const long long kn = tauN < nTiles ? rowOf(tauN) : p.nc;
         // (1) the six 16-byte gathers of this row's two U rows (L2 hits, needed first), unconditional and back to back:
         // a one-sided row gathers rod I twice, a lane past the end gathers row 0
         const int iI = valid ? cur.iI : 0;
@@ -1373,11 +1397,13 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
         if (kn < p.nc) loadTailRow<HASK>(p, (size_t)kn, nxt);
         bool on = false;
         if (valid) on = tailRowMath<HASK>(p, cur, two, k, alpha, a, b, c, d, e, f, keepPol, s0, s1, s2, mx);
+        // one ballot per 32 rows publishes, for the NEXT iteration's force kernel, which rows can be non-zero
         const unsigned mbits = __ballot_sync(0xffffffffu, on);
-        if (lane == 0 && p.maskOut) p.maskOut[k >> 5] = mbits;
+        if (lane == 0 && p.maskOut && k < p.nc) p.maskOut[k >> 5] = mbits;
         nMaybe += __popc(mbits);
         cur = nxt;
         k = kn;
+        tau = tauN;
     }
     tailEpilogue(p, s0, s1, s2, mx, nMaybe);
 }
@@ -1836,9 +1862,17 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
             k_inc_emit<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incRaw.p, conGeom(c), c.incCon.p,
                                                         c.incCol.p, (size_t)c.incStride);
         }
+        int *ghostRange = nullptr;
+        if (c.comm.active) { // where the rows that touch ghost rods sit: the tail kernel keeps them for last
+            c.ghostRange.reserve(2);
+            const int init[2] = {0, (int)nc};
+            ALENS_CUDA(cudaMemcpyAsync(c.ghostRange.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+            ALENS_CUDA(cudaStreamSynchronize(st)); // `init` lives on this stack frame
+            ghostRange = c.ghostRange.p;
+        }
         k_setup<<<gridFor(nc, 256), 256, 0, st>>>(nc, conGeom(c), c.sUser.p, useV ? c.uVelNC.p : nullptr,
                                                   c.cDelta0.p, c.cGamma0.p, c.cInvKappa.p, c.cBi.p, 1.0 / dt,
-                                                  c.vB.p, c.vTmp5.p, c.vLbFlag.p, c.vX0.p);
+                                                  c.vB.p, c.vTmp5.p, c.vLbFlag.p, c.vX0.p, c.sGhost.p, ghostRange);
         c.launches += 3;
     }
     ALENS_CUDA(cudaGetLastError());
@@ -2100,6 +2134,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     t.maskOut = c.optForceMask ? c.vMask.p : nullptr;
     t.keepXG = c.optKeepXG;
     t.pdlTrig = c.optPdl == 2;
+    t.ghostRange = (multi && c.optLateHalo && c.ghostRange.p) ? c.ghostRange.p : nullptr;
     if (multi) {
         t.own = c.cOwn.p;
         t.redOut = reinterpret_cast<double *>(c.dCounters.p); // 4 doubles of scratch
