@@ -35,7 +35,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from scenarios import box_for_volume_fraction, random_rods, thermal_velocity  # noqa: E402
 
 L_ROD, R_ROD, COLBUF, MU, DT, RES, MAXITE = 0.25, 0.0125, 0.025, 1.0, 1e-5, 1e-5, 10000
-SLAB_AXIS = 2  # multi-GPU runs: slabs along z
+SLAB_AXIS = 0  # multi-GPU runs: slabs along x (2: along z, the slowest cell axis -- see profiles/README.md, late_halo)
 SEED = 1234
 
 
@@ -232,15 +232,13 @@ def main():
 
     rods, box = make_workload(n, a.phi, SEED + rank)
     if world > 1:
-        # one global suspension: periodic box box x box x world*box, z-slab r owned by rank r (with z
-        # as the long axis: z is the slowest axis of the cell order, so the constraint rows that need the neighbours' halo are
-        # the first and last rows and the tail kernel can keep them for last); ghost rods within cutoff + skin of the slab
-        # faces are mirrored between neighbours every step
-        rods["pos"][:, 2] += rank * box
+        # one global suspension: periodic box, `world` boxes long along SLAB_AXIS, slab r owned by rank r (SURVEY.md 8d
+        # config 5); ghost rods within cutoff + skin of the slab faces are mirrored between neighbours every step
+        rods["pos"][:, SLAB_AXIS] += rank * box
         rods["gid"] = (rods["gid"] + rank * n).astype(np.int32)
         max_r = 0.5 * L_ROD + R_ROD
         skin = 0.5 * (2 * max_r + COLBUF)  # rods drift during the untimed relaxation steps
-        ctx.set_domain([0.0] * 3, [box, box, world * box], [1, 1, 1])
+        ctx.set_domain([0.0] * 3, [world * box if k == SLAB_AXIS else box for k in range(3)], [1, 1, 1])
         ctx.set_collision_params(1.0, 1.0, COLBUF)
         ctx.set_decomposition(SLAB_AXIS, rank * box, (rank + 1) * box, skin, max_r, rank * n)
         ctx.comm_create(int(1.25 * n))
@@ -392,7 +390,7 @@ def main():
         "config": {"workload": workload, "rods_per_gpu": n, "constraints": int(nc),
                    "bbpgd_iterations": int(rep.iterations), "residual": float(rep.residual),
                    "parallelism": "1 process per GPU" + ("" if world == 1 else (
-                       f", one periodic suspension of {world * n} rods in {world} z-slabs: ghost-rod exchange per step, "
+                       f", one periodic suspension of {world * n} rods in {world} {'xyz'[SLAB_AXIS]}-slabs: ghost-rod exchange per step, "
                        "U halo + 4-double allreduce per BBPGD iteration over NVLink peer memory; value = slab-steps/s "
                        "(global steps/s x GPUs)")),
                    "ghosts_rank0": ctx.num_ghosts() if world > 1 else None,
