@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <cstdio>
 #include <limits>
 
 #ifndef GEO_INVALID_INDEX
@@ -49,6 +50,32 @@ class Sylinder {
     bool isSphere(bool collision = false) const {
         return collision ? lengthCollision < radiusCollision * 2 : length < radius * 2;
     }
+    /// direction = orientation * (0,0,1) (Eigen quaternion rotation, SylinderNear.hpp:86)
+    void direction(double d[3]) const {
+        const double x = orientation[0], y = orientation[1], z = orientation[2], w = orientation[3];
+        const double ux = y + y, uy = -(x + x);
+        d[0] = w * ux + (-(z * uy));
+        d[1] = w * uy + z * ux;
+        d[2] = 1.0 + (x * uy - y * ux);
+    }
+    /// one line of SylinderAscii_*.dat, the format the reference reads back (Sylinder.cpp:101-109,
+    /// SylinderSystem.cpp:317-344): `C|S gid radius minus[3] plus[3] group`
+    void writeAscii(FILE *fptr) const {
+        double d[3];
+        direction(d);
+        const char typeChar = isImmovable ? 'S' : 'C';
+        std::fprintf(fptr, "%c %d %.8g %.8g %.8g %.8g %.8g %.8g %.8g %d\n", typeChar, gid, radius, //
+                     pos[0] - 0.5 * length * d[0], pos[1] - 0.5 * length * d[1], pos[2] - 0.5 * length * d[2],
+                     pos[0] + 0.5 * length * d[0], pos[1] + 0.5 * length * d[1], pos[2] + 0.5 * length * d[2], group);
+    }
+};
+
+/// header of SylinderAscii_*.dat (Sylinder.hpp:459-464)
+class SylinderAsciiHeader {
+  public:
+    int nparticle = 0;
+    double time = 0;
+    void writeAscii(FILE *fp) const { std::fprintf(fp, "%d \n %lf\n", nparticle, time); }
 };
 
 static_assert(sizeof(Sylinder) == 568, "Sylinder record must keep the reference layout");

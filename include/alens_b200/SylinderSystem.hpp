@@ -9,6 +9,7 @@
 #ifndef ALENS_B200_SYLINDERSYSTEM_HPP_
 #define ALENS_B200_SYLINDERSYSTEM_HPP_
 
+#include <cstdio>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -194,6 +195,19 @@ class SylinderSystem {
         for (const auto &l : links) linkMap.emplace(l.prev, l.next);
     }
     const std::multimap<int, int> &getLinkMap() const { return linkMap; }
+
+    /// SylinderAscii_<snapID>.dat (SylinderSystem.cpp:489-507): header, one line per rod, then the links `L prev next`
+    void writeAscii(const std::string &fileName) const {
+        FILE *fptr = std::fopen(fileName.c_str(), "w");
+        if (!fptr) throw std::runtime_error("writeAscii: cannot open " + fileName);
+        SylinderAsciiHeader header;
+        header.nparticle = (int)sylinderContainer.size();
+        header.time = stepCount * runConfig.dt;
+        header.writeAscii(fptr);
+        for (const auto &sy : sylinderContainer) sy.writeAscii(fptr);
+        for (const auto &kv : linkMap) std::fprintf(fptr, "L %d %d\n", kv.first, kv.second);
+        std::fclose(fptr);
+    }
 
     void collectLinkBilateral() { // :1386-1482, on the device (gid lookup = device hash table instead of the ZDD directory)
         if (linkMap.empty()) return;
