@@ -373,7 +373,7 @@ void commExchangeGhostIndices(Context &c) {
         if (m.nSend[d] > 0)
             k_map_indices<<<gridFor(m.nSend[d], 256), 256, 0, st>>>(m.nSend[d], m.sendIdx[d].p, c.userToSorted.p,
                                                                    m.sendSorted[d].p);
-    // per-rod mirror rows for the fused halo push of k_force_vel_lm
+    // per-rod mirror rows for the fused halo push of the force kernel
     for (int d = 0; d < 2; d++) {
         m.mirror[d].reserve((size_t)c.nRods + 1);
         if (c.nRods > 0) k_fill_int<<<gridFor(c.nRods, 256), 256, 0, st>>>(c.nRods, -1, m.mirror[d].p);
@@ -419,7 +419,8 @@ void commHaloVelNC(Context &c) {
     ALENS_CUDA(cudaGetLastError());
 }
 
-// fused path: k_force_vel_lm has stored the mirrored rows; release the sequence number on both neighbours
+// fused path with the dense force kernel (force_kernel = 0): it has stored the mirrored rows; release the sequence
+// number on both neighbours (k_force_vel_act does this itself, in its last CTA)
 void commSignalHalo(Context &c, unsigned long long seq) {
     unsigned long long *sf[2] = {nullptr, nullptr};
     for (int d = 0; d < 2; d++) {

@@ -118,7 +118,7 @@ struct SolverScalars {
     int done;          // 1 converged, 2 stagnated, 3 projection error
     int nhist;         // history rows written
     unsigned int ticket;   // last-block election counter of k_bb_tail
-    unsigned int ticketFv; // ... of k_force_vel_lm (fused halo push)
+    unsigned int ticketFv; // ... of the force kernel (fused halo push: the last CTA releases the neighbours' flags)
     unsigned long long maybeAcc;  // rows marked "may be non-zero" by the running k_bb_tail
     unsigned long long maybeRows; // ... by the last completed one
     unsigned long long maybeSum;  // ... summed over the applies of this solve
@@ -256,7 +256,7 @@ struct Context {
 
     // ---- incidence (rod -> constraints), built in setup ----
     DevBuf<int> incDeg, incStart, incFill; // nRods(+1)
-    DevBuf<int> incCon;                    // 4*constraint + 2*bilateral + side per slot, level-major inside a 32-rod group
+    DevBuf<int> incCon;                    // 4*constraint + 2*bilateral + side per slot; rod-major (force_kernel 1/2) or level-major inside a 32-rod group (0)
     DevBuf<int> incRaw;                    // rod-major slot lists before k_inc_emit
     DevBuf<double> incCol;                 // 6 per slot: D column block for that (rod, constraint)
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)

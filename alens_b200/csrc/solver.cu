@@ -7,12 +7,16 @@
 //
 // D is never materialised as CSR.  A constraint k stores (n, posI, posJ, idxI, idxJ); row k of D^T is
 // [n, posI x n] on rod I and [-n, posJ x (-n)] on rod J (ConstraintCollector.cpp:298-341 with normJ = -normI).
-//   k_force_vel_lm : f = D x over the level-major rod -> constraint incidence, u = M f applied analytically from
-//                 (q, 1/drag) -- one launch per operator apply.  Inside the BBPGD loop x is not read but
-//                 recomputed on the fly as P(x_prev - alpha g_prev) from the interleaved {x, g} pairs
+//   k_force_vel_act : f = D x over the rod -> constraint incidence (rod-major slots, 48-byte column records), touching
+//                 only the slots whose multiplier can be non-zero (bit mask from k_bb_tail); u = M f applied analytically
+//                 from (q, 1/drag) -- one launch per operator apply.  Inside the BBPGD loop x is not read but recomputed
+//                 on the fly as P(x_prev - alpha g_prev) from the interleaved {x, g} pairs.  (k_force_vel_lm: the dense
+//                 level-major predecessor, force_kernel = 0; k_slot_x + k_rod_sum: a two-kernel form, force_kernel = 2.)
 //   k_bb_tail   : x = P(x_prev - alpha g_prev) again (same arithmetic, same bits), y = D^T u + K^-1 x, g = y + b,
-//                 projected-gradient residual, BB dot products, deterministic two-level reduction,
-//                 step-size/termination logic in the last CTA.  One BBPGD iteration = these two launches.
+//                 projected-gradient residual, BB dot products, the may-be-non-zero bit of every row, deterministic
+//                 two-level reduction, step-size/termination logic (and, multi-GPU, the mailbox allreduce) in the last
+//                 CTA.  One BBPGD iteration = these two launches, chained with programmatic dependent launch; the host
+//                 follows the loop through two progress words in pinned memory.
 // Compiled with -fmad=false so that elementwise arithmetic rounds like the CPU restatement.
 #include "context.hpp"
 #include "comm_dev.cuh"

@@ -225,12 +225,15 @@ int alens_get_timers(alens_ctx *ctx, alens_timers *t);
  * into alens_timers.op_*_ms (the reference's ConstraintOperator::* Teuchos timers) */
 int alens_set_profiling(alens_ctx *ctx, int on);
 int alens_reset_timers(alens_ctx *ctx);
-/* tuning knobs (no effect on results): "force_pipe" 0/1 selects k_force_vel / k_force_vel_pipe for the
- * operator's D x + M step; "tail_ctas_per_sm" sizes the persistent grid of k_bb_tail; "bbpgd_batch" = BBPGD
- * iterations enqueued between two host-side convergence checks (0 = automatic) */
+/* tuning knobs, none of which changes a result bit (INTEGRATION.md 4b lists them with their defaults): "force_kernel"
+ * 1 sparse k_force_vel_act / 0 dense k_force_vel_lm / 2 k_slot_x + k_rod_sum for the operator's D x + M step;
+ * "find_split" 1/0 register-split / single-kernel pair search; "pdl", "poll", "lookahead" launch structure of the BBPGD
+ * loop; "tail_ring" TMA-staged tail; "tail_ctas_per_sm" persistent grid of k_bb_tail ("bbpgd_batch" = iterations
+ * between two host checks when "poll" is 0) */
 int alens_set_option(alens_ctx *ctx, const char *name, long long value);
-/* average device time (CUDA events) of `reps` back-to-back launches of one BBPGD kernel -- "force_vel",
- * "tail" or "update" -- on the operator of the last alens_setup_constraints.  Invalidates the setup. */
+/* average device time (CUDA events) of `reps` back-to-back launches of one BBPGD kernel -- "force_vel", "tail",
+ * "force_vel_plain" on the operator of the last alens_setup_constraints (invalidates the setup), or "force_vel_last" on
+ * the iterate / mask the last BBPGD solve left behind. */
 int alens_time_kernel(alens_ctx *ctx, const char *which, int reps, double *avgMicroseconds);
 /* number of rods / cells / candidate pairs that passed the broad phase in the last collection */
 int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCandidates, long long *nHits);
