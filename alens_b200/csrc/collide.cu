@@ -973,7 +973,6 @@ void collectPairs(Context &c) {
     c.hitList.reserve(4 * (size_t)std::max(c.nRods, 256));
     const int ctas = gridFor(g.ncell, kWarpsPerCta);
     long long total = 0;
-    PairOut out{}; // filled once the constraint arrays have their size
     auto pairOut = [&]() {
         return PairOut{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cOwn.p, c.cDelta0.p,
                        c.cGamma0.p, c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
@@ -1066,7 +1065,7 @@ void collectPairs(Context &c) {
             c.launches++;
         }
     }
-    (void)out;
+
     ALENS_CUDA(cudaGetLastError());
     c.nCon = c.nColl = total;
 }

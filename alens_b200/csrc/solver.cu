@@ -684,7 +684,6 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
     __shared__ unsigned short sSlot[kActWarps][kActBatch]; // queued slots, relative to the batch base
     __shared__ double sProd[kActWarps][2][6][32];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1;
     constexpr int PER = kActBatch / 32;
     const int nGroups = (in.nRods + 31) >> 5;
     const int gStride = gridDim.x * kActWarps;
