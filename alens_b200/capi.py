@@ -36,6 +36,7 @@ EXPORTS = [
     "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
     "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral", "alens_calc_velocity_noncon", "alens_calc_velocity_brown",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
+    "alens_dcp_query", "alens_pair_functor",
 ]
 
 
@@ -196,6 +197,26 @@ class Context:
         self._call("alens_set_rods_aos", C.c_int(n), C.c_void_p(buf.ctypes.data), C.c_size_t(stride),
                    C.c_int(1 if wrap else 0))
         self.n_rods = n
+
+    # ---- the narrow phase by itself
+    def dcp_query(self, P0, P1, Q0, Q1):
+        """DCPQuery on n segment pairs (n x 3 arrays): returns dist[n], Ploc[n,3], Qloc[n,3]"""
+        a = [np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3) for x in (P0, P1, Q0, Q1)]
+        n = len(a[0])
+        dist, P, Q = np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3))
+        self._call("alens_dcp_query", C.c_longlong(n), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(dist), _dp(P), _dp(Q))
+        return dist, P, Q
+
+    def pair_functor(self, geomI, geomJ, with_stress=True):
+        """the functor body on n (I, J) pairs; geom = n x 9 {pos, direction, lengthCollision, radiusCollision, colBuf}"""
+        gi = np.ascontiguousarray(geomI, dtype=np.float64).reshape(-1, 9)
+        gj = np.ascontiguousarray(geomJ, dtype=np.float64).reshape(-1, 9)
+        n = len(gi)
+        hit = np.zeros(max(n, 1), dtype=np.uint8)
+        blocks = np.zeros(max(n, 1), dtype=BLOCK_DTYPE)
+        self._call("alens_pair_functor", C.c_longlong(n), _dp(gi), _dp(gj), C.c_int(1 if with_stress else 0),
+                   hit.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_void_p(blocks.ctypes.data))
+        return hit[:n].astype(bool), blocks[:n]
 
     def prepare_step(self, wrap=True):
         self._call("alens_prepare_step", C.c_int(1 if wrap else 0))

@@ -513,12 +513,117 @@ void downloadBlocks(Context &c, alens_constraint_block *out, long long cap, bool
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Batch entry points of the narrow phase itself (the reference exposes both as public functors:
+// DCPQuery<3,double,Evec3>::operator(), Collision/DCPQuery.hpp:199-308, and
+// CalcSylinderNearForce::operator() / collideStress, Sylinder/SylinderNear.hpp:197-519, the latter also
+// called from SRC/TubuleSystem.cpp:738).  One independent query per thread, no neighbour search.
+__global__ void k_dcp_batch(long long n, const double *__restrict__ seg, double *__restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double *s = seg + 12 * k; // P0 P1 Q0 Q1
+    Vec3 P, Q;
+    const double d = segSegClosest(v3(s[0], s[1], s[2]), v3(s[3], s[4], s[5]), v3(s[6], s[7], s[8]), v3(s[9], s[10], s[11]), P, Q);
+    double *o = out + 7 * k;
+    o[0] = d;
+    o[1] = P.x; o[2] = P.y; o[3] = P.z;
+    o[4] = Q.x; o[5] = Q.y; o[6] = Q.z;
+}
+
+// geom: 9 doubles per rod {pos[3], direction[3], lengthCollision, radiusCollision, colBuf}
+__global__ void k_pair_functor_batch(long long n, const double *__restrict__ gI, const double *__restrict__ gJ, int withStress,
+                                     unsigned char *__restrict__ hit, alens_constraint_block *__restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double *a = gI + 9 * k, *b = gJ + 9 * k;
+    RodGeom A{v3(a[0], a[1], a[2]), v3(a[3], a[4], a[5]), a[6], a[7]};
+    RodGeom B{v3(b[0], b[1], b[2]), v3(b[3], b[4], b[5]), b[6], b[7]};
+    const double buffer = a[8] > b[8] ? a[8] : b[8]; // std::max(colBufI, colBufJ), SylinderNear.hpp:268,322,391
+    Contact ct;
+    alens_constraint_block blk;
+    memset(&blk, 0, sizeof(blk));
+    const bool h = pairContact(A, B, buffer, ct);
+    hit[k] = h ? 1 : 0;
+    if (h) {
+        blk.delta0 = ct.sep;
+        blk.gamma = ct.sep < 0 ? -ct.sep : 0;
+        blk.gidI = blk.globalIndexI = (int)(2 * k);
+        blk.gidJ = blk.globalIndexJ = (int)(2 * k + 1);
+        const double nn[3] = {ct.normI.x, ct.normI.y, ct.normI.z};
+        const double pi[3] = {ct.posI.x, ct.posI.y, ct.posI.z}, pj[3] = {ct.posJ.x, ct.posJ.y, ct.posJ.z};
+        const double li[3] = {ct.labI.x, ct.labI.y, ct.labI.z}, lj[3] = {ct.labJ.x, ct.labJ.y, ct.labJ.z};
+        for (int c = 0; c < 3; c++) {
+            blk.normI[c] = nn[c]; blk.normJ[c] = -nn[c];
+            blk.posI[c] = pi[c]; blk.posJ[c] = pj[c];
+            blk.labI[c] = li[c]; blk.labJ[c] = lj[c];
+        }
+        if (withStress) {
+            const bool sa = A.lc < 2 * A.rc, sb = B.lc < 2 * B.rc;
+            const Vec3 ez = v3(0, 0, 1);
+            if (sa && sb) collideStress(ez, ez, A.c, B.c, 0, 0, A.lc * 0.5 + A.rc, B.lc * 0.5 + B.rc, 1.0, ct.labI, ct.labJ, blk.stress);
+            else if (sa) collideStress(ez, B.d, A.c, B.c, 0, B.lc, A.lc * 0.5 + A.rc, B.rc, 1.0, ct.labI, ct.labJ, blk.stress);
+            else if (sb) collideStress(ez, A.d, B.c, A.c, 0, A.lc, B.lc * 0.5 + B.rc, A.rc, 1.0, ct.labJ, ct.labI, blk.stress);
+            else collideStress(A.d, B.d, A.c, B.c, A.lc, B.lc, A.rc, B.rc, 1.0, ct.labI, ct.labJ, blk.stress);
+        }
+    }
+    out[k] = blk;
+}
+
+void dcpBatch(Context &c, long long n, const double *P0, const double *P1, const double *Q0, const double *Q1, double *dist,
+              double *Ploc, double *Qloc) {
+    if (n <= 0) return;
+    cudaStream_t st = c.stream;
+    std::vector<double> seg(12 * (size_t)n), res(7 * (size_t)n);
+    for (long long k = 0; k < n; k++)
+        for (int d = 0; d < 3; d++) {
+            seg[12 * k + d] = P0[3 * k + d]; seg[12 * k + 3 + d] = P1[3 * k + d];
+            seg[12 * k + 6 + d] = Q0[3 * k + d]; seg[12 * k + 9 + d] = Q1[3 * k + d];
+        }
+    DevBuf<double> dSeg, dOut;
+    dSeg.reserve(seg.size());
+    dOut.reserve(res.size());
+    ALENS_CUDA(cudaMemcpyAsync(dSeg.p, seg.data(), 8 * seg.size(), cudaMemcpyHostToDevice, st));
+    k_dcp_batch<<<gridFor(n, 128), 128, 0, st>>>(n, dSeg.p, dOut.p);
+    c.launches++;
+    ALENS_CUDA(cudaGetLastError());
+    ALENS_CUDA(cudaMemcpyAsync(res.data(), dOut.p, 8 * res.size(), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    for (long long k = 0; k < n; k++) {
+        if (dist) dist[k] = res[7 * k];
+        for (int d = 0; d < 3; d++) {
+            if (Ploc) Ploc[3 * k + d] = res[7 * k + 1 + d];
+            if (Qloc) Qloc[3 * k + d] = res[7 * k + 4 + d];
+        }
+    }
+}
+
+void pairFunctorBatch(Context &c, long long n, const double *geomI, const double *geomJ, int withStress, unsigned char *hit,
+                      alens_constraint_block *blocks) {
+    if (n <= 0) return;
+    cudaStream_t st = c.stream;
+    DevBuf<double> dI, dJ;
+    DevBuf<unsigned char> dHit;
+    DevBuf<alens_constraint_block> dBlk;
+    dI.reserve(9 * (size_t)n); dJ.reserve(9 * (size_t)n); dHit.reserve((size_t)n); dBlk.reserve((size_t)n);
+    ALENS_CUDA(cudaMemcpyAsync(dI.p, geomI, 72 * (size_t)n, cudaMemcpyHostToDevice, st));
+    ALENS_CUDA(cudaMemcpyAsync(dJ.p, geomJ, 72 * (size_t)n, cudaMemcpyHostToDevice, st));
+    k_pair_functor_batch<<<gridFor(n, 128), 128, 0, st>>>(n, dI.p, dJ.p, withStress, dHit.p, dBlk.p);
+    c.launches++;
+    ALENS_CUDA(cudaGetLastError());
+    ALENS_CUDA(cudaMemcpyAsync(hit, dHit.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaMemcpyAsync(blocks, dBlk.p, sizeof(alens_constraint_block) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+}
+
 // Force the (lazily loaded) kernels of this file into the context now: loading a kernel at its first launch can
 // synchronise the context, which deadlocks against a peer rank's waiting kernel when two ranks share one GPU.
 void preloadBlockKernels() {
     cudaFuncAttributes a;
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_append));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_blocks_out));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_dcp_batch));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_pair_functor_batch));
 }
 
 } // namespace alens

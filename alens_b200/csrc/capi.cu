@@ -152,7 +152,9 @@ int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, con
             if (imm) ALENS_CUDA(cudaMemcpyAsync(c.uImm.p, imm, N, cudaMemcpyHostToDevice, st));
             else ALENS_CUDA(cudaMemsetAsync(c.uImm.p, 0, N, st));
         }
-        g_lastMaxR = hostMaxRadius(n, len, rad, c.lRatio, c.dRatio); // overlaps with the copies
+        c.maxRLocal = hostMaxRadius(n, len, rad, c.lRatio, c.dRatio); // overlaps with the copies
+        c.maxRLRatio = c.lRatio;
+        c.maxRDRatio = c.dRatio;
         rodsUploaded(c, wrap != 0);
         ALENS_CUDA(cudaEventRecord(c.ev[1], st));
         ALENS_CUDA(cudaStreamSynchronize(st));
@@ -475,6 +477,23 @@ int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCand,
         if (nCells) *nCells = c.grid.ncell;
         if (nCand) *nCand = c.statCand;
         if (nHits) *nHits = c.nColl;
+    });
+}
+
+int alens_dcp_query(alens_ctx *ctx, long long n, const double *P0, const double *P1, const double *Q0, const double *Q1,
+                    double *dist, double *Ploc, double *Qloc) {
+    return guarded(ctx, [&](Context &c) {
+        if (n < 0 || (n > 0 && (!P0 || !P1 || !Q0 || !Q1))) throw ArgError{ALENS_ERR_ARG, "alens_dcp_query: null input"};
+        dcpBatch(c, n, P0, P1, Q0, Q1, dist, Ploc, Qloc);
+    });
+}
+
+int alens_pair_functor(alens_ctx *ctx, long long n, const double *geomI, const double *geomJ, int withStress,
+                       unsigned char *hit, alens_constraint_block *blocks) {
+    return guarded(ctx, [&](Context &c) {
+        if (n < 0 || (n > 0 && (!geomI || !geomJ || !hit || !blocks)))
+            throw ArgError{ALENS_ERR_ARG, "alens_pair_functor: null argument"};
+        pairFunctorBatch(c, n, geomI, geomJ, withStress, hit, blocks);
     });
 }
 

@@ -47,7 +47,9 @@ __global__ void k_rod_pack(int n, double *__restrict__ pos, Box box, CellGrid g,
         double x = p[k];
         if (wrap) {
             const double len = box.len[k];
-            if (len > 0 && isfinite(x)) {
+            // only periodic axes: FDPS leaves the root domain at +-LARGE_FLOAT on an open axis
+            // (FDPS/domain_info.hpp:1206), so adjustPositionIntoRootDomain never moves a rod along it
+            if (box.pbc[k] && len > 0 && isfinite(x)) {
                 if (fabs(x - box.lo[k]) > 64.0 * len) x = box.lo[k] + fmod(x - box.lo[k], len); // far-away guard
                 while (x < box.lo[k]) x += len;
                 while (x >= box.hi[k]) x -= len;
@@ -78,7 +80,7 @@ __global__ void k_rod_wrap(int n, double *__restrict__ pos, Box box) {
     for (int k = 0; k < 3; k++) {
         double x = pos[3 * i + k];
         const double len = box.len[k];
-        if (len > 0 && isfinite(x)) {
+        if (box.pbc[k] && len > 0 && isfinite(x)) {
             if (fabs(x - box.lo[k]) > 64.0 * len) x = box.lo[k] + fmod(x - box.lo[k], len);
             while (x < box.lo[k]) x += len;
             while (x >= box.hi[k]) x -= len;
@@ -323,7 +325,8 @@ __device__ __forceinline__ int narrowBatch(const PairIn &in, const Box &box, dou
         RodGeom a = loadRod(in, si), b = loadRod(in, sj);
         b.c = v3(b.c.x + kx * box.len[0], b.c.y + ky * box.len[1], b.c.z + kz * box.len[2]);
         Contact ct;
-        hit = pairContact(a, b, colBuf, ct);
+        // the reference's filter is gidI >= gidJ -> skip (SylinderNear.hpp:210,225): equal gids never collide
+        hit = in.sGid[si] != in.sGid[sj] && pairContact(a, b, colBuf, ct);
     }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     const int nh = __popc(m);
@@ -677,7 +680,7 @@ k_cand_narrow(const unsigned long long *__restrict__ counters, const int4 *__res
         RodGeom a = loadRod(in, si), b = loadRod(in, sj);
         b.c = v3(b.c.x + kx * box.len[0], b.c.y + ky * box.len[1], b.c.z + kz * box.len[2]);
         Contact ct;
-        if (pairContact(a, b, colBuf, ct) && seq < 32 * W) atomicOr(&bits[(size_t)rec.z * W + (seq >> 5)], 1u << (seq & 31));
+        if (in.sGid[si] != in.sGid[sj] && pairContact(a, b, colBuf, ct) && seq < 32 * W) atomicOr(&bits[(size_t)rec.z * W + (seq >> 5)], 1u << (seq & 31));
     }
 }
 
@@ -847,7 +850,15 @@ double hostMaxRadius(int n, const double *len, const double *rad, double lRatio,
     return m;
 }
 
-double g_lastMaxR = 0; // set by the C API before rodsUploaded (single-threaded boundary)
+// device: the same maximum over the resident rods (positive doubles order like their bit patterns)
+__global__ void k_max_radius(int n, const double *__restrict__ len, const double *__restrict__ rad, double lRatio,
+                             double dRatio, unsigned long long *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double R = 0;
+    if (i < n) R = 0.5 * len[i] * lRatio + rad[i] * dRatio;
+    for (int o = 16; o; o >>= 1) R = fmax(R, __shfl_xor_sync(0xffffffffu, R, o));
+    if ((threadIdx.x & 31) == 0 && R > 0) atomicMax(out, (unsigned long long)__double_as_longlong(R));
+}
 thread_local cudaStream_t g_allocStream = nullptr;
 thread_local bool g_allocAsync = false;
 
@@ -863,7 +874,21 @@ void rodsUploaded(Context &c, bool wrap) {
         ALENS_CUDA(cudaMemsetAsync(c.uImg.p, 0, NL + 1, st));
         if (c.nLocal > 0) k_global_index<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.globalBase, c.uGlobalIdx.p);
     }
-    double maxR = g_lastMaxR;
+    if (c.maxRLRatio != c.lRatio || c.maxRDRatio != c.dRatio) {
+        // the collision ratios changed after the upload (alens_set_collision_params + alens_prepare_step):
+        // the cell size has to follow, or the 27-cell stencil would miss contacts
+        ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, sizeof(unsigned long long), st));
+        if (c.nLocal > 0)
+            k_max_radius<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.uLen.p, c.uRad.p, c.lRatio, c.dRatio,
+                                                                 c.dCounters.p);
+        unsigned long long bits = 0;
+        ALENS_CUDA(cudaMemcpyAsync(&bits, c.dCounters.p, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        memcpy(&c.maxRLocal, &bits, sizeof(double));
+        c.maxRLRatio = c.lRatio;
+        c.maxRDRatio = c.dRatio;
+    }
+    double maxR = c.maxRLocal;
     if (multi) {
         c.ghostWidth = (2 * c.maxRadiusGlobal + c.colBuf) * (1.0 + 1e-9) + c.skin;
         if (c.slabHi - c.slabLo < 2 * c.ghostWidth)

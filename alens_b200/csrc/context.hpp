@@ -200,6 +200,8 @@ struct Context {
     double skin = 0;               // how far a rod may stray outside its owner's slab
     double ghostWidth = 0;         // cutoff + skin
     double maxRadiusGlobal = 0;    // max over ALL ranks of lengthCollision/2 + radiusCollision (sets the cell size)
+    double maxRLocal = 0;          // max over this context's rods of lengthCollision/2 + radiusCollision ...
+    double maxRLRatio = -1, maxRDRatio = -1; // ... for these collision ratios (recomputed on the device when they change)
     int strays = 0;
     int globalBase = 0;            // global index of my first rod (updateSylinderMap, SylinderSystem.cpp:868-880)
 
@@ -355,6 +357,10 @@ void calcVelocityBrown(Context &c, double kBT, double dt, const double *normals1
 void calcVelocityNonCon(Context &c, const double *force, const double *velNB, const double *velB, int monolayer, double *velNonBOut);
 long long collectBoundary(Context &c, const alens_boundary *bnd, int nb);
 long long collectLinks(Context &c, const int *prevGid, const int *nextGid, long long nLinks, double linkKappa, double linkGap);
+void dcpBatch(Context &c, long long n, const double *P0, const double *P1, const double *Q0, const double *Q1, double *dist,
+              double *Ploc, double *Qloc);
+void pairFunctorBatch(Context &c, long long n, const double *geomI, const double *geomJ, int withStress, unsigned char *hit,
+                      alens_constraint_block *blocks);
 void preloadCollideKernels();
 void preloadSolverKernels();
 void preloadBlockKernels();
@@ -376,7 +382,6 @@ inline int gridFor(long long n, int block) { return (int)((n + block - 1) / bloc
 
 // shared small kernels (collide.cu)
 void launchScanInt(Context &c, const int *in, int *out, int n);
-extern double g_lastMaxR;
 double hostMaxRadius(int n, const double *len, const double *rad, double lRatio, double dRatio);
 
 } // namespace alens

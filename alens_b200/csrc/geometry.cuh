@@ -210,7 +210,7 @@ __device__ inline bool pairContact(const RodGeom &a, const RodGeom &b, double bu
         if (!(sep < buffer)) return false;
         const Vec3 dd = sp.c - q;
         const double n = norm(dd);
-        const Vec3 nI = v3(dd.x / n, dd.y / n, dd.z / n);
+        const Vec3 nI = n > 0 ? v3(dd.x / n, dd.y / n, dd.z / n) : dd; // Eigen normalized(): unchanged when |dd| = 0
         const Vec3 pSp = sp.c - sp.c, pSy = q - sy.c;
         out.sep = sep;
         if (sa) {
@@ -231,7 +231,7 @@ __device__ inline bool pairContact(const RodGeom &a, const RodGeom &b, double bu
     const Vec3 dd = Ploc - Qloc;
     const double n = norm(dd);
     out.sep = sep;
-    out.normI = v3(dd.x / n, dd.y / n, dd.z / n);
+    out.normI = n > 0 ? v3(dd.x / n, dd.y / n, dd.z / n) : dd; // Eigen normalized(): unchanged when |dd| = 0
     out.posI = Ploc - a.c;
     out.posJ = Qloc - b.c;
     out.labI = Ploc;

@@ -152,6 +152,21 @@ int alens_num_constraints(alens_ctx *ctx, long long *n);
 int alens_get_constraints(alens_ctx *ctx, alens_constraint_block *out, long long cap, int withStress,
                           int writeBack);
 
+/* ---- the narrow phase by itself ---------------------------------------------------------------- */
+/* DCPQuery<3,double,Evec3>::operator() (SimToolbox/Collision/DCPQuery.hpp:199-308), n independent segment pairs
+ * [P0,P1] x [Q0,Q1] (3n host doubles each): minimal distance and the closest points (any output may be NULL).
+ * Bit-identical to the reference header, including its behaviour on degenerate input (zero-length and parallel
+ * segments, the 0.5 fall-backs of :325-327,361-363,434-438). */
+int alens_dcp_query(alens_ctx *ctx, long long n, const double *P0, const double *P1, const double *Q0, const double *Q1,
+                    double *dist, double *Ploc, double *Qloc);
+/* CalcSylinderNearForce's per-pair body (SylinderNear.hpp:241-414: sp_sp / sp_sy / sy_sy by lengthCollision <
+ * 2 radiusCollision) + collideStress (:432-519) for n independent (target I, source J) pairs, no gid filter and no
+ * neighbour search.  geomI/geomJ: 9 host doubles per rod {pos[3], direction[3], lengthCollision, radiusCollision,
+ * colBuf} (the SylinderNearEP fields the functor reads).  hit[k] = collision found; blocks[k] = the ConstraintBlock
+ * the functor would push (gid/globalIndex = 2k, 2k+1; zeroed when there is no hit). */
+int alens_pair_functor(alens_ctx *ctx, long long n, const double *geomI, const double *geomJ, int withStress,
+                       unsigned char *hit, alens_constraint_block *blocks);
+
 /* ---- mobility ------------------------------------------------------------------------------- */
 /* SylinderSystem::calcMobOperator / calcMobMatrix (SylinderSystem.cpp:622-722) with
  * Sylinder::calcDragCoeff (Sylinder.cpp:69-82): stored as 3 inverse drag scalars per rod. */

@@ -283,10 +283,13 @@ void orc_make_rods(int n, const int *gid, const double *radius, const double *le
     }
 }
 
-/* FDPS/particle_system.hpp:798-843 adjustPositionIntoRootDomain: all three axes are wrapped */
-void orc_wrap_positions(int n, double *pos, const double lo[3], const double hi[3]) {
+/* FDPS/particle_system.hpp:798-843 adjustPositionIntoRootDomain wraps into the ROOT domain, and
+ * setPosRootDomain (FDPS/domain_info.hpp:1191-1212) only narrows the periodic axes: an open axis keeps
+ * +-LARGE_FLOAT, so a rod never moves along it.  pbc == NULL: all three axes periodic. */
+void orc_wrap_positions(int n, double *pos, const double lo[3], const double hi[3], const int *pbc) {
     for (int i = 0; i < n; i++)
         for (int k = 0; k < 3; k++) {
+            if (pbc && !pbc[k]) continue;
             double x = pos[3 * i + k];
             const double len = hi[k] - lo[k];
             while (x < lo[k]) x += len;
@@ -430,8 +433,8 @@ int orc_pair_functor(const orc_rod *a, const orc_rod *b, int withStress, orc_blo
         memcpy(Ploc, a->pos, sizeof(Ploc));
         memcpy(Qloc, b->pos, sizeof(Qloc));
         sub3(Ploc, Qloc, d);
-        const double n = norm3(d);
-        for (int k = 0; k < 3; k++) normI[k] = d[k] / n;
+        const double n = norm3(d); /* Eigen >= 3.3 normalized(): unchanged when the squared norm is not > 0 */
+        for (int k = 0; k < 3; k++) normI[k] = n > 0 ? d[k] / n : d[k];
         sub3(Ploc, a->pos, posI);
         sub3(Qloc, b->pos, posJ);
         fill_block(out, sep, sep < 0 ? -sep : 0, a, b, normI, posI, posJ, Ploc, Qloc);
@@ -452,8 +455,8 @@ int orc_pair_functor(const orc_rod *a, const orc_rod *b, int withStress, orc_blo
         const double sep = distMin - (radI + sy->radiusCollision);
         if (!(sep < buffer)) return 0;
         sub3(Ploc, Qloc, d);
-        const double n = norm3(d);
-        for (int k = 0; k < 3; k++) normI[k] = d[k] / n;
+        const double n = norm3(d); /* Eigen >= 3.3 normalized(): unchanged when the squared norm is not > 0 */
+        for (int k = 0; k < 3; k++) normI[k] = n > 0 ? d[k] / n : d[k];
         sub3(Ploc, sp->pos, posI);
         sub3(Qloc, sy->pos, posJ);
         fill_block(out, sep, sep < 0 ? -sep : 0, sp, sy, normI, posI, posJ, Ploc, Qloc);
@@ -475,8 +478,8 @@ int orc_pair_functor(const orc_rod *a, const orc_rod *b, int withStress, orc_blo
     const double sep = distMin - (a->radiusCollision + b->radiusCollision);
     if (!(sep < buffer)) return 0;
     sub3(Ploc, Qloc, d);
-    const double n = norm3(d);
-    for (int k = 0; k < 3; k++) normI[k] = d[k] / n;
+    const double n = norm3(d); /* Eigen >= 3.3 normalized(): unchanged when the squared norm is not > 0 */
+    for (int k = 0; k < 3; k++) normI[k] = n > 0 ? d[k] / n : d[k];
     sub3(Ploc, a->pos, posI);
     sub3(Qloc, b->pos, posJ);
     fill_block(out, sep, sep < 0 ? -sep : 0, a, b, normI, posI, posJ, Ploc, Qloc);

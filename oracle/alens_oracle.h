@@ -86,7 +86,7 @@ void orc_quat_to_dir(const double quat_xyzw[4], double dir[3]);
 void orc_make_rods(int n, const int *gid, const double *radius, const double *length, const double *pos,
                    const double *quat_xyzw, double diameterColRatio, double lengthColRatio, double colBuf,
                    int globalIndexBase, orc_rod *out);
-void orc_wrap_positions(int n, double *pos, const double boxLow[3], const double boxHigh[3]);
+void orc_wrap_positions(int n, double *pos, const double boxLow[3], const double boxHigh[3], const int *pbc);
 
 /* ---- pair functor (SylinderNear.hpp:197-519) */
 int orc_pair_functor(const orc_rod *a, const orc_rod *b, int withStress, orc_block *out);

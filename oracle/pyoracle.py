@@ -148,11 +148,13 @@ def make_rods(gid, radius, length, pos, quat, dRatio=1.0, lRatio=1.0, colBuf=0.3
     return out
 
 
-def wrap_positions(pos, lo, hi):
+def wrap_positions(pos, lo, hi, pbc=None):
+    """applyBoxBC: periodic axes only (pbc=None: all three periodic)."""
     pos = np.array(pos, dtype=np.float64, order="C").reshape(-1, 3)
     lo = np.ascontiguousarray(lo, dtype=np.float64)
     hi = np.ascontiguousarray(hi, dtype=np.float64)
-    lib().orc_wrap_positions(len(pos), _p(pos), _p(lo), _p(hi))
+    pb = None if pbc is None else np.ascontiguousarray(pbc, dtype=np.int32)
+    lib().orc_wrap_positions(len(pos), _p(pos), _p(lo), _p(hi), None if pb is None else _p(pb, C.c_int))
     return pos
 
 

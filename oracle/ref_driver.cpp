@@ -29,8 +29,8 @@ struct V3 {
     double dot(const V3 &o) const { return x * o.x + y * o.y + z * o.z; }
     double norm() const { return sqrt(x * x + y * y + z * z); }
     void normalize() {
-        double n = norm();
-        x /= n; y /= n; z /= n;
+        double n = norm(); // Eigen >= 3.3 normalized(): unchanged when the squared norm is not > 0
+        if (n > 0) { x /= n; y /= n; z /= n; }
     }
 };
 static inline V3 operator*(double s, const V3 &v) { return V3(v.x * s, v.y * s, v.z * s); }
@@ -220,15 +220,17 @@ int ref_pair_block(const ref_rod *a, const ref_rod *b, ref_pair *out) { return p
 // Returns number of blocks found; fetch them with ref_fdps_get().
 long long ref_fdps_collect(int n, ref_rod *rods, const double *boxLow, const double *boxHigh, const int *pbc,
                            int nthreads, int rebuild) {
-    if (nthreads > 0)
-        omp_set_num_threads(nthreads);
     if (!G.psInit) {
+        // FDPS sizes its per-thread buffers once, from omp_get_max_threads() at Initialize: do that with every
+        // core so that later calls may ask for any smaller thread count
         int argc = 0;
         char **argv = nullptr;
-        FILE *saved = stderr; (void)saved;
+        omp_set_num_threads(omp_get_num_procs());
         PS::Initialize(argc, argv);
         G.psInit = true;
     }
+    if (nthreads > 0)
+        omp_set_num_threads(std::min(nthreads, omp_get_num_procs()));
     if (rebuild || !G.dinfo) {
         delete G.tree; G.tree = nullptr; G.treeN = 0;
         delete G.psys; delete G.dinfo;

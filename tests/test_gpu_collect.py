@@ -21,7 +21,7 @@ def gpu_collect(ctx, rods, lo, hi, pbc, colbuf, dratio=1.0, lratio=1.0):
 
 
 def oracle_collect(oracle, rods, lo, hi, pbc, colbuf, dratio=1.0, lratio=1.0, method="cells"):
-    pos = oracle.wrap_positions(rods["pos"], lo, hi)
+    pos = oracle.wrap_positions(rods["pos"], lo, hi, pbc)
     orods = oracle.make_rods(rods["gid"], rods["radius"], rods["length"], pos, rods["quat"], dratio, lratio, colbuf)
     return oracle.collect_pairs(orods, lo, hi, pbc, with_stress=True, method=method), orods
 
@@ -74,7 +74,7 @@ def test_collect_rods_outside_box_are_wrapped(ctx, oracle):
     lo, hi, pbc = [0, 0, 0], [2.0] * 3, (1, 1, 0)
     g = gpu_collect(ctx, rods, lo, hi, pbc, 0.025)
     o, _ = oracle_collect(oracle, rods, lo, hi, pbc, 0.025)
-    np.testing.assert_array_equal(ctx.get_positions(), oracle.wrap_positions(rods["pos"], lo, hi))
+    np.testing.assert_array_equal(ctx.get_positions(), oracle.wrap_positions(rods["pos"], lo, hi, pbc))
     assert_blocks_equal(g, o)
 
 
@@ -127,3 +127,78 @@ def test_split_search_gives_the_same_list_row_for_row(ctx, oracle, colbuf, n):
         assert got.tobytes() == ref.tobytes()
     want, _ = oracle_collect(oracle, rods, lo, hi, pbc, colbuf)
     assert_blocks_equal(ref, want)
+
+
+# ---- the narrow phase by itself (alens_dcp_query / alens_pair_functor) -------------------------------------------
+def _segments(rng, n):
+    """random, degenerate, parallel, touching and axis-aligned segment pairs (exact zeros make the clamped-root and
+    0.5 fall-back branches of DCPQuery.hpp:311-472 reachable)"""
+    P0 = rng.normal(size=(n, 3)); P1 = P0 + rng.normal(size=(n, 3)) * rng.choice([1.0, 1e-3], size=(n, 1))
+    Q0 = rng.normal(size=(n, 3)); Q1 = Q0 + rng.normal(size=(n, 3))
+    kind = np.arange(n) % 8
+    Q1[kind == 1] = (Q0 + (P1 - P0))[kind == 1]                       # parallel, equal length
+    Q1[kind == 2] = (Q0 - 2.5 * (P1 - P0))[kind == 2]                 # antiparallel
+    Q0[kind == 3] = P0[kind == 3]                                      # shared end point
+    P1[kind == 4] = P0[kind == 4]                                      # P degenerates to a point
+    Q1[kind == 5] = Q0[kind == 5]; P1[kind == 5] = P0[kind == 5]      # both points
+    g = np.round(rng.normal(size=(n, 12)) * 2) / 2                     # half-integer lattice: exact ties and zeros
+    for a, c in ((P0, 0), (P1, 3), (Q0, 6), (Q1, 9)):
+        a[kind == 6] = g[kind == 6, c:c + 3]
+    Q1[kind == 7] = (Q0 + (P1 - P0) * (1 + 1e-12))[kind == 7]         # nearly parallel
+    return P0, P1, Q0, Q1
+
+
+def test_dcp_query_bit_exact_against_oracle_and_reference(ctx, oracle):
+    from test_oracle_properties import HAVE_REF, QUIRK
+
+    rng = np.random.default_rng(7)
+    P0, P1, Q0, Q1 = _segments(rng, 6000)
+    # the reference's reversal quirk (non-minimal distance), both orientations
+    P0[0], P1[0], Q0[0], Q1[0] = QUIRK
+    P0[1], P1[1], Q0[1], Q1[1] = QUIRK[1], QUIRK[0], QUIRK[2], QUIRK[3]
+    d, P, Q = ctx.dcp_query(P0, P1, Q0, Q1)
+    assert d[0] == 0.7071067811865476 and d[1] == 0.9265026063892198
+    for k in range(len(d)):
+        o = oracle.dcp_segseg(P0[k], P1[k], Q0[k], Q1[k])
+        assert d[k] == o[0] and np.array_equal(P[k], o[1]) and np.array_equal(Q[k], o[2]), k
+        if HAVE_REF and k < 2000:
+            r = oracle.dcp_segseg(P0[k], P1[k], Q0[k], Q1[k], which="ref")
+            assert d[k] == r[0] and np.array_equal(P[k], r[1]) and np.array_equal(Q[k], r[2]), k
+
+
+def test_pair_functor_bit_exact_against_oracle(ctx, oracle):
+    """CalcSylinderNearForce's body on independent pairs: spheres, rods, mixed, coincident centres (normalized() of a
+    zero vector stays zero, Eigen >= 3.3), against the oracle's functor incl. the stress"""
+    rng = np.random.default_rng(11)
+    n = 3000
+    rods = random_rods(2 * n, 1.2, seed=13, frac_sphere=0.3, length=0.5)
+    rods["pos"][1::2] = rods["pos"][0::2] + rng.normal(size=(n, 3)) * 0.15  # partners close by: about half of them touch
+    o = oracle.make_rods(rods["gid"], rods["radius"], rods["length"], rods["pos"], rods["quat"], 1.0, 1.0, 0.05)
+    o["pos"][1] = o["pos"][0]  # coincident centres: pair 0
+    if o["lengthCollision"][0] >= 2 * o["radiusCollision"][0] or o["lengthCollision"][1] >= 2 * o["radiusCollision"][1]:
+        o["lengthCollision"][:2] = 0.0  # make both spheres
+    geom = np.concatenate([o["pos"], o["direction"], o["lengthCollision"][:, None], o["radiusCollision"][:, None],
+                           o["colBuf"][:, None]], axis=1)
+    hit, blocks = ctx.pair_functor(geom[0::2], geom[1::2], with_stress=True)
+    nh = 0
+    for k in range(n):
+        want = oracle.pair_functor(o[2 * k], o[2 * k + 1], with_stress=True)
+        assert bool(hit[k]) == (want is not None), k
+        if want is None:
+            continue
+        nh += 1
+        for f in ("delta0", "gamma", "normI", "normJ", "posI", "posJ", "labI", "labJ", "stress"):
+            assert np.array_equal(blocks[k][f], want[f], equal_nan=True), (k, f)
+    assert hit[0] and np.all(blocks[0]["normI"] == 0)  # coincident spheres: zero normal, not NaN
+    assert 500 < nh < n - 500
+
+
+def test_equal_gids_never_collide(ctx, oracle):
+    """the reference skips gidI >= gidJ (SylinderNear.hpp:210,225): two overlapping rods with the same gid give no block"""
+    rods = random_rods(200, 0.8, seed=2)
+    rods["gid"][:] = np.arange(200) // 2  # every gid twice
+    lo, hi, pbc = [0.0] * 3, [0.8] * 3, (1, 1, 1)
+    g = gpu_collect(ctx, rods, lo, hi, pbc, 0.05)
+    o, _ = oracle_collect(oracle, rods, lo, hi, pbc, 0.05, method="brute")
+    assert len(o) > 50 and np.all(o["gidI"] < o["gidJ"])
+    assert_blocks_equal(g, o)

@@ -28,8 +28,8 @@ def _load(ctx, rods, lo, hi, pbc, colbuf):
     ctx.set_rods(rods["gid"], rods["pos"], rods["quat"], rods["length"], rods["radius"], rods["immovable"])
 
 
-def _oracle_rods(oracle, rods, lo, hi, colbuf):
-    return oracle.make_rods(rods["gid"], rods["radius"], rods["length"], oracle.wrap_positions(rods["pos"], lo, hi),
+def _oracle_rods(oracle, rods, lo, hi, colbuf, pbc):
+    return oracle.make_rods(rods["gid"], rods["radius"], rods["length"], oracle.wrap_positions(rods["pos"], lo, hi, pbc),
                             rods["quat"], 1.0, 1.0, colbuf)
 
 
@@ -52,7 +52,7 @@ def test_mixmotorsliding_as_shipped(ctx, oracle):
     _load(ctx, rods, lo, hi, pbc, colbuf)
     # the two rods are 0.07 apart centre to centre: 0.045 between the surfaces, outside colBuf -> no collision block
     assert ctx.collect_pair_collision() == 0
-    orods = _oracle_rods(oracle, rods, lo, hi, colbuf)
+    orods = _oracle_rods(oracle, rods, lo, hi, colbuf, pbc)
     assert len(oracle.collect_pairs(orods, lo, hi, pbc)) == 0
     ctx.append_constraints(motors)
     ctx.calc_mobility(mu)
@@ -96,7 +96,7 @@ def test_densemonolayer_initial_state(ctx, oracle):
     d0 = dict(zip(map(tuple, key.tolist()), blocks["delta0"][order].tolist()))
     assert all(d0[p] == v for p, v in zip(ref_pairs, z["ref_delta0"].tolist()))
     # and against the oracle of today, every field
-    orods = _oracle_rods(oracle, rods, lo, hi, colbuf)
+    orods = _oracle_rods(oracle, rods, lo, hi, colbuf, pbc)
     _compare_lists(blocks, oracle.collect_pairs(orods, lo, hi, pbc, with_stress=True))
     # one constraint solve with the example's parameters (dt 1e-5, conResTol 1e-6, mu 1)
     ctx.calc_mobility(1.0)
@@ -122,7 +122,7 @@ def test_active3dnematics_aligned(ctx, oracle):
     _load(ctx, rods, lo, hi, pbc, colbuf)
     nc = ctx.collect_pair_collision()
     blocks = ctx.get_constraints(with_stress=True).copy()
-    orods = _oracle_rods(oracle, rods, lo, hi, colbuf)
+    orods = _oracle_rods(oracle, rods, lo, hi, colbuf, pbc)
     want = oracle.collect_pairs(orods, lo, hi, pbc, with_stress=True)
     assert nc == len(want) > 100
     _compare_lists(blocks, want)

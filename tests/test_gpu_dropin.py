@@ -66,7 +66,7 @@ def test_dropin_step_equals_capi_path(tmp_path, ctx, oracle):
     rods = random_rods(n, box, seed=21)
     lo, hi, pbc = [0.0] * 3, [box] * 3, (1, 1, 0)
     vnb = thermal_velocity(rods, mu, dt, seed=5)
-    pos_w = oracle.wrap_positions(rods["pos"], lo, hi)
+    pos_w = oracle.wrap_positions(rods["pos"], lo, hi, pbc)
     orods = oracle.make_rods(rods["gid"], rods["radius"], rods["length"], pos_w, rods["quat"], 1.0, 1.0, colbuf)
     host = np.concatenate([add_bilateral(oracle, rods, orods, 40, 1), add_one_sided(orods, 30, 2)])
     nc, ite, resid, out = run_dropin(tmp_path, rods, lo, hi, pbc, colbuf, mu, dt, res, max_ite, vnb, host)

@@ -21,7 +21,7 @@ def setup_case(ctx, oracle, n=2000, box=1.6, seed=0, pbc=(1, 1, 1), frac_sphere=
                        frac_immovable=frac_immovable)
     lo, hi = [0, 0, 0], [box] * 3
     blocks = gpu_collect(ctx, rods, lo, hi, pbc, 0.025).copy()
-    pos = oracle.wrap_positions(rods["pos"], lo, hi)
+    pos = oracle.wrap_positions(rods["pos"], lo, hi, pbc)
     orods = oracle.make_rods(rods["gid"], rods["radius"], rods["length"], pos, rods["quat"], 1.0, 1.0, 0.025)
     ctx.calc_mobility(MU)
     return rods, orods, blocks

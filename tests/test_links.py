@@ -69,7 +69,7 @@ def test_gpu_links_equal_the_oracle_and_solve(ctx, oracle):
     rods, prev, nxt = filaments()
     lo, hi, pbc = [0.0] * 3, [3.0] * 3, (1, 1, 1)
     kappa, gap = 100.0, 0.01
-    pos = oracle.wrap_positions(rods["pos"], lo, hi)
+    pos = oracle.wrap_positions(rods["pos"], lo, hi, pbc)
     orods = oracle.make_rods(rods["gid"], rods["radius"], rods["length"], pos, rods["quat"], 1.0, 1.0, 0.025)
     want = oracle.collect_links(orods, prev, nxt, lo, hi, pbc, kappa, gap)
     assert len(want) == len(prev) == 40 * 11
