@@ -249,7 +249,7 @@ void commFree(Context &c) {
     m.active = false;
 }
 
-static void checkCommError(Context &c) {
+void checkCommError(Context &c) {
     int err = 0;
     ALENS_CUDA(cudaMemcpyAsync(&err, &hdrOf(c.comm.win)->error, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     ALENS_CUDA(cudaStreamSynchronize(c.stream));

@@ -376,6 +376,7 @@ void commExchangeGhostIndices(Context &c);
 void commHaloVelNC(Context &c);
 void commPushU(Context &c, unsigned long long seq);
 void commSignalHalo(Context &c, unsigned long long seq);
+void checkCommError(Context &c); // throws ALENS_ERR_COMM if a device-side wait of this rank has timed out
 void reserveConstraints(Context &c, size_t n, bool keep);
 
 inline int gridFor(long long n, int block) { return (int)((n + block - 1) / block); }

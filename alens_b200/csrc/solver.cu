@@ -1315,7 +1315,10 @@ __device__ __forceinline__ void tailEpilogue(const BbTail &p, double s0, double 
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            if (failed) { // a peer never arrived: stop the loop, tell the host
+            // a peer never arrived -- at the mailbox, or earlier at the halo wait of ANY CTA of this kernel (waitSeq sets the
+            // header's error word before that CTA takes its ticket): the rows behind that wait used stale ghost velocities,
+            // so stop the loop and tell the host (solveBBPGD throws ALENS_ERR_COMM on done == 4)
+            if (failed || (a.err && *(volatile int *)a.err)) {
                 p.scal->ticket = 0;
                 p.scal->done = 4;
                 if (p.prog) {
@@ -2264,6 +2267,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     c.timers.op_applies = c.hScal->mv;
     ALENS_CUDA(cudaGetLastError());
     if (c.hScal->done == 4) throw ArgError{ALENS_ERR_COMM, "solve: timed out waiting for a peer rank"};
+    if (c.comm.active) checkCommError(c); // a halo wait that timed out in any kernel of the loop (stale ghost velocities)
     const int n = c.hScal->ite; // iterations actually executed
     // unpack: vX0 = the iterate the operator last saw, vX1 = the one before it
     const bool older = !(c.hScal->done || n == 0);

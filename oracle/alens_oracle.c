@@ -779,6 +779,14 @@ static double vdot(long long n, const double *a, const double *b) {
     free(part);
     return s;
 }
+/* pow(v.norm2(), 2) exactly as the reference spells it (BCQPSolver.cpp:215,220,321): the square root and the
+ * squaring each round, so the result can differ from the plain dot product in the last bit */
+static double vnorm2sq(long long n, const double *a) {
+    /* gcc folds the reference's pow(x, 2) into x * x (so does every compiler the reference is built with at -O2/-O3;
+     * glibc's pow itself differs from x * x in the last bit for about 1 argument in 1000) */
+    const double nrm = sqrt(vdot(n, a, a));
+    return nrm * nrm;
+}
 static double vnorminf(long long n, const double *a) {
     double m = 0;
 #pragma omp parallel for reduction(max : m) schedule(static)
@@ -903,11 +911,11 @@ static int solve_bbpgd(const orc_op *op, const double *b, const double *lb, cons
             vupdate2(n, gkdiff, 1.0, gk, -1.0, gkm1, 0.0);
             double a = 0, bb = 0;
             if (iteCount % 2 == 0) {
-                a = vdot(n, xkdiff, xkdiff); /* pow(norm2,2) */
+                a = vnorm2sq(n, xkdiff);
                 bb = vdot(n, xkdiff, gkdiff);
             } else {
                 a = vdot(n, xkdiff, gkdiff);
-                bb = vdot(n, gkdiff, gkdiff);
+                bb = vnorm2sq(n, gkdiff);
             }
             if (fabs(bb) < 10 * DBL_EPSILON) bb += 10 * DBL_EPSILON;
             alpha = a / bb;
@@ -972,7 +980,7 @@ static int solve_apgd(const orc_op *op, const double *b, const double *lb, const
             const double leftTerm1 = vdot(n, xkp1, Axbkp1) * 0.5;
             const double leftTerm2 = vdot(n, xkp1, b);
             const double rightTerm3 = vdot(n, gVec, xkdiff);
-            const double rightTerm4 = 0.5 * Lk * vdot(n, xkdiff, xkdiff);
+            const double rightTerm4 = 0.5 * Lk * vnorm2sq(n, xkdiff);
             if ((leftTerm1 + leftTerm2) <= (rightTerm1 + rightTerm2 + rightTerm3 + rightTerm4)) break;
             Lk *= 2;
             tk = 1 / Lk;

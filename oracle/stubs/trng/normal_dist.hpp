@@ -1,0 +1,1 @@
+#include "mrg5.hpp"

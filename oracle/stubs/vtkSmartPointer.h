@@ -1,0 +1,1 @@
+#include "vtk_stub.h"
