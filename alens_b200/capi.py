@@ -36,7 +36,7 @@ EXPORTS = [
     "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
     "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral", "alens_calc_velocity_noncon", "alens_calc_velocity_brown",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
-    "alens_dcp_query", "alens_pair_functor",
+    "alens_dcp_query", "alens_pair_functor", "alens_comm_mode",
 ]
 
 
@@ -286,6 +286,11 @@ class Context:
         a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
         self._call("alens_num_ghosts", C.byref(a), C.byref(b), C.byref(c))
         return dict(ghosts=a.value, sent_left=b.value, sent_right=c.value)
+
+    def comm_mode(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self._call("alens_comm_mode", C.byref(a), C.byref(b))
+        return dict(connected=bool(a.value), fused=bool(b.value))
 
     def time_kernel(self, which, reps=20):
         us = C.c_double(0)

@@ -567,4 +567,11 @@ int alens_num_ghosts(alens_ctx *ctx, int *nGhost, int *nSentLeft, int *nSentRigh
     });
 }
 
+int alens_comm_mode(alens_ctx *ctx, int *connected, int *fused) {
+    return guarded(ctx, [&](Context &c) {
+        if (connected) *connected = c.comm.active ? 1 : 0;
+        if (fused) *fused = (c.comm.active && c.comm.fused) ? 1 : 0;
+    });
+}
+
 } // extern "C"

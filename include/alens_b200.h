@@ -280,6 +280,10 @@ int alens_comm_connect(alens_ctx *ctx, const void *blobsInRankOrder);
 int alens_comm_connect_local(alens_ctx **ctxs, int n);
 /* ghost rods received / owned rods mirrored on the left and right neighbour in the last exchange */
 int alens_num_ghosts(alens_ctx *ctx, int *nGhost, int *nSentLeft, int *nSentRight);
+/* connected: the windows are mapped; fused: every rank sits on its own GPU, so the BBPGD kernels wait for their
+ * neighbours themselves (halo wait + mailbox allreduce inside k_bb_tail, remote stores from k_force_vel_act) instead of
+ * through the one-thread helper kernels used when ranks share a device */
+int alens_comm_mode(alens_ctx *ctx, int *connected, int *fused);
 
 #ifdef __cplusplus
 }

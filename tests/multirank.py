@@ -1,6 +1,9 @@
 """Harness for the slab decomposition: run R ranks (one alens_ctx each, one host thread each) inside one process.
-With a single GPU every rank uses device 0; with >= R GPUs each rank gets its own device (same code path as the
-multi-process bench, only the bootstrap differs: alens_comm_connect_local instead of cudaIpc blobs)."""
+devices="shared": every rank on device 0 (the unfused protocol: one-thread wait / signal / reduce kernels);
+devices="spread": one rank per GPU when the box has at least R of them -- the FUSED kernels that bench.py times at N > 1
+(halo wait and mailbox allreduce inside k_bb_tail, remote U rows from k_force_vel_act); same code path as the
+multi-process bench, only the bootstrap differs (alens_comm_connect_local instead of cudaIpc blobs).
+devices=None: "spread" if possible, else "shared" (ALENS_TEST_DEVICES=0,1,... overrides)."""
 import os
 import threading
 
@@ -19,6 +22,27 @@ def split_slabs(rods, box_lo, box_hi, nranks, axis=0):
     return [np.nonzero(owner == r)[0] for r in range(nranks)]
 
 
+def gpu_count():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def pick_devices(nranks, devices=None):
+    if devices is None and os.environ.get("ALENS_TEST_DEVICES"):
+        env = [int(x) for x in os.environ["ALENS_TEST_DEVICES"].split(",")]
+        return [env[r % len(env)] for r in range(nranks)]
+    if devices is None:
+        devices = "spread" if gpu_count() >= nranks else "shared"
+    if devices == "shared":
+        return [0] * nranks
+    if devices == "spread":
+        if gpu_count() < nranks:
+            raise RuntimeError(f"devices='spread' needs {nranks} GPUs")
+        return list(range(nranks))
+    return list(devices)
+
+
 def take(rods, idx):
     return {k: v[idx] for k, v in rods.items()}
 
@@ -32,9 +56,7 @@ def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None,
     cutoff = 2 * max_r + colbuf
     skin = 0.25 * cutoff if skin is None else skin
     w = (hi[axis] - lo[axis]) / nranks
-    if devices is None:  # ALENS_TEST_DEVICES=0,1,...: spread the ranks over several GPUs (enables the fused kernels)
-        env = [int(x) for x in os.environ.get("ALENS_TEST_DEVICES", "0").split(",")]
-        devices = [env[r % len(env)] for r in range(nranks)]
+    devices = pick_devices(nranks, devices)
     ctxs = []
     base = 0
     for r in range(nranks):
@@ -63,7 +85,8 @@ def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None,
                 nc = c.collect_pair_collision()
                 c.calc_mobility(mu)
                 rep = c.solve_constraints(v, dt, res, max_ite, 0)
-            res_r.update(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), ghosts=c.num_ghosts())
+            res_r.update(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), ghosts=c.num_ghosts(),
+                         mode=c.comm_mode())
             res_r.update(c.get_force_velocity())
             if want_blocks:
                 res_r["blocks"] = c.get_constraints(with_stress=True, write_back=True)

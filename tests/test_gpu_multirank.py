@@ -4,7 +4,7 @@ relative (per-rod sums run over a different local constraint numbering)."""
 import numpy as np
 import pytest
 
-from multirank import run_ranks, split_slabs, take
+from multirank import gpu_count, run_ranks, split_slabs, take
 from scenarios import canonical_order, random_rods, thermal_velocity
 
 pytestmark = pytest.mark.gpu
@@ -30,6 +30,24 @@ def single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, max_ite, vnc):
     return out
 
 
+@pytest.fixture(params=["shared", "spread"])
+def placement(request):
+    """every multi-rank test runs twice: all ranks on device 0 (unfused helper kernels) and -- on a box with enough GPUs,
+    e.g. `gpurun --gpus 4` -- one rank per GPU, which is the fused protocol bench.py times at N > 1"""
+    return request.param
+
+
+def _devices(placement, nranks):
+    if placement == "spread" and gpu_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs for one rank per GPU (fused kernels)")
+    return placement
+
+
+def _check_mode(ranks, placement):
+    for r in ranks:
+        assert r["mode"]["connected"] and r["mode"]["fused"] == (placement == "spread")
+
+
 def slab_ordered(rods, lo, hi, nranks, axis=0):
     """reorder the global system so that rank r's rods are contiguous: global indices then coincide"""
     parts = split_slabs(rods, np.asarray(lo, float), np.asarray(hi, float), nranks, axis)
@@ -37,7 +55,7 @@ def slab_ordered(rods, lo, hi, nranks, axis=0):
 
 
 @pytest.mark.parametrize("nranks,pbc", [(2, (1, 1, 1)), (2, (1, 1, 0)), (3, (0, 1, 1))])
-def test_multirank_slabs_along_z(nranks, pbc):
+def test_multirank_slabs_along_z(nranks, pbc, placement):
     """slabs along z, the slowest axis of the cell order: the rows that read ghost velocities are the first and last rows
     of the constraint list, and the fused tail kernel (one rank per GPU) walks them last, behind its halo wait"""
     n, box, colbuf, mu, dt, res = 6000, (1.6, 1.6, 4.8), 0.025, 1.0, 1e-4, 1e-6
@@ -45,7 +63,8 @@ def test_multirank_slabs_along_z(nranks, pbc):
     rods = slab_ordered(random_rods(n, box, seed=31 + nranks), lo, hi, nranks, axis=2)
     vnc = thermal_velocity(rods, mu, dt, seed=5)
     ref = single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, 200, vnc)
-    ranks = run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, 200, vnc=vnc, axis=2)
+    ranks = run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, 200, vnc=vnc, axis=2, devices=_devices(placement, nranks))
+    _check_mode(ranks, placement)
     assert {r["report"].iterations for r in ranks} == {ref["report"].iterations}
     for name in ("velU", "forceU"):
         full = np.zeros_like(ref[name]).reshape(-1, 6)
@@ -70,13 +89,14 @@ def test_multirank_slabs_along_z(nranks, pbc):
 
 
 @pytest.mark.parametrize("nranks,pbc", [(2, (1, 1, 1)), (2, (0, 1, 0)), (3, (1, 1, 1)), (4, (1, 0, 1))])
-def test_multirank_matches_single(nranks, pbc):
+def test_multirank_matches_single(nranks, pbc, placement):
     n, box, colbuf, mu, dt, res = 6000, (4.8, 1.6, 1.6), 0.025, 1.0, 1e-4, 1e-6
     lo, hi = [0.0, 0.0, 0.0], list(box)
     rods = slab_ordered(random_rods(n, box, seed=11 + nranks), lo, hi, nranks)
     vnc = thermal_velocity(rods, mu, dt, seed=3)
     ref = single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, 200, vnc)
-    ranks = run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, 200, vnc=vnc)
+    ranks = run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, 200, vnc=vnc, devices=_devices(placement, nranks))
+    _check_mode(ranks, placement)
     assert sum(r["ghosts"]["ghosts"] for r in ranks) > 0
 
     # ---- constraint lists: every rank holds all pairs with at least one owned rod
@@ -116,7 +136,7 @@ def test_multirank_matches_single(nranks, pbc):
         np.testing.assert_allclose(h[:, 3:5], hr[:, 3:5], rtol=1e-7)
 
 
-def test_multirank_time_stepping_across_periodic_face():
+def test_multirank_time_stepping_across_periodic_face(placement):
     """three resident steps (solve -> stepEuler -> prepareStep) from an overlapping start: rods drift across slab
     faces and across the periodic box face; positions must follow the single-rank trajectory"""
     import alens_b200
@@ -139,7 +159,8 @@ def test_multirank_time_stepping_across_periodic_face():
     vel_ref = c.get_force_velocity()["velU"]
     c.close()
     ranks = run_ranks(rods, lo, hi, pbc, 2, colbuf, mu, dt, res, 2000, vnc=None, skin=0.15, steps=steps,
-                      want_blocks=False)
+                      want_blocks=False, devices=_devices(placement, 2))
+    _check_mode(ranks, placement)
     for r in ranks:
         pos, quat = r["state"]
         assert np.abs(pos - pos_ref[r["idx"]]).max() < 1e-9
@@ -149,7 +170,7 @@ def test_multirank_time_stepping_across_periodic_face():
         assert r["report"].iterations == rep.iterations
 
 
-def test_multirank_empty_rank_and_no_contacts():
+def test_multirank_empty_rank_and_no_contacts(placement):
     """a rank without rods and a system without contacts still run the collective protocol"""
     n, box = 300, (6.0, 1.0, 1.0)
     lo, hi, pbc = [0.0] * 3, list(box), (0, 0, 0)
@@ -157,7 +178,8 @@ def test_multirank_empty_rank_and_no_contacts():
     rods = slab_ordered(rods, lo, hi, 3)
     vnc = thermal_velocity(rods, 1.0, 1e-4, seed=1)
     ref = single_rank(rods, lo, hi, pbc, 0.025, 1.0, 1e-4, 1e-6, 100, vnc)
-    ranks = run_ranks(rods, lo, hi, pbc, 3, 0.025, 1.0, 1e-4, 1e-6, 100, vnc=vnc)
+    ranks = run_ranks(rods, lo, hi, pbc, 3, 0.025, 1.0, 1e-4, 1e-6, 100, vnc=vnc, devices=_devices(placement, 3))
+    _check_mode(ranks, placement)
     assert [len(r["idx"]) for r in ranks][1:] == [0, 0]
     assert ranks[0]["nc"] == ref["nc"]
     assert ranks[0]["report"].iterations == ref["report"].iterations
@@ -180,7 +202,7 @@ def test_multirank_stray_rod_is_reported():
         orig = multirank.split_slabs
         try:
             multirank.split_slabs = lambda rods_, lo_, hi_, R, axis=0: [np.arange(0, n // 2), np.arange(n // 2, n)]
-            rr(rods, lo, hi, pbc, 2, 0.025, 1.0, 1e-4, 1e-6, 10, vnc=None)
+            rr(rods, lo, hi, pbc, 2, 0.025, 1.0, 1e-4, 1e-6, 10, vnc=None, devices="shared")
         finally:
             multirank.split_slabs = orig
     assert ei.value.code == -3
