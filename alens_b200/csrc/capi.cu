@@ -437,15 +437,19 @@ int alens_reset_timers(alens_ctx *ctx) {
 int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
     return guarded(ctx, [&](Context &c) {
         const std::string k = name ? name : "";
-        if (k == "force_kernel") { // 0 dense level-major, 1 k_force_vel_act, 2 k_slot_x + k_rod_sum (both on the rod-major layout)
-            c.optForceKernel = value == 0 ? 0 : 1;
+        if (k == "force_kernel") { // 3 k_force_vel_rec (slot records), 0 dense level-major, 1 k_force_vel_act, 2 k_slot_x + k_rod_sum (rod-major layout)
+            c.optForceKernel = value == 0 ? 0 : (value == 3 ? 3 : 1);
             c.optForceSplit = value == 2;
+            if (c.optForceKernel == 3) c.optTailRing = 0; // the TMA-staged tail does not maintain the slot records
         }
         else if (k == "find_minb") c.optFindMinB = (value == 5 || value == 3) ? (int)value : 4;
         else if (k == "find_split") c.optFindSplit = value != 0;
         else if (k == "find_split_minb") c.optFindSplitMinB = value == 6 ? 6 : 8;
         else if (k == "force_minb") c.optForceMinB = (value == 3 || value == 5) ? (int)value : 4;
-        else if (k == "tail_ring") c.optTailRing = value != 0;
+        else if (k == "tail_ring") {
+            c.optTailRing = value != 0;
+            if (c.optTailRing && c.optForceKernel == 3) c.optForceKernel = 1; // see force_kernel
+        }
         else if (k == "pdl") c.optPdl = (int)std::max(0LL, std::min(2LL, value));
         else if (k == "poll") c.optPoll = value != 0;
         else if (k == "lookahead") c.optLookahead = (int)std::max(1LL, std::min(64LL, value));

@@ -263,7 +263,10 @@ struct Context {
     DevBuf<double> incCol;                 // 6 per slot: D column block for that (rod, constraint)
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
-    int optForceKernel = 1;                 // 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
+    int optForceKernel = 3;                 // 3 = k_force_vel_rec (64-byte slot records + slot-ordered live bitmap kept by k_bb_tail), 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
+    DevBuf<double> incRec;                  // force_kernel 3: 8 doubles per slot {x, g, D column block[6]}, 64-byte aligned records
+    DevBuf<int2> cSlot;                     // ... per constraint: slot of its I side / J side (-1: none, ghost or one-sided)
+    DevBuf<unsigned> slotBi;                // ... bit per slot: the slot's constraint is bilateral (constant during a solve)
     int optFindSplitMinB = 8;               // ... resident CTAs per SM of its stage-1/2 kernel (8: 64 registers)
     int optFindSplit = 1;                   // pair search: stages 1-2 -> candidates, dense narrow phase + ordered emission (0: one kernel)
     int candWords = 16;                     // bitmap words per cell (32 candidates each); follows the fullest cell of the last step

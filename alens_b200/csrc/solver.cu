@@ -351,6 +351,47 @@ __global__ void k_inc_emit_rm(int nRods, const int *__restrict__ start, int *__r
     }
 }
 
+// Record layout for k_force_vel_rec (force_kernel = 3): every incidence slot owns one 64-byte aligned record
+// {x, g, D column block[6]}.  The column block is written here, once per step; {x, g} of a slot whose constraint row can
+// be non-zero is refreshed by k_bb_tail every iteration, which also keeps the slot-ordered bitmap slotLive up to date.
+// The force kernel then needs no constraint ids at all: bitmap word -> one aligned 64-byte record per live slot.
+// cSlot[k] = (slot of row k in rod I's list, slot in rod J's list), -1 where the side has no slot (one-sided, ghost rod).
+__global__ void k_inc_emit_rec(int nRods, const int *__restrict__ start, int *__restrict__ incCon, ConGeom g,
+                               double *__restrict__ rec, int2 *__restrict__ cSlot, unsigned *__restrict__ slotBi) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp * 32 >= nRods) return;
+    const int r = warp * 32 + lane;
+    const int b = start[min(r, nRods)], e = start[min(r + 1, nRods)];
+    for (int a = b + 1; a < e; a++) { // insertion sort by (constraint, side): fixed summation order, lists are short
+        const int v = incCon[a];
+        int p = a - 1;
+        while (p >= b && incCon[p] > v) {
+            incCon[p + 1] = incCon[p];
+            p--;
+        }
+        incCon[p + 1] = v;
+    }
+    __syncwarp();
+    const int gb = __shfl_sync(0xffffffffu, b, 0), ge = __shfl_sync(0xffffffffu, e, 31);
+    for (int p = gb + lane; p < ge; p += 32) {
+        const int k2 = incCon[p];
+        const size_t kk = (size_t)(k2 >> 2);
+        const bool sideJ = k2 & 1;
+        double gx = g.n[kk], gy = g.n[kk + g.stride], gz = g.n[kk + 2 * g.stride];
+        const double *P = sideJ ? g.pJ : g.pI;
+        const double px = P[kk], py = P[kk + g.stride], pz = P[kk + 2 * g.stride];
+        if (sideJ) { gx = -gx; gy = -gy; gz = -gz; }
+        double2 *o = reinterpret_cast<double2 *>(rec + 8 * (size_t)p);
+        o[0] = make_double2(0.0, 0.0);
+        o[1] = make_double2(gx, gy);
+        o[2] = make_double2(gz, (gz * py - gy * pz));
+        o[3] = make_double2((gx * pz - gz * px), (gy * px - gx * py));
+        if (sideJ) cSlot[kk].y = p;
+        else cSlot[kk].x = p;
+        if (k2 & 2) atomicOr(slotBi + (p >> 5), 1u << (p & 31));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // setup: q = delta0/dt + D^T v_nc (ConstraintSolver.cpp:18-27), K^-1/dt, bilateral flag, x0 = gamma guess
 __global__ void k_setup(long long nc, ConGeom g, const int *__restrict__ sUser, const double *__restrict__ velNC,
@@ -907,6 +948,140 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
 }
 
 // ------------------------------------------------------------------------------------------------
+// force_kernel = 3: f = D x, u = M f from per-slot records.
+//   k_slot_init      thread per slot: {x, g} of the slot's constraint row into the record and the row's mask bit into the
+//                    slot-ordered bitmap.  Runs once per BBPGD solve (iteration 0) and in front of every apply to a plain
+//                    vector (APGD, alens_operator_apply, the gamma o biFlag apply of the split); inside the BBPGD loop
+//                    k_bb_tail keeps records and bitmap current (rows that may be non-zero: 16 % of them on the bench
+//                    workload, 2 scattered 16-byte stores each; bitmap bits flipped with atomics only when they change).
+//   k_force_vel_rec  thread per rod: slot range -> bitmap words -> for every set bit ONE aligned 64-byte record
+//                    ({x_prev, g_prev} and the column block in the same line), x = P(x_prev - alpha g_prev) as in
+//                    k_bb_tail, products added in ascending slot order (the order of every other force kernel: results
+//                    are bit-identical), u = M f.  No constraint ids, no mask-word gathers, no shared memory; rods without
+//                    a live slot (45 %) skip their mobility data.  Algorithmic bytes: 4 (N+1) + 2 S/8 + 64 live slots +
+//                    49 N_live-rods + N + 48 N.
+struct SlotInit {
+    const int *incCon;
+    long long nInc;
+    double *rec;
+    unsigned *slotLive;
+};
+template <int XMODE>
+__global__ void __launch_bounds__(256) k_slot_init(SlotInit in, XIn xin) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int code = p < in.nInc ? ldStream(in.incCon + p) : -1;
+    bool live = code >= 0;
+    if (live && xin.mask) live = (__ldg(xin.mask + (code >> 7)) >> ((code >> 2) & 31)) & 1u;
+    if (live) {
+        double2 v;
+        if (XMODE == 2) v = ldGather2(xin.xg + (code >> 2));
+        else {
+            const double xv = __ldg(xin.x + (code >> 2));
+            v = make_double2(XMODE == 1 ? 1.0 * xv * ((code & 2) ? 1.0 : 0.0) : xv, 0.0);
+        }
+        *reinterpret_cast<double2 *>(in.rec + 8 * (size_t)p) = v;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0 && p < in.nInc + 32) in.slotLive[p >> 5] = m;
+}
+
+struct FvRec {
+    const int *incStart;
+    const double *rec;
+    const unsigned *slotLive, *slotBi;
+    int nRods;
+    int update; // 1: multiplier = P(x - alpha g) of the record's pair (BBPGD iterations >= 1), 0: the record's x as it is
+};
+
+template <bool WRITE_F, bool HALO>
+__global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, double *__restrict__ U, double *__restrict__ F,
+                                                       const SolverScalars *__restrict__ scal, HaloPush hp) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = r < in.nRods;
+    int b = 0, e = 0;
+    unsigned ghost = 1;
+    int mirL = -1, mirR = -1;
+    if (act) { // incidence structure: constant during a solve, requested before the wait
+        b = __ldg(in.incStart + r);
+        e = __ldg(in.incStart + r + 1);
+        ghost = mob.ghost[r];
+        if (HALO && hp.on) {
+            if (hp.mir[0]) mirL = hp.mir[0][r];
+            if (hp.mir[1]) mirR = hp.mir[1][r];
+        }
+    }
+    pdlWait(); // records, bitmap and step size come from the previous kernel
+    if (scal && scal->done) return;
+    const double alpha = (in.update && scal) ? scal->alpha : 0.0;
+    double f[6] = {0, 0, 0, 0, 0, 0};
+    bool any = false, pushed = false;
+    if (act && e > b) {
+        for (int wd = b >> 5; wd <= (e - 1) >> 5; wd++) {
+            unsigned bits = __ldg(in.slotLive + wd);
+            const int lo = wd << 5;
+            if (b > lo) bits &= ~((1u << (b - lo)) - 1u);
+            if (e < lo + 32) bits &= (1u << (e - lo)) - 1u;
+            if (!bits) continue;
+            any = true;
+            const unsigned biw = in.update ? __ldg(in.slotBi + wd) : 0u;
+            while (bits) { // ascending slot order
+                const int q = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const double2 *cp = reinterpret_cast<const double2 *>(in.rec + 8 * (size_t)(lo + q));
+                const double2 xg = ldGather2(cp), c01 = ldGather2(cp + 1), c23 = ldGather2(cp + 2), c45 = ldGather2(cp + 3);
+                const double x = in.update ? bbStep(xg.x, xg.y, alpha, (biw >> q) & 1u) : xg.x;
+                f[0] += c01.x * x; f[1] += c01.y * x; f[2] += c23.x * x;
+                f[3] += c23.y * x; f[4] += c45.x * x; f[5] += c45.y * x;
+            }
+        }
+    }
+    if (act && !ghost) {
+        double2 u0 = make_double2(0.0, 0.0), u1 = u0, u2 = u0;
+        if (any) { // a rod without a live slot has f = 0 and therefore u = +0 exactly: its mobility data is not read
+            const double qx = ldStream(mob.dx + r), qy = ldStream(mob.dy + r), qz = ldStream(mob.dz + r);
+            const double iPara = ldStream(mob.invDrag + r), iPerp = ldStream(mob.invDrag + mob.stride + r);
+            const double iRot = ldStream(mob.invDrag + 2 * mob.stride + r);
+            const double qf = qx * f[0] + qy * f[1] + qz * f[2];
+            const double px = qf * qx, py = qf * qy, pz = qf * qz;
+            u0 = make_double2(iPara * px + iPerp * (f[0] - px), iPara * py + iPerp * (f[1] - py));
+            u1 = make_double2(iPara * pz + iPerp * (f[2] - pz), iRot * f[3]);
+            u2 = make_double2(iRot * f[4], iRot * f[5]);
+        }
+        double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
+        Up[0] = u0; Up[1] = u1; Up[2] = u2;
+        if (WRITE_F) {
+            double2 *Fp = reinterpret_cast<double2 *>(F + 6 * (size_t)r);
+            Fp[0] = make_double2(f[0], f[1]);
+            Fp[1] = make_double2(f[2], f[3]);
+            Fp[2] = make_double2(f[4], f[5]);
+        }
+        if (HALO && mirL >= 0) {
+            double2 *Rp = reinterpret_cast<double2 *>(hp.rem[0] + 6 * (size_t)mirL);
+            Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+            pushed = true;
+        }
+        if (HALO && mirR >= 0) {
+            double2 *Rp = reinterpret_cast<double2 *>(hp.rem[1] + 6 * (size_t)mirR);
+            Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+            pushed = true;
+        }
+    }
+    if (HALO && hp.on && hp.ticket) { // fused multi-GPU: the last CTA of the grid releases the neighbours' halo flags
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(hp.ticket, 1u);
+            if (t == gridDim.x - 1) {
+                *hp.ticket = 0;
+                __threadfence_system();
+                if (hp.flag[0]) stReleaseSys(hp.flag[0], hp.seq);
+                if (hp.flag[1]) stReleaseSys(hp.flag[1], hp.seq);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // The same f = D x over live slots as two light kernels (force_kernel = 2).  k_force_vel_act keeps one 32-rod group per
 // warp in ~128 registers and its time is the serial latency of a warp's groups (ids -> mask -> {x,g} + columns -> sums,
 // measured ~10 700 cycles per group at 16 resident warps per SM).  Split by data dependence instead:
@@ -1143,6 +1318,12 @@ struct BbTail {
     int *prog;                // pinned host words {completed applies, done}: the host throttles its launches on them
     int keepXG;               // store {x, g} with the L2 evict_last policy (the force kernel gathers it next)
     unsigned *maskOut;        // bit k = 1 unless the NEXT iterate's x_k is certainly 0 (see k_bb_tail); nc/32 words
+    // force_kernel = 3 (k_force_vel_rec): the tail refreshes {x, g} in the slot records of the rows whose bit is set and
+    // flips their bits in the slot-ordered bitmap when the bit differs from the one of the previous iteration (maskOut is
+    // read before it is overwritten); rec = nullptr: off
+    double *rec;
+    const int2 *cSlot;
+    unsigned *slotLive;
     const unsigned char *own; // multi-rank: 1 = this rank counts the row in the dot products (nullptr = all)
     double *redOut;           // multi-rank: the reduced partials go here, k_bb_reduce finishes the step
     // fused multi-GPU variant (one rank per device): the kernel itself waits for the neighbours' ghost rows of U
@@ -1201,6 +1382,8 @@ struct TailRow {
     double gx, gy, gz, pIx, pIy, pIz, pJx, pJy, pJz, invK, b;
     double2 xg;
     unsigned char bi;
+    int2 sl;     // slot records of the row's two sides (force_kernel = 3)
+    unsigned mw; // the row's word of the previous iteration's mask
 };
 __device__ __forceinline__ unsigned char ldStreamU8(const unsigned char *p) {
     unsigned v;
@@ -1218,6 +1401,13 @@ __device__ __forceinline__ void loadTailRow(const BbTail &p, size_t k, TailRow &
     r.b = ldStream(p.b + k);
     r.invK = HASK ? ldStream(p.invKdt + k) : 0.0;
     r.bi = ldStreamU8(p.bi + k);
+    if (p.rec) {
+        const int2 *sp = p.cSlot + k;
+        asm volatile("ld.global.cs.v2.s32 {%0, %1}, [%2];" : "=r"(r.sl.x), "=r"(r.sl.y) : "l"(sp));
+        // the row's mask word of the previous iteration: written by the previous tail kernel (two kernels ago: safe before
+        // pdlWait), overwritten further down by this very warp; plain load (the array is written by this kernel)
+        asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(r.mw) : "l"(p.maskOut + (k >> 5)));
+    }
 }
 
 // x = P(x_prev - alpha g_prev), g = A x + b, residual, BB dots; the last CTA to finish turns the partials into the
@@ -1268,7 +1458,26 @@ __device__ __forceinline__ bool tailRowMath(const BbTail &p, const TailRow &cur,
     }
     // x_next = P(x - alpha_next g) with alpha_next > 0 (the loop stops on alpha < 10 eps): a unilateral row with x = 0 and
     // g >= 0 stays exactly 0 whatever alpha_next turns out to be -- its bit is 0.  NaN counts as "may be non-zero".
-    return cur.bi != 0 || !(x == 0.0) || !(gk >= 0.0);
+    const bool on = cur.bi != 0 || !(x == 0.0) || !(gk >= 0.0);
+    if (p.rec) { // slot records for k_force_vel_rec: the pair it will take its multiplier from, and the slot bitmap
+        const int sI = cur.sl.x, sJ = cur.sl.y;
+        if (on) {
+            const double2 v = make_double2(x, gk);
+            if (sI >= 0) *reinterpret_cast<double2 *>(p.rec + 8 * (size_t)sI) = v;
+            if (sJ >= 0) *reinterpret_cast<double2 *>(p.rec + 8 * (size_t)sJ) = v;
+        }
+        const bool was = (cur.mw >> ((unsigned)k & 31u)) & 1u;
+        if (on != was) {
+            if (on) {
+                if (sI >= 0) atomicOr(p.slotLive + (sI >> 5), 1u << (sI & 31));
+                if (sJ >= 0) atomicOr(p.slotLive + (sJ >> 5), 1u << (sJ & 31));
+            } else {
+                if (sI >= 0) atomicAnd(p.slotLive + (sI >> 5), ~(1u << (sI & 31)));
+                if (sJ >= 0) atomicAnd(p.slotLive + (sJ >> 5), ~(1u << (sJ & 31)));
+            }
+        }
+    }
+    return on;
 }
 
 // end of a tail kernel: CTA partials, last-CTA election, fixed-order reduction, (multi-rank allreduce,) scalar step
@@ -1848,7 +2057,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.incStride = ((nInc + 3) & ~3LL) + 4; // component stride: 16-byte aligned bulk copies may over-read < 4 slots
     c.incCon.reserve((size_t)c.incStride + 4);
     c.incRaw.reserve((size_t)nInc + 4);
-    c.incCol.reserve(kColRec * (size_t)c.incStride + 8);
+    if (c.incLayout != 3) c.incCol.reserve(kColRec * (size_t)c.incStride + 8);
     const size_t vcap = (size_t)nc + 32; // (+ padding: bulk copies read whole 16-row groups)
     c.vX0.reserve(vcap); c.vX1.reserve(vcap); c.vG0.reserve(vcap); c.vG1.reserve(vcap);
     c.vB.reserve(vcap); c.vLbFlag.reserve(vcap); c.vTmp5.reserve(vcap); // vTmp5 = invKdt
@@ -1857,8 +2066,22 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     c.outFU.reserve(6 * (size_t)n + 6); c.outVU.reserve(6 * (size_t)n + 6);
     c.outFB.reserve(6 * (size_t)n + 6); c.outVB.reserve(6 * (size_t)n + 6);
     c.redPartial.reserve(4 * (size_t)(gridFor(std::max<long long>(nc, 1), kVecBlock) + 1));
+    if (c.incLayout == 3) { // slot records (64 bytes each), per-row slot pairs, slot bitmaps
+        c.incRec.reserve(8 * ((size_t)nInc + 8));
+        c.cSlot.reserve((size_t)nc + 32);
+        c.slotBi.reserve((size_t)(nInc >> 5) + 4);
+        c.slotLive.reserve((size_t)(nInc >> 5) + 4);
+        ALENS_CUDA(cudaMemsetAsync(c.cSlot.p, 0xff, sizeof(int2) * ((size_t)nc + 32), st));
+        ALENS_CUDA(cudaMemsetAsync(c.slotBi.p, 0, sizeof(unsigned) * ((size_t)(nInc >> 5) + 4), st));
+        ALENS_CUDA(cudaMemsetAsync(c.slotLive.p, 0, sizeof(unsigned) * ((size_t)(nInc >> 5) + 4), st));
+    }
     if (nc > 0) {
-        if (c.incLayout == 1) { // rod-major: the raw slot lists are sorted in place and ARE incCon
+        if (c.incLayout == 3) {
+            k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.cBi.p, c.sGhost.p, c.incStart.p,
+                                                         c.incFill.p, c.incCon.p);
+            k_inc_emit_rec<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incCon.p, conGeom(c), c.incRec.p, c.cSlot.p,
+                                                            c.slotBi.p);
+        } else if (c.incLayout == 1) { // rod-major: the raw slot lists are sorted in place and ARE incCon
             k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.cBi.p, c.sGhost.p, c.incStart.p,
                                                          c.incFill.p, c.incCon.p);
             k_inc_emit_rm<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incCon.p, conGeom(c), c.incCol.p);
@@ -1990,6 +2213,42 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
     const HaloPush hp = push ? *push : HaloPush{};
     if (n == 0 && !push) return;
     profBegin(c, 0);
+    if (c.incLayout == 3) { // slot records: plain vectors and iteration 0 of BBPGD first fill {x, g} and the slot bitmap
+        const bool init = XMODE != 2 || !xin.update;
+        const long long nInc = c.nInc;
+        if (init) {
+            XIn xm = xin;
+            if (XMODE != 2 && c.nCon > 0) { // rows of a plain vector that can contribute
+                c.vMask2.reserve((size_t)(c.nCon >> 5) + 2);
+                const int g = gridFor(c.nCon, kVecBlock);
+                if (XMODE == 1) k_mask_from_x<true><<<g, kVecBlock, 0, c.stream>>>(c.nCon, xin.x, c.cBi.p, c.vMask2.p);
+                else k_mask_from_x<false><<<g, kVecBlock, 0, c.stream>>>(c.nCon, xin.x, c.cBi.p, c.vMask2.p);
+                c.launches++;
+                xm.mask = c.vMask2.p;
+            }
+            const SlotInit si{c.incCon.p, nInc, c.incRec.p, c.slotLive.p};
+            k_slot_init<XMODE><<<std::max(1, gridFor(nInc + 32, 256)), 256, 0, c.stream>>>(si, xm);
+            c.launches++;
+            c.timers.op_launches++;
+        }
+        const FvRec fr{c.incStart.p, c.incRec.p, c.slotLive.p, c.slotBi.p, n, init ? 0 : 1};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.stream = c.stream;
+        cfg.attrs = at;
+        cfg.gridDim = dim3((unsigned)std::max(1, gridFor(n, 128)));
+        cfg.blockDim = dim3(128);
+        cfg.numAttrs = c.pdlNow ? 1 : 0;
+        if (XMODE == 2 && !WF && hp.on)
+            ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, (XMODE == 2 && !WF)>), fr, mobIn(c), U, F, scal, hp));
+        else ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, false>), fr, mobIn(c), U, F, scal, hp));
+        profEnd(c);
+        c.launches++;
+        c.timers.op_launches++;
+        return;
+    }
     if (c.incLayout == 1) { // rod-major slots: active-set kernels
         XIn xm = xin;
         if (XMODE != 2 && c.optForceMask && c.nCon > 0) { // plain vector: one cheap pass marks its non-zero rows
@@ -2131,14 +2390,19 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     c.vXG1.reserve((size_t)nc + 32);
     double2 *XG[2] = {c.vXG0.p, c.vXG1.p};
     c.vMask.reserve((size_t)(nc >> 5) + 2);
-    const unsigned *mask = c.optForceMask ? c.vMask.p : nullptr;
+    const unsigned *mask = (c.optForceMask || c.incLayout == 3) ? c.vMask.p : nullptr;
     const int grid = std::max(1, gridFor(nc, kVecBlock));
     const int gridTail = std::min(grid, c.numSMs * c.optTailCtasPerSM); // persistent (2 resident CTAs per SM)
     BbTail t{};
     t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.bi = c.cBi.p;
     t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = c.histCap; t.tol = tol;
-    t.maskOut = c.optForceMask ? c.vMask.p : nullptr;
-    t.keepXG = c.optKeepXG;
+    t.maskOut = (c.optForceMask || c.incLayout == 3) ? c.vMask.p : nullptr;
+    t.keepXG = c.incLayout == 3 ? 0 : c.optKeepXG; // (nothing gathers the {x, g} array when the slot records are in use)
+    if (c.incLayout == 3 && nc > 0) {
+        t.rec = c.incRec.p;
+        t.cSlot = c.cSlot.p;
+        t.slotLive = c.slotLive.p;
+    }
     t.pdlTrig = c.optPdl == 2;
     t.ghostRange = (multi && c.optLateHalo && c.ghostRange.p) ? c.ghostRange.p : nullptr;
     if (multi) {
@@ -2165,7 +2429,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
                 hp.rem[d] = reinterpret_cast<double *>(m.peerWin[q] + m.offU);
             }
             hp.on = 1;
-            if (c.incLayout == 1) { // the force kernel releases the neighbours' halo flags itself (last warp)
+            if (c.incLayout != 0) { // the force kernel releases the neighbours' halo flags itself (last CTA)
                 for (int d = 0; d < 2; d++) {
                     const int q = d == 0 ? m.left : m.right;
                     hp.flag[d] = q < 0 ? nullptr : &reinterpret_cast<CommHeader *>(m.peerWin[q])->haloSeq[1 - d];
@@ -2174,7 +2438,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
                 hp.ticket = &c.dScal.p->ticketFv;
             }
             launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p, &hp);
-            if (c.incLayout != 1) commSignalHalo(c, seq);
+            if (c.incLayout == 0) commSignalHalo(c, seq);
             t.waitFlag[0] = m.left >= 0 ? &me->haloSeq[0] : nullptr;
             t.waitFlag[1] = m.right >= 0 ? &me->haloSeq[1] : nullptr;
             t.waitSeq = seq;
@@ -2193,13 +2457,13 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     };
     // host flow control through the progress words: single rank, or every rank on its own device with the fused kernels
     // (all ranks take bit-identical scalar steps, so they stop after the same iteration)
-    const bool poll = (!multi || (fused && c.incLayout == 1)) && c.optPoll && c.hProg != nullptr;
+    const bool poll = (!multi || (fused && c.incLayout != 0)) && c.optPoll && c.hProg != nullptr;
     const unsigned long long halo0 = c.comm.seqHalo, mail0 = c.comm.seqMail;
     if (poll) {
         c.hProg[0] = 0; c.hProg[1] = 0;
         t.prog = c.hProgDev;
     }
-    c.pdlNow = (!multi || fused) && c.optPdl && c.incLayout == 1;
+    c.pdlNow = (!multi || fused) && c.optPdl && c.incLayout != 0;
     // iteration 0: g0 = A x0 + b, {x0, g0} written in place
     if (nc > 0) {
         k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, XG[0], c.vMask.p);
@@ -2325,6 +2589,10 @@ double timeKernel(Context &c, int which, int reps) {
     ALENS_CUDA(cudaMemsetAsync(c.rU.p, 0, 48 * (size_t)c.nRods, st));
     const bool prof = c.profiling;
     c.profiling = false;
+    if (c.incLayout == 3) { // slot records and bitmap of x0, and a tail that maintains them
+        launchForceVel<2, false>(c, XIn{nullptr, c.vXG0.p, 0, c.vMask.p}, c.rU.p, nullptr, c.dScal.p);
+        t.maskOut = c.vMask.p; t.rec = c.incRec.p; t.cSlot = c.cSlot.p; t.slotLive = c.slotLive.p;
+    }
     auto one = [&]() {
         if (which == 0)
             launchForceVel<2, false>(c, XIn{nullptr, c.vXG0.p, 1, c.optForceMask ? c.vMask.p : nullptr}, c.rU.p, nullptr,
@@ -2616,6 +2884,13 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit_rm));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<false>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit_rec));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_init<0>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_init<1>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_init<2>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<true, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, true>)));
 }
 
 } // namespace alens

@@ -145,9 +145,10 @@ def check_solution(ctx, oracle, rods, orods, blocks, vnc, res, max_ite, choice, 
 
 @pytest.mark.parametrize("colbuf,zero_frac", [(0.025, 0.0), (0.025, 0.85), (0.15, 0.5), (0.15, 1.0)])
 def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
-    """k_force_vel_act (rod-major slots, x == 0 skipped) against k_force_vel_lm (level-major, dense) and the oracle.
+    """k_force_vel_rec (slot records + slot bitmap kept by the tail kernel: the default), k_force_vel_act (rod-major
+    slots, x == 0 skipped) and k_slot_x + k_rod_sum against k_force_vel_lm (level-major, dense) and the oracle.
     Skipping a zero multiplier must not change a single bit; colbuf 0.15 gives 32-rod groups with more than 256
-    slots (several batches per warp)."""
+    slots (several batches per warp) and rods with more than 32 slots (several bitmap words per rod)."""
     rods = random_rods(2000, 1.6, seed=21, frac_sphere=0.1)
     lo, hi = [0, 0, 0], [1.6] * 3
     blocks = gpu_collect(ctx, rods, lo, hi, (1, 1, 1), colbuf).copy()
@@ -161,27 +162,43 @@ def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
     x[rng.uniform(size=nc) < zero_frac] = 0.0
     x[::7] *= -1.0  # negative multipliers and -0.0 occur in plain operator applies
     res = {}
-    for kern in (1, 2, 0):  # 1 k_force_vel_act, 2 k_slot_x + k_rod_sum, 0 dense level-major
+    for kern in (3, 1, 2, 0):  # 3 k_force_vel_rec, 1 k_force_vel_act, 2 k_slot_x + k_rod_sum, 0 dense level-major
         ctx.set_option("force_kernel", kern)
         ctx.setup_constraints(None, DT)
         res[kern] = ctx.operator_apply(x, want_force_vel=True)
-    for kern in (1, 2):
+        if kern == 3:  # a second apply to another vector on the same setup: stale records / bits must not leak
+            x2 = np.where(rng.uniform(size=nc) < 0.5, 0.0, rng.normal(size=nc))
+            res["x2"] = (x2, ctx.operator_apply(x2, want_force_vel=True))
+            res[3] = ctx.operator_apply(x, want_force_vel=True)
+    for kern in (3, 1, 2):
         for a, b in zip(res[0], res[kern]):
             assert np.array_equal(a, b)
+    ctx.set_option("force_kernel", 0)
+    ctx.setup_constraints(None, DT)
+    for a, b in zip(ctx.operator_apply(res["x2"][0], want_force_vel=True), res["x2"][1]):
+        assert np.array_equal(a, b)
     yo, fo, vo = oracle.operator_apply(blocks, orods, rods["immovable"], MU, DT, x)
     for a, b in zip(res[1], (yo, fo, vo)):
         assert relerr(a, b) < 1e-12 or np.abs(b).max() == 0
     # the BBPGD loop (x recomputed on the fly from {x_prev, g_prev}) gives the same iterates with both kernels
     vnc = thermal_velocity(rods, MU, DT, seed=9)
     gam = {}
-    for kern in (1, 2, 0):
+    for kern in (3, 1, 2, 0):
         ctx.set_option("force_kernel", kern)
         rep = ctx.solve_constraints(vnc, DT, 1e-30, 15, 0)
         assert rep.iterations == 15
-        gam[kern] = (ctx.get_gamma(), ctx.get_force_velocity()["velU"])
-    for kern in (1, 2):
-        assert np.array_equal(gam[0][0], gam[kern][0]) and np.array_equal(gam[0][1], gam[kern][1])
-    ctx.set_option("force_kernel", 1)
+        gam[kern] = (ctx.get_gamma(), ctx.get_force_velocity()["velU"], ctx.get_history())
+    for kern in (3, 1, 2):
+        for a, b in zip(gam[0], gam[kern]):
+            assert np.array_equal(a, b)
+    # ... and a long run on the default kernel: rows leave and re-enter the live set many times
+    for kern in (3, 0):
+        ctx.set_option("force_kernel", kern)
+        rep = ctx.solve_constraints(vnc, DT, 1e-30, 150, 0)
+        gam[kern] = (ctx.get_gamma(), ctx.get_force_velocity()["velU"], ctx.get_history())
+    for a, b in zip(gam[0], gam[3]):
+        assert np.array_equal(a, b)
+    ctx.set_option("force_kernel", 3)
 
 
 def test_bbpgd_matches_oracle_iterates(ctx, oracle):
