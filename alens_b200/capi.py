@@ -36,7 +36,8 @@ EXPORTS = [
     "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
     "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral", "alens_calc_velocity_noncon", "alens_calc_velocity_brown",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
-    "alens_dcp_query", "alens_pair_functor", "alens_comm_mode",
+    "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest",
+    "alens_get_live_stats",
 ]
 
 
@@ -286,6 +287,18 @@ class Context:
         a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
         self._call("alens_num_ghosts", C.byref(a), C.byref(b), C.byref(c))
         return dict(ghosts=a.value, sent_left=b.value, sent_right=c.value)
+
+    def get_live_stats(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._call("alens_get_live_stats", C.byref(a), C.byref(b))
+        return dict(live_slots=a.value, live_rods=b.value)
+
+    def constraint_digest(self):
+        """order-independent digest of the pool: dict(rows, list_hash, gamma_hash, sum_gamma, sum_gamma2, sum_wgamma)"""
+        u = (C.c_ulonglong * 3)()
+        f = (C.c_double * 3)()
+        self._call("alens_constraint_digest", u, f)
+        return dict(rows=int(u[0]), list_hash=int(u[1]), gamma_hash=int(u[2]), sum_gamma=f[0], sum_gamma2=f[1], sum_wgamma=f[2])
 
     def comm_mode(self):
         a, b = C.c_int(0), C.c_int(0)

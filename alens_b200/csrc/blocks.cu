@@ -616,6 +616,92 @@ void pairFunctorBatch(Context &c, long long n, const double *geomI, const double
     ALENS_CUDA(cudaStreamSynchronize(st));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Order-independent digest of the constraint list and of the solved multipliers, computed on the device (bench.py's
+// parity flag: the list of a multi-GPU run against the single-GPU run of the same suspension, fused against unfused
+// protocol, without moving 272-byte blocks to the host).  A row mirrored on two ranks is counted by the owner of rod I.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+struct DigestIn {
+    long long n;
+    const int *gidI, *gidJ;
+    const double *delta0, *labJ; // labJ: [3][stride]
+    size_t stride;
+    const unsigned char *own;    // nullptr: every row counts
+    const double *gamma;         // nullptr: no solve yet
+};
+__global__ void __launch_bounds__(256) k_constraint_digest(DigestIn in, unsigned long long *__restrict__ u64,
+                                                           double *__restrict__ part) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cnt = 0, hl = 0, hg = 0;
+    double s0 = 0, s1 = 0, s2 = 0;
+    if (k < in.n && (!in.own || in.own[k])) {
+        const unsigned long long key = ((unsigned long long)(unsigned)in.gidI[k] << 32) | (unsigned)in.gidJ[k];
+        unsigned long long h = mix64(key + 0x9E3779B97F4A7C15ull);
+        h = mix64(h + (unsigned long long)__double_as_longlong(in.labJ[k]));
+        h = mix64(h + (unsigned long long)__double_as_longlong(in.labJ[k + in.stride]));
+        h = mix64(h + (unsigned long long)__double_as_longlong(in.labJ[k + 2 * in.stride]));
+        cnt = 1;
+        hl = mix64(h + (unsigned long long)__double_as_longlong(in.delta0[k]));
+        if (in.gamma) {
+            const double g = in.gamma[k];
+            hg = mix64(h + (unsigned long long)__double_as_longlong(g));
+            const double w = (double)(h >> 44) * (1.0 / 1048576.0); // weight in [0, 1) tied to the row's identity
+            s0 = g; s1 = g * g; s2 = w * g;
+        }
+    }
+    __shared__ double sh[3][8];
+    __shared__ unsigned long long su[3][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        hl += __shfl_xor_sync(0xffffffffu, hl, o);
+        hg += __shfl_xor_sync(0xffffffffu, hg, o);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) { su[0][w] = cnt; su[1][w] = hl; su[2][w] = hg; sh[0][w] = s0; sh[1][w] = s1; sh[2][w] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) {
+            su[0][0] += su[0][i]; su[1][0] += su[1][i]; su[2][0] += su[2][i];
+            sh[0][0] += sh[0][i]; sh[1][0] += sh[1][i]; sh[2][0] += sh[2][i];
+        }
+        atomicAdd(u64 + 0, su[0][0]); atomicAdd(u64 + 1, su[1][0]); atomicAdd(u64 + 2, su[2][0]);
+        part[3 * (size_t)blockIdx.x] = sh[0][0]; part[3 * (size_t)blockIdx.x + 1] = sh[1][0];
+        part[3 * (size_t)blockIdx.x + 2] = sh[2][0];
+    }
+}
+
+void constraintDigest(Context &c, unsigned long long u64[3], double f64[3]) {
+    u64[0] = u64[1] = u64[2] = 0;
+    f64[0] = f64[1] = f64[2] = 0;
+    const long long n = c.nCon;
+    if (n <= 0) return;
+    cudaStream_t st = c.stream;
+    const int grid = gridFor(n, 256);
+    DevBuf<unsigned long long> dU;
+    DevBuf<double> dP;
+    dU.reserve(4);
+    dP.reserve(3 * (size_t)grid);
+    ALENS_CUDA(cudaMemsetAsync(dU.p, 0, 3 * sizeof(unsigned long long), st));
+    DigestIn in{n, c.cGidI.p, c.cGidJ.p, c.cDelta0.p, c.cLabJ.p, c.conCap, c.comm.active ? c.cOwn.p : nullptr,
+                c.haveSolution ? c.xSolution : nullptr};
+    k_constraint_digest<<<grid, 256, 0, st>>>(in, dU.p, dP.p);
+    c.launches++;
+    ALENS_CUDA(cudaGetLastError());
+    std::vector<double> part(3 * (size_t)grid);
+    ALENS_CUDA(cudaMemcpyAsync(u64, dU.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaMemcpyAsync(part.data(), dP.p, 8 * part.size(), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < grid; b++) // fixed order
+        for (int k = 0; k < 3; k++) f64[k] += part[3 * (size_t)b + k];
+}
+
 // Force the (lazily loaded) kernels of this file into the context now: loading a kernel at its first launch can
 // synchronise the context, which deadlocks against a peer rank's waiting kernel when two ranks share one GPU.
 void preloadBlockKernels() {
@@ -623,6 +709,7 @@ void preloadBlockKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_append));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_blocks_out));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_dcp_batch));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_constraint_digest));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_pair_functor_batch));
 }
 

@@ -442,6 +442,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
             c.optForceSplit = value == 2;
             if (c.optForceKernel == 3) c.optTailRing = 0; // the TMA-staged tail does not maintain the slot records
         }
+        else if (k == "rec_mode") c.optRecMode = value != 0;
         else if (k == "find_minb") c.optFindMinB = (value == 5 || value == 3) ? (int)value : 4;
         else if (k == "find_split") c.optFindSplit = value != 0;
         else if (k == "find_split_minb") c.optFindSplitMinB = value == 6 ? 6 : 8;
@@ -568,6 +569,75 @@ int alens_num_ghosts(alens_ctx *ctx, int *nGhost, int *nSentLeft, int *nSentRigh
         if (nGhost) *nGhost = c.nGhost;
         if (nSentLeft) *nSentLeft = c.comm.nSend[0];
         if (nSentRight) *nSentRight = c.comm.nSend[1];
+    });
+}
+
+/* ---- BCQPSolver for any caller ------------------------------------------------------------------ */
+struct alens_bcqp {
+    alens_ctx *ctx;
+    Bcqp *q;
+};
+int alens_bcqp_create_csr(alens_ctx *ctx, int n, const long long *rowPtr, const int *colInd, const double *values,
+                          const double *b, alens_bcqp **out) {
+    if (!out) return ALENS_ERR_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&](Context &c) {
+        if (!rowPtr) throw ArgError{ALENS_ERR_ARG, "alens_bcqp_create_csr: null matrix"};
+        Bcqp *q = bcqpCreate(c, n, rowPtr, colInd, values, b);
+        *out = new alens_bcqp{ctx, q};
+    });
+}
+int alens_bcqp_create_constraint(alens_ctx *ctx, const double *b, alens_bcqp **out) {
+    if (!out) return ALENS_ERR_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&](Context &c) {
+        Bcqp *q = bcqpCreate(c, 0, nullptr, nullptr, nullptr, b);
+        *out = new alens_bcqp{ctx, q};
+    });
+}
+int alens_bcqp_set_lower_bound(alens_bcqp *p, const double *lb) {
+    if (!p) return ALENS_ERR_ARG;
+    return guarded(p->ctx, [&](Context &) { bcqpSetBounds(*p->q, lb, nullptr, 1); });
+}
+int alens_bcqp_set_upper_bound(alens_bcqp *p, const double *ub) {
+    if (!p) return ALENS_ERR_ARG;
+    return guarded(p->ctx, [&](Context &) { bcqpSetBounds(*p->q, nullptr, ub, 2); });
+}
+int alens_bcqp_get_bounds(alens_bcqp *p, double *lb, double *ub) {
+    if (!p) return ALENS_ERR_ARG;
+    return guarded(p->ctx, [&](Context &) { bcqpGetBounds(*p->q, lb, ub); });
+}
+int alens_bcqp_run(alens_bcqp *p, double *x, double tol, int maxIte, int solverChoice, alens_solve_report *report) {
+    if (!p) return ALENS_ERR_ARG;
+    return guarded(p->ctx, [&](Context &) { bcqpSolve(*p->q, x, tol, maxIte, solverChoice, report); });
+}
+int alens_bcqp_history(alens_bcqp *p, double *rows6, int capRows, int *nRows) {
+    if (!p) return ALENS_ERR_ARG;
+    return guarded(p->ctx, [&](Context &) {
+        const int n = bcqpHistory(*p->q, rows6, capRows);
+        if (nRows) *nRows = n;
+    });
+}
+int alens_bcqp_size(alens_bcqp *p) { return p ? bcqpSize(*p->q) : 0; }
+void alens_bcqp_destroy(alens_bcqp *p) {
+    if (!p) return;
+    guarded(p->ctx, [&](Context &) { bcqpDestroy(p->q); });
+    delete p;
+}
+
+int alens_get_live_stats(alens_ctx *ctx, long long *liveSlots, long long *liveRods) {
+    return guarded(ctx, [&](Context &c) {
+        long long a = 0, b = 0;
+        liveStats(c, &a, &b);
+        if (liveSlots) *liveSlots = a;
+        if (liveRods) *liveRods = b;
+    });
+}
+
+int alens_constraint_digest(alens_ctx *ctx, unsigned long long counts3[3], double sums3[3]) {
+    return guarded(ctx, [&](Context &c) {
+        if (!counts3 || !sums3) throw ArgError{ALENS_ERR_ARG, "alens_constraint_digest: null output"};
+        constraintDigest(c, counts3, sums3);
     });
 }
 

@@ -264,6 +264,7 @@ struct Context {
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 3;                 // 3 = k_force_vel_rec (64-byte slot records + slot-ordered live bitmap kept by k_bb_tail), 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
+    int optRecMode = 1, recMode = 1;        // force_kernel 3: 0 = k_bb_tail copies {x, g} into the slot records, 1 = the records hold the row id and k_force_vel_rec gathers {x, g} itself
     DevBuf<double> incRec;                  // force_kernel 3: 8 doubles per slot {x, g, D column block[6]}, 64-byte aligned records
     DevBuf<int2> cSlot;                     // ... per constraint: slot of its I side / J side (-1: none, ghost or one-sided)
     DevBuf<unsigned> slotBi;                // ... bit per slot: the slot's constraint is bilateral (constant during a solve)
@@ -364,6 +365,18 @@ void dcpBatch(Context &c, long long n, const double *P0, const double *P1, const
               double *Ploc, double *Qloc);
 void pairFunctorBatch(Context &c, long long n, const double *geomI, const double *geomJ, int withStress, unsigned char *hit,
                       alens_constraint_block *blocks);
+// bcqp.cu: BCQPSolver for any caller (CSR matrix or the constraint operator, caller-set bounds)
+struct Bcqp;
+Bcqp *bcqpCreate(Context &c, int n, const long long *rowPtr, const int *col, const double *val, const double *b);
+void bcqpSetBounds(Bcqp &q, const double *lb, const double *ub, int which);
+void bcqpGetBounds(Bcqp &q, double *lb, double *ub);
+void bcqpSolve(Bcqp &q, double *x, double tol, int iteMax, int choice, alens_solve_report *rep);
+int bcqpHistory(Bcqp &q, double *rows6, int cap);
+int bcqpSize(Bcqp &q);
+Context *bcqpContext(Bcqp &q);
+void bcqpDestroy(Bcqp *q);
+void liveStats(Context &c, long long *slots, long long *rods);
+void constraintDigest(Context &c, unsigned long long u64[3], double f64[3]);
 void preloadCollideKernels();
 void preloadSolverKernels();
 void preloadBlockKernels();

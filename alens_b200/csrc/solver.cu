@@ -382,7 +382,7 @@ __global__ void k_inc_emit_rec(int nRods, const int *__restrict__ start, int *__
         const double px = P[kk], py = P[kk + g.stride], pz = P[kk + 2 * g.stride];
         if (sideJ) { gx = -gx; gy = -gy; gz = -gz; }
         double2 *o = reinterpret_cast<double2 *>(rec + 8 * (size_t)p);
-        o[0] = make_double2(0.0, 0.0);
+        o[0] = make_double2(__longlong_as_double((long long)k2), 0.0); // rec_mode 1: the slot code; rec_mode 0: {x, g} later
         o[1] = make_double2(gx, gy);
         o[2] = make_double2(gz, (gz * py - gy * pz));
         o[3] = make_double2((gx * pz - gz * px), (gy * px - gx * py));
@@ -514,6 +514,13 @@ __device__ __forceinline__ double2 ldGather2Keep(const double2 *p, unsigned long
 }
 __device__ __forceinline__ void stKeep2(double2 *p, double2 v, unsigned long long pol) {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+// 256-bit global store / load (PTX ISA 8.8, sm_100+): one 32-byte sector per instruction; p must be 32-byte aligned
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 __device__ __forceinline__ double2 ldGather2(const double2 *p) {
     double2 v;
@@ -963,7 +970,7 @@ k_force_vel_act(FvAct in, MobIn mob, XIn xin, double *__restrict__ U, double *__
 struct SlotInit {
     const int *incCon;
     long long nInc;
-    double *rec;
+    double *rec; // nullptr (rec_mode 1): only the bitmap is written, the force kernel gathers its multipliers by row id
     unsigned *slotLive;
 };
 template <int XMODE>
@@ -972,7 +979,7 @@ __global__ void __launch_bounds__(256) k_slot_init(SlotInit in, XIn xin) {
     const int code = p < in.nInc ? ldStream(in.incCon + p) : -1;
     bool live = code >= 0;
     if (live && xin.mask) live = (__ldg(xin.mask + (code >> 7)) >> ((code >> 2) & 31)) & 1u;
-    if (live) {
+    if (live && in.rec) {
         double2 v;
         if (XMODE == 2) v = ldGather2(xin.xg + (code >> 2));
         else {
@@ -991,6 +998,11 @@ struct FvRec {
     const unsigned *slotLive, *slotBi;
     int nRods;
     int update; // 1: multiplier = P(x - alpha g) of the record's pair (BBPGD iterations >= 1), 0: the record's x as it is
+    // rec_mode 1: the record's first 8 bytes hold the slot code (4 row + 2 bilateral + side); the multiplier is gathered
+    // from the row-ordered {x, g} pairs (xg) or a plain vector (x; xmode 1: times the bilateral flag)
+    const double2 *xg;
+    const double *x;
+    int xmode;
 };
 
 template <bool WRITE_F, bool HALO>
@@ -1027,11 +1039,25 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
             while (bits) { // ascending slot order
                 const int q = __ffs(bits) - 1;
                 bits &= bits - 1u;
-                const double2 *cp = reinterpret_cast<const double2 *>(in.rec + 8 * (size_t)(lo + q));
-                const double2 xg = ldGather2(cp), c01 = ldGather2(cp + 1), c23 = ldGather2(cp + 2), c45 = ldGather2(cp + 3);
-                const double x = in.update ? bbStep(xg.x, xg.y, alpha, (biw >> q) & 1u) : xg.x;
-                f[0] += c01.x * x; f[1] += c01.y * x; f[2] += c23.x * x;
-                f[3] += c23.y * x; f[4] += c45.x * x; f[5] += c45.y * x;
+                const double *cp = in.rec + 8 * (size_t)(lo + q);
+                double xp, gp, c0, c1, c2, c3, c4, c5;
+                ld256(cp, xp, gp, c0, c1); // the record's two sectors: {x, g, col[0..1]} and {col[2..5]}
+                ld256(cp + 4, c2, c3, c4, c5);
+                double x;
+                if (in.xg || in.x) { // rec_mode 1: one more (dependent) 16-byte gather, nothing written by the tail
+                    const int code = (int)__double_as_longlong(xp);
+                    if (in.xg) {
+                        const double2 v = ldGather2(in.xg + (code >> 2));
+                        x = in.update ? bbStep(v.x, v.y, alpha, (code & 2) != 0) : v.x;
+                    } else {
+                        const double xv = __ldg(in.x + (code >> 2));
+                        x = in.xmode == 1 ? 1.0 * xv * ((code & 2) ? 1.0 : 0.0) : xv;
+                    }
+                } else {
+                    x = in.update ? bbStep(xp, gp, alpha, (biw >> q) & 1u) : xp;
+                }
+                f[0] += c0 * x; f[1] += c1 * x; f[2] += c2 * x;
+                f[3] += c3 * x; f[4] += c4 * x; f[5] += c5 * x;
             }
         }
     }
@@ -1318,9 +1344,9 @@ struct BbTail {
     int *prog;                // pinned host words {completed applies, done}: the host throttles its launches on them
     int keepXG;               // store {x, g} with the L2 evict_last policy (the force kernel gathers it next)
     unsigned *maskOut;        // bit k = 1 unless the NEXT iterate's x_k is certainly 0 (see k_bb_tail); nc/32 words
-    // force_kernel = 3 (k_force_vel_rec): the tail refreshes {x, g} in the slot records of the rows whose bit is set and
-    // flips their bits in the slot-ordered bitmap when the bit differs from the one of the previous iteration (maskOut is
-    // read before it is overwritten); rec = nullptr: off
+    // force_kernel = 3 (k_force_vel_rec): the tail flips a row's bits in the slot-ordered bitmap when the row's bit differs
+    // from the one of the previous iteration (maskOut is read before it is overwritten; slotLive = nullptr: off) and, in
+    // rec_mode 0 (rec != nullptr), refreshes {x, g} in the slot records of the rows whose bit is set
     double *rec;
     const int2 *cSlot;
     unsigned *slotLive;
@@ -1401,9 +1427,11 @@ __device__ __forceinline__ void loadTailRow(const BbTail &p, size_t k, TailRow &
     r.b = ldStream(p.b + k);
     r.invK = HASK ? ldStream(p.invKdt + k) : 0.0;
     r.bi = ldStreamU8(p.bi + k);
-    if (p.rec) {
-        const int2 *sp = p.cSlot + k;
-        asm volatile("ld.global.cs.v2.s32 {%0, %1}, [%2];" : "=r"(r.sl.x), "=r"(r.sl.y) : "l"(sp));
+    if (p.slotLive) {
+        if (p.rec) { // rec_mode 0: the slots are needed for every row that may be non-zero: streamed with the row
+            const int2 *sp = p.cSlot + k;
+            asm volatile("ld.global.cs.v2.s32 {%0, %1}, [%2];" : "=r"(r.sl.x), "=r"(r.sl.y) : "l"(sp));
+        }
         // the row's mask word of the previous iteration: written by the previous tail kernel (two kernels ago: safe before
         // pdlWait), overwritten further down by this very warp; plain load (the array is written by this kernel)
         asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(r.mw) : "l"(p.maskOut + (k >> 5)));
@@ -1459,15 +1487,20 @@ __device__ __forceinline__ bool tailRowMath(const BbTail &p, const TailRow &cur,
     // x_next = P(x - alpha_next g) with alpha_next > 0 (the loop stops on alpha < 10 eps): a unilateral row with x = 0 and
     // g >= 0 stays exactly 0 whatever alpha_next turns out to be -- its bit is 0.  NaN counts as "may be non-zero".
     const bool on = cur.bi != 0 || !(x == 0.0) || !(gk >= 0.0);
-    if (p.rec) { // slot records for k_force_vel_rec: the pair it will take its multiplier from, and the slot bitmap
-        const int sI = cur.sl.x, sJ = cur.sl.y;
-        if (on) {
-            const double2 v = make_double2(x, gk);
-            if (sI >= 0) *reinterpret_cast<double2 *>(p.rec + 8 * (size_t)sI) = v;
-            if (sJ >= 0) *reinterpret_cast<double2 *>(p.rec + 8 * (size_t)sJ) = v;
+    if (p.slotLive) { // for k_force_vel_rec: the slot bitmap, and (rec_mode 0) the pair it will take its multiplier from
+        const bool was0 = (cur.mw >> ((unsigned)k & 31u)) & 1u;
+        int sI = cur.sl.x, sJ = cur.sl.y;
+        if (!p.rec && on != was0) { // rec_mode 1: the slots of the few rows whose bit flips are gathered here
+            const int2 sl = p.cSlot[k];
+            sI = sl.x; sJ = sl.y;
         }
-        const bool was = (cur.mw >> ((unsigned)k & 31u)) & 1u;
-        if (on != was) {
+        if (on && p.rec) {
+            // the whole first 32-byte sector of the record {x, g, col[0], col[1]} = {x, g, +-n_x, +-n_y} in ONE 256-bit store
+            // (sm_100): a full-sector write needs no read-for-merge in L2, a 16-byte one would
+            if (sI >= 0) st256(p.rec + 8 * (size_t)sI, x, gk, gx, gy);
+            if (sJ >= 0) st256(p.rec + 8 * (size_t)sJ, x, gk, -gx, -gy);
+        }
+        if (on != was0) {
             if (on) {
                 if (sI >= 0) atomicOr(p.slotLive + (sI >> 5), 1u << (sI & 31));
                 if (sJ >= 0) atomicOr(p.slotLive + (sJ >> 5), 1u << (sJ & 31));
@@ -2054,6 +2087,7 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
         throw ArgError{ALENS_ERR_UNSUPPORTED, "setup: more than 2^29 constraints / 2^31 incidence slots on one GPU"};
     c.nInc = nInc;
     c.incLayout = c.optForceKernel; // fixed for this setup: the force kernels follow the layout that was built
+    c.recMode = c.optRecMode;
     c.incStride = ((nInc + 3) & ~3LL) + 4; // component stride: 16-byte aligned bulk copies may over-read < 4 slots
     c.incCon.reserve((size_t)c.incStride + 4);
     c.incRaw.reserve((size_t)nInc + 4);
@@ -2226,12 +2260,16 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
                 c.launches++;
                 xm.mask = c.vMask2.p;
             }
-            const SlotInit si{c.incCon.p, nInc, c.incRec.p, c.slotLive.p};
+            const SlotInit si{c.incCon.p, nInc, c.recMode == 0 ? c.incRec.p : nullptr, c.slotLive.p};
             k_slot_init<XMODE><<<std::max(1, gridFor(nInc + 32, 256)), 256, 0, c.stream>>>(si, xm);
             c.launches++;
             c.timers.op_launches++;
         }
-        const FvRec fr{c.incStart.p, c.incRec.p, c.slotLive.p, c.slotBi.p, n, init ? 0 : 1};
+        FvRec fr{c.incStart.p, c.incRec.p, c.slotLive.p, c.slotBi.p, n, init ? 0 : 1, nullptr, nullptr, XMODE};
+        if (c.recMode == 1) {
+            if (XMODE == 2) fr.xg = xin.xg;
+            else fr.x = xin.x;
+        }
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -2399,7 +2437,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     t.maskOut = (c.optForceMask || c.incLayout == 3) ? c.vMask.p : nullptr;
     t.keepXG = c.incLayout == 3 ? 0 : c.optKeepXG; // (nothing gathers the {x, g} array when the slot records are in use)
     if (c.incLayout == 3 && nc > 0) {
-        t.rec = c.incRec.p;
+        t.rec = c.recMode == 0 ? c.incRec.p : nullptr;
         t.cSlot = c.cSlot.p;
         t.slotLive = c.slotLive.p;
     }
@@ -2545,6 +2583,42 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     return c.hScal->done == 2 ? 1 : 0;
 }
 
+// instrumentation (bench.py's roofline accounting of k_force_vel_rec): slots whose bit is set in the slot bitmap and rods
+// with at least one such slot, in the state the last solve / apply left behind
+__global__ void k_live_stats(int nRods, const int *__restrict__ incStart, const unsigned *__restrict__ slotLive,
+                             unsigned long long *__restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (r < nRods) {
+        const int b = incStart[r], e = incStart[r + 1];
+        for (int wd = b >> 5; e > b && wd <= (e - 1) >> 5; wd++) {
+            unsigned bits = slotLive[wd];
+            const int lo = wd << 5;
+            if (b > lo) bits &= ~((1u << (b - lo)) - 1u);
+            if (e < lo + 32) bits &= (1u << (e - lo)) - 1u;
+            cnt += __popc(bits);
+        }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, cnt > 0);
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(out, (unsigned long long)cnt);
+        atomicAdd(out + 1, (unsigned long long)__popc(any));
+    }
+}
+void liveStats(Context &c, long long *slots, long long *rods) {
+    *slots = *rods = 0;
+    if (c.incLayout != 3 || !c.haveSetup || c.nRods == 0 || c.nInc == 0) return;
+    cudaStream_t st = c.stream;
+    ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 2 * sizeof(unsigned long long), st));
+    k_live_stats<<<gridFor(c.nRods, 256), 256, 0, st>>>(c.nRods, c.incStart.p, c.slotLive.p, c.dCounters.p);
+    unsigned long long h[2] = {0, 0};
+    ALENS_CUDA(cudaMemcpyAsync(h, c.dCounters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    *slots = (long long)h[0];
+    *rods = (long long)h[1];
+}
+
 // instrumentation: average device time of one BBPGD kernel on the current setup (alens_time_kernel).
 // Leaves the solver scalars / iterates in an unspecified state: run a setup or solve afterwards.
 double timeKernel(Context &c, int which, int reps) {
@@ -2591,7 +2665,7 @@ double timeKernel(Context &c, int which, int reps) {
     c.profiling = false;
     if (c.incLayout == 3) { // slot records and bitmap of x0, and a tail that maintains them
         launchForceVel<2, false>(c, XIn{nullptr, c.vXG0.p, 0, c.vMask.p}, c.rU.p, nullptr, c.dScal.p);
-        t.maskOut = c.vMask.p; t.rec = c.incRec.p; t.cSlot = c.cSlot.p; t.slotLive = c.slotLive.p;
+        t.maskOut = c.vMask.p; t.rec = c.recMode == 0 ? c.incRec.p : nullptr; t.cSlot = c.cSlot.p; t.slotLive = c.slotLive.p;
     }
     auto one = [&]() {
         if (which == 0)
@@ -2630,6 +2704,9 @@ static void applyA(Context &c, const double *x, double *y) { // y = A x, caches 
     c.launches++; c.timers.op_launches++;
     c.xLastApplied = const_cast<double *>(x);
 }
+
+// for the general BCQP front end (bcqp.cu): y = A x on device vectors with the operator of the last setup
+void operatorApplyDevice(Context &c, const double *x, double *y) { applyA(c, x, y); }
 
 // BCQPSolver::solveAPGD (BCQPSolver.cpp:249-389); scalar control flow stays on the host.
 static int solveAPGD(Context &c, double tol, int maxIte) {

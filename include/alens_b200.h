@@ -219,6 +219,25 @@ int alens_operator_apply(alens_ctx *ctx, const double *x, double *y, double *for
  * alens_get_force_velocity are refreshed as in ConstraintSolver::solveConstraints. */
 int alens_bcqp_solve(alens_ctx *ctx, const double *b, double *x, double tol, int maxIte, int solverChoice,
                      alens_solve_report *report);
+/* BCQPSolver as ANY caller sees it (BCQPSolver.hpp:37-111): A = a CSR matrix of the caller (the reference's TCMAT; e.g. its
+ * own random self-test problem BCQPSolver(int, double), BCQPSolver.cpp:38-132) or the constraint operator of the last
+ * alens_setup_constraints; b and the bounds are the caller's (setLowerBound / setUpperBound; NULL = the default
+ * -+DBL_MAX/10 of setDefaultBounds, BCQPSolver.cpp:499-510).  The loops of solveBBPGD / solveAPGD run as device vector
+ * kernels, one per Tpetra call of the reference, scalar control on the host; x: in = initial guess, out = result
+ * (after an iteMax exit of BBPGD the older iterate, as in the reference).  A projection error (BCQPSolver.cpp:484-494)
+ * returns ALENS_ERR_PROJECTION. */
+typedef struct alens_bcqp alens_bcqp;
+int alens_bcqp_create_csr(alens_ctx *ctx, int n, const long long *rowPtr, const int *colInd, const double *values,
+                          const double *b, alens_bcqp **out);
+/* b == NULL: q of the setup (delta0/dt + D^T velNonCon) */
+int alens_bcqp_create_constraint(alens_ctx *ctx, const double *b, alens_bcqp **out);
+int alens_bcqp_set_lower_bound(alens_bcqp *p, const double *lb);
+int alens_bcqp_set_upper_bound(alens_bcqp *p, const double *ub);
+int alens_bcqp_get_bounds(alens_bcqp *p, double *lb, double *ub);
+int alens_bcqp_run(alens_bcqp *p, double *x, double tol, int maxIte, int solverChoice, alens_solve_report *report);
+int alens_bcqp_history(alens_bcqp *p, double *rows6, int capRows, int *nRows);
+int alens_bcqp_size(alens_bcqp *p);
+void alens_bcqp_destroy(alens_bcqp *p);
 /* IteHistory rows {ite,0,0,alpha,resPhi,mvCount} (BCQPSolver.hpp:23) */
 int alens_get_history(alens_ctx *ctx, double *rows6, int capRows, int *nRows);
 /* gamma in solver (= alens_get_constraints) order */
@@ -250,8 +269,18 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value);
  * "force_vel_plain" on the operator of the last alens_setup_constraints (invalidates the setup), or "force_vel_last" on
  * the iterate / mask the last BBPGD solve left behind. */
 int alens_time_kernel(alens_ctx *ctx, const char *which, int reps, double *avgMicroseconds);
+/* force_kernel 3: incidence slots whose bit is set in the slot bitmap, and rods with at least one such slot, as the last
+ * solve left them (what k_force_vel_rec reads per launch: 64 bytes per live slot, mobility data per live rod) */
+int alens_get_live_stats(alens_ctx *ctx, long long *liveSlots, long long *liveRods);
 /* number of rods / cells / candidate pairs that passed the broad phase in the last collection */
 int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCandidates, long long *nHits);
+
+/* Order-independent digest of the pool, computed on the device: counts3 = {rows, sum of hash(gidI, gidJ, labJ bits, delta0
+ * bits), sum of hash(gidI, gidJ, labJ bits, gamma bits)} (64-bit wrap-around sums), sums3 = {sum gamma, sum gamma^2, sum
+ * w gamma} with a weight w in [0,1) derived from the row's identity; gamma = the last solve's result (zeros before).  With a
+ * slab decomposition each rank counts the rows whose rod I it owns, so the per-rank digests ADD UP to the digest of the
+ * single-rank list (reference canonicalisation: Sylinder/Test2_MixLink/Verify.py:82-83 sorts by the same keys). */
+int alens_constraint_digest(alens_ctx *ctx, unsigned long long counts3[3], double sums3[3]);
 
 /* ---- multi-GPU (one rank per GPU) ------------------------------------------------------
  * Slab decomposition along one box axis.  Replaces, for the constraint path, the FDPS ghost exchange inside

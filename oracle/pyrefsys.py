@@ -291,7 +291,7 @@ class RefSystem:
         out = np.zeros(max(n, 1), dtype=BLOCK_DTYPE)
         gamma = np.zeros(max(n, 1))
         res_ = {k: np.zeros(n6) for k in ("forceU", "velU", "forceB", "velB")}
-        hist = np.zeros((hist_cap, 6))
+        hist = np.zeros((max(hist_cap, 1), 6))
         nh = C.c_int(0)
         rc = self._q(self.L.refsys_solve_blocks, C.c_void_p(b.ctypes.data), C.c_longlong(n), _dp(v), C.c_double(dt),
                      C.c_double(res), int(max_ite), int(choice), C.c_void_p(out.ctypes.data), _dp(gamma),
@@ -299,8 +299,8 @@ class RefSystem:
                      int(hist_cap), C.byref(nh))
         if rc <= -1000:
             raise RuntimeError("refsys_solve_blocks: ConstraintSolver and the direct BCQPSolver run disagree")
-        res_.update(gamma=gamma[:n], blocks=out[:n], history=hist[:min(nh.value, hist_cap)].copy(), nIte=nh.value - 1,
-                    status=rc)
+        res_.update(gamma=gamma[:n], blocks=out[:n], history=hist[:min(nh.value, hist_cap)].copy(),
+                    nIte=(nh.value - 1) if hist_cap > 0 else None, status=rc)
         return res_
 
 

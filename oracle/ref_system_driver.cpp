@@ -231,6 +231,10 @@ int refsys_solve_blocks(void *hp, const void *blocksIn, long long n, const doubl
         if (blocksOut) ((ConstraintBlock *)blocksOut)[i] = q0[i];
     }
 
+    if (histCap <= 0 || !hist6) { // no history wanted: one run is enough
+        if (nHist) *nHist = 0;
+        return 0;
+    }
     // the same problem through BCQPSolver directly, to read the IteHistory (steps of ConstraintSolver::setup and
     // ::solveConstraints, ConstraintSolver.cpp:4-34,60-93, spelled out with the reference's public classes)
     ConstraintCollector col2;

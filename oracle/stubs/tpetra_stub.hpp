@@ -405,33 +405,68 @@ class MultiVector {
     template <class Space>
     bool need_sync() const { return false; }
 
-    void putScalar(S a) { for (size_t i = 0; i < n_; i++) ptr()[i] = a; }
+    // elementwise kernels run on all OpenMP threads, as Kokkos' OpenMP backend would (results do not depend on it)
+    void putScalar(S a) {
+        S *y = ptr();
+        const long long n = (long long)n_;
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < n; i++) y[i] = a;
+    }
     void randomize() { randomize(S(-1), S(1)); }
     void randomize(S lo, S hi) {
         static std::mt19937_64 gen(20211011ull);
         std::uniform_real_distribution<S> d(lo, hi);
         for (size_t i = 0; i < n_; i++) ptr()[i] = d(gen);
     }
-    void scale(S a) { for (size_t i = 0; i < n_; i++) ptr()[i] = a * ptr()[i]; }
-    void scale(S a, const MultiVector &A) { for (size_t i = 0; i < n_; i++) ptr()[i] = a * A.ptr()[i]; }
+    void scale(S a) {
+        S *y = ptr();
+        const long long n = (long long)n_;
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < n; i++) y[i] = a * y[i];
+    }
+    void scale(S a, const MultiVector &A) {
+        S *y = ptr();
+        const S *x = A.ptr();
+        const long long n = (long long)n_;
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < n; i++) y[i] = a * x[i];
+    }
     void update(S a, const MultiVector &A, S b) {
         S *y = ptr();
         const S *x = A.ptr();
-        if (b == S(0)) for (size_t i = 0; i < n_; i++) y[i] = a * x[i];
-        else for (size_t i = 0; i < n_; i++) y[i] = a * x[i] + b * y[i];
+        const long long n = (long long)n_;
+        if (b == S(0)) {
+#pragma omp parallel for schedule(static)
+            for (long long i = 0; i < n; i++) y[i] = a * x[i];
+        } else {
+#pragma omp parallel for schedule(static)
+            for (long long i = 0; i < n; i++) y[i] = a * x[i] + b * y[i];
+        }
     }
     void update(S a, const MultiVector &A, S b, const MultiVector &B, S g) {
         S *z = ptr();
         const S *x = A.ptr(), *y = B.ptr();
-        if (g == S(0)) for (size_t i = 0; i < n_; i++) z[i] = a * x[i] + b * y[i];
-        else for (size_t i = 0; i < n_; i++) z[i] = a * x[i] + b * y[i] + g * z[i];
+        const long long n = (long long)n_;
+        if (g == S(0)) {
+#pragma omp parallel for schedule(static)
+            for (long long i = 0; i < n; i++) z[i] = a * x[i] + b * y[i];
+        } else {
+#pragma omp parallel for schedule(static)
+            for (long long i = 0; i < n; i++) z[i] = a * x[i] + b * y[i] + g * z[i];
+        }
     }
     // this = t*this + s*A(i)*B(i)
     void elementWiseMultiply(S s, const MultiVector &A, const MultiVector &B, S t) {
         S *c = ptr();
         const S *a = A.ptr(), *b = B.ptr();
-        if (t == S(0)) for (size_t i = 0; i < n_; i++) c[i] = s * a[i] * b[i];
-        else for (size_t i = 0; i < n_; i++) c[i] = t * c[i] + s * a[i] * b[i];
+        const long long n = (long long)n_;
+        if (t == S(0)) {
+#pragma omp parallel for schedule(static)
+            for (long long i = 0; i < n; i++) c[i] = s * a[i] * b[i];
+        } else {
+#pragma omp parallel for schedule(static)
+            for (long long i = 0; i < n; i++) c[i] = t * c[i] + s * a[i] * b[i];
+        }
     }
     // fixed chunks of 4096 entries, each summed left to right, partial sums added in chunk order: independent of the
     // thread count (Kokkos' own order depends on it) and the same order oracle/alens_oracle.c uses
@@ -453,7 +488,10 @@ class MultiVector {
     S norm2() const { return std::sqrt(dot(*this)); }
     S normInf() const {
         S m = 0;
-        for (size_t i = 0; i < n_; i++) m = std::max(m, std::fabs(ptr()[i]));
+        const S *x = ptr();
+        const long long n = (long long)n_;
+#pragma omp parallel for schedule(static) reduction(max : m)
+        for (long long i = 0; i < n; i++) m = std::max(m, std::fabs(x[i]));
         return m;
     }
     S norm1() const {

@@ -86,7 +86,7 @@ def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None,
                 c.calc_mobility(mu)
                 rep = c.solve_constraints(v, dt, res, max_ite, 0)
             res_r.update(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), ghosts=c.num_ghosts(),
-                         mode=c.comm_mode())
+                         mode=c.comm_mode(), digest=c.constraint_digest())
             res_r.update(c.get_force_velocity())
             if want_blocks:
                 res_r["blocks"] = c.get_constraints(with_stress=True, write_back=True)

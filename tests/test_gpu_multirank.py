@@ -23,7 +23,7 @@ def single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, max_ite, vnc):
     nc = c.collect_pair_collision()
     c.calc_mobility(mu)
     rep = c.solve_constraints(vnc, dt, res, max_ite, 0)
-    out = dict(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(),
+    out = dict(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), digest=c.constraint_digest(),
                blocks=c.get_constraints(with_stress=True, write_back=True))
     out.update(c.get_force_velocity())
     c.close()
@@ -117,6 +117,13 @@ def test_multirank_matches_single(nranks, pbc, placement):
     assert len(uniq) == len(want)
     for f in BLOCK_FIELDS:
         assert np.array_equal(uniq[f], want[f]), f"field {f} differs from the single-rank list"
+
+    # ---- the device-side digest bench.py uses for its parity flag: per-rank digests add up to the single-rank one
+    M = 1 << 64
+    assert sum(r["digest"]["rows"] for r in ranks) == ref["digest"]["rows"] == len(want)
+    assert sum(r["digest"]["list_hash"] for r in ranks) % M == ref["digest"]["list_hash"]
+    for k in ("sum_gamma", "sum_gamma2", "sum_wgamma"):
+        assert abs(sum(r["digest"][k] for r in ranks) - ref["digest"][k]) < 1e-9 * abs(ref["digest"][k]), k
 
     # ---- solve: same iteration count, gamma and velocities to rounding
     its = {r["report"].iterations for r in ranks}

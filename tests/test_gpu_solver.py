@@ -162,15 +162,19 @@ def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
     x[rng.uniform(size=nc) < zero_frac] = 0.0
     x[::7] *= -1.0  # negative multipliers and -0.0 occur in plain operator applies
     res = {}
-    for kern in (3, 1, 2, 0):  # 3 k_force_vel_rec, 1 k_force_vel_act, 2 k_slot_x + k_rod_sum, 0 dense level-major
-        ctx.set_option("force_kernel", kern)
+    def select(kern):  # 3: k_force_vel_rec gathering {x, g} by row id (default), 30: with {x, g} copied into the records
+        ctx.set_option("force_kernel", 3 if kern == 30 else kern)
+        ctx.set_option("rec_mode", 0 if kern == 30 else 1)
+
+    for kern in (3, 30, 1, 2, 0):  # 1 k_force_vel_act, 2 k_slot_x + k_rod_sum, 0 dense level-major
+        select(kern)
         ctx.setup_constraints(None, DT)
         res[kern] = ctx.operator_apply(x, want_force_vel=True)
         if kern == 3:  # a second apply to another vector on the same setup: stale records / bits must not leak
             x2 = np.where(rng.uniform(size=nc) < 0.5, 0.0, rng.normal(size=nc))
             res["x2"] = (x2, ctx.operator_apply(x2, want_force_vel=True))
             res[3] = ctx.operator_apply(x, want_force_vel=True)
-    for kern in (3, 1, 2):
+    for kern in (3, 30, 1, 2):
         for a, b in zip(res[0], res[kern]):
             assert np.array_equal(a, b)
     ctx.set_option("force_kernel", 0)
@@ -183,22 +187,23 @@ def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
     # the BBPGD loop (x recomputed on the fly from {x_prev, g_prev}) gives the same iterates with both kernels
     vnc = thermal_velocity(rods, MU, DT, seed=9)
     gam = {}
-    for kern in (3, 1, 2, 0):
-        ctx.set_option("force_kernel", kern)
+    for kern in (3, 30, 1, 2, 0):
+        select(kern)
         rep = ctx.solve_constraints(vnc, DT, 1e-30, 15, 0)
         assert rep.iterations == 15
         gam[kern] = (ctx.get_gamma(), ctx.get_force_velocity()["velU"], ctx.get_history())
-    for kern in (3, 1, 2):
+    for kern in (3, 30, 1, 2):
         for a, b in zip(gam[0], gam[kern]):
             assert np.array_equal(a, b)
-    # ... and a long run on the default kernel: rows leave and re-enter the live set many times
-    for kern in (3, 0):
-        ctx.set_option("force_kernel", kern)
+    # ... and a long run on the record kernels: rows leave and re-enter the live set many times
+    for kern in (3, 30, 0):
+        select(kern)
         rep = ctx.solve_constraints(vnc, DT, 1e-30, 150, 0)
         gam[kern] = (ctx.get_gamma(), ctx.get_force_velocity()["velU"], ctx.get_history())
-    for a, b in zip(gam[0], gam[3]):
-        assert np.array_equal(a, b)
-    ctx.set_option("force_kernel", 3)
+    for kern in (3, 30):
+        for a, b in zip(gam[0], gam[kern]):
+            assert np.array_equal(a, b)
+    select(3)
 
 
 def test_bbpgd_matches_oracle_iterates(ctx, oracle):
