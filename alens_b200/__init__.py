@@ -5,6 +5,6 @@ interface in ``include/alens_b200.h``) plus the C++ drop-in headers in ``include
 This Python package is only the ctypes harness that tests and bench.py drive the library with.
 It never imports anything from ``oracle/`` and has no CPU fallback.
 """
-from .capi import Library, Context, AlensError, BLOCK_DTYPE, lib_path, build, comm_connect_local  # noqa: F401
+from .capi import Library, Context, Bcqp, AlensError, BLOCK_DTYPE, lib_path, build, comm_connect_local  # noqa: F401
 
-__all__ = ["Library", "Context", "AlensError", "BLOCK_DTYPE", "lib_path", "build"]
+__all__ = ["Library", "Context", "Bcqp", "AlensError", "BLOCK_DTYPE", "lib_path", "build"]

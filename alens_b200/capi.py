@@ -37,7 +37,9 @@ EXPORTS = [
     "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral", "alens_calc_velocity_noncon", "alens_calc_velocity_brown",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
     "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest",
-    "alens_get_live_stats",
+    "alens_get_live_stats", "alens_bcqp_create_csr", "alens_bcqp_create_constraint", "alens_bcqp_set_lower_bound",
+    "alens_bcqp_set_upper_bound", "alens_bcqp_get_bounds", "alens_bcqp_run", "alens_bcqp_history", "alens_bcqp_size",
+    "alens_bcqp_destroy",
 ]
 
 
@@ -126,6 +128,63 @@ class Library:
 
     def version(self):
         return self.dll.alens_version().decode()
+
+
+class Bcqp:
+    """alens_bcqp: BCQPSolver for any caller (a CSR matrix, or the constraint operator of `ctx`'s last setup), with
+    caller-set bounds.  Mirrors SimToolbox/Constraint/BCQPSolver.hpp:37-111."""
+
+    def __init__(self, ctx, b=None, csr=None):
+        self.ctx, self.dll = ctx, ctx.lib.dll
+        self.h = C.c_void_p()
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        if csr is None:
+            rc = self.dll.alens_bcqp_create_constraint(ctx.h, _dp(bb), C.byref(self.h))
+        else:
+            rowptr, col, val = csr
+            rp = np.ascontiguousarray(rowptr, dtype=np.int64)
+            ci = np.ascontiguousarray(col, dtype=np.int32)
+            va = np.ascontiguousarray(val, dtype=np.float64)
+            rc = self.dll.alens_bcqp_create_csr(ctx.h, C.c_int(len(rp) - 1), rp.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                                ci.ctypes.data_as(C.POINTER(C.c_int)), _dp(va), _dp(bb), C.byref(self.h))
+        ctx._ck(rc)
+        self.dll.alens_bcqp_size.argtypes = [C.c_void_p]
+        self.n = self.dll.alens_bcqp_size(self.h)
+
+    def set_bounds(self, lb=None, ub=None):
+        for name, v in (("alens_bcqp_set_lower_bound", lb), ("alens_bcqp_set_upper_bound", ub)):
+            a = None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+            self.ctx._ck(getattr(self.dll, name)(self.h, _dp(a)))
+
+    def get_bounds(self):
+        lb, ub = np.zeros(max(self.n, 1)), np.zeros(max(self.n, 1))
+        self.ctx._ck(self.dll.alens_bcqp_get_bounds(self.h, _dp(lb), _dp(ub)))
+        return lb[:self.n], ub[:self.n]
+
+    def solve(self, x0, tol, max_ite, solver_choice=0):
+        x = np.array(x0, dtype=np.float64)
+        if len(x) == 0:
+            x = np.zeros(1)
+        rep = SolveReport()
+        rc = self.dll.alens_bcqp_run(self.h, _dp(x), C.c_double(tol), C.c_int(max_ite), C.c_int(solver_choice), C.byref(rep))
+        rows = np.zeros((max(rep.history_rows, 1), 6))
+        n = C.c_int(0)
+        self.dll.alens_bcqp_history(self.h, _dp(rows), C.c_int(len(rows)), C.byref(n))
+        self.ctx._ck(rc)
+        return x[:self.n], rep, rows[:min(n.value, len(rows))]
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.dll.alens_bcqp_destroy.argtypes = [C.c_void_p]
+            self.dll.alens_bcqp_destroy.restype = None
+            self.dll.alens_bcqp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:

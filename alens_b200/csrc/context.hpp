@@ -235,6 +235,7 @@ struct Context {
     DevBuf<unsigned char> sGhost; // 1 = ghost rod (owned by a neighbour rank)
     DevBuf<signed char> sImg;     // image along the slab axis
     DevBuf<double> sInvDrag; // 3 per rod: 1/para, 1/perp, 1/rot (0 if immovable)
+    DevBuf<double> sMobRec;  // the same with the direction, as one 64-byte record per rod (k_force_vel_rec)
     bool sorted = false;
 
     // ---- constraints (solver order) ----

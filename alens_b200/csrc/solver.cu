@@ -45,7 +45,8 @@ static constexpr double kHuge = DBL_MAX / 10; // BCQPSolver.cpp:499-510
 // mobility (SylinderSystem.cpp:660-662)
 __global__ void k_mob_coeff(int n, const double *__restrict__ len, const double *__restrict__ rad,
                             const unsigned char *__restrict__ imm, double mu, double *__restrict__ invDrag,
-                            size_t stride) {
+                            size_t stride, const double *__restrict__ dx, const double *__restrict__ dy,
+                            const double *__restrict__ dz, double *__restrict__ mobRec) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double Pi = 3.14159265358979323846;
@@ -66,11 +67,18 @@ __global__ void k_mob_coeff(int n, const double *__restrict__ len, const double 
     invDrag[i] = im ? 0.0 : 1 / dPara;
     invDrag[stride + i] = im ? 0.0 : 1 / dPerp;
     invDrag[2 * stride + i] = im ? 0.0 : 1 / dRot;
+    if (mobRec) { // the same six numbers as ONE 64-byte line per rod: {q, 1/zeta_para, 1/zeta_perp, 1/zeta_rot} (k_force_vel_rec)
+        double *o = mobRec + 8 * (size_t)i;
+        o[0] = dx[i]; o[1] = dy[i]; o[2] = dz[i];
+        o[3] = invDrag[i]; o[4] = invDrag[stride + i]; o[5] = invDrag[2 * stride + i];
+        o[6] = 0.0; o[7] = 0.0;
+    }
 }
 
 struct MobIn {
     const double *dx, *dy, *dz; // unit direction q
     const double *invDrag;      // [3][stride]
+    const double *rec;          // [n][8]: {q, 1/zeta_para, 1/zeta_perp, 1/zeta_rot, 0, 0}, one 64-byte line per rod
     int n;
     size_t stride;              // even (16-byte aligned component arrays)
     const unsigned char *ghost; // 1 = rod owned by a neighbour rank: its U row arrives through the halo
@@ -1005,9 +1013,11 @@ struct FvRec {
     int xmode;
 };
 
-template <bool WRITE_F, bool HALO>
-__global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, double *__restrict__ U, double *__restrict__ F,
-                                                       const SolverScalars *__restrict__ scal, HaloPush hp) {
+// SRC: where a live slot's multiplier comes from -- 0: {x, g} inside the record (rec_mode 0), 1: the row-ordered {x, g}
+// pairs, gathered by the row id in the record (rec_mode 1, BBPGD), 2: a plain vector, gathered by row id (rec_mode 1)
+template <bool WRITE_F, bool HALO, int SRC>
+__global__ void __launch_bounds__(128, 10) k_force_vel_rec(FvRec in, MobIn mob, double *__restrict__ U, double *__restrict__ F,
+                                                           const SolverScalars *__restrict__ scal, HaloPush hp) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = r < in.nRods;
     int b = 0, e = 0;
@@ -1027,32 +1037,45 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
     const double alpha = (in.update && scal) ? scal->alpha : 0.0;
     double f[6] = {0, 0, 0, 0, 0, 0};
     bool any = false, pushed = false;
-    if (act && e > b) {
-        for (int wd = b >> 5; wd <= (e - 1) >> 5; wd++) {
-            unsigned bits = __ldg(in.slotLive + wd);
+    const int w0 = b >> 5, w1 = e > b ? (e - 1) >> 5 : w0 - 1;
+    auto wordOf = [&](int wd) { // the live bits of my slot range in bitmap word wd
+        unsigned bits = __ldg(in.slotLive + wd);
+        const int lo = wd << 5;
+        if (b > lo) bits &= ~((1u << (b - lo)) - 1u);
+        if (e < lo + 32) bits &= (1u << (e - lo)) - 1u;
+        return bits;
+    };
+    // pass 1: is anything live?  (a rod's slots span 1-2 words; they are read again below, from L1)
+    for (int wd = w0; wd <= w1; wd++) any = any || wordOf(wd) != 0;
+    // the rod's mobility data (one 64-byte line) is requested NOW, together with the records below: a rod without a
+    // live slot (45 % of them) has f = 0 and therefore u = +0 exactly and never reads it
+    double qx = 0, qy = 0, qz = 0, iPara = 0;
+    double2 iPR = make_double2(0.0, 0.0); // {1/zeta_perp, 1/zeta_rot}
+    if (any && !ghost) {
+        ld256(mob.rec + 8 * (size_t)r, qx, qy, qz, iPara);
+        iPR = ldGather2(reinterpret_cast<const double2 *>(mob.rec + 8 * (size_t)r + 4));
+    }
+    if (any) {
+        for (int wd = w0; wd <= w1; wd++) {
+            unsigned bits = wordOf(wd);
             const int lo = wd << 5;
-            if (b > lo) bits &= ~((1u << (b - lo)) - 1u);
-            if (e < lo + 32) bits &= (1u << (e - lo)) - 1u;
-            if (!bits) continue;
-            any = true;
-            const unsigned biw = in.update ? __ldg(in.slotBi + wd) : 0u;
+            const unsigned biw = (SRC == 0 && in.update) ? __ldg(in.slotBi + wd) : 0u;
             while (bits) { // ascending slot order
                 const int q = __ffs(bits) - 1;
                 bits &= bits - 1u;
                 const double *cp = in.rec + 8 * (size_t)(lo + q);
                 double xp, gp, c0, c1, c2, c3, c4, c5;
-                ld256(cp, xp, gp, c0, c1); // the record's two sectors: {x, g, col[0..1]} and {col[2..5]}
+                ld256(cp, xp, gp, c0, c1); // the record's two sectors: {x | row id, g, col[0..1]} and {col[2..5]}
                 ld256(cp + 4, c2, c3, c4, c5);
                 double x;
-                if (in.xg || in.x) { // rec_mode 1: one more (dependent) 16-byte gather, nothing written by the tail
+                if (SRC == 1) { // rec_mode 1: one more (dependent) 16-byte gather, nothing written by the tail
                     const int code = (int)__double_as_longlong(xp);
-                    if (in.xg) {
-                        const double2 v = ldGather2(in.xg + (code >> 2));
-                        x = in.update ? bbStep(v.x, v.y, alpha, (code & 2) != 0) : v.x;
-                    } else {
-                        const double xv = __ldg(in.x + (code >> 2));
-                        x = in.xmode == 1 ? 1.0 * xv * ((code & 2) ? 1.0 : 0.0) : xv;
-                    }
+                    const double2 v = ldGather2(in.xg + (code >> 2));
+                    x = in.update ? bbStep(v.x, v.y, alpha, (code & 2) != 0) : v.x;
+                } else if (SRC == 2) {
+                    const int code = (int)__double_as_longlong(xp);
+                    const double xv = __ldg(in.x + (code >> 2));
+                    x = in.xmode == 1 ? 1.0 * xv * ((code & 2) ? 1.0 : 0.0) : xv;
                 } else {
                     x = in.update ? bbStep(xp, gp, alpha, (biw >> q) & 1u) : xp;
                 }
@@ -1063,15 +1086,12 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
     }
     if (act && !ghost) {
         double2 u0 = make_double2(0.0, 0.0), u1 = u0, u2 = u0;
-        if (any) { // a rod without a live slot has f = 0 and therefore u = +0 exactly: its mobility data is not read
-            const double qx = ldStream(mob.dx + r), qy = ldStream(mob.dy + r), qz = ldStream(mob.dz + r);
-            const double iPara = ldStream(mob.invDrag + r), iPerp = ldStream(mob.invDrag + mob.stride + r);
-            const double iRot = ldStream(mob.invDrag + 2 * mob.stride + r);
+        if (any) {
             const double qf = qx * f[0] + qy * f[1] + qz * f[2];
             const double px = qf * qx, py = qf * qy, pz = qf * qz;
-            u0 = make_double2(iPara * px + iPerp * (f[0] - px), iPara * py + iPerp * (f[1] - py));
-            u1 = make_double2(iPara * pz + iPerp * (f[2] - pz), iRot * f[3]);
-            u2 = make_double2(iRot * f[4], iRot * f[5]);
+            u0 = make_double2(iPara * px + iPR.x * (f[0] - px), iPara * py + iPR.x * (f[1] - py));
+            u1 = make_double2(iPara * pz + iPR.x * (f[2] - pz), iPR.y * f[3]);
+            u2 = make_double2(iPR.y * f[4], iPR.y * f[5]);
         }
         double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
         Up[0] = u0; Up[1] = u1; Up[2] = u2;
@@ -1959,7 +1979,7 @@ __global__ void k_step_euler(int n, double dt, const double *__restrict__ velNC,
 // =================================================================================================
 static size_t mobStride(int n) { return ((size_t)n + 3) & ~(size_t)1; }
 static MobIn mobIn(Context &c) {
-    return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.nRods, mobStride(c.nRods), c.sGhost.p};
+    return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.sMobRec.p, c.nRods, mobStride(c.nRods), c.sGhost.p};
 }
 static ConGeom conGeom(Context &c) { return ConGeom{c.cIdxI.p, c.cIdxJ.p, c.cN.p, c.cPI.p, c.cPJ.p, c.conCap}; }
 static FvIn fvIn(Context &c) {
@@ -1972,8 +1992,9 @@ void calcMobility(Context &c, double mu) {
     const int n = c.nRods;
     c.sInvDrag.reserve(3 * mobStride(n) + 4);
     if (n > 0) {
+        c.sMobRec.reserve(8 * (size_t)n + 8);
         k_mob_coeff<<<gridFor(n, 256), 256, 0, c.stream>>>(n, c.sLen.p, c.sRad.p, c.sImm.p, mu, c.sInvDrag.p,
-                                                           mobStride(n));
+                                                           mobStride(n), c.sDx.p, c.sDy.p, c.sDz.p, c.sMobRec.p);
         c.launches++;
     }
     ALENS_CUDA(cudaGetLastError());
@@ -2279,9 +2300,16 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
         cfg.gridDim = dim3((unsigned)std::max(1, gridFor(n, 128)));
         cfg.blockDim = dim3(128);
         cfg.numAttrs = c.pdlNow ? 1 : 0;
-        if (XMODE == 2 && !WF && hp.on)
-            ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, (XMODE == 2 && !WF)>), fr, mobIn(c), U, F, scal, hp));
-        else ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, false>), fr, mobIn(c), U, F, scal, hp));
+        constexpr int SRC1 = XMODE == 2 ? 1 : 2; // rec_mode 1: gather from the {x, g} pairs / from the plain vector
+        if (c.recMode == 0) {
+            if (XMODE == 2 && !WF && hp.on)
+                ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, (XMODE == 2 && !WF), 0>), fr, mobIn(c), U, F, scal, hp));
+            else ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, false, 0>), fr, mobIn(c), U, F, scal, hp));
+        } else {
+            if (XMODE == 2 && !WF && hp.on)
+                ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, (XMODE == 2 && !WF), SRC1>), fr, mobIn(c), U, F, scal, hp));
+            else ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, false, SRC1>), fr, mobIn(c), U, F, scal, hp));
+        }
         profEnd(c);
         c.launches++;
         c.timers.op_launches++;
@@ -2965,9 +2993,13 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_init<0>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_init<1>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_init<2>));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, false>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<true, false>)));
-    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, false, 0>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<true, false, 0>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, true, 0>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, false, 1>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, true, 1>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, false, 2>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<true, false, 2>)));
 }
 
 } // namespace alens

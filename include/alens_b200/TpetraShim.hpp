@@ -131,8 +131,41 @@ class Operator {
     virtual bool hasTransposeApply() const { return false; }
 };
 
+// CSR matrix as a TOP (the reference's TCMAT, Tpetra::CrsMatrix<double,int,int>): host arrays that the device-backed
+// BCQPSolver uploads once; apply() on host vectors is the caller's convenience (tests), not a solver path
+class CrsMatrix : public Operator {
+    Teuchos::RCP<const Map> map_;
+    std::vector<long long> ptr_;
+    std::vector<int> col_;
+    std::vector<double> val_;
+    struct alens_ctx *dev_ = nullptr;
+
+  public:
+    CrsMatrix(const Teuchos::RCP<const Map> &rowMap, std::vector<long long> rowPtr, std::vector<int> colInd,
+              std::vector<double> values)
+        : map_(rowMap), ptr_(std::move(rowPtr)), col_(std::move(colInd)), val_(std::move(values)) {}
+    void setDevice(struct alens_ctx *c) { dev_ = c; }
+    struct alens_ctx *device() const { return dev_; }
+    size_t getNodeNumRows() const { return ptr_.size() - 1; }
+    size_t getNodeNumEntries() const { return col_.size(); }
+    const std::vector<long long> &rowPtr() const { return ptr_; }
+    const std::vector<int> &colInd() const { return col_; }
+    const std::vector<double> &values() const { return val_; }
+    Teuchos::RCP<const Map> getDomainMap() const override { return map_; }
+    Teuchos::RCP<const Map> getRangeMap() const override { return map_; }
+    void apply(const Vector &X, Vector &Y, Teuchos::ETransp = Teuchos::NO_TRANS, double alpha = 1.0,
+               double beta = 0.0) const override {
+        for (size_t i = 0; i + 1 < ptr_.size(); i++) {
+            double s = 0;
+            for (long long k = ptr_[i]; k < ptr_[i + 1]; k++) s += val_[k] * X.data()[col_[k]];
+            Y.data()[i] = (beta == 0.0 ? 0.0 : beta * Y.data()[i]) + alpha * s;
+        }
+    }
+};
+
 } // namespace alens_shim
 
+using TCMAT = alens_shim::CrsMatrix;
 using TCOMM = alens_shim::Comm;
 using TMAP = alens_shim::Map;
 using TV = alens_shim::Vector;
