@@ -39,7 +39,7 @@ EXPORTS = [
     "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest",
     "alens_get_live_stats", "alens_bcqp_create_csr", "alens_bcqp_create_constraint", "alens_bcqp_set_lower_bound",
     "alens_bcqp_set_upper_bound", "alens_bcqp_get_bounds", "alens_bcqp_run", "alens_bcqp_history", "alens_bcqp_size",
-    "alens_bcqp_destroy",
+    "alens_bcqp_destroy", "alens_collect_protein_bilateral",
 ]
 
 
@@ -128,6 +128,12 @@ class Library:
 
     def version(self):
         return self.dll.alens_version().decode()
+
+
+PROTEIN_DTYPE = np.dtype([("idBind", "<i4", 2), ("indexBind", "<i4", 2), ("centerBind", "<f8", (2, 3)),
+                          ("directionBind", "<f8", (2, 3)), ("posEndBind", "<f8", (2, 3)), ("lenBind", "<f8", 2),
+                          ("forceLength", "<f8"), ("freeLength", "<f8"), ("kappa", "<f8")])
+assert PROTEIN_DTYPE.itemsize == 200
 
 
 class Bcqp:
@@ -305,6 +311,14 @@ class Context:
         out = np.zeros(6 * self.n_rods)
         self._call("alens_calc_velocity_noncon", _dp(a[0]), _dp(a[1]), _dp(a[2]), C.c_int(1 if monolayer else 0), _dp(out))
         return out
+
+    def collect_protein_bilateral(self, proteins, tubule_diameter):
+        """proteins: structured array PROTEIN_DTYPE (alens_protein_bind); returns the number of blocks added"""
+        p = np.ascontiguousarray(proteins, dtype=PROTEIN_DTYPE)
+        n = C.c_longlong(0)
+        self._call("alens_collect_protein_bilateral", C.c_void_p(p.ctypes.data), C.c_longlong(len(p)),
+                   C.c_double(tubule_diameter), C.byref(n))
+        return n.value
 
     def collect_link_bilateral(self, prev_gid, next_gid, link_kappa, link_gap):
         p = np.ascontiguousarray(prev_gid, dtype=np.int32)

@@ -415,6 +415,74 @@ long long collectLinks(Context &c, const int *prevGid, const int *nextGid, long 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Protein (crosslinker / motor) bilateral constraints: TubuleSystem::setProteinConstraints (SRC/TubuleSystem.cpp:694-745).
+// One thread per doubly bound protein: delta0 = forceLength - freeLength, gamma0 = -delta0 kappa, normI = (P - Q)/|P - Q|,
+// posI = P - centerI, posJ = Q - centerJ, lab = (P, Q), bilateral with stiffness kappa, stress by collideStress with
+// radius tubuleDiameter / 2 on both sides.  Singly bound / unbound proteins (an id < 0) produce nothing.
+__global__ void k_protein_blocks(long long n, const alens_protein_bind *__restrict__ pr, double tubuleDiameter,
+                                 alens_constraint_block *__restrict__ out, unsigned char *__restrict__ keep) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const alens_protein_bind p = pr[i];
+    alens_constraint_block q;
+    memset(&q, 0, sizeof(q));
+    const bool both = p.idBind[0] >= 0 && p.idBind[1] >= 0; // ID_UB = -1 (Protein/ProteinBindStatus.hpp)
+    keep[i] = both ? 1 : 0;
+    if (both) {
+        const Vec3 cI = v3(p.centerBind[0][0], p.centerBind[0][1], p.centerBind[0][2]);
+        const Vec3 cJ = v3(p.centerBind[1][0], p.centerBind[1][1], p.centerBind[1][2]);
+        const Vec3 dI = v3(p.directionBind[0][0], p.directionBind[0][1], p.directionBind[0][2]);
+        const Vec3 dJ = v3(p.directionBind[1][0], p.directionBind[1][1], p.directionBind[1][2]);
+        const Vec3 P = v3(p.posEndBind[0][0], p.posEndBind[0][1], p.posEndBind[0][2]);
+        const Vec3 Q = v3(p.posEndBind[1][0], p.posEndBind[1][1], p.posEndBind[1][2]);
+        const double delta0 = p.forceLength - p.freeLength;
+        const Vec3 PQ = P - Q;
+        const double pqn = norm(PQ);
+        const Vec3 nI = pqn > 0 ? v3(PQ.x / pqn, PQ.y / pqn, PQ.z / pqn) : PQ;
+        q.delta0 = delta0;
+        q.gamma = -delta0 * p.kappa;
+        q.gidI = p.idBind[0]; q.gidJ = p.idBind[1];
+        q.globalIndexI = p.indexBind[0]; q.globalIndexJ = p.indexBind[1];
+        q.oneSide = 0;
+        q.bilateral = 1;
+        q.kappa = p.kappa;
+        q.normI[0] = nI.x; q.normI[1] = nI.y; q.normI[2] = nI.z;
+        q.normJ[0] = -nI.x; q.normJ[1] = -nI.y; q.normJ[2] = -nI.z;
+        q.posI[0] = P.x - cI.x; q.posI[1] = P.y - cI.y; q.posI[2] = P.z - cI.z;
+        q.posJ[0] = Q.x - cJ.x; q.posJ[1] = Q.y - cJ.y; q.posJ[2] = Q.z - cJ.z;
+        q.labI[0] = P.x; q.labI[1] = P.y; q.labI[2] = P.z;
+        q.labJ[0] = Q.x; q.labJ[1] = Q.y; q.labJ[2] = Q.z;
+        collideStress(dI, dJ, cI, cJ, p.lenBind[0], p.lenBind[1], tubuleDiameter / 2, tubuleDiameter / 2, 1.0, P, Q, q.stress);
+    }
+    out[i] = q;
+}
+
+long long collectProteins(Context &c, const alens_protein_bind *proteins, long long n, double tubuleDiameter) {
+    if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_collect_protein_bilateral: call alens_set_rods first"};
+    if (n <= 0) return 0;
+    if (!proteins) throw ArgError{ALENS_ERR_ARG, "alens_collect_protein_bilateral: NULL protein list"};
+    cudaStream_t st = c.stream;
+    DevBuf<alens_protein_bind> dP;
+    DevBuf<alens_constraint_block> dOut;
+    DevBuf<unsigned char> dKeep;
+    dP.reserve((size_t)n); dOut.reserve((size_t)n); dKeep.reserve((size_t)n);
+    ALENS_CUDA(cudaMemcpyAsync(dP.p, proteins, sizeof(alens_protein_bind) * (size_t)n, cudaMemcpyHostToDevice, st));
+    k_protein_blocks<<<gridFor(n, 128), 128, 0, st>>>(n, dP.p, tubuleDiameter, dOut.p, dKeep.p);
+    c.launches++;
+    ALENS_CUDA(cudaGetLastError());
+    std::vector<alens_constraint_block> host((size_t)n);
+    std::vector<unsigned char> keep((size_t)n);
+    ALENS_CUDA(cudaMemcpyAsync(host.data(), dOut.p, sizeof(alens_constraint_block) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaMemcpyAsync(keep.data(), dKeep.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    size_t m = 0;
+    for (long long i = 0; i < n; i++)
+        if (keep[i]) host[m++] = host[i]; // protein order is kept
+    if (m) appendBlocks(c, host.data(), (long long)m);
+    return (long long)m;
+}
+
+// ------------------------------------------------------------------------------------------------
 struct BlocksIn {
     const int *idxI, *idxJ, *gidI, *gidJ, *sUser, *uGlobalIdx;
     const signed char *shift;
@@ -709,6 +777,7 @@ void preloadBlockKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_append));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_blocks_out));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_dcp_batch));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_protein_blocks));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_constraint_digest));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_pair_functor_batch));
 }

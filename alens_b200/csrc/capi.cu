@@ -304,6 +304,14 @@ int alens_collect_link_bilateral(alens_ctx *ctx, const int *prevGid, const int *
     });
 }
 
+int alens_collect_protein_bilateral(alens_ctx *ctx, const alens_protein_bind *proteins, long long n, double tubuleDiameter,
+                                    long long *nAdded) {
+    return guarded(ctx, [&](Context &c) {
+        const long long m = collectProteins(c, proteins, n, tubuleDiameter);
+        if (nAdded) *nAdded = m;
+    });
+}
+
 int alens_clear_constraints(alens_ctx *ctx) {
     return guarded(ctx, [&](Context &c) {
         c.nCon = c.nColl = 0;

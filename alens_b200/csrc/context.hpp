@@ -287,7 +287,8 @@ struct Context {
     bool pdlNow = false, profMute = false;  // state of the current solve
     int *hProg = nullptr, *hProgDev = nullptr; // {completed applies, done} in mapped pinned host memory
     int optLateHalo = 1;                    // multi-GPU: k_bb_tail walks the rows that need no halo first and waits for the halo behind them
-    DevBuf<int> ghostRange;                 // [0], [1]: rows reading ghost velocities lie in [0, [0]) and [[1], nc)
+    DevBuf<int> tailFlag, tailOrder;        // multi-GPU: tiles of 256 constraint rows; order = tiles without a ghost-reading row first, [nTiles] = their number
+    DevBuf<int> rodFlag, rodOrder;          // ... tiles of 128 rods; order = tiles with a rod mirrored on a neighbour first, [nTiles] = their number
     int optKeepXG = 1;                      // {x, g} pairs stored / gathered with the L2 evict_last policy
     int optForceMask = 1;                   // k_force_vel_act consults the tail kernel's "may be non-zero" bit mask before gathering {x, g}
     int optForceWaves = 1;                  // k_force_vel_act: grid = resident CTAs x this (1 = persistent)
@@ -361,6 +362,7 @@ inline void waitVelNC(Context &c) {
 void calcVelocityBrown(Context &c, double kBT, double dt, const double *normals12, unsigned long long seed, unsigned long long step, double *out);
 void calcVelocityNonCon(Context &c, const double *force, const double *velNB, const double *velB, int monolayer, double *velNonBOut);
 long long collectBoundary(Context &c, const alens_boundary *bnd, int nb);
+long long collectProteins(Context &c, const alens_protein_bind *proteins, long long n, double tubuleDiameter);
 long long collectLinks(Context &c, const int *prevGid, const int *nextGid, long long nLinks, double linkKappa, double linkGap);
 void dcpBatch(Context &c, long long n, const double *P0, const double *P1, const double *Q0, const double *Q1, double *dist,
               double *Ploc, double *Qloc);

@@ -400,21 +400,50 @@ __global__ void k_inc_emit_rec(int nRods, const int *__restrict__ start, int *__
     }
 }
 
+// Stable partition of the tile indices by a 0/1 flag, unflagged tiles first (flagFirst = 0) or flagged tiles first
+// (flagFirst = 1); order[nTiles] = size of the first group.  One CTA (at most a few 10^4 tiles).
+__global__ void k_tile_order(int nTiles, const int *__restrict__ flag, int flagFirst, int *__restrict__ order) {
+    __shared__ int sCnt[1024];
+    const int t = threadIdx.x, T = blockDim.x;
+    const int chunk = (nTiles + T - 1) / T, b = min(nTiles, t * chunk), e = min(nTiles, b + chunk);
+    int first = 0;
+    for (int i = b; i < e; i++) first += ((flag[i] != 0) == (flagFirst != 0)) ? 1 : 0;
+    sCnt[t] = first;
+    __syncthreads();
+    for (int off = 1; off < T; off <<= 1) {
+        const int v = t >= off ? sCnt[t - off] : 0;
+        __syncthreads();
+        sCnt[t] += v;
+        __syncthreads();
+    }
+    const int nFirst = sCnt[T - 1];
+    int pf = t == 0 ? 0 : sCnt[t - 1]; // tiles of the first group in front of my chunk
+    int ps = nFirst + (b - pf);        // ... of the second group
+    for (int i = b; i < e; i++) {
+        if ((flag[i] != 0) == (flagFirst != 0)) order[pf++] = i;
+        else order[ps++] = i;
+    }
+    if (t == 0) order[nTiles] = nFirst;
+}
+// tiles of 128 rods (k_force_vel_rec's CTA) that contain a rod mirrored on a neighbour rank
+__global__ void k_rod_tile_flag(int nRods, const int *__restrict__ mirL, const int *__restrict__ mirR, int *__restrict__ flag) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRods) return;
+    if ((mirL && mirL[r] >= 0) || (mirR && mirR[r] >= 0)) flag[r >> 7] = 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // setup: q = delta0/dt + D^T v_nc (ConstraintSolver.cpp:18-27), K^-1/dt, bilateral flag, x0 = gamma guess
 __global__ void k_setup(long long nc, ConGeom g, const int *__restrict__ sUser, const double *__restrict__ velNC,
                         const double *__restrict__ delta0, const double *__restrict__ gamma0,
                         const double *__restrict__ invKappa, const unsigned char *__restrict__ bi, double invDt,
                         double *__restrict__ b, double *__restrict__ invKdt, double *__restrict__ lbFlag,
-                        double *__restrict__ x0, const unsigned char *__restrict__ ghost, int *__restrict__ ghostRange) {
+                        double *__restrict__ x0, const unsigned char *__restrict__ ghost, int *__restrict__ tileFlag) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nc) return;
-    if (ghostRange) { // multi-GPU: rows that read a ghost rod's velocity lie in [0, ghostRange[0]) and [ghostRange[1], nc)
+    if (tileFlag) { // multi-GPU: tiles of 256 rows (k_bb_tail's unit of work) that contain a row reading a ghost rod's velocity
         const int j = g.idxJ[k];
-        if (ghost[g.idxI[k]] || (j >= 0 && ghost[j])) {
-            if (k < nc / 2) atomicMax(&ghostRange[0], (int)k + 1);
-            else atomicMin(&ghostRange[1], (int)k);
-        }
+        if (ghost[g.idxI[k]] || (j >= 0 && ghost[j])) tileFlag[k / kVecBlock] = 1;
     }
     double dnc = 0;
     if (velNC) {
@@ -563,6 +592,10 @@ struct HaloPush {
     unsigned long long *flag[2];
     unsigned long long seq;
     unsigned int *ticket;
+    // k_force_vel_rec: CTA b works on rod tile order[b]; the tiles that contain a mirrored rod come first (order[gridDim] of
+    // them) and only their CTAs take a ticket: the neighbours' halo flags are released as soon as the boundary is done,
+    // while the interior tiles are still being worked on (nullptr: natural order, every CTA takes a ticket)
+    const int *order;
 };
 
 // Where the force kernel takes x from.  XMODE 0: a plain vector.  XMODE 1: gamma_b = gamma o biFlag
@@ -1016,9 +1049,14 @@ struct FvRec {
 // SRC: where a live slot's multiplier comes from -- 0: {x, g} inside the record (rec_mode 0), 1: the row-ordered {x, g}
 // pairs, gathered by the row id in the record (rec_mode 1, BBPGD), 2: a plain vector, gathered by row id (rec_mode 1)
 template <bool WRITE_F, bool HALO, int SRC>
-__global__ void __launch_bounds__(128, 10) k_force_vel_rec(FvRec in, MobIn mob, double *__restrict__ U, double *__restrict__ F,
-                                                           const SolverScalars *__restrict__ scal, HaloPush hp) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, double *__restrict__ U, double *__restrict__ F,
+                                                       const SolverScalars *__restrict__ scal, HaloPush hp) {
+    int tile = blockIdx.x, nTicket = gridDim.x;
+    if (HALO && hp.on && hp.order) {
+        tile = hp.order[blockIdx.x];
+        nTicket = hp.order[gridDim.x];
+    }
+    const int r = tile * blockDim.x + threadIdx.x;
     const bool act = r < in.nRods;
     int b = 0, e = 0;
     unsigned ghost = 1;
@@ -1037,28 +1075,14 @@ __global__ void __launch_bounds__(128, 10) k_force_vel_rec(FvRec in, MobIn mob, 
     const double alpha = (in.update && scal) ? scal->alpha : 0.0;
     double f[6] = {0, 0, 0, 0, 0, 0};
     bool any = false, pushed = false;
-    const int w0 = b >> 5, w1 = e > b ? (e - 1) >> 5 : w0 - 1;
-    auto wordOf = [&](int wd) { // the live bits of my slot range in bitmap word wd
-        unsigned bits = __ldg(in.slotLive + wd);
-        const int lo = wd << 5;
-        if (b > lo) bits &= ~((1u << (b - lo)) - 1u);
-        if (e < lo + 32) bits &= (1u << (e - lo)) - 1u;
-        return bits;
-    };
-    // pass 1: is anything live?  (a rod's slots span 1-2 words; they are read again below, from L1)
-    for (int wd = w0; wd <= w1; wd++) any = any || wordOf(wd) != 0;
-    // the rod's mobility data (one 64-byte line) is requested NOW, together with the records below: a rod without a
-    // live slot (45 % of them) has f = 0 and therefore u = +0 exactly and never reads it
-    double qx = 0, qy = 0, qz = 0, iPara = 0;
-    double2 iPR = make_double2(0.0, 0.0); // {1/zeta_perp, 1/zeta_rot}
-    if (any && !ghost) {
-        ld256(mob.rec + 8 * (size_t)r, qx, qy, qz, iPara);
-        iPR = ldGather2(reinterpret_cast<const double2 *>(mob.rec + 8 * (size_t)r + 4));
-    }
-    if (any) {
-        for (int wd = w0; wd <= w1; wd++) {
-            unsigned bits = wordOf(wd);
+    if (act && e > b) {
+        for (int wd = b >> 5; wd <= (e - 1) >> 5; wd++) {
+            unsigned bits = __ldg(in.slotLive + wd);
             const int lo = wd << 5;
+            if (b > lo) bits &= ~((1u << (b - lo)) - 1u);
+            if (e < lo + 32) bits &= (1u << (e - lo)) - 1u;
+            if (!bits) continue;
+            any = true;
             const unsigned biw = (SRC == 0 && in.update) ? __ldg(in.slotBi + wd) : 0u;
             while (bits) { // ascending slot order
                 const int q = __ffs(bits) - 1;
@@ -1083,6 +1107,13 @@ __global__ void __launch_bounds__(128, 10) k_force_vel_rec(FvRec in, MobIn mob, 
                 f[3] += c3 * x; f[4] += c4 * x; f[5] += c5 * x;
             }
         }
+    }
+    // a rod without a live slot (45 % of them) has f = 0 and therefore u = +0 exactly and never reads its mobility data
+    double qx = 0, qy = 0, qz = 0, iPara = 0;
+    double2 iPR = make_double2(0.0, 0.0); // {1/zeta_perp, 1/zeta_rot}
+    if (any && !ghost) {
+        ld256(mob.rec + 8 * (size_t)r, qx, qy, qz, iPara); // one 64-byte line per rod
+        iPR = ldGather2(reinterpret_cast<const double2 *>(mob.rec + 8 * (size_t)r + 4));
     }
     if (act && !ghost) {
         double2 u0 = make_double2(0.0, 0.0), u1 = u0, u2 = u0;
@@ -1112,17 +1143,22 @@ __global__ void __launch_bounds__(128, 10) k_force_vel_rec(FvRec in, MobIn mob, 
             pushed = true;
         }
     }
-    if (HALO && hp.on && hp.ticket) { // fused multi-GPU: the last CTA of the grid releases the neighbours' halo flags
-        if (pushed) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned t = atomicAdd(hp.ticket, 1u);
-            if (t == gridDim.x - 1) {
-                *hp.ticket = 0;
-                __threadfence_system();
-                if (hp.flag[0]) stReleaseSys(hp.flag[0], hp.seq);
-                if (hp.flag[1]) stReleaseSys(hp.flag[1], hp.seq);
+    if (HALO && hp.on && hp.ticket) { // fused multi-GPU: the last CTA of the BOUNDARY tiles releases the neighbours' halo flags
+        if ((int)blockIdx.x < nTicket) {
+            if (pushed) __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned t = atomicAdd(hp.ticket, 1u);
+                if ((int)t == nTicket - 1) {
+                    *hp.ticket = 0;
+                    __threadfence_system();
+                    if (hp.flag[0]) stReleaseSys(hp.flag[0], hp.seq);
+                    if (hp.flag[1]) stReleaseSys(hp.flag[1], hp.seq);
+                }
             }
+        } else if (nTicket == 0 && blockIdx.x == 0 && threadIdx.x == 0) { // nothing is mirrored: the flags still advance
+            if (hp.flag[0]) stReleaseSys(hp.flag[0], hp.seq);
+            if (hp.flag[1]) stReleaseSys(hp.flag[1], hp.seq);
         }
     }
 }
@@ -1359,7 +1395,7 @@ struct BbTail {
     int histCap;
     double tol;
     int ite; // iteration number of this launch (0 = initial gradient)
-    const int *ghostRange;    // multi-GPU: rows reading ghost velocities are in [0, [0]) and [[1], nc) (k_setup); nullptr: unknown
+    const int *tileOrder;     // multi-GPU: [nTiles] tile indices, tiles without a ghost-reading row first; [nTiles] = their number (nullptr: natural order, wait at the start)
     int pdlTrig;              // see FvAct
     int *prog;                // pinned host words {completed applies, done}: the host throttles its launches on them
     int keepXG;               // store {x, g} with the L2 evict_last policy (the force kernel gathers it next)
@@ -1613,19 +1649,15 @@ template <bool HASK>
 __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     const int done = p.scal->done;
     const double alpha = p.scal->alpha; // plain loads: every thread reads the same two words, which L1 broadcasts
-    // Rows are walked in tiles of 256 (one per CTA trip, grid-stride).  Multi-GPU: the tiles are rotated so that the rows
-    // reading a ghost rod's velocity (the first and last rows when the slab axis is the slowest cell axis, k_setup) come
-    // LAST; the wait for the neighbours' halo sits in front of the first such tile, behind all the work that needs no halo.
+    // Rows are walked in tiles of 256 (one per CTA trip, grid-stride).  Multi-GPU: the tiles that contain a row reading a
+    // ghost rod's velocity come LAST; the wait for the neighbours' halo sits in front of the first such tile, behind all
+    // the work that needs no halo (the neighbours' force kernels push their mirrored rows FIRST, see k_force_vel_rec).
     const int nTiles = (int)((p.nc + kVecBlock - 1) / kVecBlock);
-    int shift = 0, nClean = 0;
-    if (p.waitSeq && p.ghostRange) {
-        const int g0 = p.ghostRange[0], g1 = p.ghostRange[1];
-        shift = min((g0 + kVecBlock - 1) / kVecBlock, nTiles);
-        nClean = max(0, g1 / kVecBlock - shift);
-    }
+    // p.tileOrder (k_tile_order, built at setup): the tiles without a ghost-reading row first (nClean of them), then the
+    // others -- whatever the slab axis
+    const int nClean = (p.waitSeq && p.tileOrder) ? p.tileOrder[nTiles] : 0;
     auto rowOf = [&](int tau) -> long long {
-        int tile = tau + shift;
-        if (tile >= nTiles) tile -= nTiles;
+        const int tile = (p.waitSeq && p.tileOrder) ? p.tileOrder[tau] : tau;
         return (long long)tile * kVecBlock + threadIdx.x;
     };
     int tau = blockIdx.x;
@@ -2146,17 +2178,30 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
             k_inc_emit<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incRaw.p, conGeom(c), c.incCon.p,
                                                         c.incCol.p, (size_t)c.incStride);
         }
-        int *ghostRange = nullptr;
-        if (c.comm.active) { // where the rows that touch ghost rods sit: the tail kernel keeps them for last
-            c.ghostRange.reserve(2);
-            const int init[2] = {0, (int)nc};
-            ALENS_CUDA(cudaMemcpyAsync(c.ghostRange.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-            ALENS_CUDA(cudaStreamSynchronize(st)); // `init` lives on this stack frame
-            ghostRange = c.ghostRange.p;
+        int *tileFlag = nullptr;
+        const int nTiles = gridFor(nc, kVecBlock), nRodTiles = gridFor(std::max(n, 1), 128);
+        if (c.comm.active) { // which tiles of rows read ghost velocities (k_bb_tail keeps them for last), which tiles of
+                             // rods are mirrored on a neighbour (k_force_vel_rec computes and pushes them first)
+            c.tailFlag.reserve((size_t)nTiles + 1);
+            c.tailOrder.reserve((size_t)nTiles + 2);
+            c.rodFlag.reserve((size_t)nRodTiles + 1);
+            c.rodOrder.reserve((size_t)nRodTiles + 2);
+            ALENS_CUDA(cudaMemsetAsync(c.tailFlag.p, 0, sizeof(int) * ((size_t)nTiles + 1), st));
+            ALENS_CUDA(cudaMemsetAsync(c.rodFlag.p, 0, sizeof(int) * ((size_t)nRodTiles + 1), st));
+            tileFlag = c.tailFlag.p;
         }
         k_setup<<<gridFor(nc, 256), 256, 0, st>>>(nc, conGeom(c), c.sUser.p, useV ? c.uVelNC.p : nullptr,
                                                   c.cDelta0.p, c.cGamma0.p, c.cInvKappa.p, c.cBi.p, 1.0 / dt,
-                                                  c.vB.p, c.vTmp5.p, c.vLbFlag.p, c.vX0.p, c.sGhost.p, ghostRange);
+                                                  c.vB.p, c.vTmp5.p, c.vLbFlag.p, c.vX0.p, c.sGhost.p, tileFlag);
+        if (c.comm.active) {
+            const Comm &m = c.comm;
+            if (n > 0)
+                k_rod_tile_flag<<<gridFor(n, 256), 256, 0, st>>>(n, m.left >= 0 ? m.mirror[0].p : nullptr,
+                                                                 m.right >= 0 ? m.mirror[1].p : nullptr, c.rodFlag.p);
+            k_tile_order<<<1, 1024, 0, st>>>(nTiles, c.tailFlag.p, 0, c.tailOrder.p);
+            k_tile_order<<<1, 1024, 0, st>>>(nRodTiles, c.rodFlag.p, 1, c.rodOrder.p);
+            c.launches += 3;
+        }
         c.launches += 3;
     }
     ALENS_CUDA(cudaGetLastError());
@@ -2470,7 +2515,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
         t.slotLive = c.slotLive.p;
     }
     t.pdlTrig = c.optPdl == 2;
-    t.ghostRange = (multi && c.optLateHalo && c.ghostRange.p) ? c.ghostRange.p : nullptr;
+    t.tileOrder = (multi && c.optLateHalo && c.tailOrder.p && nc > 0) ? c.tailOrder.p : nullptr;
     if (multi) {
         t.own = c.cOwn.p;
         t.redOut = reinterpret_cast<double *>(c.dCounters.p); // 4 doubles of scratch
@@ -2502,6 +2547,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
                 }
                 hp.seq = seq;
                 hp.ticket = &c.dScal.p->ticketFv;
+                if (c.incLayout == 3 && c.optLateHalo && c.rodOrder.p && c.nRods > 0) hp.order = c.rodOrder.p;
             }
             launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p, &hp);
             if (c.incLayout == 0) commSignalHalo(c, seq);

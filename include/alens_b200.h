@@ -143,6 +143,19 @@ int alens_collect_boundary_collision(alens_ctx *ctx, const alens_boundary *bound
  * Both rods of a link must be owned by this rank (links across slabs: push the block with alens_append_constraints). */
 int alens_collect_link_bilateral(alens_ctx *ctx, const int *prevGid, const int *nextGid, long long nLinks, double linkKappa,
                                  double linkGap, long long *nAdded);
+/* The fields of ProteinData / ProteinBindStatus that TubuleSystem::setProteinConstraints (SRC/TubuleSystem.cpp:694-745)
+ * reads for one protein (Protein/ProteinBindStatus.hpp: idBind, indexBind, centerBind, directionBind, posEndBind, lenBind;
+ * ProteinData::getProteinForceLength(), property.freeLength, property.kappa).  idBind < 0 = that end is unbound (ID_UB). */
+typedef struct alens_protein_bind {
+    int idBind[2], indexBind[2];
+    double centerBind[2][3], directionBind[2][3], posEndBind[2][3], lenBind[2];
+    double forceLength, freeLength, kappa;
+} alens_protein_bind;
+/* TubuleSystem::setProteinConstraints on the device: one bilateral block per DOUBLY bound protein (delta0 = forceLength -
+ * freeLength, gamma0 = -delta0 kappa, normI = (P - Q)/|P - Q|, posI/J relative to the rod centres, stress by collideStress
+ * with radius tubuleDiameter / 2), appended in protein order; indexBind = globalIndex of the rods (this rank's). */
+int alens_collect_protein_bilateral(alens_ctx *ctx, const alens_protein_bind *proteins, long long n, double tubuleDiameter,
+                                    long long *nAdded);
 int alens_clear_constraints(alens_ctx *ctx); /* ConstraintCollector::clear */
 /* ConstraintCollector::getLocalNumberOfConstraints (ConstraintCollector.cpp:30-36) */
 int alens_num_constraints(alens_ctx *ctx, long long *n);

@@ -372,6 +372,14 @@ def brown_normals(seed, n_rods):
     return out
 
 
+def collide_stress(dirI, dirJ, cI, cJ, lenI, lenJ, radI, radJ, rho, P, Q):
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (dirI, dirJ, cI, cJ, P, Q)]
+    out = np.zeros(9)
+    lib().refsys_collide_stress(_dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), C.c_double(lenI), C.c_double(lenJ),
+                                C.c_double(radI), C.c_double(radJ), C.c_double(rho), _dp(a[4]), _dp(a[5]), _dp(out))
+    return out
+
+
 def drag_coeff(length, radius, mu):
     a, b, c = C.c_double(), C.c_double(), C.c_double()
     lib().refsys_drag_coeff(C.c_double(length), C.c_double(radius), C.c_double(mu), C.byref(a), C.byref(b), C.byref(c))

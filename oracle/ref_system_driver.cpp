@@ -391,6 +391,20 @@ void refsys_brown_normals(int seed, int nRods, double *out12) {
     }
 }
 
+// CalcSylinderNearForce::collideStress (SylinderNear.hpp:432-484), the public static the link and protein code call
+void refsys_collide_stress(const double *dirI, const double *dirJ, const double *centerI, const double *centerJ, double lenI,
+                           double lenJ, double radI, double radJ, double rho, const double *Ploc, const double *Qloc,
+                           double *stress9) {
+    Emat3 st;
+    CalcSylinderNearForce::collideStress(Evec3(dirI[0], dirI[1], dirI[2]), Evec3(dirJ[0], dirJ[1], dirJ[2]),
+                                         Evec3(centerI[0], centerI[1], centerI[2]), Evec3(centerJ[0], centerJ[1], centerJ[2]),
+                                         lenI, lenJ, radI, radJ, rho, Evec3(Ploc[0], Ploc[1], Ploc[2]),
+                                         Evec3(Qloc[0], Qloc[1], Qloc[2]), st);
+    ConstraintBlock blk;
+    blk.setStress(st);
+    for (int k = 0; k < 9; k++) stress9[k] = blk.stress[k];
+}
+
 // Sylinder::calcDragCoeff (Sylinder.cpp:69-82)
 void refsys_drag_coeff(double length, double radius, double viscosity, double *para, double *perp, double *rot) {
     const double pos[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1};
