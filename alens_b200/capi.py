@@ -39,7 +39,7 @@ EXPORTS = [
     "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest",
     "alens_get_live_stats", "alens_bcqp_create_csr", "alens_bcqp_create_constraint", "alens_bcqp_set_lower_bound",
     "alens_bcqp_set_upper_bound", "alens_bcqp_get_bounds", "alens_bcqp_run", "alens_bcqp_history", "alens_bcqp_size",
-    "alens_bcqp_destroy", "alens_collect_protein_bilateral",
+    "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps",
 ]
 
 
@@ -360,6 +360,17 @@ class Context:
         a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
         self._call("alens_num_ghosts", C.byref(a), C.byref(b), C.byref(c))
         return dict(ghosts=a.value, sent_left=b.value, sent_right=c.value)
+
+    def get_stamps(self, cap=4096):
+        buf = np.zeros((cap, 8), dtype=np.uint64)
+        n = C.c_int(0)
+        self._call("alens_get_stamps", buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.c_int(cap), C.byref(n))
+        return buf[:min(n.value, cap)]
+
+    def get_pool_stats(self):
+        a, b, c = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        self._call("alens_get_pool_stats", C.byref(a), C.byref(b), C.byref(c))
+        return dict(collision=a.value, one_side=b.value, bilateral=c.value)
 
     def get_live_stats(self):
         a, b = C.c_longlong(0), C.c_longlong(0)

@@ -451,6 +451,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
             if (c.optForceKernel == 3) c.optTailRing = 0; // the TMA-staged tail does not maintain the slot records
         }
         else if (k == "rec_mode") c.optRecMode = value != 0;
+        else if (k == "stamps") c.optStamps = value != 0;
         else if (k == "find_minb") c.optFindMinB = (value == 5 || value == 3) ? (int)value : 4;
         else if (k == "find_split") c.optFindSplit = value != 0;
         else if (k == "find_split_minb") c.optFindSplitMinB = value == 6 ? 6 : 8;
@@ -631,6 +632,23 @@ void alens_bcqp_destroy(alens_bcqp *p) {
     if (!p) return;
     guarded(p->ctx, [&](Context &) { bcqpDestroy(p->q); });
     delete p;
+}
+
+int alens_get_stamps(alens_ctx *ctx, unsigned long long *stamps8, int capIterations, int *nIterations) {
+    return guarded(ctx, [&](Context &c) {
+        const int n = std::min(c.stampIters, capIterations);
+        if (n > 0 && stamps8)
+            ALENS_CUDA(cudaMemcpy(stamps8, c.dStamps.p, 64 * (size_t)n, cudaMemcpyDeviceToHost));
+        if (nIterations) *nIterations = c.stampIters;
+    });
+}
+
+int alens_get_pool_stats(alens_ctx *ctx, long long *nCollision, long long *nOneSide, long long *nBilateral) {
+    return guarded(ctx, [&](Context &c) {
+        if (nCollision) *nCollision = c.nColl;
+        if (nOneSide) *nOneSide = c.nOneSide;
+        if (nBilateral) *nBilateral = c.nBilateral;
+    });
 }
 
 int alens_get_live_stats(alens_ctx *ctx, long long *liveSlots, long long *liveRods) {

@@ -265,6 +265,9 @@ struct Context {
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 3;                 // 3 = k_force_vel_rec (64-byte slot records + slot-ordered live bitmap kept by k_bb_tail), 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
+    int optStamps = 0, stampCap = 0, stampIters = 0; // per-iteration nanosecond stamps of the BBPGD kernels (instrumentation)
+    DevBuf<unsigned long long> dStamps;
+    unsigned long long *stampNow = nullptr;
     int optRecMode = 1, recMode = 1;        // force_kernel 3: 0 = k_bb_tail copies {x, g} into the slot records, 1 = the records hold the row id and k_force_vel_rec gathers {x, g} itself
     DevBuf<double> incRec;                  // force_kernel 3: 8 doubles per slot {x, g, D column block[6]}, 64-byte aligned records
     DevBuf<int2> cSlot;                     // ... per constraint: slot of its I side / J side (-1: none, ghost or one-sided)

@@ -532,6 +532,15 @@ __device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, u
 // touch data that is at least TWO kernels old.  That holds because every kernel signals pdlLaunchDependents() only
 // AFTER its own pdlWait(): when a dependent starts, the predecessor of its predecessor is complete.
 // Both are no-ops in a kernel that was launched without the attribute.
+// instrumentation (alens_set_option("stamps", 1)): nanosecond stamps of one BBPGD iteration, 8 words per iteration:
+// [0] first force CTA past its dependency wait (min), [1] force kernel released the halo flags, [2] last force CTA done (max),
+// [3] first tail CTA past its dependency wait (min), [4] first tail CTA reached the halo wait (min), [5] last tail CTA
+// saw the halo (max), [6] last tail CTA finished its rows (ticket), [7] allreduce complete / scalar step taken
+__device__ __forceinline__ unsigned long long globalNs() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -1044,6 +1053,7 @@ struct FvRec {
     const double2 *xg;
     const double *x;
     int xmode;
+    unsigned long long *stamp; // 8 words of this iteration (nullptr: off)
 };
 
 // SRC: where a live slot's multiplier comes from -- 0: {x, g} inside the record (rec_mode 0), 1: the row-ordered {x, g}
@@ -1072,6 +1082,7 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
     }
     pdlWait(); // records, bitmap and step size come from the previous kernel
     if (scal && scal->done) return;
+    if (in.stamp && threadIdx.x == 0) atomicMin(in.stamp + 0, globalNs());
     const double alpha = (in.update && scal) ? scal->alpha : 0.0;
     double f[6] = {0, 0, 0, 0, 0, 0};
     bool any = false, pushed = false;
@@ -1154,6 +1165,7 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
                     __threadfence_system();
                     if (hp.flag[0]) stReleaseSys(hp.flag[0], hp.seq);
                     if (hp.flag[1]) stReleaseSys(hp.flag[1], hp.seq);
+                    if (in.stamp) in.stamp[1] = globalNs();
                 }
             }
         } else if (nTicket == 0 && blockIdx.x == 0 && threadIdx.x == 0) { // nothing is mirrored: the flags still advance
@@ -1161,6 +1173,7 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
             if (hp.flag[1]) stReleaseSys(hp.flag[1], hp.seq);
         }
     }
+    if (in.stamp && threadIdx.x == 0) atomicMax(in.stamp + 2, globalNs());
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1406,6 +1419,7 @@ struct BbTail {
     double *rec;
     const int2 *cSlot;
     unsigned *slotLive;
+    unsigned long long *stamp; // 8 words of this iteration (nullptr: off)
     const unsigned char *own; // multi-rank: 1 = this rank counts the row in the dot products (nullptr = all)
     double *redOut;           // multi-rank: the reduced partials go here, k_bb_reduce finishes the step
     // fused multi-GPU variant (one rank per device): the kernel itself waits for the neighbours' ghost rows of U
@@ -1449,6 +1463,7 @@ __device__ __forceinline__ void bbScalarStep(const BbTail &p, const double out[4
         sc->alpha = alpha;
         if (alpha < DBL_EPSILON * 10) sc->done = 2; // stagnation (BCQPSolver.cpp:229-233)
     }
+    if (p.stamp) p.stamp[7] = globalNs();
     if (p.prog) { // host flow control: no stream synchronisation inside the loop
         volatile int *pg = p.prog;
         pg[1] = sc->done;
@@ -1585,6 +1600,7 @@ __device__ __forceinline__ void tailEpilogue(const BbTail &p, double s0, double 
     __syncthreads();
     if (!last) return;
     __threadfence();
+    if (p.stamp && threadIdx.x == 0) p.stamp[6] = globalNs();
     // fixed-order reduction of the per-CTA partials
     s0 = s1 = s2 = mx = 0;
     const volatile double *pp = p.partial;
@@ -1668,6 +1684,7 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     pdlWait(); // U comes from the force kernel right in front
     if (p.pdlTrig) pdlLaunchDependents();
     if (done) return;
+    if (p.stamp && threadIdx.x == 0) atomicMin(p.stamp + 3, globalNs());
     bool waited = p.waitSeq == 0;
     const int lane = threadIdx.x & 31;
     int nMaybe = 0; // rows of this warp whose bit is set (statistics for the roofline accounting of the force kernel)
@@ -1675,8 +1692,10 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     while (tau < nTiles) {
         if (!waited && tau >= nClean) { // ghost rows of U: pushed by the neighbours' force kernels (CTA-uniform test)
             if (threadIdx.x == 0) {
+                if (p.stamp) atomicMin(p.stamp + 4, globalNs());
                 if (p.waitFlag[0]) waitSeq(p.waitFlag[0], p.waitSeq, p.red.err);
                 if (p.waitFlag[1]) waitSeq(p.waitFlag[1], p.waitSeq, p.red.err);
+                if (p.stamp) atomicMax(p.stamp + 5, globalNs());
             }
             __syncthreads();
             waited = true;
@@ -2331,7 +2350,8 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
             c.launches++;
             c.timers.op_launches++;
         }
-        FvRec fr{c.incStart.p, c.incRec.p, c.slotLive.p, c.slotBi.p, n, init ? 0 : 1, nullptr, nullptr, XMODE};
+        FvRec fr{c.incStart.p, c.incRec.p, c.slotLive.p, c.slotBi.p, n, init ? 0 : 1, nullptr, nullptr, XMODE,
+                 XMODE == 2 ? c.stampNow : nullptr};
         if (c.recMode == 1) {
             if (XMODE == 2) fr.xg = xin.xg;
             else fr.x = xin.x;
@@ -2524,7 +2544,17 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     // multi-rank: ghost rows of U are pushed to / awaited from the neighbours between the two kernels, and
     // k_bb_reduce replaces the last-CTA scalar step
     const bool fused = multi && c.comm.fused;
+    if (c.optStamps) { // 8 words per iteration: min-stamps start at ~0ull, the others at 0
+        c.stampCap = std::min(maxIte, 4096) + 2;
+        c.dStamps.reserve(8 * (size_t)c.stampCap);
+        std::vector<unsigned long long> init(8 * (size_t)c.stampCap, 0ull);
+        for (int i = 0; i < c.stampCap; i++) init[8 * i] = init[8 * i + 3] = init[8 * i + 4] = ~0ull;
+        ALENS_CUDA(cudaMemcpyAsync(c.dStamps.p, init.data(), 8 * init.size(), cudaMemcpyHostToDevice, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+    }
     auto applyAndTail = [&](const XIn &x) {
+        t.stamp = (c.optStamps && t.ite < c.stampCap) ? c.dStamps.p + 8 * (size_t)t.ite : nullptr;
+        c.stampNow = t.stamp;
         if (fused) {
             // the force kernel also stores the mirrored rows of U into the neighbours' windows, a one-thread kernel
             // releases their halo flags; the tail waits for its own flags before the first gather and finishes
@@ -2639,6 +2669,8 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
         }
     }
     c.pdlNow = false;
+    c.stampNow = nullptr;
+    c.stampIters = c.optStamps ? std::min(c.hScal->ite + 1, c.stampCap) : 0;
     c.timers.op_rows_live = (long long)c.hScal->maybeSum;
     c.timers.op_applies = c.hScal->mv;
     ALENS_CUDA(cudaGetLastError());

@@ -63,6 +63,7 @@ def parse():
     p.add_argument("--cpu-iters", type=int, default=12, help="BBPGD iterations of the fixed-count parity solve")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (and the N = 1 parity check in it)")
     p.add_argument("--no-parity", action="store_true", help="skip the N > 1 digest check")
+    p.add_argument("--stamps", action="store_true", help="one extra (untimed) solve with per-iteration nanosecond stamps")
     a = p.parse_args()
     if a.phi is None:
         a.phi = 0.40 if a.workload == "S2" else 0.10
@@ -453,6 +454,33 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
+    # ---- where an iteration's time goes (untimed extra solve with %globaltimer stamps inside the two kernels) ----
+    breakdown = None
+    if a.stamps:
+        ctx.set_option("stamps", 1)
+        step_resident()
+        ctx.set_option("stamps", 0)
+        st = ctx.get_stamps().astype(np.float64)
+        if len(st) > 4:
+            st = st[2:]  # steady state
+            iv = {"force_us": st[:, 2] - st[:, 0], "force_to_halo_release_us": st[:, 1] - st[:, 0],
+                  "gap_force_to_tail_us": st[:, 3] - st[:, 2], "tail_rows_us": st[:, 6] - st[:, 3],
+                  "tail_halo_wait_us": np.maximum(st[:, 5] - st[:, 4], 0), "tail_start_to_halo_wait_us": st[:, 4] - st[:, 3],
+                  "allreduce_us": st[:, 7] - st[:, 6], "gap_tail_to_next_force_us": np.append(st[1:, 0] - st[:-1, 7], np.nan),
+                  "iteration_us": np.append(st[1:, 0] - st[:-1, 0], np.nan)}
+            if world == 1:
+                iv.pop("force_to_halo_release_us"); iv.pop("tail_halo_wait_us"); iv.pop("tail_start_to_halo_wait_us")
+            mine = np.array([float(np.nanmean(v)) * 1e-3 for v in iv.values()])
+            if world > 1:
+                tt = torch.from_numpy(mine).cuda()
+                allr = [torch.zeros_like(tt) for _ in range(world)]
+                dist.all_gather(allr, tt)
+                per_rank = np.stack([x.cpu().numpy() for x in allr])
+            else:
+                per_rank = mine[None]
+            breakdown = {k: {"rank0": round(float(per_rank[0, i]), 2), "max_over_ranks": round(float(per_rank[:, i].max()), 2),
+                             "min_over_ranks": round(float(per_rank[:, i].min()), 2)} for i, k in enumerate(iv)}
+
     # ---- N > 1 parity (untimed): digests of the ranks against the same suspension on ONE GPU, fused against unfused ----
     parity = None
     if world > 1 and not a.no_parity:
@@ -545,6 +573,8 @@ def main():
         "cpu_baseline": cpu,
         "parity": parity,
     }
+    if breakdown:
+        line["iteration_breakdown_us"] = breakdown
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

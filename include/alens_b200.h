@@ -282,6 +282,15 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value);
  * "force_vel_plain" on the operator of the last alens_setup_constraints (invalidates the setup), or "force_vel_last" on
  * the iterate / mask the last BBPGD solve left behind. */
 int alens_time_kernel(alens_ctx *ctx, const char *which, int reps, double *avgMicroseconds);
+/* alens_set_option("stamps", 1): %globaltimer stamps (ns) of every BBPGD iteration of the last solve, 8 words each:
+ * [0] force kernel: first CTA past its dependency wait, [1] halo flags released to the neighbours, [2] last CTA done;
+ * [3] tail kernel: first CTA past its dependency wait, [4] first CTA reached the halo wait, [5] last CTA saw the halo,
+ * [6] all rows done (last CTA elected), [7] allreduce over the ranks complete and scalar step taken.  Row 0 = iteration 0.
+ * (Multi-GPU: skew between ranks shows up as [5]-[4] and [7]-[6]; the clocks of different GPUs are not aligned.) */
+int alens_get_stamps(alens_ctx *ctx, unsigned long long *stamps8, int capIterations, int *nIterations);
+/* what the pool holds: pair-collision blocks, one-sided blocks, bilateral blocks.  nBilateral == 0 means forceBi and
+ * velocityBi of the next solve are identically zero: a caller need not fetch them (alens_get_force_velocity with NULL) */
+int alens_get_pool_stats(alens_ctx *ctx, long long *nCollision, long long *nOneSide, long long *nBilateral);
 /* force_kernel 3: incidence slots whose bit is set in the slot bitmap, and rods with at least one such slot, as the last
  * solve left them (what k_force_vel_rec reads per launch: 64 bytes per live slot, mobility data per live rod) */
 int alens_get_live_stats(alens_ctx *ctx, long long *liveSlots, long long *liveRods);

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "ConstraintBlock.hpp"
+#include "VtkPolyWriter.hpp"
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -82,6 +83,44 @@ class ConstraintCollector {
         out.reserve(getLocalNumberOfConstraints());
         for (auto &q : *constraintPoolPtr) out.insert(out.end(), q.begin(), q.end());
         return out;
+    }
+
+    /// ConBlock_r<rank>_<postfix>.vtp: one line per block from labI to labJ (ConstraintCollector.cpp:103-224)
+    void writeVTP(const std::string &folder, const std::string &prefix, const std::string &postfix, int rank) const {
+        using alens_vtk::Column;
+        const std::vector<ConstraintBlock> b = flatten();
+        const size_t n = b.size();
+        std::vector<double> ends(6 * n);
+        std::vector<int32_t> gid(2 * n), gidx(2 * n), one(n), bi(n);
+        std::vector<float> posIJ(6 * n), normIJ(6 * n), d0(n), gam(n), kap(n), stress(9 * n);
+        for (size_t i = 0; i < n; i++) {
+            for (int k = 0; k < 3; k++) {
+                ends[6 * i + k] = b[i].labI[k];         ends[6 * i + 3 + k] = b[i].labJ[k];
+                posIJ[6 * i + k] = (float)b[i].posI[k];   posIJ[6 * i + 3 + k] = (float)b[i].posJ[k];
+                normIJ[6 * i + k] = (float)b[i].normI[k]; normIJ[6 * i + 3 + k] = (float)b[i].normJ[k];
+            }
+            gid[2 * i] = b[i].gidI; gid[2 * i + 1] = b[i].gidJ;
+            gidx[2 * i] = b[i].globalIndexI; gidx[2 * i + 1] = b[i].globalIndexJ;
+            one[i] = b[i].oneSide ? 1 : 0;
+            bi[i] = b[i].bilateral ? 1 : 0;
+            d0[i] = (float)b[i].delta0; gam[i] = (float)b[i].gamma; kap[i] = (float)b[i].kappa;
+            for (int k = 0; k < 9; k++) stress[9 * i + k] = (float)b[i].stress[k];
+        }
+        alens_vtk::writeLinePiece(folder + '/' + prefix + "ConBlock_r" + std::to_string(rank) + "_" + postfix + ".vtp", (int)n, ends,
+                                  {Column::of("gid", 1, gid), Column::of("globalIndex", 1, gidx), Column::of("posIJ", 3, posIJ),
+                                   Column::of("normIJ", 3, normIJ)},
+                                  {Column::of("oneSide", 1, one), Column::of("bilateral", 1, bi), Column::of("delta0", 1, d0),
+                                   Column::of("gamma", 1, gam), Column::of("kappa", 1, kap), Column::of("Stress", 9, stress)});
+    }
+    /// ConBlock_<postfix>.pvtp (ConstraintCollector.cpp:76-101)
+    void writePVTP(const std::string &folder, const std::string &prefix, const std::string &postfix, const int nProcs) const {
+        std::vector<std::string> pieces;
+        for (int i = 0; i < nProcs; i++) pieces.push_back(prefix + "ConBlock_r" + std::to_string(i) + "_" + postfix + ".vtp");
+        alens_vtk::writeParallelIndex(folder + "/" + prefix + "ConBlock_" + postfix + ".pvtp",
+                                      {{"gid", "Int32", 1}, {"globalIndex", "Int32", 1}, {"posIJ", "Float32", 3}, {"normIJ", "Float32", 3}},
+                                      {{"oneSide", "Int32", 1}, {"bilateral", "Int32", 1}, {"delta0", "Float32", 1},
+                                       {"gamma", "Float32", 1}, {"kappa", "Float32", 1}, {"Stress", "Float32", 9}},
+                                      pieces);
     }
 
     /// replace the pool content by every block the device holds (collision blocks first, then the host

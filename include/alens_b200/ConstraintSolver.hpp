@@ -79,7 +79,12 @@ class ConstraintSolver {
                                            : mobMapRcp;
         auto mk = [&]() { return Teuchos::RCP<TV>(std::make_shared<TV>(mob, true)); };
         forceuRcp = mk(); veluRcp = mk(); forcebRcp = mk(); velbRcp = mk();
-        ck(alens_get_force_velocity(ctx_, forceuRcp->data(), veluRcp->data(), forcebRcp->data(), velbRcp->data()));
+        // without a bilateral block force_b = D gamma_b and vel_b = M force_b (ConstraintSolver.cpp:98-101) are identically
+        // zero: the zero-initialised vectors above already hold the result, and 96 bytes per rod stay off the PCIe bus
+        long long nBi = 0;
+        ck(alens_get_pool_stats(ctx_, nullptr, nullptr, &nBi));
+        ck(alens_get_force_velocity(ctx_, forceuRcp->data(), veluRcp->data(), nBi ? forcebRcp->data() : nullptr,
+                                    nBi ? velbRcp->data() : nullptr));
     }
 
     /// the same log line as ConstraintSolver.cpp:92-93 ("RECORD: BCQP residue ...")

@@ -7,6 +7,10 @@
 
 #include <cmath>
 #include <cstring>
+#include <string>
+#include <vector>
+
+#include "VtkPolyWriter.hpp"
 #include <cstdio>
 #include <limits>
 
@@ -58,6 +62,94 @@ class Sylinder {
         d[1] = w * uy + z * ux;
         d[2] = 1.0 + (x * uy - y * ux);
     }
+    /// Eigen's quaternion * vector (QuaternionBase::_transformVector): uv = q.vec x v; uv += uv; v + w uv + q.vec x uv
+    void rotate(const double v[3], double out[3]) const {
+        const double x = orientation[0], y = orientation[1], z = orientation[2], w = orientation[3];
+        double ux = y * v[2] - z * v[1], uy = z * v[0] - x * v[2], uz = x * v[1] - y * v[0];
+        ux += ux; uy += uy; uz += uz;
+        out[0] = v[0] + w * ux + (y * uz - z * uy);
+        out[1] = v[1] + w * uy + (z * ux - x * uz);
+        out[2] = v[2] + w * uz + (x * uy - y * ux);
+    }
+
+    /// the columns of Sylinder_r<rank>_<postfix>.vtp in the reference's order (Sylinder.hpp:185-259, :281-453)
+    struct VtkColumn {
+        const char *name;
+        int ncomp;
+        const char *type;
+    };
+    static const std::vector<VtkColumn> &vtkCellColumns() {
+        static const std::vector<VtkColumn> cols = {
+            {"gid", 1, "Int32"}, {"group", 1, "Int32"}, {"isImmovable", 1, "UInt8"}, {"radius", 1, "Float32"},
+            {"radiusCollision", 1, "Float32"}, {"length", 1, "Float32"}, {"lengthCollision", 1, "Float32"},
+            {"vel", 3, "Float32"}, {"omega", 3, "Float32"}, {"velCollision", 3, "Float32"}, {"omegaCollision", 3, "Float32"},
+            {"velBilateral", 3, "Float32"}, {"omegaBilateral", 3, "Float32"}, {"velNonBrown", 3, "Float32"},
+            {"omegaNonBrown", 3, "Float32"}, {"force", 3, "Float32"}, {"torque", 3, "Float32"},
+            {"forceCollision", 3, "Float32"}, {"torqueCollision", 3, "Float32"}, {"forceBilateral", 3, "Float32"},
+            {"torqueBilateral", 3, "Float32"}, {"forceNonBrown", 3, "Float32"}, {"torqueNonBrown", 3, "Float32"},
+            {"velBrown", 3, "Float32"}, {"omegaBrown", 3, "Float32"}, {"xnorm", 3, "Float32"}, {"znorm", 3, "Float32"}};
+        return cols;
+    }
+    /// Sylinder::writeVTP: one line per rod between its two end points, `prefix` ends in '/' (a folder)
+    template <class Container>
+    static void writeVTP(const Container &sylinder, const int sylinderNumber, const std::string &prefix,
+                         const std::string &postfix, int rank) {
+        using alens_vtk::Column;
+        const size_t n = (size_t)sylinderNumber;
+        std::vector<double> ends(6 * n);
+        std::vector<uint8_t> label(2 * n), imm(n);
+        std::vector<int32_t> gid(n), group(n);
+        std::vector<float> scal[4];
+        for (auto &v : scal) v.resize(n);
+        // the 3-vectors of the record, in file order: member pointers into the 568-byte layout
+        double (Sylinder::*const vecs[])[3] = {&Sylinder::vel, &Sylinder::omega, &Sylinder::velCol, &Sylinder::omegaCol,
+                                               &Sylinder::velBi, &Sylinder::omegaBi, &Sylinder::velNonB, &Sylinder::omegaNonB,
+                                               &Sylinder::force, &Sylinder::torque, &Sylinder::forceCol, &Sylinder::torqueCol,
+                                               &Sylinder::forceBi, &Sylinder::torqueBi, &Sylinder::forceNonB,
+                                               &Sylinder::torqueNonB, &Sylinder::velBrown, &Sylinder::omegaBrown};
+        constexpr int NV = sizeof(vecs) / sizeof(vecs[0]);
+        std::vector<float> v3[NV + 2];
+        for (auto &v : v3) v.resize(3 * n);
+        for (size_t i = 0; i < n; i++) {
+            const Sylinder &sy = sylinder[i];
+            const double ex[3] = {1, 0, 0}, ez[3] = {0, 0, 1};
+            double nx[3], nz[3];
+            sy.rotate(ex, nx);
+            sy.rotate(ez, nz);
+            for (int k = 0; k < 3; k++) {
+                ends[6 * i + k] = sy.pos[k] - nz[k] * (sy.length * 0.5);
+                ends[6 * i + 3 + k] = sy.pos[k] + nz[k] * (sy.length * 0.5);
+                for (int a = 0; a < NV; a++) v3[a][3 * i + k] = (float)(sy.*vecs[a])[k];
+                v3[NV][3 * i + k] = (float)nx[k];
+                v3[NV + 1][3 * i + k] = (float)nz[k];
+            }
+            label[2 * i] = 0;
+            label[2 * i + 1] = 1;
+            gid[i] = sy.gid;
+            group[i] = sy.group;
+            imm[i] = sy.isImmovable ? 1 : 0;
+            scal[0][i] = (float)sy.radius; scal[1][i] = (float)sy.radiusCollision;
+            scal[2][i] = (float)sy.length; scal[3][i] = (float)sy.lengthCollision;
+        }
+        const auto &cols = vtkCellColumns();
+        std::vector<Column> cell;
+        cell.push_back(Column::of(cols[0].name, 1, gid));
+        cell.push_back(Column::of(cols[1].name, 1, group));
+        cell.push_back(Column::of(cols[2].name, 1, imm));
+        for (int a = 0; a < 4; a++) cell.push_back(Column::of(cols[3 + a].name, 1, scal[a]));
+        for (int a = 0; a < NV + 2; a++) cell.push_back(Column::of(cols[7 + a].name, 3, v3[a]));
+        alens_vtk::writeLinePiece(prefix + "Sylinder_r" + std::to_string(rank) + "_" + postfix + ".vtp", sylinderNumber, ends,
+                                  {Column::of("endLabel", 1, label)}, cell);
+    }
+    /// Sylinder::writePVTP: the parallel index over nProcs piece files
+    static void writePVTP(const std::string &prefix, const std::string &postfix, const int nProcs) {
+        std::vector<alens_vtk::Field> cell;
+        for (const auto &c : vtkCellColumns()) cell.push_back({c.name, c.type, c.ncomp});
+        std::vector<std::string> pieces;
+        for (int i = 0; i < nProcs; i++) pieces.push_back("Sylinder_r" + std::to_string(i) + "_" + postfix + ".vtp");
+        alens_vtk::writeParallelIndex(prefix + "Sylinder_" + postfix + ".pvtp", {{"endLabel", "UInt8", 1}}, cell, pieces);
+    }
+
     /// one line of SylinderAscii_*.dat, the format the reference reads back (Sylinder.cpp:101-109,
     /// SylinderSystem.cpp:317-344): `C|S gid radius minus[3] plus[3] group`
     void writeAscii(FILE *fptr) const {

@@ -9,6 +9,7 @@
 #ifndef ALENS_B200_SYLINDERSYSTEM_HPP_
 #define ALENS_B200_SYLINDERSYSTEM_HPP_
 
+#include <algorithm>
 #include <cstdio>
 #include <map>
 #include <memory>
@@ -195,6 +196,50 @@ class SylinderSystem {
         for (const auto &l : links) linkMap.emplace(l.prev, l.next);
     }
     const std::multimap<int, int> &getLinkMap() const { return linkMap; }
+
+    // ---- output, as the reference lays it out (SylinderSystem.cpp:478-560): ./result/result<lo>-<hi>/ holds
+    // SylinderAscii_<snap>.dat, Sylinder_r<rank>_<snap>.vtp + Sylinder_<snap>.pvtp, ConBlock_r<rank>_<snap>.vtp +
+    // ConBlock_<snap>.pvtp; ./TimeStepInfo.txt and ./result/simBox.vtk next to it
+    int snapID = 0;
+    unsigned restartRngSeed = 0;
+    int getSnapID() { return snapID; }
+    std::string getCurrentResultFolder() { return getResultFolderWithID(snapID); }
+    std::string getResultFolderWithID(int snapID_) {
+        const int num = std::max(400 / commRcp->getSize(), 1);
+        const int k = snapID_ / num;
+        return "./result/result" + std::to_string(k * num) + "-" + std::to_string(k * num + num - 1) + "/";
+    }
+    bool getIfWriteResultCurrentStep() { return stepCount % static_cast<int>(runConfig.timeSnap / runConfig.dt) == 0; }
+    void writeBox() const { // :535-551
+        FILE *f = std::fopen("./result/simBox.vtk", "w");
+        if (!f) throw std::runtime_error("writeBox: cannot open ./result/simBox.vtk");
+        std::fprintf(f, "# vtk DataFile Version 3.0\nvtk file\nASCII\nDATASET RECTILINEAR_GRID\nDIMENSIONS 2 2 2\n");
+        const char ax[3] = {'X', 'Y', 'Z'};
+        for (int k = 0; k < 3; k++)
+            std::fprintf(f, "%c_COORDINATES 2 float\n%g %g\n", ax[k], runConfig.simBoxLow[k], runConfig.simBoxHigh[k]);
+        std::fprintf(f, "CELL_DATA 1\nPOINT_DATA 8\n");
+        std::fclose(f);
+    }
+    /// writeResult (:553-560): pulls every block back from the device (gamma written back, stress scaled) for the
+    /// constraint file; `makeFolder` is the host's mkdir (the reference uses IOHelper::makeSubFolder)
+    void writeResult() {
+        const std::string base = getCurrentResultFolder();
+        writeAscii(base + "SylinderAscii_" + std::to_string(snapID) + ".dat");
+        const int rank = commRcp->getRank(), size = commRcp->getSize();
+        Sylinder::writeVTP(sylinderContainer, (int)sylinderContainer.size(), base, std::to_string(snapID), rank);
+        conCollectorPtr->pullFromDevice(ctx_, true, true);
+        conCollectorPtr->writeVTP(base, "", std::to_string(snapID), rank);
+        if (rank == 0) {
+            Sylinder::writePVTP(base, std::to_string(snapID), size);
+            conCollectorPtr->writePVTP(base, "", std::to_string(snapID), size);
+            FILE *f = std::fopen((base + "../../TimeStepInfo.txt").c_str(), "w"); // :509-521
+            if (f) {
+                std::fprintf(f, "%u\n%u\n%u\nSylinder_%d.pvtp\n", restartRngSeed, (unsigned)stepCount, (unsigned)snapID, snapID);
+                std::fclose(f);
+            }
+        }
+        snapID++;
+    }
 
     /// SylinderAscii_<snapID>.dat (SylinderSystem.cpp:489-507): header, one line per rod, then the links `L prev next`
     void writeAscii(const std::string &fileName) const {

@@ -264,6 +264,11 @@ class RefSystem:
         self.L.refsys_get_force_velocity(self.h, _dp(out["forceU"]), _dp(out["velU"]), _dp(out["forceB"]), _dp(out["velB"]))
         return out
 
+    def write_result(self):
+        """SylinderSystem::writeResult into <workdir>/result/result0-399/ (returns that folder)"""
+        self._q(self.L.refsys_write_result)
+        return os.path.join(self.workdir, "result", "result0-399")
+
     def sum_force_velocity(self):
         self._q(self.L.refsys_sum_force_velocity)
 

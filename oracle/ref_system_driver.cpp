@@ -198,6 +198,8 @@ void refsys_get_force_velocity(void *hp, double *fu, double *vu, double *fb, dou
 void refsys_sum_force_velocity(void *hp) { ((Handle *)hp)->sys.sumForceVelocity(); }
 void refsys_step_euler(void *hp) { ((Handle *)hp)->sys.stepEuler(); }
 void refsys_run_step(void *hp) { ((Handle *)hp)->sys.runStep(false); }
+// SylinderSystem::writeResult (SylinderSystem.cpp:553-560): SylinderAscii, Sylinder / ConBlock .vtp + .pvtp, TimeStepInfo
+void refsys_write_result(void *hp) { ((Handle *)hp)->sys.writeResult(); }
 void refsys_timing_summary(void *hp) { ((Handle *)hp)->sys.printTimingSummary(true); }
 
 // The reference's ConstraintCollector + ConstraintSolver + BCQPSolver on a GIVEN block list (queue 0 of a fresh pool),
