@@ -42,7 +42,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from scenarios import box_for_volume_fraction, random_rods, thermal_velocity  # noqa: E402
 
 L_ROD, R_ROD, COLBUF, MU, DT, RES, MAXITE = 0.25, 0.0125, 0.025, 1.0, 1e-5, 1e-5, 10000
-SLAB_AXIS = 0  # multi-GPU runs: slabs along x (2: along z, the slowest cell axis -- see profiles/README.md, late_halo)
+# multi-GPU runs: slabs along z, the slowest axis of the cell order -- the rods a neighbour mirrors and the rows that read
+# ghost velocities are then contiguous at the two ends of the sorted arrays, so only ~10 % of the force kernel's CTAs take
+# part in the halo release and the tail kernel keeps ~10 % of its tiles for after the halo wait (with x-slabs every tile
+# contains boundary rods; profiles/README.md).  ALENS_SLAB_AXIS=0/1/2 overrides.
+SLAB_AXIS = int(os.environ.get("ALENS_SLAB_AXIS", "2"))
 SEED = 1234
 
 

@@ -10,8 +10,13 @@
 #define ALENS_B200_SYLINDERSYSTEM_HPP_
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <fstream>
 #include <map>
+#include <random>
+#include <sstream>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -52,13 +57,145 @@ class SylinderSystem {
     SylinderSystem(const SylinderConfig &config, std::vector<Sylinder> rods, int device = 0) {
         initialize(config, std::move(rods), device);
     }
+    /// the reference's constructors (SylinderSystem.hpp:172-186, SylinderSystem.cpp:27-33)
+    SylinderSystem(const std::string &configFile, const std::string &posFile, int argc, char **argv) {
+        initialize(SylinderConfig(configFile), posFile, argc, argv);
+    }
+    SylinderSystem(const SylinderConfig &config, const std::string &posFile, int argc, char **argv) {
+        initialize(config, posFile, argc, argv);
+    }
     ~SylinderSystem() {
         if (ctx_) alens_destroy(ctx_);
     }
     SylinderSystem(const SylinderSystem &) = delete;
     SylinderSystem &operator=(const SylinderSystem &) = delete;
 
-    /// rods are handed over by the caller (the reference reads them from file or draws them, :35-104)
+    /// SylinderSystem::initialize(config, posFile, argc, argv) (:35-104): rods from `posFile` if it exists
+    /// (setInitialFromFile :317-375), else drawn from the configuration (setInitialFromConfig :218-261); links from the
+    /// `L prev next` lines of the same file (:377-405).  The CUDA device is the process's local rank
+    /// (ALENS_DEVICE, LOCAL_RANK or OMPI_COMM_WORLD_LOCAL_RANK; default 0).
+    void initialize(const SylinderConfig &config, const std::string &posFile, int /*argc*/, char ** /*argv*/) {
+        runConfig = config;
+        std::vector<Sylinder> rods;
+        bool haveFile = false;
+        {
+            std::ifstream probe(posFile.c_str());
+            haveFile = !posFile.empty() && probe.good(); // IOHelper::fileExist
+        }
+        if (haveFile) {
+            rods = readSylinderFile(posFile);
+            setLinkMapFromFile(posFile);
+        } else {
+            rods = drawInitialRods(config);
+        }
+        int device = 0;
+        for (const char *name : {"ALENS_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"})
+            if (const char *v = std::getenv(name)) {
+                device = std::atoi(v);
+                break;
+            }
+        initialize(config, std::move(rods), device);
+    }
+
+    /// Equatn::FromTwoVectors((0,0,1), d) (Eigen's setFromTwoVectors; d antiparallel to z: a half turn about x)
+    static void orientationFromDirection(const double d_[3], double q[4]) {
+        const double n = std::sqrt(d_[0] * d_[0] + d_[1] * d_[1] + d_[2] * d_[2]);
+        const double d[3] = {d_[0] / n, d_[1] / n, d_[2] / n};
+        const double c = d[2];
+        if (c < -1.0 + 1e-12) {
+            q[0] = 1; q[1] = 0; q[2] = 0; q[3] = 0;
+            return;
+        }
+        const double s = std::sqrt((1.0 + c) * 2.0), invs = 1.0 / s;
+        q[0] = -d[1] * invs; q[1] = d[0] * invs; q[2] = 0.0; q[3] = s * 0.5; // axis = z x d
+    }
+    /// one `C|S gid radius mx my mz px py pz [group]` line per rod (parseSylinder, :320-344)
+    static std::vector<Sylinder> readSylinderFile(const std::string &filename) {
+        std::ifstream f(filename);
+        if (!f) throw std::runtime_error("cannot open " + filename);
+        std::string line;
+        std::getline(f, line); // two header lines
+        std::getline(f, line);
+        std::vector<Sylinder> rods;
+        while (std::getline(f, line)) {
+            if (line.empty() || (line[0] != 'C' && line[0] != 'S')) continue;
+            std::stringstream ss(line);
+            char type;
+            int gid, group = -1;
+            double radius, m[3], p[3];
+            ss >> type >> gid >> radius >> m[0] >> m[1] >> m[2] >> p[0] >> p[1] >> p[2];
+            ss >> group;
+            Sylinder sy;
+            for (int k = 0; k < 3; k++) sy.pos[k] = (m[k] + p[k]) * 0.5;
+            sy.gid = gid;
+            sy.group = group;
+            sy.isImmovable = type == 'S';
+            sy.radius = sy.radiusCollision = radius;
+            sy.length = std::sqrt(std::pow(p[0] - m[0], 2) + std::pow(p[1] - m[1], 2) + std::pow(p[2] - m[2], 2));
+            sy.lengthCollision = sy.length;
+            const double dir[3] = {p[0] - m[0], p[1] - m[1], p[2] - m[2]}, ez[3] = {0, 0, 1};
+            orientationFromDirection(sy.length > 1e-7 ? dir : ez, sy.orientation);
+            sy.clear();
+            rods.push_back(sy);
+        }
+        return rods;
+    }
+    void setLinkMapFromFile(const std::string &filename) { // :377-405
+        std::ifstream f(filename);
+        std::string line;
+        std::getline(f, line);
+        std::getline(f, line);
+        linkMap.clear();
+        while (std::getline(f, line)) {
+            if (line.empty() || line[0] != 'L') continue;
+            std::stringstream ss(line);
+            char h;
+            int prev, next;
+            ss >> h >> prev >> next;
+            linkMap.emplace(prev, next);
+        }
+    }
+    /// setInitialFromConfig (:218-261): sylinderNumber rods, uniform in the init box, lengths sylinderLength (log-normal
+    /// with sylinderLengthSigma > 0, redrawn until shorter than half the smallest box edge), orientation by getOrient
+    /// (:190-216: a component of initOrient outside [-1, 1] is random).  The reference draws from per-thread TRNG streams;
+    /// here one std::mt19937_64 seeded with rngSeed (documented deviation: TRNG is not a dependency of this library).
+    static std::vector<Sylinder> drawInitialRods(const SylinderConfig &cfg) {
+        std::mt19937_64 gen(cfg.rngSeed);
+        std::uniform_real_distribution<double> u01(0.0, 1.0);
+        std::lognormal_distribution<double> ln(cfg.sylinderLength > 0 ? cfg.sylinderLength : 1.0,
+                                               cfg.sylinderLengthSigma > 0 ? cfg.sylinderLengthSigma : 1.0);
+        double edge[3], minEdge = 1e300;
+        for (int k = 0; k < 3; k++) {
+            edge[k] = cfg.initBoxHigh[k] - cfg.initBoxLow[k];
+            minEdge = std::min(minEdge, edge[k]);
+        }
+        const double pi = 3.14159265358979323846;
+        std::vector<Sylinder> rods((size_t)std::max(cfg.sylinderNumber, 0));
+        for (int i = 0; i < (int)rods.size(); i++) {
+            double length = cfg.sylinderLength;
+            if (cfg.sylinderLengthSigma > 0) do length = ln(gen); while (length >= minEdge * 0.5);
+            double pos[3], p[3], q[4];
+            for (int k = 0; k < 3; k++) pos[k] = u01(gen) * edge[k] + cfg.initBoxLow[k];
+            bool allRandom = true;
+            for (int k = 0; k < 3; k++) {
+                const double o = cfg.initOrient[k];
+                if (o < -1 || o > 1) p[k] = 2 * u01(gen) - 1;
+                else { p[k] = o; allRandom = false; }
+            }
+            if (allRandom) { // EquatnHelper::setUnitRandomEquatn: uniform on SO(3)
+                const double u1 = u01(gen), u2 = u01(gen), u3 = u01(gen);
+                const double a = std::sqrt(1 - u1), b = std::sqrt(u1);
+                q[3] = a * std::sin(2 * pi * u2); q[0] = a * std::cos(2 * pi * u2);
+                q[1] = b * std::sin(2 * pi * u3); q[2] = b * std::cos(2 * pi * u3);
+            } else {
+                orientationFromDirection(p, q);
+            }
+            rods[i] = Sylinder(i, cfg.sylinderDiameter / 2, cfg.sylinderDiameter / 2, length, length, pos, q);
+        }
+        return rods;
+    }
+
+    /// rods are handed over by the caller
     void initialize(const SylinderConfig &config, std::vector<Sylinder> rods, int device = 0) {
         runConfig = config;
         stepCount = 0;

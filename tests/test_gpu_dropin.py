@@ -99,3 +99,67 @@ def test_dropin_step_equals_capi_path(tmp_path, ctx, oracle):
     assert rep.residual < res / dt and ref["resFinal"] < res / dt
     assert np.abs(out["velU"] - ref["velU"]).max() < 50 * res / dt
     assert np.abs(out["velB"] - ref["velB"]).max() < 50 * res / dt
+
+
+def test_mirror_main_program_follows_the_reference_main_program(tmp_path):
+    """the C++ mirror driven like SimToolbox/Sylinder/SylinderSystem_main.cpp -- SylinderSystem(configFile, posFile, argc,
+    argv), then prepareStep / runStep, then writeResult -- from the SAME RunConfig.yaml and SylinderInitial.dat as the
+    reference's own SylinderSystem (oracle/_ref/libalens_refsys.so).  A dilute suspension of two-rod filaments whose links
+    are stretched (linkGap below the actual gap): bilateral constraints only, so both sides solve the same list."""
+    from oracle import pyrefsys as pr
+
+    if not pr.available():
+        pytest.skip("oracle/_ref/libalens_refsys.so missing")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
+    rng = np.random.default_rng(5)
+    nf, L, R = 60, 0.5, 0.0125
+    box = 12.0
+    centers = rng.uniform(1.5, box - 1.5, size=(nf, 3))
+    d = rng.normal(size=(nf, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    gap = 0.08  # > colBuf: the two rods of a filament do not collide
+    rods = dict(gid=np.arange(2 * nf, dtype=np.int32), pos=np.zeros((2 * nf, 3)), quat=np.zeros((2 * nf, 4)),
+                length=np.full(2 * nf, L), radius=np.full(2 * nf, R), immovable=np.zeros(2 * nf, dtype=np.uint8))
+    from scenarios import quat_from_z_to
+    rods["pos"][0::2] = centers - d * (0.5 * L + R + 0.5 * gap)
+    rods["pos"][1::2] = centers + d * (0.5 * L + R + 0.5 * gap)
+    rods["quat"][0::2] = rods["quat"][1::2] = quat_from_z_to(d)
+    rods["immovable"][0] = 1
+    links = [(2 * k, 2 * k + 1) for k in range(nf)]
+    cfg = dict(pr.DEFAULTS)
+    cfg.update(simBoxLow=[0.0] * 3, simBoxHigh=[box] * 3, simBoxPBC=[True, False, True], sylinderColBuf=0.025, viscosity=0.9,
+               dt=1e-4, conResTol=1e-9, conMaxIte=100000, linkKappa=150.0, linkGap=0.02, initPreSteps=0, timeSnap=1.0,
+               logLevel=5, timerLevel=5)
+    work = tmp_path / "mirror"
+    (work / "result" / "result0-399").mkdir(parents=True)
+    pr.write_yaml(str(work / "RunConfig.yaml"), cfg)
+    pr.write_dat(str(work / "SylinderInitial.dat"), rods, links)
+    exe = os.path.join(ROOT, "tests", "cpp", "test_system_main")
+    steps = 3
+    r = subprocess.run([exe, str(steps), str(work / "out.bin")], cwd=str(work), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = (work / "out.bin").read_bytes()
+    n = int(np.frombuffer(raw[:4], dtype=np.int32)[0])
+    got = np.frombuffer(raw[4:4 + 568 * n], dtype=pr.SYLINDER_DTYPE)
+    nl = int(np.frombuffer(raw[4 + 568 * n:8 + 568 * n], dtype=np.int32)[0])
+    glinks = np.frombuffer(raw[8 + 568 * n:], dtype=np.int32).reshape(nl, 2)
+    assert n == 2 * nf and sorted(map(tuple, glinks.tolist())) == links
+    # the reference, from the same two files
+    s = pr.RefSystem(yaml_file=str(work / "RunConfig.yaml"), pos_file=str(work / "SylinderInitial.dat"), nthreads=1)
+    init = s.sylinders().copy()
+    for _ in range(steps):
+        s.prepare_step()
+        s.run_step()
+        assert s.constraints()["bilateral"].all() and len(s.constraints()) == nf  # links only
+    s.prepare_step()
+    want = s.sylinders()
+    assert np.array_equal(got["gid"], want["gid"]) and np.array_equal(got["isImmovable"], want["isImmovable"])
+    assert np.array_equal(got["length"], want["length"]) and np.array_equal(got["radius"], want["radius"])
+    moved = np.abs(want["pos"] - init["pos"]).max()
+    assert moved > 1e-4
+    assert np.abs(got["pos"] - want["pos"]).max() < 1e-6 * moved
+    assert np.abs(got["orientation"] - want["orientation"]).max() < 1e-8
+    assert np.all(got["pos"][0] == init["pos"][0])  # the immovable rod
+    for name in ("Sylinder_r0_0.vtp", "Sylinder_0.pvtp", "ConBlock_r0_0.vtp", "ConBlock_0.pvtp", "SylinderAscii_0.dat"):
+        assert (work / "result" / "result0-399" / name).stat().st_size > 100, name
+    s.close()
