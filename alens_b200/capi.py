@@ -39,7 +39,7 @@ EXPORTS = [
     "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest",
     "alens_get_live_stats", "alens_bcqp_create_csr", "alens_bcqp_create_constraint", "alens_bcqp_set_lower_bound",
     "alens_bcqp_set_upper_bound", "alens_bcqp_get_bounds", "alens_bcqp_run", "alens_bcqp_history", "alens_bcqp_size",
-    "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps",
+    "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps", "alens_mix_pair_search",
 ]
 
 
@@ -263,6 +263,21 @@ class Context:
         self._call("alens_set_rods_aos", C.c_int(n), C.c_void_p(buf.ctypes.data), C.c_size_t(stride),
                    C.c_int(1 if wrap else 0))
         self.n_rods = n
+
+    def mix_pair_search(self, trg_pos, trg_rs, src_rs=None):
+        """targets x resident rods within max(rs_t, rs_j): returns (rowPtr[n+1], local rod indices)"""
+        tp = np.ascontiguousarray(trg_pos, dtype=np.float64).reshape(-1, 3)
+        tr = np.ascontiguousarray(trg_rs, dtype=np.float64)
+        sr = None if src_rs is None else np.ascontiguousarray(src_rs, dtype=np.float64)
+        n = len(tp)
+        row = np.zeros(n + 1, dtype=np.int64)
+        tot = C.c_longlong(0)
+        self._call("alens_mix_pair_search", C.c_longlong(n), _dp(tp), _dp(tr), _dp(sr), row.ctypes.data_as(C.POINTER(C.c_longlong)),
+                   None, C.c_longlong(0), C.byref(tot))
+        idx = np.zeros(max(tot.value, 1), dtype=np.int32)
+        self._call("alens_mix_pair_search", C.c_longlong(n), _dp(tp), _dp(tr), _dp(sr), row.ctypes.data_as(C.POINTER(C.c_longlong)),
+                   idx.ctypes.data_as(C.POINTER(C.c_int)), C.c_longlong(len(idx)), C.byref(tot))
+        return row, idx[:tot.value]
 
     # ---- the narrow phase by itself
     def dcp_query(self, P0, P1, Q0, Q1):

@@ -4,7 +4,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <unordered_set>
 #include <vector>
 
 using namespace alens;
@@ -38,6 +40,30 @@ static int guarded(alens_ctx *ctx, F &&f) {
         ctx->c.err = "host allocation failed";
         return ALENS_ERR_ARG;
     }
+}
+
+// BCQP handles outlive nothing: alens_destroy retires the handles still open on its context (their device memory goes
+// with the context); a retired handle answers ALENS_ERR_STATE and alens_bcqp_destroy only frees the shell.
+struct alens_bcqp {
+    alens_ctx *ctx;
+    alens::Bcqp *q;
+};
+static std::mutex g_bcqpMutex;
+static std::unordered_set<alens_bcqp *> g_bcqpOpen;
+static void retireBcqpOf(alens_ctx *ctx) {
+    std::lock_guard<std::mutex> lock(g_bcqpMutex);
+    for (alens_bcqp *p : g_bcqpOpen)
+        if (p->ctx == ctx && p->q) {
+            alens::bcqpDestroy(p->q);
+            p->q = nullptr;
+            p->ctx = nullptr;
+        }
+}
+static alens_bcqp *openBcqp(alens_ctx *ctx, alens::Bcqp *q) {
+    alens_bcqp *p = new alens_bcqp{ctx, q};
+    std::lock_guard<std::mutex> lock(g_bcqpMutex);
+    g_bcqpOpen.insert(p);
+    return p;
 }
 
 static float evMs(Context &c, int a, int b) {
@@ -83,6 +109,7 @@ void alens_destroy(alens_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->c.device);
     cudaDeviceSynchronize();
+    retireBcqpOf(ctx);
     commFree(ctx->c);
     g_allocAsync = false; // the stream goes away: remaining buffers are released with cudaFree
     ctxFree(ctx->c);
@@ -452,6 +479,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
         }
         else if (k == "rec_mode") c.optRecMode = value != 0;
         else if (k == "stamps") c.optStamps = value != 0;
+        else if (k == "u_window") c.optUWindow = value != 0;
         else if (k == "find_minb") c.optFindMinB = (value == 5 || value == 3) ? (int)value : 4;
         else if (k == "find_split") c.optFindSplit = value != 0;
         else if (k == "find_split_minb") c.optFindSplitMinB = value == 6 ? 6 : 8;
@@ -491,6 +519,15 @@ int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCand,
         if (nCells) *nCells = c.grid.ncell;
         if (nCand) *nCand = c.statCand;
         if (nHits) *nHits = c.nColl;
+    });
+}
+
+int alens_mix_pair_search(alens_ctx *ctx, long long nTargets, const double *targetPos, const double *targetRSearch,
+                          const double *sourceRSearch, long long *rowPtr, int *sourceIndex, long long capPairs,
+                          long long *nPairs) {
+    return guarded(ctx, [&](Context &c) {
+        const long long m = mixPairSearch(c, nTargets, targetPos, targetRSearch, sourceRSearch, rowPtr, sourceIndex, capPairs);
+        if (nPairs) *nPairs = m;
     });
 }
 
@@ -582,10 +619,6 @@ int alens_num_ghosts(alens_ctx *ctx, int *nGhost, int *nSentLeft, int *nSentRigh
 }
 
 /* ---- BCQPSolver for any caller ------------------------------------------------------------------ */
-struct alens_bcqp {
-    alens_ctx *ctx;
-    Bcqp *q;
-};
 int alens_bcqp_create_csr(alens_ctx *ctx, int n, const long long *rowPtr, const int *colInd, const double *values,
                           const double *b, alens_bcqp **out) {
     if (!out) return ALENS_ERR_ARG;
@@ -593,7 +626,7 @@ int alens_bcqp_create_csr(alens_ctx *ctx, int n, const long long *rowPtr, const 
     return guarded(ctx, [&](Context &c) {
         if (!rowPtr) throw ArgError{ALENS_ERR_ARG, "alens_bcqp_create_csr: null matrix"};
         Bcqp *q = bcqpCreate(c, n, rowPtr, colInd, values, b);
-        *out = new alens_bcqp{ctx, q};
+        *out = openBcqp(ctx, q);
     });
 }
 int alens_bcqp_create_constraint(alens_ctx *ctx, const double *b, alens_bcqp **out) {
@@ -601,36 +634,45 @@ int alens_bcqp_create_constraint(alens_ctx *ctx, const double *b, alens_bcqp **o
     *out = nullptr;
     return guarded(ctx, [&](Context &c) {
         Bcqp *q = bcqpCreate(c, 0, nullptr, nullptr, nullptr, b);
-        *out = new alens_bcqp{ctx, q};
+        *out = openBcqp(ctx, q);
     });
 }
 int alens_bcqp_set_lower_bound(alens_bcqp *p, const double *lb) {
     if (!p) return ALENS_ERR_ARG;
+    if (!p->q) return ALENS_ERR_STATE; // its context is gone
     return guarded(p->ctx, [&](Context &) { bcqpSetBounds(*p->q, lb, nullptr, 1); });
 }
 int alens_bcqp_set_upper_bound(alens_bcqp *p, const double *ub) {
     if (!p) return ALENS_ERR_ARG;
+    if (!p->q) return ALENS_ERR_STATE; // its context is gone
     return guarded(p->ctx, [&](Context &) { bcqpSetBounds(*p->q, nullptr, ub, 2); });
 }
 int alens_bcqp_get_bounds(alens_bcqp *p, double *lb, double *ub) {
     if (!p) return ALENS_ERR_ARG;
+    if (!p->q) return ALENS_ERR_STATE; // its context is gone
     return guarded(p->ctx, [&](Context &) { bcqpGetBounds(*p->q, lb, ub); });
 }
 int alens_bcqp_run(alens_bcqp *p, double *x, double tol, int maxIte, int solverChoice, alens_solve_report *report) {
     if (!p) return ALENS_ERR_ARG;
+    if (!p->q) return ALENS_ERR_STATE; // its context is gone
     return guarded(p->ctx, [&](Context &) { bcqpSolve(*p->q, x, tol, maxIte, solverChoice, report); });
 }
 int alens_bcqp_history(alens_bcqp *p, double *rows6, int capRows, int *nRows) {
     if (!p) return ALENS_ERR_ARG;
+    if (!p->q) return ALENS_ERR_STATE; // its context is gone
     return guarded(p->ctx, [&](Context &) {
         const int n = bcqpHistory(*p->q, rows6, capRows);
         if (nRows) *nRows = n;
     });
 }
-int alens_bcqp_size(alens_bcqp *p) { return p ? bcqpSize(*p->q) : 0; }
+int alens_bcqp_size(alens_bcqp *p) { return (p && p->q) ? bcqpSize(*p->q) : 0; }
 void alens_bcqp_destroy(alens_bcqp *p) {
     if (!p) return;
-    guarded(p->ctx, [&](Context &) { bcqpDestroy(p->q); });
+    {
+        std::lock_guard<std::mutex> lock(g_bcqpMutex);
+        g_bcqpOpen.erase(p);
+    }
+    if (p->q) guarded(p->ctx, [&](Context &) { bcqpDestroy(p->q); });
     delete p;
 }
 

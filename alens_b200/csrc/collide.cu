@@ -1096,11 +1096,146 @@ void collectPairs(Context &c) {
 }
 
 // Force the (lazily loaded) kernels of this file into the context now: loading a kernel at its first launch can
+// ------------------------------------------------------------------------------------------------
+// Two-species short-range search on the rods' cell list: MixPairInteraction<...>::computeForce
+// (SimToolbox/MPI/MixPairInteraction.hpp:148-311: an FDPS Symmetry tree over targets + sources) for TARGET points the
+// caller hands in (protein ends, ...) against the resident rods as SOURCES.  For target t every rod j (and every periodic
+// image of it) with |x_t - x_j| <= max(rs_t, rs_j) -- the distance the reference's search guarantees -- is reported, in
+// (target, cell walk) order; the caller's functor does the fine test, as in the reference.  Thread per target, count pass +
+// fill pass; the walk covers ceil(rsMax / cell edge) cells per direction.
+struct MixIn {
+    long long nTrg;
+    const double *tPos, *tRs; // [3 nTrg], [nTrg]
+    const double *sX, *sY, *sZ, *sRs; // sorted rods
+    const int *cellStart, *sUser;
+    CellGrid g;
+    Box box;
+    int reach[3];
+};
+template <bool FILL>
+__global__ void k_mix_search(MixIn in, long long *__restrict__ rowPtr, int *__restrict__ out, long long cap) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= in.nTrg) return;
+    double x[3] = {in.tPos[3 * t], in.tPos[3 * t + 1], in.tPos[3 * t + 2]};
+    int c[3];
+    for (int k = 0; k < 3; k++) {
+        if (in.box.pbc[k] && in.box.len[k] > 0) { // applyBoxBC on the mixed system (MixPairInteraction.hpp:268)
+            while (x[k] < in.box.lo[k]) x[k] += in.box.len[k];
+            while (x[k] >= in.box.hi[k]) x[k] -= in.box.len[k];
+        }
+        int ci = (int)floor((x[k] - in.g.lo[k]) * in.g.inv[k]);
+        c[k] = ci < 0 ? 0 : (ci >= in.g.n[k] ? in.g.n[k] - 1 : ci);
+    }
+    const double rt = in.tRs[t];
+    long long pos = FILL ? rowPtr[t] : 0, cnt = 0;
+    for (int dz = -in.reach[2]; dz <= in.reach[2]; dz++)
+        for (int dy = -in.reach[1]; dy <= in.reach[1]; dy++)
+            for (int dx = -in.reach[0]; dx <= in.reach[0]; dx++) {
+                const int d[3] = {dx, dy, dz};
+                int cc[3];
+                double shift[3];
+                bool ok = true;
+                for (int k = 0; k < 3; k++) {
+                    int ck = c[k] + d[k];
+                    int img = 0;
+                    if (ck < 0 || ck >= in.g.n[k]) {
+                        if (!in.g.per[k]) { ok = false; break; }
+                        img = (int)floor((double)ck / in.g.n[k]);
+                        ck -= img * in.g.n[k];
+                    }
+                    cc[k] = ck;
+                    shift[k] = img * in.box.len[k];
+                }
+                if (!ok) continue;
+                const int cell = (cc[2] * in.g.n[1] + cc[1]) * in.g.n[0] + cc[0];
+                for (int s = in.cellStart[cell]; s < in.cellStart[cell + 1]; s++) {
+                    const double ex = in.sX[s] + shift[0] - x[0], ey = in.sY[s] + shift[1] - x[1], ez = in.sZ[s] + shift[2] - x[2];
+                    const double rr = fmax(rt, in.sRs[s]);
+                    if (ex * ex + ey * ey + ez * ez <= rr * rr) {
+                        if (FILL && pos + cnt < cap) out[pos + cnt] = in.sUser[s];
+                        cnt++;
+                    }
+                }
+            }
+    if (!FILL) rowPtr[t] = cnt;
+}
+__global__ void k_mix_src_radius(int n, const int *__restrict__ sUser, const double *__restrict__ userRs, const double *__restrict__ sLen,
+                                 const double *__restrict__ sRad, const double *__restrict__ sLc, const double *__restrict__ sRc,
+                                 double colBuf, double *__restrict__ sRs) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    // SylinderNearEP::getRSearch (SylinderNear.hpp:108-113) unless the caller brings its own radii
+    sRs[s] = userRs ? userRs[sUser[s]] : 0.5 * fmax(sLen[s] + 2 * sRad[s], sLc[s] + 2 * sRc[s]) + colBuf;
+}
+long long mixPairSearch(Context &c, long long nTrg, const double *trgPos, const double *trgRs, const double *srcRs,
+                        long long *rowPtr, int *srcIdx, long long cap) {
+    if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_mix_pair_search: call alens_set_rods first"};
+    if (c.comm.active) throw ArgError{ALENS_ERR_UNSUPPORTED, "alens_mix_pair_search: single-rank entry"};
+    if (nTrg < 0 || (nTrg > 0 && (!trgPos || !trgRs || !rowPtr))) throw ArgError{ALENS_ERR_ARG, "alens_mix_pair_search: null input"};
+    cudaStream_t st = c.stream;
+    const int n = c.nRods;
+    DevBuf<double> dPos, dRs, dSrcUser, dSrcRs;
+    DevBuf<long long> dRow;
+    DevBuf<int> dOut;
+    dPos.reserve(3 * (size_t)nTrg + 3); dRs.reserve((size_t)nTrg + 1); dRow.reserve((size_t)nTrg + 2); dSrcRs.reserve((size_t)n + 1);
+    double rsMax = 0;
+    for (long long t = 0; t < nTrg; t++) rsMax = std::max(rsMax, trgRs[t]);
+    if (srcRs) {
+        dSrcUser.reserve((size_t)n + 1);
+        ALENS_CUDA(cudaMemcpyAsync(dSrcUser.p, srcRs, 8 * (size_t)c.nLocal, cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < c.nLocal; i++) rsMax = std::max(rsMax, srcRs[i]);
+    } else {
+        rsMax = std::max(rsMax, c.maxRLocal + c.colBuf); // getRSearch <= lengthCollision/2 + radiusCollision + colBuf for ratios >= 1
+        rsMax = std::max(rsMax, c.maxRLocal / std::min(std::min(c.lRatio, c.dRatio), 1.0) + c.colBuf);
+    }
+    if (nTrg > 0) {
+        ALENS_CUDA(cudaMemcpyAsync(dPos.p, trgPos, 24 * (size_t)nTrg, cudaMemcpyHostToDevice, st));
+        ALENS_CUDA(cudaMemcpyAsync(dRs.p, trgRs, 8 * (size_t)nTrg, cudaMemcpyHostToDevice, st));
+    }
+    if (n > 0)
+        k_mix_src_radius<<<gridFor(n, 256), 256, 0, st>>>(n, c.sUser.p, srcRs ? dSrcUser.p : nullptr, c.sLen.p, c.sRad.p, c.sLc.p,
+                                                          c.sRc.p, c.colBuf, dSrcRs.p);
+    MixIn in{nTrg, dPos.p, dRs.p, c.sX.p, c.sY.p, c.sZ.p, dSrcRs.p, c.cellStart.p, c.sUser.p, c.grid, c.box, {0, 0, 0}};
+    for (int k = 0; k < 3; k++) {
+        const double edge = c.grid.inv[k] > 0 ? 1.0 / c.grid.inv[k] : 1e300;
+        in.reach[k] = (int)std::ceil(rsMax / edge);
+        if (in.reach[k] > 64) throw ArgError{ALENS_ERR_UNSUPPORTED, "alens_mix_pair_search: search radius spans more than 64 cells"};
+    }
+    long long total = 0;
+    if (nTrg > 0) {
+        k_mix_search<false><<<gridFor(nTrg, 128), 128, 0, st>>>(in, dRow.p, nullptr, 0);
+        // the row pointer is a host output: counts come back, the exclusive sum runs here, the offsets go down again
+        ALENS_CUDA(cudaMemcpyAsync(rowPtr, dRow.p, 8 * (size_t)nTrg, cudaMemcpyDeviceToHost, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        for (long long t = 0; t < nTrg; t++) {
+            const long long cnt = rowPtr[t];
+            rowPtr[t] = total;
+            total += cnt;
+        }
+        rowPtr[nTrg] = total;
+        c.launches += 2;
+        if (total > 0 && srcIdx && cap >= total) {
+            dOut.reserve((size_t)total);
+            ALENS_CUDA(cudaMemcpyAsync(dRow.p, rowPtr, 8 * (size_t)nTrg, cudaMemcpyHostToDevice, st));
+            k_mix_search<true><<<gridFor(nTrg, 128), 128, 0, st>>>(in, dRow.p, dOut.p, total);
+            c.launches++;
+            ALENS_CUDA(cudaMemcpyAsync(srcIdx, dOut.p, 4 * (size_t)total, cudaMemcpyDeviceToHost, st));
+            ALENS_CUDA(cudaStreamSynchronize(st));
+        }
+    } else if (rowPtr) {
+        rowPtr[0] = 0;
+    }
+    ALENS_CUDA(cudaGetLastError());
+    return total;
+}
+
 // synchronise the context, which deadlocks against a peer rank's waiting kernel when two ranks share one GPU.
 void preloadCollideKernels() {
     cudaFuncAttributes a;
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_pack));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_wrap));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_mix_search<false>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_mix_search<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_global_index));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_local_image));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_scan_int));

@@ -265,6 +265,7 @@ struct Context {
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 3;                 // 3 = k_force_vel_rec (64-byte slot records + slot-ordered live bitmap kept by k_bb_tail), 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
+    int optUWindow = 0; // experiment: see setupConstraints
     int optStamps = 0, stampCap = 0, stampIters = 0; // per-iteration nanosecond stamps of the BBPGD kernels (instrumentation)
     DevBuf<unsigned long long> dStamps;
     unsigned long long *stampNow = nullptr;
@@ -383,6 +384,8 @@ Context *bcqpContext(Bcqp &q);
 void bcqpDestroy(Bcqp *q);
 void liveStats(Context &c, long long *slots, long long *rods);
 void constraintDigest(Context &c, unsigned long long u64[3], double f64[3]);
+long long mixPairSearch(Context &c, long long nTrg, const double *trgPos, const double *trgRs, const double *srcRs,
+                        long long *rowPtr, int *srcIdx, long long cap);
 void preloadCollideKernels();
 void preloadSolverKernels();
 void preloadBlockKernels();

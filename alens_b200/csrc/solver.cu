@@ -1481,6 +1481,7 @@ struct TailRow {
     unsigned char bi;
     int2 sl;     // slot records of the row's two sides (force_kernel = 3)
     unsigned mw; // the row's word of the previous iteration's mask
+    unsigned char own; // multi-rank: this rank counts the row in the dot products (streamed with the row, not at use)
 };
 __device__ __forceinline__ unsigned char ldStreamU8(const unsigned char *p) {
     unsigned v;
@@ -1498,6 +1499,7 @@ __device__ __forceinline__ void loadTailRow(const BbTail &p, size_t k, TailRow &
     r.b = ldStream(p.b + k);
     r.invK = HASK ? ldStream(p.invKdt + k) : 0.0;
     r.bi = ldStreamU8(p.bi + k);
+    r.own = p.own ? ldStreamU8(p.own + k) : (unsigned char)1;
     if (p.slotLive) {
         if (p.rec) { // rec_mode 0: the slots are needed for every row that may be non-zero: streamed with the row
             const int2 *sp = p.cSlot + k;
@@ -1548,7 +1550,7 @@ __device__ __forceinline__ bool tailRowMath(const BbTail &p, const TailRow &cur,
     int err = 0;
     const double q = projGrad(x, gk, cur.bi ? 1.0 : 0.0, err);
     mx = fmax(mx, err ? INFINITY : fabs(q));
-    if (p.ite > 0 && (!p.own || p.own[k])) { // a row mirrored on two ranks is counted by the owner of rod I
+    if (p.ite > 0 && cur.own) { // a row mirrored on two ranks is counted by the owner of rod I
         const double dx = 1.0 * x + (-1.0) * xp;
         const double dg = 1.0 * gk + (-1.0) * gp;
         s0 += dx * dx;
@@ -2167,6 +2169,16 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     const size_t vcap = (size_t)nc + 32; // (+ padding: bulk copies read whole 16-row groups)
     c.vX0.reserve(vcap); c.vX1.reserve(vcap); c.vG0.reserve(vcap); c.vG1.reserve(vcap);
     c.vB.reserve(vcap); c.vLbFlag.reserve(vcap); c.vTmp5.reserve(vcap); // vTmp5 = invKdt
+    if (c.optUWindow && !c.comm.active && !c.rU.external) { // experiment: U in cudaMalloc'ed, IPC-exported memory (as in multi-GPU runs)
+        double *p = nullptr;
+        ALENS_CUDA(cudaMalloc((void **)&p, 8 * (6 * (size_t)n + 64) * 2));
+        cudaIpcMemHandle_t h;
+        ALENS_CUDA(cudaIpcGetMemHandle(&h, p));
+        c.rU.release();
+        c.rU.p = p;
+        c.rU.cap = (6 * (size_t)n + 64) * 2;
+        c.rU.external = true;
+    }
     c.rU.reserve(6 * (size_t)n + 6); c.rF.reserve(6 * (size_t)n + 6);
     c.rUb.reserve(6 * (size_t)n + 6); c.rFb.reserve(6 * (size_t)n + 6);
     c.outFU.reserve(6 * (size_t)n + 6); c.outVU.reserve(6 * (size_t)n + 6);

@@ -165,6 +165,18 @@ int alens_num_constraints(alens_ctx *ctx, long long *n);
 int alens_get_constraints(alens_ctx *ctx, alens_constraint_block *out, long long cap, int withStress,
                           int writeBack);
 
+/* ---- two-species neighbour search ------------------------------------------------------------- */
+/* MixPairInteraction<FPT, FPS, EPT, EPS, Force>::computeForce (SimToolbox/MPI/MixPairInteraction.hpp:148-311; the protein ->
+ * rod search of SRC/TubuleSystem.cpp) on the rods' cell list: for every TARGET point t (host arrays targetPos[3n],
+ * targetRSearch[n]) the resident rods j, and their periodic images, with |x_t - x_j| <= max(rs_t, rs_j) -- the distance
+ * FDPS' Symmetry search guarantees; the caller's functor makes the fine decision as in the reference.  sourceRSearch:
+ * per local rod, or NULL = SylinderNearEP::getRSearch (SylinderNear.hpp:108-113).  Result in CSR form: rowPtr[nTargets + 1]
+ * and sourceIndex[rowPtr[nTargets]] (local rod indices).  If capPairs is too small only rowPtr and *nPairs are filled: call
+ * again with a larger buffer.  Call after alens_set_rods / alens_prepare_step. */
+int alens_mix_pair_search(alens_ctx *ctx, long long nTargets, const double *targetPos, const double *targetRSearch,
+                          const double *sourceRSearch, long long *rowPtr, int *sourceIndex, long long capPairs,
+                          long long *nPairs);
+
 /* ---- the narrow phase by itself ---------------------------------------------------------------- */
 /* DCPQuery<3,double,Evec3>::operator() (SimToolbox/Collision/DCPQuery.hpp:199-308), n independent segment pairs
  * [P0,P1] x [Q0,Q1] (3n host doubles each): minimal distance and the closest points (any output may be NULL).

@@ -122,8 +122,9 @@ class SylinderSystem {
             std::stringstream ss(line);
             char type;
             int gid, group = -1;
-            double radius, m[3], p[3];
+            double radius = 0, m[3] = {0, 0, 0}, p[3] = {0, 0, 0};
             ss >> type >> gid >> radius >> m[0] >> m[1] >> m[2] >> p[0] >> p[1] >> p[2];
+            if (ss.fail()) throw std::runtime_error("readSylinderFile: malformed line: " + line);
             ss >> group;
             Sylinder sy;
             for (int k = 0; k < 3; k++) sy.pos[k] = (m[k] + p[k]) * 0.5;

@@ -121,7 +121,7 @@ def write_dat(path, rods, links=()):
             m = rods["pos"][i] - 0.5 * rods["length"][i] * d
             p = rods["pos"][i] + 0.5 * rods["length"][i] * d
             t = "S" if rods["immovable"][i] else "C"
-            f.write(f"{t} {int(rods['gid'][i])} {rods['radius'][i]!r} " + " ".join(repr(float(x)) for x in (*m, *p)) + " -1\n")
+            f.write(f"{t} {int(rods['gid'][i])} {float(rods['radius'][i])!r} " + " ".join(repr(float(x)) for x in (*m, *p)) + " -1\n")
         for a, b in links:
             f.write(f"L {int(a)} {int(b)}\n")
 
@@ -404,3 +404,31 @@ def boundary_project(kind, center, axis, radius, inside, query):
     lib().refsys_boundary_project({"sphere": 0, "wall": 1, "tube": 2}[kind], _dp(c), _dp(a), C.c_double(radius),
                                   int(bool(inside)), _dp(q), _dp(proj), _dp(delta))
     return proj, delta
+
+
+def mix_search(trg_pos, trg_rs, src_pos, src_rs, box_low, box_high, pbc, nthreads=1):
+    """the reference's MixPairInteraction (SimToolbox/MPI/MixPairInteraction.hpp) driven like MPI/MixPairInteraction_test.cpp:
+    every (target, source image) FDPS gives the functor with distance <= max(rsTrg, rsSrc).  Returns (pairs[k, 2], dist[k])
+    sorted by (target, source, dist)."""
+    L = lib()
+    L.refmix_search.restype = C.c_longlong
+    tp = np.ascontiguousarray(trg_pos, dtype=np.float64)
+    sp = np.ascontiguousarray(src_pos, dtype=np.float64)
+    tr = np.ascontiguousarray(trg_rs, dtype=np.float64)
+    sr = np.ascontiguousarray(src_rs, dtype=np.float64)
+    lo = np.ascontiguousarray(box_low, dtype=np.float64)
+    hi = np.ascontiguousarray(box_high, dtype=np.float64)
+    pb = np.ascontiguousarray(pbc, dtype=np.int32)
+    cap = 64 * (len(tp) + len(sp)) + 1024
+    while True:
+        pairs = np.zeros((cap, 2), dtype=np.int64)
+        dist = np.zeros(cap)
+        with _Quiet():
+            n = L.refmix_search(len(tp), _dp(tp), _dp(tr), len(sp), _dp(sp), _dp(sr), _dp(lo), _dp(hi), _ip(pb), C.c_longlong(cap),
+                                C.c_void_p(pairs.ctypes.data), _dp(dist), int(nthreads))
+        if n <= cap:
+            break
+        cap = int(n)
+    pairs, dist = pairs[:n], dist[:n]
+    order = np.lexsort((dist, pairs[:, 1], pairs[:, 0]))
+    return pairs[order], dist[order]

@@ -23,6 +23,7 @@
 
 #include "Constraint/BCQPSolver.hpp"
 #include "Constraint/ConstraintSolver.hpp"
+#include "MPI/MixPairInteraction.hpp"
 #include "Sylinder/SylinderSystem.hpp"
 #include "Util/Logger.hpp"
 
@@ -66,6 +67,51 @@ void copyTV(const Teuchos::RCP<const TV> &v, double *out, size_t n) {
     auto p = v->getLocalView<Kokkos::HostSpace>();
     for (size_t i = 0; i < n; i++) out[i] = p(i, 0);
 }
+} // namespace
+
+
+// ---- two-species search (SimToolbox/MPI/MixPairInteraction.hpp), driven like MPI/MixPairInteraction_test.cpp
+namespace {
+struct MixPoint { // the particle type of that test (Point / Query)
+    int gid;
+    double RSearch;
+    double pos[3];
+    inline double getRSearch() const { return RSearch; }
+    inline const PS::F64vec3 getPos() const { return PS::F64vec3(pos[0], pos[1], pos[2]); }
+    inline void setPos(const PS::F64vec3 &newPos) { pos[0] = newPos.x; pos[1] = newPos.y; pos[2] = newPos.z; }
+    inline void copyFromFP(const MixPoint &other) { *this = other; }
+};
+struct MixCount {
+    int nbCount = 0;
+    void clear() { nbCount = 0; }
+};
+struct MixRecord { // every (target, source image) FDPS hands to the functor whose distance passes `r2 <= max(rs)^2`
+    std::vector<long long> *out; // trg gid, src gid
+    std::vector<double> *dist;
+    void operator()(const MixEPI<MixPoint> *const trgPtr, const PS::S32 nTrg, const MixEPJ<MixPoint> *const srcPtr,
+                    const PS::S32 nSrc, MixCount *const forcePtr) {
+        for (int t = 0; t < nTrg; t++) {
+            forcePtr[t].clear();
+            if (!trgPtr[t].trgFlag) continue;
+            const auto tp = trgPtr[t].getPos();
+            const double rt = trgPtr[t].getRSearch();
+            for (int s = 0; s < nSrc; s++) {
+                if (!srcPtr[s].srcFlag) continue;
+                const double r2 = tp.getDistanceSQ(srcPtr[s].getPos());
+                const double rr = std::max(rt, srcPtr[s].getRSearch());
+                if (r2 <= rr * rr) {
+                    forcePtr[t].nbCount++;
+#pragma omp critical
+                    {
+                        out->push_back(trgPtr[t].epTrg.gid);
+                        out->push_back(srcPtr[s].epSrc.gid);
+                        dist->push_back(std::sqrt(r2));
+                    }
+                }
+            }
+        }
+    }
+};
 } // namespace
 
 extern "C" {
@@ -428,5 +474,55 @@ void refsys_boundary_project(int type, const double *center, const double *axis,
     if (type == 0) SphereShell(c, radius, inside != 0).project(query, project, delta);
     else if (type == 1) Wall(c, a).project(query, project, delta);
     else Tube(c, a, radius, inside != 0).project(query, project, delta);
+}
+
+// MixPairInteraction<Trg, Src, Trg, Src, Count>: all (target, source image) pairs within max(rsTrg, rsSrc).
+// pairs[2 k] = target index, pairs[2 k + 1] = source index, dist[k]; returns the number found (may exceed cap)
+long long refmix_search(int nTrg, const double *trgPos, const double *trgRs, int nSrc, const double *srcPos,
+                        const double *srcRs, const double *boxLow, const double *boxHigh, const int *pbc, long long cap,
+                        long long *pairs, double *dist, int nthreads) {
+    initOnce(std::max(1, nthreads));
+    PS::ParticleSystem<MixPoint> sysTrg, sysSrc;
+    sysTrg.initialize();
+    sysSrc.initialize();
+    sysTrg.setNumberOfParticleLocal(nTrg);
+    sysSrc.setNumberOfParticleLocal(nSrc);
+    for (int i = 0; i < nTrg; i++) {
+        sysTrg[i].gid = i;
+        sysTrg[i].RSearch = trgRs[i];
+        for (int k = 0; k < 3; k++) sysTrg[i].pos[k] = trgPos[3 * i + k];
+    }
+    for (int i = 0; i < nSrc; i++) {
+        sysSrc[i].gid = i;
+        sysSrc[i].RSearch = srcRs[i];
+        for (int k = 0; k < 3; k++) sysSrc[i].pos[k] = srcPos[3 * i + k];
+    }
+    PS::DomainInfo dinfo;
+    dinfo.initialize();
+    const int code = (pbc[0] ? 1 : 0) + (pbc[1] ? 2 : 0) + (pbc[2] ? 4 : 0);
+    const PS::BOUNDARY_CONDITION bc[8] = {PS::BOUNDARY_CONDITION_OPEN,        PS::BOUNDARY_CONDITION_PERIODIC_X,
+                                          PS::BOUNDARY_CONDITION_PERIODIC_Y,  PS::BOUNDARY_CONDITION_PERIODIC_XY,
+                                          PS::BOUNDARY_CONDITION_PERIODIC_Z,  PS::BOUNDARY_CONDITION_PERIODIC_XZ,
+                                          PS::BOUNDARY_CONDITION_PERIODIC_YZ, PS::BOUNDARY_CONDITION_PERIODIC_XYZ};
+    dinfo.setBoundaryCondition(bc[code]);
+    dinfo.setPosRootDomain(PS::F64vec3(boxLow[0], boxLow[1], boxLow[2]), PS::F64vec3(boxHigh[0], boxHigh[1], boxHigh[2]));
+    dinfo.decomposeDomainAll(sysSrc);
+    sysSrc.exchangeParticle(dinfo);
+    sysTrg.exchangeParticle(dinfo);
+    MixPairInteraction<MixPoint, MixPoint, MixPoint, MixPoint, MixCount> mix;
+    mix.initialize();
+    mix.updateSystem(sysTrg, sysSrc, dinfo);
+    mix.updateTree();
+    std::vector<long long> out;
+    std::vector<double> d;
+    MixRecord ftr{&out, &d};
+    mix.computeForce<MixRecord>(ftr, dinfo);
+    const long long n = (long long)d.size();
+    for (long long k = 0; k < std::min(n, cap); k++) {
+        pairs[2 * k] = out[2 * k];
+        pairs[2 * k + 1] = out[2 * k + 1];
+        dist[k] = d[k];
+    }
+    return n;
 }
 }

@@ -96,16 +96,20 @@ def test_constraint_operator_with_caller_bounds(ctx, oracle):
     A = (DTm @ M @ DTm.T).tocsr()
     A.sort_indices()
     qvec = d0 / DT + DTm @ vnc
+    # bounds on the scale of the multipliers themselves (a free solve gives it): a cap that is active and a slightly negative floor
+    big = np.finfo(float).max / 10
+    free, _, _ = pr.bcqp_solve_csr(A.indptr, A.indices, A.data, qvec, np.zeros(nc), np.full(nc, big), g0, 1e-30, 60, 0)
     rng = np.random.default_rng(0)
-    lb = -0.05 * rng.uniform(size=nc) * np.abs(qvec).max() * DT  # slightly negative multipliers allowed
-    ub = np.full(nc, 0.3 * np.abs(g0).max() + 1e-3)              # ... and capped
+    lb = -0.02 * rng.uniform(size=nc) * free.max()
+    ub = np.full(nc, 0.3 * free.max())
+    x0 = np.clip(g0, lb, ub)
     q = alens_b200.Bcqp(ctx)  # the constraint operator of the setup, b = its q
     q.set_bounds(lb, ub)
     for choice, ite in ((0, 25), (1, 12)):
-        x, rep, hist = q.solve(g0, 1e-30, ite, choice)
-        xr, hr, _ = pr.bcqp_solve_csr(A.indptr, A.indices, A.data, qvec, lb, ub, g0, 1e-30, ite, choice)
-        assert rep.iterations == ite
-        assert np.all(x >= lb) and np.all(x <= ub) and (x == ub).sum() > 0  # the caller's bounds are honoured
+        x, rep, hist = q.solve(x0, 1e-30, ite, choice)
+        xr, hr, _ = pr.bcqp_solve_csr(A.indptr, A.indices, A.data, qvec, lb, ub, x0, 1e-30, ite, choice)
+        assert rep.iterations == len(hr) - 1 == ite
+        assert np.all(x >= lb) and np.all(x <= ub) and (x == ub).sum() > 10 and (x < 0).sum() > 100  # the caller's bounds
         assert relerr(x, xr) < 1e-7
         np.testing.assert_allclose(hist[:, 4], hr[:, 4], rtol=1e-6)
     # a projection error is reported, not ignored (BCQPSolver.cpp:484-494)
@@ -141,3 +145,22 @@ def test_cpp_bcqpsolver_mirror_selftest(tmp_path):
         if rcr == 0:
             assert np.abs(x - xr).max() < 1e-5
         assert np.all(x >= lb) and np.all(x <= ub)
+
+
+def test_handle_outliving_its_context_is_retired_not_dangling(alens_lib):
+    """alens_destroy retires the BCQP handles still open on the context: later calls answer ALENS_ERR_STATE (-3,
+    no crash), alens_bcqp_destroy frees the shell"""
+    import scipy.sparse as sp
+
+    c = alens_b200.Context(device=0)
+    A = sp.identity(8, format="csr")
+    q = alens_b200.Bcqp(c, b=-np.ones(8), csr=(A.indptr, A.indices, A.data))
+    x, rep, _ = q.solve(np.zeros(8), 1e-12, 50, 0)
+    assert np.allclose(x, 1.0)
+    c.close()
+    rep = alens_b200.capi.SolveReport()
+    import ctypes as C
+    xx = np.zeros(8)
+    rc = q.dll.alens_bcqp_run(q.h, xx.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(1e-6), C.c_int(5), C.c_int(0), C.byref(rep))
+    assert rc == -3
+    q.close()

@@ -301,3 +301,22 @@ def test_example_configs_against_committed_reference_outputs(oracle):
             r = s.solve_blocks(blocks, vnc, dt, res, max_ite, choice)
             _assert_same_solve(r, o)
             s.close()
+
+
+@pytest.mark.parametrize("pbc", [(1, 1, 1), (0, 0, 0), (1, 0, 1)])
+def test_reference_two_species_search_is_the_all_images_ball_query(pbc):
+    """SimToolbox/MPI/MixPairInteraction.hpp driven like MPI/MixPairInteraction_test.cpp: what FDPS hands the functor,
+    filtered by distance <= max(rsTrg, rsSrc), is exactly the brute-force set over periodic images -- the statement
+    tests/test_gpu_mix.py holds the device search to"""
+    from mixsearch import brute_mix_pairs
+
+    rng = np.random.default_rng(1)
+    lo, hi = [0.0, 0.0, 0.0], [10.0, 8.0, 6.0]
+    nt, ns = 300, 500
+    trg = rng.uniform(-1, 11, size=(nt, 3)) if all(pbc) else rng.uniform(0.01, 0.99, size=(nt, 3)) * np.array(hi)
+    src = rng.uniform(0, 1, size=(ns, 3)) * np.array(hi)
+    trs, srs = rng.uniform(0.1, 1.5, size=nt), rng.uniform(0.1, 0.9, size=ns)
+    pairs, dist = pr.mix_search(trg, trs, src, srs, lo, hi, pbc)
+    want = brute_mix_pairs(trg, trs, src, srs, lo, hi, pbc)
+    assert len(want) > 500 and np.array_equal(pairs, want)
+    assert np.all(dist <= np.maximum(trs[pairs[:, 0]], srs[pairs[:, 1]]))
