@@ -39,7 +39,7 @@ EXPORTS = [
     "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest",
     "alens_get_live_stats", "alens_bcqp_create_csr", "alens_bcqp_create_constraint", "alens_bcqp_set_lower_bound",
     "alens_bcqp_set_upper_bound", "alens_bcqp_get_bounds", "alens_bcqp_run", "alens_bcqp_history", "alens_bcqp_size",
-    "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps", "alens_mix_pair_search",
+    "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps", "alens_mix_pair_search", "alens_migrate_rods", "alens_get_rod_identity", "alens_set_rod_tags", "alens_get_rod_tags",
 ]
 
 
@@ -263,6 +263,35 @@ class Context:
         self._call("alens_set_rods_aos", C.c_int(n), C.c_void_p(buf.ctypes.data), C.c_size_t(stride),
                    C.c_int(1 if wrap else 0))
         self.n_rods = n
+
+    def migrate_rods(self):
+        """collective: rods that left the slab move to the neighbour rank; returns (sent, received)"""
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._call("alens_migrate_rods", C.byref(a), C.byref(b))
+        n, base = C.c_int(0), C.c_int(0)
+        self._call("alens_get_rod_identity", C.byref(n), C.byref(base), None, None, None, None)
+        self.n_rods = n.value
+        return a.value, b.value
+
+    def set_rod_tags(self, tags):
+        t = None if tags is None else np.ascontiguousarray(tags, dtype=np.int64)
+        self._call("alens_set_rod_tags", None if t is None else t.ctypes.data_as(C.POINTER(C.c_longlong)))
+
+    def get_rod_tags(self):
+        t = np.zeros(max(self.n_rods, 1), dtype=np.int64)
+        self._call("alens_get_rod_tags", t.ctypes.data_as(C.POINTER(C.c_longlong)))
+        return t[:self.n_rods]
+
+    def get_rod_identity(self):
+        """(globalIndexBase, gid, length, radius, immovable) of the resident owned rods"""
+        n, base = C.c_int(0), C.c_int(0)
+        self._call("alens_get_rod_identity", C.byref(n), C.byref(base), None, None, None, None)
+        self.n_rods = n.value
+        m = max(n.value, 1)
+        gid, le, ra, im = np.zeros(m, dtype=np.int32), np.zeros(m), np.zeros(m), np.zeros(m, dtype=np.uint8)
+        self._call("alens_get_rod_identity", C.byref(n), C.byref(base), gid.ctypes.data_as(C.POINTER(C.c_int)), _dp(le), _dp(ra),
+                   im.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return base.value, gid[:n.value], le[:n.value], ra[:n.value], im[:n.value]
 
     def mix_pair_search(self, trg_pos, trg_rs, src_rs=None):
         """targets x resident rods within max(rs_t, rs_j): returns (rowPtr[n+1], local rod indices)"""

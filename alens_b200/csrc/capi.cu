@@ -165,6 +165,7 @@ int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, con
         cudaStream_t st = c.stream;
         ALENS_CUDA(cudaEventRecord(c.ev[0], st));
         if (n != c.nLocal) c.haveVelNC = false;
+        c.haveTags = false;
         c.nLocal = n;
         c.nRods = n;
         const size_t N = (size_t)n;
@@ -210,7 +211,38 @@ int alens_set_rods_aos(alens_ctx *ctx, int n, const void *sy, size_t stride, int
         memcpy(&pos[3 * (size_t)i], p + 80, 24);
         memcpy(&q[4 * (size_t)i], p + 104, 32);
     }
-    return alens_set_rods(ctx, n, gid.data(), pos.data(), q.data(), len.data(), rad.data(), imm.data(), wrap);
+    // Sylinder::group (offset 12) rides along as the rod's tag: it stays with the rod when the rod migrates
+    std::vector<long long> tag(n);
+    for (int i = 0; i < n; i++) {
+        int g;
+        memcpy(&g, base + (size_t)i * stride + 12, 4);
+        tag[i] = g;
+    }
+    const int rc = alens_set_rods(ctx, n, gid.data(), pos.data(), q.data(), len.data(), rad.data(), imm.data(), wrap);
+    return rc != ALENS_OK ? rc : alens_set_rod_tags(ctx, tag.data());
+}
+
+int alens_set_rod_tags(alens_ctx *ctx, const long long *tags) {
+    return guarded(ctx, [&](Context &c) {
+        c.haveTags = tags != nullptr;
+        if (!tags) return;
+        c.uTag.reserve((size_t)c.nLocal + 1);
+        if (c.nLocal > 0) ALENS_CUDA(cudaMemcpyAsync(c.uTag.p, tags, 8 * (size_t)c.nLocal, cudaMemcpyHostToDevice, c.stream));
+        ALENS_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+int alens_get_rod_tags(alens_ctx *ctx, long long *tags) {
+    return guarded(ctx, [&](Context &c) {
+        if (!tags) throw ArgError{ALENS_ERR_ARG, "alens_get_rod_tags: NULL output"};
+        if (c.nLocal == 0) return;
+        if (!c.haveTags) {
+            memset(tags, 0, 8 * (size_t)c.nLocal);
+            return;
+        }
+        ALENS_CUDA(cudaMemcpyAsync(tags, c.uTag.p, 8 * (size_t)c.nLocal, cudaMemcpyDeviceToHost, c.stream));
+        ALENS_CUDA(cudaStreamSynchronize(c.stream));
+    });
 }
 
 int alens_prepare_step(alens_ctx *ctx, int wrap) {
@@ -294,6 +326,25 @@ int alens_get_rod_state(alens_ctx *ctx, double *pos, double *quat) {
                 ALENS_CUDA(cudaMemcpyAsync(quat, c.uQuat.p, 32 * (size_t)c.nLocal, cudaMemcpyDeviceToHost, c.stream));
             ALENS_CUDA(cudaStreamSynchronize(c.stream));
         }
+    });
+}
+
+int alens_migrate_rods(alens_ctx *ctx, long long *nSent, long long *nReceived) {
+    return guarded(ctx, [&](Context &c) { commMigrate(c, nSent, nReceived); });
+}
+
+int alens_get_rod_identity(alens_ctx *ctx, int *nLocal, int *globalIndexBase, int *gid, double *length, double *radius,
+                           unsigned char *immovable) {
+    return guarded(ctx, [&](Context &c) {
+        if (nLocal) *nLocal = c.nLocal;
+        if (globalIndexBase) *globalIndexBase = c.globalBase;
+        const size_t n = (size_t)c.nLocal;
+        if (n == 0) return;
+        if (gid) ALENS_CUDA(cudaMemcpyAsync(gid, c.uGid.p, 4 * n, cudaMemcpyDeviceToHost, c.stream));
+        if (length) ALENS_CUDA(cudaMemcpyAsync(length, c.uLen.p, 8 * n, cudaMemcpyDeviceToHost, c.stream));
+        if (radius) ALENS_CUDA(cudaMemcpyAsync(radius, c.uRad.p, 8 * n, cudaMemcpyDeviceToHost, c.stream));
+        if (immovable) ALENS_CUDA(cudaMemcpyAsync(immovable, c.uImm.p, n, cudaMemcpyDeviceToHost, c.stream));
+        ALENS_CUDA(cudaStreamSynchronize(c.stream));
     });
 }
 
@@ -479,6 +530,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
         }
         else if (k == "rec_mode") c.optRecMode = value != 0;
         else if (k == "stamps") c.optStamps = value != 0;
+        else if (k == "halo_debug") c.optHaloDebug = (int)value;
         else if (k == "u_window") c.optUWindow = value != 0;
         else if (k == "find_minb") c.optFindMinB = (value == 5 || value == 3) ? (int)value : 4;
         else if (k == "find_split") c.optFindSplit = value != 0;

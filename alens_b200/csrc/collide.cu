@@ -862,6 +862,11 @@ __global__ void k_max_radius(int n, const double *__restrict__ len, const double
 thread_local cudaStream_t g_allocStream = nullptr;
 thread_local bool g_allocAsync = false;
 
+// applyBoxBC on the resident owned rods (periodic axes only)
+void wrapRodPositions(Context &c) {
+    if (c.nLocal > 0) k_rod_wrap<<<gridFor(c.nLocal, 256), 256, 0, c.stream>>>(c.nLocal, c.uPos.p, c.box);
+}
+
 void rodsUploaded(Context &c, bool wrap) {
     cudaStream_t st = c.stream;
     const bool multi = c.comm.active;

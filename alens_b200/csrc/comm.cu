@@ -60,7 +60,7 @@ __global__ void k_ghost_list(int n, const int *__restrict__ flag, const int *__r
     if (i < n && flag[i]) list[scan[i]] = i;
 }
 
-// one ghost record = 17 doubles: pos3, quat4, length, radius, velNonCon6, (gid, globalIndex), (immovable, image)
+// one ghost record = 18 doubles: pos3, quat4, length, radius, velNonCon6, (gid, globalIndex), (immovable, image), host tag
 __global__ void k_ghost_pack(int n, const int *__restrict__ list, GhostSrc s, int image, double *__restrict__ dst) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -73,6 +73,7 @@ __global__ void k_ghost_pack(int n, const int *__restrict__ list, GhostSrc s, in
     for (int k = 0; k < 6; k++) d[9 + k] = s.velNC ? s.velNC[6 * (size_t)i + k] : 0.0;
     d[15] = __hiloint2double(s.gid[i], s.globalBase + i);
     d[16] = __hiloint2double(s.imm ? (int)s.imm[i] : 0, image + s.img[i]); // own image + the channel's
+    d[17] = __longlong_as_double(s.tag ? s.tag[i] : 0LL);
 }
 __global__ void k_ghost_unpack(int n, const double *__restrict__ src, GhostDst o, int base) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,6 +90,7 @@ __global__ void k_ghost_unpack(int n, const double *__restrict__ src, GhostDst o
     o.globalIdx[i] = __double2loint(d[15]);
     o.imm[i] = (unsigned char)__double2hiint(d[16]);
     o.img[i] = (signed char)__double2loint(d[16]);
+    if (o.tag) o.tag[i] = __double_as_longlong(d[17]);
 }
 
 // after the cell sort: tell the sender where each of its ghosts sits in my sorted arrays
@@ -298,7 +300,7 @@ void commExchangeGhosts(Context &c) {
     // pack straight into the neighbours' windows; image = how the rod appears in the receiver's frame
     const unsigned long long seq = ++m.seqGhost;
     GhostSrc src{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.uImg.p,
-                 c.haveVelNC ? c.uVelNC.p : nullptr, c.globalBase};
+                 c.haveVelNC ? c.uVelNC.p : nullptr, c.globalBase, nullptr};
     unsigned long long *sf[2] = {nullptr, nullptr};
     long long *sc[2] = {nullptr, nullptr};
     for (int d = 0; d < 2; d++) {
@@ -333,7 +335,7 @@ void commExchangeGhosts(Context &c) {
     c.uImg.reserve(N + 1, st, true, n); c.uGlobalIdx.reserve(N + 1, st, true, n);
     if (c.haveVelNC) c.uVelNC.reserve(6 * N + 6, st, true, 6 * (size_t)n);
     GhostDst dst{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.uImg.p, c.uGlobalIdx.p,
-                 c.haveVelNC ? c.uVelNC.p : nullptr};
+                 c.haveVelNC ? c.uVelNC.p : nullptr, nullptr};
     int base = n;
     for (int ch = 0; ch < 2; ch++) {
         if (m.nRecv[ch] > 0)
@@ -385,6 +387,175 @@ void commExchangeGhostIndices(Context &c) {
     ALENS_CUDA(cudaGetLastError());
     ALENS_CUDA(cudaStreamSynchronize(st));
     checkCommError(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rod migration (the device-side counterpart of decomposeDomain + exchangeSylinder, SylinderSystem.cpp:617-620, for slabs):
+// owned rods whose (wrapped) centre left the slab move to the neighbour slab through the ghost channels, the remaining
+// rods keep their order, arrivals are appended (left neighbour's first), and every rank learns every rank's new count
+// (-> globalIndex base, updateSylinderMap :868-880).  Collective; call between alens_step_euler and alens_prepare_step.
+__global__ void k_migrate_flags(int n, const double *__restrict__ pos, int axis, double lo, double hi, double boxLen,
+                                int periodic, int haveLeft, int haveRight, int *__restrict__ fL, int *__restrict__ fR,
+                                int *__restrict__ keep, int *__restrict__ lost) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = pos[3 * (size_t)i + axis];
+    double xa = x; // the periodic image of the centre that is nearest to my slab
+    if (periodic) {
+        const double mid = 0.5 * (lo + hi);
+        if (fabs(x - boxLen - mid) < fabs(xa - mid)) xa = x - boxLen;
+        if (fabs(x + boxLen - mid) < fabs(xa - mid)) xa = x + boxLen;
+    }
+    const int L = (haveLeft && xa < lo) ? 1 : 0, R = (haveRight && xa >= hi) ? 1 : 0;
+    const double w = hi - lo;
+    if ((L && xa < lo - w) || (R && xa >= hi + w)) atomicAdd(lost, 1); // further than the next slab: not a neighbour's rod
+    fL[i] = L;
+    fR[i] = R;
+    keep[i] = (L || R) ? 0 : 1;
+}
+template <typename T, int W>
+__global__ void k_compact(int n, const int *__restrict__ keep, const int *__restrict__ scan, const T *__restrict__ src,
+                          T *__restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const size_t o = (size_t)scan[i];
+    for (int w = 0; w < W; w++) dst[W * o + w] = src[W * (size_t)i + w];
+}
+struct PeerHeaders {
+    CommHeader *h[kMaxRanks];
+};
+__global__ void k_publish_count(PeerHeaders peers, int R, int myRank, long long count, unsigned long long seq) {
+    const int q = threadIdx.x;
+    if (q >= R) return;
+    peers.h[q]->cnt[myRank] = count;
+    __threadfence_system();
+    stReleaseSys(&peers.h[q]->cntSeq[myRank], seq);
+}
+__global__ void k_wait_counts(CommHeader *me, int R, unsigned long long seq) {
+    const int q = threadIdx.x;
+    if (q < R) waitSeq(&me->cntSeq[q], seq, &me->error);
+}
+
+template <typename T, int W>
+static void compactInto(Context &c, int n, int nKeep, int nNew, const int *keep, const int *scan, DevBuf<T> &buf) {
+    DevBuf<T> out;
+    out.reserve((size_t)W * ((size_t)std::max(nNew, n) + 1) + 8);
+    if (n > 0) k_compact<T, W><<<gridFor(n, 256), 256, 0, c.stream>>>(n, keep, scan, buf.p, out.p);
+    std::swap(buf.p, out.p);
+    std::swap(buf.cap, out.cap);
+    (void)nKeep;
+}
+
+void commMigrate(Context &c, long long *nSent, long long *nReceived) {
+    Comm &m = c.comm;
+    if (!m.active) throw ArgError{ALENS_ERR_STATE, "alens_migrate_rods: no communicator (alens_comm_connect first)"};
+    if (!c.uPos.p && c.nLocal > 0) throw ArgError{ALENS_ERR_STATE, "alens_migrate_rods: no resident rods"};
+    cudaStream_t st = c.stream;
+    waitVelNC(c);
+    const int n = c.nLocal, ax = c.slabAxis;
+    CommHeader *me = hdrOf(m.win);
+    wrapRodPositions(c); // positions into the box first (applyBoxBC), as prepareStep does
+    DevBuf<int> fL, fR, keep, scanL, scanR, scanK;
+    fL.reserve(n + 8); fR.reserve(n + 8); keep.reserve(n + 8);
+    scanL.reserve(n + 8); scanR.reserve(n + 8); scanK.reserve(n + 8);
+    ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, sizeof(unsigned long long), st));
+    if (n > 0)
+        k_migrate_flags<<<gridFor(n, 256), 256, 0, st>>>(n, c.uPos.p, ax, c.slabLo, c.slabHi, c.box.len[ax], c.box.pbc[ax],
+                                                         m.left >= 0, m.right >= 0, fL.p, fR.p, keep.p,
+                                                         reinterpret_cast<int *>(c.dCounters.p));
+    launchScanInt(c, fL.p, scanL.p, n);
+    launchScanInt(c, fR.p, scanR.p, n);
+    launchScanInt(c, keep.p, scanK.p, n);
+    int cnt[3] = {0, 0, 0}, lost = 0;
+    ALENS_CUDA(cudaMemcpyAsync(&cnt[0], scanL.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaMemcpyAsync(&cnt[1], scanR.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaMemcpyAsync(&cnt[2], scanK.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaMemcpyAsync(&lost, c.dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    const bool overflow = (size_t)cnt[0] > m.capGhost || (size_t)cnt[1] > m.capGhost;
+    if (overflow) cnt[0] = cnt[1] = 0; // stay collective: send nothing, report below
+    DevBuf<int> listL, listR;
+    listL.reserve((size_t)cnt[0] + 1); listR.reserve((size_t)cnt[1] + 1);
+    if (n > 0 && !overflow) {
+        k_ghost_list<<<gridFor(n, 256), 256, 0, st>>>(n, fL.p, scanL.p, listL.p);
+        k_ghost_list<<<gridFor(n, 256), 256, 0, st>>>(n, fR.p, scanR.p, listR.p);
+    }
+    const unsigned long long seq = ++m.seqGhost;
+    GhostSrc src{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.uImg.p,
+                 c.haveVelNC ? c.uVelNC.p : nullptr, c.globalBase, c.haveTags ? c.uTag.p : nullptr};
+    unsigned long long *sf[2] = {nullptr, nullptr};
+    long long *sc[2] = {nullptr, nullptr};
+    const int *lists[2] = {listL.p, listR.p};
+    for (int d = 0; d < 2; d++) {
+        unsigned char *w = nbWin(c, d);
+        if (!w) continue;
+        const int ch = 1 - d;
+        if (cnt[d] > 0)
+            k_ghost_pack<<<gridFor(cnt[d], 128), 128, 0, st>>>(cnt[d], lists[d], src, 0,
+                                                               reinterpret_cast<double *>(w + m.offChan[ch]));
+        sf[d] = &hdrOf(w)->chanSeq[ch];
+        sc[d] = &hdrOf(w)->chanCount[ch];
+    }
+    k_signal<<<1, 1, 0, st>>>(sf[0], sc[0], cnt[0], sf[1], sc[1], cnt[1], seq, nullptr);
+    k_wait_seq<<<1, 1, 0, st>>>(m.left >= 0 ? &me->chanSeq[0] : nullptr, m.right >= 0 ? &me->chanSeq[1] : nullptr, seq,
+                                &me->error, nullptr);
+    long long rc[2] = {0, 0};
+    ALENS_CUDA(cudaMemcpyAsync(rc, me->chanCount, sizeof(rc), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    checkCommError(c);
+    const int nRecv[2] = {m.left >= 0 ? (int)rc[0] : 0, m.right >= 0 ? (int)rc[1] : 0};
+    const int nKeep = overflow ? n : cnt[2];
+    const int nNew = nKeep + nRecv[0] + nRecv[1];
+    if ((size_t)nNew > m.capRods) throw ArgError{ALENS_ERR_COMM, "comm: rod capacity of the window exceeded"};
+    if (!overflow) { // the rods that stay, in their order
+        compactInto<int, 1>(c, n, nKeep, nNew, keep.p, scanK.p, c.uGid);
+        compactInto<double, 3>(c, n, nKeep, nNew, keep.p, scanK.p, c.uPos);
+        compactInto<double, 4>(c, n, nKeep, nNew, keep.p, scanK.p, c.uQuat);
+        compactInto<double, 1>(c, n, nKeep, nNew, keep.p, scanK.p, c.uLen);
+        compactInto<double, 1>(c, n, nKeep, nNew, keep.p, scanK.p, c.uRad);
+        compactInto<unsigned char, 1>(c, n, nKeep, nNew, keep.p, scanK.p, c.uImm);
+        if (c.haveVelNC) compactInto<double, 6>(c, n, nKeep, nNew, keep.p, scanK.p, c.uVelNC);
+        if (c.haveTags) compactInto<long long, 1>(c, n, nKeep, nNew, keep.p, scanK.p, c.uTag);
+    }
+    const size_t N = (size_t)nNew;
+    c.uGid.reserve(N + 1, st, true, nKeep); c.uPos.reserve(3 * N + 3, st, true, 3 * (size_t)nKeep);
+    c.uQuat.reserve(4 * N + 4, st, true, 4 * (size_t)nKeep); c.uLen.reserve(N + 1, st, true, nKeep);
+    c.uRad.reserve(N + 1, st, true, nKeep); c.uImm.reserve(N + 1, st, true, nKeep);
+    c.uImg.reserve(N + 1); c.uGlobalIdx.reserve(N + 1);
+    if (c.haveVelNC) c.uVelNC.reserve(6 * N + 6, st, true, 6 * (size_t)nKeep);
+    if (c.haveTags) c.uTag.reserve(N + 1, st, true, nKeep);
+    GhostDst dst{c.uGid.p, c.uPos.p, c.uQuat.p, c.uLen.p, c.uRad.p, c.uImm.p, c.uImg.p, c.uGlobalIdx.p,
+                 c.haveVelNC ? c.uVelNC.p : nullptr, c.haveTags ? c.uTag.p : nullptr};
+    int base = nKeep;
+    for (int ch = 0; ch < 2; ch++) {
+        if (nRecv[ch] > 0)
+            k_ghost_unpack<<<gridFor(nRecv[ch], 128), 128, 0, st>>>(
+                nRecv[ch], reinterpret_cast<const double *>(m.win + m.offChan[ch]), dst, base);
+        base += nRecv[ch];
+    }
+    // every rank's new count to every rank; doubles as the barrier behind which the channels may be written again
+    const unsigned long long cs = ++m.seqCnt;
+    PeerHeaders peers{};
+    for (int q = 0; q < c.nranks; q++) peers.h[q] = hdrOf(m.peerWin[q]);
+    k_publish_count<<<1, 32, 0, st>>>(peers, c.nranks, c.rank, (long long)nNew, cs);
+    k_wait_counts<<<1, 32, 0, st>>>(me, c.nranks, cs);
+    long long all[kMaxRanks] = {};
+    ALENS_CUDA(cudaMemcpyAsync(all, me->cnt, sizeof(long long) * c.nranks, cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    checkCommError(c);
+    long long before = 0;
+    for (int q = 0; q < c.rank; q++) before += all[q];
+    c.globalBase = (int)before;
+    c.nLocal = c.nRods = nNew;
+    c.nGhost = 0;
+    c.sorted = false;
+    c.haveMob = c.haveSetup = c.haveSolution = false;
+    c.launches += 16;
+    if (nSent) *nSent = (long long)cnt[0] + cnt[1];
+    if (nReceived) *nReceived = (long long)nRecv[0] + nRecv[1];
+    ALENS_CUDA(cudaGetLastError());
+    if (overflow) throw ArgError{ALENS_ERR_COMM, "alens_migrate_rods: more rods leave than a channel holds (alens_comm_create maxLocalRods too small)"};
+    if (lost > 0) throw ArgError{ALENS_ERR_STATE, "alens_migrate_rods: a rod moved further than the neighbouring slab: redistribute on the host"};
 }
 
 // velNonCon of the mirrored rods -> the neighbours' user-order vector (ghost rows), staged through the channel
@@ -473,6 +644,16 @@ void preloadCommKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_copy6_rows));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_fill_int));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_build_mirror));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_migrate_flags));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_publish_count));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_wait_counts));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_compact<int, 1>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_compact<double, 1>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_compact<double, 3>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_compact<double, 4>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_compact<double, 6>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_compact<unsigned char, 1>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_compact<long long, 1>)));
 }
 
 } // namespace alens

@@ -126,7 +126,7 @@ struct SolverScalars {
 
 // ---- multi-GPU (comm.cu) ----------------------------------------------------------------------
 static constexpr int kMaxRanks = 16;
-static constexpr int kGhostRec = 17; // doubles per ghost record
+static constexpr int kGhostRec = 18; // doubles per ghost record
 
 // start of every rank's window; every word below is written by a PEER (remote store) and polled locally
 struct CommHeader {
@@ -138,6 +138,9 @@ struct CommHeader {
     unsigned long long mailSeq[2][kMaxRanks]; // [parity][source rank]
     double mail[2][kMaxRanks][4];             // BBPGD partial sums {dx.dx, dx.dg, dg.dg, max |q|}
     int error;                                // set by a waiter that timed out
+    // rod migration (commMigrate): every rank publishes its new number of owned rods to every rank
+    unsigned long long cntSeq[kMaxRanks];
+    long long cnt[kMaxRanks];
 };
 
 struct CommBlob { // what a rank publishes to its peers (multi-process bootstrap)
@@ -153,6 +156,7 @@ struct GhostSrc {
     const signed char *img;
     const double *velNC;
     int globalBase;
+    const long long *tag; // the host's per-rod tag (alens_set_rod_tags); nullptr: none
 };
 struct GhostDst {
     int *gid;
@@ -161,6 +165,7 @@ struct GhostDst {
     signed char *img;
     int *globalIdx;
     double *velNC;
+    long long *tag; // nullptr: not stored
 };
 
 struct Comm {
@@ -171,7 +176,7 @@ struct Comm {
     unsigned char *peerWin[kMaxRanks] = {};
     bool ipcMapped[kMaxRanks] = {};
     size_t offChan[2] = {}, offAck[2] = {}, offU = 0, capGhost = 0, capRods = 0;
-    unsigned long long seqGhost = 0, seqAck = 0, seqVec = 0, seqHalo = 0, seqMail = 0; // lockstep counters
+    unsigned long long seqGhost = 0, seqAck = 0, seqVec = 0, seqHalo = 0, seqMail = 0, seqCnt = 0; // lockstep counters
     DevBuf<int> sendIdx[2];    // user index of my rods mirrored on the left / right neighbour
     DevBuf<int> sendSorted[2]; // their sorted index (source rows of the U halo)
     DevBuf<int> mirror[2];     // per sorted rod: its row on the left / right neighbour, -1 if not mirrored there
@@ -211,6 +216,8 @@ struct Context {
     int nGhost = 0;
     DevBuf<signed char> uImg; // image of a ghost along the slab axis (-1, 0, +1); 0 for owned rods
     DevBuf<int> uGlobalIdx;   // global index (owner's numbering)
+    DevBuf<long long> uTag; // the host's per-rod tag (e.g. Sylinder::group): travels with a migrating rod
+    bool haveTags = false;
     DevBuf<int> uGid;
     DevBuf<double> uPos, uQuat, uLen, uRad; // 3n, 4n, n, n
     DevBuf<unsigned char> uImm;
@@ -266,6 +273,7 @@ struct Context {
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 3;                 // 3 = k_force_vel_rec (64-byte slot records + slot-ordered live bitmap kept by k_bb_tail), 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
     int optUWindow = 0; // experiment: see setupConstraints
+    int optHaloDebug = 0; // timing experiments only (results are wrong): 1 = no remote U stores, 2 = no fence + ticket
     int optStamps = 0, stampCap = 0, stampIters = 0; // per-iteration nanosecond stamps of the BBPGD kernels (instrumentation)
     DevBuf<unsigned long long> dStamps;
     unsigned long long *stampNow = nullptr;
@@ -408,6 +416,8 @@ inline int gridFor(long long n, int block) { return (int)((n + block - 1) / bloc
 
 // shared small kernels (collide.cu)
 void launchScanInt(Context &c, const int *in, int *out, int n);
+void wrapRodPositions(Context &c);
+void commMigrate(Context &c, long long *nSent, long long *nReceived);
 double hostMaxRadius(int n, const double *len, const double *rad, double lRatio, double dRatio);
 
 } // namespace alens

@@ -601,10 +601,12 @@ struct HaloPush {
     unsigned long long *flag[2];
     unsigned long long seq;
     unsigned int *ticket;
-    // k_force_vel_rec: CTA b works on rod tile order[b]; the tiles that contain a mirrored rod come first (order[gridDim] of
-    // them) and only their CTAs take a ticket: the neighbours' halo flags are released as soon as the boundary is done,
-    // while the interior tiles are still being worked on (nullptr: natural order, every CTA takes a ticket)
-    const int *order;
+    // k_force_vel_rec: only the CTAs whose 128-rod tile holds a mirrored rod (tileFlag[b] != 0, *nBoundary of them) read
+    // the mirror indices, push, fence and take a ticket; the last of them releases the neighbours' halo flags.  The tail
+    // kernel waits for those flags behind all its rows that need no halo, so nothing is gained by running the boundary
+    // tiles first -- and a CTA whose tile index hangs on a load starts late.  (nullptr: every CTA takes a ticket)
+    const int *tileFlag, *nBoundary;
+    int debug; // timing experiments (alens_set_option halo_debug)
 };
 
 // Where the force kernel takes x from.  XMODE 0: a plain vector.  XMODE 1: gamma_b = gamma o biFlag
@@ -1061,24 +1063,19 @@ struct FvRec {
 template <bool WRITE_F, bool HALO, int SRC>
 __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, double *__restrict__ U, double *__restrict__ F,
                                                        const SolverScalars *__restrict__ scal, HaloPush hp) {
-    int tile = blockIdx.x, nTicket = gridDim.x;
-    if (HALO && hp.on && hp.order) {
-        tile = hp.order[blockIdx.x];
-        nTicket = hp.order[gridDim.x];
-    }
-    const int r = tile * blockDim.x + threadIdx.x;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = r < in.nRods;
     int b = 0, e = 0;
     unsigned ghost = 1;
-    int mirL = -1, mirR = -1;
+    int boundary = 1, nTicket = gridDim.x; // (needed at the very end only: these two loads are never waited for early)
+    if (HALO && hp.on && hp.tileFlag) {
+        boundary = __ldg(hp.tileFlag + blockIdx.x);
+        nTicket = __ldg(hp.nBoundary);
+    }
     if (act) { // incidence structure: constant during a solve, requested before the wait
         b = __ldg(in.incStart + r);
         e = __ldg(in.incStart + r + 1);
         ghost = mob.ghost[r];
-        if (HALO && hp.on) {
-            if (hp.mir[0]) mirL = hp.mir[0][r];
-            if (hp.mir[1]) mirR = hp.mir[1][r];
-        }
     }
     pdlWait(); // records, bitmap and step size come from the previous kernel
     if (scal && scal->done) return;
@@ -1086,7 +1083,7 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
     const double alpha = (in.update && scal) ? scal->alpha : 0.0;
     double f[6] = {0, 0, 0, 0, 0, 0};
     bool any = false, pushed = false;
-    if (act && e > b) {
+    if (act && e > b && !ghost) { // (a ghost rod's force is its owner's business: its slots are skipped)
         for (int wd = b >> 5; wd <= (e - 1) >> 5; wd++) {
             unsigned bits = __ldg(in.slotLive + wd);
             const int lo = wd << 5;
@@ -1143,20 +1140,23 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
             Fp[1] = make_double2(f[2], f[3]);
             Fp[2] = make_double2(f[4], f[5]);
         }
-        if (HALO && mirL >= 0) {
-            double2 *Rp = reinterpret_cast<double2 *>(hp.rem[0] + 6 * (size_t)mirL);
-            Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
-            pushed = true;
-        }
-        if (HALO && mirR >= 0) {
-            double2 *Rp = reinterpret_cast<double2 *>(hp.rem[1] + 6 * (size_t)mirR);
-            Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
-            pushed = true;
+        if (HALO && hp.on && boundary && !(hp.debug & 1)) { // where this rod is mirrored (boundary tiles only: 8 % of the rods' tiles)
+            const int mirL = hp.mir[0] ? __ldg(hp.mir[0] + r) : -1, mirR = hp.mir[1] ? __ldg(hp.mir[1] + r) : -1;
+            if (mirL >= 0) {
+                double2 *Rp = reinterpret_cast<double2 *>(hp.rem[0] + 6 * (size_t)mirL);
+                Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+                pushed = true;
+            }
+            if (mirR >= 0) {
+                double2 *Rp = reinterpret_cast<double2 *>(hp.rem[1] + 6 * (size_t)mirR);
+                Rp[0] = u0; Rp[1] = u1; Rp[2] = u2;
+                pushed = true;
+            }
         }
     }
     if (HALO && hp.on && hp.ticket) { // fused multi-GPU: the last CTA of the BOUNDARY tiles releases the neighbours' halo flags
-        if ((int)blockIdx.x < nTicket) {
-            if (pushed) __threadfence_system();
+        if (boundary && nTicket > 0) {
+            if (pushed && !(hp.debug & 2)) __threadfence_system();
             __syncthreads();
             if (threadIdx.x == 0) {
                 const unsigned t = atomicAdd(hp.ticket, 1u);
@@ -1673,13 +1673,13 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     const int nTiles = (int)((p.nc + kVecBlock - 1) / kVecBlock);
     // p.tileOrder (k_tile_order, built at setup): the tiles without a ghost-reading row first (nClean of them), then the
     // others -- whatever the slab axis
-    const int nClean = (p.waitSeq && p.tileOrder) ? p.tileOrder[nTiles] : 0;
-    auto rowOf = [&](int tau) -> long long {
-        const int tile = (p.waitSeq && p.tileOrder) ? p.tileOrder[tau] : tau;
-        return (long long)tile * kVecBlock + threadIdx.x;
-    };
-    int tau = blockIdx.x;
-    long long k = tau < nTiles ? rowOf(tau) : p.nc;
+    // (the tile id of trip t + 2 is requested in trip t: the streaming loads of trip t + 1 never wait for an index)
+    const bool ordered = p.waitSeq && p.tileOrder;
+    const int nClean = ordered ? __ldg(p.tileOrder + nTiles) : 0;
+    auto tileOf = [&](int tau) -> int { return (ordered && tau < nTiles) ? __ldg(p.tileOrder + tau) : tau; };
+    int tau = blockIdx.x, tauN = tau + gridDim.x;
+    int tileN = tileOf(tauN);
+    long long k = tau < nTiles ? (long long)tileOf(tau) * kVecBlock + threadIdx.x : p.nc;
     double s0 = 0, s1 = 0, s2 = 0, mx = 0;
     TailRow cur, nxt;
     if (k < p.nc) loadTailRow<HASK>(p, (size_t)k, cur); // all of it at least two kernels old (see pdlWait)
@@ -1693,18 +1693,18 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     const unsigned long long keepPol = policyEvictLast();
     while (tau < nTiles) {
         if (!waited && tau >= nClean) { // ghost rows of U: pushed by the neighbours' force kernels (CTA-uniform test)
-            if (threadIdx.x == 0) {
+            if (threadIdx.x < 2) { // one thread per neighbour: the two polls overlap
                 if (p.stamp) atomicMin(p.stamp + 4, globalNs());
-                if (p.waitFlag[0]) waitSeq(p.waitFlag[0], p.waitSeq, p.red.err);
-                if (p.waitFlag[1]) waitSeq(p.waitFlag[1], p.waitSeq, p.red.err);
+                if (p.waitFlag[threadIdx.x]) waitSeq(p.waitFlag[threadIdx.x], p.waitSeq, p.red.err);
                 if (p.stamp) atomicMax(p.stamp + 5, globalNs());
             }
             __syncthreads();
             waited = true;
         }
         const bool valid = k < p.nc;
-        const int tauN = tau + gridDim.x;
-        const long long kn = tauN < nTiles ? rowOf(tauN) : p.nc;
+        const int tauNN = tauN + gridDim.x;
+        const int tileNN = tileOf(tauNN);
+        const long long kn = tauN < nTiles ? (long long)tileN * kVecBlock + threadIdx.x : p.nc;
         // (1) the six 16-byte gathers of this row's two U rows (L2 hits, needed first), unconditional and back to back:
         // a one-sided row gathers rod I twice, a lane past the end gathers row 0
         const int iI = valid ? cur.iI : 0;
@@ -1725,6 +1725,8 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
         cur = nxt;
         k = kn;
         tau = tauN;
+        tauN = tauNN;
+        tileN = tileNN;
     }
     tailEpilogue(p, s0, s1, s2, mx, nMaybe);
 }
@@ -2582,6 +2584,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
                 hp.rem[d] = reinterpret_cast<double *>(m.peerWin[q] + m.offU);
             }
             hp.on = 1;
+            hp.debug = c.optHaloDebug;
             if (c.incLayout != 0) { // the force kernel releases the neighbours' halo flags itself (last CTA)
                 for (int d = 0; d < 2; d++) {
                     const int q = d == 0 ? m.left : m.right;
@@ -2589,7 +2592,10 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
                 }
                 hp.seq = seq;
                 hp.ticket = &c.dScal.p->ticketFv;
-                if (c.incLayout == 3 && c.optLateHalo && c.rodOrder.p && c.nRods > 0) hp.order = c.rodOrder.p;
+                if (c.incLayout == 3 && c.optLateHalo && c.rodOrder.p && c.nRods > 0) {
+                    hp.tileFlag = c.rodFlag.p;
+                    hp.nBoundary = c.rodOrder.p + gridFor(c.nRods, 128); // k_tile_order: order[nTiles] = flagged tiles
+                }
             }
             launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p, &hp);
             if (c.incLayout == 0) commSignalHalo(c, seq);

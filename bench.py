@@ -377,6 +377,10 @@ def main():
         ctx.comm_connect(slabs.exchange_blobs(ctx.comm_export()))  # the only host-side collective of the data path
     rods, relax_info = relax_on_gpu(ctx, rods, gbox, a.relax, configured=world > 1)
     vnc = thermal_velocity(rods, MU, DT, seed=SEED + 17 + rank)
+    # timing experiments that break results (never set for a reported number): applied after the relaxation steps
+    for kv in os.environ.get("ALENS_LATE_OPTIONS", "").split(","):
+        if "=" in kv:
+            ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
     # pinned host buffers for the e2e leg
     def pin(x):

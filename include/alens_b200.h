@@ -342,6 +342,22 @@ int alens_comm_connect(alens_ctx *ctx, const void *blobsInRankOrder);
 /* single-process bootstrap: n contexts (rank order) driven by n host threads; devices may coincide */
 int alens_comm_connect_local(alens_ctx **ctxs, int n);
 /* ghost rods received / owned rods mirrored on the left and right neighbour in the last exchange */
+/* Device-side rod migration, the slab counterpart of decomposeDomain + exchangeSylinder (SylinderSystem.cpp:617-620):
+ * COLLECTIVE over the connected ranks, to be called on the resident state between alens_step_euler and
+ * alens_prepare_step.  Owned rods whose wrapped centre left this rank's slab move to the neighbouring slab through the
+ * peer-memory channels (record: gid, position, orientation, length, radius, immovable flag, velNonCon row); the rods that
+ * stay keep their order, arrivals follow (left neighbour's first); every rank's globalIndex base is renumbered
+ * (updateSylinderMap, :868-880).  ALENS_ERR_STATE if a rod moved further than the neighbouring slab (the host has to
+ * redistribute then).  The caller learns its new local set with alens_get_rod_identity + alens_get_rod_state. */
+int alens_migrate_rods(alens_ctx *ctx, long long *nSent, long long *nReceived);
+/* One opaque 64-bit tag per owned rod (local order), kept on the device and carried along by alens_migrate_rods -- what
+ * FDPS's exchangeParticle does for the rest of the Sylinder record.  alens_set_rods_aos stores Sylinder::group there.
+ * alens_set_rods clears the tags; NULL clears them too. */
+int alens_set_rod_tags(alens_ctx *ctx, const long long *tags);
+int alens_get_rod_tags(alens_ctx *ctx, long long *tags);
+/* the resident owned rods in the context's order; any output may be NULL (call once with NULL arrays for the count) */
+int alens_get_rod_identity(alens_ctx *ctx, int *nLocal, int *globalIndexBase, int *gid, double *length, double *radius,
+                           unsigned char *immovable);
 int alens_num_ghosts(alens_ctx *ctx, int *nGhost, int *nSentLeft, int *nSentRight);
 /* connected: the windows are mapped; fused: every rank sits on its own GPU, so the BBPGD kernels wait for their
  * neighbours themselves (halo wait + mailbox allreduce inside k_bb_tail, remote stores from k_force_vel_act) instead of

@@ -38,14 +38,19 @@ class SylinderSystem {
     Teuchos::RCP<const TCOMM> commRcp;
     Teuchos::RCP<TMAP> sylinderMapRcp, sylinderMobilityMapRcp;
     Teuchos::RCP<TOP> mobilityOperatorRcp; ///< placeholder: the mobility lives on the device
+    bool multiRank_ = false; ///< slab decomposition: one SylinderSystem (one GPU) per rank
 
     void ck(int rc) const {
         if (rc != ALENS_OK) throw std::runtime_error(alens_last_error(ctx_));
     }
     void updateSylinderMap() { // :868-880
         const int nLocal = (int)sylinderContainer.size();
-        sylinderMapRcp = getTMAPFromLocalSize(nLocal, commRcp);
-        sylinderMobilityMapRcp = getTMAPFromLocalSize(nLocal * 6, commRcp);
+        // multi-rank: the exclusive scan of the ranks' rod counts is kept by the device layer (alens_set_decomposition at
+        // start, renumbered by every alens_migrate_rods), as getTMAPFromLocalSize's MPI scan does in the reference
+        int offset = 0;
+        if (multiRank_) ck(alens_get_rod_identity(ctx_, nullptr, &offset, nullptr, nullptr, nullptr, nullptr));
+        sylinderMapRcp = getTMAPFromLocalSize(nLocal, commRcp, offset);
+        sylinderMobilityMapRcp = getTMAPFromLocalSize(nLocal * 6, commRcp, 6 * offset);
         const int base = sylinderMapRcp->getMinGlobalIndex();
         for (int i = 0; i < nLocal; i++) sylinderContainer[i].globalIndex = i + base;
     }
@@ -218,6 +223,68 @@ class SylinderSystem {
             }
         }
     }
+
+
+    // ---- more than one rank: slabs along one box axis, one SylinderSystem (one GPU) per rank.  What FDPS's DomainInfo +
+    // exchangeParticle and Tpetra's maps do in the reference (SylinderSystem.cpp:569-620, :868-880) is done by the device
+    // layer: ghost rods, halo of the rod velocities, allreduce of the BBPGD scalars, rod migration.
+    struct Decomposition {
+        int rank = 0, nranks = 1;
+        int axis = 2;                        ///< slab axis (z: the slowest axis of the cell order, boundaries are contiguous)
+        double skin = 0;                     ///< how far a rod may drift out of its slab before it is migrated (>= one step's motion)
+        double globalMaxBoundingRadius = 0;  ///< max over ALL ranks of lengthCollision / 2 + radiusCollision
+        int globalIndexBase = 0;             ///< number of rods on the ranks below this one (MPI_Exscan of the local counts)
+        long long maxLocalRods = 0;          ///< capacity of the communication window: the SAME number on every rank
+    };
+    /// rank `dec.rank` of `dec.nranks`: this rank's rods are those of `rods` (they must lie in its slab).  The communicator
+    /// is connected afterwards (connectLocal, or exportCommBlob + connectComm around the host's MPI_Allgather); the initial
+    /// collision resolution (:88-101) then runs with resolveInitialCollisions().
+    void initialize(const SylinderConfig &config, std::vector<Sylinder> rods, int device, const Decomposition &dec) {
+        runConfig = config;
+        stepCount = 0;
+        multiRank_ = dec.nranks > 1;
+        commRcp = getMPIWORLDTCOMM(dec.rank, dec.nranks);
+        if (alens_create(device, dec.rank, dec.nranks, &ctx_) != ALENS_OK) throw std::runtime_error(alens_last_error(nullptr));
+        conSolverPtr = std::make_shared<ConstraintSolver>(ctx_);
+        conCollectorPtr = std::make_shared<ConstraintCollector>();
+        sylinderContainer = std::move(rods);
+        const int pbc[3] = {runConfig.simBoxPBC[0], runConfig.simBoxPBC[1], runConfig.simBoxPBC[2]};
+        ck(alens_set_domain(ctx_, runConfig.simBoxLow, runConfig.simBoxHigh, pbc));
+        ck(alens_set_collision_params(ctx_, runConfig.sylinderDiameterColRatio, runConfig.sylinderLengthColRatio,
+                                      runConfig.sylinderColBuf));
+        if (multiRank_) {
+            const double lo = runConfig.simBoxLow[dec.axis], w = (runConfig.simBoxHigh[dec.axis] - lo) / dec.nranks;
+            ck(alens_set_decomposition(ctx_, dec.axis, lo + dec.rank * w, lo + (dec.rank + 1) * w, dec.skin,
+                                       dec.globalMaxBoundingRadius, dec.globalIndexBase));
+            if (dec.maxLocalRods <= 0) throw std::invalid_argument("Decomposition::maxLocalRods: the window capacity (same on all ranks)");
+            ck(alens_comm_create(ctx_, dec.maxLocalRods));
+        }
+    }
+    std::vector<char> exportCommBlob() { // what this rank publishes to its peers (cudaIpc handle of its window)
+        std::vector<char> blob((size_t)alens_comm_blob_size());
+        ck(alens_comm_export(ctx_, blob.data()));
+        return blob;
+    }
+    void connectComm(const std::vector<char> &blobsInRankOrder) { ck(alens_comm_connect(ctx_, blobsInRankOrder.data())); }
+    /// ranks living in one process (one host thread each)
+    static void connectLocal(const std::vector<SylinderSystem *> &ranks) {
+        std::vector<alens_ctx *> c;
+        for (auto *r : ranks) c.push_back(r->ctx_);
+        if (alens_comm_connect_local(c.data(), (int)c.size()) != ALENS_OK) throw std::runtime_error(alens_last_error(c[0]));
+    }
+    void resolveInitialCollisions() { // :88-101
+        if (runConfig.sylinderFixed) return;
+        for (int i = 0; i < runConfig.initPreSteps; i++) {
+            prepareStep();
+            calcVelocityNonCon();
+            resolveConstraints();
+            saveForceVelocityConstraints();
+            sumForceVelocity();
+            stepEuler();
+        }
+    }
+    void setBrownianOnDevice(bool on) { brownianOnDevice = on; }
+    bool isMultiRank() const { return multiRank_; }
 
     alens_ctx *deviceContext() { return ctx_; }
     const std::vector<Sylinder> &getContainer() { return sylinderContainer; }
@@ -458,12 +525,47 @@ class SylinderSystem {
     void stepEuler() { // :816-827
         if (runConfig.sylinderFixed) return;
         ck(alens_step_euler(ctx_, runConfig.dt));
+        if (multiRank_) { // rods that left the slab move to the neighbour rank, on the device (:617-620 in the reference)
+            long long sent = 0, received = 0;
+            ck(alens_migrate_rods(ctx_, &sent, &received));
+            if (sent + received > 0) {
+                refillContainerFromDevice();
+                return;
+            }
+        }
         const size_t n = sylinderContainer.size();
         std::vector<double> pos(3 * n), q(4 * n);
         ck(alens_get_rod_state(ctx_, pos.data(), q.data()));
         for (size_t i = 0; i < n; i++) {
             for (int k = 0; k < 3; k++) sylinderContainer[i].pos[k] = pos[3 * i + k];
             for (int k = 0; k < 4; k++) sylinderContainer[i].orientation[k] = q[4 * i + k];
+        }
+    }
+    /// the rank's rod set changed: gid, shape, state and group (the rod's tag) come from the device, the per-step fields
+    /// (velocities, forces, collision sizes, globalIndex) are rebuilt by the next prepareStep as for every rod
+    void refillContainerFromDevice() {
+        int n = 0, base = 0;
+        ck(alens_get_rod_identity(ctx_, &n, &base, nullptr, nullptr, nullptr, nullptr));
+        std::vector<int> gid((size_t)n + 1);
+        std::vector<double> len((size_t)n + 1), rad((size_t)n + 1), pos(3 * (size_t)n + 3), q(4 * (size_t)n + 4);
+        std::vector<unsigned char> imm((size_t)n + 1);
+        std::vector<long long> tag((size_t)n + 1);
+        ck(alens_get_rod_identity(ctx_, &n, &base, gid.data(), len.data(), rad.data(), imm.data()));
+        ck(alens_get_rod_state(ctx_, pos.data(), q.data()));
+        ck(alens_get_rod_tags(ctx_, tag.data()));
+        sylinderContainer.assign((size_t)n, Sylinder());
+        for (int i = 0; i < n; i++) {
+            Sylinder &sy = sylinderContainer[i];
+            sy.gid = gid[i];
+            sy.group = (int)tag[i];
+            sy.isImmovable = imm[i] != 0;
+            sy.radius = rad[i];
+            sy.length = len[i];
+            sy.radiusCollision = rad[i] * runConfig.sylinderDiameterColRatio;
+            sy.lengthCollision = len[i] * runConfig.sylinderLengthColRatio;
+            sy.colBuf = runConfig.sylinderColBuf;
+            for (int k = 0; k < 3; k++) sy.pos[k] = pos[3 * (size_t)i + k];
+            for (int k = 0; k < 4; k++) sy.orientation[k] = q[4 * (size_t)i + k];
         }
     }
 

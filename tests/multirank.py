@@ -48,8 +48,11 @@ def take(rods, idx):
 
 
 def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None, skin=None, axis=0, devices=None,
-              steps=1, want_blocks=True):
-    """returns per-rank dicts (idx = global rod indices owned, blocks, gamma, forceU/velU/..., report, history)"""
+              steps=1, want_blocks=True, migrate=False, brown=None):
+    """returns per-rank dicts (idx = global rod indices owned, blocks, gamma, forceU/velU/..., report, history).
+    migrate: alens_migrate_rods between stepEuler and prepareStep (the rank's rod set changes: `gid` tells which it holds
+    at the end, `migrated` = (sent, received) totals); brown = (kBT, seed): velNonCon = the device's Brownian velocity,
+    keyed by (seed, step, gid) and therefore the same whatever the decomposition"""
     lo, hi = np.asarray(lo, float), np.asarray(hi, float)
     parts = split_slabs(rods, lo, hi, nranks, axis)
     max_r = float(np.max(0.5 * rods["length"] + rods["radius"]))
@@ -78,13 +81,24 @@ def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None,
             c.set_rods(loc["gid"], loc["pos"], loc["quat"], loc["length"], loc["radius"], loc["immovable"], wrap=True)
             v = None if vnc is None else np.ascontiguousarray(vnc.reshape(-1, 6)[idx]).reshape(-1)
             res_r = dict(idx=idx)
+            moved = [0, 0]
             for s in range(steps):
                 if s > 0:
                     c.step_euler(dt)
+                    if migrate:
+                        a, b = c.migrate_rods()
+                        moved[0] += a
+                        moved[1] += b
                     c.prepare_step(True)
                 nc = c.collect_pair_collision()
                 c.calc_mobility(mu)
+                if brown is not None:
+                    vb = c.calc_velocity_brown(brown[0], dt, None, brown[1], s)
+                    c.calc_velocity_noncon(vel_brown=vb)
+                    v = None
                 rep = c.solve_constraints(v, dt, res, max_ite, 0)
+            res_r["migrated"] = tuple(moved)
+            res_r["identity"] = c.get_rod_identity()
             res_r.update(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), ghosts=c.num_ghosts(),
                          mode=c.comm_mode(), digest=c.constraint_digest())
             res_r.update(c.get_force_velocity())

@@ -112,10 +112,12 @@ def test_constraint_operator_with_caller_bounds(ctx, oracle):
         assert np.all(x >= lb) and np.all(x <= ub) and (x == ub).sum() > 10 and (x < 0).sum() > 100  # the caller's bounds
         assert relerr(x, xr) < 1e-7
         np.testing.assert_allclose(hist[:, 4], hr[:, 4], rtol=1e-6)
-    # a projection error is reported, not ignored (BCQPSolver.cpp:484-494)
-    q.set_bounds(np.full(nc, 1.0), np.full(nc, -1.0))
+    # a projection error is reported, not ignored (BCQPSolver.cpp:484-494).  With finite numbers the three branches of the
+    # projected gradient cover every case; the error branch is what a NaN iterate falls into
+    bad = x0.copy()
+    bad[3] = np.nan
     with pytest.raises(alens_b200.AlensError) as ei:
-        q.solve(g0, 1e-6, 5, 0)
+        q.solve(bad, 1e-6, 5, 0)
     assert ei.value.code == -5
     q.close()
 

@@ -163,3 +163,19 @@ def test_mirror_main_program_follows_the_reference_main_program(tmp_path):
     for name in ("Sylinder_r0_0.vtp", "Sylinder_0.pvtp", "ConBlock_r0_0.vtp", "ConBlock_0.pvtp", "SylinderAscii_0.dat"):
         assert (work / "result" / "result0-399" / name).stat().st_size > 100, name
     s.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_mirror_on_several_ranks_with_device_side_migration(nranks):
+    """include/alens_b200/SylinderSystem.hpp on `nranks` ranks (one host thread + one context each; one GPU each when the
+    box has them): Brownian steps with rods crossing slab faces, against one SylinderSystem holding everything
+    (tests/cpp/test_multirank.cpp: each gid exactly once, group travels with the rod, contiguous globalIndex, positions)"""
+    import torch
+
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
+    exe = os.path.join(ROOT, "tests", "cpp", "test_multirank")
+    env = dict(os.environ)
+    if torch.cuda.device_count() >= nranks:
+        env["ALENS_TEST_DEVICES"] = ",".join(str(i) for i in range(nranks))
+    r = subprocess.run([exe, str(nranks), "5"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "PASS" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])

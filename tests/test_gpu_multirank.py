@@ -213,3 +213,57 @@ def test_multirank_stray_rod_is_reported():
         finally:
             multirank.split_slabs = orig
     assert ei.value.code == -3
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_multirank_device_side_rod_migration_tracks_the_single_rank_trajectory(placement, nranks):
+    """resident Brownian steps (solve -> stepEuler -> alens_migrate_rods -> prepareStep) without any host redistribution:
+    rods diffuse across slab faces and the periodic box face, move to the neighbour rank on the device, and every rod
+    follows the single-rank trajectory (SylinderSystem.cpp:617-620 is what the reference does instead).  Few, large steps:
+    the collision dynamics amplify rounding differences step by step, a long run can only be compared statistically."""
+    import alens_b200
+
+    n, box, colbuf, mu, dt, res, steps, kbt, seed = 1500 * nranks, (2.0 * nranks, 1.5, 1.5), 0.025, 1.0, 1e-4, 1e-11, 6, 20.0, 9
+    lo, hi, pbc = [0.0] * 3, list(box), (1, 1, 1)
+    rods = slab_ordered(random_rods(n, box, seed=78), lo, hi, nranks)
+    c = alens_b200.Context(0)
+    c.set_domain(lo, hi, pbc)
+    c.set_collision_params(1.0, 1.0, colbuf)
+    c.set_rods(rods["gid"], rods["pos"], rods["quat"], rods["length"], rods["radius"], rods["immovable"], wrap=True)
+    for s in range(steps):
+        if s > 0:
+            c.step_euler(dt)
+            c.prepare_step(True)
+        c.collect_pair_collision()
+        c.calc_mobility(mu)
+        vb = c.calc_velocity_brown(kbt, dt, None, seed, s)
+        c.calc_velocity_noncon(vel_brown=vb)
+        c.solve_constraints(None, dt, res, 20000, 0)
+    pos_ref, quat_ref = c.get_rod_state()
+    c.close()
+    by_gid = {int(g): i for i, g in enumerate(rods["gid"])}
+    ranks = run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, 20000, vnc=None, skin=0.1, steps=steps,
+                      want_blocks=False, devices=_devices(placement, nranks), migrate=True, brown=(kbt, seed))
+    _check_mode(ranks, placement)
+    seen = []
+    w = box[0] / nranks
+    base = 0
+    for r, out in enumerate(ranks):
+        gbase, gid, length, radius, imm = out["identity"]
+        pos, quat = out["state"]
+        assert gbase == base and len(gid) == len(pos)
+        base += len(gid)
+        idx = np.array([by_gid[int(g)] for g in gid], dtype=int)
+        seen.extend(idx.tolist())
+        assert np.array_equal(length, rods["length"][idx]) and np.array_equal(radius, rods["radius"][idx])
+        assert np.array_equal(imm, rods["immovable"][idx])
+        d = pos - pos_ref[idx]
+        d -= np.round(d / np.array(box)) * np.array(box)
+        assert np.abs(d).max() < 1e-7
+        assert np.abs(quat - quat_ref[idx]).max() < 1e-6
+        # every rod a rank holds was inside its slab (up to one step of drift) when it was last migrated
+        x = np.mod(pos[:, 0], box[0])
+        dist = np.minimum(np.abs(x - (r + 0.5) * w), box[0] - np.abs(x - (r + 0.5) * w))
+        assert dist.max() < 0.5 * w + 0.25
+    assert sorted(seen) == list(range(n))  # nobody lost, nobody duplicated
+    assert sum(o["migrated"][0] for o in ranks) == sum(o["migrated"][1] for o in ranks) > 20
