@@ -1620,8 +1620,7 @@ __device__ __forceinline__ void tailEpilogue(const BbTail &p, double s0, double 
             const int q = threadIdx.x;
             double *dst = a.mailPeer[q];
             dst[0] = out[0]; dst[1] = out[1]; dst[2] = out[2]; dst[3] = out[3];
-            __threadfence_system();
-            stReleaseSys(a.seqPeer[q], a.seq);
+            stReleaseSys(a.seqPeer[q], a.seq); // (release: this thread's four stores are ordered before the flag; no extra fence)
             if (!waitSeq(a.seqMine + q, a.seq, a.err)) {
                 failed = 1;
             } else {
