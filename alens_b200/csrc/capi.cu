@@ -528,9 +528,12 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
             c.optForceSplit = value == 2;
             if (c.optForceKernel == 3) c.optTailRing = 0; // the TMA-staged tail does not maintain the slot records
         }
-        else if (k == "rec_mode") c.optRecMode = value != 0;
+        else if (k == "rec_mode") c.optRecMode = (value < 0 || value > 2) ? 1 : (int)value; // 2: records hold M * column
         else if (k == "stamps") c.optStamps = value != 0;
         else if (k == "halo_debug") c.optHaloDebug = (int)value;
+        else if (k == "l2_fetch") { // cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes): a device-wide hint
+            ALENS_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+        }
         else if (k == "u_window") c.optUWindow = value != 0;
         else if (k == "find_minb") c.optFindMinB = (value == 5 || value == 3) ? (int)value : 4;
         else if (k == "find_split") c.optFindSplit = value != 0;

@@ -277,9 +277,11 @@ struct Context {
     int optStamps = 0, stampCap = 0, stampIters = 0; // per-iteration nanosecond stamps of the BBPGD kernels (instrumentation)
     DevBuf<unsigned long long> dStamps;
     unsigned long long *stampNow = nullptr;
-    int optRecMode = 1, recMode = 1;        // force_kernel 3: 0 = k_bb_tail copies {x, g} into the slot records, 1 = the records hold the row id and k_force_vel_rec gathers {x, g} itself
+    bool recDirty = false;                  // rec_mode 2: alens_calc_mobility ran after the setup, the records must be rebuilt
+    int optRecMode = 2, recMode = 2;        // force_kernel 3: 0 = k_bb_tail copies {x, g} into the slot records, 1 = the records hold the row id and k_force_vel_rec gathers {x, g} itself, 2 = as 1 with M * column in the record (no mobility read)
     DevBuf<double> incRec;                  // force_kernel 3: 8 doubles per slot {x, g, D column block[6]}, 64-byte aligned records
     DevBuf<int2> cSlot;                     // ... per constraint: slot of its I side / J side (-1: none, ghost or one-sided)
+    DevBuf<int2> rodHead; // force_kernel 3: per rod {first slot, live bits of its first 32 slots}
     DevBuf<unsigned> slotBi;                // ... bit per slot: the slot's constraint is bilateral (constant during a solve)
     int optFindSplitMinB = 8;               // ... resident CTAs per SM of its stage-1/2 kernel (8: 64 registers)
     int optFindSplit = 1;                   // pair search: stages 1-2 -> candidates, dense narrow phase + ordered emission (0: one kernel)

@@ -364,8 +364,11 @@ __global__ void k_inc_emit_rm(int nRods, const int *__restrict__ start, int *__r
 // be non-zero is refreshed by k_bb_tail every iteration, which also keeps the slot-ordered bitmap slotLive up to date.
 // The force kernel then needs no constraint ids at all: bitmap word -> one aligned 64-byte record per live slot.
 // cSlot[k] = (slot of row k in rod I's list, slot in rod J's list), -1 where the side has no slot (one-sided, ghost rod).
+// mobRec != nullptr (rec_mode 2): the record holds M_rod * column instead of the column, so that the force kernel adds up
+// the rod's VELOCITY directly (u = sum_s (M c_s) x_s) and never reads the rod's mobility data.
 __global__ void k_inc_emit_rec(int nRods, const int *__restrict__ start, int *__restrict__ incCon, ConGeom g,
-                               double *__restrict__ rec, int2 *__restrict__ cSlot, unsigned *__restrict__ slotBi) {
+                               double *__restrict__ rec, int2 *__restrict__ cSlot, unsigned *__restrict__ slotBi,
+                               const double *__restrict__ mobRec) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp * 32 >= nRods) return;
     const int r = warp * 32 + lane;
@@ -381,7 +384,21 @@ __global__ void k_inc_emit_rec(int nRods, const int *__restrict__ start, int *__
     }
     __syncwarp();
     const int gb = __shfl_sync(0xffffffffu, b, 0), ge = __shfl_sync(0xffffffffu, e, 31);
-    for (int p = gb + lane; p < ge; p += 32) {
+    for (int base = gb; base < ge; base += 32) { // (warp-uniform trip count: the owner search below shuffles)
+        const int p = base + lane;
+        int owner = 0; // lane whose rod owns slot p: the last lane with start <= p
+        if (mobRec) {
+            int lo = 0, hi = 31;
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (lo + hi + 1) >> 1;
+                const int bm = __shfl_sync(0xffffffffu, b, mid);
+                if (bm <= p) lo = mid;
+                else hi = mid - 1;
+            }
+            owner = warp * 32 + lo;
+        }
+        if (p >= ge) continue;
         const int k2 = incCon[p];
         const size_t kk = (size_t)(k2 >> 2);
         const bool sideJ = k2 & 1;
@@ -389,11 +406,22 @@ __global__ void k_inc_emit_rec(int nRods, const int *__restrict__ start, int *__
         const double *P = sideJ ? g.pJ : g.pI;
         const double px = P[kk], py = P[kk + g.stride], pz = P[kk + 2 * g.stride];
         if (sideJ) { gx = -gx; gy = -gy; gz = -gz; }
+        double c0 = gx, c1 = gy, c2 = gz, c3 = (gz * py - gy * pz), c4 = (gx * pz - gz * px), c5 = (gy * px - gx * py);
+        if (mobRec) { // M c with Mtt = qq^T/zPara + (I - qq^T)/zPerp, Mrr = I/zRot
+            const double *m = mobRec + 8 * (size_t)owner;
+            const double qx = m[0], qy = m[1], qz = m[2], iPara = m[3], iPerp = m[4], iRot = m[5];
+            const double qf = qx * c0 + qy * c1 + qz * c2;
+            const double ax = qf * qx, ay = qf * qy, az = qf * qz;
+            c0 = iPara * ax + iPerp * (c0 - ax);
+            c1 = iPara * ay + iPerp * (c1 - ay);
+            c2 = iPara * az + iPerp * (c2 - az);
+            c3 = iRot * c3; c4 = iRot * c4; c5 = iRot * c5;
+        }
         double2 *o = reinterpret_cast<double2 *>(rec + 8 * (size_t)p);
-        o[0] = make_double2(__longlong_as_double((long long)k2), 0.0); // rec_mode 1: the slot code; rec_mode 0: {x, g} later
-        o[1] = make_double2(gx, gy);
-        o[2] = make_double2(gz, (gz * py - gy * pz));
-        o[3] = make_double2((gx * pz - gz * px), (gy * px - gx * py));
+        o[0] = make_double2(__longlong_as_double((long long)k2), 0.0); // rec_mode 1/2: the slot code; rec_mode 0: {x, g} later
+        o[1] = make_double2(c0, c1);
+        o[2] = make_double2(c2, c3);
+        o[3] = make_double2(c4, c5);
         if (sideJ) cSlot[kk].y = p;
         else cSlot[kk].x = p;
         if (k2 & 2) atomicOr(slotBi + (p >> 5), 1u << (p & 31));
@@ -1044,6 +1072,28 @@ __global__ void __launch_bounds__(256) k_slot_init(SlotInit in, XIn xin) {
     if ((threadIdx.x & 31) == 0 && p < in.nInc + 32) in.slotLive[p >> 5] = m;
 }
 
+// Rod headers (force_kernel = 3): head[r] = {first slot of rod r, live bits of its first 32 slots}.  One 8-byte load gives
+// a rod thread its slot range AND its live mask (a second dependent load -- the word of the slot-ordered bitmap -- only for
+// the few rods with more than 32 slots).  The bits are kept current by k_bb_tail next to the slot-ordered bitmap.
+__global__ void k_rod_head_build(int nRods, const int *__restrict__ incStart, int2 *__restrict__ head) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= nRods) head[r] = make_int2(incStart[r], 0);
+}
+__global__ void k_rod_head_init(int nRods, int2 *__restrict__ head, const unsigned *__restrict__ slotLive) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRods) return;
+    const int b = head[r].x, e = head[r + 1].x;
+    unsigned bits = 0;
+    if (e > b) { // bits [b, min(e, b + 32)) of the slot-ordered bitmap
+        const int wd = b >> 5, sh = b & 31;
+        const unsigned long long two = (unsigned long long)slotLive[wd] | ((unsigned long long)slotLive[wd + 1] << 32);
+        bits = (unsigned)(two >> sh);
+        const int cnt = e - b;
+        if (cnt < 32) bits &= (1u << cnt) - 1u;
+    }
+    head[r].y = (int)bits;
+}
+
 struct FvRec {
     const int *incStart;
     const double *rec;
@@ -1056,11 +1106,16 @@ struct FvRec {
     const double *x;
     int xmode;
     unsigned long long *stamp; // 8 words of this iteration (nullptr: off)
+    // rec_mode 2 (MCOL): the records hold M * column.  The two applies of a solve that also return the FORCE rebuild the
+    // column of a live slot from the row's geometry (n, posI / posJ), as k_inc_emit_rec does.
+    const double *gn, *gpI, *gpJ;
+    size_t gstride;
+    const int2 *head; // rod headers {first slot, live bits of the first 32 slots}
 };
 
 // SRC: where a live slot's multiplier comes from -- 0: {x, g} inside the record (rec_mode 0), 1: the row-ordered {x, g}
 // pairs, gathered by the row id in the record (rec_mode 1, BBPGD), 2: a plain vector, gathered by row id (rec_mode 1)
-template <bool WRITE_F, bool HALO, int SRC>
+template <bool WRITE_F, bool HALO, int SRC, bool MCOL = false>
 __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, double *__restrict__ U, double *__restrict__ F,
                                                        const SolverScalars *__restrict__ scal, HaloPush hp) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1073,28 +1128,44 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
         nTicket = __ldg(hp.nBoundary);
     }
     if (act) { // incidence structure: constant during a solve, requested before the wait
-        b = __ldg(in.incStart + r);
         e = __ldg(in.incStart + r + 1);
         ghost = mob.ghost[r];
     }
-    pdlWait(); // records, bitmap and step size come from the previous kernel
+    pdlWait(); // records, bitmaps and step size come from the previous kernel
     if (scal && scal->done) return;
     if (in.stamp && threadIdx.x == 0) atomicMin(in.stamp + 0, globalNs());
     const double alpha = (in.update && scal) ? scal->alpha : 0.0;
     double f[6] = {0, 0, 0, 0, 0, 0};
     bool any = false, pushed = false;
+    unsigned first = 0;
+    if (act) { // {first slot, live bits of the first 32 slots}: written by the tail kernel (plain load, after the wait)
+        const int2 h = in.head[r];
+        b = h.x;
+        first = (unsigned)h.y;
+    }
     if (act && e > b && !ghost) { // (a ghost rod's force is its owner's business: its slots are skipped)
-        for (int wd = b >> 5; wd <= (e - 1) >> 5; wd++) {
-            unsigned bits = __ldg(in.slotLive + wd);
-            const int lo = wd << 5;
-            if (b > lo) bits &= ~((1u << (b - lo)) - 1u);
-            if (e < lo + 32) bits &= (1u << (e - lo)) - 1u;
+        // piece 0: the header's 32 bits (slots b .. b + 31); further pieces (rods with more than 32 slots): words of the
+        // slot-ordered bitmap, restricted to this rod's slots beyond the header's
+        const int b2 = b + 32;
+        for (int piece = 0, wd = b2 >> 5; piece == 0 || (e > b2 && wd <= (e - 1) >> 5); piece++) {
+            unsigned bits;
+            int lo;
+            if (piece == 0) {
+                bits = first;
+                lo = b;
+            } else {
+                bits = __ldg(in.slotLive + wd);
+                lo = wd << 5;
+                if (b2 > lo) bits &= ~((1u << (b2 - lo)) - 1u);
+                if (e < lo + 32) bits &= (1u << (e - lo)) - 1u;
+                wd++;
+            }
             if (!bits) continue;
             any = true;
-            const unsigned biw = (SRC == 0 && in.update) ? __ldg(in.slotBi + wd) : 0u;
             while (bits) { // ascending slot order
                 const int q = __ffs(bits) - 1;
                 bits &= bits - 1u;
+                const unsigned biw = (SRC == 0 && in.update) ? __ldg(in.slotBi + ((lo + q) >> 5)) >> ((lo + q) & 31) : 0u;
                 const double *cp = in.rec + 8 * (size_t)(lo + q);
                 double xp, gp, c0, c1, c2, c3, c4, c5;
                 ld256(cp, xp, gp, c0, c1); // the record's two sectors: {x | row id, g, col[0..1]} and {col[2..5]}
@@ -1109,7 +1180,18 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
                     const double xv = __ldg(in.x + (code >> 2));
                     x = in.xmode == 1 ? 1.0 * xv * ((code & 2) ? 1.0 : 0.0) : xv;
                 } else {
-                    x = in.update ? bbStep(xp, gp, alpha, (biw >> q) & 1u) : xp;
+                    x = in.update ? bbStep(xp, gp, alpha, biw & 1u) : xp;
+                }
+                if (MCOL && WRITE_F) { // the column itself, from the row's geometry (2 launches per solve)
+                    const int code = (int)__double_as_longlong(xp);
+                    const size_t kk = (size_t)(code >> 2);
+                    const bool sideJ = code & 1;
+                    double gx = in.gn[kk], gy = in.gn[kk + in.gstride], gz = in.gn[kk + 2 * in.gstride];
+                    const double *P = sideJ ? in.gpJ : in.gpI;
+                    const double px = P[kk], py = P[kk + in.gstride], pz = P[kk + 2 * in.gstride];
+                    if (sideJ) { gx = -gx; gy = -gy; gz = -gz; }
+                    c0 = gx; c1 = gy; c2 = gz;
+                    c3 = (gz * py - gy * pz); c4 = (gx * pz - gz * px); c5 = (gy * px - gx * py);
                 }
                 f[0] += c0 * x; f[1] += c1 * x; f[2] += c2 * x;
                 f[3] += c3 * x; f[4] += c4 * x; f[5] += c5 * x;
@@ -1119,13 +1201,17 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
     // a rod without a live slot (45 % of them) has f = 0 and therefore u = +0 exactly and never reads its mobility data
     double qx = 0, qy = 0, qz = 0, iPara = 0;
     double2 iPR = make_double2(0.0, 0.0); // {1/zeta_perp, 1/zeta_rot}
-    if (any && !ghost) {
+    if ((!MCOL || WRITE_F) && any && !ghost) {
         ld256(mob.rec + 8 * (size_t)r, qx, qy, qz, iPara); // one 64-byte line per rod
         iPR = ldGather2(reinterpret_cast<const double2 *>(mob.rec + 8 * (size_t)r + 4));
     }
     if (act && !ghost) {
         double2 u0 = make_double2(0.0, 0.0), u1 = u0, u2 = u0;
-        if (any) {
+        if (MCOL && !WRITE_F) { // the sums ARE the velocity
+            u0 = make_double2(f[0], f[1]);
+            u1 = make_double2(f[2], f[3]);
+            u2 = make_double2(f[4], f[5]);
+        } else if (any) {
             const double qf = qx * f[0] + qy * f[1] + qz * f[2];
             const double px = qf * qx, py = qf * qy, pz = qf * qz;
             u0 = make_double2(iPara * px + iPR.x * (f[0] - px), iPara * py + iPR.x * (f[1] - py));
@@ -1419,6 +1505,7 @@ struct BbTail {
     double *rec;
     const int2 *cSlot;
     unsigned *slotLive;
+    int2 *head;               // rod headers: the live bits of a rod's first 32 slots are flipped there as well
     unsigned long long *stamp; // 8 words of this iteration (nullptr: off)
     const unsigned char *own; // multi-rank: 1 = this rank counts the row in the dot products (nullptr = all)
     double *redOut;           // multi-rank: the reduced partials go here, k_bb_reduce finishes the step
@@ -1574,12 +1661,20 @@ __device__ __forceinline__ bool tailRowMath(const BbTail &p, const TailRow &cur,
             if (sJ >= 0) st256(p.rec + 8 * (size_t)sJ, x, gk, -gx, -gy);
         }
         if (on != was0) {
+            // position of the slot inside its rod's list: the first 32 live bits of a rod sit in its header
+            const int jI = sI >= 0 ? sI - p.head[cur.iI].x : 32, jJ = sJ >= 0 ? sJ - p.head[cur.iJ].x : 32;
+            unsigned *hI = reinterpret_cast<unsigned *>(&p.head[cur.iI].y);
+            unsigned *hJ = reinterpret_cast<unsigned *>(&p.head[sJ >= 0 ? cur.iJ : cur.iI].y);
             if (on) {
                 if (sI >= 0) atomicOr(p.slotLive + (sI >> 5), 1u << (sI & 31));
                 if (sJ >= 0) atomicOr(p.slotLive + (sJ >> 5), 1u << (sJ & 31));
+                if (jI < 32) atomicOr(hI, 1u << jI);
+                if (jJ < 32) atomicOr(hJ, 1u << jJ);
             } else {
                 if (sI >= 0) atomicAnd(p.slotLive + (sI >> 5), ~(1u << (sI & 31)));
                 if (sJ >= 0) atomicAnd(p.slotLive + (sJ >> 5), ~(1u << (sJ & 31)));
+                if (jI < 32) atomicAnd(hI, ~(1u << jI));
+                if (jJ < 32) atomicAnd(hJ, ~(1u << jJ));
             }
         }
     }
@@ -2053,6 +2148,7 @@ void calcMobility(Context &c, double mu) {
     }
     ALENS_CUDA(cudaGetLastError());
     c.haveMob = true;
+    if (c.haveSetup && c.incLayout == 3 && c.recMode == 2) c.recDirty = true; // the slot records hold M * column
 }
 
 void mobilityApply(Context &c, const double *x, double *y) {
@@ -2193,13 +2289,20 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
         ALENS_CUDA(cudaMemsetAsync(c.cSlot.p, 0xff, sizeof(int2) * ((size_t)nc + 32), st));
         ALENS_CUDA(cudaMemsetAsync(c.slotBi.p, 0, sizeof(unsigned) * ((size_t)(nInc >> 5) + 4), st));
         ALENS_CUDA(cudaMemsetAsync(c.slotLive.p, 0, sizeof(unsigned) * ((size_t)(nInc >> 5) + 4), st));
+        c.rodHead.reserve((size_t)n + 2);
+        k_rod_head_build<<<gridFor(n + 1, 256), 256, 0, st>>>(n, c.incStart.p, c.rodHead.p);
+        c.launches++;
     }
     if (nc > 0) {
         if (c.incLayout == 3) {
             k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.cBi.p, c.sGhost.p, c.incStart.p,
                                                          c.incFill.p, c.incCon.p);
+            // rec_mode 2 needs the rods' mobility for M * column; without it (setup before alens_calc_mobility) this setup
+            // falls back to plain columns
+            if (c.recMode == 2 && !c.haveMob) c.recMode = 1;
             k_inc_emit_rec<<<gridFor(n, 128), 128, 0, st>>>(n, c.incStart.p, c.incCon.p, conGeom(c), c.incRec.p, c.cSlot.p,
-                                                            c.slotBi.p);
+                                                            c.slotBi.p, c.recMode == 2 ? c.sMobRec.p : nullptr);
+            c.recDirty = false;
         } else if (c.incLayout == 1) { // rod-major: the raw slot lists are sorted in place and ARE incCon
             k_inc_fill<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.cBi.p, c.sGhost.p, c.incStart.p,
                                                          c.incFill.p, c.incCon.p);
@@ -2360,12 +2463,20 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
             }
             const SlotInit si{c.incCon.p, nInc, c.recMode == 0 ? c.incRec.p : nullptr, c.slotLive.p};
             k_slot_init<XMODE><<<std::max(1, gridFor(nInc + 32, 256)), 256, 0, c.stream>>>(si, xm);
-            c.launches++;
-            c.timers.op_launches++;
+            if (n > 0) k_rod_head_init<<<gridFor(n, 256), 256, 0, c.stream>>>(n, c.rodHead.p, c.slotLive.p);
+            c.launches += 2;
+            c.timers.op_launches += 2;
         }
+        if (c.recDirty) { // alens_calc_mobility ran after the setup: M * column again (the sort inside is a no-op now)
+            k_inc_emit_rec<<<gridFor(n, 128), 128, 0, c.stream>>>(n, c.incStart.p, c.incCon.p, conGeom(c), c.incRec.p,
+                                                                  c.cSlot.p, c.slotBi.p, c.sMobRec.p);
+            c.launches++;
+            c.recDirty = false;
+        }
+        const ConGeom cg = conGeom(c);
         FvRec fr{c.incStart.p, c.incRec.p, c.slotLive.p, c.slotBi.p, n, init ? 0 : 1, nullptr, nullptr, XMODE,
-                 XMODE == 2 ? c.stampNow : nullptr};
-        if (c.recMode == 1) {
+                 XMODE == 2 ? c.stampNow : nullptr, cg.n, cg.pI, cg.pJ, cg.stride, c.rodHead.p};
+        if (c.recMode != 0) {
             if (XMODE == 2) fr.xg = xin.xg;
             else fr.x = xin.x;
         }
@@ -2383,6 +2494,10 @@ static void launchForceVel(Context &c, const XIn &xin, double *U, double *F, con
             if (XMODE == 2 && !WF && hp.on)
                 ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, (XMODE == 2 && !WF), 0>), fr, mobIn(c), U, F, scal, hp));
             else ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, false, 0>), fr, mobIn(c), U, F, scal, hp));
+        } else if (c.recMode == 2) {
+            if (XMODE == 2 && !WF && hp.on)
+                ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, (XMODE == 2 && !WF), SRC1, true>), fr, mobIn(c), U, F, scal, hp));
+            else ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, false, SRC1, true>), fr, mobIn(c), U, F, scal, hp));
         } else {
             if (XMODE == 2 && !WF && hp.on)
                 ALENS_CUDA(cudaLaunchKernelEx(&cfg, (k_force_vel_rec<WF, (XMODE == 2 && !WF), SRC1>), fr, mobIn(c), U, F, scal, hp));
@@ -2546,6 +2661,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
         t.rec = c.recMode == 0 ? c.incRec.p : nullptr;
         t.cSlot = c.cSlot.p;
         t.slotLive = c.slotLive.p;
+        t.head = c.rodHead.p;
     }
     t.pdlTrig = c.optPdl == 2;
     t.tileOrder = (multi && c.optLateHalo && c.tailOrder.p && nc > 0) ? c.tailOrder.p : nullptr;
@@ -2788,7 +2904,7 @@ double timeKernel(Context &c, int which, int reps) {
     c.profiling = false;
     if (c.incLayout == 3) { // slot records and bitmap of x0, and a tail that maintains them
         launchForceVel<2, false>(c, XIn{nullptr, c.vXG0.p, 0, c.vMask.p}, c.rU.p, nullptr, c.dScal.p);
-        t.maskOut = c.vMask.p; t.rec = c.recMode == 0 ? c.incRec.p : nullptr; t.cSlot = c.cSlot.p; t.slotLive = c.slotLive.p;
+        t.maskOut = c.vMask.p; t.rec = c.recMode == 0 ? c.incRec.p : nullptr; t.cSlot = c.cSlot.p; t.slotLive = c.slotLive.p; t.head = c.rodHead.p;
     }
     auto one = [&]() {
         if (which == 0)
@@ -3085,6 +3201,8 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mask_from_x<false>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_inc_emit_rec));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_head_build));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_head_init));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_init<0>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_init<1>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_slot_init<2>));
@@ -3095,6 +3213,10 @@ void preloadSolverKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, true, 1>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, false, 2>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<true, false, 2>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, false, 1, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, true, 1, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<false, false, 2, true>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_force_vel_rec<true, false, 2, true>)));
 }
 
 } // namespace alens

@@ -335,11 +335,12 @@ def main():
     stream = torch.cuda.Stream()
     ctx = alens_b200.Context(device=local, rank=rank, nranks=world)
     ctx.set_stream(stream.cuda_stream)
-    # tuning knobs for A/B measurements (none of them changes a result bit): ALENS_OPTIONS="force_kernel=1,rec_mode=0"
+    # tuning knobs for A/B measurements: ALENS_OPTIONS="force_kernel=1,rec_mode=0" (only rec_mode 2 against the others changes
+    # result bits: it sums M * column instead of applying M to the summed force)
     opts = dict(kv.split("=") for kv in os.environ.get("ALENS_OPTIONS", "").split(",") if "=" in kv)
     for k, v in opts.items():
         ctx.set_option(k, int(v))
-    fk, rec_mode = int(opts.get("force_kernel", 3)), int(opts.get("rec_mode", 1))
+    fk, rec_mode = int(opts.get("force_kernel", 3)), int(opts.get("rec_mode", 2))
 
     max_r = 0.5 * L_ROD + R_ROD
     skin = 0.5 * (2 * max_r + COLBUF)  # rods drift during the untimed relaxation steps
@@ -509,7 +510,12 @@ def main():
     # and out (2 bits); the slot-bitmap bits of the few rows whose liveness flips are negligible.
     live_rows = tm["op_rows_live"] / max(tm["op_applies"], 1)
     dense_force = 52.0 * ninc + 16.0 * nc + 96.0 * n  # what the dense level-major kernel (force_kernel=0) moves
-    if fk == 3 and rec_mode == 1:
+    if fk == 3 and rec_mode == 2:
+        # records hold M * column: as rec_mode 1 without the mobility line of the rods that have a live slot
+        kern = {"k_force_vel_rec": (tm["op_force_vel_ms"], tm["op_force_vel_n"],
+                                    4.0 * (n + 1) + ninc / 8.0 + 80.0 * live["live_slots"] + 49.0 * n),
+                "k_bb_tail": (tm["op_dtrans_ms"], tm["op_dtrans_n"], 129.0 * nc + nc / 4.0)}
+    elif fk == 3 and rec_mode == 1:
         # records hold the row id: + one 16-byte {x, g} gather per live slot; the tail only flips bitmap bits
         kern = {"k_force_vel_rec": (tm["op_force_vel_ms"], tm["op_force_vel_n"],
                                     4.0 * (n + 1) + ninc / 8.0 + 80.0 * live["live_slots"] + 48.0 * live["live_rods"] + 49.0 * n),

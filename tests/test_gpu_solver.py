@@ -162,11 +162,12 @@ def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
     x[rng.uniform(size=nc) < zero_frac] = 0.0
     x[::7] *= -1.0  # negative multipliers and -0.0 occur in plain operator applies
     res = {}
-    def select(kern):  # 3: k_force_vel_rec gathering {x, g} by row id (default), 30: with {x, g} copied into the records
-        ctx.set_option("force_kernel", 3 if kern == 30 else kern)
-        ctx.set_option("rec_mode", 0 if kern == 30 else 1)
+    def select(kern):  # 3: k_force_vel_rec gathering {x, g} by row id (default), 30: with {x, g} copied into the records,
+        # 32: records hold M * column (the velocity is summed directly: same numbers up to rounding, not bit for bit)
+        ctx.set_option("force_kernel", 3 if kern in (30, 32) else kern)
+        ctx.set_option("rec_mode", {30: 0, 32: 2}.get(kern, 1))  # (3 = rec_mode 1 here; the library's default is 2)
 
-    for kern in (3, 30, 1, 2, 0):  # 1 k_force_vel_act, 2 k_slot_x + k_rod_sum, 0 dense level-major
+    for kern in (3, 30, 32, 1, 2, 0):  # 1 k_force_vel_act, 2 k_slot_x + k_rod_sum, 0 dense level-major
         select(kern)
         ctx.setup_constraints(None, DT)
         res[kern] = ctx.operator_apply(x, want_force_vel=True)
@@ -177,6 +178,9 @@ def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
     for kern in (3, 30, 1, 2):
         for a, b in zip(res[0], res[kern]):
             assert np.array_equal(a, b)
+    y32, f32, v32 = res[32]
+    assert np.array_equal(f32, res[0][1])  # the force comes from the row geometry: bit for bit
+    assert relerr(y32, res[0][0]) < 1e-13 and relerr(v32, res[0][2]) < 1e-13
     ctx.set_option("force_kernel", 0)
     ctx.setup_constraints(None, DT)
     for a, b in zip(ctx.operator_apply(res["x2"][0], want_force_vel=True), res["x2"][1]):
@@ -187,7 +191,7 @@ def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
     # the BBPGD loop (x recomputed on the fly from {x_prev, g_prev}) gives the same iterates with both kernels
     vnc = thermal_velocity(rods, MU, DT, seed=9)
     gam = {}
-    for kern in (3, 30, 1, 2, 0):
+    for kern in (3, 30, 32, 1, 2, 0):
         select(kern)
         rep = ctx.solve_constraints(vnc, DT, 1e-30, 15, 0)
         assert rep.iterations == 15
@@ -195,6 +199,8 @@ def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
     for kern in (3, 30, 1, 2):
         for a, b in zip(gam[0], gam[kern]):
             assert np.array_equal(a, b)
+    assert relerr(gam[32][0], gam[0][0]) < 1e-9 and relerr(gam[32][1], gam[0][1]) < 1e-9
+    np.testing.assert_allclose(gam[32][2][:, 3:5], gam[0][2][:, 3:5], rtol=1e-8)
     # ... and a long run on the record kernels: rows leave and re-enter the live set many times
     for kern in (3, 30, 0):
         select(kern)
@@ -203,7 +209,7 @@ def test_force_kernels_agree_bit_for_bit(ctx, oracle, colbuf, zero_frac):
     for kern in (3, 30):
         for a, b in zip(gam[0], gam[kern]):
             assert np.array_equal(a, b)
-    select(3)
+    select(32)  # back to the defaults
 
 
 def test_bbpgd_matches_oracle_iterates(ctx, oracle):
