@@ -1567,7 +1567,6 @@ struct TailRow {
     double2 xg;
     unsigned char bi;
     int2 sl;     // slot records of the row's two sides (force_kernel = 3)
-    unsigned mw; // the row's word of the previous iteration's mask
     unsigned char own; // multi-rank: this rank counts the row in the dot products (streamed with the row, not at use)
 };
 __device__ __forceinline__ unsigned char ldStreamU8(const unsigned char *p) {
@@ -1592,9 +1591,6 @@ __device__ __forceinline__ void loadTailRow(const BbTail &p, size_t k, TailRow &
             const int2 *sp = p.cSlot + k;
             asm volatile("ld.global.cs.v2.s32 {%0, %1}, [%2];" : "=r"(r.sl.x), "=r"(r.sl.y) : "l"(sp));
         }
-        // the row's mask word of the previous iteration: written by the previous tail kernel (two kernels ago: safe before
-        // pdlWait), overwritten further down by this very warp; plain load (the array is written by this kernel)
-        asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(r.mw) : "l"(p.maskOut + (k >> 5)));
     }
 }
 
@@ -1607,6 +1603,31 @@ __device__ __forceinline__ void loadTailRow(const BbTail &p, size_t k, TailRow &
 // 8 B/row are skipped.
 // one row of the tail: x = P(x_prev - alpha g_prev), y = row k of D^T times U (+ K^-1 x), g = y + b, the row's share of the
 // residual and of the BB dot products; stores {x, g}; returns the row's "may be non-zero next time" bit
+// a row's liveness flipped: its two slot bits in the slot-ordered bitmap and, for a slot among the first 32 of its rod, in
+// the rod's header.  Out of line: a few thousand rows per launch take this path, and k_bb_tail's loop is at its register limit.
+// (pointers, not the parameter struct: a reference to it would put a copy of all kernel parameters on the stack)
+__device__ __noinline__ void tailFlipBits(int2 *head, unsigned *slotLive, int sI, int sJ, int iI, int iJ, bool on) {
+    const int jI = sI >= 0 ? sI - head[iI].x : 32, jJ = sJ >= 0 ? sJ - head[iJ].x : 32;
+    unsigned *hI = reinterpret_cast<unsigned *>(&head[iI].y);
+    unsigned *hJ = reinterpret_cast<unsigned *>(&head[sJ >= 0 ? iJ : iI].y);
+    if (on) {
+        if (sI >= 0) atomicOr(slotLive + (sI >> 5), 1u << (sI & 31));
+        if (sJ >= 0) atomicOr(slotLive + (sJ >> 5), 1u << (sJ & 31));
+        if (jI < 32) atomicOr(hI, 1u << jI);
+        if (jJ < 32) atomicOr(hJ, 1u << jJ);
+    } else {
+        if (sI >= 0) atomicAnd(slotLive + (sI >> 5), ~(1u << (sI & 31)));
+        if (sJ >= 0) atomicAnd(slotLive + (sJ >> 5), ~(1u << (sJ & 31)));
+        if (jI < 32) atomicAnd(hI, ~(1u << jI));
+        if (jJ < 32) atomicAnd(hJ, ~(1u << jJ));
+    }
+}
+
+__device__ __noinline__ void tailFlipRow(int2 *head, unsigned *slotLive, const int2 *cSlot, long long k, int iI, int iJ, bool on) {
+    const int2 sl = cSlot[k];
+    tailFlipBits(head, slotLive, sl.x, sl.y, iI, iJ, on);
+}
+
 template <bool HASK>
 __device__ __forceinline__ bool tailRowMath(const BbTail &p, const TailRow &cur, bool two, long long k, double alpha,
                                             const double2 &a, const double2 &b, const double2 &c, const double2 &d,
@@ -1648,34 +1669,20 @@ __device__ __forceinline__ bool tailRowMath(const BbTail &p, const TailRow &cur,
     // g >= 0 stays exactly 0 whatever alpha_next turns out to be -- its bit is 0.  NaN counts as "may be non-zero".
     const bool on = cur.bi != 0 || !(x == 0.0) || !(gk >= 0.0);
     if (p.slotLive) { // for k_force_vel_rec: the slot bitmap, and (rec_mode 0) the pair it will take its multiplier from
-        const bool was0 = (cur.mw >> ((unsigned)k & 31u)) & 1u;
-        int sI = cur.sl.x, sJ = cur.sl.y;
-        if (!p.rec && on != was0) { // rec_mode 1: the slots of the few rows whose bit flips are gathered here
-            const int2 sl = p.cSlot[k];
-            sI = sl.x; sJ = sl.y;
-        }
-        if (on && p.rec) {
-            // the whole first 32-byte sector of the record {x, g, col[0], col[1]} = {x, g, +-n_x, +-n_y} in ONE 256-bit store
-            // (sm_100): a full-sector write needs no read-for-merge in L2, a 16-byte one would
-            if (sI >= 0) st256(p.rec + 8 * (size_t)sI, x, gk, gx, gy);
-            if (sJ >= 0) st256(p.rec + 8 * (size_t)sJ, x, gk, -gx, -gy);
-        }
-        if (on != was0) {
-            // position of the slot inside its rod's list: the first 32 live bits of a rod sit in its header
-            const int jI = sI >= 0 ? sI - p.head[cur.iI].x : 32, jJ = sJ >= 0 ? sJ - p.head[cur.iJ].x : 32;
-            unsigned *hI = reinterpret_cast<unsigned *>(&p.head[cur.iI].y);
-            unsigned *hJ = reinterpret_cast<unsigned *>(&p.head[sJ >= 0 ? cur.iJ : cur.iI].y);
+        // the row's bit of the previous iteration is a function of what this row has just read: {x_prev, g_prev} (k_bb_init
+        // applies the same rule to the initial guess, with g = 0)
+        const bool was0 = cur.bi != 0 || !(xp == 0.0) || !(gp >= 0.0);
+        if (p.rec) { // rec_mode 0: the slots came with the row
+            const int sI = cur.sl.x, sJ = cur.sl.y;
             if (on) {
-                if (sI >= 0) atomicOr(p.slotLive + (sI >> 5), 1u << (sI & 31));
-                if (sJ >= 0) atomicOr(p.slotLive + (sJ >> 5), 1u << (sJ & 31));
-                if (jI < 32) atomicOr(hI, 1u << jI);
-                if (jJ < 32) atomicOr(hJ, 1u << jJ);
-            } else {
-                if (sI >= 0) atomicAnd(p.slotLive + (sI >> 5), ~(1u << (sI & 31)));
-                if (sJ >= 0) atomicAnd(p.slotLive + (sJ >> 5), ~(1u << (sJ & 31)));
-                if (jI < 32) atomicAnd(hI, ~(1u << jI));
-                if (jJ < 32) atomicAnd(hJ, ~(1u << jJ));
+                // the whole first 32-byte sector of the record {x, g, col[0], col[1]} = {x, g, +-n_x, +-n_y} in ONE 256-bit
+                // store (sm_100): a full-sector write needs no read-for-merge in L2, a 16-byte one would
+                if (sI >= 0) st256(p.rec + 8 * (size_t)sI, x, gk, gx, gy);
+                if (sJ >= 0) st256(p.rec + 8 * (size_t)sJ, x, gk, -gx, -gy);
             }
+            if (on != was0) tailFlipBits(p.head, p.slotLive, sI, sJ, cur.iI, cur.iJ, on);
+        } else if (on != was0) { // rec_mode 1 / 2: the slots of the few rows whose bit flips are gathered out of line
+            tailFlipRow(p.head, p.slotLive, p.cSlot, k, cur.iI, cur.iJ, on);
         }
     }
     return on;
@@ -1956,13 +1963,13 @@ __global__ void k_mask_from_x(long long nc, const double *__restrict__ x, const 
 
 // BBPGD keeps its iterates as interleaved {x, g} pairs: start from x0, and unpack the two newest iterates afterwards
 __global__ void k_bb_init(long long nc, const double *__restrict__ x0, double2 *__restrict__ xg,
-                          unsigned *__restrict__ mask) {
+                          unsigned *__restrict__ mask, const unsigned char *__restrict__ bi) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool on = false;
     if (k < nc) {
         const double x = x0[k];
         xg[k] = make_double2(x, 0.0);
-        on = !(x == 0.0);
+        on = !(x == 0.0) || bi[k] != 0; // k_bb_tail's rule for "may be non-zero next time" at {x0, g = 0}
     }
     const unsigned m = __ballot_sync(0xffffffffu, on); // rows of the initial guess that can contribute to D x0
     if ((threadIdx.x & 31) == 0 && k < nc && mask) mask[k >> 5] = m;
@@ -2741,7 +2748,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
     c.pdlNow = (!multi || fused) && c.optPdl && c.incLayout != 0;
     // iteration 0: g0 = A x0 + b, {x0, g0} written in place
     if (nc > 0) {
-        k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, XG[0], c.vMask.p);
+        k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, XG[0], c.vMask.p, c.cBi.p);
         c.launches++;
     }
     t.ite = 0; t.xgPrev = XG[0]; t.xgOut = XG[0];
@@ -2894,7 +2901,7 @@ double timeKernel(Context &c, int which, int reps) {
     c.vXG0.reserve((size_t)nc + 1);
     c.vXG1.reserve((size_t)nc + 1);
     c.vMask.reserve((size_t)(nc >> 5) + 2);
-    k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, c.vXG0.p, c.vMask.p);
+    k_bb_init<<<grid, kVecBlock, 0, st>>>(nc, c.vX0.p, c.vXG0.p, c.vMask.p, c.cBi.p);
     BbTail t{};
     t.nc = nc; t.g = conGeom(c); t.U = c.rU.p; t.b = c.vB.p; t.invKdt = c.vTmp5.p; t.bi = c.cBi.p;
     t.partial = c.redPartial.p; t.scal = c.dScal.p; t.hist = c.dHist.p; t.histCap = 0; t.tol = -1.0;

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q -x --durations=3 2>&1 | tail -30 > gpurun_out/r2q_pytest.txt; tail -8 gpurun_out/r2q_pytest.txt
-for o in "rec_mode=2" "rec_mode=1" "rec_mode=0"; do
+for o in "rec_mode=2" "rec_mode=0"; do
   ALENS_OPTIONS="$o" timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --stamps 2> gpurun_out/r2q_err.txt | tail -1 > "gpurun_out/r2q_$o.json"
   python - "$o" <<'PY'
 import json,sys
