@@ -364,6 +364,7 @@ __global__ void k_inc_emit_rm(int nRods, const int *__restrict__ start, int *__r
 // be non-zero is refreshed by k_bb_tail every iteration, which also keeps the slot-ordered bitmap slotLive up to date.
 // The force kernel then needs no constraint ids at all: bitmap word -> one aligned 64-byte record per live slot.
 // cSlot[k] = (slot of row k in rod I's list, slot in rod J's list), -1 where the side has no slot (one-sided, ghost rod).
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d); // 256-bit store, below
 // mobRec != nullptr (rec_mode 2): the record holds M_rod * column instead of the column, so that the force kernel adds up
 // the rod's VELOCITY directly (u = sum_s (M c_s) x_s) and never reads the rod's mobility data.
 __global__ void k_inc_emit_rec(int nRods, const int *__restrict__ start, int *__restrict__ incCon, ConGeom g,
@@ -417,11 +418,9 @@ __global__ void k_inc_emit_rec(int nRods, const int *__restrict__ start, int *__
             c2 = iPara * az + iPerp * (c2 - az);
             c3 = iRot * c3; c4 = iRot * c4; c5 = iRot * c5;
         }
-        double2 *o = reinterpret_cast<double2 *>(rec + 8 * (size_t)p);
-        o[0] = make_double2(__longlong_as_double((long long)k2), 0.0); // rec_mode 1/2: the slot code; rec_mode 0: {x, g} later
-        o[1] = make_double2(c0, c1);
-        o[2] = make_double2(c2, c3);
-        o[3] = make_double2(c4, c5);
+        // two 256-bit stores = two full 32-byte sectors (rec_mode 1/2: the slot code in front; rec_mode 0: {x, g} go there later)
+        st256(rec + 8 * (size_t)p, __longlong_as_double((long long)k2), 0.0, c0, c1);
+        st256(rec + 8 * (size_t)p + 4, c2, c3, c4, c5);
         if (sideJ) cSlot[kk].y = p;
         else cSlot[kk].x = p;
         if (k2 & 2) atomicOr(slotBi + (p >> 5), 1u << (p & 31));
@@ -1218,6 +1217,8 @@ __global__ void __launch_bounds__(128) k_force_vel_rec(FvRec in, MobIn mob, doub
             u1 = make_double2(iPara * pz + iPR.x * (f[2] - pz), iPR.y * f[3]);
             u2 = make_double2(iPR.y * f[4], iPR.y * f[5]);
         }
+        // (not storing a row that is zero and stays zero -- 45 % of the rods -- was measured: 2 us slower, the state bit costs
+        // more than the 22 MB of stores it saves)
         double2 *Up = reinterpret_cast<double2 *>(U + 6 * (size_t)r);
         Up[0] = u0; Up[1] = u1; Up[2] = u2;
         if (WRITE_F) {
@@ -2729,7 +2730,13 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
             launchTail(c, t, gridTail);
             return;
         }
-        launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p);
+        if (!multi && (c.optHaloDebug & 4)) { // timing experiment: the HALO instantiation without any neighbour
+            HaloPush fake{};
+            fake.on = 1;
+            launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p, &fake);
+        } else {
+            launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p);
+        }
         if (multi) commPushU(c, ++c.comm.seqHalo);
         launchTail(c, t, gridTail);
         if (multi) {
