@@ -18,7 +18,7 @@ static_assert(sizeof(alens_constraint_block) == 272, "ConstraintBlock layout");
 
 struct AppendIn {
     const int *uI, *uJ, *gidI, *gidJ;
-    const unsigned char *oneSide, *bi;
+    const unsigned char *oneSide, *bi, *own;
     const double *delta0, *gamma, *kappa;
     const double *vec; // [15][n]: n(3) pI(3) pJ(3) labI(3) labJ(3)
     long long n;
@@ -43,7 +43,7 @@ __global__ void k_append(AppendIn in, ConOut o, const int *__restrict__ userToSo
     o.shift[k] = 13;
     o.bi[k] = in.bi[i];
     o.oneSide[k] = in.oneSide[i];
-    o.own[k] = 1;
+    o.own[k] = in.own[i]; // 0: rod I is a ghost here, the row is counted by the rank that owns it
     o.delta0[k] = in.delta0[i];
     o.gamma0[k] = in.gamma[i];
     const double kap = in.kappa[i];
@@ -58,18 +58,22 @@ __global__ void k_append(AppendIn in, ConOut o, const int *__restrict__ userToSo
     }
 }
 
-void appendBlocks(Context &c, const alens_constraint_block *b, long long n) {
+// userIdx (optional): 2 n user indices (I, J) into this rank's rod arrays, ghosts included -- the device-side block
+// generators know them; host-generated blocks are addressed by globalIndex and must refer to owned rods
+void appendBlocks(Context &c, const alens_constraint_block *b, long long n, const int *userIdx) {
     if (!c.sorted) throw ArgError{ALENS_ERR_STATE, "alens_append_constraints: call alens_set_rods first"};
     if (n <= 0) return;
     const int off = c.globalBase; // rank offset of globalIndex (SylinderSystem.cpp:868-880)
     std::vector<int> uI(n), uJ(n), gI(n), gJ(n);
-    std::vector<unsigned char> one(n), bi(n);
+    std::vector<unsigned char> one(n), bi(n), own(n);
     std::vector<double> d0(n), gm(n), kp(n), vec(15 * (size_t)n);
     for (long long i = 0; i < n; i++) {
         const alens_constraint_block &q = b[i];
-        const int li = q.globalIndexI - off, lj = q.globalIndexJ - off;
-        if (li < 0 || li >= c.nLocal || (!q.oneSide && (lj < 0 || lj >= c.nLocal)))
+        const int li = userIdx ? userIdx[2 * i] : q.globalIndexI - off, lj = userIdx ? userIdx[2 * i + 1] : q.globalIndexJ - off;
+        const int lim = userIdx ? c.nRods : c.nLocal;
+        if (li < 0 || li >= lim || (!q.oneSide && (lj < 0 || lj >= lim)))
             throw ArgError{ALENS_ERR_ARG, "alens_append_constraints: globalIndex out of range"};
+        own[i] = li < c.nLocal ? 1 : 0;
         if (!q.oneSide)
             for (int k = 0; k < 3; k++)
                 if (q.normJ[k] != -q.normI[k])
@@ -89,18 +93,18 @@ void appendBlocks(Context &c, const alens_constraint_block *b, long long n) {
     cudaStream_t st = c.stream;
     reserveConstraints(c, (size_t)(c.nCon + n), true);
     DevBuf<int> dI, dJ, dgI, dgJ;
-    DevBuf<unsigned char> dOne, dBi;
+    DevBuf<unsigned char> dOne, dBi, dOwn;
     DevBuf<double> dD0, dGm, dKp, dVec;
-    dI.reserve(n); dJ.reserve(n); dgI.reserve(n); dgJ.reserve(n); dOne.reserve(n); dBi.reserve(n);
+    dI.reserve(n); dJ.reserve(n); dgI.reserve(n); dgJ.reserve(n); dOne.reserve(n); dBi.reserve(n); dOwn.reserve(n);
     dD0.reserve(n); dGm.reserve(n); dKp.reserve(n); dVec.reserve(15 * (size_t)n);
     auto up = [&](void *d, const void *h, size_t bytes) {
         ALENS_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
     };
     up(dI.p, uI.data(), 4 * n); up(dJ.p, uJ.data(), 4 * n); up(dgI.p, gI.data(), 4 * n); up(dgJ.p, gJ.data(), 4 * n);
-    up(dOne.p, one.data(), n); up(dBi.p, bi.data(), n);
+    up(dOne.p, one.data(), n); up(dBi.p, bi.data(), n); up(dOwn.p, own.data(), n);
     up(dD0.p, d0.data(), 8 * n); up(dGm.p, gm.data(), 8 * n); up(dKp.p, kp.data(), 8 * n);
     up(dVec.p, vec.data(), 8 * 15 * (size_t)n);
-    AppendIn in{dI.p, dJ.p, dgI.p, dgJ.p, dOne.p, dBi.p, dD0.p, dGm.p, dKp.p, dVec.p, n};
+    AppendIn in{dI.p, dJ.p, dgI.p, dgJ.p, dOne.p, dBi.p, dOwn.p, dD0.p, dGm.p, dKp.p, dVec.p, n};
     ConOut o{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cOwn.p, c.cDelta0.p,
              c.cGamma0.p, c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
     k_append<<<gridFor(n, 256), 256, 0, st>>>(in, o, c.userToSorted.p, c.nCon);
@@ -319,18 +323,28 @@ __device__ __forceinline__ void pbcImage2(double lb, double ub, double &x, doubl
 struct LinkRods {
     const int *userToSorted, *sGid;
     const double *sX, *sY, *sZ, *sDx, *sDy, *sDz, *sLen, *sRad;
-    int globalBase;
+    const int *uGlobalIdx; // global index of every rod of this rank, ghosts included (the owner's numbering)
+    int nLocal;            // user indices >= nLocal are ghost rods (slab decomposition)
+    int multi;
 };
 __global__ void k_links(long long nLinks, const int *__restrict__ prevGid, const int *__restrict__ nextGid,
                         const int *__restrict__ keys, const int *__restrict__ vals, unsigned mask, LinkRods R, Box box,
-                        double linkKappa, double linkGap, alens_constraint_block *__restrict__ out, int *__restrict__ missing) {
+                        double linkKappa, double linkGap, alens_constraint_block *__restrict__ out, int *__restrict__ missing,
+                        int2 *__restrict__ userIdx) {
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nLinks) return;
     const int uI = gidLookup(prevGid[l], keys, vals, mask), uJ = gidLookup(nextGid[l], keys, vals, mask);
-    if (uI < 0 || uJ < 0) {
+    userIdx[l] = make_int2(-1, -1); // "not this rank's link"
+    // Slab decomposition: every rank is handed the whole link map (as every rank of the reference reads it, :377-405).  A
+    // link is this rank's business when it owns at least one of the two rods; the other one is then an owned rod or a
+    // ghost (both ranks build the block from identical rod data, as for a contact across a slab face).
+    const bool ownI = uI >= 0 && uI < R.nLocal, ownJ = uJ >= 0 && uJ < R.nLocal;
+    if (R.multi && !ownI && !ownJ) return;
+    if (uI < 0 || uJ < 0) { // an end is neither owned nor within the ghost layer (single rank: not there at all)
         atomicAdd(missing, 1);
         return;
     }
+    userIdx[l] = make_int2(uI, uJ);
     const int sI = R.userToSorted[uI], sJ = R.userToSorted[uJ];
     const Vec3 cI = v3(R.sX[sI], R.sY[sI], R.sZ[sI]), dI = v3(R.sDx[sI], R.sDy[sI], R.sDz[sI]);
     const Vec3 dJ = v3(R.sDx[sJ], R.sDy[sJ], R.sDz[sJ]);
@@ -359,8 +373,8 @@ __global__ void k_links(long long nLinks, const int *__restrict__ prevGid, const
     q.gamma = delta0 < 0 ? -delta0 : 0;
     q.gidI = R.sGid[sI];
     q.gidJ = R.sGid[sJ];
-    q.globalIndexI = R.globalBase + uI;
-    q.globalIndexJ = R.globalBase + uJ;
+    q.globalIndexI = R.uGlobalIdx[uI];
+    q.globalIndexJ = R.uGlobalIdx[uJ];
     q.oneSide = 0;
     q.bilateral = 1;
     q.kappa = linkKappa;
@@ -381,7 +395,7 @@ long long collectLinks(Context &c, const int *prevGid, const int *nextGid, long 
     if (!prevGid || !nextGid) throw ArgError{ALENS_ERR_ARG, "alens_collect_link_bilateral: NULL gid list"};
     cudaStream_t st = c.stream;
     unsigned size = 64;
-    while (size < 2u * (unsigned)std::max(c.nLocal, 1)) size <<= 1;
+    while (size < 2u * (unsigned)std::max(c.nRods, 1)) size <<= 1;
     DevBuf<int> keys, vals, dPrev, dNext, dMissing;
     keys.reserve(size); vals.reserve(size); dPrev.reserve((size_t)nLinks); dNext.reserve((size_t)nLinks); dMissing.reserve(1);
     {
@@ -393,25 +407,39 @@ long long collectLinks(Context &c, const int *prevGid, const int *nextGid, long 
     }
     ALENS_CUDA(cudaMemcpyAsync(dPrev.p, prevGid, sizeof(int) * (size_t)nLinks, cudaMemcpyHostToDevice, st));
     ALENS_CUDA(cudaMemcpyAsync(dNext.p, nextGid, sizeof(int) * (size_t)nLinks, cudaMemcpyHostToDevice, st));
-    if (c.nLocal > 0)
-        k_gid_table_build<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.uGid.p, keys.p, vals.p, size - 1);
+    const int nTab = c.nRods; // owned rods and, with the slab decomposition, the ghost layer
+    if (nTab > 0) k_gid_table_build<<<gridFor(nTab, 256), 256, 0, st>>>(nTab, c.uGid.p, keys.p, vals.p, size - 1);
     DevBuf<alens_constraint_block> dOut;
+    DevBuf<int2> dIdx;
     dOut.reserve((size_t)nLinks);
+    dIdx.reserve((size_t)nLinks);
     const LinkRods R{c.userToSorted.p, c.sGid.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLen.p, c.sRad.p,
-                     c.globalBase};
+                     c.uGlobalIdx.p, c.nLocal, c.comm.active ? 1 : 0};
     k_links<<<gridFor(nLinks, 128), 128, 0, st>>>(nLinks, dPrev.p, dNext.p, keys.p, vals.p, size - 1, R, c.box, linkKappa,
-                                                  linkGap, dOut.p, dMissing.p);
+                                                  linkGap, dOut.p, dMissing.p, dIdx.p);
     c.launches += 2;
     int missing = 0;
     std::vector<alens_constraint_block> host((size_t)nLinks);
+    std::vector<int2> idx((size_t)nLinks);
     ALENS_CUDA(cudaMemcpyAsync(&missing, dMissing.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     ALENS_CUDA(cudaMemcpyAsync(host.data(), dOut.p, sizeof(alens_constraint_block) * (size_t)nLinks, cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaMemcpyAsync(idx.data(), dIdx.p, sizeof(int2) * (size_t)nLinks, cudaMemcpyDeviceToHost, st));
     ALENS_CUDA(cudaStreamSynchronize(st));
     if (missing)
         throw ArgError{ALENS_ERR_ARG, "alens_collect_link_bilateral: " + std::to_string(missing) +
-                                          " link end(s) refer to a gid this rank does not own"};
-    appendBlocks(c, host.data(), nLinks);
-    return nLinks;
+                                          (c.comm.active ? " link(s) join an owned rod to a rod outside this rank's ghost layer"
+                                                         : " link end(s) refer to a gid this rank does not own")};
+    std::vector<int> user; // links this rank takes part in, in the caller's order
+    user.reserve(2 * (size_t)nLinks);
+    size_t m = 0;
+    for (long long l = 0; l < nLinks; l++) {
+        if (idx[l].x < 0) continue;
+        host[m++] = host[l];
+        user.push_back(idx[l].x);
+        user.push_back(idx[l].y);
+    }
+    if (m) appendBlocks(c, host.data(), (long long)m, user.data());
+    return (long long)m;
 }
 
 // ------------------------------------------------------------------------------------------------

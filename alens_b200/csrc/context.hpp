@@ -355,7 +355,7 @@ void ctxInit(Context &c);
 void ctxFree(Context &c);
 void rodsUploaded(Context &c, bool wrap);           // rod_pack + cell list + sorted SoA
 void collectPairs(Context &c);                      // broad + narrow phase
-void appendBlocks(Context &c, const alens_constraint_block *b, long long n);
+void appendBlocks(Context &c, const alens_constraint_block *b, long long n, const int *userIdx = nullptr);
 void downloadBlocks(Context &c, alens_constraint_block *out, long long cap, bool withStress, bool writeBack);
 void calcMobility(Context &c, double mu);
 void mobilityApply(Context &c, const double *x, double *y);

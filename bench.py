@@ -511,10 +511,11 @@ def main():
     live_rows = tm["op_rows_live"] / max(tm["op_applies"], 1)
     dense_force = 52.0 * ninc + 16.0 * nc + 96.0 * n  # what the dense level-major kernel (force_kernel=0) moves
     if fk == 3 and rec_mode == 2:
-        # records hold M * column: as rec_mode 1 without the mobility line of the rods that have a live slot
+        # records hold M * column: no mobility line; rod header (8 B) + end of the slot range (4 B) per rod instead of the
+        # slot bitmap; 64-byte record + 16-byte {x, g} pair per live slot; ghost flag (1 B) and U row (48 B) per rod
         kern = {"k_force_vel_rec": (tm["op_force_vel_ms"], tm["op_force_vel_n"],
-                                    4.0 * (n + 1) + ninc / 8.0 + 80.0 * live["live_slots"] + 49.0 * n),
-                "k_bb_tail": (tm["op_dtrans_ms"], tm["op_dtrans_n"], 129.0 * nc + nc / 4.0)}
+                                    12.0 * n + 80.0 * live["live_slots"] + 49.0 * n),
+                "k_bb_tail": (tm["op_dtrans_ms"], tm["op_dtrans_n"], 129.0 * nc + nc / 8.0)}
     elif fk == 3 and rec_mode == 1:
         # records hold the row id: + one 16-byte {x, g} gather per live slot; the tail only flips bitmap bits
         kern = {"k_force_vel_rec": (tm["op_force_vel_ms"], tm["op_force_vel_n"],

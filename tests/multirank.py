@@ -48,11 +48,12 @@ def take(rods, idx):
 
 
 def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None, skin=None, axis=0, devices=None,
-              steps=1, want_blocks=True, migrate=False, brown=None):
+              steps=1, want_blocks=True, migrate=False, brown=None, links=None):
     """returns per-rank dicts (idx = global rod indices owned, blocks, gamma, forceU/velU/..., report, history).
     migrate: alens_migrate_rods between stepEuler and prepareStep (the rank's rod set changes: `gid` tells which it holds
     at the end, `migrated` = (sent, received) totals); brown = (kBT, seed): velNonCon = the device's Brownian velocity,
-    keyed by (seed, step, gid) and therefore the same whatever the decomposition"""
+    keyed by (seed, step, gid) and therefore the same whatever the decomposition; links = (prevGid, nextGid, kappa, gap):
+    EVERY rank is handed the whole link map, as every rank of the reference reads it"""
     lo, hi = np.asarray(lo, float), np.asarray(hi, float)
     parts = split_slabs(rods, lo, hi, nranks, axis)
     max_r = float(np.max(0.5 * rods["length"] + rods["radius"]))
@@ -91,6 +92,8 @@ def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None,
                         moved[1] += b
                     c.prepare_step(True)
                 nc = c.collect_pair_collision()
+                if links is not None:
+                    res_r["links_added"] = c.collect_link_bilateral(links[0], links[1], links[2], links[3])
                 c.calc_mobility(mu)
                 if brown is not None:
                     vb = c.calc_velocity_brown(brown[0], dt, None, brown[1], s)

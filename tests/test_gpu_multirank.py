@@ -13,7 +13,7 @@ BLOCK_FIELDS = ("delta0", "gidI", "gidJ", "globalIndexI", "globalIndexJ", "oneSi
                 "normJ", "posI", "posJ", "labI", "labJ")
 
 
-def single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, max_ite, vnc):
+def single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, max_ite, vnc, links=None):
     import alens_b200
 
     c = alens_b200.Context(0)
@@ -21,6 +21,8 @@ def single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, max_ite, vnc):
     c.set_collision_params(1.0, 1.0, colbuf)
     c.set_rods(rods["gid"], rods["pos"], rods["quat"], rods["length"], rods["radius"], rods["immovable"], wrap=True)
     nc = c.collect_pair_collision()
+    if links is not None:
+        c.collect_link_bilateral(links[0], links[1], links[2], links[3])
     c.calc_mobility(mu)
     rep = c.solve_constraints(vnc, dt, res, max_ite, 0)
     out = dict(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), digest=c.constraint_digest(),
@@ -267,3 +269,57 @@ def test_multirank_device_side_rod_migration_tracks_the_single_rank_trajectory(p
         assert dist.max() < 0.5 * w + 0.25
     assert sorted(seen) == list(range(n))  # nobody lost, nobody duplicated
     assert sum(o["migrated"][0] for o in ranks) == sum(o["migrated"][1] for o in ranks) > 20
+
+
+@pytest.mark.parametrize("nranks,pbc", [(2, (1, 1, 1)), (3, (1, 0, 1))])
+def test_multirank_links_across_slab_faces(nranks, pbc, placement):
+    """filaments (rods chained by spring links, SylinderSystem::collectLinkBilateral :1386-1482) that cross slab faces and the
+    periodic box face: every rank gets the whole link map, builds the blocks of the links it owns a rod of (the partner is an
+    owned rod or a ghost), the two copies of a cross-slab link are bit-identical and the solve equals the single-rank one"""
+    rng = np.random.default_rng(4)
+    box, colbuf, mu, dt, res = (4.8, 1.6, 1.6), 0.025, 1.0, 1e-4, 1e-6
+    lo, hi = [0.0, 0.0, 0.0], list(box)
+    L, R, gap = 0.25, 0.0125, 0.03
+    nfil, per = 260, 5
+    from scenarios import quat_from_z_to
+
+    start = rng.uniform(0, 1, size=(nfil, 3)) * np.array(box)
+    d = rng.normal(size=(nfil, 3))
+    d[:, 0] += 1.5 * np.sign(d[:, 0])  # mostly along x: most filaments cross a slab face
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    pos = (start[:, None, :] + d[:, None, :] * ((L + 2 * R + gap) * np.arange(per))[None, :, None]).reshape(-1, 3)
+    n = nfil * per
+    rods = dict(gid=rng.permutation(n).astype(np.int32), pos=pos, quat=np.repeat(quat_from_z_to(d), per, axis=0),
+                length=np.full(n, L), radius=np.full(n, R), immovable=np.zeros(n, dtype=np.uint8))
+    idx = np.arange(n).reshape(nfil, per)
+    prev, nxt = rods["gid"][idx[:, :-1].reshape(-1)], rods["gid"][idx[:, 1:].reshape(-1)]
+    order = np.concatenate(split_slabs(rods, np.asarray(lo), np.asarray(hi), nranks))
+    rods = take(rods, order)
+    links = (prev, nxt, 120.0, 0.02)  # linkGap below the actual gap: the springs pull
+    vnc = thermal_velocity(rods, mu, dt, seed=8)
+    ref = single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, 300, vnc, links=links)
+    ranks = run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, 300, vnc=vnc, devices=_devices(placement, nranks),
+                      links=links)
+    _check_mode(ranks, placement)
+    assert sum(r["links_added"] for r in ranks) > len(prev)  # some links are held by two ranks
+    allb = np.concatenate([r["blocks"] for r in ranks])
+    allb = allb[canonical_order(allb)]
+    same = np.zeros(len(allb), bool)
+    same[1:] = ((allb["gidI"][1:] == allb["gidI"][:-1]) & (allb["gidJ"][1:] == allb["gidJ"][:-1]) &
+                (allb["labJ"][1:] == allb["labJ"][:-1]).all(axis=1))
+    dup = np.nonzero(same)[0]
+    assert (allb["bilateral"][dup] == 1).sum() > 5, "no cross-slab link in the test system"
+    for f in BLOCK_FIELDS + ("gamma", "stress"):
+        assert np.array_equal(allb[f][dup], allb[f][dup - 1]), f"mirrored rows differ in {f}"
+    uniq = allb[~same]
+    want = ref["blocks"][canonical_order(ref["blocks"])]
+    assert len(uniq) == len(want) and (want["bilateral"] == 1).sum() == len(prev)
+    for f in BLOCK_FIELDS:
+        assert np.array_equal(uniq[f], want[f]), f
+    assert {r["report"].iterations for r in ranks} == {ref["report"].iterations}
+    assert np.abs(uniq["gamma"] - want["gamma"]).max() < 1e-9 * np.abs(want["gamma"]).max()
+    for name in ("velU", "forceU", "velB", "forceB"):
+        full = np.zeros_like(ref[name]).reshape(-1, 6)
+        for r in ranks:
+            full[r["idx"]] = r[name].reshape(-1, 6)
+        assert np.abs(full.reshape(-1) - ref[name]).max() < 1e-9 * np.abs(ref[name]).max(), name
