@@ -140,7 +140,10 @@ int alens_collect_boundary_collision(alens_ctx *ctx, const alens_boundary *bound
  * the reference's linkMap) one bilateral block between the plus end of `prev` and the minus end of `next` (true length and
  * radius, nearest periodic image), delta0 = distance - rI - rJ - linkGap, kappa = linkKappa, stress by collideStress.
  * Blocks are appended in link order; the gid -> rod lookup (the reference's ZDD directory) is a device hash table.
- * Both rods of a link must be owned by this rank (links across slabs: push the block with alens_append_constraints). */
+ * One rank: both gids must exist.  Slab decomposition: hand EVERY rank the whole link map (as every rank of the reference
+ * reads it); a rank builds the blocks of the links it owns at least one rod of -- the partner may be a ghost, both owners of a
+ * cross-slab link build the same block -- and skips the others; *nAdded counts the blocks this rank built.  An owned rod whose
+ * partner lies outside the ghost layer (cutoff + skin) is ALENS_ERR_ARG. */
 int alens_collect_link_bilateral(alens_ctx *ctx, const int *prevGid, const int *nextGid, long long nLinks, double linkKappa,
                                  double linkGap, long long *nAdded);
 /* The fields of ProteinData / ProteinBindStatus that TubuleSystem::setProteinConstraints (SRC/TubuleSystem.cpp:694-745)
