@@ -531,6 +531,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
         else if (k == "rec_mode") c.optRecMode = (value < 0 || value > 2) ? 1 : (int)value; // 2: records hold M * column
         else if (k == "stamps") c.optStamps = value != 0;
         else if (k == "halo_debug") c.optHaloDebug = (int)value;
+        else if (k == "tail_push") c.optTailPush = value != 0;
         else if (k == "l2_fetch") { // cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes): a device-wide hint
             ALENS_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
         }

@@ -94,9 +94,11 @@ __global__ void k_ghost_unpack(int n, const double *__restrict__ src, GhostDst o
 }
 
 // after the cell sort: tell the sender where each of its ghosts sits in my sorted arrays
-__global__ void k_ack_indices(int n, const int *__restrict__ userToSorted, int base, int *__restrict__ dstRemote) {
+__global__ void k_ack_indices(int n, const int *__restrict__ userToSorted, int base, int *__restrict__ dstRemote,
+                              int *__restrict__ remoteGhostBase, int ghostBase) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) dstRemote[e] = userToSorted[base + e];
+    if (e == 0) *remoteGhostBase = ghostBase; // where this neighbour's velocities are expected in my U (staging rows)
 }
 __global__ void k_map_indices(int n, const int *__restrict__ list, const int *__restrict__ userToSorted,
                               int *__restrict__ out) {
@@ -145,7 +147,7 @@ void commAllocWindow(Context &c, long long maxLocalRods) {
     if (m.win) throw ArgError{ALENS_ERR_STATE, "comm: window already allocated"};
     if (c.nranks > kMaxRanks) throw ArgError{ALENS_ERR_UNSUPPORTED, "comm: more than 16 ranks"};
     m.capGhost = (size_t)std::max<long long>(maxLocalRods / 3, 4096);
-    m.capRods = (size_t)maxLocalRods + 2 * m.capGhost + 64;
+    m.capRods = (size_t)maxLocalRods + 4 * m.capGhost + 64; // owned + ghost rods, + the ghosts' staging rows of U
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = al(sizeof(CommHeader));
     for (int d = 0; d < 2; d++) { m.offChan[d] = off; off = al(off + m.capGhost * kGhostRec * sizeof(double)); }
@@ -362,9 +364,11 @@ void commExchangeGhostIndices(Context &c) {
         unsigned char *w = nbWin(c, ch);
         if (!w) continue;
         const int dirThere = 1 - ch; // over there I am its right / left neighbour
-        if (m.nRecv[ch] > 0)
-            k_ack_indices<<<gridFor(m.nRecv[ch], 256), 256, 0, st>>>(m.nRecv[ch], c.userToSorted.p, base,
-                                                                    reinterpret_cast<int *>(w + m.offAck[dirThere]));
+        // (always launched: the staging base goes over with the acks.  Ghost g of this rank, user index nLocal + g, has its
+        // velocity expected in row nRods + g of U: contiguous per neighbour, in the neighbour's send order)
+        k_ack_indices<<<std::max(1, gridFor(m.nRecv[ch], 256)), 256, 0, st>>>(
+            m.nRecv[ch], c.userToSorted.p, base, reinterpret_cast<int *>(w + m.offAck[dirThere]),
+            &hdrOf(w)->ghostBase[dirThere], c.nRods + (base - c.nLocal));
         sf[ch] = &hdrOf(w)->ackSeq[dirThere];
         base += m.nRecv[ch];
     }
@@ -385,6 +389,7 @@ void commExchangeGhostIndices(Context &c) {
     }
     c.launches += 8;
     ALENS_CUDA(cudaGetLastError());
+    ALENS_CUDA(cudaMemcpyAsync(m.pushBase, me->ghostBase, sizeof(m.pushBase), cudaMemcpyDeviceToHost, st));
     ALENS_CUDA(cudaStreamSynchronize(st));
     checkCommError(c);
 }

@@ -141,6 +141,9 @@ struct CommHeader {
     // rod migration (commMigrate): every rank publishes its new number of owned rods to every rank
     unsigned long long cntSeq[kMaxRanks];
     long long cnt[kMaxRanks];
+    // written by my left / right neighbour with its index acks: the row of ITS rod-velocity vector where the velocities of the
+    // rods I mirror over there are expected, contiguous and in my send order (tail_push)
+    int ghostBase[2];
 };
 
 struct CommBlob { // what a rank publishes to its peers (multi-process bootstrap)
@@ -183,6 +186,7 @@ struct Comm {
     bool fused = false;        // every rank has its own device: kernels may wait on peers (see solver.cu)
     int devOfRank[kMaxRanks] = {};
     int nSend[2] = {0, 0}, nRecv[2] = {0, 0};
+    int pushBase[2] = {0, 0}; // CommHeader::ghostBase as read back after the ack exchange
 };
 
 struct Context {
@@ -273,6 +277,7 @@ struct Context {
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 3;                 // 3 = k_force_vel_rec (64-byte slot records + slot-ordered live bitmap kept by k_bb_tail), 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
     int optUWindow = 0; // experiment: see setupConstraints
+    int optTailPush = 0;  // fused multi-GPU, measured alternative (slower): the tail kernel instead of the force kernel copies the mirrored rows of U to the neighbours (contiguous staging rows)
     int optHaloDebug = 0; // timing experiments only (results are wrong): 1 = no remote U stores, 2 = no fence + ticket
     int optStamps = 0, stampCap = 0, stampIters = 0; // per-iteration nanosecond stamps of the BBPGD kernels (instrumentation)
     DevBuf<unsigned long long> dStamps;
@@ -281,6 +286,7 @@ struct Context {
     int optRecMode = 2, recMode = 2;        // force_kernel 3: 0 = k_bb_tail copies {x, g} into the slot records, 1 = the records hold the row id and k_force_vel_rec gathers {x, g} itself, 2 = as 1 with M * column in the record (no mobility read)
     DevBuf<double> incRec;                  // force_kernel 3: 8 doubles per slot {x, g, D column block[6]}, 64-byte aligned records
     DevBuf<int2> cSlot;                     // ... per constraint: slot of its I side / J side (-1: none, ghost or one-sided)
+    DevBuf<int> cIdxIU, cIdxJU; // fused multi-GPU: the rod rows the tail kernel gathers U from (ghost rods: the staging rows behind nRods)
     DevBuf<int2> rodHead; // force_kernel 3: per rod {first slot, live bits of its first 32 slots}
     DevBuf<unsigned> slotBi;                // ... bit per slot: the slot's constraint is bilateral (constant during a solve)
     int optFindSplitMinB = 8;               // ... resident CTAs per SM of its stage-1/2 kernel (8: 64 registers)

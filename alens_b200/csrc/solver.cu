@@ -7,13 +7,17 @@
 //
 // D is never materialised as CSR.  A constraint k stores (n, posI, posJ, idxI, idxJ); row k of D^T is
 // [n, posI x n] on rod I and [-n, posJ x (-n)] on rod J (ConstraintCollector.cpp:298-341 with normJ = -normI).
-//   k_force_vel_act : f = D x over the rod -> constraint incidence (rod-major slots, 48-byte column records), touching
-//                 only the slots whose multiplier can be non-zero (bit mask from k_bb_tail); u = M f applied analytically
-//                 from (q, 1/drag) -- one launch per operator apply.  Inside the BBPGD loop x is not read but recomputed
-//                 on the fly as P(x_prev - alpha g_prev) from the interleaved {x, g} pairs.  (k_force_vel_lm: the dense
-//                 level-major predecessor, force_kernel = 0; k_slot_x + k_rod_sum: a two-kernel form, force_kernel = 2.)
+//   k_force_vel_rec : f = D x and u = M f over the rod -> constraint incidence, touching only the slots whose multiplier can
+//                 be non-zero: thread per rod, rod header {first slot, live bits} -> one 64-byte record per live slot
+//                 {row id, M * column} + the row's {x, g} pair; the sums are the rod's velocity (force_kernel = 3,
+//                 rec_mode = 2: the default; rec_mode 0 / 1 keep the plain column and apply M from (q, 1/drag)).  One
+//                 launch per operator apply.  Inside the BBPGD loop x is not read but recomputed on the fly as
+//                 P(x_prev - alpha g_prev) from the interleaved {x, g} pairs.  Predecessors kept as cross-checks:
+//                 k_force_vel_act (rod-major slots + row mask, force_kernel = 1), k_slot_x + k_rod_sum (2), the dense
+//                 level-major k_force_vel_lm (0).
 //   k_bb_tail   : x = P(x_prev - alpha g_prev) again (same arithmetic, same bits), y = D^T u + K^-1 x, g = y + b,
-//                 projected-gradient residual, BB dot products, the may-be-non-zero bit of every row, deterministic
+//                 projected-gradient residual, BB dot products, the may-be-non-zero bit of every row (and the flips of
+//                 the slot bits / rod headers k_force_vel_rec reads), deterministic
 //                 two-level reduction, step-size/termination logic (and, multi-GPU, the mailbox allreduce) in the last
 //                 CTA.  One BBPGD iteration = these two launches, chained with programmatic dependent launch; the host
 //                 follows the loop through two progress words in pinned memory.
@@ -1507,6 +1511,15 @@ struct BbTail {
     const int2 *cSlot;
     unsigned *slotLive;
     int2 *head;               // rod headers: the live bits of a rod's first 32 slots are flipped there as well
+    // fused multi-GPU, tail_push: the rows of U mirrored on the neighbours are copied into their windows HERE, by every CTA
+    // before its first row (two entries per thread), instead of by the force kernel that computes them: remote stores
+    // issued from the force kernel cost it 8 us, here they overlap the 70 us of rows that need no halo
+    const int *pushSrc[2];    // my sorted rod rows that are mirrored on the left / right neighbour
+    int pushBase[2];          // first staging row over there: entry e goes to row pushBase + e (contiguous remote writes)
+    int pushN[2];
+    double *pushRem[2];       // the neighbours' U
+    unsigned long long *pushFlag[2];
+    unsigned int *pushTicket;
     unsigned long long *stamp; // 8 words of this iteration (nullptr: off)
     const unsigned char *own; // multi-rank: 1 = this rank counts the row in the dot products (nullptr = all)
     double *redOut;           // multi-rank: the reduced partials go here, k_bb_reduce finishes the step
@@ -1789,12 +1802,45 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
     if (p.pdlTrig) pdlLaunchDependents();
     if (done) return;
     if (p.stamp && threadIdx.x == 0) atomicMin(p.stamp + 3, globalNs());
+    // Mirrored rows of U -> the neighbours' windows: the remote stores are issued now and drain while this CTA works on its
+    // first rows; the fence + ticket that lets the last CTA release the neighbours' halo flags comes kPushTrips trips later
+    // (a fence right here waits ~25 us for the burst of remote writes), and in any case before this CTA waits for ITS halo.
+    bool pushed = false;
+    int pushTrip = p.pushTicket ? 0 : -1; // -1: nothing (more) to finish
+    if (p.pushTicket) {
+#pragma unroll
+        for (int d = 0; d < 2; d++)
+            for (int e = blockIdx.x * kVecBlock + threadIdx.x; e < p.pushN[d]; e += gridDim.x * kVecBlock) {
+                const double2 *src = reinterpret_cast<const double2 *>(p.U + 6 * (size_t)__ldg(p.pushSrc[d] + e));
+                double2 *dst = reinterpret_cast<double2 *>(p.pushRem[d] + 6 * (size_t)(p.pushBase[d] + e));
+                const double2 a = src[0], b = src[1], c = src[2];
+                dst[0] = a; dst[1] = b; dst[2] = c;
+                pushed = true;
+            }
+    }
+    auto finishPush = [&]() { // CTA-uniform
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned tk = atomicAdd(p.pushTicket, 1u);
+            if (tk == gridDim.x - 1) {
+                *p.pushTicket = 0;
+                __threadfence_system();
+                if (p.pushFlag[0]) stReleaseSys(p.pushFlag[0], p.waitSeq);
+                if (p.pushFlag[1]) stReleaseSys(p.pushFlag[1], p.waitSeq);
+                if (p.stamp) p.stamp[1] = globalNs();
+            }
+        }
+        pushTrip = -1;
+    };
+    constexpr int kPushTrips = 10;
     bool waited = p.waitSeq == 0;
     const int lane = threadIdx.x & 31;
     int nMaybe = 0; // rows of this warp whose bit is set (statistics for the roofline accounting of the force kernel)
     const unsigned long long keepPol = policyEvictLast();
     while (tau < nTiles) {
-        if (!waited && tau >= nClean) { // ghost rows of U: pushed by the neighbours' force kernels (CTA-uniform test)
+        if (pushTrip >= 0 && (++pushTrip > kPushTrips || (!waited && tau >= nClean))) finishPush();
+        if (!waited && tau >= nClean) { // ghost rows of U: pushed by the neighbours (CTA-uniform test)
             if (threadIdx.x < 2) { // one thread per neighbour: the two polls overlap
                 if (p.stamp) atomicMin(p.stamp + 4, globalNs());
                 if (p.waitFlag[threadIdx.x]) waitSeq(p.waitFlag[threadIdx.x], p.waitSeq, p.red.err);
@@ -1830,6 +1876,7 @@ __global__ void __launch_bounds__(kVecBlock, 2) k_bb_tail(BbTail p) {
         tauN = tauNN;
         tileN = tileNN;
     }
+    if (pushTrip >= 0) finishPush(); // (a CTA with fewer trips, or none)
     tailEpilogue(p, s0, s1, s2, mx, nMaybe);
 }
 
@@ -2138,6 +2185,17 @@ static size_t mobStride(int n) { return ((size_t)n + 3) & ~(size_t)1; }
 static MobIn mobIn(Context &c) {
     return MobIn{c.sDx.p, c.sDy.p, c.sDz.p, c.sInvDrag.p, c.sMobRec.p, c.nRods, mobStride(c.nRods), c.sGhost.p};
 }
+// fused multi-GPU with tail_push: the tail kernel gathers a ghost rod's velocity from the staging rows behind the sorted rods
+// (row nRods + g for ghost g = user index nLocal + g), where the neighbour's tail kernel writes them contiguously
+__global__ void k_remap_ghost_rows(long long nc, const int *__restrict__ idxI, const int *__restrict__ idxJ,
+                                   const unsigned char *__restrict__ ghost, const int *__restrict__ sUser, int nLocal, int nRods,
+                                   int *__restrict__ outI, int *__restrict__ outJ) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    const int i = idxI[k], j = idxJ[k];
+    outI[k] = ghost[i] ? nRods + (sUser[i] - nLocal) : i;
+    outJ[k] = (j >= 0 && ghost[j]) ? nRods + (sUser[j] - nLocal) : j;
+}
 static ConGeom conGeom(Context &c) { return ConGeom{c.cIdxI.p, c.cIdxJ.p, c.cN.p, c.cPI.p, c.cPJ.p, c.conCap}; }
 static FvIn fvIn(Context &c) {
     return FvIn{c.incStart.p, c.incCon.p, c.incCol.p, (size_t)c.incStride, c.nRods};
@@ -2343,7 +2401,11 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
                                                                  m.right >= 0 ? m.mirror[1].p : nullptr, c.rodFlag.p);
             k_tile_order<<<1, 1024, 0, st>>>(nTiles, c.tailFlag.p, 0, c.tailOrder.p);
             k_tile_order<<<1, 1024, 0, st>>>(nRodTiles, c.rodFlag.p, 1, c.rodOrder.p);
-            c.launches += 3;
+            c.cIdxIU.reserve((size_t)nc + 32);
+            c.cIdxJU.reserve((size_t)nc + 32);
+            k_remap_ghost_rows<<<gridFor(nc, 256), 256, 0, st>>>(nc, c.cIdxI.p, c.cIdxJ.p, c.sGhost.p, c.sUser.p, c.nLocal,
+                                                               c.nRods, c.cIdxIU.p, c.cIdxJU.p);
+            c.launches += 4;
         }
         c.launches += 3;
     }
@@ -2708,7 +2770,21 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
             }
             hp.on = 1;
             hp.debug = c.optHaloDebug;
-            if (c.incLayout != 0) { // the force kernel releases the neighbours' halo flags itself (last CTA)
+            const bool tailPush = c.incLayout == 3 && c.optTailPush;
+            if (tailPush) { // the tail kernel copies the mirrored rows and releases the flags (see BbTail::pushSrc)
+                for (int d = 0; d < 2; d++) {
+                    const int q = d == 0 ? m.left : m.right;
+                    t.pushN[d] = q < 0 ? 0 : m.nSend[d];
+                    t.pushSrc[d] = m.sendSorted[d].p;
+                    t.pushBase[d] = m.pushBase[d];
+                    t.pushRem[d] = q < 0 ? nullptr : reinterpret_cast<double *>(m.peerWin[q] + m.offU);
+                    t.pushFlag[d] = q < 0 ? nullptr : &reinterpret_cast<CommHeader *>(m.peerWin[q])->haloSeq[1 - d];
+                }
+                t.pushTicket = &c.dScal.p->ticketFv;
+                t.g.idxI = c.cIdxIU.p; // ghost rods: the staging rows
+                t.g.idxJ = c.cIdxJU.p;
+                launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p);
+            } else if (c.incLayout != 0) { // the force kernel releases the neighbours' halo flags itself (last CTA)
                 for (int d = 0; d < 2; d++) {
                     const int q = d == 0 ? m.left : m.right;
                     hp.flag[d] = q < 0 ? nullptr : &reinterpret_cast<CommHeader *>(m.peerWin[q])->haloSeq[1 - d];
@@ -2720,7 +2796,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
                     hp.nBoundary = c.rodOrder.p + gridFor(c.nRods, 128); // k_tile_order: order[nTiles] = flagged tiles
                 }
             }
-            launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p, &hp);
+            if (!tailPush) launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p, &hp);
             if (c.incLayout == 0) commSignalHalo(c, seq);
             t.waitFlag[0] = m.left >= 0 ? &me->haloSeq[0] : nullptr;
             t.waitFlag[1] = m.right >= 0 ? &me->haloSeq[1] : nullptr;
