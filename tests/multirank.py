@@ -48,7 +48,7 @@ def take(rods, idx):
 
 
 def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None, skin=None, axis=0, devices=None,
-              steps=1, want_blocks=True, migrate=False, brown=None, links=None):
+              steps=1, want_blocks=True, migrate=False, brown=None, links=None, options=None):
     """returns per-rank dicts (idx = global rod indices owned, blocks, gamma, forceU/velU/..., report, history).
     migrate: alens_migrate_rods between stepEuler and prepareStep (the rank's rod set changes: `gid` tells which it holds
     at the end, `migrated` = (sent, received) totals); brown = (kBT, seed): velNonCon = the device's Brownian velocity,
@@ -65,6 +65,8 @@ def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None,
     base = 0
     for r in range(nranks):
         c = alens_b200.Context(device=devices[r], rank=r, nranks=nranks)
+        for k, v in (options or {}).items():
+            c.set_option(k, v)
         c.set_domain(lo, hi, pbc)
         c.set_collision_params(1.0, 1.0, colbuf)
         c.set_decomposition(axis, lo[axis] + r * w, lo[axis] + (r + 1) * w, skin, max_r, base)

@@ -323,3 +323,26 @@ def test_multirank_links_across_slab_faces(nranks, pbc, placement):
         for r in ranks:
             full[r["idx"]] = r[name].reshape(-1, 6)
         assert np.abs(full.reshape(-1) - ref[name]).max() < 1e-9 * np.abs(ref[name]).max(), name
+
+
+def test_multirank_tail_push_alternative():
+    """`tail_push = 1`: the tail kernel (not the force kernel) copies the mirrored rows of U into contiguous staging rows of
+    the neighbours' vectors and gathers ghost velocities from its own staging rows -- same results (one rank per GPU only:
+    the fused kernels)"""
+    nranks = 2
+    if gpu_count() < nranks:
+        pytest.skip("needs one GPU per rank")
+    n, box, colbuf, mu, dt, res = 6000, (1.6, 1.6, 4.8), 0.025, 1.0, 1e-4, 1e-6
+    lo, hi, pbc = [0.0, 0.0, 0.0], list(box), (1, 1, 1)
+    rods = slab_ordered(random_rods(n, box, seed=33), lo, hi, nranks, axis=2)
+    vnc = thermal_velocity(rods, mu, dt, seed=5)
+    ref = single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, 200, vnc)
+    ranks = run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, 200, vnc=vnc, axis=2, devices="spread",
+                      options={"tail_push": 1})
+    _check_mode(ranks, "spread")
+    assert {r["report"].iterations for r in ranks} == {ref["report"].iterations}
+    for name in ("velU", "forceU"):
+        full = np.zeros_like(ref[name]).reshape(-1, 6)
+        for r in ranks:
+            full[r["idx"]] = r[name].reshape(-1, 6)
+        assert np.abs(full.reshape(-1) - ref[name]).max() < 1e-9 * np.abs(ref[name]).max(), name
