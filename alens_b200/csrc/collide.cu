@@ -901,9 +901,13 @@ void rodsUploaded(Context &c, bool wrap) {
         // owned rods are wrapped first, then the neighbours' rods near my faces are appended as ghosts
         if (wrap && c.nLocal > 0) k_rod_wrap<<<gridFor(c.nLocal, 256), 256, 0, st>>>(c.nLocal, c.uPos.p, c.box);
         ALENS_CUDA(cudaMemsetAsync(c.dCounters.p, 0, 4 * sizeof(unsigned long long), st));
+        // an open slab axis: the first and the last slab extend to infinity (a rod may leave the box there, as on one rank)
+        const bool openAxis = !c.box.pbc[c.slabAxis];
+        const double ownLo = (openAxis && c.rank == 0) ? -INFINITY : c.slabLo;
+        const double ownHi = (openAxis && c.rank == c.nranks - 1) ? INFINITY : c.slabHi;
         if (c.nLocal > 0)
             k_local_image<<<gridFor(c.nLocal, 256), 256, 0, st>>>(
-                c.nLocal, c.uPos.p, c.slabAxis, c.slabLo, c.slabHi, c.skin, c.box.len[c.slabAxis],
+                c.nLocal, c.uPos.p, c.slabAxis, ownLo, ownHi, c.skin, c.box.len[c.slabAxis],
                 c.box.pbc[c.slabAxis], c.uImg.p, reinterpret_cast<int *>(c.dCounters.p));
         int strays = 0;
         ALENS_CUDA(cudaMemcpyAsync(&strays, c.dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, st));
