@@ -67,7 +67,9 @@ def parse():
     p.add_argument("--cpu-iters", type=int, default=12, help="BBPGD iterations of the fixed-count parity solve")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (and the N = 1 parity check in it)")
     p.add_argument("--no-parity", action="store_true", help="skip the N > 1 digest check")
-    p.add_argument("--stamps", action="store_true", help="one extra (untimed) solve with per-iteration nanosecond stamps")
+    p.add_argument("--stamps", action="store_true", default=True,
+                   help="one extra (untimed) solve with per-iteration nanosecond stamps (default: on)")
+    p.add_argument("--no-stamps", dest="stamps", action="store_false")
     a = p.parse_args()
     if a.phi is None:
         a.phi = 0.40 if a.workload == "S2" else 0.10
@@ -590,6 +592,15 @@ def main():
     }
     if breakdown:
         line["iteration_breakdown_us"] = breakdown
+        # the same algorithmic bytes over the kernels' durations INSIDE the running loop (first to last %globaltimer stamp of a
+        # launch, programmatic dependent launch and warm L2 as in production) next to the event-timed isolated launches above
+        inl = {}
+        for kname, key in (("k_force_vel_rec", "force_us"), ("k_force_vel_act", "force_us"), ("k_bb_tail", "tail_rows_us")):
+            if kname in kern and key in breakdown and breakdown[key]["max_over_ranks"] > 0:
+                us = breakdown[key]["max_over_ranks"]
+                gbps = kern[kname][2] / (us * 1e-6) / 1e9
+                inl[kname] = {"us": us, "GBps": round(gbps, 1), "frac": round(gbps / peak, 4)}
+        line["roofline"]["in_loop"] = inl
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
