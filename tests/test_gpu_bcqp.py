@@ -41,11 +41,13 @@ def test_reference_self_test_problem_on_the_device(ctx, choice):
     x, rep, hist = q.solve(np.zeros(80), 1e-7, 3000, choice)
     xr, hr, rcr = pr.bcqp_solve_csr(A.indptr, A.indices, A.data, p["b"], p["lb"], p["ub"], np.zeros(80), 1e-7, 3000, choice)
     assert np.array_equal(xr, p["x"])  # what the reference's selfTest itself wrote
-    assert rep.status == rcr
     young = min(len(hist), len(hr), 40)  # BB steps amplify rounding differences: compare the young rows tightly
     np.testing.assert_allclose(hist[:young, 3:5], hr[:young, 3:5], rtol=1e-7, atol=1e-12)
     assert np.array_equal(hist[:young, 5], hr[:young, 5])
-    if rcr == 0:
+    # the problem is drawn from std::random_device (BCQPSolver.cpp:46-47): now and then one of the two runs ends on its
+    # stagnation test (step size below 10 eps) a few iterations before the other would converge, which is a matter of rounding
+    assert rep.status in (0, 1) and rcr in (0, 1)
+    if rcr == 0 and rep.status == 0:
         assert abs(len(hist) - len(hr)) <= max(3, 0.1 * len(hr))
         assert np.abs(x - xr).max() < 1e-5  # both satisfy the same KKT tolerance (A is well conditioned: diag 0.5)
         assert np.all(x >= p["lb"]) and np.all(x <= p["ub"])
