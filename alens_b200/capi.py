@@ -39,7 +39,7 @@ EXPORTS = [
     "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest",
     "alens_get_live_stats", "alens_bcqp_create_csr", "alens_bcqp_create_constraint", "alens_bcqp_set_lower_bound",
     "alens_bcqp_set_upper_bound", "alens_bcqp_get_bounds", "alens_bcqp_run", "alens_bcqp_history", "alens_bcqp_size",
-    "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps", "alens_mix_pair_search", "alens_migrate_rods", "alens_get_rod_identity", "alens_set_rod_tags", "alens_get_rod_tags",
+    "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps", "alens_mix_pair_search", "alens_migrate_rods", "alens_get_rod_identity", "alens_set_rod_state", "alens_set_rod_tags", "alens_get_rod_tags",
 ]
 
 
@@ -263,6 +263,16 @@ class Context:
         self._call("alens_set_rods_aos", C.c_int(n), C.c_void_p(buf.ctypes.data), C.c_size_t(stride),
                    C.c_int(1 if wrap else 0))
         self.n_rods = n
+
+    def set_rod_state(self, pos, quat, wrap=True):
+        """positions + orientations of the resident rod set (everything else unchanged since set_rods)"""
+        p = np.ascontiguousarray(pos, dtype=np.float64)
+        q = np.ascontiguousarray(quat, dtype=np.float64)
+        assert len(p.reshape(-1, 3)) == self.n_rods and len(q.reshape(-1, 4)) == self.n_rods
+        self._call("alens_set_rod_state", _dp(p), _dp(q), C.c_int(1 if wrap else 0))
+
+    def set_rod_state_raw(self, pos_p, quat_p, wrap=True):
+        self._call("alens_set_rod_state", C.c_void_p(pos_p), C.c_void_p(quat_p), C.c_int(1 if wrap else 0))
 
     def migrate_rods(self):
         """collective: rods that left the slab move to the neighbour rank; returns (sent, received)"""

@@ -190,6 +190,24 @@ int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, con
     });
 }
 
+int alens_set_rod_state(alens_ctx *ctx, const double *pos, const double *quat, int wrap) {
+    return guarded(ctx, [&](Context &c) {
+        if (!c.haveBox || !c.uPos.p) throw ArgError{ALENS_ERR_STATE, "alens_set_rod_state: call alens_set_rods first"};
+        if (c.nLocal > 0 && (!pos || !quat)) throw ArgError{ALENS_ERR_ARG, "alens_set_rod_state: null input"};
+        cudaStream_t st = c.stream;
+        ALENS_CUDA(cudaEventRecord(c.ev[0], st));
+        const size_t N = (size_t)c.nLocal;
+        if (N > 0) {
+            ALENS_CUDA(cudaMemcpyAsync(c.uPos.p, pos, 24 * N, cudaMemcpyHostToDevice, st));
+            ALENS_CUDA(cudaMemcpyAsync(c.uQuat.p, quat, 32 * N, cudaMemcpyHostToDevice, st));
+        }
+        rodsUploaded(c, wrap != 0);
+        ALENS_CUDA(cudaEventRecord(c.ev[1], st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        c.timers.upload_ms = evMs(c, 0, 1);
+    });
+}
+
 int alens_set_rods_aos(alens_ctx *ctx, int n, const void *sy, size_t stride, int wrap) {
     if (!ctx) return ALENS_ERR_ARG;
     if (n < 0 || (n > 0 && !sy) || stride < 136) {

@@ -410,7 +410,9 @@ def main():
     e2e_out = [h_out[0].data_ptr(), h_out[1].data_ptr(), 0, 0]
 
     def step_e2e():
-        upload()
+        # this step's inputs: positions, orientations and velNonCon.  gids, lengths, radii and immovable flags do not change
+        # from step to step and stay resident (alens_set_rod_state is alens_set_rods without them)
+        ctx.set_rod_state_raw(h_pos.data_ptr(), h_quat.data_ptr(), wrap=True)
         ctx.set_velocity_noncon_async_raw(h_vnc.data_ptr())  # this step's velNonCon: its H2D overlaps the pair search
         nc = ctx.collect_pair_collision()
         ctx.calc_mobility(MU)
@@ -581,9 +583,9 @@ def main():
                    "relaxation": [list(map(int, x)) for x in relax_info],
                    "phase_ms_per_step": {k: round(v / a.steps, 3) for k, v in phase.items()}},
         "e2e": {"value": round(steps_total / (ms_e2e * 1e-3), 3), "unit": "steps/s",
-                "h2d_bytes_per_step": int(n * (4 + 24 + 32 + 8 + 8 + 1 + 48)), "d2h_bytes_per_step": int(n * 2 * 48),
+                "h2d_bytes_per_step": int(n * (24 + 32 + 48)), "d2h_bytes_per_step": int(n * 2 * 48),
                 "ms_per_step": round(ms_e2e / a.steps, 3),
-                "note": "forceUni + velUni come back; the bilateral arrays are identically zero for a collision-only pool"},
+                "note": "up: positions, orientations, velNonCon of the step (gid / length / radius / immovable flag stay resident); down: forceUni + velUni (the bilateral arrays are identically zero for a collision-only pool)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,

@@ -108,6 +108,10 @@ int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, con
                    const double *length, const double *radius, const unsigned char *immovable, int wrapIntoBox);
 /* same from an array of reference `Sylinder` records (568-byte AoS), stride in bytes */
 int alens_set_rods_aos(alens_ctx *ctx, int n, const void *sylinders, size_t stride, int wrapIntoBox);
+/* The per-step form of alens_set_rods for a rod set whose gids, lengths, radii and immovable flags did not change since the
+ * last alens_set_rods: only position and orientation (56 of 77 bytes per rod) cross the bus, the rest of prepareStep
+ * (applyBoxBC, ghost exchange, cell list) runs as usual.  ALENS_ERR_STATE without resident rods. */
+int alens_set_rod_state(alens_ctx *ctx, const double *pos, const double *orientation, int wrapIntoBox);
 /* SylinderSystem::prepareStep on the rods already resident on the device (after alens_step_euler or a
  * previous alens_set_rods): box wrap, cell list, sorted SoA -- no host traffic. */
 int alens_prepare_step(alens_ctx *ctx, int wrapIntoBox);

@@ -202,3 +202,28 @@ def test_equal_gids_never_collide(ctx, oracle):
     o, _ = oracle_collect(oracle, rods, lo, hi, pbc, 0.05, method="brute")
     assert len(o) > 50 and np.all(o["gidI"] < o["gidJ"])
     assert_blocks_equal(g, o)
+
+
+def test_set_rod_state_is_set_rods_without_the_static_fields(ctx, oracle):
+    """alens_set_rod_state: new positions / orientations for the resident rod set -> the same constraint list as a full
+    alens_set_rods of the moved rods"""
+    rng = np.random.default_rng(3)
+    rods = random_rods(3000, 2.0, seed=5, frac_sphere=0.1, frac_immovable=0.05)
+    lo, hi, pbc = [0, 0, 0], [2.0] * 3, (1, 0, 1)
+    moved = dict(rods)
+    moved["pos"] = rods["pos"] + rng.normal(0, 0.05, size=rods["pos"].shape)
+    q = rods["quat"] + rng.normal(0, 0.05, size=rods["quat"].shape)
+    moved["quat"] = q / np.linalg.norm(q, axis=1)[:, None]
+    want = gpu_collect(ctx, moved, lo, hi, pbc, 0.025).copy()
+    gpu_collect(ctx, rods, lo, hi, pbc, 0.025)
+    ctx.set_rod_state(moved["pos"], moved["quat"], wrap=True)
+    n = ctx.collect_pair_collision()
+    got = ctx.get_constraints(with_stress=True)
+    assert n == len(want) > 3000
+    assert_blocks_equal(got, want)
+    import alens_b200
+    c2 = alens_b200.Context(device=0)
+    c2.set_domain(lo, hi, pbc)
+    with pytest.raises(alens_b200.AlensError):
+        c2.set_rod_state(np.zeros((0, 3)), np.zeros((0, 4)))  # no alens_set_rods yet: ALENS_ERR_STATE
+    c2.close()
