@@ -66,6 +66,74 @@ static alens_bcqp *openBcqp(alens_ctx *ctx, alens::Bcqp *q) {
     return p;
 }
 
+// ---- host buffers that are not page-locked (a std::vector of the host application): the runtime's own staging copies them
+// at 6-10 GB/s on one thread.  Large transfers go through the context's page-locked bounce buffers in chunks instead: the DMA
+// of chunk k+1 overlaps the host copy of chunk k, which runs on all cores.  Page-locked callers (bench.py) keep the direct path.
+static bool isPageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static void hostCopyParallel(void *dst, const void *src, size_t bytes) {
+    const size_t blk = (size_t)1 << 18;
+    const long long nb = (long long)((bytes + blk - 1) / blk);
+#pragma omp parallel for schedule(static)
+    for (long long b = 0; b < nb; b++) {
+        const size_t o = (size_t)b * blk;
+        memcpy((char *)dst + o, (const char *)src + o, std::min(blk, bytes - o));
+    }
+}
+static constexpr size_t kBounceChunk = (size_t)8 << 20;
+static constexpr size_t kBounceMin = (size_t)1 << 20; // smaller transfers: not worth it
+// device -> host; returns after the data is in `dst` (synchronises the stream)
+static void downloadAny(Context &c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return;
+    cudaStream_t st = c.stream;
+    if (bytes < kBounceMin || !isPageable(dst)) {
+        ALENS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    char *b0 = (char *)c.pinBounce[0].reserve(kBounceChunk), *b1 = (char *)c.pinBounce[1].reserve(kBounceChunk);
+    char *buf[2] = {b0, b1};
+    const size_t nChunk = (bytes + kBounceChunk - 1) / kBounceChunk;
+    auto len = [&](size_t k) { return std::min(kBounceChunk, bytes - k * kBounceChunk); };
+    ALENS_CUDA(cudaMemcpyAsync(buf[0], src, len(0), cudaMemcpyDeviceToHost, st));
+    for (size_t k = 0; k < nChunk; k++) {
+        ALENS_CUDA(cudaStreamSynchronize(st)); // chunk k is in its bounce buffer
+        if (k + 1 < nChunk)
+            ALENS_CUDA(cudaMemcpyAsync(buf[(k + 1) & 1], (const char *)src + (k + 1) * kBounceChunk, len(k + 1),
+                                       cudaMemcpyDeviceToHost, st));
+        hostCopyParallel((char *)dst + k * kBounceChunk, buf[k & 1], len(k));
+    }
+}
+// host -> device; the host buffer may be reused when this returns
+static void uploadAny(Context &c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return;
+    cudaStream_t st = c.stream;
+    if (bytes < kBounceMin || !isPageable(src)) {
+        ALENS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        ALENS_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    char *b0 = (char *)c.pinBounce[0].reserve(kBounceChunk), *b1 = (char *)c.pinBounce[1].reserve(kBounceChunk);
+    char *buf[2] = {b0, b1};
+    cudaEvent_t &e0 = c.ev[6], &e1 = c.ev[7];
+    cudaEvent_t ev[2] = {e0, e1};
+    const size_t nChunk = (bytes + kBounceChunk - 1) / kBounceChunk;
+    for (size_t k = 0; k < nChunk; k++) {
+        const size_t n = std::min(kBounceChunk, bytes - k * kBounceChunk);
+        if (k >= 2) ALENS_CUDA(cudaEventSynchronize(ev[k & 1])); // the DMA that last read this bounce buffer is done
+        hostCopyParallel(buf[k & 1], (const char *)src + k * kBounceChunk, n);
+        ALENS_CUDA(cudaMemcpyAsync((char *)dst + k * kBounceChunk, buf[k & 1], n, cudaMemcpyHostToDevice, st));
+        ALENS_CUDA(cudaEventRecord(ev[k & 1], st));
+    }
+    ALENS_CUDA(cudaStreamSynchronize(st));
+}
+
 static float evMs(Context &c, int a, int b) {
     float ms = 0;
     cudaEventElapsedTime(&ms, c.ev[a], c.ev[b]);
@@ -214,30 +282,43 @@ int alens_set_rods_aos(alens_ctx *ctx, int n, const void *sy, size_t stride, int
         ctx->c.err = "alens_set_rods_aos: bad arguments";
         return ALENS_ERR_ARG;
     }
-    // field offsets of the reference `Sylinder` record (Sylinder.hpp:38-57): gid 0, isImmovable 16,
-    // radius 24, length 40, pos 80, orientation 104
-    std::vector<int> gid(n);
-    std::vector<double> pos(3 * (size_t)n), q(4 * (size_t)n), len(n), rad(n);
-    std::vector<unsigned char> imm(n);
+    // field offsets of the reference `Sylinder` record (Sylinder.hpp:38-57): gid 0, group 12, isImmovable 16,
+    // radius 24, length 40, pos 80, orientation 104.  The 85 hot bytes of every 568-byte record are gathered by all host
+    // cores into ONE page-locked staging buffer (grow-only, kept by the context), from where the copies run at full
+    // PCIe speed; Sylinder::group rides along as the rod's tag (it stays with the rod when the rod migrates).
+    const size_t N = (size_t)n;
+    auto al = [](size_t x) { return (x + 63) & ~(size_t)63; };
+    const size_t oPos = 0, oQ = oPos + al(24 * N), oLen = oQ + al(32 * N), oRad = oLen + al(8 * N), oTag = oRad + al(8 * N),
+                 oGid = oTag + al(8 * N), oImm = oGid + al(4 * N), total = oImm + al(N) + 64;
+    char *stage = nullptr;
+    try {
+        stage = (char *)ctx->c.pinAos.reserve(total);
+    } catch (const CudaError &) {
+        cudaGetLastError();
+        ctx->c.err = "alens_set_rods_aos: cannot allocate the page-locked staging buffer";
+        return ALENS_ERR_CUDA;
+    }
+    double *pos = (double *)(stage + oPos), *q = (double *)(stage + oQ), *len = (double *)(stage + oLen),
+           *rad = (double *)(stage + oRad);
+    long long *tag = (long long *)(stage + oTag);
+    int *gid = (int *)(stage + oGid);
+    unsigned char *imm = (unsigned char *)(stage + oImm);
     const char *base = (const char *)sy;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < n; i++) {
         const char *p = base + (size_t)i * stride;
+        int g;
         memcpy(&gid[i], p + 0, 4);
+        memcpy(&g, p + 12, 4);
+        tag[i] = g;
         imm[i] = *(const unsigned char *)(p + 16);
         memcpy(&rad[i], p + 24, 8);
         memcpy(&len[i], p + 40, 8);
         memcpy(&pos[3 * (size_t)i], p + 80, 24);
         memcpy(&q[4 * (size_t)i], p + 104, 32);
     }
-    // Sylinder::group (offset 12) rides along as the rod's tag: it stays with the rod when the rod migrates
-    std::vector<long long> tag(n);
-    for (int i = 0; i < n; i++) {
-        int g;
-        memcpy(&g, base + (size_t)i * stride + 12, 4);
-        tag[i] = g;
-    }
-    const int rc = alens_set_rods(ctx, n, gid.data(), pos.data(), q.data(), len.data(), rad.data(), imm.data(), wrap);
-    return rc != ALENS_OK ? rc : alens_set_rod_tags(ctx, tag.data());
+    const int rc = alens_set_rods(ctx, n, gid, pos, q, len, rad, imm, wrap);
+    return rc != ALENS_OK ? rc : alens_set_rod_tags(ctx, tag);
 }
 
 int alens_set_rod_tags(alens_ctx *ctx, const long long *tags) {
@@ -281,9 +362,7 @@ int alens_set_velocity_noncon(alens_ctx *ctx, const double *v) {
             return;
         }
         c.uVelNC.reserve(6 * (size_t)c.nRods + 6);
-        if (c.nLocal > 0)
-            ALENS_CUDA(cudaMemcpyAsync(c.uVelNC.p, v, 48 * (size_t)c.nLocal, cudaMemcpyHostToDevice, c.stream));
-        ALENS_CUDA(cudaStreamSynchronize(c.stream));
+        if (c.nLocal > 0) uploadAny(c, c.uVelNC.p, v, 48 * (size_t)c.nLocal);
         c.haveVelNC = true;
     });
 }
@@ -329,20 +408,15 @@ int alens_set_profiling(alens_ctx *ctx, int on) {
 
 int alens_get_positions(alens_ctx *ctx, double *pos) {
     return guarded(ctx, [&](Context &c) {
-        if (c.nLocal > 0) {
-            ALENS_CUDA(cudaMemcpyAsync(pos, c.uPos.p, 24 * (size_t)c.nLocal, cudaMemcpyDeviceToHost, c.stream));
-            ALENS_CUDA(cudaStreamSynchronize(c.stream));
-        }
+        if (c.nLocal > 0) downloadAny(c, pos, c.uPos.p, 24 * (size_t)c.nLocal);
     });
 }
 
 int alens_get_rod_state(alens_ctx *ctx, double *pos, double *quat) {
     return guarded(ctx, [&](Context &c) {
         if (c.nLocal > 0) {
-            if (pos) ALENS_CUDA(cudaMemcpyAsync(pos, c.uPos.p, 24 * (size_t)c.nLocal, cudaMemcpyDeviceToHost, c.stream));
-            if (quat)
-                ALENS_CUDA(cudaMemcpyAsync(quat, c.uQuat.p, 32 * (size_t)c.nLocal, cudaMemcpyDeviceToHost, c.stream));
-            ALENS_CUDA(cudaStreamSynchronize(c.stream));
+            if (pos) downloadAny(c, pos, c.uPos.p, 24 * (size_t)c.nLocal);
+            if (quat) downloadAny(c, quat, c.uQuat.p, 32 * (size_t)c.nLocal);
         }
     });
 }
@@ -509,10 +583,15 @@ int alens_get_force_velocity(alens_ctx *ctx, double *fU, double *vU, double *fB,
         cudaStream_t st = c.stream;
         ALENS_CUDA(cudaEventRecord(c.ev[0], st));
         if (bytes) {
-            if (fU) ALENS_CUDA(cudaMemcpyAsync(fU, c.outFU.p, bytes, cudaMemcpyDeviceToHost, st));
-            if (vU) ALENS_CUDA(cudaMemcpyAsync(vU, c.outVU.p, bytes, cudaMemcpyDeviceToHost, st));
-            if (fB) ALENS_CUDA(cudaMemcpyAsync(fB, c.outFB.p, bytes, cudaMemcpyDeviceToHost, st));
-            if (vB) ALENS_CUDA(cudaMemcpyAsync(vB, c.outVB.p, bytes, cudaMemcpyDeviceToHost, st));
+            double *dst[4] = {fU, vU, fB, vB};
+            const double *src[4] = {c.outFU.p, c.outVU.p, c.outFB.p, c.outVB.p};
+            bool anyPageable = false;
+            for (int k = 0; k < 4; k++) anyPageable = anyPageable || (dst[k] && bytes >= kBounceMin && isPageable(dst[k]));
+            for (int k = 0; k < 4; k++) {
+                if (!dst[k]) continue;
+                if (anyPageable) downloadAny(c, dst[k], src[k], bytes);
+                else ALENS_CUDA(cudaMemcpyAsync(dst[k], src[k], bytes, cudaMemcpyDeviceToHost, st));
+            }
         }
         ALENS_CUDA(cudaEventRecord(c.ev[1], st));
         ALENS_CUDA(cudaStreamSynchronize(st));

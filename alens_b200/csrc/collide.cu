@@ -843,6 +843,7 @@ static void chooseGrid(Context &c, double maxR) {
 // host: max bounding radius; called with the host arrays at upload time
 double hostMaxRadius(int n, const double *len, const double *rad, double lRatio, double dRatio) {
     double m = 0;
+#pragma omp parallel for schedule(static) reduction(max : m)
     for (int i = 0; i < n; i++) {
         const double R = 0.5 * len[i] * lRatio + rad[i] * dRatio;
         if (R > m) m = R;

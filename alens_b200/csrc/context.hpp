@@ -351,6 +351,8 @@ struct Context {
     int profUsed = 0;
 
     PinnedBuf pin0, pin1;
+    PinnedBuf pinBounce[2]; // 8 MB each: transfers from / to host memory that is not page-locked (capi.cu: downloadAny)
+    PinnedBuf pinAos; // alens_set_rods_aos: the gathered hot fields of the caller's Sylinder records
 
     // ---- multi-GPU ----
     void *nccl = nullptr; // ncclComm_t

@@ -20,6 +20,7 @@ class ConstraintSolver {
     int solverChoice = 0;
     Teuchos::RCP<const TMAP> mobMapRcp;
     Teuchos::RCP<TV> velncRcp, forceuRcp, forcebRcp, veluRcp, velbRcp, gammaRcp;
+    Teuchos::RCP<TV> zeroRcp; ///< the bilateral force / velocity of a pool without a bilateral block (never written)
     IteHistory history;
     alens_solve_report report{};
 
@@ -77,12 +78,19 @@ class ConstraintSolver {
         Teuchos::RCP<const TMAP> mob = mobMapRcp.is_null()
                                            ? Teuchos::RCP<const TMAP>(getTMAPFromLocalSize(6 * report.n_rods, comm))
                                            : mobMapRcp;
-        auto mk = [&]() { return Teuchos::RCP<TV>(std::make_shared<TV>(mob, true)); };
-        forceuRcp = mk(); veluRcp = mk(); forcebRcp = mk(); velbRcp = mk();
         // without a bilateral block force_b = D gamma_b and vel_b = M force_b (ConstraintSolver.cpp:98-101) are identically
-        // zero: the zero-initialised vectors above already hold the result, and 96 bytes per rod stay off the PCIe bus
+        // zero: ONE zero vector (kept across steps while the size stays) stands for both, and 96 bytes per rod stay off the
+        // PCIe bus.  The vectors a download fills completely are not zeroed first (48 MB each at 1M rods).
         long long nBi = 0;
         ck(alens_get_pool_stats(ctx_, nullptr, nullptr, &nBi));
+        auto mk = [&](bool zero) { return Teuchos::RCP<TV>(std::make_shared<TV>(mob, zero)); };
+        forceuRcp = mk(false); veluRcp = mk(false);
+        if (nBi) {
+            forcebRcp = mk(false); velbRcp = mk(false);
+        } else {
+            if (zeroRcp.is_null() || zeroRcp->getLocalLength() != (size_t)mob->getNodeNumElements()) zeroRcp = mk(true);
+            forcebRcp = zeroRcp; velbRcp = zeroRcp;
+        }
         ck(alens_get_force_velocity(ctx_, forceuRcp->data(), veluRcp->data(), nBi ? forcebRcp->data() : nullptr,
                                     nBi ? velbRcp->data() : nullptr));
     }

@@ -26,6 +26,13 @@
 #include "Sylinder.hpp"
 #include "SylinderConfig.hpp"
 
+// the per-rod host loops run on all cores when the host program is compiled with OpenMP, as the reference's do
+#ifdef _OPENMP
+#define ALENS_OMP_FOR _Pragma("omp parallel for schedule(static)")
+#else
+#define ALENS_OMP_FOR
+#endif
+
 class SylinderSystem {
     alens_ctx *ctx_ = nullptr;
     int stepCount = 0;
@@ -52,6 +59,7 @@ class SylinderSystem {
         sylinderMapRcp = getTMAPFromLocalSize(nLocal, commRcp, offset);
         sylinderMobilityMapRcp = getTMAPFromLocalSize(nLocal * 6, commRcp, 6 * offset);
         const int base = sylinderMapRcp->getMinGlobalIndex();
+        ALENS_OMP_FOR
         for (int i = 0; i < nLocal; i++) sylinderContainer[i].globalIndex = i + base;
     }
 
@@ -299,6 +307,7 @@ class SylinderSystem {
         ck(alens_set_collision_params(ctx_, runConfig.sylinderDiameterColRatio, runConfig.sylinderLengthColRatio,
                                       runConfig.sylinderColBuf));
         const int nLocal = (int)sylinderContainer.size();
+        ALENS_OMP_FOR
         for (int i = 0; i < nLocal; i++) {
             auto &sy = sylinderContainer[i];
             sy.clear();
@@ -309,7 +318,9 @@ class SylinderSystem {
         }
         if (runConfig.monolayer) { // :907-918 (direction flattened into the xy plane)
             const double monoZ = (runConfig.simBoxHigh[2] + runConfig.simBoxLow[2]) / 2;
-            for (auto &sy : sylinderContainer) {
+            ALENS_OMP_FOR
+            for (int i = 0; i < nLocal; i++) {
+                auto &sy = sylinderContainer[i];
                 sy.pos[2] = monoZ;
                 const double *q = sy.orientation;
                 double dx = 2 * (q[0] * q[2] + q[3] * q[1]), dy = 2 * (q[1] * q[2] - q[3] * q[0]);
@@ -325,8 +336,9 @@ class SylinderSystem {
         // upload (+ applyBoxBC + cell list) and bring the wrapped positions back into the container
         ck(alens_set_rods_aos(ctx_, nLocal, sylinderContainer.data(), sizeof(Sylinder), 1));
         if (nLocal > 0) {
-            std::vector<double> pos(3 * (size_t)nLocal);
-            ck(alens_get_positions(ctx_, pos.data()));
+            const std::unique_ptr<double[]> pos(new double[3 * (size_t)nLocal]); // (not zero-filled: the download fills it)
+            ck(alens_get_positions(ctx_, pos.get()));
+            ALENS_OMP_FOR
             for (int i = 0; i < nLocal; i++)
                 for (int k = 0; k < 3; k++) sylinderContainer[i].pos[k] = pos[3 * (size_t)i + k];
         }
@@ -357,12 +369,14 @@ class SylinderSystem {
         double *v = velocityNonConRcp->data();
         auto monoZero = [&](double *p) {
             if (!runConfig.monolayer) return;
+            ALENS_OMP_FOR
             for (int i = 0; i < nLocal; i++) p[6 * i + 2] = p[6 * i + 3] = p[6 * i + 4] = 0;
         };
         if (!forcePartNonBrownRcp.is_null()) {
             ck(alens_mobility_apply(ctx_, forcePartNonBrownRcp->data(), v)); // mobilityOperatorRcp->apply
             monoZero(v);
             const double *f = forcePartNonBrownRcp->data();
+            ALENS_OMP_FOR
             for (int i = 0; i < nLocal; i++)
                 for (int k = 0; k < 3; k++) {
                     sylinderContainer[i].forceNonB[k] = f[6 * i + k];
@@ -373,6 +387,7 @@ class SylinderSystem {
             monoZero(velocityPartNonBrownRcp->data());
             velocityNonConRcp->update(1.0, *velocityPartNonBrownRcp, 1.0);
         }
+        ALENS_OMP_FOR
         for (int i = 0; i < nLocal; i++)
             for (int k = 0; k < 3; k++) {
                 sylinderContainer[i].velNonB[k] = v[6 * i + k];
@@ -382,6 +397,7 @@ class SylinderSystem {
             monoZero(velocityBrownRcp->data());
             velocityNonConRcp->update(1.0, *velocityBrownRcp, 1.0);
             const double *b = velocityBrownRcp->data();
+            ALENS_OMP_FOR
             for (int i = 0; i < nLocal; i++)
                 for (int k = 0; k < 3; k++) {
                     sylinderContainer[i].velBrown[k] = b[6 * i + k];
@@ -499,6 +515,7 @@ class SylinderSystem {
         const double *vu = velocityUniRcp->data(), *vb = velocityBiRcp->data();
         const double *fu = forceUniRcp->data(), *fb = forceBiRcp->data();
         const int n = (int)sylinderContainer.size();
+        ALENS_OMP_FOR
         for (int i = 0; i < n; i++) {
             auto &sy = sylinderContainer[i];
             for (int k = 0; k < 3; k++) {
@@ -511,13 +528,17 @@ class SylinderSystem {
     }
 
     void sumForceVelocity() { // :802-814
-        for (auto &sy : sylinderContainer)
+        const int nAll = (int)sylinderContainer.size();
+        ALENS_OMP_FOR
+        for (int i = 0; i < nAll; i++) {
+            auto &sy = sylinderContainer[i];
             for (int k = 0; k < 3; k++) {
                 sy.vel[k] = sy.velNonB[k] + sy.velBrown[k] + sy.velCol[k] + sy.velBi[k];
                 sy.omega[k] = sy.omegaNonB[k] + sy.omegaBrown[k] + sy.omegaCol[k] + sy.omegaBi[k];
                 sy.force[k] = sy.forceNonB[k] + sy.forceCol[k] + sy.forceBi[k];
                 sy.torque[k] = sy.torqueNonB[k] + sy.torqueCol[k] + sy.torqueBi[k];
             }
+        }
     }
 
     /// Euler step on the device copy (vel = velNonCon + velUni + velBi, quaternion rotated by omega*dt,
@@ -534,8 +555,9 @@ class SylinderSystem {
             }
         }
         const size_t n = sylinderContainer.size();
-        std::vector<double> pos(3 * n), q(4 * n);
-        ck(alens_get_rod_state(ctx_, pos.data(), q.data()));
+        const std::unique_ptr<double[]> pos(new double[3 * n + 1]), q(new double[4 * n + 1]);
+        ck(alens_get_rod_state(ctx_, pos.get(), q.get()));
+        ALENS_OMP_FOR
         for (size_t i = 0; i < n; i++) {
             for (int k = 0; k < 3; k++) sylinderContainer[i].pos[k] = pos[3 * i + k];
             for (int k = 0; k < 4; k++) sylinderContainer[i].orientation[k] = q[4 * i + k];
@@ -554,6 +576,7 @@ class SylinderSystem {
         ck(alens_get_rod_state(ctx_, pos.data(), q.data()));
         ck(alens_get_rod_tags(ctx_, tag.data()));
         sylinderContainer.assign((size_t)n, Sylinder());
+        ALENS_OMP_FOR
         for (int i = 0; i < n; i++) {
             Sylinder &sy = sylinderContainer[i];
             sy.gid = gid[i];

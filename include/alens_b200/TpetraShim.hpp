@@ -62,10 +62,22 @@ class Map {
     Teuchos::RCP<const Comm> getComm() const { return comm_; }
 };
 
-// single-column vector with Tpetra's update/scale/dot/norm spellings
+// single-column vector with Tpetra's update/scale/dot/norm spellings.  zeroOut = false leaves the storage
+// uninitialised, as Tpetra's constructor does (vectors that a download fills completely); the loops run on all cores when the
+// host program is compiled with OpenMP -- at 1M rods these vectors are 48 MB each
+#ifdef _OPENMP
+#define ALENS_SHIM_OMP_FOR _Pragma("omp parallel for schedule(static)")
+#define ALENS_SHIM_OMP_SUM _Pragma("omp parallel for schedule(static) reduction(+ : s)")
+#define ALENS_SHIM_OMP_MAX _Pragma("omp parallel for schedule(static) reduction(max : m)")
+#else
+#define ALENS_SHIM_OMP_FOR
+#define ALENS_SHIM_OMP_SUM
+#define ALENS_SHIM_OMP_MAX
+#endif
 class Vector {
     Teuchos::RCP<const Map> map_;
-    std::vector<double> v_;
+    std::unique_ptr<double[]> v_;
+    long long n_ = 0;
 
   public:
     struct View {
@@ -83,40 +95,69 @@ class Vector {
         size_t dimension_0() const { return n; }
         size_t dimension_1() const { return 1; }
     };
-    Vector(const Teuchos::RCP<const Map> &map, bool /*zeroOut*/ = true)
-        : map_(map), v_(map ? map->getNodeNumElements() : 0, 0.0) {}
+    Vector(const Teuchos::RCP<const Map> &map, bool zeroOut = true)
+        : map_(map), v_(new double[(map ? map->getNodeNumElements() : 0) + 1]), n_(map ? map->getNodeNumElements() : 0) {
+        if (zeroOut) putScalar(0.0);
+    }
+    Vector(const Vector &o) : map_(o.map_), v_(new double[o.n_ + 1]), n_(o.n_) {
+        ALENS_SHIM_OMP_FOR
+        for (long long i = 0; i < n_; i++) v_[i] = o.v_[i];
+    }
+    Vector &operator=(const Vector &o) {
+        if (this != &o) {
+            Vector t(o);
+            std::swap(map_, t.map_);
+            std::swap(v_, t.v_);
+            std::swap(n_, t.n_);
+        }
+        return *this;
+    }
     const Teuchos::RCP<const Map> &getMap() const { return map_; }
-    size_t getLocalLength() const { return v_.size(); }
+    size_t getLocalLength() const { return (size_t)n_; }
     size_t getNumVectors() const { return 1; }
-    double *data() { return v_.data(); }
-    const double *data() const { return v_.data(); }
+    double *data() { return v_.get(); }
+    const double *data() const { return v_.get(); }
     template <class Space = void>
-    View getLocalView() { return View{v_.data(), v_.size()}; }
+    View getLocalView() { return View{v_.get(), (size_t)n_}; }
     template <class Space = void>
-    ConstView getLocalView() const { return ConstView{v_.data(), v_.size()}; }
+    ConstView getLocalView() const { return ConstView{v_.get(), (size_t)n_}; }
     template <class Space = void>
     void modify() {}
-    void putScalar(double a) { std::fill(v_.begin(), v_.end(), a); }
-    void scale(double a) { for (auto &x : v_) x *= a; }
-    void scale(double a, const Vector &A) { for (size_t i = 0; i < v_.size(); i++) v_[i] = a * A.v_[i]; }
+    void putScalar(double a) {
+        ALENS_SHIM_OMP_FOR
+        for (long long i = 0; i < n_; i++) v_[i] = a;
+    }
+    void scale(double a) {
+        ALENS_SHIM_OMP_FOR
+        for (long long i = 0; i < n_; i++) v_[i] *= a;
+    }
+    void scale(double a, const Vector &A) {
+        ALENS_SHIM_OMP_FOR
+        for (long long i = 0; i < n_; i++) v_[i] = a * A.v_[i];
+    }
     void update(double a, const Vector &A, double b) {
-        for (size_t i = 0; i < v_.size(); i++) v_[i] = b * v_[i] + a * A.v_[i];
+        ALENS_SHIM_OMP_FOR
+        for (long long i = 0; i < n_; i++) v_[i] = b * v_[i] + a * A.v_[i];
     }
     void update(double a, const Vector &A, double b, const Vector &B, double g) {
-        for (size_t i = 0; i < v_.size(); i++) v_[i] = g * v_[i] + a * A.v_[i] + b * B.v_[i];
+        ALENS_SHIM_OMP_FOR
+        for (long long i = 0; i < n_; i++) v_[i] = g * v_[i] + a * A.v_[i] + b * B.v_[i];
     }
     void elementWiseMultiply(double s, const Vector &A, const Vector &B, double t) {
-        for (size_t i = 0; i < v_.size(); i++) v_[i] = t * v_[i] + s * A.v_[i] * B.v_[i];
+        ALENS_SHIM_OMP_FOR
+        for (long long i = 0; i < n_; i++) v_[i] = t * v_[i] + s * A.v_[i] * B.v_[i];
     }
     double dot(const Vector &o) const {
         double s = 0;
-        for (size_t i = 0; i < v_.size(); i++) s += v_[i] * o.v_[i];
+        ALENS_SHIM_OMP_SUM
+        for (long long i = 0; i < n_; i++) s += v_[i] * o.v_[i];
         return s;
     }
     double norm2() const { return std::sqrt(dot(*this)); }
     double normInf() const {
         double m = 0;
-        for (double x : v_) m = std::max(m, std::fabs(x));
+        ALENS_SHIM_OMP_MAX
+        for (long long i = 0; i < n_; i++) m = std::max(m, std::fabs(v_[i]));
         return m;
     }
 };
@@ -183,7 +224,7 @@ inline Teuchos::RCP<TMAP> getTMAPFromLocalSize(int localSize, const Teuchos::RCP
 }
 inline Teuchos::RCP<TV> getTVFromVector(const std::vector<double> &in, const Teuchos::RCP<const TCOMM> &comm) {
     auto map = getTMAPFromLocalSize((int)in.size(), comm);
-    Teuchos::RCP<TV> v(std::make_shared<TV>(Teuchos::RCP<const TMAP>(map), true));
+    Teuchos::RCP<TV> v(std::make_shared<TV>(Teuchos::RCP<const TMAP>(map), false));
     std::copy(in.begin(), in.end(), v->data());
     return v;
 }
