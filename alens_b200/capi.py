@@ -39,7 +39,7 @@ EXPORTS = [
     "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest",
     "alens_get_live_stats", "alens_bcqp_create_csr", "alens_bcqp_create_constraint", "alens_bcqp_set_lower_bound",
     "alens_bcqp_set_upper_bound", "alens_bcqp_get_bounds", "alens_bcqp_run", "alens_bcqp_history", "alens_bcqp_size",
-    "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps", "alens_mix_pair_search", "alens_migrate_rods", "alens_get_rod_identity", "alens_set_rod_state", "alens_set_rod_tags", "alens_get_rod_tags",
+    "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps", "alens_mix_pair_search", "alens_migrate_rods", "alens_get_rod_identity", "alens_set_rod_state", "alens_get_long_rod_stats", "alens_set_rod_tags", "alens_get_rod_tags",
 ]
 
 
@@ -564,6 +564,11 @@ class Context:
 
     def reset_timers(self):
         self._call("alens_reset_timers")
+
+    def get_long_rod_stats(self):
+        a, b, r0, r1 = C.c_longlong(0), C.c_longlong(0), C.c_double(0), C.c_double(0)
+        self._call("alens_get_long_rod_stats", C.byref(a), C.byref(b), C.byref(r0), C.byref(r1))
+        return dict(long_rods=a.value, long_rows=b.value, short_radius=r0.value, max_radius=r1.value)
 
     def get_collect_stats(self):
         a, b, c = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)

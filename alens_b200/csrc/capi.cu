@@ -248,7 +248,7 @@ int alens_set_rods(alens_ctx *ctx, int n, const int *gid, const double *pos, con
             if (imm) ALENS_CUDA(cudaMemcpyAsync(c.uImm.p, imm, N, cudaMemcpyHostToDevice, st));
             else ALENS_CUDA(cudaMemsetAsync(c.uImm.p, 0, N, st));
         }
-        c.maxRLocal = hostMaxRadius(n, len, rad, c.lRatio, c.dRatio); // overlaps with the copies
+        c.maxRLocal = hostMaxRadius(n, len, rad, c.lRatio, c.dRatio, &c.meanRLocal); // overlaps with the copies
         c.maxRLRatio = c.lRatio;
         c.maxRDRatio = c.dRatio;
         rodsUploaded(c, wrap != 0);
@@ -629,6 +629,7 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
         else if (k == "stamps") c.optStamps = value != 0;
         else if (k == "halo_debug") c.optHaloDebug = (int)value;
         else if (k == "tail_push") c.optTailPush = value != 0;
+        else if (k == "long_rods") c.optLongRods = value <= 0 ? 0.0 : value / 100.0; // percent of the mean bounding radius (200 = default)
         else if (k == "l2_fetch") { // cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes): a device-wide hint
             ALENS_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
         }
@@ -672,6 +673,15 @@ int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCand,
         if (nCells) *nCells = c.grid.ncell;
         if (nCand) *nCand = c.statCand;
         if (nHits) *nHits = c.nColl;
+    });
+}
+
+int alens_get_long_rod_stats(alens_ctx *ctx, long long *nLongRods, long long *nLongRows, double *shortRadius, double *maxRadius) {
+    return guarded(ctx, [&](Context &c) {
+        if (nLongRods) *nLongRods = c.nLongRods;
+        if (nLongRows) *nLongRows = c.nLongRows;
+        if (shortRadius) *shortRadius = c.shortR;
+        if (maxRadius) *maxRadius = c.maxRLocal;
     });
 }
 

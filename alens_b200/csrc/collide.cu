@@ -841,13 +841,15 @@ static void chooseGrid(Context &c, double maxR) {
 }
 
 // host: max bounding radius; called with the host arrays at upload time
-double hostMaxRadius(int n, const double *len, const double *rad, double lRatio, double dRatio) {
-    double m = 0;
-#pragma omp parallel for schedule(static) reduction(max : m)
+double hostMaxRadius(int n, const double *len, const double *rad, double lRatio, double dRatio, double *meanOut) {
+    double m = 0, sum = 0;
+#pragma omp parallel for schedule(static) reduction(max : m) reduction(+ : sum)
     for (int i = 0; i < n; i++) {
         const double R = 0.5 * len[i] * lRatio + rad[i] * dRatio;
         if (R > m) m = R;
+        sum += R;
     }
+    if (meanOut) *meanOut = n > 0 ? sum / n : 0.0;
     return m;
 }
 
@@ -891,10 +893,15 @@ void rodsUploaded(Context &c, bool wrap) {
         ALENS_CUDA(cudaMemcpyAsync(&bits, c.dCounters.p, sizeof(bits), cudaMemcpyDeviceToHost, st));
         ALENS_CUDA(cudaStreamSynchronize(st));
         memcpy(&c.maxRLocal, &bits, sizeof(double));
+        c.meanRLocal = 0; // (unknown for the new ratios: no long-rod pass until the next alens_set_rods)
         c.maxRLRatio = c.lRatio;
         c.maxRDRatio = c.dRatio;
     }
     double maxR = c.maxRLocal;
+    // Polydisperse rods: the cell edge follows shortR = min(maxR, long_rods x mean bounding radius); the few rods above it
+    // ("long" rods) are paired with partners beyond the 27-cell stencil by a separate pass (collectLongRods).  One rank only.
+    c.shortR = maxR;
+    if (!multi && c.optLongRods > 0 && c.meanRLocal > 0 && maxR > c.optLongRods * c.meanRLocal) c.shortR = c.optLongRods * c.meanRLocal;
     if (multi) {
         c.ghostWidth = (2 * c.maxRadiusGlobal + c.colBuf) * (1.0 + 1e-9) + c.skin;
         if (c.slabHi - c.slabLo < 2 * c.ghostWidth)
@@ -919,7 +926,15 @@ void rodsUploaded(Context &c, bool wrap) {
         maxR = c.maxRadiusGlobal;
     }
     const int n = c.nRods;
-    chooseGrid(c, maxR);
+    chooseGrid(c, multi ? maxR : c.shortR);
+    if (c.shortR < maxR) { // the long-rod pass needs at least 3 cells along a periodic axis (one image per neighbour cell)
+        bool ok = true;
+        for (int k = 0; k < 3; k++) ok = ok && (!c.grid.per[k] || c.grid.n[k] >= 3);
+        if (!ok) {
+            c.shortR = maxR;
+            chooseGrid(c, maxR);
+        }
+    }
     const CellGrid g = c.grid;
     c.uCell.reserve(n);
     c.userToSorted.reserve(n);
@@ -989,9 +1004,237 @@ void reserveConstraints(Context &c, size_t n, bool keep) {
     c.conCap = ncap;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Long rods (polydisperse suspensions).  The cell edge is sized for rods up to a bounding radius shortR; the stencil search
+// above finds every contact between rods whose cells are neighbours, whatever their length.  What it cannot see is a contact
+// of a LONG rod (bounding radius > shortR) with a partner more than one cell away.  Those come from two extra passes, both
+// exact from the start (closest-point query on every pair that survives a point / segment distance test):
+//   k_long_cells  warp per long rod A: the cells overlapping A's box grown by shortR + r_A + colBuf hold the centres of all
+//                 SHORT partners; cells within the stencil of A's own cell are skipped (already searched)
+//   k_long_long   warp per long rod A: all long rods behind it in the list (few), nearest periodic image, pairs whose cells
+//                 are neighbours skipped
+// Count pass, scan, fill pass; rows go behind the stencil rows in (long rod, cell walk, partner) order: deterministic.
+// One image per pair: rods must be shorter than half a periodic box edge (as the image code of a row assumes anyway).
+__device__ __forceinline__ void emitRow(const PairOut &out, size_t k, int si, int sj, int code, const Contact &ct,
+                                        const PairIn &in) {
+    const size_t S = out.stride;
+    out.idxI[k] = si;
+    out.idxJ[k] = sj;
+    out.gidI[k] = in.sGid[si];
+    out.gidJ[k] = in.sGid[sj];
+    out.shift[k] = (signed char)code;
+    out.bi[k] = 0;
+    out.oneSide[k] = 0;
+    out.own[k] = in.sGhost[si] ? 0 : 1;
+    out.delta0[k] = ct.sep;
+    out.gamma0[k] = ct.sep < 0 ? -ct.sep : 0;
+    out.invKappa[k] = 0;
+    out.kappa[k] = 0;
+    out.n[k] = ct.normI.x; out.n[k + S] = ct.normI.y; out.n[k + 2 * S] = ct.normI.z;
+    out.pI[k] = ct.posI.x; out.pI[k + S] = ct.posI.y; out.pI[k + 2 * S] = ct.posI.z;
+    out.pJ[k] = ct.posJ.x; out.pJ[k + S] = ct.posJ.y; out.pJ[k + 2 * S] = ct.posJ.z;
+    out.labI[k] = ct.labI.x; out.labI[k + S] = ct.labI.y; out.labI[k + 2 * S] = ct.labI.z;
+    out.labJ[k] = ct.labJ.x; out.labJ[k + S] = ct.labJ.y; out.labJ[k + 2 * S] = ct.labJ.z;
+}
+__global__ void k_long_flags(int n, const double *__restrict__ sLc, const double *__restrict__ sRc, double shortR,
+                             int *__restrict__ flag) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) flag[s] = (0.5 * sLc[s] + sRc[s] > shortR) ? 1 : 0;
+}
+__global__ void k_long_list(int n, const int *__restrict__ flag, const int *__restrict__ scan, int *__restrict__ list) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n && flag[s]) list[scan[s]] = s;
+}
+// squared distance of point p to the segment c -+ h d (d unit)
+__device__ __forceinline__ double pointSegDist2(Vec3 p, Vec3 c, Vec3 d, double h) {
+    const Vec3 w = p - c;
+    double t = w.x * d.x + w.y * d.y + w.z * d.z;
+    t = fmin(fmax(t, -h), h);
+    const double ex = w.x - t * d.x, ey = w.y - t * d.y, ez = w.z - t * d.z;
+    return ex * ex + ey * ey + ez * ez;
+}
+// the exact test of long rod a against partner b seen through image (kx, ky, kz) of b; canonical roles as everywhere
+__device__ __forceinline__ bool longPairHit(const PairIn &in, const Box &box, double colBuf, int a, int b, int kx, int ky, int kz,
+                                            int &si, int &sj, int &code, Contact &ct) {
+    const int ga = in.sGid[a], gb = in.sGid[b];
+    if (ga == gb) return false; // equal gids never collide (SylinderNear.hpp:210,225)
+    if (ga < gb) {
+        si = a; sj = b;
+    } else {
+        si = b; sj = a;
+        kx = -kx; ky = -ky; kz = -kz;
+    }
+    code = (kx + 1) + 3 * (ky + 1) + 9 * (kz + 1);
+    RodGeom I = loadRod(in, si), J = loadRod(in, sj);
+    J.c = v3(J.c.x + kx * box.len[0], J.c.y + ky * box.len[1], J.c.z + kz * box.len[2]);
+    return pairContact(I, J, colBuf, ct);
+}
+struct LongIn {
+    int nLong;
+    const int *list;     // sorted indices of the long rods, ascending
+    const int *flag;     // per sorted rod: 1 = long
+    const int *cellOfUser, *sUser; // assigned cell of a sorted rod s = cellOfUser[sUser[s]]
+    double shortR;
+};
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_long_cells(LongIn L, PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ counts,
+                                                    const int *__restrict__ starts, long long base, PairOut out) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= L.nLong) return;
+    const int a = L.list[w];
+    const RodGeom A = loadRod(in, a);
+    const double hA = 0.5 * A.lc;
+    const double reach = (L.shortR + A.rc + colBuf) * (1.0 + 1e-9);
+    const double ctr[3] = {A.c.x, A.c.y, A.c.z}, dir[3] = {A.d.x, A.d.y, A.d.z};
+    const int cellA = L.cellOfUser[L.sUser[a]];
+    const int ca[3] = {cellA % g.n[0], (cellA / g.n[0]) % g.n[1], cellA / (g.n[0] * g.n[1])};
+    int u0[3], u1[3];
+    for (int k = 0; k < 3; k++) {
+        const double e = fabs(hA * dir[k]) + reach;
+        long long lo = (long long)floor((ctr[k] - e - g.lo[k]) * g.inv[k]), hi = (long long)floor((ctr[k] + e - g.lo[k]) * g.inv[k]);
+        if (!g.per[k] || g.inv[k] <= 0) { // open axis: rods outside the grid sit in its boundary cells
+            lo = lo < 0 ? 0 : (lo >= g.n[k] ? g.n[k] - 1 : lo);
+            hi = hi < 0 ? 0 : (hi >= g.n[k] ? g.n[k] - 1 : hi);
+        } else if (hi - lo + 1 > g.n[k]) { // never the same cell through two images
+            lo = ca[k] - (g.n[k] - 1) / 2;
+            hi = lo + g.n[k] - 1;
+        }
+        u0[k] = (int)lo;
+        u1[k] = (int)hi;
+    }
+    long long pos = FILL ? base + starts[w] : 0;
+    int cnt = 0;
+    for (int uz = u0[2]; uz <= u1[2]; uz++)
+        for (int uy = u0[1]; uy <= u1[1]; uy++)
+            for (int ux = u0[0]; ux <= u1[0]; ux++) {
+                if (abs(ux - ca[0]) <= 1 && abs(uy - ca[1]) <= 1 && abs(uz - ca[2]) <= 1) continue; // the stencil search has it
+                const int u[3] = {ux, uy, uz};
+                int cc[3], kk[3];
+                for (int k = 0; k < 3; k++) {
+                    int img = 0, ck = u[k];
+                    if (ck < 0 || ck >= g.n[k]) { // (periodic axis: open axes were clamped above)
+                        img = (int)floor((double)ck / g.n[k]);
+                        ck -= img * g.n[k];
+                    }
+                    cc[k] = ck;
+                    kk[k] = img;
+                }
+                const int cell = (cc[2] * g.n[1] + cc[1]) * g.n[0] + cc[0];
+                const int jb = in.cellStart[cell], je = in.cellStart[cell + 1];
+                const Vec3 shift = v3(kk[0] * box.len[0], kk[1] * box.len[1], kk[2] * box.len[2]);
+                for (int j0 = jb; j0 < je; j0 += 32) {
+                    const int b = j0 + lane;
+                    bool hit = false;
+                    int si = 0, sj = 0, code = 13;
+                    Contact ct;
+                    if (b < je && !L.flag[b]) { // short partners only: long ones belong to k_long_long
+                        const Vec3 cb = v3(in.sX[b] + shift.x, in.sY[b] + shift.y, in.sZ[b] + shift.z);
+                        const double rb = 0.5 * in.sLc[b] + in.sRc[b] + A.rc + colBuf;
+                        if (pointSegDist2(cb, A.c, A.d, hA) <= rb * rb * (1.0 + 1e-9))
+                            hit = longPairHit(in, box, colBuf, a, b, kk[0], kk[1], kk[2], si, sj, code, ct);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (FILL && hit) emitRow(out, (size_t)(pos + cnt + __popc(m & ((1u << lane) - 1u))), si, sj, code, ct, in);
+                    cnt += __popc(m);
+                }
+            }
+    if (!FILL && lane == 0) counts[w] = cnt;
+}
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_long_long(LongIn L, PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ counts,
+                                                   const int *__restrict__ starts, long long base, PairOut out) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= L.nLong) return;
+    const int a = L.list[w];
+    const RodGeom A = loadRod(in, a);
+    const double hA = 0.5 * A.lc;
+    const int cellA = L.cellOfUser[L.sUser[a]];
+    const int ca[3] = {cellA % g.n[0], (cellA / g.n[0]) % g.n[1], cellA / (g.n[0] * g.n[1])};
+    long long pos = FILL ? base + starts[w] : 0;
+    int cnt = 0;
+    for (int l0 = w + 1; l0 < L.nLong; l0 += 32) {
+        const int lb = l0 + lane;
+        bool hit = false;
+        int si = 0, sj = 0, code = 13;
+        Contact ct;
+        if (lb < L.nLong) {
+            const int b = L.list[lb];
+            double cb[3] = {in.sX[b], in.sY[b], in.sZ[b]};
+            const double ctr[3] = {A.c.x, A.c.y, A.c.z};
+            int kk[3] = {0, 0, 0};
+            for (int k = 0; k < 3; k++)
+                if (g.per[k] && box.len[k] > 0) { // nearest image of b
+                    kk[k] = -(int)rint((cb[k] - ctr[k]) / box.len[k]);
+                    cb[k] += kk[k] * box.len[k];
+                }
+            const int cellB = L.cellOfUser[L.sUser[b]];
+            const int cbx = cellB % g.n[0] + kk[0] * g.n[0], cby = (cellB / g.n[0]) % g.n[1] + kk[1] * g.n[1],
+                      cbz = cellB / (g.n[0] * g.n[1]) + kk[2] * g.n[2];
+            const bool stencil = abs(cbx - ca[0]) <= 1 && abs(cby - ca[1]) <= 1 && abs(cbz - ca[2]) <= 1;
+            const double rb = 0.5 * in.sLc[b] + in.sRc[b] + A.rc + colBuf;
+            if (!stencil && pointSegDist2(v3(cb[0], cb[1], cb[2]), A.c, A.d, hA) <= rb * rb * (1.0 + 1e-9))
+                hit = longPairHit(in, box, colBuf, a, b, kk[0], kk[1], kk[2], si, sj, code, ct);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (FILL && hit) emitRow(out, (size_t)(pos + cnt + __popc(m & ((1u << lane) - 1u))), si, sj, code, ct, in);
+        cnt += __popc(m);
+    }
+    if (!FILL && lane == 0) counts[w] = cnt;
+}
+
 static PairIn pairIn(Context &c) {
     return PairIn{c.cellStart.p, c.sGid.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p, c.sDz.p, c.sLc.p, c.sRc.p,
                   c.bUx.p, c.bUy.p, c.bUz.p, c.bH.p, c.bRho.p, c.sImg.p, c.sGhost.p};
+}
+
+
+// the rows of the long rods (see k_long_cells); `total` stencil rows are in place.  Returns the number of rows added.
+static long long collectLongRods(Context &c, long long total) {
+    cudaStream_t st = c.stream;
+    const int n = c.nRods;
+    const CellGrid g = c.grid;
+    DevBuf<int> flag, scan, list, cnt1, cnt2, st1, st2;
+    flag.reserve((size_t)n + 8); scan.reserve((size_t)n + 8);
+    k_long_flags<<<gridFor(n, 256), 256, 0, st>>>(n, c.sLc.p, c.sRc.p, c.shortR, flag.p);
+    launchScanInt(c, flag.p, scan.p, n);
+    int nLong = 0;
+    ALENS_CUDA(cudaMemcpyAsync(&nLong, scan.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    c.launches += 1;
+    c.nLongRods = nLong;
+    c.nLongRows = 0;
+    if (nLong == 0) return 0;
+    list.reserve((size_t)nLong + 8); cnt1.reserve((size_t)nLong + 8); cnt2.reserve((size_t)nLong + 8);
+    st1.reserve((size_t)nLong + 8); st2.reserve((size_t)nLong + 8);
+    k_long_list<<<gridFor(n, 256), 256, 0, st>>>(n, flag.p, scan.p, list.p);
+    const LongIn L{nLong, list.p, flag.p, c.uCell.p, c.sUser.p, c.shortR};
+    auto pairOut = [&]() {
+        return PairOut{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.cShift.p, c.cBi.p, c.cOneSide.p, c.cOwn.p, c.cDelta0.p,
+                       c.cGamma0.p, c.cInvKappa.p, c.cKappa.p, c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.conCap};
+    };
+    const int grid = gridFor((long long)nLong * 32, 128);
+    k_long_cells<false><<<grid, 128, 0, st>>>(L, pairIn(c), c.box, g, c.colBuf, cnt1.p, nullptr, 0, pairOut());
+    k_long_long<false><<<grid, 128, 0, st>>>(L, pairIn(c), c.box, g, c.colBuf, cnt2.p, nullptr, 0, pairOut());
+    launchScanInt(c, cnt1.p, st1.p, nLong);
+    launchScanInt(c, cnt2.p, st2.p, nLong);
+    int t1 = 0, t2 = 0;
+    ALENS_CUDA(cudaMemcpyAsync(&t1, st1.p + nLong, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaMemcpyAsync(&t2, st2.p + nLong, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    c.launches += 3;
+    const long long extra = (long long)t1 + t2;
+    if (total + extra > 0x7fffffffLL) throw ArgError{ALENS_ERR_UNSUPPORTED, "collect: more than 2^31 constraints on one GPU"};
+    if (extra > 0) {
+        c.nCon = total; // (rows to keep when the arrays are re-laid out)
+        reserveConstraints(c, (size_t)(total + extra), true);
+        if (t1 > 0) k_long_cells<true><<<grid, 128, 0, st>>>(L, pairIn(c), c.box, g, c.colBuf, nullptr, st1.p, total, pairOut());
+        if (t2 > 0) k_long_long<true><<<grid, 128, 0, st>>>(L, pairIn(c), c.box, g, c.colBuf, nullptr, st2.p, total + t1, pairOut());
+        c.launches += 2;
+    }
+    ALENS_CUDA(cudaGetLastError());
+    c.nLongRows = extra;
+    return extra;
 }
 
 void collectPairs(Context &c) {
@@ -1102,6 +1345,8 @@ void collectPairs(Context &c) {
     }
 
     ALENS_CUDA(cudaGetLastError());
+    c.nLongRods = c.nLongRows = 0;
+    if (!c.comm.active && c.shortR < c.maxRLocal) total += collectLongRods(c, total);
     c.nCon = c.nColl = total;
 }
 
@@ -1245,6 +1490,12 @@ void preloadCollideKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_pack));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_rod_wrap));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mix_search<false>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_long_flags));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_long_list));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_long_cells<false>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_long_cells<true>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_long_long<false>));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_long_long<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_mix_search<true>));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_global_index));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_local_image));

@@ -209,6 +209,10 @@ struct Context {
     double skin = 0;               // how far a rod may stray outside its owner's slab
     double ghostWidth = 0;         // cutoff + skin
     double maxRadiusGlobal = 0;    // max over ALL ranks of lengthCollision/2 + radiusCollision (sets the cell size)
+    double meanRLocal = 0;         // mean of the same quantity (polydisperse rods: see shortR)
+    double shortR = 0;             // bounding radius the cell grid is sized for; rods above it take the long-rod pass
+    double optLongRods = 2.0;      // shortR = this factor x mean bounding radius when the longest rod exceeds it (0: off)
+    long long nLongRods = 0, nLongRows = 0; // statistics of the last collect
     double maxRLocal = 0;          // max over this context's rods of lengthCollision/2 + radiusCollision ...
     double maxRLRatio = -1, maxRDRatio = -1; // ... for these collision ratios (recomputed on the device when they change)
     int strays = 0;
@@ -428,6 +432,6 @@ inline int gridFor(long long n, int block) { return (int)((n + block - 1) / bloc
 void launchScanInt(Context &c, const int *in, int *out, int n);
 void wrapRodPositions(Context &c);
 void commMigrate(Context &c, long long *nSent, long long *nReceived);
-double hostMaxRadius(int n, const double *len, const double *rad, double lRatio, double dRatio);
+double hostMaxRadius(int n, const double *len, const double *rad, double lRatio, double dRatio, double *meanOut = nullptr);
 
 } // namespace alens

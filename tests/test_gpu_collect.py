@@ -227,3 +227,30 @@ def test_set_rod_state_is_set_rods_without_the_static_fields(ctx, oracle):
     with pytest.raises(alens_b200.AlensError):
         c2.set_rod_state(np.zeros((0, 3)), np.zeros((0, 4)))  # no alens_set_rods yet: ALENS_ERR_STATE
     c2.close()
+
+
+@pytest.mark.parametrize("pbc,sigma,n,box", [((1, 1, 1), 0.2, 9000, 2.4), ((0, 1, 0), 0.4, 7000, 2.4), ((1, 1, 1), 0.7, 6000, 2.0)])
+def test_polydisperse_rods_long_rod_pass(ctx, oracle, pbc, sigma, n, box):
+    """log-normal lengths: the cell grid is sized for twice the mean bounding radius, the few longer rods are paired with
+    far partners by the long-rod pass -- the list must still be P_geo (all block fields bit for bit), and equal to the list
+    of the plain search with cells sized for the longest rod (long_rods = 0)"""
+    rods = random_rods(n, box, seed=41, length=0.1, radius=0.02, length_sigma=sigma, frac_sphere=0.05)
+    rods["length"][::60] = 0.44 * box  # a few rods that cross many cells: most of their contacts are far from their centre
+    rods["length"] = np.minimum(rods["length"], 0.45 * box)  # (one image per pair: shorter than half the box)
+    lo, hi = [0, 0, 0], [box] * 3
+    got = gpu_collect(ctx, rods, lo, hi, pbc, 0.05).copy()
+    st = ctx.get_long_rod_stats()
+    want, _ = oracle_collect(oracle, rods, lo, hi, pbc, 0.05)
+    assert_blocks_equal(got, want)
+    assert st["long_rods"] > 10 and st["short_radius"] < st["max_radius"]
+    assert st["long_rows"] > (20 if sigma < 0.5 else 0), st  # contacts the 27-cell stencil cannot see
+    ctx.set_option("long_rods", 0)
+    plain = gpu_collect(ctx, rods, lo, hi, pbc, 0.05).copy()
+    assert ctx.get_long_rod_stats()["long_rods"] == 0
+    ctx.set_option("long_rods", 200)
+    assert_blocks_equal(got, plain)
+    # and the solve runs on the extended list
+    gpu_collect(ctx, rods, lo, hi, pbc, 0.05)
+    ctx.calc_mobility(1.0)
+    rep = ctx.solve_constraints(np.zeros(6 * n), 1e-4, 1e-5, 50, 0)
+    assert rep.iterations > 0 and np.isfinite(rep.residual)
