@@ -134,12 +134,19 @@ class ClockSampler:
         return out
 
 
+LENGTH_SIGMA = float(os.environ.get("ALENS_LENGTH_SIGMA", "0"))  # polydisperse variant of S1 (not the headline workload)
+
+
 def make_workload(n, phi, seed, kind="S1"):
     """returns rods and the box edge lengths (3-vector, low corner at the origin)"""
     if kind == "S2":
         return dense_nematic(n, phi, seed)
     box = box_for_volume_fraction(n, L_ROD, R_ROD, phi)
     rods = random_rods(n, box, L_ROD, R_ROD, seed=seed)
+    if LENGTH_SIGMA > 0:  # log-normal lengths with the same mean (setInitialFromConfig draws them like this, :228-232)
+        rng = np.random.default_rng(seed + 99)
+        L = L_ROD * np.exp(LENGTH_SIGMA * rng.normal(size=n) - 0.5 * LENGTH_SIGMA**2)
+        rods["length"] = np.minimum(L, 0.4 * box)
     return rods, np.full(3, box)
 
 
