@@ -633,7 +633,6 @@ int alens_set_option(alens_ctx *ctx, const char *name, long long value) {
         else if (k == "l2_fetch") { // cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes): a device-wide hint
             ALENS_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
         }
-        else if (k == "u_window") c.optUWindow = value != 0;
         else if (k == "find_minb") c.optFindMinB = (value == 5 || value == 3) ? (int)value : 4;
         else if (k == "find_split") c.optFindSplit = value != 0;
         else if (k == "find_split_minb") c.optFindSplitMinB = value == 6 ? 6 : 8;

@@ -280,9 +280,8 @@ struct Context {
     long long nInc = 0, incStride = 0; // slots; component stride of incCol (multiple of 4, > nInc)
     long long nOneSide = 0, nBilateral = 0; // host-side counts of appended one-sided / bilateral blocks
     int optForceKernel = 3;                 // 3 = k_force_vel_rec (64-byte slot records + slot-ordered live bitmap kept by k_bb_tail), 1 = k_force_vel_act (rod-major slots, zero multipliers skipped), 0 = k_force_vel_lm (level-major, dense)
-    int optUWindow = 0; // experiment: see setupConstraints
     int optTailPush = 0;  // fused multi-GPU, measured alternative (slower): the tail kernel instead of the force kernel copies the mirrored rows of U to the neighbours (contiguous staging rows)
-    int optHaloDebug = 0; // timing experiments only (results are wrong): 1 = no remote U stores, 2 = no fence + ticket
+    int optHaloDebug = 0; // multi-GPU timing experiments only (results are wrong): 1 = no remote U stores, 2 = no fence
     int optStamps = 0, stampCap = 0, stampIters = 0; // per-iteration nanosecond stamps of the BBPGD kernels (instrumentation)
     DevBuf<unsigned long long> dStamps;
     unsigned long long *stampNow = nullptr;

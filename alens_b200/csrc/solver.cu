@@ -2332,16 +2332,6 @@ void setupConstraints(Context &c, const double *velNC, double dt) {
     const size_t vcap = (size_t)nc + 32; // (+ padding: bulk copies read whole 16-row groups)
     c.vX0.reserve(vcap); c.vX1.reserve(vcap); c.vG0.reserve(vcap); c.vG1.reserve(vcap);
     c.vB.reserve(vcap); c.vLbFlag.reserve(vcap); c.vTmp5.reserve(vcap); // vTmp5 = invKdt
-    if (c.optUWindow && !c.comm.active && !c.rU.external) { // experiment: U in cudaMalloc'ed, IPC-exported memory (as in multi-GPU runs)
-        double *p = nullptr;
-        ALENS_CUDA(cudaMalloc((void **)&p, 8 * (6 * (size_t)n + 64) * 2));
-        cudaIpcMemHandle_t h;
-        ALENS_CUDA(cudaIpcGetMemHandle(&h, p));
-        c.rU.release();
-        c.rU.p = p;
-        c.rU.cap = (6 * (size_t)n + 64) * 2;
-        c.rU.external = true;
-    }
     c.rU.reserve(6 * (size_t)n + 6); c.rF.reserve(6 * (size_t)n + 6);
     c.rUb.reserve(6 * (size_t)n + 6); c.rFb.reserve(6 * (size_t)n + 6);
     c.outFU.reserve(6 * (size_t)n + 6); c.outVU.reserve(6 * (size_t)n + 6);
@@ -2806,13 +2796,7 @@ static int solveBBPGD(Context &c, double tol, int maxIte) {
             launchTail(c, t, gridTail);
             return;
         }
-        if (!multi && (c.optHaloDebug & 4)) { // timing experiment: the HALO instantiation without any neighbour
-            HaloPush fake{};
-            fake.on = 1;
-            launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p, &fake);
-        } else {
-            launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p);
-        }
+        launchForceVel<2, false>(c, x, c.rU.p, nullptr, c.dScal.p);
         if (multi) commPushU(c, ++c.comm.seqHalo);
         launchTail(c, t, gridTail);
         if (multi) {
