@@ -525,4 +525,29 @@ long long refmix_search(int nTrg, const double *trgPos, const double *trgRs, int
     }
     return n;
 }
+
+// SylinderConfig::SylinderConfig(file) (SylinderConfig.cpp:6-90): the parsed run parameters as a flat array, for the test
+// of the mirror's own reader.  out[0..33]; returns the number of boundaries.
+int refsys_parse_config(const char *yamlPath, double *out) {
+    initOnce(0);
+    SylinderConfig c(yamlPath);
+    int k = 0;
+    out[k++] = c.rngSeed; out[k++] = c.logLevel; out[k++] = c.timerLevel;
+    for (int d = 0; d < 3; d++) out[k++] = c.simBoxLow[d];
+    for (int d = 0; d < 3; d++) out[k++] = c.simBoxHigh[d];
+    for (int d = 0; d < 3; d++) out[k++] = c.simBoxPBC[d] ? 1 : 0;
+    out[k++] = c.monolayer ? 1 : 0;
+    for (int d = 0; d < 3; d++) out[k++] = c.initBoxLow[d];
+    for (int d = 0; d < 3; d++) out[k++] = c.initBoxHigh[d];
+    for (int d = 0; d < 3; d++) out[k++] = c.initOrient[d];
+    out[k++] = c.initCircularX ? 1 : 0; out[k++] = c.initPreSteps;
+    out[k++] = c.viscosity; out[k++] = c.KBT; out[k++] = c.linkKappa; out[k++] = c.linkGap;
+    out[k++] = c.sylinderFixed ? 1 : 0; out[k++] = c.sylinderNumber; out[k++] = c.sylinderLength;
+    out[k++] = c.sylinderLengthSigma; out[k++] = c.sylinderDiameter; out[k++] = c.sylinderDiameterColRatio;
+    out[k++] = c.sylinderLengthColRatio; out[k++] = c.sylinderColBuf;
+    out[k++] = c.dt; out[k++] = c.timeTotal; out[k++] = c.timeSnap; out[k++] = c.conResTol; out[k++] = c.conMaxIte;
+    out[k++] = c.conSolverChoice;
+    out[k] = k; // self-check: number of values written before this one
+    return (int)c.boundaryPtr.size();
+}
 }
