@@ -680,7 +680,7 @@ int alens_get_long_rod_stats(alens_ctx *ctx, long long *nLongRods, long long *nL
         if (nLongRods) *nLongRods = c.nLongRods;
         if (nLongRows) *nLongRows = c.nLongRows;
         if (shortRadius) *shortRadius = c.shortR;
-        if (maxRadius) *maxRadius = c.maxRLocal;
+        if (maxRadius) *maxRadius = c.gridMaxR;
     });
 }
 

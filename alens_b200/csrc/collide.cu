@@ -903,6 +903,10 @@ void rodsUploaded(Context &c, bool wrap) {
     c.shortR = maxR;
     if (!multi && c.optLongRods > 0 && c.meanRLocal > 0 && maxR > c.optLongRods * c.meanRLocal) c.shortR = c.optLongRods * c.meanRLocal;
     if (multi) {
+        // (the ghost layer is as wide as the longest rod of ALL ranks needs; the cells follow this rank's own mean)
+        if (c.optLongRods > 0 && c.meanRLocal > 0 && c.maxRadiusGlobal > c.optLongRods * c.meanRLocal)
+            c.shortR = c.optLongRods * c.meanRLocal;
+        else c.shortR = c.maxRadiusGlobal;
         c.ghostWidth = (2 * c.maxRadiusGlobal + c.colBuf) * (1.0 + 1e-9) + c.skin;
         if (c.slabHi - c.slabLo < 2 * c.ghostWidth)
             throw ArgError{ALENS_ERR_ARG, "slab decomposition: a slab must be at least 2 x (cutoff + skin) wide"};
@@ -926,7 +930,8 @@ void rodsUploaded(Context &c, bool wrap) {
         maxR = c.maxRadiusGlobal;
     }
     const int n = c.nRods;
-    chooseGrid(c, multi ? maxR : c.shortR);
+    c.gridMaxR = maxR;
+    chooseGrid(c, c.shortR);
     if (c.shortR < maxR) { // the long-rod pass needs at least 3 cells along a periodic axis (one image per neighbour cell)
         bool ok = true;
         for (int k = 0; k < 3; k++) ok = ok && (!c.grid.per[k] || c.grid.n[k] >= 3);
@@ -1086,7 +1091,15 @@ __global__ void __launch_bounds__(128) k_long_cells(LongIn L, PairIn in, Box box
     const RodGeom A = loadRod(in, a);
     const double hA = 0.5 * A.lc;
     const double reach = (L.shortR + A.rc + colBuf) * (1.0 + 1e-9);
-    const double ctr[3] = {A.c.x, A.c.y, A.c.z}, dir[3] = {A.d.x, A.d.y, A.d.z};
+    // slab decomposition: a ghost (or an owned rod that strayed across the periodic face) is binned, and seen, at its
+    // APPARENT position along the slab axis: original coordinate + image x box length; the pair's image code is the
+    // difference of the two images there (the slab axis of the grid is not periodic)
+    const int imgA = g.axis >= 0 ? in.sImg[a] : 0;
+    const bool ghostA = g.axis >= 0 && in.sGhost[a] != 0;
+    double ctr[3] = {A.c.x, A.c.y, A.c.z};
+    if (g.axis >= 0) ctr[g.axis] += imgA * g.axisLen;
+    const Vec3 cA = v3(ctr[0], ctr[1], ctr[2]);
+    const double dir[3] = {A.d.x, A.d.y, A.d.z};
     const int cellA = L.cellOfUser[L.sUser[a]];
     const int ca[3] = {cellA % g.n[0], (cellA / g.n[0]) % g.n[1], cellA / (g.n[0] * g.n[1])};
     int u0[3], u1[3];
@@ -1128,11 +1141,17 @@ __global__ void __launch_bounds__(128) k_long_cells(LongIn L, PairIn in, Box box
                     bool hit = false;
                     int si = 0, sj = 0, code = 13;
                     Contact ct;
-                    if (b < je && !L.flag[b]) { // short partners only: long ones belong to k_long_long
-                        const Vec3 cb = v3(in.sX[b] + shift.x, in.sY[b] + shift.y, in.sZ[b] + shift.z);
+                    if (b < je && !L.flag[b] && !(ghostA && in.sGhost[b])) { // short partners only: long ones belong to k_long_long
+                        double cbv[3] = {in.sX[b] + shift.x, in.sY[b] + shift.y, in.sZ[b] + shift.z};
+                        int kb[3] = {kk[0], kk[1], kk[2]};
+                        if (g.axis >= 0) {
+                            const int imgB = in.sImg[b];
+                            cbv[g.axis] += imgB * g.axisLen;
+                            kb[g.axis] = imgB - imgA;
+                        }
                         const double rb = 0.5 * in.sLc[b] + in.sRc[b] + A.rc + colBuf;
-                        if (pointSegDist2(cb, A.c, A.d, hA) <= rb * rb * (1.0 + 1e-9))
-                            hit = longPairHit(in, box, colBuf, a, b, kk[0], kk[1], kk[2], si, sj, code, ct);
+                        if (pointSegDist2(v3(cbv[0], cbv[1], cbv[2]), cA, A.d, hA) <= rb * rb * (1.0 + 1e-9))
+                            hit = longPairHit(in, box, colBuf, a, b, kb[0], kb[1], kb[2], si, sj, code, ct);
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, hit);
                     if (FILL && hit) emitRow(out, (size_t)(pos + cnt + __popc(m & ((1u << lane) - 1u))), si, sj, code, ct, in);
@@ -1151,6 +1170,11 @@ __global__ void __launch_bounds__(128) k_long_long(LongIn L, PairIn in, Box box,
     const double hA = 0.5 * A.lc;
     const int cellA = L.cellOfUser[L.sUser[a]];
     const int ca[3] = {cellA % g.n[0], (cellA / g.n[0]) % g.n[1], cellA / (g.n[0] * g.n[1])};
+    const int imgA = g.axis >= 0 ? in.sImg[a] : 0;
+    const bool ghostA = g.axis >= 0 && in.sGhost[a] != 0;
+    double ctrA[3] = {A.c.x, A.c.y, A.c.z};
+    if (g.axis >= 0) ctrA[g.axis] += imgA * g.axisLen; // apparent position (see k_long_cells)
+    const Vec3 cA = v3(ctrA[0], ctrA[1], ctrA[2]);
     long long pos = FILL ? base + starts[w] : 0;
     int cnt = 0;
     for (int l0 = w + 1; l0 < L.nLong; l0 += 32) {
@@ -1161,19 +1185,27 @@ __global__ void __launch_bounds__(128) k_long_long(LongIn L, PairIn in, Box box,
         if (lb < L.nLong) {
             const int b = L.list[lb];
             double cb[3] = {in.sX[b], in.sY[b], in.sZ[b]};
-            const double ctr[3] = {A.c.x, A.c.y, A.c.z};
+            const double *ctr = ctrA;
             int kk[3] = {0, 0, 0};
+            int kcell[3] = {0, 0, 0}; // image in units of the grid (the slab axis of the grid is not periodic)
             for (int k = 0; k < 3; k++)
                 if (g.per[k] && box.len[k] > 0) { // nearest image of b
                     kk[k] = -(int)rint((cb[k] - ctr[k]) / box.len[k]);
                     cb[k] += kk[k] * box.len[k];
+                    kcell[k] = kk[k];
                 }
+            if (g.axis >= 0) {
+                const int imgB = in.sImg[b];
+                cb[g.axis] += imgB * g.axisLen;
+                kk[g.axis] = imgB - imgA;
+            }
+            const bool bothGhost = ghostA && in.sGhost[b];
             const int cellB = L.cellOfUser[L.sUser[b]];
-            const int cbx = cellB % g.n[0] + kk[0] * g.n[0], cby = (cellB / g.n[0]) % g.n[1] + kk[1] * g.n[1],
-                      cbz = cellB / (g.n[0] * g.n[1]) + kk[2] * g.n[2];
+            const int cbx = cellB % g.n[0] + kcell[0] * g.n[0], cby = (cellB / g.n[0]) % g.n[1] + kcell[1] * g.n[1],
+                      cbz = cellB / (g.n[0] * g.n[1]) + kcell[2] * g.n[2];
             const bool stencil = abs(cbx - ca[0]) <= 1 && abs(cby - ca[1]) <= 1 && abs(cbz - ca[2]) <= 1;
             const double rb = 0.5 * in.sLc[b] + in.sRc[b] + A.rc + colBuf;
-            if (!stencil && pointSegDist2(v3(cb[0], cb[1], cb[2]), A.c, A.d, hA) <= rb * rb * (1.0 + 1e-9))
+            if (!stencil && !bothGhost && pointSegDist2(v3(cb[0], cb[1], cb[2]), cA, A.d, hA) <= rb * rb * (1.0 + 1e-9))
                 hit = longPairHit(in, box, colBuf, a, b, kk[0], kk[1], kk[2], si, sj, code, ct);
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -1346,7 +1378,7 @@ void collectPairs(Context &c) {
 
     ALENS_CUDA(cudaGetLastError());
     c.nLongRods = c.nLongRows = 0;
-    if (!c.comm.active && c.shortR < c.maxRLocal) total += collectLongRods(c, total);
+    if (c.shortR < c.gridMaxR) total += collectLongRods(c, total);
     c.nCon = c.nColl = total;
 }
 

@@ -210,6 +210,7 @@ struct Context {
     double ghostWidth = 0;         // cutoff + skin
     double maxRadiusGlobal = 0;    // max over ALL ranks of lengthCollision/2 + radiusCollision (sets the cell size)
     double meanRLocal = 0;         // mean of the same quantity (polydisperse rods: see shortR)
+    double gridMaxR = 0;           // the largest bounding radius the pair search has to serve (all ranks)
     double shortR = 0;             // bounding radius the cell grid is sized for; rods above it take the long-rod pass
     double optLongRods = 2.0;      // shortR = this factor x mean bounding radius when the longest rod exceeds it (0: off)
     long long nLongRods = 0, nLongRows = 0; // statistics of the last collect

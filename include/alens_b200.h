@@ -315,7 +315,7 @@ int alens_get_pool_stats(alens_ctx *ctx, long long *nCollision, long long *nOneS
 int alens_get_live_stats(alens_ctx *ctx, long long *liveSlots, long long *liveRods);
 /* number of rods / cells / candidate pairs that passed the broad phase in the last collection */
 int alens_get_collect_stats(alens_ctx *ctx, long long *nCells, long long *nCandidates, long long *nHits);
-/* Polydisperse rods (one rank): the cell edge follows shortRadius = min(max, long_rods x mean) of the rods' bounding radii
+/* Polydisperse rods: the cell edge follows shortRadius = min(max, long_rods x mean) of the rods' bounding radii
  * (lengthCollision / 2 + radiusCollision; option "long_rods" in percent, default 200, 0 = off); rods above it are paired
  * with partners beyond the 27-cell stencil by a separate exact pass whose rows follow the stencil rows.  Statistics of the
  * last alens_collect_pair_collision: long rods, rows they added, the two radii. */

@@ -102,6 +102,7 @@ def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None,
                     c.calc_velocity_noncon(vel_brown=vb)
                     v = None
                 rep = c.solve_constraints(v, dt, res, max_ite, 0)
+            res_r["long"] = c.get_long_rod_stats()
             res_r["migrated"] = tuple(moved)
             res_r["identity"] = c.get_rod_identity()
             res_r.update(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), ghosts=c.num_ghosts(),

@@ -350,3 +350,41 @@ def test_multirank_tail_push_alternative():
         for r in ranks:
             full[r["idx"]] = r[name].reshape(-1, 6)
         assert np.abs(full.reshape(-1) - ref[name]).max() < 1e-9 * np.abs(ref[name]).max(), name
+
+
+@pytest.mark.parametrize("nranks,pbc", [(2, (1, 1, 1)), (3, (0, 1, 1))])
+def test_multirank_polydisperse_long_rod_pass(nranks, pbc, placement):
+    """rods much longer than the mean with the slab decomposition: the cells follow twice the rank's mean bounding radius, the
+    ghost layer the longest rod of all ranks; the long-rod pass sees ghosts at their apparent positions -- list, gamma and
+    velocities must equal the single-rank run (which itself equals P_geo, test_gpu_collect.py)"""
+    n, box, colbuf, mu, dt, res = 7000, (2.4 * nranks, 1.6, 1.6), 0.05, 1.0, 1e-4, 1e-6
+    lo, hi = [0.0, 0.0, 0.0], list(box)
+    rods = random_rods(n, box, seed=51, length=0.1, radius=0.02, length_sigma=0.2, frac_sphere=0.05)
+    rods["length"][::50] = 0.7  # 14 % of a slab, 7 x the mean
+    rods = slab_ordered(rods, lo, hi, nranks)
+    vnc = thermal_velocity(rods, mu, dt, seed=6)
+    ref = single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, 150, vnc)
+    ranks = run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, 150, vnc=vnc, devices=_devices(placement, nranks))
+    _check_mode(ranks, placement)
+    allb = np.concatenate([r["blocks"] for r in ranks])
+    allb = allb[canonical_order(allb)]
+    same = np.zeros(len(allb), bool)
+    same[1:] = ((allb["gidI"][1:] == allb["gidI"][:-1]) & (allb["gidJ"][1:] == allb["gidJ"][:-1]) &
+                (allb["labJ"][1:] == allb["labJ"][:-1]).all(axis=1))
+    dup = np.nonzero(same)[0]
+    assert len(dup) > 0
+    for f in BLOCK_FIELDS + ("gamma", "stress"):
+        assert np.array_equal(allb[f][dup], allb[f][dup - 1]), f"mirrored rows differ in {f}"
+    uniq = allb[~same]
+    want = ref["blocks"][canonical_order(ref["blocks"])]
+    assert len(uniq) == len(want) > 3000
+    for f in BLOCK_FIELDS:
+        assert np.array_equal(uniq[f], want[f]), f
+    assert {r["report"].iterations for r in ranks} == {ref["report"].iterations}
+    assert np.abs(uniq["gamma"] - want["gamma"]).max() < 1e-8 * np.abs(want["gamma"]).max()  # 150 BB iterations
+    for name in ("velU", "forceU"):
+        full = np.zeros_like(ref[name]).reshape(-1, 6)
+        for r in ranks:
+            full[r["idx"]] = r[name].reshape(-1, 6)
+        assert np.abs(full.reshape(-1) - ref[name]).max() < 1e-8 * np.abs(ref[name]).max(), name  # (north_star tolerance)
+    assert any(r["long"]["long_rows"] > 0 for r in ranks) and all(r["long"]["short_radius"] < r["long"]["max_radius"] for r in ranks)
