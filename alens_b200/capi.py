@@ -36,7 +36,7 @@ EXPORTS = [
     "alens_comm_connect", "alens_comm_connect_local", "alens_num_ghosts", "alens_prepare_step", "alens_set_velocity_noncon",
     "alens_set_velocity_noncon_async", "alens_collect_boundary_collision", "alens_collect_link_bilateral", "alens_calc_velocity_noncon", "alens_calc_velocity_brown",
     "alens_set_profiling", "alens_bcqp_solve", "alens_set_option", "alens_time_kernel",
-    "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest",
+    "alens_dcp_query", "alens_pair_functor", "alens_comm_mode", "alens_constraint_digest", "alens_sum_constraint_stress",
     "alens_get_live_stats", "alens_bcqp_create_csr", "alens_bcqp_create_constraint", "alens_bcqp_set_lower_bound",
     "alens_bcqp_set_upper_bound", "alens_bcqp_get_bounds", "alens_bcqp_run", "alens_bcqp_history", "alens_bcqp_size",
     "alens_bcqp_destroy", "alens_collect_protein_bilateral", "alens_get_pool_stats", "alens_get_stamps", "alens_mix_pair_search", "alens_migrate_rods", "alens_get_rod_identity", "alens_set_rod_state", "alens_get_long_rod_stats", "alens_set_rod_tags", "alens_get_rod_tags",
@@ -437,6 +437,14 @@ class Context:
         f = (C.c_double * 3)()
         self._call("alens_constraint_digest", u, f)
         return dict(rows=int(u[0]), list_hash=int(u[1]), gamma_hash=int(u[2]), sum_gamma=f[0], sum_gamma2=f[1], sum_wgamma=f[2])
+
+    def sum_constraint_stress(self, with_one_side=False):
+        """(uni, bi): 3x3 sums of gamma * unit stress over the unilateral / bilateral blocks of the last solve
+        (ConstraintCollector::sumLocalConstraintStress after writeBackGamma), reduced on the device"""
+        u = np.zeros(9)
+        b = np.zeros(9)
+        self._call("alens_sum_constraint_stress", C.c_int(1 if with_one_side else 0), _dp(u), _dp(b))
+        return u.reshape(3, 3), b.reshape(3, 3)
 
     def comm_mode(self):
         a, b = C.c_int(0), C.c_int(0)

@@ -522,6 +522,29 @@ struct BlocksIn {
     int globalIndexBase;
 };
 
+// collideStress of collision block k for unit gamma, by the shape of the two rods (SylinderNear.hpp:289-290, :350-351,
+// :409-410); J at the periodic image the block was found with
+__device__ __forceinline__ void blockUnitStress(const BlocksIn &in, long long k, int si, int sj, Vec3 labI, Vec3 labJ,
+                                                double stress[9]) {
+    const int code = in.shift[k];
+    const int kx = code % 3 - 1, ky = (code / 3) % 3 - 1, kz = code / 9 - 1;
+    const Vec3 cI = v3(in.sX[si], in.sY[si], in.sZ[si]);
+    const Vec3 cJ = v3(in.sX[sj] + kx * in.box.len[0], in.sY[sj] + ky * in.box.len[1], in.sZ[sj] + kz * in.box.len[2]);
+    const Vec3 dI = v3(in.sDx[si], in.sDy[si], in.sDz[si]), dJ = v3(in.sDx[sj], in.sDy[sj], in.sDz[sj]);
+    const double lcI = in.sLc[si], rcI = in.sRc[si], lcJ = in.sLc[sj], rcJ = in.sRc[sj];
+    const bool sa = lcI < 2 * rcI, sb = lcJ < 2 * rcJ;
+    const Vec3 ez = v3(0, 0, 1);
+    if (sa && sb) { // two spheres
+        collideStress(ez, ez, cI, cJ, 0, 0, lcI * 0.5 + rcI, lcJ * 0.5 + rcJ, 1.0, labI, labJ, stress);
+    } else if (sa) { // sphere I, sylinder J
+        collideStress(ez, dJ, cI, cJ, 0, lcJ, lcI * 0.5 + rcI, rcJ, 1.0, labI, labJ, stress);
+    } else if (sb) { // sylinder I, sphere J: same call with (sphere, sylinder) argument order
+        collideStress(ez, dI, cJ, cI, 0, lcI, lcJ * 0.5 + rcJ, rcI, 1.0, labJ, labI, stress);
+    } else {
+        collideStress(dI, dJ, cI, cJ, lcI, lcJ, rcI, rcJ, 1.0, labI, labJ, stress);
+    }
+}
+
 // one thread per collision block: assemble the 272-byte record (and the unit-gamma stress)
 __global__ void k_blocks_out(long long n, BlocksIn in, int withStress, int writeBack, alens_constraint_block *out) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -548,27 +571,8 @@ __global__ void k_blocks_out(long long n, BlocksIn in, int withStress, int write
         b.labI[c] = in.labI[k + c * S];
         b.labJ[c] = in.labJ[k + c * S];
     }
-    if (withStress) {
-        const int code = in.shift[k];
-        const int kx = code % 3 - 1, ky = (code / 3) % 3 - 1, kz = code / 9 - 1;
-        const Vec3 cI = v3(in.sX[si], in.sY[si], in.sZ[si]);
-        const Vec3 cJ = v3(in.sX[sj] + kx * in.box.len[0], in.sY[sj] + ky * in.box.len[1],
-                           in.sZ[sj] + kz * in.box.len[2]);
-        const Vec3 dI = v3(in.sDx[si], in.sDy[si], in.sDz[si]), dJ = v3(in.sDx[sj], in.sDy[sj], in.sDz[sj]);
-        const double lcI = in.sLc[si], rcI = in.sRc[si], lcJ = in.sLc[sj], rcJ = in.sRc[sj];
-        const bool sa = lcI < 2 * rcI, sb = lcJ < 2 * rcJ;
-        const Vec3 labI = v3(b.labI[0], b.labI[1], b.labI[2]), labJ = v3(b.labJ[0], b.labJ[1], b.labJ[2]);
-        const Vec3 ez = v3(0, 0, 1);
-        if (sa && sb) { // SylinderNear.hpp:289-290
-            collideStress(ez, ez, cI, cJ, 0, 0, lcI * 0.5 + rcI, lcJ * 0.5 + rcJ, 1.0, labI, labJ, b.stress);
-        } else if (sa) { // sphere I, sylinder J: SylinderNear.hpp:350-351
-            collideStress(ez, dJ, cI, cJ, 0, lcJ, lcI * 0.5 + rcI, rcJ, 1.0, labI, labJ, b.stress);
-        } else if (sb) { // sylinder I, sphere J: same call with (sphere, sylinder) argument order
-            collideStress(ez, dI, cJ, cI, 0, lcI, lcJ * 0.5 + rcJ, rcI, 1.0, labJ, labI, b.stress);
-        } else { // SylinderNear.hpp:409-410
-            collideStress(dI, dJ, cI, cJ, lcI, lcJ, rcI, rcJ, 1.0, labI, labJ, b.stress);
-        }
-    }
+    if (withStress)
+        blockUnitStress(in, k, si, sj, v3(b.labI[0], b.labI[1], b.labI[2]), v3(b.labJ[0], b.labJ[1], b.labJ[2]), b.stress);
     if (writeBack && in.gamma) { // ConstraintCollector.cpp:449-458
         b.gamma = in.gamma[k];
         for (int c = 0; c < 9; c++) b.stress[c] *= b.gamma;
@@ -606,6 +610,73 @@ void downloadBlocks(Context &c, alens_constraint_block *out, long long cap, bool
                 for (int k = 0; k < 9; k++) b.stress[k] *= b.gamma;
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sum of the block stresses after the write-back of gamma (ConstraintCollector::sumLocalConstraintStress,
+// Constraint/ConstraintCollector.cpp:38-74, as SylinderSystem::calcConStress uses it every step,
+// SylinderSystem.cpp:1226-1263) without bringing the blocks to the host: collision blocks are evaluated and reduced on the
+// device (fixed grid, per-CTA partial sums added in CTA order: the result does not depend on the run), the appended
+// blocks (boundary / link / protein: their unit stress is the host's) on the host with the solved gamma.
+static constexpr int kStressCtas = 148 * 4;
+__global__ void __launch_bounds__(128) k_stress_sum(long long n, BlocksIn in, const unsigned char *__restrict__ own,
+                                                    double *__restrict__ part) {
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t S = in.stride;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        if (own && !own[k]) continue; // a row held by two ranks is counted by the owner of rod I
+        const Vec3 labI = v3(in.labI[k], in.labI[k + S], in.labI[k + 2 * S]);
+        const Vec3 labJ = v3(in.labJ[k], in.labJ[k + S], in.labJ[k + 2 * S]);
+        double s[9];
+        blockUnitStress(in, k, in.idxI[k], in.idxJ[k], labI, labJ, s);
+        const double gm = in.gamma[k];
+        for (int c = 0; c < 9; c++) acc[c] += s[c] * gm;
+    }
+    __shared__ double sh[4][9];
+    for (int c = 0; c < 9; c++) {
+        double v = acc[c];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) part[9 * (size_t)blockIdx.x + threadIdx.x] = ((sh[0][threadIdx.x] + sh[1][threadIdx.x]) + sh[2][threadIdx.x]) + sh[3][threadIdx.x];
+}
+
+void sumConstraintStress(Context &c, bool withOneSide, double uni[9], double bi[9]) {
+    if (!c.haveSolution) throw ArgError{ALENS_ERR_STATE, "alens_sum_constraint_stress: needs a solve"};
+    for (int k = 0; k < 9; k++) uni[k] = bi[k] = 0;
+    cudaStream_t st = c.stream;
+    const long long nColl = c.nColl, nHost = c.nCon - c.nColl;
+    const bool multi = c.comm.active;
+    std::vector<double> part, g((size_t)nHost);
+    std::vector<unsigned char> own((size_t)nHost, 1);
+    DevBuf<double> dPart;
+    int grid = 0;
+    if (nColl > 0) {
+        grid = (int)std::min<long long>(kStressCtas, (nColl + 127) / 128);
+        dPart.reserve(9 * (size_t)grid);
+        BlocksIn in{c.cIdxI.p, c.cIdxJ.p, c.cGidI.p, c.cGidJ.p, c.sUser.p, c.uGlobalIdx.p, c.cShift.p, c.cDelta0.p, c.cGamma0.p,
+                    c.cN.p, c.cPI.p, c.cPJ.p, c.cLabI.p, c.cLabJ.p, c.sX.p, c.sY.p, c.sZ.p, c.sDx.p, c.sDy.p,
+                    c.sDz.p, c.sLc.p, c.sRc.p, c.xSolution, c.conCap, c.box, 0};
+        k_stress_sum<<<grid, 128, 0, st>>>(nColl, in, multi ? c.cOwn.p : nullptr, dPart.p);
+        c.launches++;
+        ALENS_CUDA(cudaGetLastError());
+        part.resize(9 * (size_t)grid);
+        ALENS_CUDA(cudaMemcpyAsync(part.data(), dPart.p, 8 * part.size(), cudaMemcpyDeviceToHost, st));
+    }
+    if (nHost > 0) {
+        ALENS_CUDA(cudaMemcpyAsync(g.data(), c.xSolution + nColl, 8 * (size_t)nHost, cudaMemcpyDeviceToHost, st));
+        if (multi) ALENS_CUDA(cudaMemcpyAsync(own.data(), c.cOwn.p + nColl, (size_t)nHost, cudaMemcpyDeviceToHost, st));
+    }
+    ALENS_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < grid; b++) // collision blocks are unilateral and two-sided
+        for (int k = 0; k < 9; k++) uni[k] += part[9 * (size_t)b + k];
+    for (long long i = 0; i < nHost; i++) {
+        const alens_constraint_block &b = c.hostBlocks[(size_t)i];
+        if ((b.oneSide && !withOneSide) || !own[(size_t)i]) continue;
+        double *dst = b.bilateral ? bi : uni;
+        for (int k = 0; k < 9; k++) dst[k] += b.stress[k] * g[(size_t)i];
     }
 }
 
@@ -804,6 +875,7 @@ void preloadBlockKernels() {
     cudaFuncAttributes a;
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_append));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_blocks_out));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, k_stress_sum));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_dcp_batch));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_protein_blocks));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_constraint_digest));

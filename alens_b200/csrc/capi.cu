@@ -871,6 +871,13 @@ int alens_constraint_digest(alens_ctx *ctx, unsigned long long counts3[3], doubl
     });
 }
 
+int alens_sum_constraint_stress(alens_ctx *ctx, int withOneSide, double uniStress[9], double biStress[9]) {
+    return guarded(ctx, [&](Context &c) {
+        if (!uniStress || !biStress) throw ArgError{ALENS_ERR_ARG, "alens_sum_constraint_stress: null output"};
+        sumConstraintStress(c, withOneSide != 0, uniStress, biStress);
+    });
+}
+
 int alens_comm_mode(alens_ctx *ctx, int *connected, int *fused) {
     return guarded(ctx, [&](Context &c) {
         if (connected) *connected = c.comm.active ? 1 : 0;

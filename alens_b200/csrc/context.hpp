@@ -369,6 +369,7 @@ void rodsUploaded(Context &c, bool wrap);           // rod_pack + cell list + so
 void collectPairs(Context &c);                      // broad + narrow phase
 void appendBlocks(Context &c, const alens_constraint_block *b, long long n, const int *userIdx = nullptr);
 void downloadBlocks(Context &c, alens_constraint_block *out, long long cap, bool withStress, bool writeBack);
+void sumConstraintStress(Context &c, bool withOneSide, double uni[9], double bi[9]);
 void calcMobility(Context &c, double mu);
 void mobilityApply(Context &c, const double *x, double *y);
 void setupConstraints(Context &c, const double *velNC, double dt);

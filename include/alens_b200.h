@@ -327,6 +327,14 @@ int alens_get_long_rod_stats(alens_ctx *ctx, long long *nLongRods, long long *nL
  * slab decomposition each rank counts the rows whose rod I it owns, so the per-rank digests ADD UP to the digest of the
  * single-rank list (reference canonicalisation: Sylinder/Test2_MixLink/Verify.py:82-83 sorts by the same keys). */
 int alens_constraint_digest(alens_ctx *ctx, unsigned long long counts3[3], double sums3[3]);
+/* ConstraintCollector::sumLocalConstraintStress (Constraint/ConstraintCollector.cpp:38-74) after writeBackGamma, the sum
+ * SylinderSystem::calcConStress takes every step (SylinderSystem.cpp:1226-1263), without bringing the blocks to the host:
+ * row-major 3x3 sums of gamma * (unit stress) over the unilateral and the bilateral blocks of the last solve; one-sided
+ * blocks are skipped unless withOneSide.  Collision blocks are evaluated (collideStress, SylinderNear.hpp:432-519) and
+ * reduced on the device in a fixed order; appended blocks contribute the stress they were appended with.  LOCAL sums:
+ * with a slab decomposition a rank counts the blocks whose rod I it owns, and the caller adds the ranks' results as the
+ * reference does (Teuchos::reduceAll, :1252-1253).  ALENS_ERR_STATE before a solve. */
+int alens_sum_constraint_stress(alens_ctx *ctx, int withOneSide, double uniStress[9], double biStress[9]);
 
 /* ---- multi-GPU (one rank per GPU) ------------------------------------------------------
  * Slab decomposition along one box axis.  Replaces, for the constraint path, the FDPS ghost exchange inside

@@ -62,6 +62,21 @@ class Sylinder {
         d[1] = w * uy + z * ux;
         d[2] = 1.0 + (x * uy - y * ux);
     }
+    /// Sylinder::stepEuler (Sylinder.cpp:91-99) with EquatnHelper::rotateEquatn (Util/EquatnHelper.hpp:74-90) on the host:
+    /// used when a run is restarted (the device copy is stepped by alens_step_euler)
+    void stepEuler(double dt) {
+        for (int k = 0; k < 3; k++) pos[k] += vel[k] * dt;
+        const double w = std::sqrt(omega[0] * omega[0] + omega[1] * omega[1] + omega[2] * omega[2]);
+        if (w < std::numeric_limits<float>::epsilon()) return;
+        const double winv = 1 / w, sw = std::sin(w * dt / 2), cw = std::cos(w * dt / 2);
+        const double s = orientation[3], p[3] = {orientation[0], orientation[1], orientation[2]};
+        const double cr[3] = {omega[1] * p[2] - omega[2] * p[1], omega[2] * p[0] - omega[0] * p[2], omega[0] * p[1] - omega[1] * p[0]};
+        double q[4];
+        for (int k = 0; k < 3; k++) q[k] = s * sw * omega[k] * winv + cw * p[k] + sw * winv * cr[k];
+        q[3] = s * cw - (p[0] * omega[0] + p[1] * omega[1] + p[2] * omega[2]) * sw * winv;
+        const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        for (int k = 0; k < 4; k++) orientation[k] = q[k] / n;
+    }
     /// Eigen's quaternion * vector (QuaternionBase::_transformVector): uv = q.vec x v; uv += uv; v + w uv + q.vec x uv
     void rotate(const double v[3], double out[3]) const {
         const double x = orientation[0], y = orientation[1], z = orientation[2], w = orientation[3];

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <functional>
 #include <map>
 #include <random>
 #include <sstream>
@@ -209,10 +210,104 @@ class SylinderSystem {
         return rods;
     }
 
+    /// setInitialFromVTKFile (:406-476): the rods of a Sylinder_<snap>.pvtp written by writeResult (or by the reference):
+    /// centre = midpoint of the two end points, orientation = FromTwoVectors(ez, znorm), the Float32 cell arrays gid, group,
+    /// isImmovable, length, lengthCollision, radius, radiusCollision, vel, omega
+    static std::vector<Sylinder> readSylinderVTK(const std::string &pvtpFileName) {
+        const alens_vtk::PolyData pd = alens_vtk::readParallel(pvtpFileName);
+        const size_t n = pd.numberOfPoints() / 2; // two points per sylinder
+        const auto &gid = pd.cell("gid"), &group = pd.cell("group"), &imm = pd.cell("isImmovable");
+        const auto &len = pd.cell("length"), &lenC = pd.cell("lengthCollision"), &rad = pd.cell("radius");
+        const auto &radC = pd.cell("radiusCollision"), &znorm = pd.cell("znorm"), &vel = pd.cell("vel"), &omega = pd.cell("omega");
+        for (const alens_vtk::Array *a : {&gid, &group, &imm, &len, &lenC, &rad, &radC})
+            if (a->v.size() != n) throw std::runtime_error("readSylinderVTK: array length != number of rods in " + pvtpFileName);
+        for (const alens_vtk::Array *a : {&znorm, &vel, &omega})
+            if (a->v.size() != 3 * n) throw std::runtime_error("readSylinderVTK: vector array length != 3 x rods in " + pvtpFileName);
+        std::vector<Sylinder> rods(n);
+        ALENS_OMP_FOR
+        for (long long i = 0; i < (long long)n; i++) {
+            Sylinder &sy = rods[(size_t)i];
+            for (int k = 0; k < 3; k++) {
+                sy.pos[k] = (pd.points[6 * (size_t)i + k] + pd.points[6 * (size_t)i + 3 + k]) * 0.5;
+                sy.vel[k] = vel.v[3 * (size_t)i + k];
+                sy.omega[k] = omega.v[3 * (size_t)i + k];
+            }
+            sy.gid = (int)gid.v[(size_t)i];
+            sy.group = (int)group.v[(size_t)i];
+            sy.isImmovable = imm.v[(size_t)i] > 0;
+            sy.length = len.v[(size_t)i];
+            sy.lengthCollision = lenC.v[(size_t)i];
+            sy.radius = rad.v[(size_t)i];
+            sy.radiusCollision = radC.v[(size_t)i];
+            const double d[3] = {znorm.v[3 * (size_t)i], znorm.v[3 * (size_t)i + 1], znorm.v[3 * (size_t)i + 2]};
+            orientationFromDirection(d, sy.orientation);
+        }
+        return rods;
+    }
+
+    /// what a restart file (TimeStepInfo.txt, written by writeResult :509-521) holds
+    struct RestartInfo {
+        unsigned rngSeed = 0;
+        int stepCount = 0, snapID = 0;
+        std::string pvtpFileName, asciiFileName;
+    };
+    static RestartInfo readRestartFile(const std::string &restartFile) {
+        std::ifstream f(restartFile);
+        if (!f) throw std::runtime_error("reinitialize: cannot open " + restartFile);
+        RestartInfo r;
+        f >> r.rngSeed >> r.stepCount >> r.snapID >> r.pvtpFileName;
+        if (f.fail()) throw std::runtime_error("reinitialize: malformed restart file " + restartFile);
+        r.asciiFileName = r.pvtpFileName; // Sylinder_<snap>.pvtp -> SylinderAscii_<snap>.dat (:143-147)
+        const size_t dot = r.asciiFileName.find_last_of('.'), us = r.asciiFileName.find_last_of('_');
+        if (dot == std::string::npos || us == std::string::npos) throw std::runtime_error("reinitialize: bad pvtp name in " + restartFile);
+        r.asciiFileName.replace(dot, 5, ".dat");
+        r.asciiFileName.replace(us, 1, "Ascii_");
+        return r;
+    }
+
+    /// SylinderSystem::reinitialize (:106-175): resume from the snapshot a restart file names -- rods from the .pvtp, links
+    /// from the .dat next to it (both in getCurrentResultFolder()), one Euler step with the stored velocities (the
+    /// snapshot is written before the step that follows it), then stepCount and snapID move on by one.  The reference
+    /// re-seeds its generator with restartRngSeed + 1; the device-side Brownian generator is keyed by (rngSeed, stepCount),
+    /// so runConfig.rngSeed takes that value.
+    void reinitialize(const SylinderConfig &config, const std::string &restartFile, int /*argc*/, char ** /*argv*/,
+                      bool eulerStep = true) {
+        const RestartInfo info = readRestartFile(restartFile);
+        commRcp = getMPIWORLDTCOMM();
+        snapID = info.snapID;
+        const std::string baseFolder = getCurrentResultFolder();
+        std::vector<Sylinder> rods = readSylinderVTK(baseFolder + info.pvtpFileName);
+        setLinkMapFromFile(baseFolder + info.asciiFileName);
+        if (eulerStep && !config.sylinderFixed) {
+            const long long n = (long long)rods.size();
+            ALENS_OMP_FOR
+            for (long long i = 0; i < n; i++) rods[(size_t)i].stepEuler(config.dt);
+        }
+        int device = 0;
+        for (const char *name : {"ALENS_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"})
+            if (const char *v = std::getenv(name)) {
+                device = std::atoi(v);
+                break;
+            }
+        SylinderConfig resumed = config;
+        resumed.initPreSteps = 0; // no initial collision resolution on a restart (:106-175 has none)
+        restartRngSeed = info.rngSeed + 1;
+        resumed.rngSeed = restartRngSeed;
+        if (ctx_) {
+            alens_destroy(ctx_);
+            ctx_ = nullptr;
+        }
+        initialize(resumed, std::move(rods), device);
+        runConfig.initPreSteps = config.initPreSteps;
+        stepCount = info.stepCount + 1;
+        snapID = info.snapID + 1;
+    }
+
     /// rods are handed over by the caller
     void initialize(const SylinderConfig &config, std::vector<Sylinder> rods, int device = 0) {
         runConfig = config;
         stepCount = 0;
+        restartRngSeed = runConfig.rngSeed; // :41
         commRcp = getMPIWORLDTCOMM();
         if (alens_create(device, 0, 1, &ctx_) != ALENS_OK) throw std::runtime_error(alens_last_error(nullptr));
         conSolverPtr = std::make_shared<ConstraintSolver>(ctx_);
@@ -601,6 +696,112 @@ class SylinderSystem {
         ck(alens_calc_velocity_brown(ctx_, runConfig.KBT, runConfig.dt, nullptr, (unsigned long long)runConfig.rngSeed,
                                      (unsigned long long)stepCount, v.data()));
         velocityBrownRcp = getTVFromVector(v, commRcp);
+    }
+
+    // ---- per-step diagnostics of the reference (called by SRC/TubuleSystem.cpp after every step).  Their reductions over
+    // the ranks go through `sumOverRanks` / `maxOverRanks`: identity on one rank; a multi-rank host program assigns its own
+    // (e.g. [](double *v, int n) { MPI_Allreduce(MPI_IN_PLACE, v, n, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD); }), the
+    // counterpart of Teuchos::reduceAll on commRcp.
+    std::function<void(double *, int)> sumOverRanks = [](double *, int) {};
+    std::function<void(int *, int)> maxOverRanks = [](int *, int) {};
+    bool printRecords = true; ///< the reference's spdlog "RECORD:" lines on stdout (rank 0)
+
+    struct ConStress {
+        double uni[9], bi[9]; ///< row-major, in units of n kBT (scaled by 1 / (nGlobal KBT))
+    };
+    /// calcConStress (:1226-1263): the gamma-weighted stress sums of the last solve, reduced on the device
+    /// (alens_sum_constraint_stress) instead of over a host pool
+    ConStress calcConStress() {
+        ConStress r;
+        ck(alens_sum_constraint_stress(ctx_, 0, r.uni, r.bi));
+        double n = (double)sylinderContainer.size();
+        sumOverRanks(&n, 1);
+        const double scaleFactor = 1 / (n * runConfig.KBT);
+        double both[18];
+        for (int k = 0; k < 9; k++) {
+            both[k] = r.uni[k] * scaleFactor;
+            both[9 + k] = r.bi[k] * scaleFactor;
+        }
+        sumOverRanks(both, 18);
+        for (int k = 0; k < 9; k++) {
+            r.uni[k] = both[k];
+            r.bi[k] = both[9 + k];
+        }
+        if (printRecords && commRcp->getRank() == 0 && runConfig.logLevel <= 2) {
+            std::printf("RECORD: ColXF,%g,%g,%g,%g,%g,%g,%g,%g,%g\n", r.uni[0], r.uni[1], r.uni[2], r.uni[3], r.uni[4], r.uni[5],
+                        r.uni[6], r.uni[7], r.uni[8]);
+            std::printf("RECORD: BiXF,%g,%g,%g,%g,%g,%g,%g,%g,%g\n", r.bi[0], r.bi[1], r.bi[2], r.bi[3], r.bi[4], r.bi[5], r.bi[6],
+                        r.bi[7], r.bi[8]);
+        }
+        return r;
+    }
+
+    struct OrderParameter {
+        double p[3], Q[9]; ///< polar vector and nematic tensor, averaged over all rods
+    };
+    /// calcOrderParameter (:1265-1310): direction = orientation * ez as Eigen evaluates it
+    OrderParameter calcOrderParameter() {
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0, s8 = 0, s9 = 0, s10 = 0, s11 = 0;
+        const int nLocal = (int)sylinderContainer.size();
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11)
+#endif
+        for (int i = 0; i < nLocal; i++) {
+            double d[3];
+            sylinderContainer[i].direction(d);
+            s0 += d[0]; s1 += d[1]; s2 += d[2];
+            s3 += d[0] * d[0] - 1 / 3.0; s4 += d[0] * d[1]; s5 += d[0] * d[2];
+            s6 += d[1] * d[0]; s7 += d[1] * d[1] - 1 / 3.0; s8 += d[1] * d[2];
+            s9 += d[2] * d[0]; s10 += d[2] * d[1]; s11 += d[2] * d[2] - 1 / 3.0;
+        }
+        double pQ[13] = {s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, (double)nLocal};
+        sumOverRanks(pQ, 13);
+        OrderParameter r;
+        for (int k = 0; k < 3; k++) r.p[k] = pQ[k] * (1.0 / pQ[12]);
+        for (int k = 0; k < 9; k++) r.Q[k] = pQ[3 + k] * (1.0 / pQ[12]);
+        if (printRecords && commRcp->getRank() == 0 && runConfig.logLevel <= 2)
+            std::printf("RECORD: Order P,%g,%g,%g,Q,%g,%g,%g,%g,%g,%g,%g,%g,%g\n", r.p[0], r.p[1], r.p[2], r.Q[0], r.Q[1], r.Q[2],
+                        r.Q[3], r.Q[4], r.Q[5], r.Q[6], r.Q[7], r.Q[8]);
+        return r;
+    }
+
+    /// calcVolFrac (:292-312): returns the volume fraction (the reference logs it)
+    double calcVolFrac() {
+        double vol = 0;
+        const int nLocal = (int)sylinderContainer.size();
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : vol)
+#endif
+        for (int i = 0; i < nLocal; i++) {
+            const auto &sy = sylinderContainer[i];
+            vol += 3.1415926535 * (0.25 * sy.length * std::pow(sy.radius * 2, 2) + std::pow(sy.radius * 2, 3) / 6);
+        }
+        sumOverRanks(&vol, 1);
+        const double boxVolume = (runConfig.simBoxHigh[0] - runConfig.simBoxLow[0]) *
+                                 (runConfig.simBoxHigh[1] - runConfig.simBoxLow[1]) *
+                                 (runConfig.simBoxHigh[2] - runConfig.simBoxLow[2]);
+        if (printRecords && commRcp->getRank() == 0)
+            std::printf("Volume Sylinder = %g\nVolume fraction = %g\n", vol, vol / boxVolume);
+        return vol / boxVolume;
+    }
+
+    /// getMaxGid (:1162-1174): (local, global)
+    std::pair<int, int> getMaxGid() {
+        int maxGidLocal = 0;
+        for (const auto &sy : sylinderContainer) maxGidLocal = std::max(maxGidLocal, sy.gid);
+        int maxGidGlobal = maxGidLocal;
+        maxOverRanks(&maxGidGlobal, 1);
+        return std::pair<int, int>(maxGidLocal, maxGidGlobal);
+    }
+
+    /// printTimingSummary (:1484-1489): the device layer's phase times of the last step instead of Teuchos' timers
+    void printTimingSummary(const bool zeroOut = true) {
+        if (runConfig.timerLevel > 2) return;
+        alens_timers t{};
+        if (alens_get_timers(ctx_, &t) != ALENS_OK) return;
+        std::printf("SylinderSystem timing (ms): upload %g, collect %g, setup %g, solve %g, split %g\n", t.upload_ms, t.collect_ms,
+                    t.setup_ms, t.solve_ms, t.split_ms);
+        if (zeroOut) alens_reset_timers(ctx_);
     }
 
     void runStep(bool count_flag = true) { // :948-969 (writeResult is the host's business)

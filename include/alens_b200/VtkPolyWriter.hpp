@@ -1,4 +1,4 @@
-// VtkPolyWriter.hpp -- VTK XML PolyData (.vtp / .pvtp) output in the wire format the reference produces, so that its
+// VtkPolyWriter.hpp -- VTK XML PolyData (.vtp / .pvtp) output (and, for restarts, input) in the wire format the reference produces, so that its
 // post-processing (ParaView states, Examples/*/*.pvsm, the Verify.py scripts) reads our results unchanged:
 //   * one line cell per record (two points), arrays as base64 "binary" DataArrays with a UInt32 byte count in front,
 //     header and payload encoded separately (SimToolbox/Util/IOHelper.hpp:231-251, Util/Base64.hpp:248-262)
@@ -10,9 +10,14 @@
 #define ALENS_B200_VTKPOLYWRITER_HPP_
 
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <fstream>
+#include <iterator>
+#include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace alens_vtk {
@@ -113,6 +118,153 @@ inline void writeParallelIndex(const std::string &path, const std::vector<Field>
     f << "<PPoints> \n<PDataArray NumberOfComponents=\"3\" type=\"Float64\" format=\"binary\"/>\n</PPoints> \n";
     for (const auto &p : pieces) f << "<Piece Source=\"" << p << "\"/>\n";
     f << "</PPolyData>\n</VTKFile>\n";
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Reader for the same wire format: what SylinderSystem::setInitialFromVTKFile (SylinderSystem.cpp:406-476) takes from
+// vtkXMLPPolyDataReader when a run is restarted -- the points and the cell arrays of every piece of a .pvtp index,
+// concatenated in piece order.  Only the encoding the writers above (and the reference's IOHelper) produce is read:
+// format="binary" (base64, UInt32 byte count encoded in front of the payload), uncompressed, little endian.
+
+inline std::vector<unsigned char> base64Decode(const std::string &in, size_t begin, size_t end) {
+    static const std::vector<int> T = [] {
+        std::vector<int> t(256, -1);
+        const char *a = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+        for (int i = 0; i < 64; i++) t[(unsigned char)a[i]] = i;
+        return t;
+    }();
+    std::vector<unsigned char> out;
+    out.reserve((end - begin) / 4 * 3);
+    unsigned acc = 0;
+    int bits = 0;
+    for (size_t i = begin; i < end; i++) {
+        const int v = T[(unsigned char)in[i]];
+        if (v < 0) continue; // '=' padding and white space
+        acc = (acc << 6) | (unsigned)v;
+        bits += 6;
+        if (bits >= 8) {
+            bits -= 8;
+            out.push_back((unsigned char)((acc >> bits) & 0xff));
+        }
+    }
+    return out;
+}
+
+/// one DataArray, widened to double (Int32 / UInt8 / Float32 / Float64)
+struct Array {
+    int ncomp = 1;
+    std::vector<double> v;
+    size_t tuples() const { return ncomp > 0 ? v.size() / (size_t)ncomp : 0; }
+};
+struct PolyData {
+    std::vector<double> points; ///< 3 per point
+    std::vector<std::pair<std::string, Array>> pointData, cellData;
+    const Array &cell(const std::string &name) const {
+        for (const auto &c : cellData)
+            if (c.first == name) return c.second;
+        throw std::runtime_error("vtk: no cell array named " + name);
+    }
+    size_t numberOfPoints() const { return points.size() / 3; }
+};
+
+inline std::string xmlAttr(const std::string &tag, const std::string &key) {
+    const size_t a = tag.find(key + "=\"");
+    if (a == std::string::npos) return "";
+    const size_t b = a + key.size() + 2, e = tag.find('"', b);
+    return e == std::string::npos ? "" : tag.substr(b, e - b);
+}
+
+/// appends the arrays of one .vtp piece to `out` (arrays are matched by name, in file order for the first piece)
+inline void readPiece(const std::string &path, PolyData &out) {
+    std::ifstream f(path, std::ios::in | std::ios::binary);
+    if (!f) throw std::runtime_error("vtk: cannot open " + path);
+    const std::string s((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    auto sectionOf = [&](size_t at) { // which of <Points> / <PointData> / <CellData> / other encloses position `at`
+        const char *names[3] = {"<Points>", "<PointData", "<CellData"};
+        const char *ends[3] = {"</Points>", "</PointData>", "</CellData>"};
+        for (int k = 0; k < 3; k++) {
+            const size_t a = s.rfind(names[k], at);
+            if (a == std::string::npos) continue;
+            const size_t e = s.find(ends[k], a);
+            if (e != std::string::npos && e > at) return k;
+        }
+        return 3;
+    };
+    size_t at = 0;
+    while ((at = s.find("<DataArray", at)) != std::string::npos) {
+        const size_t close = s.find('>', at);
+        if (close == std::string::npos) break;
+        const std::string tag = s.substr(at, close - at + 1);
+        const size_t endTag = s.find("</DataArray>", close);
+        if (endTag == std::string::npos) throw std::runtime_error("vtk: unterminated DataArray in " + path);
+        const int sec = sectionOf(at);
+        at = endTag;
+        if (sec == 3) continue; // connectivity / offsets
+        if (xmlAttr(tag, "format") != "binary") throw std::runtime_error("vtk: only format=\"binary\" is read: " + path);
+        const std::string type = xmlAttr(tag, "type"), name = xmlAttr(tag, "Name");
+        const std::string nc = xmlAttr(tag, "NumberOfComponents");
+        // the UInt32 byte count is encoded on its own: 4 bytes -> 8 characters
+        size_t b = close + 1;
+        while (b < endTag && (s[b] == '\n' || s[b] == '\r' || s[b] == ' ' || s[b] == '\t')) b++;
+        if (endTag - b < 8) throw std::runtime_error("vtk: short DataArray " + name);
+        const std::vector<unsigned char> head = base64Decode(s, b, b + 8);
+        if (head.size() < 4) throw std::runtime_error("vtk: bad DataArray header " + name);
+        const uint32_t bytes = (uint32_t)head[0] | ((uint32_t)head[1] << 8) | ((uint32_t)head[2] << 16) | ((uint32_t)head[3] << 24);
+        const std::vector<unsigned char> raw = base64Decode(s, b + 8, endTag);
+        if (raw.size() < bytes) throw std::runtime_error("vtk: truncated DataArray " + name);
+        Array a;
+        a.ncomp = nc.empty() ? 1 : std::atoi(nc.c_str());
+        auto widen = [&](auto zero) {
+            using T = decltype(zero);
+            const size_t n = bytes / sizeof(T);
+            a.v.resize(n);
+            for (size_t i = 0; i < n; i++) {
+                T t;
+                std::memcpy(&t, raw.data() + i * sizeof(T), sizeof(T));
+                a.v[i] = (double)t;
+            }
+        };
+        if (type == "Float64") widen(double(0));
+        else if (type == "Float32") widen(float(0));
+        else if (type == "Int32") widen(int32_t(0));
+        else if (type == "UInt8") widen(uint8_t(0));
+        else throw std::runtime_error("vtk: unsupported DataArray type " + type);
+        if (sec == 0) {
+            out.points.insert(out.points.end(), a.v.begin(), a.v.end());
+            continue;
+        }
+        auto &list = sec == 1 ? out.pointData : out.cellData;
+        bool found = false;
+        for (auto &c : list)
+            if (c.first == name) {
+                c.second.v.insert(c.second.v.end(), a.v.begin(), a.v.end());
+                found = true;
+            }
+        if (!found) list.emplace_back(name, std::move(a));
+    }
+}
+
+/// a .pvtp index: every <Piece Source="..."/> (relative to the index), merged in order; a .vtp is read by itself
+inline PolyData readParallel(const std::string &path) {
+    PolyData out;
+    if (path.size() > 4 && path.compare(path.size() - 4, 4, ".vtp") == 0) {
+        readPiece(path, out);
+        return out;
+    }
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("vtk: cannot open " + path);
+    const std::string s((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    const size_t slash = path.find_last_of('/');
+    const std::string dir = slash == std::string::npos ? "" : path.substr(0, slash + 1);
+    size_t at = 0;
+    while ((at = s.find("<Piece", at)) != std::string::npos) {
+        const size_t close = s.find('>', at);
+        if (close == std::string::npos) break;
+        const std::string src = xmlAttr(s.substr(at, close - at + 1), "Source");
+        if (!src.empty()) readPiece(dir + src, out);
+        at = close;
+    }
+    return out;
 }
 
 } // namespace alens_vtk

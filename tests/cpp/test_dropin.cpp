@@ -7,7 +7,9 @@
 //          then n x {int gid, double radius, length, pos[3], quat[4]}, then 6n doubles velNonBrown,
 //          int nb, nb x ConstraintBlock (272 B) host blocks pushed into the pool before runStep
 // out.bin: long long nc, int iterations, double residual, 6n x4 doubles (fU, vU, fB, vB), n x (pos[3],quat[4])
-//          after the step, nc doubles gamma, nc x ConstraintBlock after writebackGamma
+//          after the step, nc doubles gamma, nc x ConstraintBlock after writebackGamma, then the per-step diagnostics:
+//          18 doubles calcConStress (uni, bi), 12 doubles calcOrderParameter (p, Q), 1 double calcVolFrac, 2 ints getMaxGid
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -42,6 +44,7 @@ int main(int argc, char **argv) {
     rd(fi, &maxIte);
     cfg.conMaxIte = maxIte;
     cfg.initPreSteps = 0;
+    cfg.KBT = 0.5; // scale of calcConStress (no Brownian motion: the velocities are the test's input)
     std::vector<Sylinder> rods(n);
     for (int i = 0; i < n; i++) {
         int gid;
@@ -84,6 +87,8 @@ int main(int argc, char **argv) {
         }
         auto g = solver.getGamma();
         wr(fo, g->data(), (size_t)rep.n_constraints);
+        sys.printRecords = false;
+        const auto stress = sys.calcConStress(); // device-side sum: before the pool is refilled from the device
         solver.writebackGamma();
         auto blocks = sys.getConstraintCollector()->flatten();
         if ((long long)blocks.size() != rep.n_constraints) return 3;
@@ -91,6 +96,26 @@ int main(int argc, char **argv) {
         // velCol of rod 0 must equal velocityUni[0..2] (saveForceVelocityConstraints)
         const auto &s0 = sys.getContainer()[0];
         if (n > 0 && s0.velCol[0] != sys.getVelocityUni()->data()[0]) return 4;
+        wr(fo, stress.uni, 9);
+        wr(fo, stress.bi, 9);
+        { // ... and the same sums from the refilled pool, as the reference takes them
+            double u[9], b[9];
+            sys.getConstraintCollector()->sumLocalConstraintStress(u, b, false);
+            for (int k = 0; k < 9; k++) {
+                const double su = u[k] / (n * cfg.KBT), sb = b[k] / (n * cfg.KBT);
+                if (std::fabs(su - stress.uni[k]) > 1e-12 * (1 + std::fabs(su)) || std::fabs(sb - stress.bi[k]) > 1e-12 * (1 + std::fabs(sb)))
+                    return 6;
+            }
+        }
+        const auto op = sys.calcOrderParameter();
+        wr(fo, op.p, 3);
+        wr(fo, op.Q, 9);
+        const double phi = sys.calcVolFrac();
+        wr(fo, &phi);
+        const auto mg = sys.getMaxGid();
+        wr(fo, &mg.first);
+        wr(fo, &mg.second);
+        sys.printTimingSummary();
         fclose(fo);
     } catch (const std::exception &e) {
         fprintf(stderr, "exception: %s\n", e.what());

@@ -106,7 +106,7 @@ def run_ranks(rods, lo, hi, pbc, nranks, colbuf, mu, dt, res, max_ite, vnc=None,
             res_r["migrated"] = tuple(moved)
             res_r["identity"] = c.get_rod_identity()
             res_r.update(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), ghosts=c.num_ghosts(),
-                         mode=c.comm_mode(), digest=c.constraint_digest())
+                         mode=c.comm_mode(), digest=c.constraint_digest(), stress=c.sum_constraint_stress())
             res_r.update(c.get_force_velocity())
             if want_blocks:
                 res_r["blocks"] = c.get_constraints(with_stress=True, write_back=True)

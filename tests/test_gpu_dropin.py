@@ -16,6 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "test_dropin")
 
 
+def oracle_directions(quat):
+    """orientation * ez for (x, y, z, w) quaternions"""
+    x, y, z, w = quat.T
+    return np.stack([2 * (x * z + w * y), 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)], axis=1)
+
+
 def build_exe():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
 
@@ -56,6 +62,11 @@ def run_dropin(tmp_path, rods, lo, hi, pbc, colbuf, mu, dt, res, max_ite, vnb, h
     out["gamma"] = np.frombuffer(buf, dtype="<f8", count=nc, offset=off)
     off += 8 * nc
     out["blocks"] = np.frombuffer(buf, dtype=BLOCK_DTYPE, count=nc, offset=off)
+    off += BLOCK_DTYPE.itemsize * nc
+    diag = np.frombuffer(buf, dtype="<f8", count=31, offset=off)
+    out["stress_uni"], out["stress_bi"] = diag[:9].reshape(3, 3), diag[9:18].reshape(3, 3)
+    out["order_p"], out["order_Q"], out["vol_frac"] = diag[18:21], diag[21:30].reshape(3, 3), diag[30]
+    out["max_gid"] = struct.unpack_from("<ii", buf, off + 31 * 8)
     out["record"] = r.stderr
     return nc, ite, resid, out
 
@@ -68,7 +79,9 @@ def test_dropin_step_equals_capi_path(tmp_path, ctx, oracle):
     vnb = thermal_velocity(rods, mu, dt, seed=5)
     pos_w = oracle.wrap_positions(rods["pos"], lo, hi, pbc)
     orods = oracle.make_rods(rods["gid"], rods["radius"], rods["length"], pos_w, rods["quat"], 1.0, 1.0, colbuf)
-    host = np.concatenate([add_bilateral(oracle, rods, orods, 40, 1), add_one_sided(orods, 30, 2)])
+    one = add_one_sided(orods, 30, 2)
+    one["stress"] = np.random.default_rng(8).normal(size=(30, 9))  # counted only by sumLocalConstraintStress(withOneSide)
+    host = np.concatenate([add_bilateral(oracle, rods, orods, 40, 1), one])
     nc, ite, resid, out = run_dropin(tmp_path, rods, lo, hi, pbc, colbuf, mu, dt, res, max_ite, vnb, host)
     assert "RECORD: BCQP residue" in out["record"]
 
@@ -89,6 +102,27 @@ def test_dropin_step_equals_capi_path(tmp_path, ctx, oracle):
     assert np.array_equal(out["gamma"], ctx.get_gamma())
     wb = ctx.get_constraints(with_stress=True, write_back=True)
     assert out["blocks"].tobytes() == wb.tobytes()
+    # per-step diagnostics of the mirror (calcConStress / calcOrderParameter / calcVolFrac / getMaxGid): the stress sums
+    # come from the device-side reduction and equal the sums over the written-back blocks (KBT = 0.5 in test_dropin.cpp)
+    uni, bi = ctx.sum_constraint_stress()
+    two = wb["oneSide"] == 0
+    ref_uni = wb["stress"][two & (wb["bilateral"] == 0)].sum(axis=0).reshape(3, 3)
+    ref_bi = wb["stress"][two & (wb["bilateral"] != 0)].sum(axis=0).reshape(3, 3)
+    assert np.abs(ref_uni).max() > 0 and np.abs(ref_bi).max() > 0
+    np.testing.assert_allclose(uni, ref_uni, rtol=1e-12, atol=1e-12 * np.abs(ref_uni).max())
+    np.testing.assert_allclose(bi, ref_bi, rtol=1e-12, atol=1e-12 * np.abs(ref_bi).max())
+    uni1, _ = ctx.sum_constraint_stress(with_one_side=True)
+    ref_uni1 = wb["stress"][wb["bilateral"] == 0].sum(axis=0).reshape(3, 3)
+    np.testing.assert_allclose(uni1, ref_uni1, rtol=1e-12, atol=1e-12 * np.abs(ref_uni1).max())
+    assert np.abs(uni1 - uni).max() > 0
+    np.testing.assert_allclose(out["stress_uni"], uni / (n * 0.5), rtol=1e-14, atol=0)
+    np.testing.assert_allclose(out["stress_bi"], bi / (n * 0.5), rtol=1e-14, atol=0)
+    d = oracle_directions(rods["quat"])
+    np.testing.assert_allclose(out["order_p"], d.mean(axis=0), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out["order_Q"], (d[:, :, None] * d[:, None, :]).mean(axis=0) - np.eye(3) / 3, rtol=0, atol=1e-13)
+    vol = np.pi * (0.25 * rods["length"] * (2 * rods["radius"]) ** 2 + (2 * rods["radius"]) ** 3 / 6)
+    assert abs(out["vol_frac"] - vol.sum() / box**3) < 1e-9 * out["vol_frac"]  # the reference's pi has 11 digits
+    assert out["max_gid"] == (int(rods["gid"].max()),) * 2
     ctx.step_euler(dt)
     p, q = ctx.get_rod_state()
     assert np.array_equal(out["pos"], p) and np.array_equal(out["quat"], q)
@@ -136,8 +170,10 @@ def test_mirror_main_program_follows_the_reference_main_program(tmp_path):
     pr.write_dat(str(work / "SylinderInitial.dat"), rods, links)
     exe = os.path.join(ROOT, "tests", "cpp", "test_system_main")
     steps = 3
-    r = subprocess.run([exe, str(steps), str(work / "out.bin")], cwd=str(work), capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stderr[-2000:]
+    # "restart": afterwards a second system resumes from a snapshot (reinitialize, SylinderSystem.cpp:106-175) and follows the first
+    r = subprocess.run([exe, str(steps), str(work / "out.bin"), "restart"], cwd=str(work), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "restart ok" in r.stdout, r.stderr[-2000:]
+    assert (work / "TimeStepInfo.txt").read_text().split() == [str(cfg["rngSeed"]), str(steps), "1", "Sylinder_1.pvtp"]
     raw = (work / "out.bin").read_bytes()
     n = int(np.frombuffer(raw[:4], dtype=np.int32)[0])
     got = np.frombuffer(raw[4:4 + 568 * n], dtype=pr.SYLINDER_DTYPE)

@@ -26,7 +26,7 @@ def single_rank(rods, lo, hi, pbc, colbuf, mu, dt, res, max_ite, vnc, links=None
     c.calc_mobility(mu)
     rep = c.solve_constraints(vnc, dt, res, max_ite, 0)
     out = dict(nc=nc, report=rep, gamma=c.get_gamma(), history=c.get_history(), digest=c.constraint_digest(),
-               blocks=c.get_constraints(with_stress=True, write_back=True))
+               stress=c.sum_constraint_stress(), blocks=c.get_constraints(with_stress=True, write_back=True))
     out.update(c.get_force_velocity())
     c.close()
     return out
@@ -126,6 +126,12 @@ def test_multirank_matches_single(nranks, pbc, placement):
     assert sum(r["digest"]["list_hash"] for r in ranks) % M == ref["digest"]["list_hash"]
     for k in ("sum_gamma", "sum_gamma2", "sum_wgamma"):
         assert abs(sum(r["digest"][k] for r in ranks) - ref["digest"][k]) < 1e-9 * abs(ref["digest"][k]), k
+
+    # ---- calcConStress: the ranks' device-side stress sums (rows counted by the owner of rod I) add up
+    for k in (0, 1):
+        tot, one = sum(r["stress"][k] for r in ranks), ref["stress"][k]
+        assert np.abs(tot - one).max() <= 1e-9 * max(np.abs(one).max(), 1e-300), ("uni", "bi")[k]
+    assert np.abs(ref["stress"][0]).max() > 0
 
     # ---- solve: same iteration count, gamma and velocities to rounding
     its = {r["report"].iterations for r in ranks}
@@ -322,6 +328,12 @@ def test_multirank_links_across_slab_faces(nranks, pbc, placement):
         assert np.array_equal(uniq[f], want[f]), f
     assert {r["report"].iterations for r in ranks} == {ref["report"].iterations}
     assert np.abs(uniq["gamma"] - want["gamma"]).max() < 1e-9 * np.abs(want["gamma"]).max()
+    for k in (0, 1):  # calcConStress: a link held by two ranks is counted once, by the owner of its rod I
+        tot, one = sum(r["stress"][k] for r in ranks), ref["stress"][k]
+        assert np.abs(tot - one).max() <= 1e-9 * max(np.abs(one).max(), 1e-300), ("uni", "bi")[k]
+    assert np.abs(ref["stress"][1]).max() > 0
+    assert np.abs(ref["stress"][1] - want["stress"][want["bilateral"] == 1].sum(axis=0).reshape(3, 3)).max() <= \
+        1e-12 * np.abs(ref["stress"][1]).max()
     for name in ("velU", "forceU", "velB", "forceB"):
         full = np.zeros_like(ref[name]).reshape(-1, 6)
         for r in ranks:
