@@ -117,7 +117,7 @@ def test_dropin_step_equals_capi_path(tmp_path, ctx, oracle):
     assert np.abs(uni1 - uni).max() > 0
     np.testing.assert_allclose(out["stress_uni"], uni / (n * 0.5), rtol=1e-14, atol=0)
     np.testing.assert_allclose(out["stress_bi"], bi / (n * 0.5), rtol=1e-14, atol=0)
-    d = oracle_directions(rods["quat"])
+    d = oracle_directions(out["quat"])  # the diagnostics are taken after runStep: the moved rods
     np.testing.assert_allclose(out["order_p"], d.mean(axis=0), rtol=0, atol=1e-13)
     np.testing.assert_allclose(out["order_Q"], (d[:, :, None] * d[:, None, :]).mean(axis=0) - np.eye(3) / 3, rtol=0, atol=1e-13)
     vol = np.pi * (0.25 * rods["length"] * (2 * rods["radius"]) ** 2 + (2 * rods["radius"]) ** 3 / 6)
