@@ -314,6 +314,32 @@ def check_parity_n1(ctx, pr, sysr, vnc, iters):
     return res
 
 
+def bind_near_gpu(local):
+    """N > 1: keep this rank's host threads -- and with them the pinned buffers they first touch -- on the CPUs next to its
+    GPU (NVML's affinity mask), so that the per-step host<->device copies of 8 ranks do not all cross the socket link.
+    Returns a description for the bench line, or None when the box gives no usable mask."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        idx = local
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(t.strip().isdigit() for t in vis.split(",")) and local < len(vis.split(",")):
+            idx = int(vis.split(",")[local])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = near & allowed
+        if len(use) < 4 or len(use) == len(allowed):
+            return None
+        os.sched_setaffinity(0, use)
+        return f"{len(use)} of {len(allowed)} cpus (NVML affinity of GPU {idx})"
+    except Exception:  # noqa: BLE001 -- placement is an optimisation, never a reason to fail
+        return None
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -332,6 +358,9 @@ def main():
         if rank != 0:
             return 0
         return reference_arm(a, int(a.rods), workload, ncores)
+
+    # (N = 1 stays unbound: its cpu_baseline leg gives the reference every host core)
+    host_affinity = bind_near_gpu(local) if world > 1 and os.environ.get("ALENS_NO_BIND") != "1" else None
 
     import torch
     import torch.distributed as dist
@@ -591,6 +620,7 @@ def main():
                        "U halo + 4-double allreduce per BBPGD iteration over NVLink peer memory; value = " +
                        ("global steps/s" if strong else "slab-steps/s (global steps/s x GPUs)"))),
                    "ghosts_rank0": ctx.num_ghosts() if world > 1 else None,
+                   "host_affinity_rank0": host_affinity,
                    "l2": "inputs larger than L2 (constraint + incidence arrays > 600 MB)",
                    "relaxation": [list(map(int, x)) for x in relax_info],
                    "phase_ms_per_step": {k: round(v / a.steps, 3) for k, v in phase.items()}},

@@ -1,6 +1,7 @@
 // tests/cpp/bench_mirror.cpp -- wall clock per step of the reference's main loop (prepareStep(); runStep();) through the C++
 // mirror at the bench size: what a host application that switches its includes (option A) gets, host loops
 // over the 568-byte Sylinder records included.  Not a test; `make bench_mirror && ./bench_mirror [nRods] [steps]`.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -60,6 +61,25 @@ int main(int argc, char **argv) {
             tPrep += ms(t0, t1);
             tRun += ms(t1, t2);
         }
+        // the per-step stress diagnostic (SylinderSystem::calcConStress): device-side reduction against the reference's way,
+        // a walk over the host pool (which the mirror first has to refill from the device)
+        sys.runConfig.KBT = 1.0;
+        sys.printRecords = false;
+        sys.calcConStress();
+        const auto s0 = now();
+        const auto cs = sys.calcConStress();
+        const auto s1 = now();
+        sys.getConstraintCollector()->pullFromDevice(sys.deviceContext(), true, true);
+        double uni[9], bi[9];
+        sys.getConstraintCollector()->sumLocalConstraintStress(uni, bi, false);
+        const auto s2 = now();
+        double err = 0, scale = 0;
+        for (int k = 0; k < 9; k++) {
+            err = std::max(err, std::fabs(uni[k] / n - cs.uni[k]));
+            scale = std::max(scale, std::fabs(cs.uni[k]));
+        }
+        std::printf("{\"calcConStress_device_ms\": %.3f, \"pool_refill_and_host_sum_ms\": %.3f, \"rel_diff\": %.3g}\n", ms(s0, s1),
+                    ms(s1, s2), err / scale);
         const auto &rep = sys.getConstraintSolver()->getReport();
         std::printf("{\"mirror_ms_per_step\": %.3f, \"prepareStep_ms\": %.3f, \"runStep_ms\": %.3f, \"rods\": %d, \"constraints\": %lld, "
                     "\"bbpgd_iterations\": %d, \"steps\": %d}\n",
