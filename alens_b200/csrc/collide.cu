@@ -380,7 +380,9 @@ __device__ __forceinline__ int stageCandidates(int cnt, const int *qi, const int
     return cnt;
 }
 
-template <int MINB, bool NARROW>
+// MULTI = false: the instantiation for a context without ghost rods (no slab decomposition): the ghost bookkeeping of the
+// inner loop is compiled out.
+template <int MINB, bool NARROW, bool MULTI = true>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ cellHits, int4 *__restrict__ hitList,
               unsigned long long hitCap, unsigned long long *__restrict__ counters) {
@@ -397,7 +399,7 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
     const int axMul = g.axis == 0 ? 1 : (g.axis == 1 ? 3 : (g.axis == 2 ? 9 : 0));
-    const bool multi = g.axis >= 0; // ghost rods exist
+    const bool multi = MULTI && g.axis >= 0; // ghost rods exist
     const int cell = blockIdx.x * kWarpsPerCta + w;
     if (cell >= g.ncell) return;
     const int ib = in.cellStart[cell], ie = in.cellStart[cell + 1];
@@ -495,34 +497,63 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                         }
                     }
                     __syncwarp();
-                    // m == nI is the flush pass: the staged source tile is about to be replaced
-                    for (int m = 0; m <= nI; m++) {
-                        const bool flush = m == nI;
+                    // Targets in blocks of 32.  Stage 1 only records, per lane and staged source, WHICH targets of the block pass
+                    // (one bit each): no warp vote, no queue traffic inside the arithmetic loop.  The bits are then turned
+                    // into stage-1 queue entries, per step one for each of a lane's two source slots (slots `lane` of all lanes
+                    // first, then `32 + lane`; a slot's targets in ascending order), stage 2 draining the queue whenever
+                    // it holds 32.  The pass with
+                    // mb >= nI only flushes: the staged source tile is about to be replaced.
+                    for (int mb = 0; mb <= nI; mb += 32) {
+                        const bool flush = mb >= nI;
+                        unsigned h0 = 0, h1 = 0;
                         if (!flush) {
-                            // ---- stage 1: target m against the 64 staged sources (branch-free)
-                            const int si = i0 + m;
-                            const float4 a = tA[w][m];
-                            const bool gi = multi && sG[w][m] >= 32;
-                            unsigned pass[2];
+                            const int mEnd = min(nI, mb + 32);
+                            for (int m = mb; m < mEnd; m++) {
+                                // ---- stage 1: target m against the 64 staged sources (branch-free)
+                                const float4 a = tA[w][m];
+                                // each pair once inside the target cell (the row that holds it lists the sources in sorted
+                                // order: those behind the target).  Elsewhere every source counts; a rod can meet itself
+                                // there only through a periodic image (fewer than 3 cells on that axis), and equal gids are
+                                // dropped by the exact query (canonicalPair / narrowBatch), as the reference's gid filter does.
+                                const int after = own ? i0 + m : -2;
+                                bool gi = false;
+                                if (MULTI) gi = multi && sG[w][m] >= 32;
+                                bool pass[2];
 #pragma unroll
-                            for (int q = 0; q < 2; q++) {
-                                const float fx = xj[q] - a.x, fy = yj[q] - a.y, fz = zj[q] - a.z;
-                                const float cutS = (a.w + Sj[q]) * slackF;
-                                const unsigned near = __fmaf_rn(fx, fx, __fmaf_rn(fy, fy, fz * fz)) <= cutS * cutS;
-                                // each pair once inside the target cell; a rod never pairs with its own image
-                                const unsigned keep = own ? (sjv[q] > si) : (sjv[q] != si);
-                                const unsigned gg = gi & gh[q]; // two ghosts: not this rank's constraint
-                                pass[q] = near & keep & (gg ^ 1u);
+                                for (int q = 0; q < 2; q++) {
+                                    const float fx = xj[q] - a.x, fy = yj[q] - a.y, fz = zj[q] - a.z;
+                                    const float cutS = (a.w + Sj[q]) * slackF;
+                                    pass[q] = (__fmaf_rn(fx, fx, __fmaf_rn(fy, fy, fz * fz)) <= cutS * cutS) && sjv[q] > after;
+                                    if (MULTI) pass[q] = pass[q] && !(gi && gh[q]); // two ghosts: not this rank's constraint
+                                }
+                                h0 |= (pass[0] ? 1u : 0u) << (m - mb);
+                                h1 |= (pass[1] ? 1u : 0u) << (m - mb);
                             }
-                            const unsigned m0 = __ballot_sync(0xffffffffu, pass[0]), m1 = __ballot_sync(0xffffffffu, pass[1]);
-                            if ((m0 | m1) == 0) continue;
-                            const int n0 = __popc(m0);
-                            if (pass[0]) q1[qn1 + __popc(m0 & lt)] = (unsigned short)(m | (lane << 6));
-                            if (pass[1]) q1[qn1 + n0 + __popc(m1 & lt)] = (unsigned short)(m | ((32 + lane) << 6));
-                            qn1 += n0 + __popc(m1);
-                            __syncwarp();
                         }
-                        while (qn1 >= 32 || (flush && qn1 > 0)) {
+                        for (;;) {
+                            bool more = true; // (warp-uniform) some lane still holds a passer
+                            if (qn1 < 32) {   // room for 64 more entries
+                                const unsigned a0 = __ballot_sync(0xffffffffu, h0 != 0), a1 = __ballot_sync(0xffffffffu, h1 != 0);
+                                more = (a0 | a1) != 0;
+                                if (more) {
+                                    const int n0 = __popc(a0);
+                                    if (h0) {
+                                        q1[qn1 + __popc(a0 & lt)] = (unsigned short)((mb + __ffs(h0) - 1) | (lane << 6));
+                                        h0 &= h0 - 1;
+                                    }
+                                    if (h1) {
+                                        q1[qn1 + n0 + __popc(a1 & lt)] = (unsigned short)((mb + __ffs(h1) - 1) | ((32 + lane) << 6));
+                                        h1 &= h1 - 1;
+                                    }
+                                    qn1 += n0 + __popc(a1);
+                                    __syncwarp();
+                                }
+                            }
+                            if (!(qn1 >= 32 || (flush && qn1 > 0))) {
+                                if (more) continue;
+                                break;
+                            }
+                            {
                             // ---- stage 2 on the first min(32, qn1) queued pairs: the two capsule tests
                             const int cnt = min(32, qn1);
                             bool pass = false;
@@ -574,11 +605,15 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                             if (msk) {
                                 if (pass) {
                                     const int p = qn + __popc(msk & lt);
-                                    const int gi = sG[w][tm], gj = sGj[w][js];
                                     qi[p] = i0 + tm;
                                     qj[p] = j0 + js;
                                     // image of j relative to i: cell wrap + difference of the ghost images
-                                    qs[p] = code + (((gj + 32) & 63) - ((gi + 32) & 63)) * axMul;
+                                    int rel = code;
+                                    if (MULTI) {
+                                        const int gi = sG[w][tm], gj = sGj[w][js];
+                                        rel += (((gj + 32) & 63) - ((gi + 32) & 63)) * axMul;
+                                    }
+                                    qs[p] = rel;
                                 }
                                 qn += __popc(msk);
                                 nCand += __popc(msk);
@@ -598,6 +633,7 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                                 }
                             }
                             __syncwarp();
+                            }
                         }
                     }
                     __syncwarp();
@@ -1304,6 +1340,10 @@ void collectPairs(Context &c) {
                 k_pairs_find<6, false><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p,
                                                                            c.hitList.p, (unsigned long long)c.hitList.cap,
                                                                            c.dCounters.p);
+            else if (g.axis < 0)
+                k_pairs_find<8, false, false><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p,
+                                                                                  c.hitList.p, (unsigned long long)c.hitList.cap,
+                                                                                  c.dCounters.p);
             else
                 k_pairs_find<8, false><<<ctas, kWarpsPerCta * 32, 0, st>>>(pairIn(c), c.box, g, c.colBuf, c.cellHits.p,
                                                                            c.hitList.p, (unsigned long long)c.hitList.cap,
@@ -1540,6 +1580,7 @@ void preloadCollideKernels() {
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<5, true>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<3, true>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<8, false>)));
+    ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<8, false, false>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, (k_pairs_find<6, false>)));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_cand_narrow));
     ALENS_CUDA(cudaFuncGetAttributes(&a, k_cell_hit_count));
