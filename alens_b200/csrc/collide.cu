@@ -501,9 +501,8 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                     // (one bit each): no warp vote, no queue traffic inside the arithmetic loop.  The bits are then turned
                     // into stage-1 queue entries, per step one for each of a lane's two source slots (slots `lane` of all lanes
                     // first, then `32 + lane`; a slot's targets in ascending order), stage 2 draining the queue whenever
-                    // it holds 32.  The pass with
-                    // mb >= nI only flushes: the staged source tile is about to be replaced.
-                    for (int mb = 0; mb <= nI; mb += 32) {
+                    // it holds 32.  The last pass (mb >= nI) only flushes: the staged source tile is about to be replaced.
+                    for (int mb = 0;; mb += 32) {
                         const bool flush = mb >= nI;
                         unsigned h0 = 0, h1 = 0;
                         if (!flush) {
@@ -635,6 +634,7 @@ k_pairs_find(PairIn in, Box box, CellGrid g, double colBuf, int *__restrict__ ce
                             __syncwarp();
                             }
                         }
+                        if (flush) break;
                     }
                     __syncwarp();
                 }
