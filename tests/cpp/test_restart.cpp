@@ -4,6 +4,7 @@
 //   test_restart <folder>                    (the folder must exist; files go to <folder>/result/result0-399/)
 //   test_restart read <file.pvtp> <out.bin>  rods of a snapshot as raw 568-byte Sylinder records (tests/test_cpp_restart.py
 //                                            reads the REFERENCE's own files through this)
+//   test_restart euler <in.bin> <dt> <out.bin>  Sylinder::stepEuler(dt) on raw Sylinder records (compared with the reference's)
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -20,6 +21,22 @@
 
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
+    if (std::string(argv[1]) == "euler") {
+        if (argc < 5) return 2;
+        FILE *f = std::fopen(argv[2], "rb");
+        CHECK(f);
+        std::vector<Sylinder> rods;
+        Sylinder one;
+        while (std::fread((void *)&one, sizeof(Sylinder), 1, f) == 1) rods.push_back(one);
+        std::fclose(f);
+        const double dt = std::atof(argv[3]);
+        for (auto &sy : rods) sy.stepEuler(dt);
+        f = std::fopen(argv[4], "wb");
+        CHECK(f);
+        std::fwrite((const void *)rods.data(), sizeof(Sylinder), rods.size(), f);
+        std::fclose(f);
+        return 0;
+    }
     if (std::string(argv[1]) == "read") {
         if (argc < 4) return 2;
         std::vector<Sylinder> rods;

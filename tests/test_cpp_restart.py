@@ -60,3 +60,27 @@ def test_reads_the_snapshot_the_reference_writes(tmp_path):
         return np.stack([2 * (x * z + w * y), 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)], axis=1)
 
     assert np.abs(direction(got["orientation"]) - direction(ref["orientation"])).max() < 3e-7  # znorm is Float32
+
+
+@pytest.mark.skipif(not pr.available(), reason="oracle/_ref/libalens_refsys.so not built (needs /root/reference)")
+def test_host_euler_step_equals_the_reference(tmp_path):
+    """Sylinder::stepEuler of the mirror (the step a restart takes on the host) against the reference's own
+    Sylinder::stepEuler + EquatnHelper::rotateEquatn (Sylinder.cpp:91-99, Util/EquatnHelper.hpp:74-90)"""
+    _build()
+    rng = np.random.default_rng(4)
+    n, dt = 400, 2e-3
+    rods = np.zeros(n, dtype=pr.SYLINDER_DTYPE)
+    rods["pos"] = rng.uniform(-5, 5, size=(n, 3))
+    q = rng.normal(size=(n, 4))
+    rods["orientation"] = q / np.linalg.norm(q, axis=1)[:, None]
+    rods["vel"] = rng.normal(size=(n, 3))
+    rods["omega"] = rng.normal(size=(n, 3)) * rng.choice([0.0, 1e-9, 1.0, 40.0], size=(n, 1))  # below and above the float-epsilon cut
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    rods.tofile(fin)
+    r = subprocess.run([EXE, "euler", str(fin), repr(dt), str(fout)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = np.fromfile(fout, dtype=pr.SYLINDER_DTYPE)
+    for i in range(n):
+        p, o = pr.sylinder_step_euler(rods["pos"][i], rods["orientation"][i], rods["vel"][i], rods["omega"][i], dt)
+        assert np.array_equal(got["pos"][i], p), i
+        assert np.abs(got["orientation"][i] - o).max() < 4e-16, i  # same formula; Eigen normalises with a vectorised norm
