@@ -13,14 +13,16 @@
 //   k_scan_int      exclusive scan of the histogram                      (single CTA)
 //   k_cell_scatter  counting-sort scatter                                (1 thread / rod)
 //   k_cell_order    per-cell sort by user index (determinism) + gather of the sorted SoA (1 warp / cell)
-//   k_pairs_find    one warp per cell, half stencil as 5 x-contiguous rows; broad phase = bounding-sphere test
-//                   (fp64) + two point/axis capsule tests (fp32, conservative slack) with warp ballot
-//                   compaction into a shared-memory queue; dense 32-lane narrow-phase (DCP) batches; hits
-//                   are staged as 16-byte records (i, j, cell, seq|image) through a warp-aggregated atomic
-//   scan            exclusive scan of per-cell hit counts (3-kernel tiled scan)
-//   k_pairs_emit    one thread per staged hit: contact re-evaluated for the hits only and written to the
-//                   constraint SoA at cellHitStart[cell] + seq  (deterministic order, one DCP pass over
-//                   the candidates instead of two)
+//   k_pairs_find    one warp per cell, half stencil as 5 x-contiguous rows; broad phase in fp32 with conservative slack:
+//                   bounding-sphere tests (passers kept as per-lane bit masks), then the point/axis capsule tests and a
+//                   separating-direction test on 32 queued pairs at a time; survivors are staged as 16-byte candidates
+//                   (i, j, cell, seq|image) through a warp-aggregated atomic
+//   k_cand_narrow   one thread per candidate: exact fp64 closest-point query (DCP); a contact sets its bit in the cell's bitmap
+//   k_cell_hit_count + scan: contacts per cell and their exclusive prefix (3-kernel tiled scan)
+//   k_pairs_emit2   one thread per candidate with its bit set: contact re-evaluated and written to the constraint SoA at
+//                   cellHitStart[cell] + rank of the bit (deterministic order)
+//   (k_pairs_find<NARROW=true> + k_pairs_emit: the single-kernel variant, kept as fallback and cross-check)
+//   k_long_cells / k_long_long: exact passes for rods longer than the cells were sized for (polydisperse lengths)
 #include "context.hpp"
 #include "geometry.cuh"
 
@@ -347,8 +349,9 @@ __device__ __forceinline__ int narrowBatch(const PairIn &in, const Box &box, dou
 // x-adjacent cells: cells adjacent in x are adjacent in the sorted arrays, so a row is one contiguous range of source
 // rods (plus at most two wrapped single cells at a periodic boundary).  Three stages with two warp-private
 // compaction queues, so that every stage runs on (nearly) full warps.
-//   stage 1  bounding-sphere test, fp32, lanes = source rods (two per lane: independent dependency chains),
-//            loop over the target tile; passers are queued as (target slot, source slot)
+//   stage 1  bounding-sphere test, fp32, lanes = source rods (two per lane: independent dependency chains), loop over a
+//            block of 32 targets; a passer is one bit in the lane's two mask registers, and after the block the bits are
+//            queued as (target slot, source slot) -- no vote or shared-memory traffic inside the arithmetic loop
 //   stage 2  on 32 queued pairs at a time: the two point/axis capsule tests, fp32, operands of both rods from
 //            the shared-memory tiles; passers are queued as (i, j, image code)
 //   stage 3  narrowBatch: exact fp64 closest-point query on 32 queued candidates at a time
@@ -360,7 +363,7 @@ __device__ __forceinline__ int narrowBatch(const PairIn &in, const Box &box, dou
 // ~1e-6 of |dd| <= cut once the sphere test has passed) is covered by the factor 1 + 2e-5 and the absolute slack
 // 1e-5 cut.  A pair the fp64 narrow phase would accept is never rejected; what is accepted in excess is decided
 // exactly by the narrow phase.  The candidate order (hence the constraint order inside a cell) is deterministic:
-// (target tile, stencil row, source tile, target, source).
+// (target tile, stencil row, source tile, block of 32 targets, k-th passing target of a source slot, source slot).
 static constexpr int kJTile = 64; // source rods staged per warp
 
 // NARROW = false: the kernel stops after stage 2 and stages its queued candidates (i, j, cell, seq | image) instead of
